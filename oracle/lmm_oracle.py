@@ -1,0 +1,544 @@
+"""CPU oracle for the LinearMixingModels.jl inference hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (``linearmixingmodels.jl_b200/``,
+``liblmm.so``) may import, call, link or execute this file; only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do.
+
+PARITY UNPINNED (in the strict sense): Julia is not available in the build container and the
+reference's own tests hold no golden logpdf / mean / var numbers -- only
+*equivalence identities* (OILMM == ILMM == dense multi-output GP == sum of single GPs) and a few
+known answers (permutations, ``noise_var``, ``reshape_y``, ``Orthogonal`` validation).  This file
+is a NumPy/SciPy Float64 restatement (LAPACK ``dpotrf``/``dtrtrs`` through OpenBLAS -- the routine
+family Julia's ``cholesky`` and ``\\`` reach) pinned by exactly those identities and known answers
+(``tests/test_oracle_identities.py``) and by a long-double/dense cross-check.
+
+Every function cites the reference lines it follows (paths relative to /root/reference).  The
+arithmetic of AbstractGPs 0.3.x / KernelFunctions 0.10.x / Distances 0.10.x is not vendored in the
+reference; it is restated from the published behaviour of those packages at the versions pinned in
+``examples/Manifest.toml`` and anchored on the reference's call sites.
+
+Conventions: all arrays Float64.  ``x`` is (N,) or (N, D) (one row per input).  Multi-output
+vectors are *by outputs*: ``y[(j-1)N + i]`` = output j at input i, i.e. ``y.reshape(p, N)`` in
+NumPy C-order is the p x N matrix ``Y`` of ``reshape_y`` (src/ilmm.jl:43).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import scipy.linalg as sla
+
+LOG2PI = math.log(2.0 * math.pi)
+
+SE, MATERN32, MATERN52 = 0, 1, 2
+KERNEL_NAMES = {SE: "SEKernel", MATERN32: "Matern32Kernel", MATERN52: "Matern52Kernel"}
+
+
+# --------------------------------------------------------------------------------------------
+# KernelFunctions / Distances semantics
+# --------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Kernel:
+    """``variance * (base ∘ ScaleTransform(inv_lengthscale))``.
+
+    ``variance`` is KernelFunctions' ``ScaledKernel`` (``0.5 * SEKernel()``,
+    test/independent_mogp.jl:108); ``inv_lengthscale`` its ``ScaleTransform`` -- inputs are
+    multiplied by it *before* pairwise distances are taken.
+    """
+
+    kind: int = SE
+    variance: float = 1.0
+    inv_lengthscale: float = 1.0
+
+
+@dataclass(frozen=True)
+class GP:
+    """``GP(mean_const, kernel)`` -- AbstractGPs ``GP(c::Real, k)`` / ``GP(k)`` (zero mean)."""
+
+    kernel: Kernel = Kernel()
+    mean_const: float = 0.0
+
+
+def _as2d(x: np.ndarray) -> np.ndarray:
+    x = np.asarray(x, dtype=np.float64)
+    return x.reshape(-1, 1) if x.ndim == 1 else x
+
+
+def pairwise_sqdist(a: np.ndarray, b: Optional[np.ndarray] = None, *, form: str = "gemm") -> np.ndarray:
+    """Squared Euclidean pairwise distances.
+
+    ``form="gemm"`` restates Distances.jl 0.10 ``pairwise(SqEuclidean(), a, b; dims=1)``:
+    ``max(|a_i|^2 + |b_j|^2 - 2 a_i.b_j, 0)`` with the cross term from a GEMM, and an exactly zero
+    diagonal in the symmetric case.  ``form="direct"`` is ``sum((a_i - b_j)^2)`` (used to report
+    the oracle-vs-oracle spread).
+    """
+    a = _as2d(a)
+    sym = b is None
+    bb = a if sym else _as2d(b)
+    if form == "direct":
+        d2 = np.zeros((a.shape[0], bb.shape[0]))
+        for k in range(a.shape[1]):
+            diff = a[:, k][:, None] - bb[:, k][None, :]
+            d2 += diff * diff
+        return d2
+    sa = np.sum(a * a, axis=1)
+    sb = sa if sym else np.sum(bb * bb, axis=1)
+    if a.shape[1] == 1:
+        # K=1 GEMM: a single correctly rounded product per entry (what dgemm/FMA-from-zero gives).
+        r = a[:, 0][:, None] * bb[:, 0][None, :]
+    else:
+        r = a @ bb.T
+    d2 = np.maximum((sa[:, None] + sb[None, :]) - 2.0 * r, 0.0)
+    if sym:
+        np.fill_diagonal(d2, 0.0)
+    return d2
+
+
+def kappa(kind: int, d2: np.ndarray) -> np.ndarray:
+    """Base kernel as a function of the squared distance (KernelFunctions ``kappa``).
+
+    SE: exp(-d²/2) on SqEuclidean; Matern32: (1+√3 d)exp(-√3 d); Matern52:
+    (1+√5 d+5d²/3)exp(-√5 d) on Euclidean d = sqrt(d²).
+    """
+    if kind == SE:
+        return np.exp(-d2 / 2.0)
+    d = np.sqrt(d2)
+    if kind == MATERN32:
+        s = math.sqrt(3.0) * d
+        return (1.0 + s) * np.exp(-s)
+    if kind == MATERN52:
+        s = math.sqrt(5.0) * d
+        return (1.0 + s + 5.0 * d * d / 3.0) * np.exp(-s)
+    raise ValueError(f"unsupported kernel kind {kind}")
+
+
+def kernelmatrix(k: Kernel, x: np.ndarray, x2: Optional[np.ndarray] = None, *, form: str = "gemm") -> np.ndarray:
+    """``kernelmatrix(k, x[, x2])`` = ``variance * map(κ, pairwise(metric, s*x, s*x2))``."""
+    xs = _as2d(x) * k.inv_lengthscale
+    x2s = None if x2 is None else _as2d(x2) * k.inv_lengthscale
+    return k.variance * kappa(k.kind, pairwise_sqdist(xs, x2s, form=form))
+
+
+def kernelmatrix_diag(k: Kernel, x: np.ndarray) -> np.ndarray:
+    """``kernelmatrix_diag(k, x)`` = κ(0)·variance per point."""
+    return np.full(_as2d(x).shape[0], k.variance, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# AbstractGPs single-output exact GP
+# --------------------------------------------------------------------------------------------
+def _chol_lower(C: np.ndarray) -> np.ndarray:
+    """``cholesky(Symmetric(C))`` -> lower factor (LAPACK dpotrf); raises LinAlgError if not PD."""
+    return sla.cholesky(C, lower=True, check_finite=False)
+
+
+def _fwd(L: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """``C.U' \\ B`` (dtrtrs, lower, no-trans)."""
+    return sla.solve_triangular(L, B, lower=True, check_finite=False)
+
+
+def _bwd(L: np.ndarray, B: np.ndarray) -> np.ndarray:
+    return sla.solve_triangular(L, B, lower=True, trans="T", check_finite=False)
+
+
+def gp_logpdf(f: GP, x, noise: float, y: np.ndarray, *, form: str = "gemm") -> float:
+    """AbstractGPs ``logpdf(f(x, σ²), y)``: -(n log2π + logdet C + |C.U'⁻¹(y-m)|²)/2."""
+    n = len(y)
+    C = kernelmatrix(f.kernel, x, form=form)
+    C[np.diag_indices_from(C)] += noise
+    L = _chol_lower(C)
+    z = _fwd(L, np.asarray(y, dtype=np.float64) - f.mean_const)
+    return -0.5 * (n * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(z @ z))
+
+
+@dataclass
+class PosteriorGP:
+    """AbstractGPs ``PosteriorGP(prior, (α, C, x, δ))`` with C kept as its lower factor L."""
+
+    prior: GP
+    alpha: np.ndarray
+    L: np.ndarray
+    x: np.ndarray
+    delta: np.ndarray
+    form: str = "gemm"
+
+
+def gp_posterior(f: GP, x, noise: float, y: np.ndarray, *, form: str = "gemm") -> PosteriorGP:
+    """AbstractGPs ``posterior(f(x, σ²), y)``: C = chol(K+σ²I), δ = y-m, α = C \\ δ."""
+    C = kernelmatrix(f.kernel, x, form=form)
+    C[np.diag_indices_from(C)] += noise
+    L = _chol_lower(C)
+    delta = np.asarray(y, dtype=np.float64) - f.mean_const
+    alpha = _bwd(L, _fwd(L, delta))
+    return PosteriorGP(f, alpha, L, np.asarray(x, dtype=np.float64), delta, form)
+
+
+def gp_mean(f, xs) -> np.ndarray:
+    n = _as2d(xs).shape[0]
+    if isinstance(f, PosteriorGP):
+        Ksx = kernelmatrix(f.prior.kernel, xs, f.x, form=f.form)
+        return f.prior.mean_const + Ksx @ f.alpha
+    return np.full(n, f.mean_const, dtype=np.float64)
+
+
+def gp_var(f, xs) -> np.ndarray:
+    if isinstance(f, PosteriorGP):
+        Kxs = kernelmatrix(f.prior.kernel, f.x, xs, form=f.form)
+        V = _fwd(f.L, Kxs)
+        return kernelmatrix_diag(f.prior.kernel, xs) - np.sum(V * V, axis=0)
+    return kernelmatrix_diag(f.kernel, xs)
+
+
+def gp_cov(f, xs) -> np.ndarray:
+    if isinstance(f, PosteriorGP):
+        Kxs = kernelmatrix(f.prior.kernel, f.x, xs, form=f.form)
+        V = _fwd(f.L, Kxs)
+        return kernelmatrix(f.prior.kernel, xs, form=f.form) - V.T @ V
+    return kernelmatrix(f.kernel, xs)
+
+
+def finite_marginals(f, xs, noise: float = 1e-18) -> Tuple[np.ndarray, np.ndarray]:
+    """``mean_and_var(f(x, σ²))`` = (m(x), diag K + σ²); default FiniteGP noise is 1e-18."""
+    return gp_mean(f, xs), gp_var(f, xs) + noise
+
+
+def finite_logpdf(f, xs, noise: float, y: np.ndarray) -> float:
+    """logpdf of a FiniteGP over a prior *or* posterior latent (used for ``logpdf(post(x*,σ²), y*)``)."""
+    if not isinstance(f, PosteriorGP):
+        return gp_logpdf(f, xs, noise, y)
+    n = len(y)
+    C = gp_cov(f, xs)
+    C[np.diag_indices_from(C)] += noise
+    L = _chol_lower(C)
+    z = _fwd(L, np.asarray(y, dtype=np.float64) - gp_mean(f, xs))
+    return -0.5 * (n * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(z @ z))
+
+
+def finite_rand(f, xs, noise: float, z: np.ndarray) -> np.ndarray:
+    """``rand(rng, f(x, σ²))`` = m + C.U' * z with z ~ N(0, I) supplied by the caller."""
+    C = gp_cov(f, xs)
+    C[np.diag_indices_from(C)] += noise
+    return gp_mean(f, xs) + _chol_lower(C) @ z
+
+
+# --------------------------------------------------------------------------------------------
+# LinearMixingModels: Orthogonal, project, regulariser (src/orthogonal_matrix.jl, src/oilmm.jl, src/ilmm.jl)
+# --------------------------------------------------------------------------------------------
+def validate_orthogonal(U: np.ndarray) -> None:
+    """src/orthogonal_matrix.jl:21-23 -- ``isapprox(U'U, I)`` (Frobenius norm, rtol=sqrt(eps))."""
+    U = np.asarray(U, dtype=np.float64)
+    m = U.shape[1]
+    G = U.T @ U
+    eye = np.eye(m)
+    rtol = math.sqrt(np.finfo(np.float64).eps)
+    if not np.linalg.norm(G - eye) <= rtol * max(np.linalg.norm(G), np.linalg.norm(eye)):
+        raise ValueError("`U` is not an orthogonal matrix")
+
+
+def noise_var_known_answer() -> int:
+    """test/ilmm.jl:56 -- ``noise_var(Diagonal(Fill(2, 3))) == 2``."""
+    return 2
+
+
+def reshape_y(y: np.ndarray, N: int) -> np.ndarray:
+    """src/ilmm.jl:43 -- ``reshape(y, N, :)'`` -> p x N with Y[j, i] = y[j*N + i] (0-based)."""
+    y = np.asarray(y, dtype=np.float64)
+    return y.reshape(-1, N)
+
+
+def project_orthogonal(U: np.ndarray, S: np.ndarray, sigma2: float) -> Tuple[np.ndarray, np.ndarray]:
+    """src/oilmm.jl:20-30 -- T = sqrt(S) \\ U', ΣT = diag(σ² inv(S))."""
+    S = np.asarray(S, dtype=np.float64)
+    T = U.T / np.sqrt(S)[:, None]
+    return T, sigma2 * (1.0 / S)
+
+
+def regulariser_orthogonal(U: np.ndarray, S: np.ndarray, sigma2: float, Y: np.ndarray) -> float:
+    """src/oilmm.jl:101-113."""
+    n = Y.shape[1]
+    p, m = U.shape
+    R = (np.eye(p) - U @ U.T) @ Y
+    return -(n * (float(np.sum(np.log(S))) + (p - m) * math.log(2.0 * math.pi * sigma2)) + float(np.sum(R * R)) / sigma2) / 2.0
+
+
+def project_general(H: np.ndarray, sigma2: float) -> Tuple[np.ndarray, np.ndarray]:
+    """src/ilmm.jl:61-68 -- includes the hard-coded 1e-9 jitter."""
+    H = np.asarray(H, dtype=np.float64)
+    m = H.shape[1]
+    ST_inv = H.T @ H / sigma2 + 1e-9 * np.eye(m)
+    L = _chol_lower(ST_inv)
+    T = _bwd(L, _fwd(L, H.T)) / sigma2
+    ST = T @ (sigma2 * np.eye(H.shape[0])) @ T.T
+    return T, ST
+
+
+def regulariser_general(H: np.ndarray, sigma2: float, Y: np.ndarray) -> float:
+    """src/ilmm.jl:171-181."""
+    p, m = H.shape
+    n = Y.shape[1]
+    T, ST = project_general(H, sigma2)
+    _, logdet_ST = np.linalg.slogdet(ST)
+    R = Y - H @ (T @ Y)
+    return -(n * ((p - m) * LOG2PI + (p * math.log(sigma2) - logdet_ST)) + float(np.sum(R * R)) / sigma2) / 2.0
+
+
+# --------------------------------------------------------------------------------------------
+# IndependentMOGP (src/independent_mogp.jl)
+# --------------------------------------------------------------------------------------------
+def indices_outputs_to_features(N: int, p: int) -> np.ndarray:
+    """src/independent_mogp.jl:135-139, 0-based.  Known answer test/independent_mogp.jl:86-98."""
+    return np.arange(N * p).reshape(p, N).T.reshape(-1)
+
+
+def indices_features_to_outputs(N: int, p: int) -> np.ndarray:
+    """src/independent_mogp.jl:141-145, 0-based."""
+    return np.arange(N * p).reshape(N, p).T.reshape(-1)
+
+
+def imogp_logpdf(fs: Sequence[GP], x, sigma2: float, y: np.ndarray, *, form: str = "gemm") -> float:
+    """src/independent_mogp.jl:74-80 -- y by outputs; sum of single-output logpdfs."""
+    N = _as2d(x).shape[0]
+    Y = reshape_y(y, N)
+    return float(sum(gp_logpdf(f, x, sigma2, Y[i], form=form) for i, f in enumerate(fs)))
+
+
+def imogp_logpdf_by_features(fs, x, sigma2, y_feat) -> float:
+    """src/independent_mogp.jl:222-229."""
+    N = _as2d(x).shape[0]
+    return imogp_logpdf(fs, x, sigma2, np.asarray(y_feat)[indices_features_to_outputs(N, len(fs))])
+
+
+def imogp_posterior(fs: Sequence[GP], x, sigma2: float, y: np.ndarray, *, form: str = "gemm") -> List[PosteriorGP]:
+    """src/independent_mogp.jl:119-126."""
+    N = _as2d(x).shape[0]
+    Y = reshape_y(y, N)
+    return [gp_posterior(f, x, sigma2, Y[i], form=form) for i, f in enumerate(fs)]
+
+
+def imogp_mean_and_var(fs, xs, sigma2: float) -> Tuple[np.ndarray, np.ndarray]:
+    """src/independent_mogp.jl:50-57 + FiniteGP noise: mean / var concatenated by outputs."""
+    M = np.concatenate([gp_mean(f, xs) for f in fs])
+    V = np.concatenate([gp_var(f, xs) for f in fs]) + sigma2
+    return M, V
+
+
+def imogp_cov(fs, xs) -> np.ndarray:
+    """src/independent_mogp.jl:60-63 -- dense block diagonal."""
+    return sla.block_diag(*[gp_cov(f, xs) for f in fs])
+
+
+def imogp_rand(fs, xs, sigma2: float, z: np.ndarray) -> np.ndarray:
+    """src/independent_mogp.jl:83-86 -- z holds N normals per latent, latent-major."""
+    N = _as2d(xs).shape[0]
+    Z = np.asarray(z, dtype=np.float64).reshape(len(fs), N)
+    return np.concatenate([finite_rand(f, xs, sigma2, Z[i]) for i, f in enumerate(fs)])
+
+
+# --------------------------------------------------------------------------------------------
+# OILMM (src/oilmm.jl)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class OILMMModel:
+    """``ILMM(IndependentMOGP(fs), Orthogonal(U, Diagonal(S)))`` -- fs may be priors or posteriors."""
+
+    fs: list
+    U: np.ndarray
+    S: np.ndarray
+
+    @property
+    def H(self) -> np.ndarray:
+        return self.U * np.sqrt(self.S)[None, :]
+
+
+def _check_out_dim(p_x: int, p_H: int) -> None:
+    if p_x != p_H:  # src/ilmm.jl:52
+        raise RuntimeError("out dim of x != out dim of f.")
+
+
+def oilmm_logpdf_terms(model: OILMMModel, x, sigma2: float, y: np.ndarray, *, form: str = "gemm"):
+    """Per-latent lml terms and the regulariser -- src/oilmm.jl:79-93."""
+    N = _as2d(x).shape[0]
+    Y = reshape_y(y, N)
+    _check_out_dim(Y.shape[0], model.U.shape[0])
+    T, ST = project_orthogonal(model.U, model.S, sigma2)
+    Ty = T @ Y
+    lmls = [
+        (gp_logpdf(f, x, ST[i], Ty[i], form=form) if not isinstance(f, PosteriorGP) else finite_logpdf(f, x, ST[i], Ty[i]))
+        for i, f in enumerate(model.fs)
+    ]
+    return np.array(lmls), regulariser_orthogonal(model.U, model.S, sigma2, Y)
+
+
+def oilmm_logpdf(model: OILMMModel, x, sigma2: float, y: np.ndarray, *, form: str = "gemm") -> float:
+    lmls, reg = oilmm_logpdf_terms(model, x, sigma2, y, form=form)
+    return float(np.sum(lmls) + reg)
+
+
+def oilmm_posterior(model: OILMMModel, x, sigma2: float, y: np.ndarray, *, form: str = "gemm") -> OILMMModel:
+    """src/oilmm.jl:116-134 -- the posterior is an OILMM whose latents are PosteriorGPs."""
+    N = _as2d(x).shape[0]
+    Y = reshape_y(y, N)
+    _check_out_dim(Y.shape[0], model.U.shape[0])
+    T, ST = project_orthogonal(model.U, model.S, sigma2)
+    Ty = T @ Y
+    posts = [gp_posterior(f, x, ST[i], Ty[i], form=form) for i, f in enumerate(model.fs)]
+    return OILMMModel(posts, model.U, model.S)
+
+
+def oilmm_mean_and_var(model: OILMMModel, xs, sigma2: float) -> Tuple[np.ndarray, np.ndarray]:
+    """src/oilmm.jl:57-76 -- latent marginals (default FiniteGP noise 1e-18), mixed, by outputs."""
+    ML = np.stack([finite_marginals(f, xs)[0] for f in model.fs])
+    VL = np.stack([finite_marginals(f, xs)[1] for f in model.fs])
+    H = model.H
+    M = H @ ML
+    V = (H * H) @ VL + sigma2
+    return M.reshape(-1), V.reshape(-1)
+
+
+def oilmm_rand(model: OILMMModel, xs, sigma2: float, z_latent: np.ndarray, z_noise: np.ndarray) -> np.ndarray:
+    """src/oilmm.jl:40-54 -- latent draws use the default noise 1e-18; normals supplied by caller."""
+    N = _as2d(xs).shape[0]
+    Z = np.asarray(z_latent, dtype=np.float64).reshape(len(model.fs), N)
+    X = np.stack([finite_rand(f, xs, 1e-18, Z[i]) for i, f in enumerate(model.fs)])  # m x N
+    F = (model.H @ X).reshape(-1)
+    return F + math.sqrt(sigma2) * np.asarray(z_noise, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# ILMM with a general mixing matrix (src/ilmm.jl)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class ILMMPosterior:
+    """``ILMM(PosteriorGP{IndependentMOGP}, H)`` -- joint (mN) posterior over the latents."""
+
+    fs: list
+    H: np.ndarray
+    x: np.ndarray
+    alpha: np.ndarray  # (mN,)
+    L: np.ndarray  # (mN, mN) lower
+
+
+def _latent_prior_cov(fs, x, form="gemm") -> np.ndarray:
+    return sla.block_diag(*[kernelmatrix(f.kernel, x, form=form) for f in fs])
+
+
+def ilmm_logpdf(fs: Sequence[GP], H: np.ndarray, x, sigma2: float, y: np.ndarray, *, form: str = "gemm") -> float:
+    """src/ilmm.jl:150-163 -- projected (mN x mN) dense form + regulariser."""
+    N = _as2d(x).shape[0]
+    H = np.asarray(H, dtype=np.float64)
+    p, m = H.shape
+    Y = reshape_y(y, N)
+    _check_out_dim(Y.shape[0], p)
+    T, ST = project_general(H, sigma2)
+    yproj = (T @ Y).reshape(-1)  # by outputs over the m latents
+    C = _latent_prior_cov(fs, x, form) + np.kron(ST, np.eye(N))
+    mean = np.concatenate([np.full(N, f.mean_const) for f in fs])
+    L = _chol_lower(C)
+    z = _fwd(L, yproj - mean)
+    lml = -0.5 * (m * N * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(z @ z))
+    return lml + regulariser_general(H, sigma2, Y)
+
+
+def ilmm_posterior(fs: Sequence[GP], H: np.ndarray, x, sigma2: float, y: np.ndarray, *, form: str = "gemm") -> ILMMPosterior:
+    """src/ilmm.jl:184-198."""
+    N = _as2d(x).shape[0]
+    H = np.asarray(H, dtype=np.float64)
+    Y = reshape_y(y, N)
+    _check_out_dim(Y.shape[0], H.shape[0])
+    T, ST = project_general(H, sigma2)
+    yproj = (T @ Y).reshape(-1)
+    C = _latent_prior_cov(fs, x, form) + np.kron(ST, np.eye(N))
+    mean = np.concatenate([np.full(N, f.mean_const) for f in fs])
+    L = _chol_lower(C)
+    alpha = _bwd(L, _fwd(L, yproj - mean))
+    return ILMMPosterior(list(fs), H, np.asarray(x, dtype=np.float64), alpha, L)
+
+
+def _ilmm_latent_mean_and_cov(f, xs, form="gemm") -> Tuple[np.ndarray, np.ndarray]:
+    """``mean_and_cov(f(x_mo))`` for prior (list of GP) or joint posterior, incl. the 1e-18 noise."""
+    Ns = _as2d(xs).shape[0]
+    if isinstance(f, ILMMPosterior):
+        m = len(f.fs)
+        Ksx = sla.block_diag(*[kernelmatrix(g.kernel, xs, f.x, form=form) for g in f.fs])  # (mNs, mN)
+        prior_mean = np.concatenate([np.full(Ns, g.mean_const) for g in f.fs])
+        mean = prior_mean + Ksx @ f.alpha
+        V = _fwd(f.L, Ksx.T)
+        cov = sla.block_diag(*[kernelmatrix(g.kernel, xs, form=form) for g in f.fs]) - V.T @ V
+    else:
+        mean = np.concatenate([np.full(Ns, g.mean_const) for g in f])
+        cov = _latent_prior_cov(f, xs, form)
+    return mean, cov + 1e-18 * np.eye(cov.shape[0])
+
+
+def ilmm_mean_and_cov(f, H: np.ndarray, xs, sigma2: float) -> Tuple[np.ndarray, np.ndarray]:
+    """src/ilmm.jl:108-139 -- M = (H⊗I) m_lat, C = (H⊗I) C_lat (H⊗I)' + σ² I."""
+    Ns = _as2d(xs).shape[0]
+    mean, cov = _ilmm_latent_mean_and_cov(f, xs)
+    Hf = np.kron(np.asarray(H, dtype=np.float64), np.eye(Ns))
+    C = Hf @ cov @ Hf.T
+    return Hf @ mean, C + sigma2 * np.eye(C.shape[0])
+
+
+def ilmm_mean_and_var(f, H: np.ndarray, xs, sigma2: float) -> Tuple[np.ndarray, np.ndarray]:
+    """src/ilmm.jl:122-129."""
+    M, C = ilmm_mean_and_cov(f, H, xs, sigma2)
+    return M, np.diag(C).copy()
+
+
+def ilmm_rand(fs: Sequence[GP], H: np.ndarray, xs, sigma2: float, z_latent: np.ndarray, z_noise: np.ndarray) -> np.ndarray:
+    """src/ilmm.jl:78-87 -- latent jitter 1e-12, then ``vec(reshape(latent, N, m) * H') + sqrt(σ²) ε``."""
+    lat = imogp_rand(fs, xs, 1e-12, z_latent).reshape(len(fs), -1)  # m x N
+    return (np.asarray(H, dtype=np.float64) @ lat).reshape(-1) + math.sqrt(sigma2) * np.asarray(z_noise, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# Independent dense check: GP(LinearMixingModelKernel(kernels, H')) (test/ilmm.jl:5)
+# --------------------------------------------------------------------------------------------
+def dense_mogp_cov(fs: Sequence[GP], H: np.ndarray, x, x2=None, *, form: str = "gemm") -> np.ndarray:
+    """Σ_i (h_i h_iᵀ) ⊗ K_i for by-outputs inputs (pN x pN')."""
+    H = np.asarray(H, dtype=np.float64)
+    out = None
+    for i, f in enumerate(fs):
+        blk = np.kron(np.outer(H[:, i], H[:, i]), kernelmatrix(f.kernel, x, x2, form=form))
+        out = blk if out is None else out + blk
+    return out
+
+
+def dense_mogp_mean(fs: Sequence[GP], H: np.ndarray, x) -> np.ndarray:
+    N = _as2d(x).shape[0]
+    lat = np.stack([np.full(N, f.mean_const) for f in fs])
+    return (np.asarray(H, dtype=np.float64) @ lat).reshape(-1)
+
+
+def dense_mogp_logpdf(fs: Sequence[GP], H: np.ndarray, x, sigma2: float, y: np.ndarray, *, form: str = "gemm") -> float:
+    C = dense_mogp_cov(fs, H, x, form=form)
+    C[np.diag_indices_from(C)] += sigma2
+    L = _chol_lower(C)
+    z = _fwd(L, np.asarray(y, dtype=np.float64) - dense_mogp_mean(fs, H, x))
+    return -0.5 * (len(y) * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(z @ z))
+
+
+def dense_mogp_posterior_mean_and_var(fs, H, x, sigma2, y, xs, sigma2_pred) -> Tuple[np.ndarray, np.ndarray]:
+    """Textbook Gaussian conditioning on the dense pN x pN model; predictive noise added to var."""
+    C = dense_mogp_cov(fs, H, x)
+    C[np.diag_indices_from(C)] += sigma2
+    L = _chol_lower(C)
+    delta = np.asarray(y, dtype=np.float64) - dense_mogp_mean(fs, H, x)
+    alpha = _bwd(L, _fwd(L, delta))
+    Ksx = dense_mogp_cov(fs, H, xs, x)
+    mean = dense_mogp_mean(fs, H, xs) + Ksx @ alpha
+    V = _fwd(L, Ksx.T)
+    var = np.diag(dense_mogp_cov(fs, H, xs)) - np.sum(V * V, axis=0) + sigma2_pred
+    return mean, var
+
+
+# --------------------------------------------------------------------------------------------
+# Synthetic workloads shared by tests and bench: identical bytes for oracle and GPU
+# --------------------------------------------------------------------------------------------
+def orthogonal_from_seed(p: int, m: int, seed: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+    """U, S = thin SVD of uniform(0,1) p x m, as the tests/notebook do (test/oilmm.jl:45-46)."""
+    rng = np.random.default_rng(seed)
+    U, S, _ = np.linalg.svd(rng.uniform(0.0, 1.0, size=(p, m)), full_matrices=False)
+    return np.ascontiguousarray(U), np.ascontiguousarray(S)
