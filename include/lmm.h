@@ -1,0 +1,198 @@
+/*
+ * lmm.h -- C ABI of liblmm.so: the B200 (sm_100a) implementation of the LinearMixingModels.jl
+ * inference hot path.  This is the drop-in boundary: the Julia shim
+ * (linearmixingmodels.jl_b200/julia/LinearMixingModelsB200.jl) binds these symbols with `ccall`
+ * and keeps the reference's exported types/method signatures; the Python host mirror
+ * (linearmixingmodels.jl_b200/api.py) binds the same symbols with ctypes.
+ *
+ * The reference has no FFI of its own (pure Julia multiple dispatch).  Each entry point below
+ * names the reference method body (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *  - Every function returns int: 0 = ok; > 0 = LAPACK-style `info` (1-based index of the first
+ *    non-positive pivot; the failing latent is reported through lmm_last_error and *info_latent)
+ *    -> Julia PosDefException(info); < 0 = LMM_E_* below.
+ *  - All matrices are column-major Float64 (Julia Matrix / NumPy order='F').  Multi-output vectors
+ *    are "by outputs": y[(j-1)N + i] = output j at input i == the N x p column-major matrix
+ *    (src/ilmm.jl:43 reshape_y).  x is D x N column-major (ColVecs; a Vector{Float64} has D = 1).
+ *  - Pointer arguments are HOST memory owned by the caller unless documented otherwise; x / y
+ *    / U / S / H inputs may alternatively be DEVICE pointers on the context's GPU (detected with
+ *    cudaPointerGetAttributes) -- bench.py's HBM-resident timing uses that.  The library never
+ *    retains a caller pointer after return.
+ *  - Calls are synchronous and thread-safe per context (one mutex per lmm_ctx; cudaSetDevice on
+ *    entry).  There is no CPU fallback: without a CUDA device every compute entry returns
+ *    LMM_E_CUDA.
+ */
+#ifndef LMM_H_
+#define LMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMM_OK 0
+#define LMM_E_ARG (-1)            /* bad argument / null pointer / non-positive size          */
+#define LMM_E_OUT_DIM (-2)        /* "out dim of x != out dim of f."  src/ilmm.jl:52          */
+#define LMM_E_UNSUPPORTED (-3)    /* kernel / mean / option outside the supported set         */
+#define LMM_E_CUDA (-4)           /* CUDA runtime error or no device                          */
+#define LMM_E_NCCL (-5)           /* NCCL unavailable or failed                               */
+#define LMM_E_NOT_ORTHOGONAL (-6) /* "`U` is not an orthogonal matrix" src/orthogonal_matrix.jl:22 */
+#define LMM_E_OOM (-7)            /* device memory exhausted                                  */
+
+/* Base kernels (KernelFunctions.jl): SEKernel, Matern32Kernel, Matern52Kernel. */
+#define LMM_KERNEL_SE 0
+#define LMM_KERNEL_MATERN32 1
+#define LMM_KERNEL_MATERN52 2
+
+/* One latent `GP(mean_const, variance * (base_kernel ∘ ScaleTransform(inv_lengthscale)))`. */
+typedef struct lmm_gp_desc {
+  int32_t kind;           /* LMM_KERNEL_*                                   */
+  int32_t reserved;       /* must be 0                                      */
+  double variance;        /* ScaledKernel σ² (1.0 for a plain kernel)       */
+  double inv_lengthscale; /* ScaleTransform s (1.0 for a plain kernel)      */
+  double mean_const;      /* ZeroMean -> 0.0; ConstMean(c) -> c             */
+} lmm_gp_desc;
+
+typedef struct lmm_ctx lmm_ctx;   /* owns device, stream, memory pool, optional NCCL communicator */
+typedef struct lmm_post lmm_post; /* device-resident posterior: per-latent factor L_i, α_i, δ_i, x */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int lmm_ctx_create(int device, lmm_ctx** out);
+int lmm_ctx_destroy(lmm_ctx* ctx);
+const char* lmm_last_error(lmm_ctx* ctx);
+const char* lmm_version(void);
+/* Tunables: "distance_form" (0 = Distances.jl gemm form [default], 1 = direct differences),
+ * "outer_block" (tile columns per outer Cholesky step, default 8), "gemm_impl" (0 = cp.async
+ * pipeline DMMA kernel). */
+int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value);
+/* Counters since context creation: kernels launched by this library, bytes copied H2D / D2H. */
+int lmm_ctx_counters(lmm_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* CUDA-event time (ms) of the device work of the most recent compute call, and of its dominant
+ * stages: [0] total, [1] kernel-matrix build, [2] Cholesky, [3] solves, [4] projection,
+ * [5] prediction (cross-cov + TRSM + back-projection), [6] Cholesky trailing-update GEMM launches
+ * count (as a double), [7] reserved. */
+int lmm_ctx_last_timings(lmm_ctx* ctx, double out_ms[8]);
+
+/* ---- multi-GPU: one process (and one context) per GPU; latents are block-sharded over ranks --- */
+/* (no counterpart in the reference: it is single-process) */
+int lmm_comm_unique_id(void* out_128_bytes);
+int lmm_comm_init(lmm_ctx* ctx, const void* unique_id_128_bytes, int nranks, int rank);
+/* Without NCCL (tests on CPU-only hosts, gloo plumbing): declare the shard only; the caller
+ * reduces `lml_terms` / partial back-projections itself. */
+int lmm_comm_set_shard(lmm_ctx* ctx, int nranks, int rank);
+
+/* ---- Orthogonal(U, S): src/orthogonal_matrix.jl:21-23 (_validate) ----------------------------- */
+/* U is p x m column-major.  Host-side check `isapprox(U'U, I)`; returns LMM_E_NOT_ORTHOGONAL. */
+int lmm_orthogonal_validate(const double* U, int p, int m);
+
+/* ---- OILMM: src/oilmm.jl -------------------------------------------------------------------- */
+/* logpdf(fx::FiniteGP{<:OILMM}, y)  src/oilmm.jl:79-93 (+ project :20-30, regulariser :101-113).
+ * out_dim is fx.x.out_dim (checked against p: src/ilmm.jl:52).  lml_terms (nullable) receives
+ * the m per-latent terms followed by the regulariser (m+1 doubles). */
+int lmm_oilmm_logpdf(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
+                     const double* U, const double* S, int p, double sigma2, const double* y,
+                     int out_dim, double* out_logpdf, double* lml_terms, int* info_latent);
+
+/* posterior(fx::FiniteGP{<:OILMM}, y)  src/oilmm.jl:116-134.  One factorisation per latent is
+ * shared with the logpdf when out_logpdf != NULL (the reference factorises twice). */
+int lmm_oilmm_posterior(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N,
+                        int D, const double* U, const double* S, int p, double sigma2,
+                        const double* y, int out_dim, lmm_post** out_post, double* out_logpdf,
+                        double* lml_terms, int* info_latent);
+
+/* mean_and_var(fx::FiniteGP{<:OILMM}) on *prior* latents  src/oilmm.jl:57-76.  mean/var are
+ * p*Ns by outputs. */
+int lmm_oilmm_prior_mean_and_var(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* xs,
+                                 int Ns, int D, const double* U, const double* S, int p,
+                                 double sigma2, int out_dim, double* mean, double* var);
+
+/* rand(rng, fx::FiniteGP{<:OILMM}) on prior latents  src/oilmm.jl:40-54.  z_latent: m*N standard
+ * normals (latent-major, the order Julia's rng is consumed in); z_noise: p*N. */
+int lmm_oilmm_rand(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
+                   const double* U, const double* S, int p, double sigma2, int out_dim,
+                   const double* z_latent, const double* z_noise, double* out, int* info_latent);
+
+/* Hyper-parameter sweep (BASELINE config 5): logpdf for n_sweep inverse-lengthscale settings
+ * applied to every latent (multiplying each latent's own inv_lengthscale); the projection and
+ * regulariser are shared, factors are streamed through one arena. out: n_sweep doubles. */
+int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N,
+                           int D, const double* U, const double* S, int p, double sigma2,
+                           const double* y, int out_dim, const double* inv_lengthscale_scales,
+                           int n_sweep, double* out_logpdfs, int* info_latent);
+
+/* ---- posterior handle: the OILMM/ILMM/IndependentMOGP whose latents are PosteriorGPs -------- */
+/* mean_and_var(post(x*, σ²))  src/oilmm.jl:57-76 on PosteriorGP latents (AbstractGPs posterior
+ * mean/var); for an IndependentMOGP posterior: src/independent_mogp.jl:50-57; ILMM: src/ilmm.jl:122-129. */
+int lmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean,
+                          double* var);
+/* logpdf(post(x*, σ²), y*)  (test/oilmm.jl:84): OILMM logpdf with PosteriorGP latents. */
+int lmm_post_logpdf(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys,
+                    double* out_logpdf, int* info_latent);
+/* rand(rng, post(x*, σ²))  src/oilmm.jl:40-54 with PosteriorGP latents. */
+int lmm_post_rand(lmm_post* post, const double* xs, int Ns, double sigma2, const double* z_latent,
+                  const double* z_noise, double* out, int* info_latent);
+/* PosteriorGP field access (α, C, δ) for latent i (global index): L is N x N column-major lower
+ * (upper part zero); any of L / alpha / delta may be NULL.  Returns LMM_E_ARG if latent i is
+ * not resident on this rank. */
+int lmm_post_export(lmm_post* post, int i, double* L, double* alpha, double* delta);
+int lmm_post_info(lmm_post* post, int* kind, int* m, int* p, int* N, int* D, int64_t* device_bytes);
+int lmm_post_free(lmm_post* post);
+
+/* ---- IndependentMOGP: src/independent_mogp.jl ---------------------------------------------- */
+/* logpdf src/independent_mogp.jl:74-80 (by outputs; by-features callers permute with
+ * lmm_reorder_indices first, :222-229). */
+int lmm_imogp_logpdf(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
+                     double sigma2, const double* y, int out_dim, double* out_logpdf,
+                     double* lml_terms, int* info_latent);
+/* posterior src/independent_mogp.jl:119-126. */
+int lmm_imogp_posterior(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
+                        double sigma2, const double* y, int out_dim, lmm_post** out_post,
+                        double* out_logpdf, int* info_latent);
+/* rand src/independent_mogp.jl:83-86. */
+int lmm_imogp_rand(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
+                   double sigma2, int out_dim, const double* z, double* out, int* info_latent);
+/* indices_which_reorder_{outputs_to_features,features_to_outputs}  src/independent_mogp.jl:135-145
+ * (0-based; direction 0 = outputs->features, 1 = features->outputs). */
+int lmm_reorder_indices(int N, int p, int direction, int64_t* out);
+
+/* ---- ILMM with a general mixing matrix: src/ilmm.jl ------------------------------------------ */
+#define LMM_ILMM_FORM_PROJECTED 0 /* the reference's (mN x mN) form, incl. the 1e-9 jitter :63 */
+#define LMM_ILMM_FORM_DENSE 1     /* H K H' + σ²I, pN x pN (test oracle form, test/ilmm.jl:5)  */
+/* logpdf src/ilmm.jl:150-163 (+ project :61-68, regulariser :171-181).  H is p x m column-major. */
+int lmm_ilmm_logpdf(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
+                    const double* H, int p, double sigma2, const double* y, int out_dim, int form,
+                    double* out_logpdf, int* info);
+/* posterior src/ilmm.jl:184-198 (projected form; joint (mN) factor). */
+int lmm_ilmm_posterior(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N,
+                       int D, const double* H, int p, double sigma2, const double* y, int out_dim,
+                       lmm_post** out_post, double* out_logpdf, int* info);
+/* mean_and_var on prior latents src/ilmm.jl:122-129. */
+int lmm_ilmm_prior_mean_and_var(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* xs,
+                                int Ns, int D, const double* H, int p, double sigma2, int out_dim,
+                                double* mean, double* var);
+/* rand src/ilmm.jl:78-87 (latent jitter 1e-12). */
+int lmm_ilmm_rand(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
+                  const double* H, int p, double sigma2, int out_dim, const double* z_latent,
+                  const double* z_noise, double* out, int* info_latent);
+
+/* ---- batched blocked Cholesky primitive: the `cholesky(Symmetric(C))` / dpotrf call site ---- */
+/* A: batch matrices, each N x N column-major (lower triangle read).  L_out (nullable): same
+ * shape, lower factor with zero upper part.  logdet_out (nullable): batch doubles = 2 Σ log L_jj.
+ * info (nullable): batch ints, 0 or 1-based failing pivot.  Returns max(info). */
+int lmm_potrf_batched(lmm_ctx* ctx, const double* A, int N, int batch, double* L_out,
+                      double* logdet_out, int* info);
+/* Same factorisation run on synthetic SPD matrices generated on the device (kernel-matrix build
+ * of `desc` at x plus `noise` on the diagonal), nothing copied back but logdet: the kernel-level
+ * benchmark used for roofline numbers.  out_ms receives the CUDA-event time of the factorisation
+ * alone (kernel-matrix build excluded). */
+int lmm_potrf_bench(lmm_ctx* ctx, const lmm_gp_desc* desc, const double* x, int N, int D,
+                    double noise, int batch, double* logdet_out, double* out_ms_kmat,
+                    double* out_ms_chol);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMM_H_ */

@@ -1,0 +1,766 @@
+"""Host-side mirror of the LinearMixingModels.jl / AbstractGPs interface for the inference hot
+path, on top of the liblmm C ABI (include/lmm.h).
+
+Julia is not installed in the build image, so this Python layer plays the role of the Julia shim
+(`julia/LinearMixingModelsB200.jl` holds the ccall version a maintainer would load): same
+exported names (src/LinearMixingModels.jl:21-24), same argument meaning, same error behaviour:
+
+    f  = ILMM(independent_mogp([GP(SEKernel()), GP(Matern32Kernel())]), Orthogonal(U, S))
+    fx = f(MOInputIsotopicByOutputs(x, p), 0.1)
+    logpdf(fx, y); post = posterior(fx, y); mean_and_var(post(x_test, 0.1)); rand(rng, fx)
+
+Dispatch mirrors the reference: `H` an `Orthogonal` => OILMM path (src/oilmm.jl:13), a plain
+matrix => general ILMM (src/ilmm.jl); inputs must be `MOInputIsotopicByOutputs` with scalar noise
+(src/ilmm.jl:45) -- anything else raises TypeError (Julia: MethodError).  All numerics run in
+liblmm on the GPU; nothing here computes on the CPU beyond argument marshalling.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import weakref
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import GpDesc, PosDefException, as_f64, ptr
+
+__all__ = [
+    "SEKernel", "SqExponentialKernel", "Matern32Kernel", "Matern52Kernel", "ScaleTransform", "with_lengthscale",
+    "GP", "MOInputIsotopicByOutputs", "MOInputIsotopicByFeatures", "ColVecs", "RowVecs",
+    "ILMM", "OILMM", "Orthogonal", "IndependentMOGP", "independent_mogp", "get_latent_gp",
+    "FiniteGP", "Normal", "logpdf", "posterior", "mean_and_var", "mean", "var", "marginals", "rand",
+    "PosDefException", "Context", "default_context", "noise_var", "reshape_y", "unpack",
+    "indices_which_reorder_outputs_to_features", "indices_which_reorder_features_to_outputs",
+]
+
+
+# --------------------------------------------------------------------------------------------
+# context
+# --------------------------------------------------------------------------------------------
+class Context:
+    """Owns one `lmm_ctx` (device, stream, memory pool, optional NCCL communicator)."""
+
+    def __init__(self, device: Optional[int] = None):
+        self.lib = _lib.load()
+        if device is None:
+            device = _current_device()
+        h = C.c_void_p()
+        rc = self.lib.lmm_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(
+                f"lmm_ctx_create(device={device}) failed with code {rc}: a CUDA device is required "
+                "(liblmm has no CPU fallback)"
+            )
+        self.handle = h
+        self.device = int(device)
+        self.nranks, self.rank = 1, 0
+        self._finalizer = weakref.finalize(self, self.lib.lmm_ctx_destroy, h)
+
+    # -- helpers
+    def error(self) -> str:
+        return (self.lib.lmm_last_error(self.handle) or b"").decode()
+
+    def set_option(self, key: str, value: float) -> None:
+        rc = self.lib.lmm_ctx_set_option(self.handle, key.encode(), float(value))
+        if rc != 0:
+            raise ValueError(self.error())
+
+    def counters(self) -> Tuple[int, int, int]:
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.lib.lmm_ctx_counters(self.handle, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def last_timings(self) -> np.ndarray:
+        out = np.zeros(8)
+        self.lib.lmm_ctx_last_timings(self.handle, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def set_shard(self, nranks: int, rank: int) -> None:
+        rc = self.lib.lmm_comm_set_shard(self.handle, nranks, rank)
+        if rc != 0:
+            raise ValueError("bad shard")
+        self.nranks, self.rank = nranks, rank
+
+    def init_nccl(self, unique_id: bytes, nranks: int, rank: int) -> None:
+        buf = C.create_string_buffer(unique_id, 128)
+        rc = self.lib.lmm_comm_init(self.handle, C.cast(buf, C.c_void_p), nranks, rank)
+        if rc != 0:
+            raise RuntimeError(f"lmm_comm_init failed ({rc}): {self.error()}")
+        self.nranks, self.rank = nranks, rank
+
+    def check(self, rc: int, info_latent: int = -1):
+        if rc == 0:
+            return
+        msg = self.error()
+        if rc > 0:
+            raise PosDefException(rc, info_latent, msg)
+        if rc == _lib.LMM_E_OUT_DIM:
+            raise RuntimeError("out dim of x != out dim of f.")  # src/ilmm.jl:52
+        if rc == _lib.LMM_E_NOT_ORTHOGONAL:
+            raise ValueError("`U` is not an orthogonal matrix")
+        if rc == _lib.LMM_E_OOM:
+            raise MemoryError(msg)
+        if rc in (_lib.LMM_E_ARG, _lib.LMM_E_UNSUPPORTED):
+            raise ValueError(msg)
+        raise RuntimeError(f"liblmm error {rc}: {msg}")
+
+
+def _current_device() -> int:
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def set_default_context(ctx: Optional[Context]) -> None:
+    global _default_ctx
+    _default_ctx = ctx
+
+
+# --------------------------------------------------------------------------------------------
+# kernels, GP, inputs (KernelFunctions / AbstractGPs names)
+# --------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Kernel:
+    kind: int
+    variance: float = 1.0
+    inv_lengthscale: float = 1.0
+
+    def __rmul__(self, s):  # `0.5 * SEKernel()` -> ScaledKernel
+        if not (isinstance(s, (int, float)) and s > 0):
+            raise TypeError("kernel scale must be a positive real")
+        return Kernel(self.kind, self.variance * float(s), self.inv_lengthscale)
+
+    __mul__ = __rmul__
+
+    def compose(self, t: "ScaleTransform") -> "Kernel":  # `k ∘ ScaleTransform(s)`
+        return Kernel(self.kind, self.variance, self.inv_lengthscale * t.s)
+
+    __matmul__ = compose
+
+
+@dataclass(frozen=True)
+class ScaleTransform:
+    s: float
+
+
+def SEKernel() -> Kernel:
+    return Kernel(0)
+
+
+SqExponentialKernel = SEKernel
+
+
+def Matern32Kernel() -> Kernel:
+    return Kernel(1)
+
+
+def Matern52Kernel() -> Kernel:
+    return Kernel(2)
+
+
+def with_lengthscale(k: Kernel, l: float) -> Kernel:
+    return k.compose(ScaleTransform(1.0 / float(l)))
+
+
+class AbstractGP:
+    def __call__(self, x, sigma2=1e-18):
+        return FiniteGP(self, x, sigma2)
+
+
+class GP(AbstractGP):
+    """`GP(kernel)` (zero mean) or `GP(c, kernel)` (constant mean c)."""
+
+    def __init__(self, *args):
+        if len(args) == 1:
+            self.mean_const, self.kernel = 0.0, args[0]
+        elif len(args) == 2:
+            self.mean_const, self.kernel = float(args[0]), args[1]
+        else:
+            raise TypeError("GP(kernel) or GP(mean_const, kernel)")
+        if not isinstance(self.kernel, Kernel):
+            raise TypeError("unsupported kernel type (liblmm supports SE / Matern32 / Matern52, scaled and stretched)")
+
+    def __eq__(self, other):
+        return isinstance(other, GP) and (self.mean_const, self.kernel) == (other.mean_const, other.kernel)
+
+    def __hash__(self):
+        return hash((self.mean_const, self.kernel))
+
+
+class ColVecs:
+    """D x N matrix whose columns are the inputs."""
+
+    def __init__(self, X):
+        self.X = np.asarray(X, dtype=np.float64)
+
+    def points(self) -> np.ndarray:  # (N, D) C-order == D x N column-major
+        return np.ascontiguousarray(self.X.T)
+
+
+class RowVecs:
+    """N x D matrix whose rows are the inputs."""
+
+    def __init__(self, X):
+        self.X = np.asarray(X, dtype=np.float64)
+
+    def points(self) -> np.ndarray:
+        return np.ascontiguousarray(self.X)
+
+
+def _points(x) -> np.ndarray:
+    """(N, D) C-contiguous float64 view of a Vector{<:Real} / ColVecs / RowVecs input."""
+    if isinstance(x, (ColVecs, RowVecs)):
+        return x.points()
+    if _is_device_tensor(x):
+        return x
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim != 1:
+        raise TypeError("inputs must be a real vector, ColVecs or RowVecs")
+    return np.ascontiguousarray(a.reshape(-1, 1))
+
+
+def _is_device_tensor(a) -> bool:
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+class MOInputIsotopicByOutputs:
+    """Element (j-1)N + i is (x[i], j)."""
+
+    def __init__(self, x, out_dim: int):
+        self.x = x
+        self.out_dim = int(out_dim)
+
+    def __len__(self):
+        return _npoints(self.x) * self.out_dim
+
+
+class MOInputIsotopicByFeatures:
+    """Element (i-1)p + j is (x[i], j)."""
+
+    def __init__(self, x, out_dim: int):
+        self.x = x
+        self.out_dim = int(out_dim)
+
+    def __len__(self):
+        return _npoints(self.x) * self.out_dim
+
+
+def _npoints(x) -> int:
+    p = _points(x)
+    return int(p.shape[0])
+
+
+def indices_which_reorder_outputs_to_features(x) -> np.ndarray:
+    """src/independent_mogp.jl:135-139 (0-based)."""
+    out = np.zeros(len(x), dtype=np.int64)
+    _lib.load().lmm_reorder_indices(_npoints(x.x), x.out_dim, 0, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def indices_which_reorder_features_to_outputs(x) -> np.ndarray:
+    """src/independent_mogp.jl:141-145 (0-based)."""
+    out = np.zeros(len(x), dtype=np.int64)
+    _lib.load().lmm_reorder_indices(_npoints(x.x), x.out_dim, 1, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# models (src/LinearMixingModels.jl:21-24 exports)
+# --------------------------------------------------------------------------------------------
+class Orthogonal:
+    """`Orthogonal(U, S; validate_fields=true)`: H = U * sqrt(S)  (src/orthogonal_matrix.jl:11-19)."""
+
+    def __init__(self, U, S, validate_fields: bool = True):
+        U = np.asarray(U, dtype=np.float64)
+        S = np.asarray(S, dtype=np.float64)
+        if S.ndim == 2:  # Diagonal(S) given as a matrix
+            S = np.diag(S).copy()
+        if U.ndim != 2 or S.ndim != 1 or U.shape[1] != S.shape[0]:
+            raise TypeError("Orthogonal(U::Matrix p x m, S::Diagonal m x m)")
+        self.U = np.asfortranarray(U)
+        self.S = np.ascontiguousarray(S)
+        if validate_fields:
+            rc = _lib.load().lmm_orthogonal_validate(ptr(self.U), U.shape[0], U.shape[1])
+            if rc == _lib.LMM_E_NOT_ORTHOGONAL:
+                raise ValueError("`U` is not an orthogonal matrix")  # ArgumentError, src/orthogonal_matrix.jl:22
+
+    @property
+    def shape(self):
+        return self.U.shape
+
+    def __array__(self, dtype=None, copy=None):  # collect(H)
+        return self.U * np.sqrt(self.S)[None, :]
+
+
+class IndependentMOGP(AbstractGP):
+    """src/independent_mogp.jl:10-12."""
+
+    def __init__(self, fs: Sequence[AbstractGP]):
+        fs = list(fs)
+        if not fs or not all(isinstance(f, (GP, PosteriorGP)) for f in fs):
+            raise TypeError("IndependentMOGP(fs::Vector{<:AbstractGP})")
+        self.fs = fs
+
+
+def independent_mogp(fs) -> IndependentMOGP:
+    return IndependentMOGP(fs)
+
+
+class ILMM(AbstractGP):
+    """src/ilmm.jl:16-19.  `OILMM` is the case H::Orthogonal with IndependentMOGP latents."""
+
+    def __init__(self, f: AbstractGP, H):
+        if not isinstance(f, AbstractGP):
+            raise TypeError("ILMM(f::AbstractGP, H::AbstractMatrix)")
+        self.f = f
+        self.H = H if isinstance(H, Orthogonal) else np.asfortranarray(np.asarray(H, dtype=np.float64))
+        if not isinstance(H, Orthogonal) and self.H.ndim != 2:
+            raise TypeError("H must be a matrix")
+
+
+class _OILMMMeta(type):
+    def __instancecheck__(cls, obj):
+        return isinstance(obj, ILMM) and isinstance(obj.f, IndependentMOGP) and isinstance(obj.H, Orthogonal)
+
+
+class OILMM(metaclass=_OILMMMeta):
+    """`const OILMM = ILMM{<:IndependentMOGP,<:Orthogonal}` (src/oilmm.jl:13): usable in isinstance."""
+
+    def __new__(cls, fs, H):
+        f = fs if isinstance(fs, IndependentMOGP) else IndependentMOGP(fs)
+        if not isinstance(H, Orthogonal):
+            raise TypeError("OILMM needs an Orthogonal mixing matrix")
+        return ILMM(f, H)
+
+
+def get_latent_gp(f: ILMM):
+    return f.f
+
+
+class PosteriorGP(AbstractGP):
+    """View of one latent `PosteriorGP(prior, (α, C, x, δ))` held on the device."""
+
+    def __init__(self, owner: "_PostHandle", index: int, prior: GP):
+        self._owner, self.index, self.prior = owner, index, prior
+
+    def _export(self, want_L=False):
+        return self._owner.export(self.index, want_L)
+
+    @property
+    def alpha(self):
+        return self._export()[1]
+
+    @property
+    def delta(self):
+        return self._export()[2]
+
+    @property
+    def C(self):
+        """Lower Cholesky factor L of K + Σ (C.L in Julia)."""
+        return self._export(True)[0]
+
+
+class _PostHandle:
+    """Owns an `lmm_post*`."""
+
+    def __init__(self, ctx: Context, handle, N: int, joint_n: int = 0):
+        self.ctx, self.handle, self.N, self.joint_n = ctx, handle, N, joint_n
+        self._finalizer = weakref.finalize(self, ctx.lib.lmm_post_free, handle)
+
+    def free(self):
+        self._finalizer()
+
+    def export(self, i: int, want_L: bool):
+        n = self.joint_n or self.N
+        L = np.zeros((n, n), order="F") if want_L else None
+        a, d = np.zeros(n), np.zeros(n)
+        rc = self.ctx.lib.lmm_post_export(self.handle, i, ptr(L), ptr(a), ptr(d))
+        self.ctx.check(rc)
+        return L, a, d
+
+    def device_bytes(self) -> int:
+        b = C.c_int64()
+        self.ctx.lib.lmm_post_info(self.handle, None, None, None, None, None, C.byref(b))
+        return b.value
+
+
+class _JointPosterior(AbstractGP):
+    """`PosteriorGP{IndependentMOGP}`: joint (mN) posterior of a general ILMM (src/ilmm.jl:196)."""
+
+    def __init__(self, owner: _PostHandle, prior: IndependentMOGP):
+        self._owner, self.prior = owner, prior
+
+
+# --------------------------------------------------------------------------------------------
+# FiniteGP and the AbstractGPs verbs
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Normal:
+    mu: float
+    sigma: float
+
+
+class FiniteGP:
+    """`f(x, σ²)`; only isotropic scalar noise (`Diagonal(Fill(σ², n))`) reaches the fast paths."""
+
+    def __init__(self, f: AbstractGP, x, sigma2=1e-18):
+        self.f, self.x = f, x
+        if not isinstance(sigma2, (int, float, np.floating)):
+            raise TypeError("only scalar observation noise is supported on this path (src/ilmm.jl:45)")
+        self.sigma2 = float(sigma2)
+
+    def __len__(self):
+        return len(self.x)
+
+
+def noise_var(fx: FiniteGP) -> float:
+    """src/ilmm.jl:41."""
+    return fx.sigma2
+
+
+def reshape_y(y, N: int) -> np.ndarray:
+    """src/ilmm.jl:43: `reshape(y, N, :)'` (p x N)."""
+    return np.asarray(y).reshape(-1, N)
+
+
+def unpack(fx: FiniteGP):
+    """src/ilmm.jl:45-54."""
+    if not (isinstance(fx.f, ILMM) and isinstance(fx.x, MOInputIsotopicByOutputs)):
+        raise TypeError("unpack(fx::FiniteGP{<:ILMM,<:MOInputIsotopicByOutputs,<:Diagonal{<:Real,<:Fill}})")
+    H = fx.f.H
+    if fx.x.out_dim != H.shape[0]:
+        raise RuntimeError("out dim of x != out dim of f.")
+    return fx.f.f, H, fx.sigma2, fx.x.x
+
+
+def _descs(fs: Sequence[GP]):
+    arr = (GpDesc * len(fs))()
+    for i, f in enumerate(fs):
+        g = f.prior if isinstance(f, PosteriorGP) else f
+        arr[i] = GpDesc(g.kernel.kind, 0, g.kernel.variance, g.kernel.inv_lengthscale, g.mean_const)
+    return arr
+
+
+def _yvec(y, n: int):
+    if _is_device_tensor(y):
+        if y.numel() != n:
+            raise ValueError("length of y does not match the inputs")
+        return y
+    a = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    if a.shape[0] != n:
+        raise ValueError("length of y does not match the inputs")
+    return a
+
+
+def _ctx_of(fx: FiniteGP) -> Context:
+    f = fx.f
+    owner = None
+    if isinstance(f, ILMM):
+        lat = f.f
+        if isinstance(lat, IndependentMOGP) and isinstance(lat.fs[0], PosteriorGP):
+            owner = lat.fs[0]._owner
+        elif isinstance(lat, _JointPosterior):
+            owner = lat._owner
+    elif isinstance(f, IndependentMOGP) and isinstance(f.fs[0], PosteriorGP):
+        owner = f.fs[0]._owner
+    return owner.ctx if owner is not None else default_context()
+
+
+def _post_owner(fx: FiniteGP) -> Optional[_PostHandle]:
+    f = fx.f
+    lat = f.f if isinstance(f, ILMM) else f
+    if isinstance(lat, IndependentMOGP) and isinstance(lat.fs[0], PosteriorGP):
+        return lat.fs[0]._owner
+    if isinstance(lat, _JointPosterior):
+        return lat._owner
+    return None
+
+
+def _require_by_outputs(fx: FiniteGP):
+    if not isinstance(fx.x, MOInputIsotopicByOutputs):
+        raise TypeError("this method needs MOInputIsotopicByOutputs inputs (src/ilmm.jl:45)")
+
+
+def logpdf(fx: FiniteGP, y) -> float:
+    """`logpdf(fx, y)`: src/oilmm.jl:79-93, src/ilmm.jl:150-163, src/independent_mogp.jl:74-80,222-229."""
+    return _logpdf_impl(fx, y)[0]
+
+
+def logpdf_terms(fx: FiniteGP, y) -> np.ndarray:
+    """Per-latent lml terms followed by the regulariser (OILMM / IndependentMOGP)."""
+    return _logpdf_impl(fx, y)[1]
+
+
+def _logpdf_impl(fx: FiniteGP, y):
+    f = fx.f
+    ctx = _ctx_of(fx)
+    lib = ctx.lib
+    out = C.c_double()
+    il = C.c_int(-1)
+    owner = _post_owner(fx)
+    if isinstance(f, IndependentMOGP) and isinstance(fx.x, MOInputIsotopicByFeatures):
+        # src/independent_mogp.jl:222-229
+        xo = MOInputIsotopicByOutputs(fx.x.x, fx.x.out_dim)
+        idx = indices_which_reorder_features_to_outputs(fx.x)
+        return _logpdf_impl(FiniteGP(f, xo, fx.sigma2), np.asarray(y, dtype=np.float64)[idx])
+    _require_by_outputs(fx)
+    pts = _points(fx.x.x)
+    N, D = int(pts.shape[0]), int(pts.shape[1])
+    if owner is not None:
+        if isinstance(f, ILMM) and f.H.shape[0] != fx.x.out_dim:
+            raise RuntimeError("out dim of x != out dim of f.")
+        yv = _yvec(y, N * fx.x.out_dim)
+        rc = lib.lmm_post_logpdf(owner.handle, ptr(pts), N, fx.sigma2, ptr(yv), C.byref(out), C.byref(il))
+        ctx.check(rc, il.value)
+        return out.value, None
+    if isinstance(f, ILMM):
+        lat, H, s2, _ = unpack(fx)
+        if not isinstance(lat, IndependentMOGP):
+            raise TypeError("ILMM latents must be an IndependentMOGP")
+        m = len(lat.fs)
+        yv = _yvec(y, N * fx.x.out_dim)
+        if isinstance(H, Orthogonal):
+            terms = np.zeros(m + 1)
+            rc = lib.lmm_oilmm_logpdf(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H.U), ptr(H.S), H.shape[0], s2, ptr(yv),
+                                      fx.x.out_dim, C.byref(out), ptr(terms), C.byref(il))
+            ctx.check(rc, il.value)
+            return out.value, terms
+        rc = lib.lmm_ilmm_logpdf(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H), H.shape[0], s2, ptr(yv), fx.x.out_dim,
+                                 _lib_ilmm_form(), C.byref(out), C.byref(il))
+        ctx.check(rc, il.value)
+        return out.value, None
+    if isinstance(f, IndependentMOGP):
+        m = len(f.fs)
+        yv = _yvec(y, N * fx.x.out_dim)
+        terms = np.zeros(m + 1)
+        rc = lib.lmm_imogp_logpdf(ctx.handle, _descs(f.fs), m, ptr(pts), N, D, fx.sigma2, ptr(yv), fx.x.out_dim, C.byref(out),
+                                  ptr(terms), C.byref(il))
+        ctx.check(rc, il.value)
+        return out.value, terms
+    raise TypeError(f"logpdf not defined for FiniteGP of {type(f).__name__}")
+
+
+_ILMM_FORM = 0
+
+
+def _lib_ilmm_form() -> int:
+    return _ILMM_FORM
+
+
+def set_ilmm_form(form: int) -> None:
+    """0: the reference's projected (mN) form; 1: dense pN form H K H' + σ²I (test oracle form)."""
+    global _ILMM_FORM
+    _ILMM_FORM = int(form)
+
+
+def posterior(fx: FiniteGP, y, with_logpdf: bool = False):
+    """`posterior(fx, y)`: src/oilmm.jl:116-134, src/ilmm.jl:184-198, src/independent_mogp.jl:119-126.
+    `with_logpdf=True` additionally returns logpdf(fx, y) from the same factorisation."""
+    f = fx.f
+    ctx = _ctx_of(fx)
+    lib = ctx.lib
+    if _post_owner(fx) is not None:
+        raise NotImplementedError("conditioning a posterior again (sequential conditioning) is a SURVEY §8f item")
+    _require_by_outputs(fx)
+    pts = _points(fx.x.x)
+    N, D = int(pts.shape[0]), int(pts.shape[1])
+    h = C.c_void_p()
+    out = C.c_double()
+    il = C.c_int(-1)
+    lp = C.byref(out) if with_logpdf else None
+    if isinstance(f, ILMM):
+        lat, H, s2, _ = unpack(fx)
+        if not isinstance(lat, IndependentMOGP):
+            raise TypeError("ILMM latents must be an IndependentMOGP")
+        m = len(lat.fs)
+        yv = _yvec(y, N * fx.x.out_dim)
+        if isinstance(H, Orthogonal):
+            rc = lib.lmm_oilmm_posterior(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H.U), ptr(H.S), H.shape[0], s2, ptr(yv),
+                                         fx.x.out_dim, C.byref(h), lp, None, C.byref(il))
+            ctx.check(rc, il.value)
+            owner = _PostHandle(ctx, h, N)
+            post = ILMM(IndependentMOGP([PosteriorGP(owner, i, g) for i, g in enumerate(lat.fs)]), H)
+        else:
+            rc = lib.lmm_ilmm_posterior(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H), H.shape[0], s2, ptr(yv), fx.x.out_dim,
+                                        C.byref(h), lp, C.byref(il))
+            ctx.check(rc, il.value)
+            owner = _PostHandle(ctx, h, N, joint_n=m * N)
+            post = ILMM(_JointPosterior(owner, lat), H)
+    elif isinstance(f, IndependentMOGP):
+        m = len(f.fs)
+        yv = _yvec(y, N * fx.x.out_dim)
+        rc = lib.lmm_imogp_posterior(ctx.handle, _descs(f.fs), m, ptr(pts), N, D, fx.sigma2, ptr(yv), fx.x.out_dim, C.byref(h), lp,
+                                     C.byref(il))
+        ctx.check(rc, il.value)
+        owner = _PostHandle(ctx, h, N)
+        post = IndependentMOGP([PosteriorGP(owner, i, g) for i, g in enumerate(f.fs)])
+    else:
+        raise TypeError(f"posterior not defined for FiniteGP of {type(f).__name__}")
+    return (post, out.value) if with_logpdf else post
+
+
+def mean_and_var(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
+    """`mean_and_var(fx)`: src/oilmm.jl:57-76, src/ilmm.jl:122-129, src/independent_mogp.jl:50-57."""
+    f = fx.f
+    ctx = _ctx_of(fx)
+    lib = ctx.lib
+    owner = _post_owner(fx)
+    x = fx.x
+    reorder = None
+    if isinstance(f, IndependentMOGP) and isinstance(x, MOInputIsotopicByFeatures):
+        reorder = indices_which_reorder_outputs_to_features(x)  # src/independent_mogp.jl:169-179
+        x = MOInputIsotopicByOutputs(x.x, x.out_dim)
+    elif not isinstance(x, MOInputIsotopicByOutputs):
+        raise TypeError("this method needs MOInput inputs")
+    pts = _points(x.x)
+    Ns, D = int(pts.shape[0]), int(pts.shape[1])
+    p = x.out_dim
+    M, V = np.zeros(p * Ns), np.zeros(p * Ns)
+    if isinstance(f, ILMM) and f.H.shape[0] != p:
+        raise RuntimeError("out dim of x != out dim of f.")
+    if owner is not None:
+        rc = lib.lmm_post_mean_and_var(owner.handle, ptr(pts), Ns, fx.sigma2, ptr(M), ptr(V))
+        ctx.check(rc)
+    elif isinstance(f, ILMM):
+        lat, H = f.f, f.H
+        m = len(lat.fs)
+        if isinstance(H, Orthogonal):
+            rc = lib.lmm_oilmm_prior_mean_and_var(ctx.handle, _descs(lat.fs), m, ptr(pts), Ns, D, ptr(H.U), ptr(H.S), p, fx.sigma2, p,
+                                                  ptr(M), ptr(V))
+        else:
+            rc = lib.lmm_ilmm_prior_mean_and_var(ctx.handle, _descs(lat.fs), m, ptr(pts), Ns, D, ptr(H), p, fx.sigma2, p, ptr(M), ptr(V))
+        ctx.check(rc)
+    elif isinstance(f, IndependentMOGP):
+        if len(f.fs) != p:
+            raise RuntimeError("out dim of x != out dim of f.")
+        # prior: mean const, var = variance + σ² (src/independent_mogp.jl:50-57); trivial, no kernel needed
+        M = np.concatenate([np.full(Ns, g.mean_const) for g in f.fs])
+        V = np.concatenate([np.full(Ns, g.kernel.variance + fx.sigma2) for g in f.fs])
+    else:
+        raise TypeError(f"mean_and_var not defined for FiniteGP of {type(f).__name__}")
+    if reorder is not None:
+        M, V = M[reorder], V[reorder]
+    return M, V
+
+
+def mean(fx: FiniteGP) -> np.ndarray:
+    return mean_and_var(fx)[0]  # src/ilmm.jl:142
+
+
+def var(fx: FiniteGP) -> np.ndarray:
+    return mean_and_var(fx)[1]  # src/ilmm.jl:145
+
+
+def marginals(fx: FiniteGP) -> List[Normal]:
+    """AbstractGPs generic: `Normal.(m, sqrt.(v))`."""
+    M, V = mean_and_var(fx)
+    return [Normal(float(a), math.sqrt(float(b))) for a, b in zip(M, V)]
+
+
+def rand(*args):
+    """`rand([rng,] fx[, n_samples])`: src/oilmm.jl:40-54, src/ilmm.jl:78-106, src/independent_mogp.jl:83-99.
+    Standard normals are drawn on the host from `rng` in the reference's order (latent 1..m, N each;
+    then p*N noise draws) and handed to the library, so a sample is a deterministic function of them."""
+    args = list(args)
+    rng = args.pop(0) if isinstance(args[0], np.random.Generator) else np.random.default_rng()
+    fx = args.pop(0)
+    if args:
+        return np.stack([_rand_one(rng, fx) for _ in range(int(args[0]))], axis=1)  # src/ilmm.jl:90-92
+    return _rand_one(rng, fx)
+
+
+def _rand_one(rng, fx: FiniteGP) -> np.ndarray:
+    f = fx.f
+    ctx = _ctx_of(fx)
+    lib = ctx.lib
+    owner = _post_owner(fx)
+    by_features = isinstance(f, IndependentMOGP) and isinstance(fx.x, MOInputIsotopicByFeatures)
+    if not by_features:
+        _require_by_outputs(fx)
+    pts = _points(fx.x.x)
+    N, D = int(pts.shape[0]), int(pts.shape[1])
+    p = fx.x.out_dim
+    il = C.c_int(-1)
+    out = np.zeros(p * N)
+    if isinstance(f, ILMM):
+        if f.H.shape[0] != p:
+            raise RuntimeError("out dim of x != out dim of f.")
+        m = f.H.shape[1]
+        z_lat = rng.standard_normal(m * N)
+        z_noise = rng.standard_normal(p * N)
+        if owner is not None:
+            rc = lib.lmm_post_rand(owner.handle, ptr(pts), N, fx.sigma2, ptr(z_lat), ptr(z_noise), ptr(out), C.byref(il))
+        elif isinstance(f.H, Orthogonal):
+            rc = lib.lmm_oilmm_rand(ctx.handle, _descs(f.f.fs), m, ptr(pts), N, D, ptr(f.H.U), ptr(f.H.S), p, fx.sigma2, p, ptr(z_lat),
+                                    ptr(z_noise), ptr(out), C.byref(il))
+        else:
+            rc = lib.lmm_ilmm_rand(ctx.handle, _descs(f.f.fs), m, ptr(pts), N, D, ptr(f.H), p, fx.sigma2, p, ptr(z_lat), ptr(z_noise),
+                                   ptr(out), C.byref(il))
+        ctx.check(rc, il.value)
+        return out
+    if isinstance(f, IndependentMOGP):
+        m = len(f.fs)
+        z = rng.standard_normal(m * N)
+        if owner is not None:
+            rc = lib.lmm_post_rand(owner.handle, ptr(pts), N, fx.sigma2, ptr(z), None, ptr(out), C.byref(il))
+        else:
+            rc = lib.lmm_imogp_rand(ctx.handle, _descs(f.fs), m, ptr(pts), N, D, fx.sigma2, p, ptr(z), ptr(out), C.byref(il))
+        ctx.check(rc, il.value)
+        if by_features:  # src/independent_mogp.jl:217-220
+            return out.reshape(m, N).T.reshape(-1).copy()
+        return out
+    raise TypeError(f"rand not defined for FiniteGP of {type(f).__name__}")
+
+
+def logpdf_sweep(fx: FiniteGP, y, inv_lengthscale_scales) -> np.ndarray:
+    """BASELINE config 5: OILMM logpdf for a batch of lengthscale settings in one call."""
+    lat, H, s2, _ = unpack(fx)
+    if not isinstance(H, Orthogonal):
+        raise TypeError("logpdf_sweep needs an OILMM")
+    ctx = _ctx_of(fx)
+    pts = _points(fx.x.x)
+    N, D = int(pts.shape[0]), int(pts.shape[1])
+    m = len(lat.fs)
+    sc = as_f64(inv_lengthscale_scales).reshape(-1)
+    out = np.zeros(sc.shape[0])
+    il = C.c_int(-1)
+    yv = _yvec(y, N * fx.x.out_dim)
+    rc = ctx.lib.lmm_oilmm_logpdf_sweep(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H.U), ptr(H.S), H.shape[0], s2, ptr(yv),
+                                        fx.x.out_dim, ptr(sc), sc.shape[0], ptr(out), C.byref(il))
+    ctx.check(rc, il.value)
+    return out
+
+
+def potrf_batched(A: np.ndarray, ctx: Optional[Context] = None):
+    """Batched blocked Cholesky of `A[b]` (symmetric, lower read): returns (L, logdet, info)."""
+    ctx = ctx or default_context()
+    A = np.asarray(A, dtype=np.float64)
+    if A.ndim == 2:
+        A = A[None]
+    batch, N, _ = A.shape
+    Af = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))  # each matrix column-major
+    L = np.zeros_like(Af)
+    logdet = np.zeros(batch)
+    info = np.zeros(batch, dtype=np.int32)
+    rc = ctx.lib.lmm_potrf_batched(ctx.handle, ptr(Af), N, batch, ptr(L), ptr(logdet), ptr(info))
+    if rc < 0:
+        ctx.check(rc)
+    return np.transpose(L, (0, 2, 1)), logdet, info

@@ -1,0 +1,1081 @@
+// liblmm C ABI (include/lmm.h): contexts, posterior handles, host-side orchestration of the
+// batched blocked Cholesky and of the OILMM / IndependentMOGP / ILMM inference path.
+// There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lmm.h"
+#include "kernels.h"
+
+using namespace lmm;
+
+namespace {
+const double LOG2PI = 1.8378770664093453;  // log(2π)
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen: no link-time dependency; picks up the libnccl.so.2 already loaded by the
+// host process (torch bundles one) or the system one.
+// ------------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+    api.GetUniqueId = (int (*)(NcclId*))dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+    api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+  });
+  return api;
+}
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct lmm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::string err;
+  int distance_form = 0;
+  int outer_block = 8;
+  int nranks = 1, rank = 0;
+  void* comm = nullptr;
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[8];
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  int fail_cuda(cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %s at api.cu:%d (%s)", cudaGetErrorString(e), line, what);
+    err = buf;
+    cudaGetLastError();  // clear non-sticky error state
+    return e == cudaErrorMemoryAllocation ? LMM_E_OOM : LMM_E_CUDA;
+  }
+};
+
+#define CU(expr)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (expr);                                           \
+    if (e__ != cudaSuccess) return ctx->fail_cuda(e__, #expr, __LINE__); \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  lmm_ctx* c = nullptr;
+  void* p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFreeAsync(p, c->stream);
+    p = nullptr;
+  }
+  cudaError_t alloc(lmm_ctx* ctx, size_t bytes) {
+    release();
+    c = ctx;
+    if (bytes == 0) bytes = 8;
+    return cudaMallocAsync(&p, bytes, ctx->stream);
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  void* detach() {
+    void* q = p;
+    p = nullptr;
+    return q;
+  }
+};
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Copy n doubles from a caller pointer (host or device) into device memory at dst.
+cudaError_t copy_in(lmm_ctx* ctx, double* dst, const double* src, size_t n) {
+  if (is_device_ptr(src)) return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+  ctx->h2d += (int64_t)(n * sizeof(double));
+  return cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+}
+cudaError_t copy_out(lmm_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  ctx->d2h += (int64_t)bytes;
+  return cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+}
+
+inline int ntiles(int n) { return (n + TILE - 1) / TILE; }
+
+void shard_range(const lmm_ctx* ctx, int m, int& lo, int& hi) {
+  lo = (int)(((int64_t)m * ctx->rank) / ctx->nranks);
+  hi = (int)(((int64_t)m * (ctx->rank + 1)) / ctx->nranks);
+}
+
+int check_descs(lmm_ctx* ctx, const lmm_gp_desc* d, int m) {
+  for (int i = 0; i < m; ++i) {
+    if (d[i].kind < 0 || d[i].kind > 2) return ctx->fail(LMM_E_UNSUPPORTED, "unsupported kernel kind (only SE, Matern32, Matern52)");
+    if (!(d[i].variance > 0.0) || !(d[i].inv_lengthscale > 0.0)) return ctx->fail(LMM_E_ARG, "kernel variance and inv_lengthscale must be positive");
+  }
+  return LMM_OK;
+}
+
+// lml_i = -(N log2π + logdet_i + quad_i)/2 ; optional regulariser slot.
+__global__ void lml_terms_kernel(double* terms, int slot0, int nb, const double* logdet, const double* quad, int n, double log2pi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb) terms[slot0 + i] = -((double)n * log2pi + logdet[i] + quad[i]) / 2.0;
+}
+__global__ void regulariser_kernel(double* slot, double c0, const double* resid, double sigma2) {
+  slot[0] = -(c0 + resid[0] / sigma2) / 2.0;
+}
+__global__ void add_scalar_kernel(double* v, size_t n, double s) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] += s;
+}
+// out[i*stride_out + n] = a[i*stride_in + n] + s  (latent-major copy with offset)
+__global__ void copy_add_kernel(double* out, size_t stride_out, const double* in, size_t stride_in, int n, double s) {
+  const int i = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[(size_t)i * stride_out + k] = in[(size_t)i * stride_in + k] + s;
+}
+// v[i][k] = mean_i + v[i][k]   and   w = a*x + y helpers for rand
+__global__ void add_mean_kernel(double* v, size_t stride, int n, const LatentParams* params) {
+  const int i = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) v[(size_t)i * stride + k] += params[i].mean;
+}
+__global__ void axpy_kernel(double* y, const double* x, size_t n, double a) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fma(a, x[i], y[i]);
+}
+
+// ---- batched blocked Cholesky (left-looking over blocks of `outer_block` tile columns) -------
+// For every block column [s0, s1): one wide trailing update against all previous columns
+// (K = s0 tiles, output written once), then per tile column: narrow update inside the block,
+// diagonal-tile factor (+ inverse, logdet, info), panel TRSM as a GEMM with the inverse.
+cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
+  const int nt = L.nt, ob = ctx->outer_block;
+  GemmArgs g{};
+  g.A = operand(L);
+  g.B = operand(L);
+  g.C = operand(L);
+  g.W = W;
+  g.w_batch_stride = wstride;
+  g.sym = 1;
+  cudaError_t e;
+  for (int s0 = 0; s0 < nt; s0 += ob) {
+    const int s1 = (s0 + ob < nt) ? s0 + ob : nt;
+    if (s0 > 0) {
+      g.i0 = s0; g.j0 = s0; g.k0 = 0; g.k1 = s0;
+      if ((e = launch_gemm(ctx->stream, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
+      ++ctx->launches;
+      ctx->timings[6] += 1;
+    }
+    for (int jj = s0; jj < s1; ++jj) {
+      if (jj > s0) {
+        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+        if ((e = launch_gemm(ctx->stream, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+        ctx->timings[6] += 1;
+      }
+      if ((e = launch_potrf_tile(ctx->stream, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
+      ++ctx->launches;
+      if (jj + 1 < nt) {
+        g.i0 = jj + 1; g.j0 = jj;
+        if ((e = launch_gemm(ctx->stream, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+    }
+  }
+  return cudaSuccess;
+}
+
+// X <- X L^{-T} for a rectangular tiled X (rows = e.g. test points): the same update/TRSM sweep
+// with X's tile rows appended under the factor.
+cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch) {
+  const int nt = L.nt, ob = ctx->outer_block;
+  GemmArgs g{};
+  g.A = operand(X);
+  g.B = operand(L);
+  g.C = operand(X);
+  g.W = W;
+  g.w_batch_stride = wstride;
+  g.sym = 0;
+  g.i0 = 0;
+  cudaError_t e;
+  for (int s0 = 0; s0 < nt; s0 += ob) {
+    const int s1 = (s0 + ob < nt) ? s0 + ob : nt;
+    if (s0 > 0) {
+      g.j0 = s0; g.k0 = 0; g.k1 = s0;
+      if ((e = launch_gemm(ctx->stream, GEMM_UPDATE, g, s1 - s0, X.ntr, batch)) != cudaSuccess) return e;
+      ++ctx->launches;
+    }
+    for (int jj = s0; jj < s1; ++jj) {
+      if (jj > s0) {
+        g.j0 = jj; g.k0 = s0; g.k1 = jj;
+        if ((e = launch_gemm(ctx->stream, GEMM_UPDATE, g, 1, X.ntr, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+      g.j0 = jj;
+      if ((e = launch_gemm(ctx->stream, GEMM_TRSM, g, 1, X.ntr, batch)) != cudaSuccess) return e;
+      ++ctx->launches;
+    }
+  }
+  return cudaSuccess;
+}
+
+size_t factor_bytes_per_latent(int nt) { return (sym_tiles(nt) + (size_t)nt) * TT * sizeof(double); }
+
+void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const double* noise, int lo, int hi, double ls_scale = 1.0) {
+  hp.resize(hi - lo);
+  for (int i = lo; i < hi; ++i) {
+    LatentParams& q = hp[i - lo];
+    q.kind = d[i].kind;
+    q.pad = 0;
+    q.variance = d[i].variance;
+    q.inv_ls = d[i].inv_lengthscale * ls_scale;
+    q.noise = noise[i];
+    q.mean = d[i].mean_const;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// posterior handle
+// ------------------------------------------------------------------------------------------------
+enum { POST_OILMM = 0, POST_IMOGP = 1, POST_ILMM = 2 };
+
+struct lmm_post {
+  lmm_ctx* ctx = nullptr;
+  int kind = POST_OILMM;
+  int m = 0, p = 0, N = 0, D = 1, nt = 0;
+  int lo = 0, hi = 0;  // resident latents [lo, hi)
+  std::vector<lmm_gp_desc> descs;
+  std::vector<double> noise;  // per latent (all m)
+  std::vector<double> H;      // p x m column-major (U sqrt(S) for OILMM)
+  std::vector<double> U, S;
+  double sigma2 = 0.0;
+  // device
+  double* d_xpad = nullptr;  // [Npad][D]
+  double* d_L = nullptr;     // TiledSym, batch = hi - lo (ILMM: batch 1 over mN)
+  double* d_W = nullptr;     // [batch][nt] tiles
+  double* d_alpha = nullptr; // [batch][Npad]
+  double* d_delta = nullptr; // [batch][Npad]
+  LatentParams* d_params = nullptr;
+  double* d_H = nullptr;
+  size_t bytes = 0;
+  int big_n = 0, big_nt = 0;  // ILMM joint dimension mN and its tile count
+
+  int nloc() const { return hi - lo; }
+  size_t npad() const { return (size_t)nt * TILE; }
+  TiledSym Lsym() const { return TiledSym{d_L, kind == POST_ILMM ? big_nt : nt, sym_tiles(kind == POST_ILMM ? big_nt : nt) * TT}; }
+  size_t wstride() const { return (size_t)(kind == POST_ILMM ? big_nt : nt) * TT; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: context
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* lmm_version(void) { return "liblmm 0.1.0 (sm_100a)"; }
+
+extern "C" int lmm_ctx_create(int device, lmm_ctx** out) {
+  if (!out) return LMM_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return LMM_E_CUDA;  // no CPU fallback
+  }
+  if (device < 0 || device >= ndev) return LMM_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return LMM_E_CUDA;
+  lmm_ctx* ctx = new lmm_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return LMM_E_CUDA;
+  }
+  for (auto& e : ctx->ev) cudaEventCreate(&e);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return LMM_OK;
+}
+
+extern "C" int lmm_ctx_destroy(lmm_ctx* ctx) {
+  if (!ctx) return LMM_E_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
+  for (auto& e : ctx->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return LMM_OK;
+}
+
+extern "C" const char* lmm_last_error(lmm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
+  if (!ctx || !key) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::string k(key);
+  if (k == "distance_form") {
+    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_ARG, "distance_form must be 0 or 1");
+    ctx->distance_form = (int)value;
+  } else if (k == "outer_block") {
+    if (value < 1 || value > 64) return ctx->fail(LMM_E_ARG, "outer_block must be in [1, 64]");
+    ctx->outer_block = (int)value;
+  } else if (k == "gemm_impl") {
+    if (value != 0.0) return ctx->fail(LMM_E_UNSUPPORTED, "only gemm_impl 0 exists");
+  } else {
+    return ctx->fail(LMM_E_UNSUPPORTED, "unknown option " + k);
+  }
+  return LMM_OK;
+}
+
+extern "C" int lmm_ctx_counters(lmm_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!ctx) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (kernel_launches) *kernel_launches = ctx->launches;
+  if (h2d_bytes) *h2d_bytes = ctx->h2d;
+  if (d2h_bytes) *d2h_bytes = ctx->d2h;
+  return LMM_OK;
+}
+
+extern "C" int lmm_ctx_last_timings(lmm_ctx* ctx, double out_ms[8]) {
+  if (!ctx || !out_ms) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (int i = 0; i < 8; ++i) out_ms[i] = ctx->timings[i];
+  return LMM_OK;
+}
+
+extern "C" int lmm_comm_unique_id(void* out_128_bytes) {
+  if (!out_128_bytes) return LMM_E_ARG;
+  NcclApi& api = nccl_api();
+  if (!api.ok) return LMM_E_NCCL;
+  NcclId id;
+  if (api.GetUniqueId(&id) != 0) return LMM_E_NCCL;
+  memcpy(out_128_bytes, &id, 128);
+  return LMM_OK;
+}
+
+extern "C" int lmm_comm_set_shard(lmm_ctx* ctx, int nranks, int rank) {
+  if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  return LMM_OK;
+}
+
+extern "C" int lmm_comm_init(lmm_ctx* ctx, const void* unique_id_128_bytes, int nranks, int rank) {
+  if (!ctx || !unique_id_128_bytes || nranks < 1 || rank < 0 || rank >= nranks) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  NcclApi& api = nccl_api();
+  if (!api.ok) return ctx->fail(LMM_E_NCCL, "libnccl.so.2 not found (dlopen)");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return LMM_E_CUDA;
+  NcclId id;
+  memcpy(&id, unique_id_128_bytes, 128);
+  int r = api.CommInitRank(&ctx->comm, nranks, id, rank);
+  if (r != 0) return ctx->fail(LMM_E_NCCL, std::string("ncclCommInitRank: ") + (api.GetErrorString ? api.GetErrorString(r) : "?"));
+  ctx->nranks = nranks;
+  ctx->rank = rank;
+  return LMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Orthogonal validation (host): src/orthogonal_matrix.jl:21-23  isapprox(U'U, I)
+// ------------------------------------------------------------------------------------------------
+extern "C" int lmm_orthogonal_validate(const double* U, int p, int m) {
+  if (!U || p <= 0 || m <= 0) return LMM_E_ARG;
+  // |U'U - I|_F <= sqrt(eps) * max(|U'U|_F, |I|_F)
+  double diff2 = 0.0, g2 = 0.0;
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b < m; ++b) {
+      double s = 0.0;
+      for (int j = 0; j < p; ++j) s += U[(size_t)a * p + j] * U[(size_t)b * p + j];
+      g2 += s * s;
+      const double d = s - (a == b ? 1.0 : 0.0);
+      diff2 += d * d;
+    }
+  const double rtol = 1.4901161193847656e-08;  // sqrt(eps(Float64))
+  const double nrm = std::max(std::sqrt(g2), std::sqrt((double)m));
+  if (!(std::sqrt(diff2) <= rtol * nrm)) return LMM_E_NOT_ORTHOGONAL;
+  return LMM_OK;
+}
+
+extern "C" int lmm_reorder_indices(int N, int p, int direction, int64_t* out) {
+  if (N <= 0 || p <= 0 || !out || (direction != 0 && direction != 1)) return LMM_E_ARG;
+  // direction 0: vec(reshape(1:pN, N, p)')  (src/independent_mogp.jl:138)
+  // direction 1: vec(reshape(1:pN, p, N)')  (src/independent_mogp.jl:144)
+  if (direction == 0) {
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < p; ++j) out[(size_t)i * p + j] = (int64_t)j * N + i;
+  } else {
+    for (int j = 0; j < p; ++j)
+      for (int i = 0; i < N; ++i) out[(size_t)j * N + i] = (int64_t)i * p + j;
+  }
+  return LMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Core: per-latent exact GP logpdf / posterior over a set of independent latents
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// Projection description (host): Ty = T Y  (m x p), residual |Y - Q (P Y)|², regulariser constant.
+struct Projection {
+  std::vector<double> T;      // m x p col-major
+  std::vector<double> P, Q;   // m x p, p x m (empty: no regulariser)
+  std::vector<double> noise;  // per latent diagonal noise
+  double reg_c0 = 0.0;        // n * (...) part of the regulariser
+  bool has_reg = false;
+};
+
+struct RunOut {
+  lmm_post** post = nullptr;
+  double* logpdf = nullptr;
+  double* lml_terms = nullptr;
+  int* info_latent = nullptr;
+};
+
+// The shared driver for OILMM (src/oilmm.jl:79-93, 116-134) and IndependentMOGP
+// (src/independent_mogp.jl:74-80, 119-126).
+int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const double* x, int N, int D, int p, double sigma2,
+                const double* y, const Projection& pr, const double* Hhost, const double* Uhost, const double* Shost, RunOut out) {
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  for (double& t : ctx->timings) t = 0.0;
+  int lo, hi;
+  shard_range(ctx, m, lo, hi);
+  const int mloc = hi - lo;
+  const int nt = ntiles(N);
+  const size_t npad = (size_t)nt * TILE;
+  const bool keep = out.post != nullptr;
+
+  CU(cudaEventRecord(ctx->ev[0], st));
+  // ---- stage inputs
+  DevBuf b_x, b_y, b_T, b_P, b_Q, b_means, b_ty, b_resid_part, b_resid, b_terms;
+  CU(b_x.alloc(ctx, npad * D * sizeof(double)));
+  CU(cudaMemsetAsync(b_x.p, 0, npad * D * sizeof(double), st));
+  CU(copy_in(ctx, b_x.as<double>(), x, (size_t)N * D));
+  const double* d_y = y;
+  if (!is_device_ptr(y)) {
+    CU(b_y.alloc(ctx, (size_t)p * N * sizeof(double)));
+    CU(copy_in(ctx, b_y.as<double>(), y, (size_t)p * N));
+    d_y = b_y.as<double>();
+  }
+  CU(b_T.alloc(ctx, pr.T.size() * sizeof(double)));
+  CU(copy_in(ctx, b_T.as<double>(), pr.T.data(), pr.T.size()));
+  if (pr.has_reg) {
+    CU(b_P.alloc(ctx, pr.P.size() * sizeof(double)));
+    CU(copy_in(ctx, b_P.as<double>(), pr.P.data(), pr.P.size()));
+    CU(b_Q.alloc(ctx, pr.Q.size() * sizeof(double)));
+    CU(copy_in(ctx, b_Q.as<double>(), pr.Q.data(), pr.Q.size()));
+  }
+  std::vector<double> hmeans(mloc > 0 ? mloc : 1, 0.0);
+  for (int i = lo; i < hi; ++i) hmeans[i - lo] = latents[i].mean_const;
+  CU(b_means.alloc(ctx, hmeans.size() * sizeof(double)));
+  CU(copy_in(ctx, b_means.as<double>(), hmeans.data(), hmeans.size()));
+  std::vector<LatentParams> hparams;
+  fill_params(hparams, latents, pr.noise.data(), lo, hi);
+  DevBuf b_params;
+  CU(b_params.alloc(ctx, (hparams.size() + 1) * sizeof(LatentParams)));
+  if (mloc > 0) {
+    ctx->h2d += (int64_t)(hparams.size() * sizeof(LatentParams));
+    CU(cudaMemcpyAsync(b_params.p, hparams.data(), hparams.size() * sizeof(LatentParams), cudaMemcpyHostToDevice, st));
+  }
+
+  // ---- projection + residual (K2/K3)
+  CU(b_ty.alloc(ctx, (size_t)(mloc > 0 ? mloc : 1) * npad * sizeof(double)));
+  CU(cudaMemsetAsync(b_ty.p, 0, (size_t)(mloc > 0 ? mloc : 1) * npad * sizeof(double), st));
+  const int nblk = (N + 31) / 32;
+  CU(b_resid_part.alloc(ctx, (size_t)nblk * sizeof(double)));
+  CU(b_resid.alloc(ctx, sizeof(double)));
+  CU(b_terms.alloc(ctx, (size_t)(m + 1) * sizeof(double)));
+  CU(cudaMemsetAsync(b_terms.p, 0, (size_t)(m + 1) * sizeof(double), st));
+  const bool do_reg = pr.has_reg && ctx->rank == 0;
+  {
+    int nb_out = 0;
+    CU(launch_project(st, d_y, N, p, b_T.as<double>(), m, lo, mloc, b_means.as<double>(), b_ty.as<double>(), npad,
+                      do_reg ? b_P.as<double>() : nullptr, do_reg ? b_Q.as<double>() : nullptr, b_resid_part.as<double>(), &nb_out));
+    ++ctx->launches;
+    if (do_reg) {
+      CU(launch_sum_partials(st, b_resid_part.as<double>(), nblk, b_resid.as<double>()));
+      regulariser_kernel<<<1, 1, 0, st>>>(b_terms.as<double>() + m, pr.reg_c0, b_resid.as<double>(), sigma2);
+      CU(cudaGetLastError());
+      ctx->launches += 2;
+    }
+  }
+  CU(cudaEventRecord(ctx->ev[1], st));
+
+  // ---- factor storage: all local latents when a posterior is kept, else a streamed arena
+  const size_t per_lat = factor_bytes_per_latent(nt);
+  int chunk = mloc;
+  if (!keep && mloc > 0) {
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    size_t budget = (size_t)((double)fr * 0.80);
+    size_t fit = budget / (per_lat + 6 * npad * sizeof(double));
+    if (fit < 1) fit = 1;
+    if ((size_t)chunk > fit) chunk = (int)fit;
+  }
+  DevBuf b_L, b_W, b_alpha, b_r, b_z, b_logdet, b_quad, b_info;
+  std::vector<int> hinfo(mloc > 0 ? mloc : 1, 0);
+  float ms_kmat = 0, ms_chol = 0, ms_solve = 0;
+  if (mloc > 0) {
+    CU(b_L.alloc(ctx, (size_t)chunk * sym_tiles(nt) * TT * sizeof(double)));
+    CU(b_W.alloc(ctx, (size_t)chunk * nt * TT * sizeof(double)));
+    CU(b_r.alloc(ctx, (size_t)chunk * npad * sizeof(double)));
+    CU(b_z.alloc(ctx, (size_t)chunk * npad * sizeof(double)));
+    if (keep) CU(b_alpha.alloc(ctx, (size_t)mloc * npad * sizeof(double)));
+    CU(b_logdet.alloc(ctx, (size_t)mloc * sizeof(double)));
+    CU(b_quad.alloc(ctx, (size_t)mloc * sizeof(double)));
+    CU(b_info.alloc(ctx, (size_t)mloc * sizeof(int)));
+    CU(cudaMemsetAsync(b_logdet.p, 0, (size_t)mloc * sizeof(double), st));
+    CU(cudaMemsetAsync(b_info.p, 0, (size_t)mloc * sizeof(int), st));
+    for (int c0 = 0; c0 < mloc; c0 += chunk) {
+      const int nb = (c0 + chunk <= mloc) ? chunk : mloc - c0;
+      TiledSym L{b_L.as<double>(), nt, sym_tiles(nt) * TT};
+      double* W = b_W.as<double>();
+      const size_t wstride = (size_t)nt * TT;
+      const LatentParams* dp = b_params.as<LatentParams>() + c0;
+      double* delta = b_ty.as<double>() + (size_t)c0 * npad;
+      CU(cudaEventRecord(ctx->ev[2], st));
+      CU(launch_kmat_sym(st, L, nb, b_x.as<double>(), N, D, dp, ctx->distance_form));
+      ++ctx->launches;
+      CU(cudaEventRecord(ctx->ev[3], st));
+      CU(chol_factor(ctx, L, W, wstride, nb, b_logdet.as<double>() + c0, b_info.as<int>() + c0));
+      CU(cudaEventRecord(ctx->ev[4], st));
+      CU(cudaMemcpyAsync(b_r.p, delta, (size_t)nb * npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CU(launch_fwd_solve(st, L, W, wstride, b_r.as<double>(), b_z.as<double>(), npad, nb, &ctx->launches));
+      CU(launch_sumsq(st, b_z.as<double>(), npad, (int)npad, nb, b_quad.as<double>() + c0));
+      ++ctx->launches;
+      if (keep) {
+        CU(cudaMemcpyAsync(b_r.p, b_z.p, (size_t)nb * npad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(launch_bwd_solve(st, L, W, wstride, b_r.as<double>(), b_alpha.as<double>() + (size_t)c0 * npad, npad, nb, &ctx->launches));
+      }
+      lml_terms_kernel<<<(nb + 127) / 128, 128, 0, st>>>(b_terms.as<double>(), lo + c0, nb, b_logdet.as<double>() + c0,
+                                                         b_quad.as<double>() + c0, N, LOG2PI);
+      CU(cudaGetLastError());
+      ++ctx->launches;
+      CU(cudaEventRecord(ctx->ev[5], st));
+      if (c0 + chunk < mloc || true) {
+        // accumulate stage timings per chunk (needs a sync; cheap relative to a chunk's factorisation)
+        CU(cudaEventSynchronize(ctx->ev[5]));
+        float a = 0, bq = 0, c = 0;
+        cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&bq, ctx->ev[3], ctx->ev[4]);
+        cudaEventElapsedTime(&c, ctx->ev[4], ctx->ev[5]);
+        ms_kmat += a; ms_chol += bq; ms_solve += c;
+      }
+    }
+  }
+  // ---- reduce the per-latent terms across ranks (one NCCL all-reduce over NVLink) and read back
+  if (ctx->comm && ctx->nranks > 1) {
+    int r = nccl_api().AllReduce(b_terms.p, b_terms.p, (size_t)(m + 1), NCCL_DOUBLE, NCCL_SUM, ctx->comm, st);
+    if (r != 0) return ctx->fail(LMM_E_NCCL, "ncclAllReduce failed");
+  }
+  std::vector<double> hterms(m + 1, 0.0);
+  CU(copy_out(ctx, hterms.data(), b_terms.p, (size_t)(m + 1) * sizeof(double)));
+  if (mloc > 0) CU(copy_out(ctx, hinfo.data(), b_info.p, (size_t)mloc * sizeof(int)));
+  CU(cudaEventRecord(ctx->ev[6], st));
+  CU(cudaStreamSynchronize(st));
+  {
+    float tot = 0, prj = 0;
+    cudaEventElapsedTime(&tot, ctx->ev[0], ctx->ev[6]);
+    cudaEventElapsedTime(&prj, ctx->ev[0], ctx->ev[1]);
+    ctx->timings[0] = tot; ctx->timings[1] = ms_kmat; ctx->timings[2] = ms_chol; ctx->timings[3] = ms_solve; ctx->timings[4] = prj;
+  }
+  for (int i = 0; i < mloc; ++i) {
+    if (hinfo[i] > 0) {
+      int pivot = hinfo[i] > N ? N : hinfo[i];
+      if (out.info_latent) *out.info_latent = lo + i;
+      char buf[128];
+      snprintf(buf, sizeof buf, "PosDefException: latent %d is not positive definite (pivot %d)", lo + i, pivot);
+      ctx->err = buf;
+      return pivot;
+    }
+  }
+  if (out.info_latent) *out.info_latent = -1;
+  if (out.lml_terms) memcpy(out.lml_terms, hterms.data(), (size_t)(m + 1) * sizeof(double));
+  if (out.logpdf) {
+    double s = 0.0;
+    for (int i = 0; i < m; ++i) s += hterms[i];
+    *out.logpdf = s + hterms[m];
+  }
+  if (keep) {
+    lmm_post* P = new lmm_post();
+    P->ctx = ctx; P->kind = kind; P->m = m; P->p = p; P->N = N; P->D = D; P->nt = nt; P->lo = lo; P->hi = hi;
+    P->descs.assign(latents, latents + m);
+    P->noise = pr.noise;
+    P->H.assign(Hhost, Hhost + (size_t)p * m);
+    if (Uhost) P->U.assign(Uhost, Uhost + (size_t)p * m);
+    if (Shost) P->S.assign(Shost, Shost + m);
+    P->sigma2 = sigma2;
+    DevBuf b_H;
+    CU(b_H.alloc(ctx, (size_t)p * m * sizeof(double)));
+    CU(copy_in(ctx, b_H.as<double>(), Hhost, (size_t)p * m));
+    CU(cudaStreamSynchronize(st));
+    P->bytes = (size_t)mloc * (per_lat + 2 * npad * sizeof(double)) + npad * D * sizeof(double);
+    P->d_xpad = (double*)b_x.detach();
+    P->d_L = (double*)b_L.detach();
+    P->d_W = (double*)b_W.detach();
+    P->d_alpha = (double*)b_alpha.detach();
+    P->d_delta = (double*)b_ty.detach();
+    P->d_params = (LatentParams*)b_params.detach();
+    P->d_H = (double*)b_H.detach();
+    *out.post = P;
+  }
+  return LMM_OK;
+}
+
+int oilmm_projection(lmm_ctx* ctx, const double* U, const double* S, int p, int m, double sigma2, int N, Projection& pr,
+                     std::vector<double>& H) {
+  for (int i = 0; i < m; ++i)
+    if (!(S[i] > 0.0)) return ctx->fail(LMM_E_ARG, "S must have positive entries");
+  if (!(sigma2 > 0.0)) return ctx->fail(LMM_E_ARG, "noise variance must be positive");
+  pr.T.resize((size_t)m * p);
+  pr.P.resize((size_t)m * p);
+  pr.Q.assign(U, U + (size_t)p * m);
+  pr.noise.resize(m);
+  H.resize((size_t)p * m);
+  double logdetS = 0.0;
+  for (int i = 0; i < m; ++i) {
+    const double rs = std::sqrt(S[i]);
+    for (int j = 0; j < p; ++j) {
+      const double u = U[(size_t)i * p + j];
+      pr.T[(size_t)j * m + i] = u / rs;  // T = sqrt(S) \ U'        src/oilmm.jl:24
+      pr.P[(size_t)j * m + i] = u;       // U'
+      H[(size_t)i * p + j] = u * rs;     // U * sqrt(S)             src/oilmm.jl:69
+    }
+    pr.noise[i] = sigma2 * (1.0 / S[i]);  // diag(σ² * inv(S))      src/oilmm.jl:27
+    logdetS += std::log(S[i]);
+  }
+  // -(n (logdet(S) + (p-m) log(2πσ²)) + |(I-UU')Y|²/σ²)/2          src/oilmm.jl:111-112
+  pr.reg_c0 = (double)N * (logdetS + (double)(p - m) * std::log(2.0 * M_PI * sigma2));
+  pr.has_reg = true;
+  return LMM_OK;
+}
+
+int check_common(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const void* x, int N, int D, int p, int out_dim) {
+  if (!latents || !x || m <= 0 || N <= 0 || D <= 0 || p <= 0) return ctx->fail(LMM_E_ARG, "null pointer or non-positive size");
+  if (D > 64) return ctx->fail(LMM_E_UNSUPPORTED, "input dimension D > 64 is not supported");
+  if (out_dim != p) return ctx->fail(LMM_E_OUT_DIM, "out dim of x != out dim of f.");
+  return check_descs(ctx, latents, m);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// OILMM
+// ------------------------------------------------------------------------------------------------
+extern "C" int lmm_oilmm_posterior(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
+                                   const double* U, const double* S, int p, double sigma2, const double* y, int out_dim,
+                                   lmm_post** out_post, double* out_logpdf, double* lml_terms, int* info_latent) {
+  if (!ctx) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (out_post) *out_post = nullptr;
+  int rc = check_common(ctx, latents, m, x, N, D, p, out_dim);
+  if (rc) return rc;
+  if (!U || !S || !y) return ctx->fail(LMM_E_ARG, "null pointer");
+  if (m > p) return ctx->fail(LMM_E_ARG, "more latents than outputs");
+  Projection pr;
+  std::vector<double> H;
+  if ((rc = oilmm_projection(ctx, U, S, p, m, sigma2, N, pr, H))) return rc;
+  RunOut out{out_post, out_logpdf, lml_terms, info_latent};
+  return latents_run(ctx, POST_OILMM, latents, m, x, N, D, p, sigma2, y, pr, H.data(), U, S, out);
+}
+
+extern "C" int lmm_oilmm_logpdf(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D, const double* U,
+                                const double* S, int p, double sigma2, const double* y, int out_dim, double* out_logpdf,
+                                double* lml_terms, int* info_latent) {
+  if (!out_logpdf && !lml_terms) return LMM_E_ARG;
+  return lmm_oilmm_posterior(ctx, latents, m, x, N, D, U, S, p, sigma2, y, out_dim, nullptr, out_logpdf, lml_terms, info_latent);
+}
+
+// ------------------------------------------------------------------------------------------------
+// IndependentMOGP
+// ------------------------------------------------------------------------------------------------
+extern "C" int lmm_imogp_posterior(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D, double sigma2,
+                                   const double* y, int out_dim, lmm_post** out_post, double* out_logpdf, int* info_latent) {
+  if (!ctx) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (out_post) *out_post = nullptr;
+  int rc = check_common(ctx, fs, m, x, N, D, m, out_dim);
+  if (rc) return rc;
+  if (!y) return ctx->fail(LMM_E_ARG, "null pointer");
+  if (!(sigma2 > 0.0)) return ctx->fail(LMM_E_ARG, "noise variance must be positive");
+  Projection pr;
+  pr.T.assign((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) pr.T[(size_t)i * m + i] = 1.0;
+  pr.noise.assign(m, sigma2);
+  pr.has_reg = false;
+  std::vector<double> H = pr.T;
+  RunOut out{out_post, out_logpdf, nullptr, info_latent};
+  return latents_run(ctx, POST_IMOGP, fs, m, x, N, D, m, sigma2, y, pr, H.data(), nullptr, nullptr, out);
+}
+
+extern "C" int lmm_imogp_logpdf(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D, double sigma2,
+                                const double* y, int out_dim, double* out_logpdf, double* lml_terms, int* info_latent) {
+  if (!ctx) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = check_common(ctx, fs, m, x, N, D, m, out_dim);
+  if (rc) return rc;
+  if (!y || (!out_logpdf && !lml_terms)) return ctx->fail(LMM_E_ARG, "null pointer");
+  if (!(sigma2 > 0.0)) return ctx->fail(LMM_E_ARG, "noise variance must be positive");
+  Projection pr;
+  pr.T.assign((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) pr.T[(size_t)i * m + i] = 1.0;
+  pr.noise.assign(m, sigma2);
+  pr.has_reg = false;
+  std::vector<double> H = pr.T;
+  RunOut out{nullptr, out_logpdf, lml_terms, info_latent};
+  return latents_run(ctx, POST_IMOGP, fs, m, x, N, D, m, sigma2, y, pr, H.data(), nullptr, nullptr, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Posterior handle
+// ------------------------------------------------------------------------------------------------
+extern "C" int lmm_post_free(lmm_post* post) {
+  if (!post) return LMM_E_ARG;
+  lmm_ctx* ctx = post->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  cudaSetDevice(ctx->device);
+  void* ptrs[] = {post->d_xpad, post->d_L, post->d_W, post->d_alpha, post->d_delta, post->d_params, post->d_H};
+  for (void* q : ptrs)
+    if (q) cudaFreeAsync(q, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  delete post;
+  return LMM_OK;
+}
+
+extern "C" int lmm_post_info(lmm_post* post, int* kind, int* m, int* p, int* N, int* D, int64_t* device_bytes) {
+  if (!post) return LMM_E_ARG;
+  if (kind) *kind = post->kind;
+  if (m) *m = post->m;
+  if (p) *p = post->p;
+  if (N) *N = post->N;
+  if (D) *D = post->D;
+  if (device_bytes) *device_bytes = (int64_t)post->bytes;
+  return LMM_OK;
+}
+
+extern "C" int lmm_post_export(lmm_post* post, int i, double* Lout, double* alpha, double* delta) {
+  if (!post) return LMM_E_ARG;
+  lmm_ctx* ctx = post->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  int b, n;
+  if (post->kind == POST_ILMM) {
+    if (i != 0) return ctx->fail(LMM_E_ARG, "an ILMM posterior has one joint factor (i = 0)");
+    b = 0;
+    n = post->big_n;
+  } else {
+    if (i < post->lo || i >= post->hi) return ctx->fail(LMM_E_ARG, "latent not resident on this rank");
+    b = i - post->lo;
+    n = post->N;
+  }
+  const size_t vstride = post->kind == POST_ILMM ? (size_t)post->big_nt * TILE : post->npad();
+  if (Lout) {
+    DevBuf dense;
+    CU(dense.alloc(ctx, (size_t)n * n * sizeof(double)));
+    CU(cudaMemsetAsync(dense.p, 0, (size_t)n * n * sizeof(double), ctx->stream));
+    CU(launch_untile_lower(ctx->stream, post->Lsym(), b, dense.as<double>(), n));
+    ++ctx->launches;
+    CU(copy_out(ctx, Lout, dense.p, (size_t)n * n * sizeof(double)));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (alpha) CU(copy_out(ctx, alpha, post->d_alpha + (size_t)b * vstride, (size_t)n * sizeof(double)));
+  if (delta) CU(copy_out(ctx, delta, post->d_delta + (size_t)b * vstride, (size_t)n * sizeof(double)));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LMM_OK;
+}
+
+namespace {
+
+// Latent posterior marginals at xs for the resident latents: ML/VL [nloc][nspad] on the device.
+// mean*_i = m_i + K(x*,x) α_i ; var*_i = k(x*,x*) - colsumsq(L_i^{-1} K(x,x*))   (AbstractGPs)
+int post_latent_marginals(lmm_post* post, const double* d_xspad, int Ns, int nts, double* d_ML, double* d_VL) {
+  lmm_ctx* ctx = post->ctx;
+  cudaStream_t st = ctx->stream;
+  const int nloc = post->nloc(), nt = post->nt;
+  const size_t nspad = (size_t)nts * TILE;
+  if (nloc == 0) return LMM_OK;
+  const size_t per_lat = (size_t)nts * nt * TT * sizeof(double);
+  size_t fr = 0, tot = 0;
+  CU(cudaMemGetInfo(&fr, &tot));
+  size_t fit = (size_t)((double)fr * 0.8) / per_lat;
+  if (fit < 1) fit = 1;
+  const int chunk = (size_t)nloc < fit ? nloc : (int)fit;
+  DevBuf b_V;
+  CU(b_V.alloc(ctx, (size_t)chunk * per_lat));
+  const TiledSym L = post->Lsym();
+  for (int c0 = 0; c0 < nloc; c0 += chunk) {
+    const int nb = (c0 + chunk <= nloc) ? chunk : nloc - c0;
+    TiledRect V{b_V.as<double>(), nts, nt, (size_t)nts * nt * TT};
+    TiledSym Lc{L.base + (size_t)c0 * L.batch_stride, nt, L.batch_stride};
+    const double* Wc = post->d_W + (size_t)c0 * post->wstride();
+    const LatentParams* dp = post->d_params + c0;
+    CU(launch_kmat_cross(st, V, nb, d_xspad, Ns, post->d_xpad, post->N, post->D, dp, ctx->distance_form));
+    CU(launch_rect_gemv(st, V, post->d_alpha + (size_t)c0 * post->npad(), post->npad(), d_ML + (size_t)c0 * nspad, nspad, dp, 1, nb));
+    ctx->launches += 2;
+    CU(trsm_right_lt(ctx, V, Lc, Wc, post->wstride(), nb));
+    CU(launch_rect_rowsumsq(st, V, d_VL + (size_t)c0 * nspad, nspad, dp, nb));
+    ++ctx->launches;
+  }
+  return LMM_OK;
+}
+
+}  // namespace
+
+namespace {
+int ilmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean, double* var);
+}
+
+extern "C" int lmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean, double* var) {
+  if (!post || !xs || Ns <= 0 || !mean || !var) return LMM_E_ARG;
+  lmm_ctx* ctx = post->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  if (post->kind == POST_ILMM) return ilmm_post_mean_and_var(post, xs, Ns, sigma2, mean, var);
+  cudaStream_t st = ctx->stream;
+  for (double& t : ctx->timings) t = 0.0;
+  const int nts = ntiles(Ns), nloc = post->nloc(), p = post->p, m = post->m;
+  const size_t nspad = (size_t)nts * TILE;
+  CU(cudaEventRecord(ctx->ev[0], st));
+  DevBuf b_xs, b_ML, b_VL, b_mean, b_var;
+  CU(b_xs.alloc(ctx, nspad * post->D * sizeof(double)));
+  CU(cudaMemsetAsync(b_xs.p, 0, nspad * post->D * sizeof(double), st));
+  CU(copy_in(ctx, b_xs.as<double>(), xs, (size_t)Ns * post->D));
+  CU(b_ML.alloc(ctx, (size_t)(nloc > 0 ? nloc : 1) * nspad * sizeof(double)));
+  CU(b_VL.alloc(ctx, (size_t)(nloc > 0 ? nloc : 1) * nspad * sizeof(double)));
+  int rc = post_latent_marginals(post, b_xs.as<double>(), Ns, nts, b_ML.as<double>(), b_VL.as<double>());
+  if (rc) return rc;
+  // one buffer [mean | var] so that a single all-reduce covers both
+  const size_t nout = (size_t)p * Ns;
+  CU(b_mean.alloc(ctx, 2 * nout * sizeof(double)));
+  double* d_mean = b_mean.as<double>();
+  double* d_var = d_mean + nout;
+  const bool multi = ctx->comm && ctx->nranks > 1;
+  if (post->kind == POST_OILMM) {
+    // M = H M_lat ; V = (H∘H)(V_lat + 1e-18) + σ²     src/oilmm.jl:61-75 (1e-18: default FiniteGP noise)
+    CU(cudaMemsetAsync(d_mean, 0, 2 * nout * sizeof(double), st));
+    CU(launch_backproject(st, post->d_H, p, m, post->lo, nloc, b_ML.as<double>(), b_VL.as<double>(), nspad, Ns, 1e-18, sigma2,
+                          multi ? 0 : 1, d_mean, d_var));
+    ++ctx->launches;
+  } else {
+    // IndependentMOGP: mean/var concatenated by outputs, var + σ²   src/independent_mogp.jl:50-57
+    CU(cudaMemsetAsync(d_mean, 0, 2 * nout * sizeof(double), st));
+    if (nloc > 0) {
+      dim3 grid((unsigned)((Ns + 255) / 256), (unsigned)nloc);
+      copy_add_kernel<<<grid, 256, 0, st>>>(d_mean + (size_t)post->lo * Ns, Ns, b_ML.as<double>(), nspad, Ns, 0.0);
+      copy_add_kernel<<<grid, 256, 0, st>>>(d_var + (size_t)post->lo * Ns, Ns, b_VL.as<double>(), nspad, Ns, multi ? 0.0 : sigma2);
+      CU(cudaGetLastError());
+      ctx->launches += 2;
+    }
+  }
+  if (multi) {
+    int r = nccl_api().AllReduce(d_mean, d_mean, 2 * nout, NCCL_DOUBLE, NCCL_SUM, ctx->comm, st);
+    if (r != 0) return ctx->fail(LMM_E_NCCL, "ncclAllReduce failed");
+    add_scalar_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(d_var, nout, sigma2);
+    CU(cudaGetLastError());
+    ++ctx->launches;
+  }
+  CU(copy_out(ctx, mean, d_mean, nout * sizeof(double)));
+  CU(copy_out(ctx, var, d_var, nout * sizeof(double)));
+  CU(cudaEventRecord(ctx->ev[1], st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->timings[0] = ms;
+  ctx->timings[5] = ms;
+  return LMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OILMM prior marginals: src/oilmm.jl:57-76 with GP latents (mean const, var = variance + 1e-18)
+// ------------------------------------------------------------------------------------------------
+extern "C" int lmm_oilmm_prior_mean_and_var(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* xs, int Ns, int D,
+                                            const double* U, const double* S, int p, double sigma2, int out_dim, double* mean,
+                                            double* var) {
+  if (!ctx) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = check_common(ctx, latents, m, xs, Ns, D, p, out_dim);
+  if (rc) return rc;
+  if (!U || !S || !mean || !var) return ctx->fail(LMM_E_ARG, "null pointer");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  Projection pr;
+  std::vector<double> H;
+  if ((rc = oilmm_projection(ctx, U, S, p, m, sigma2, Ns, pr, H))) return rc;
+  // latent marginals are constants along n: build ML/VL on the host side of the (tiny) m x Ns arrays
+  std::vector<double> ML((size_t)m * Ns), VL((size_t)m * Ns);
+  for (int i = 0; i < m; ++i)
+    for (int n = 0; n < Ns; ++n) {
+      ML[(size_t)i * Ns + n] = latents[i].mean_const;
+      VL[(size_t)i * Ns + n] = latents[i].variance;
+    }
+  DevBuf b_H, b_ML, b_VL, b_out;
+  CU(b_H.alloc(ctx, H.size() * sizeof(double)));
+  CU(copy_in(ctx, b_H.as<double>(), H.data(), H.size()));
+  CU(b_ML.alloc(ctx, ML.size() * sizeof(double)));
+  CU(copy_in(ctx, b_ML.as<double>(), ML.data(), ML.size()));
+  CU(b_VL.alloc(ctx, VL.size() * sizeof(double)));
+  CU(copy_in(ctx, b_VL.as<double>(), VL.data(), VL.size()));
+  const size_t nout = (size_t)p * Ns;
+  CU(b_out.alloc(ctx, 2 * nout * sizeof(double)));
+  CU(launch_backproject(st, b_H.as<double>(), p, m, 0, m, b_ML.as<double>(), b_VL.as<double>(), Ns, Ns, 1e-18, sigma2, 1,
+                        b_out.as<double>(), b_out.as<double>() + nout));
+  ++ctx->launches;
+  CU(copy_out(ctx, mean, b_out.p, nout * sizeof(double)));
+  CU(copy_out(ctx, var, b_out.as<double>() + nout, nout * sizeof(double)));
+  CU(cudaStreamSynchronize(st));
+  return LMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched Cholesky primitive
+// ------------------------------------------------------------------------------------------------
+extern "C" int lmm_potrf_batched(lmm_ctx* ctx, const double* A, int N, int batch, double* L_out, double* logdet_out, int* info) {
+  if (!ctx) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!A || N <= 0 || batch <= 0) return ctx->fail(LMM_E_ARG, "null pointer or non-positive size");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  for (double& t : ctx->timings) t = 0.0;
+  const int nt = ntiles(N);
+  DevBuf b_A, b_L, b_W, b_logdet, b_info;
+  const double* dA = A;
+  if (!is_device_ptr(A)) {
+    CU(b_A.alloc(ctx, (size_t)batch * N * N * sizeof(double)));
+    CU(copy_in(ctx, b_A.as<double>(), A, (size_t)batch * N * N));
+    dA = b_A.as<double>();
+  }
+  CU(b_L.alloc(ctx, (size_t)batch * sym_tiles(nt) * TT * sizeof(double)));
+  CU(b_W.alloc(ctx, (size_t)batch * nt * TT * sizeof(double)));
+  CU(b_logdet.alloc(ctx, (size_t)batch * sizeof(double)));
+  CU(b_info.alloc(ctx, (size_t)batch * sizeof(int)));
+  CU(cudaMemsetAsync(b_logdet.p, 0, (size_t)batch * sizeof(double), st));
+  CU(cudaMemsetAsync(b_info.p, 0, (size_t)batch * sizeof(int), st));
+  TiledSym L{b_L.as<double>(), nt, sym_tiles(nt) * TT};
+  CU(launch_tile_from_dense(st, L, batch, dA, N));
+  ++ctx->launches;
+  CU(cudaEventRecord(ctx->ev[0], st));
+  CU(chol_factor(ctx, L, b_W.as<double>(), (size_t)nt * TT, batch, b_logdet.as<double>(), b_info.as<int>()));
+  CU(cudaEventRecord(ctx->ev[1], st));
+  std::vector<int> hinfo(batch, 0);
+  CU(copy_out(ctx, hinfo.data(), b_info.p, (size_t)batch * sizeof(int)));
+  if (logdet_out) CU(copy_out(ctx, logdet_out, b_logdet.p, (size_t)batch * sizeof(double)));
+  if (L_out) {
+    DevBuf dense;
+    CU(dense.alloc(ctx, (size_t)N * N * sizeof(double)));
+    for (int b = 0; b < batch; ++b) {
+      CU(cudaMemsetAsync(dense.p, 0, (size_t)N * N * sizeof(double), st));
+      CU(launch_untile_lower(st, L, b, dense.as<double>(), N));
+      ++ctx->launches;
+      CU(copy_out(ctx, L_out + (size_t)b * N * N, dense.p, (size_t)N * N * sizeof(double)));
+      CU(cudaStreamSynchronize(st));
+    }
+  }
+  CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->timings[0] = ms;
+  ctx->timings[2] = ms;
+  int worst = 0;
+  for (int b = 0; b < batch; ++b) {
+    int v = hinfo[b] > N ? N : hinfo[b];
+    if (info) info[b] = v;
+    if (v > worst) worst = v;
+  }
+  return worst;
+}
+
+extern "C" int lmm_potrf_bench(lmm_ctx* ctx, const lmm_gp_desc* desc, const double* x, int N, int D, double noise, int batch,
+                               double* logdet_out, double* out_ms_kmat, double* out_ms_chol) {
+  if (!ctx) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!desc || !x || N <= 0 || D <= 0 || batch <= 0) return ctx->fail(LMM_E_ARG, "null pointer or non-positive size");
+  int rc = check_descs(ctx, desc, 1);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  for (double& t : ctx->timings) t = 0.0;
+  const int nt = ntiles(N);
+  const size_t npad = (size_t)nt * TILE;
+  DevBuf b_x, b_L, b_W, b_logdet, b_info, b_params;
+  CU(b_x.alloc(ctx, npad * D * sizeof(double)));
+  CU(cudaMemsetAsync(b_x.p, 0, npad * D * sizeof(double), st));
+  CU(copy_in(ctx, b_x.as<double>(), x, (size_t)N * D));
+  std::vector<LatentParams> hp(batch);
+  for (int b = 0; b < batch; ++b) {
+    hp[b].kind = desc->kind; hp[b].pad = 0; hp[b].variance = desc->variance; hp[b].inv_ls = desc->inv_lengthscale;
+    hp[b].noise = noise; hp[b].mean = desc->mean_const;
+  }
+  CU(b_params.alloc(ctx, hp.size() * sizeof(LatentParams)));
+  CU(cudaMemcpyAsync(b_params.p, hp.data(), hp.size() * sizeof(LatentParams), cudaMemcpyHostToDevice, st));
+  CU(b_L.alloc(ctx, (size_t)batch * sym_tiles(nt) * TT * sizeof(double)));
+  CU(b_W.alloc(ctx, (size_t)batch * nt * TT * sizeof(double)));
+  CU(b_logdet.alloc(ctx, (size_t)batch * sizeof(double)));
+  CU(b_info.alloc(ctx, (size_t)batch * sizeof(int)));
+  CU(cudaMemsetAsync(b_logdet.p, 0, (size_t)batch * sizeof(double), st));
+  CU(cudaMemsetAsync(b_info.p, 0, (size_t)batch * sizeof(int), st));
+  TiledSym L{b_L.as<double>(), nt, sym_tiles(nt) * TT};
+  CU(cudaEventRecord(ctx->ev[0], st));
+  CU(launch_kmat_sym(st, L, batch, b_x.as<double>(), N, D, b_params.as<LatentParams>(), ctx->distance_form));
+  ++ctx->launches;
+  CU(cudaEventRecord(ctx->ev[1], st));
+  CU(chol_factor(ctx, L, b_W.as<double>(), (size_t)nt * TT, batch, b_logdet.as<double>(), b_info.as<int>()));
+  CU(cudaEventRecord(ctx->ev[2], st));
+  std::vector<int> hinfo(batch, 0);
+  CU(copy_out(ctx, hinfo.data(), b_info.p, (size_t)batch * sizeof(int)));
+  if (logdet_out) CU(copy_out(ctx, logdet_out, b_logdet.p, (size_t)batch * sizeof(double)));
+  CU(cudaStreamSynchronize(st));
+  float a = 0, c = 0;
+  cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&c, ctx->ev[1], ctx->ev[2]);
+  if (out_ms_kmat) *out_ms_kmat = a;
+  if (out_ms_chol) *out_ms_chol = c;
+  ctx->timings[0] = a + c; ctx->timings[1] = a; ctx->timings[2] = c;
+  int worst = 0;
+  for (int b = 0; b < batch; ++b) {
+    int v = hinfo[b] > N ? N : hinfo[b];
+    if (v > worst) worst = v;
+  }
+  return worst;
+}
+
+#include "api_ext.inc"

@@ -1,0 +1,160 @@
+// Dense ILMM assembly (K14/K15 of SURVEY.md §2.3): the (mN x mN) projected covariance
+// blockdiag(K_a) + ΣT ⊗ I_N of src/ilmm.jl:160-162 and the (pN x pN) form H K H' + σ²I
+// (test/ilmm.jl:5, src/ilmm.jl:136) are written tile by tile straight into the Cholesky
+// workspace: no kron(), no BlockDiagonal -> Matrix copy, K_a entries are recomputed in registers.
+// Also the block-diagonal cross-covariance K(x*, x) of the joint ILMM posterior and the per-point
+// Gram reduction its predictive variance needs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace lmm {
+
+__device__ __forceinline__ double kernel_pair(const LatentParams& lp, const double* __restrict__ xa, const double* __restrict__ xb,
+                                              int D, int form, bool same_point) {
+  if (same_point) return kappa_eval(lp.kind, lp.variance, 0.0);
+  double a[64], b[64];
+  double sa = 0.0, sb = 0.0;
+  for (int k = 0; k < D; ++k) {
+    a[k] = xa[k] * lp.inv_ls;
+    b[k] = xb[k] * lp.inv_ls;
+    sa = fma(a[k], a[k], sa);
+    sb = fma(b[k], b[k], sb);
+  }
+  return kappa_eval(lp.kind, lp.variance, sqdist(a, b, D, sa, sb, form));
+}
+
+// mode 0 (projected): dim = m*N, val = [a==b] k_a(i,j) + E[a,b] [i==j]      (E = ΣT, m x m col-major)
+// mode 1 (dense):     dim = q*N, val = sum_l Hm[a,l] Hm[b,l] k_l(i,j) + E0 [a==b][i==j]   (Hm: q x m col-major)
+__global__ void __launch_bounds__(256) assemble_ilmm_kernel(TiledSym out, const double* __restrict__ x, int N, int D,
+                                                            const LatentParams* __restrict__ params, int m, int q,
+                                                            const double* __restrict__ E, const double* __restrict__ Hm, int mode,
+                                                            int form) {
+  const int tl = blockIdx.x;
+  int I = (int)((sqrt(8.0 * (double)tl + 1.0) - 1.0) * 0.5);
+  while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tl) ++I;
+  while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
+  const int J = tl - (int)((size_t)I * (I + 1) / 2);
+  const int dim = q * N;
+  double* tile = out.tile(0, I, J);
+  for (int e = threadIdx.x; e < TT; e += 256) {
+    int r, c;
+    tile_rc(e, r, c);
+    const int gr = I * TILE + r, gc = J * TILE + c;
+    double val;
+    if (gr >= dim || gc >= dim) {
+      val = (gr == gc) ? 1.0 : 0.0;
+    } else {
+      const int a = gr / N, i = gr % N, b = gc / N, j = gc % N;
+      const double* xi = x + (size_t)i * D;
+      const double* xj = x + (size_t)j * D;
+      if (mode == 0) {
+        val = (a == b) ? kernel_pair(params[a], xi, xj, D, form, i == j) : 0.0;
+        if (i == j) val += E[(size_t)b * m + a];
+      } else {
+        val = 0.0;
+        for (int l = 0; l < m; ++l)
+          val = fma(Hm[(size_t)l * q + a] * Hm[(size_t)l * q + b], kernel_pair(params[l], xi, xj, D, form, i == j), val);
+        if (gr == gc) val += E[0];
+      }
+    }
+    tile[e] = val;
+  }
+}
+
+cudaError_t launch_assemble_ilmm(cudaStream_t st, TiledSym out, const double* x, int N, int D, const LatentParams* params, int m,
+                                 int q, const double* E, const double* Hm, int mode, int form) {
+  assemble_ilmm_kernel<<<(unsigned)sym_tiles(out.nt), 256, 0, st>>>(out, x, N, D, params, m, q, E, Hm, mode, form);
+  return cudaGetLastError();
+}
+
+// Block-diagonal cross-covariance: rows (a, n) over x* (m*Ns), cols (b, i) over x (m*N).
+__global__ void __launch_bounds__(256) assemble_cross_blockdiag_kernel(TiledRect out, const double* __restrict__ xs, int Ns,
+                                                                       const double* __restrict__ x, int N, int D,
+                                                                       const LatentParams* __restrict__ params, int m, int form) {
+  const int R = blockIdx.x / out.ntc, J = blockIdx.x % out.ntc;
+  double* tile = out.tile(0, R, J);
+  for (int e = threadIdx.x; e < TT; e += 256) {
+    int r, c;
+    tile_rc(e, r, c);
+    const int gr = R * TILE + r, gc = J * TILE + c;
+    double val = 0.0;
+    if (gr < m * Ns && gc < m * N) {
+      const int a = gr / Ns, n = gr % Ns, b = gc / N, i = gc % N;
+      if (a == b) val = kernel_pair(params[a], xs + (size_t)n * D, x + (size_t)i * D, D, form, false);
+    }
+    tile[e] = val;
+  }
+}
+cudaError_t launch_assemble_cross_blockdiag(cudaStream_t st, TiledRect out, const double* xs, int Ns, const double* x, int N, int D,
+                                            const LatentParams* params, int m, int form) {
+  assemble_cross_blockdiag_kernel<<<(unsigned)(out.ntr * out.ntc), 256, 0, st>>>(out, xs, Ns, x, N, D, params, m, form);
+  return cudaGetLastError();
+}
+
+// ILMM predictive marginals from the joint latent posterior.  V = Kc L^{-T} (rows (a,n)).
+// grid (Ns).  mean[j*Ns+n] = sum_a H[j,a] (mean_a + mlat[a*Ns+n]);
+// var[j*Ns+n] = sum_ab H[j,a] H[j,b] ( [a==b](variance_a + 1e-18) - sum_r V[(a,n),r] V[(b,n),r] ) + sigma2
+__global__ void __launch_bounds__(256) ilmm_predict_kernel(TiledRect V, int Ns, int m, int p, const double* __restrict__ H,
+                                                           const LatentParams* __restrict__ params,
+                                                           const double* __restrict__ mlat, double sigma2,
+                                                           double* __restrict__ mean, double* __restrict__ var) {
+  extern __shared__ double G[];  // m*m
+  __shared__ double red[256];
+  const int n = blockIdx.x, t = threadIdx.x;
+  const int ncols = V.ntc * TILE;
+  for (int a = 0; a < m; ++a) {
+    for (int b = 0; b <= a; ++b) {
+      const int ra = a * Ns + n, rb = b * Ns + n;
+      const double* ta = V.base + (size_t)(ra / TILE) * V.ntc * TT;
+      const double* tb = V.base + (size_t)(rb / TILE) * V.ntc * TT;
+      double s = 0.0;
+      for (int c = t; c < ncols; c += 256) {
+        const size_t off = (size_t)(c / TILE) * TT;
+        s = fma(ta[off + tile_elem(ra % TILE, c % TILE)], tb[off + tile_elem(rb % TILE, c % TILE)], s);
+      }
+      red[t] = s;
+      __syncthreads();
+      for (int w = 128; w > 0; w >>= 1) {
+        if (t < w) red[t] += red[t + w];
+        __syncthreads();
+      }
+      if (t == 0) {
+        G[a * m + b] = red[0];
+        G[b * m + a] = red[0];
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = t; j < p; j += 256) {
+    double sm_ = 0.0, sv = 0.0;
+    for (int a = 0; a < m; ++a) {
+      const double ha = H[(size_t)a * p + j];
+      sm_ = fma(ha, params[a].mean + mlat[(size_t)a * Ns + n], sm_);
+      for (int b = 0; b < m; ++b) {
+        const double c = ((a == b) ? (params[a].variance + 1e-18) : 0.0) - G[a * m + b];
+        sv = fma(ha * H[(size_t)b * p + j], c, sv);
+      }
+    }
+    mean[(size_t)j * Ns + n] = sm_;
+    var[(size_t)j * Ns + n] = sv + sigma2;
+  }
+}
+cudaError_t launch_ilmm_predict(cudaStream_t st, TiledRect V, int Ns, int m, int p, const double* H, const LatentParams* params,
+                                const double* mlat, double sigma2, double* mean, double* var) {
+  ilmm_predict_kernel<<<Ns, 256, (size_t)m * m * sizeof(double), st>>>(V, Ns, m, p, H, params, mlat, sigma2, mean, var);
+  return cudaGetLastError();
+}
+
+// Gather rows: dst[u][:] = src[idx[u]][:]  (delta replication for the hyper-parameter sweep)
+__global__ void gather_rows_kernel(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ idx, size_t stride) {
+  const int u = blockIdx.y;
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < stride) dst[(size_t)u * stride + k] = src[(size_t)idx[u] * stride + k];
+}
+cudaError_t launch_gather_rows(cudaStream_t st, double* dst, const double* src, const int* idx, size_t stride, int n) {
+  dim3 grid((unsigned)((stride + 255) / 256), (unsigned)n);
+  gather_rows_kernel<<<grid, 256, 0, st>>>(dst, src, idx, stride);
+  return cudaGetLastError();
+}
+
+}  // namespace lmm

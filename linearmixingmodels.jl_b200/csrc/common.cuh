@@ -1,0 +1,100 @@
+// Shared definitions for liblmm (sm_100a only).
+//
+// HBM layout of a symmetric / lower-triangular N x N matrix ("TiledSym"): N is padded to
+// nt*128; only tiles (I, J) with I >= J are stored, row-panel-major: tile (I, J) lives at
+// ((I*(I+1))/2 + J) * 16384 doubles, so the row panel L[I, 0:J] a trailing update streams is ONE
+// contiguous run of HBM.  Inside a 128x128 tile elements are "k4-interleaved":
+//     elem(r, c) = (c/4)*512 + (r/8)*32 + (r%8)*4 + (c%4)
+// i.e. every (8 rows x 4 cols) block is 32 contiguous doubles in exactly the lane order of the
+// FP64 tensor-core fragment of mma.m8n8k4 (lane = (r%8)*4 + c%4) for BOTH the A operand (rows of
+// tile (I,k)) and the B operand (rows of tile (J,k), used transposed).  A 16-column k-chunk of a
+// tile is one contiguous 16 KB run, fragment loads from shared memory are conflict-free 256 B
+// warp accesses without any swizzle, and the accumulator fragment maps to 16 B stores.
+// Rectangular operands ("TiledRect", e.g. K(x*, x) rows) use the same tiles, row-major by tile.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lmm {
+
+constexpr int TILE = 128;
+constexpr int TT = TILE * TILE;  // doubles per tile
+
+__host__ __device__ __forceinline__ int tile_elem(int r, int c) {
+  return ((c >> 2) << 9) + ((r >> 3) << 5) + ((r & 7) << 2) + (c & 3);
+}
+// inverse: offset e in [0, 16384) -> (r, c)
+__host__ __device__ __forceinline__ void tile_rc(int e, int& r, int& c) {
+  r = (((e >> 5) & 15) << 3) + ((e >> 2) & 7);
+  c = ((e >> 9) << 2) + (e & 3);
+}
+__host__ __device__ __forceinline__ size_t sym_tile_index(int I, int J) {
+  return (size_t)I * (size_t)(I + 1) / 2 + (size_t)J;
+}
+__host__ __device__ __forceinline__ size_t sym_tiles(int nt) { return (size_t)nt * (size_t)(nt + 1) / 2; }
+
+struct TiledSym {
+  double* base;
+  int nt;
+  size_t batch_stride;  // doubles
+  __host__ __device__ __forceinline__ double* tile(int b, int I, int J) const {
+    return base + (size_t)b * batch_stride + sym_tile_index(I, J) * TT;
+  }
+};
+
+struct TiledRect {
+  double* base;
+  int ntr, ntc;
+  size_t batch_stride;  // doubles
+  __host__ __device__ __forceinline__ double* tile(int b, int R, int J) const {
+    return base + (size_t)b * batch_stride + ((size_t)R * ntc + J) * TT;
+  }
+};
+
+// Per-latent kernel parameters on the device.
+struct LatentParams {
+  int kind;
+  int pad;
+  double variance;
+  double inv_ls;
+  double noise;  // added on the diagonal (ΣT_i for OILMM, σ² for IndependentMOGP)
+  double mean;
+};
+
+// κ(d²)·variance -- KernelFunctions kappa for SE / Matern32 / Matern52.
+__device__ __forceinline__ double kappa_eval(int kind, double variance, double d2) {
+  double v;
+  if (kind == 0) {
+    v = exp(-d2 / 2.0);
+  } else {
+    double d = sqrt(d2);
+    if (kind == 1) {
+      double s = 1.7320508075688772 * d;  // sqrt(3)
+      v = (1.0 + s) * exp(-s);
+    } else {
+      double s = 2.23606797749979 * d;  // sqrt(5)
+      v = (1.0 + s + 5.0 * d * d / 3.0) * exp(-s);
+    }
+  }
+  return variance * v;
+}
+
+// Squared distance of scaled points.  form 0: Distances.jl pairwise (|a|²+|b|² - 2 a·b, clamped at
+// 0); form 1: direct differences.  a, b point at D scaled coordinates.
+__device__ __forceinline__ double sqdist(const double* a, const double* b, int D, double sa, double sb, int form) {
+  if (form == 0) {
+    double dot = 0.0;
+    for (int k = 0; k < D; ++k) dot = fma(a[k], b[k], dot);
+    double t = sa + sb;
+    double d2 = t - 2.0 * dot;
+    return d2 > 0.0 ? d2 : 0.0;
+  }
+  double d2 = 0.0;
+  for (int k = 0; k < D; ++k) {
+    double df = a[k] - b[k];
+    d2 = fma(df, df, d2);
+  }
+  return d2;
+}
+
+}  // namespace lmm

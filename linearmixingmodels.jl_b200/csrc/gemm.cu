@@ -1,0 +1,153 @@
+// FP64 tensor-core (DMMA) tile GEMM: the trailing update / panel solve of the batched blocked
+// Cholesky (K6) and of the posterior TRSM (K10).  Replaces the dsyrk/dgemm/dtrsm calls LAPACK
+// dpotrf makes under `cholesky(Symmetric(C))` (reference call site src/oilmm.jl:90,128 via
+// AbstractGPs).
+//
+//   UPDATE: C(I,J) -= sum_{k in [k0,k1)} A(I,k) * B(J,k)^T        (128x128 tiles, K = 128 per k)
+//   TRSM  : C(I,J)  = C(I,J) * W(J)^T        with W(J) = inv(L(J,J)) (lower triangular)
+//
+// One CTA = one 128x128 output tile, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 m8n8k4 DMMA
+// fragments (64 accumulator doubles / thread).  Operands stream through a 4-stage cp.async ring
+// of 16-column k-chunks (16 KB of A + 16 KB of B per stage; chunks of consecutive k-tiles are
+// contiguous in HBM thanks to the row-panel-major tile order).  The k4-interleaved tile layout
+// makes every fragment load a conflict-free 256 B warp access (see common.cuh).
+// Bound: FP64 tensor pipe (64 FMA/clk/SM): 2*128^3 flop per k-tile per CTA vs 256 KB of L2->SM
+// traffic -> 16 flop/B, far above the L2 balance; HBM traffic is lower still (row panels are
+// shared through L2 by the CTAs of one tile row / column).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace lmm {
+
+constexpr int GEMM_STAGES = 4;
+constexpr int CHUNK = 2048;  // doubles per operand per stage (128 rows x 16 k)
+constexpr size_t GEMM_SMEM = (size_t)GEMM_STAGES * 2 * CHUNK * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) gemm_tile_kernel(GemmArgs g) {
+  extern __shared__ __align__(128) double smem[];
+  const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
+  if (g.sym && I < J) return;
+
+  double* Ctile = g.C.tile(b, I, J);
+  const double* Asrc;
+  const double* Bsrc;
+  int nchunks;
+  if (MODE == GEMM_UPDATE) {
+    Asrc = g.A.tile(b, I, g.k0);
+    Bsrc = g.B.tile(b, J, g.k0);
+    nchunks = (g.k1 - g.k0) * 8;
+  } else {
+    Asrc = Ctile;
+    Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
+    nchunks = 8;
+  }
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 1, wn = warp >> 1;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto issue = [&](int q) {
+    double* sa = smem + (size_t)(q % GEMM_STAGES) * (2 * CHUNK);
+    double* sb = sa + CHUNK;
+    const double* ga = Asrc + (size_t)q * CHUNK;
+    const double* gb = Bsrc + (size_t)q * CHUNK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = (tid + i * 256) * 2;
+      cp_async16(sa + idx, ga + idx);
+      cp_async16(sb + idx, gb + idx);
+    }
+  };
+
+#pragma unroll
+  for (int q = 0; q < GEMM_STAGES - 1; ++q) {
+    if (q < nchunks) issue(q);
+    cp_async_commit();
+  }
+
+  for (int q = 0; q < nchunks; ++q) {
+    cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();
+    const int qn = q + GEMM_STAGES - 1;
+    if (qn < nchunks) issue(qn);
+    cp_async_commit();
+
+    const double* sa = smem + (size_t)(q % GEMM_STAGES) * (2 * CHUNK) + (wm * 8) * 32 + lane;
+    const double* sb = smem + (size_t)(q % GEMM_STAGES) * (2 * CHUNK) + CHUNK + (wn * 4) * 32 + lane;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      double a[8], bq[4];
+#pragma unroll
+      for (int mb = 0; mb < 8; ++mb) a[mb] = sa[ks * 512 + mb * 32];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) bq[nb] = sb[ks * 512 + nb * 32];
+#pragma unroll
+      for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bq[nb]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // Epilogue.  Accumulator fragment (mb, nb): rows R = wm*64 + mb*8 + lane/4, cols
+  // Cc = wn*32 + nb*8 + 2*(lane%4) + {0,1}  ->  one 16-byte store in the interleaved layout.
+  const int g4 = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int mb = 0; mb < 8; ++mb) {
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const int cg = wn * 8 + nb * 2 + (t4 >> 1);  // Cc / 4
+      const int off = (cg << 9) + ((wm * 8 + mb) << 5) + (g4 << 2) + ((t4 & 1) << 1);
+      double2* ptr = reinterpret_cast<double2*>(Ctile + off);
+      double2 v;
+      if (MODE == GEMM_UPDATE) {
+        v = *ptr;
+        v.x -= acc[mb][nb][0];
+        v.y -= acc[mb][nb][1];
+      } else {
+        v.x = acc[mb][nb][0];
+        v.y = acc[mb][nb][1];
+      }
+      *ptr = v;
+    }
+  }
+}
+
+cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch) {
+  if (ncols <= 0 || nrows <= 0 || batch <= 0) return cudaSuccess;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel<GEMM_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tile_kernel<GEMM_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
+  if (mode == GEMM_UPDATE)
+    gemm_tile_kernel<GEMM_UPDATE><<<grid, 256, GEMM_SMEM, st>>>(a);
+  else
+    gemm_tile_kernel<GEMM_TRSM><<<grid, 256, GEMM_SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace lmm

@@ -1,0 +1,86 @@
+// Host-callable launchers of the liblmm kernels (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace lmm {
+
+// ---- kmat.cu
+cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const double* xpad, int N, int D,
+                            const LatentParams* params, int form);
+cudaError_t launch_kmat_cross(cudaStream_t st, TiledRect out, int batch, const double* xa_pad, int Na, const double* xb_pad,
+                              int Nb, int D, const LatentParams* params, int form);
+
+// ---- gemm.cu : C(I,J) -= sum_k X(I,k) L(J,k)^T   |   C(I,J) = C(I,J) W(J)^T
+struct TileOperand {
+  double* base;
+  size_t batch_stride;  // doubles
+  int rect;             // 0: packed-lower tiles, 1: rectangular (row-major by tile, ntc tiles per row)
+  int ntc;
+  __host__ __device__ __forceinline__ double* tile(int b, int I, int k) const {
+    return base + (size_t)b * batch_stride + (rect ? ((size_t)I * ntc + k) : sym_tile_index(I, k)) * TT;
+  }
+};
+inline TileOperand operand(const TiledSym& s) { return TileOperand{s.base, s.batch_stride, 0, s.nt}; }
+inline TileOperand operand(const TiledRect& r) { return TileOperand{r.base, r.batch_stride, 1, r.ntc}; }
+struct GemmArgs {
+  TileOperand A;          // rows I of the left operand (UPDATE only)
+  TileOperand B;          // rows J of the right operand, used transposed (UPDATE only)
+  TileOperand C;          // output tiles (I, J); TRSM reads its left operand from C
+  const double* W;        // inverse diagonal tiles [batch][nt] (TRSM only)
+  size_t w_batch_stride;
+  int i0, j0;             // tile (I, J) = (i0 + blockIdx.y, j0 + blockIdx.x)
+  int k0, k1;             // UPDATE: k-tile range
+  int sym;                // skip tiles with I < J
+};
+enum { GEMM_UPDATE = 0, GEMM_TRSM = 1 };
+cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch);
+
+// ---- potrf.cu : factor diagonal tile (J,J) in place, W(J) = inv(L_JJ), logdet += 2*sum(log diag)
+cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int batch, double* logdet,
+                              int* info);
+
+// ---- solve.cu
+// forward: z = L^{-1} r; backward: a = L^{-T} r.  rvec[batch][nt*128] is consumed (destroyed).
+cudaError_t launch_fwd_solve(cudaStream_t st, TiledSym L, const double* W, size_t w_batch_stride, double* rvec, double* zvec,
+                             size_t vec_stride, int batch, int64_t* launches);
+cudaError_t launch_bwd_solve(cudaStream_t st, TiledSym L, const double* W, size_t w_batch_stride, double* rvec, double* avec,
+                             size_t vec_stride, int batch, int64_t* launches);
+// out[b] = sum_i v[b][i]^2 (fixed order)
+cudaError_t launch_sumsq(cudaStream_t st, const double* v, size_t stride, int n, int batch, double* out);
+// y[b][R*128 + r] = add[b] + sum_J T(R,J) x[b][J*128 + :]   over a rectangular tiled matrix
+cudaError_t launch_rect_gemv(cudaStream_t st, TiledRect A, const double* x, size_t x_stride, double* y, size_t y_stride,
+                             const LatentParams* params, int add_mean, int batch);
+// y[b][R*128 + r] = base[b] - sum_J sum_c T(R,J)(r,c)^2     (posterior variance)
+cudaError_t launch_rect_rowsumsq(cudaStream_t st, TiledRect A, double* y, size_t y_stride, const LatentParams* params, int batch);
+// y = L * z for a packed-lower factor (rand): y[b][I] = sum_{J<=I} L(I,J) z[b][J]
+cudaError_t launch_lower_gemv(cudaStream_t st, TiledSym L, const double* z, size_t z_stride, double* y, size_t y_stride, int batch);
+// untile: copy factor b to a dense N x N column-major matrix (lower, zero upper)
+cudaError_t launch_untile_lower(cudaStream_t st, TiledSym L, int b, double* dense, int N);
+// tile: dense N x N col-major (lower read, mirrored) -> tiles (identity on padding)
+cudaError_t launch_tile_from_dense(cudaStream_t st, TiledSym L, int batch, const double* dense, int N);
+
+// ---- proj.cu
+// Ty[i][n] = sum_j T[i + lat0][j] Y[j][n] - mean_i  (i < mloc), written to ty[i*ty_stride + n], zero padding to ty_stride
+// resid_partial[blk] = sum over the block's columns of |Y - Q (P Y)|^2
+cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const double* T, int m, int lat0, int mloc,
+                           const double* means, double* ty, size_t ty_stride, const double* P, const double* Q,
+                           double* resid_partial, int* nblocks_out);
+cudaError_t launch_sum_partials(cudaStream_t st, const double* partial, int n, double* out);
+// back-projection: mean[j*Ns+n] = sum_i H[j, lat0+i] ML[i][n]; var = sum_i H^2 (VL + jitter) (+ sigma2 if add_noise)
+cudaError_t launch_backproject(cudaStream_t st, const double* H, int p, int m, int lat0, int mloc, const double* ML,
+                               const double* VL, size_t lat_stride, int Ns, double jitter, double sigma2, int add_noise,
+                               double* mean, double* var);
+
+}  // namespace lmm
+
+namespace lmm {
+// ---- assemble.cu
+cudaError_t launch_assemble_ilmm(cudaStream_t st, TiledSym out, const double* x, int N, int D, const LatentParams* params, int m,
+                                 int q, const double* E, const double* Hm, int mode, int form);
+cudaError_t launch_assemble_cross_blockdiag(cudaStream_t st, TiledRect out, const double* xs, int Ns, const double* x, int N, int D,
+                                            const LatentParams* params, int m, int form);
+cudaError_t launch_ilmm_predict(cudaStream_t st, TiledRect V, int Ns, int m, int p, const double* H, const LatentParams* params,
+                                const double* mlat, double sigma2, double* mean, double* var);
+cudaError_t launch_gather_rows(cudaStream_t st, double* dst, const double* src, const int* idx, size_t stride, int n);
+}  // namespace lmm

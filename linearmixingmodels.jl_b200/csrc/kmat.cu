@@ -1,0 +1,176 @@
+// Fused kernel-matrix builders (K4/K5 of SURVEY.md §2.3; reference call site src/oilmm.jl:90 ->
+// AbstractGPs mean_and_cov -> KernelFunctions kernelmatrix -> Distances pairwise + map(κ), then
+// `+ Diagonal(ΣT_i)`).  One pass: scaled inputs -> pairwise squared distance -> κ -> variance
+// scale -> (+ noise on the diagonal) written straight into the tiled factorisation workspace.
+// The two 128-point input tiles are staged into shared memory with one TMA bulk copy each
+// (cp.async.bulk + mbarrier).  HBM-write bound: 8 bytes per stored element, lower tiles only.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace lmm {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+// Stage the two point tiles (rows of xpad, D doubles per point) and scale them by inv_ls.
+// smem layout: xa[128*D] | xb[128*D] | sa[128] | sb[128]
+__device__ __forceinline__ void stage_points(double* xa, double* xb, double* sa, double* sb, const double* ga, const double* gb,
+                                             int D, double inv_ls, uint64_t* bar) {
+  const uint32_t bytes = (uint32_t)(TILE * D * sizeof(double));
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, 2 * bytes);
+    bulk_g2s(xa, ga, bytes, bar);
+    bulk_g2s(xb, gb, bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  for (int i = threadIdx.x; i < TILE * D; i += blockDim.x) {
+    xa[i] *= inv_ls;
+    xb[i] *= inv_ls;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * TILE; i += blockDim.x) {
+    const double* v = (i < TILE) ? xa + (size_t)i * D : xb + (size_t)(i - TILE) * D;
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) s = fma(v[k], v[k], s);
+    if (i < TILE) sa[i] = s; else sb[i - TILE] = s;
+  }
+  __syncthreads();
+}
+
+// grid: (lower tiles, batch).  Writes K_b + noise_b*I (identity on the padding) into L tiles.
+__global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const double* __restrict__ xpad, int N, int D,
+                                                       const LatentParams* __restrict__ params, int form) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* xa = reinterpret_cast<double*>(smem_raw);
+  double* xb = xa + TILE * D;
+  double* sa = xb + TILE * D;
+  double* sb = sa + TILE;
+  __shared__ __align__(8) uint64_t bar;
+
+  const int b = blockIdx.y;
+  // linear lower-tile index -> (I, J)
+  const int t = blockIdx.x;
+  int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)t) ++I;
+  while ((size_t)I * (I + 1) / 2 > (size_t)t) --I;
+  const int J = t - (int)((size_t)I * (I + 1) / 2);
+  const LatentParams lp = params[b];
+
+  stage_points(xa, xb, sa, sb, xpad + (size_t)I * TILE * D, xpad + (size_t)J * TILE * D, D, lp.inv_ls, &bar);
+
+  double* tile = out.tile(b, I, J);
+  const int r0 = I * TILE, c0 = J * TILE;
+  for (int e = 2 * threadIdx.x; e < TT; e += 2 * blockDim.x) {
+    int r, c;
+    tile_rc(e, r, c);  // (r, c) and (r, c+1)
+    double2 v;
+    double* vv = reinterpret_cast<double*>(&v);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int gr = r0 + r, gc = c0 + c + q;
+      double val;
+      if (gr >= N || gc >= N) {
+        val = (gr == gc) ? 1.0 : 0.0;
+      } else if (gr == gc) {
+        val = kappa_eval(lp.kind, lp.variance, 0.0) + lp.noise;
+      } else {
+        double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)(c + q) * D, D, sa[r], sb[c + q], form);
+        val = kappa_eval(lp.kind, lp.variance, d2);
+      }
+      vv[q] = val;
+    }
+    *reinterpret_cast<double2*>(tile + e) = v;
+  }
+}
+
+// grid: (ntr*ntc, batch).  Rows = points of xa_pad (e.g. x*), cols = points of xb_pad (train x).
+// Padding rows/cols are zero.
+__global__ void __launch_bounds__(256) kmat_cross_kernel(TiledRect out, const double* __restrict__ xa_pad, int Na,
+                                                         const double* __restrict__ xb_pad, int Nb, int D,
+                                                         const LatentParams* __restrict__ params, int form) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* xa = reinterpret_cast<double*>(smem_raw);
+  double* xb = xa + TILE * D;
+  double* sa = xb + TILE * D;
+  double* sb = sa + TILE;
+  __shared__ __align__(8) uint64_t bar;
+
+  const int b = blockIdx.y;
+  const int R = blockIdx.x / out.ntc, J = blockIdx.x % out.ntc;
+  const LatentParams lp = params[b];
+  stage_points(xa, xb, sa, sb, xa_pad + (size_t)R * TILE * D, xb_pad + (size_t)J * TILE * D, D, lp.inv_ls, &bar);
+
+  double* tile = out.tile(b, R, J);
+  const int r0 = R * TILE, c0 = J * TILE;
+  for (int e = 2 * threadIdx.x; e < TT; e += 2 * blockDim.x) {
+    int r, c;
+    tile_rc(e, r, c);
+    double2 v;
+    double* vv = reinterpret_cast<double*>(&v);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int gr = r0 + r, gc = c0 + c + q;
+      double val = 0.0;
+      if (gr < Na && gc < Nb) {
+        double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)(c + q) * D, D, sa[r], sb[c + q], form);
+        val = kappa_eval(lp.kind, lp.variance, d2);
+      }
+      vv[q] = val;
+    }
+    *reinterpret_cast<double2*>(tile + e) = v;
+  }
+}
+
+static size_t kmat_smem(int D) { return (size_t)(2 * TILE * D + 2 * TILE) * sizeof(double); }
+
+cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const double* xpad, int N, int D,
+                            const LatentParams* params, int form) {
+  size_t sm = kmat_smem(D);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kmat_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((unsigned)sym_tiles(out.nt), (unsigned)batch);
+  kmat_sym_kernel<<<grid, 256, sm, st>>>(out, xpad, N, D, params, form);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kmat_cross(cudaStream_t st, TiledRect out, int batch, const double* xa_pad, int Na, const double* xb_pad,
+                              int Nb, int D, const LatentParams* params, int form) {
+  size_t sm = kmat_smem(D);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kmat_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((unsigned)(out.ntr * out.ntc), (unsigned)batch);
+  kmat_cross_kernel<<<grid, 256, sm, st>>>(out, xa_pad, Na, xb_pad, Nb, D, params, form);
+  return cudaGetLastError();
+}
+
+}  // namespace lmm

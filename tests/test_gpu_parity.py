@@ -1,0 +1,305 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / host mirror) against the CPU
+oracle on identical seeded inputs.  Tolerance: 1e-9 relative on logpdf, posterior means and
+variances (BASELINE.json north_star), written next to each assertion."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from oracle import lmm_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def lmm():
+    import lmm_b200
+
+    lmm_b200.default_context()  # fails loudly without a GPU / without liblmm.so
+    return lmm_b200
+
+
+KMAP = {o.SE: "SEKernel", o.MATERN32: "Matern32Kernel", o.MATERN52: "Matern52Kernel"}
+
+
+def to_lmm_gp(lmm, g: o.GP):
+    k = getattr(lmm, KMAP[g.kernel.kind])()
+    k = g.kernel.variance * k if g.kernel.variance != 1.0 else k
+    if g.kernel.inv_lengthscale != 1.0:
+        k = k.compose(lmm.ScaleTransform(g.kernel.inv_lengthscale))
+    return lmm.GP(g.mean_const, k)
+
+
+def make_problem(N, p, m, Ns, seed=0, D=1, means=False, kinds=None):
+    rng = np.random.default_rng(seed)
+    if D == 1:
+        x = np.sort(rng.uniform(0, max(N / 100.0, 4.0), N))
+        xs = rng.uniform(0, max(N / 100.0, 4.0), Ns)
+    else:
+        x = rng.uniform(0, 3.0, (N, D))
+        xs = rng.uniform(0, 3.0, (Ns, D))
+    U, S = o.orthogonal_from_seed(p, m, seed=seed + 1)
+    kinds = kinds or [o.SE, o.MATERN32, o.MATERN52]
+    fs = [
+        o.GP(o.Kernel(kinds[i % len(kinds)], float(rng.uniform(0.5, 1.5)), float(rng.uniform(0.5, 2.0))),
+             float(rng.normal()) if means else 0.0)
+        for i in range(m)
+    ]
+    y = rng.standard_normal(p * N)
+    return x, xs, U, S, fs, y
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("N,batch", [(50, 2), (128, 1), (300, 3), (1000, 2)])
+def test_potrf_batched_matches_lapack(lmm, N, batch):
+    rng = np.random.default_rng(N)
+    A = rng.standard_normal((batch, N, N))
+    A = A @ np.transpose(A, (0, 2, 1)) / N + np.eye(N)[None] * 0.5
+    L, logdet, info = lmm.potrf_batched(A)
+    assert np.all(info == 0)
+    for b in range(batch):
+        Lr = sla.cholesky(A[b], lower=True)
+        np.testing.assert_allclose(L[b], Lr, rtol=1e-10, atol=1e-12)
+        assert rel(logdet[b], 2 * np.sum(np.log(np.diag(Lr)))) < 1e-11 or abs(logdet[b]) < 1e-9
+        assert np.all(np.triu(L[b], 1) == 0.0)
+
+
+def test_potrf_reports_non_pd(lmm):
+    A = np.eye(200)
+    A[150, 150] = -1.0
+    L, logdet, info = lmm.potrf_batched(np.stack([np.eye(200), A]))
+    assert info[0] == 0 and info[1] == 151
+
+
+@pytest.mark.parametrize(
+    "N,p,m,Ns,D,means",
+    [(50, 3, 2, 7, 1, False), (3, 3, 3, 2, 1, False), (700, 8, 4, 33, 1, True), (260, 5, 5, 130, 2, True), (1, 2, 1, 1, 1, False)],
+)
+def test_oilmm_logpdf_posterior_marginals(lmm, N, p, m, Ns, D, means):
+    """src/oilmm.jl:79-93, 116-134, 57-76 vs oracle (BASELINE config 1 is the first case)."""
+    x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=N, D=D, means=means)
+    s2 = 0.1
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    assert isinstance(f, lmm.OILMM)
+    xin = lmm.MOInputIsotopicByOutputs(x if D == 1 else lmm.RowVecs(x), p)
+    xsin = lmm.MOInputIsotopicByOutputs(xs if D == 1 else lmm.RowVecs(xs), p)
+    fx = f(xin, s2)
+    ref_terms, ref_reg = o.oilmm_logpdf_terms(om, x, s2, y)
+    lp = lmm.logpdf(fx, y)
+    assert rel(lp, float(np.sum(ref_terms) + ref_reg)) < RTOL
+    terms = lmm.logpdf_terms(fx, y)
+    np.testing.assert_allclose(terms[:m], ref_terms, rtol=RTOL)
+    assert rel(terms[m], ref_reg) < RTOL or abs(ref_reg) < 1e-9
+    post, lp2 = lmm.posterior(fx, y, with_logpdf=True)
+    assert lp2 == lp
+    M, V = lmm.mean_and_var(post(xsin, s2))
+    opost = o.oilmm_posterior(om, x, s2, y)
+    Mr, Vr = o.oilmm_mean_and_var(opost, xs, s2)
+    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(V, Vr, rtol=RTOL)
+    # PosteriorGP fields (α, C, δ)
+    g0 = post.f.fs[m - 1]
+    np.testing.assert_allclose(g0.alpha, opost.fs[m - 1].alpha, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(g0.delta, opost.fs[m - 1].delta, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(g0.C, opost.fs[m - 1].L, rtol=1e-8, atol=1e-10)
+    # prior marginals
+    Mp, Vp = lmm.mean_and_var(f(xsin, s2))
+    Mpr, Vpr = o.oilmm_mean_and_var(om, xs, s2)
+    np.testing.assert_allclose(Mp, Mpr, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(Vp, Vpr, rtol=RTOL)
+    marg = lmm.marginals(post(xsin, s2))
+    assert len(marg) == p * Ns and abs(marg[0].sigma ** 2 - V[0]) < 1e-12
+
+
+def test_oilmm_mid_size_multi_tile(lmm):
+    """Several tile columns and more than one outer block: N = 1300 (11 tiles)."""
+    N, p, m, Ns = 1300, 6, 3, 200
+    x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=5, means=True)
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+    assert rel(lmm.logpdf(fx, y), o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
+    post = lmm.posterior(fx, y)
+    M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
+    Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
+    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(V, Vr, rtol=RTOL)
+
+
+def test_distance_form_option(lmm):
+    x, xs, U, S, fs, y = make_problem(300, 4, 2, 5, seed=11)
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    fx = f(lmm.MOInputIsotopicByOutputs(x, 4), 0.1)
+    ctx = lmm.default_context()
+    ctx.set_option("distance_form", 1)
+    try:
+        assert rel(lmm.logpdf(fx, y), o.oilmm_logpdf(om, x, 0.1, y, form="direct")) < RTOL
+    finally:
+        ctx.set_option("distance_form", 0)
+
+
+def test_independent_mogp(lmm):
+    """src/independent_mogp.jl:74-80,119-126,222-229 with const means (test/independent_mogp.jl:33-34)."""
+    rng = np.random.default_rng(3)
+    N, Ns = 150, 11
+    x = np.sort(rng.uniform(0, 5, N))
+    xs = rng.uniform(0, 5, Ns)
+    fs = [o.GP(o.Kernel(o.MATERN32), 30.0), o.GP(o.Kernel(o.SE, 0.5), 10.0)]
+    y = np.concatenate([30 + rng.standard_normal(N), 10 + rng.standard_normal(N)])
+    f = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    fx = f(lmm.MOInputIsotopicByOutputs(x, 2), 0.1)
+    assert rel(lmm.logpdf(fx, y), o.imogp_logpdf(fs, x, 0.1, y)) < RTOL
+    # by features
+    yf = y[o.indices_outputs_to_features(N, 2)]
+    fxf = f(lmm.MOInputIsotopicByFeatures(x, 2), 0.1)
+    assert rel(lmm.logpdf(fxf, yf), o.imogp_logpdf(fs, x, 0.1, y)) < RTOL
+    post = lmm.posterior(fx, y)
+    M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, 2), 0.1))
+    posts = o.imogp_posterior(fs, x, 0.1, y)
+    Mr, Vr = o.imogp_mean_and_var(posts, xs, 0.1)
+    np.testing.assert_allclose(M, Mr, rtol=RTOL)
+    np.testing.assert_allclose(V, Vr, rtol=RTOL)
+    Mf, Vf = lmm.mean_and_var(post(lmm.MOInputIsotopicByFeatures(xs, 2), 0.1))
+    np.testing.assert_allclose(Mf, Mr[o.indices_outputs_to_features(Ns, 2)], rtol=RTOL)
+    # rand: deterministic given the normals
+    z = np.random.default_rng(9).standard_normal(2 * N)
+    s = lmm.rand(np.random.default_rng(9), fx)
+    np.testing.assert_allclose(s, o.imogp_rand(fs, x, 0.1, z), rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("form", [0, 1])
+def test_ilmm_logpdf_forms(lmm, form):
+    """src/ilmm.jl:150-163 (projected form) and the dense pN form (test/ilmm.jl:5)."""
+    rng = np.random.default_rng(4)
+    N, p, m = 200, 4, 3
+    x = np.sort(rng.uniform(0, 4, N))
+    H = rng.uniform(0, 1, (p, m))
+    fs = [o.GP(o.Kernel(o.SE, 1.0, 1.1), 0.3), o.GP(o.Kernel(o.MATERN32)), o.GP(o.Kernel(o.MATERN52, 0.7, 0.8), -0.2)]
+    y = rng.standard_normal(p * N)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), H)
+    assert not isinstance(f, lmm.OILMM)
+    fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+    lmm.set_ilmm_form(form)
+    try:
+        got = lmm.logpdf(fx, y)
+    finally:
+        lmm.set_ilmm_form(0)
+    ref = o.ilmm_logpdf(fs, H, x, 0.1, y) if form == 0 else o.dense_mogp_logpdf(fs, H, x, 0.1, y)
+    assert rel(got, ref) < RTOL
+
+
+def test_ilmm_posterior_marginals(lmm):
+    """src/ilmm.jl:184-198 + 122-129 on the joint posterior."""
+    rng = np.random.default_rng(6)
+    N, Ns, p, m = 150, 9, 3, 2
+    x = np.sort(rng.uniform(0, 4, N))
+    xs = rng.uniform(0, 4, Ns)
+    H = rng.uniform(0, 1, (p, m))
+    fs = [o.GP(o.Kernel(o.SE), 0.5), o.GP(o.Kernel(o.MATERN32, 0.8, 1.2))]
+    y = rng.standard_normal(p * N)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), H)
+    fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+    post, lp = lmm.posterior(fx, y, with_logpdf=True)
+    assert rel(lp, o.ilmm_logpdf(fs, H, x, 0.1, y)) < RTOL
+    M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
+    Mr, Vr = o.ilmm_mean_and_var(o.ilmm_posterior(fs, H, x, 0.1, y), H, xs, 0.1)
+    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(V, Vr, rtol=RTOL)
+    Mp, Vp = lmm.mean_and_var(f(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
+    Mpr, Vpr = o.ilmm_mean_and_var(fs, H, xs, 0.1)
+    np.testing.assert_allclose(Mp, Mpr, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(Vp, Vpr, rtol=RTOL)
+
+
+def test_rand_prior_and_posterior(lmm):
+    """src/oilmm.jl:40-54 and src/ilmm.jl:78-87: samples are a deterministic function of the normals."""
+    rng = np.random.default_rng(8)
+    N, p, m, Ns = 6, 3, 2, 4
+    x = np.linspace(0, 10, N)
+    xs = np.array([1.3, 4.1, 6.2, 9.4])
+    U, S = o.orthogonal_from_seed(p, m, seed=2)
+    fs = [o.GP(o.Kernel(o.MATERN32)), o.GP(o.Kernel(o.MATERN32, 1.0, 2.0), 0.4)]
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+    g = np.random.default_rng(21)
+    zl, zn = g.standard_normal(m * N), g.standard_normal(p * N)
+    s = lmm.rand(np.random.default_rng(21), fx)
+    assert s.shape == (p * N,)
+    np.testing.assert_allclose(s, o.oilmm_rand(om, x, 0.1, zl, zn), rtol=1e-7, atol=1e-8)
+    assert lmm.rand(np.random.default_rng(1), fx, 3).shape == (p * N, 3)
+    # general ILMM
+    Hm = om.H
+    fi = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), Hm)
+    si = lmm.rand(np.random.default_rng(21), fi(lmm.MOInputIsotopicByOutputs(x, p), 0.1))
+    np.testing.assert_allclose(si, o.ilmm_rand(fs, Hm, x, 0.1, zl, zn), rtol=1e-7, atol=1e-8)
+    # posterior sample and posterior logpdf at test points (test/oilmm.jl:84-86)
+    y = o.oilmm_rand(om, x, 0.1, zl, zn)
+    post = lmm.posterior(fx, y)
+    opost = o.oilmm_posterior(om, x, 0.1, y)
+    g = np.random.default_rng(22)
+    zl2, zn2 = g.standard_normal(m * Ns), g.standard_normal(p * Ns)
+    pfx = post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1)
+    sp = lmm.rand(np.random.default_rng(22), pfx)
+    np.testing.assert_allclose(sp, o.oilmm_rand(opost, xs, 0.1, zl2, zn2), rtol=1e-6, atol=1e-7)
+    ys = np.random.default_rng(23).standard_normal(p * Ns)
+    assert rel(lmm.logpdf(pfx, ys), o.oilmm_logpdf(opost, xs, 0.1, ys)) < RTOL
+
+
+def test_posterior_logpdf_larger(lmm):
+    N, p, m, Ns = 400, 4, 3, 150
+    x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=31, means=True)
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    post = lmm.posterior(f(lmm.MOInputIsotopicByOutputs(x, p), 0.1), y)
+    ys = np.random.default_rng(1).standard_normal(p * Ns)
+    got = lmm.logpdf(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.2), ys)
+    ref = o.oilmm_logpdf(o.oilmm_posterior(om, x, 0.1, y), xs, 0.2, ys)
+    assert rel(got, ref) < RTOL
+
+
+def test_logpdf_sweep(lmm):
+    """BASELINE config 5 shape at test scale: one call, several lengthscale settings."""
+    N, p, m = 300, 6, 3
+    x, _, U, S, fs, y = make_problem(N, p, m, 1, seed=41)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    scales = np.geomspace(0.5, 2.0, 4)
+    got = lmm.logpdf_sweep(f(lmm.MOInputIsotopicByOutputs(x, p), 0.1), y, scales)
+    for s, v in zip(scales, got):
+        fs_s = [o.GP(o.Kernel(g.kernel.kind, g.kernel.variance, g.kernel.inv_lengthscale * s), g.mean_const) for g in fs]
+        assert rel(v, o.oilmm_logpdf(o.OILMMModel(fs_s, U, S), x, 0.1, y)) < RTOL
+
+
+def test_errors(lmm):
+    x, xs, U, S, fs, y = make_problem(20, 3, 2, 2, seed=1)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    with pytest.raises(RuntimeError, match="out dim of x != out dim of f."):
+        lmm.logpdf(f(lmm.MOInputIsotopicByOutputs(x, 4), 0.1), np.zeros(80))
+    with pytest.raises(ValueError, match="not an orthogonal matrix"):
+        lmm.Orthogonal(np.random.default_rng(0).uniform(size=(3, 2)), S)
+    with pytest.raises(TypeError):
+        lmm.logpdf(f(lmm.MOInputIsotopicByFeatures(x, 3), 0.1), y)  # MethodError in Julia: src/ilmm.jl:45
+    # duplicate inputs and vanishing noise: singular latent covariance -> PosDefException
+    xd = np.array([0.0, 0.0, 1.0])
+    fi = lmm.independent_mogp([lmm.GP(lmm.SEKernel())])
+    with pytest.raises(lmm.PosDefException):
+        lmm.logpdf(fi(lmm.MOInputIsotopicByOutputs(xd, 1), 1e-300), np.zeros(3))
+
+
+def test_device_resident_inputs(lmm):
+    """x / y may already live in HBM (bench.py's `value` arm): same result as host inputs."""
+    import torch
+
+    x, xs, U, S, fs, y = make_problem(500, 4, 2, 3, seed=51)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    a = lmm.logpdf(f(lmm.MOInputIsotopicByOutputs(x, 4), 0.1), y)
+    xd = torch.from_numpy(x.reshape(-1, 1)).cuda()
+    yd = torch.from_numpy(y).cuda()
+    b = lmm.logpdf(f(lmm.MOInputIsotopicByOutputs(xd, 4), 0.1), yd)
+    assert a == b
