@@ -65,7 +65,8 @@ int lmm_ctx_destroy(lmm_ctx* ctx);
 const char* lmm_last_error(lmm_ctx* ctx);
 const char* lmm_version(void);
 /* Tunables: "distance_form" (0 = Distances.jl gemm form [default], 1 = direct differences),
- * "outer_block" (tile columns per outer Cholesky step, default 8), "gemm_impl" (0 = cp.async
+ * "outer_block" (tile columns per outer Cholesky step, default 8), "streams" (latent groups
+ * factored concurrently on separate CUDA streams, default 4, 1..8), "gemm_impl" (0 = cp.async
  * pipeline DMMA kernel). */
 int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value);
 /* Counters since context creation: kernels launched by this library, bytes copied H2D / D2H. */

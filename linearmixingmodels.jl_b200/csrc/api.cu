@@ -68,6 +68,12 @@ struct lmm_ctx {
   int64_t launches = 0, h2d = 0, d2h = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[8];
+  // latent groups run their (latency-bound) panel steps on separate streams so that one group's
+  // diagonal-tile factorisation overlaps the other groups' trailing updates
+  static constexpr int MAX_GROUPS = 8;
+  int ngroups = 4;
+  cudaStream_t gstream[MAX_GROUPS];
+  cudaEvent_t ev_fork, ev_join[MAX_GROUPS];
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -184,7 +190,8 @@ __global__ void axpy_kernel(double* y, const double* x, size_t n, double a) {
 // For every block column [s0, s1): one wide trailing update against all previous columns
 // (K = s0 tiles, output written once), then per tile column: narrow update inside the block,
 // diagonal-tile factor (+ inverse, logdet, info), panel TRSM as a GEMM with the inverse.
-cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
+cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double* W, size_t wstride, int batch, double* logdet,
+                               int* info) {
   const int nt = L.nt, ob = ctx->outer_block;
   GemmArgs g{};
   g.A = operand(L);
@@ -198,22 +205,22 @@ cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int
     const int s1 = (s0 + ob < nt) ? s0 + ob : nt;
     if (s0 > 0) {
       g.i0 = s0; g.j0 = s0; g.k0 = 0; g.k1 = s0;
-      if ((e = launch_gemm(ctx->stream, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
+      if ((e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
       ++ctx->launches;
       ctx->timings[6] += 1;
     }
     for (int jj = s0; jj < s1; ++jj) {
       if (jj > s0) {
         g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
-        if ((e = launch_gemm(ctx->stream, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
+        if ((e = launch_gemm(st, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
         ++ctx->launches;
         ctx->timings[6] += 1;
       }
-      if ((e = launch_potrf_tile(ctx->stream, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
+      if ((e = launch_potrf_tile(st, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
       ++ctx->launches;
       if (jj + 1 < nt) {
         g.i0 = jj + 1; g.j0 = jj;
-        if ((e = launch_gemm(ctx->stream, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
+        if ((e = launch_gemm(st, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
         ++ctx->launches;
       }
     }
@@ -221,9 +228,27 @@ cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int
   return cudaSuccess;
 }
 
+// Fork the batch into latent groups on separate streams (joined back into ctx->stream).
+cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
+  const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
+  if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info);
+  cudaError_t e;
+  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
+  for (int gi = 0; gi < G; ++gi) {
+    const int b0 = (int)((int64_t)batch * gi / G), b1 = (int)((int64_t)batch * (gi + 1) / G);
+    cudaStream_t st = ctx->gstream[gi];
+    if ((e = cudaStreamWaitEvent(st, ctx->ev_fork, 0)) != cudaSuccess) return e;
+    TiledSym Lg{L.base + (size_t)b0 * L.batch_stride, L.nt, L.batch_stride};
+    if ((e = chol_factor_stream(ctx, st, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0, logdet + b0, info + b0)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ctx->ev_join[gi], st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[gi], 0)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 // X <- X L^{-T} for a rectangular tiled X (rows = e.g. test points): the same update/TRSM sweep
 // with X's tile rows appended under the factor.
-cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch) {
+cudaError_t trsm_right_lt_stream(lmm_ctx* ctx, cudaStream_t st, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch) {
   const int nt = L.nt, ob = ctx->outer_block;
   GemmArgs g{};
   g.A = operand(X);
@@ -238,19 +263,37 @@ cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W
     const int s1 = (s0 + ob < nt) ? s0 + ob : nt;
     if (s0 > 0) {
       g.j0 = s0; g.k0 = 0; g.k1 = s0;
-      if ((e = launch_gemm(ctx->stream, GEMM_UPDATE, g, s1 - s0, X.ntr, batch)) != cudaSuccess) return e;
+      if ((e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, X.ntr, batch)) != cudaSuccess) return e;
       ++ctx->launches;
     }
     for (int jj = s0; jj < s1; ++jj) {
       if (jj > s0) {
         g.j0 = jj; g.k0 = s0; g.k1 = jj;
-        if ((e = launch_gemm(ctx->stream, GEMM_UPDATE, g, 1, X.ntr, batch)) != cudaSuccess) return e;
+        if ((e = launch_gemm(st, GEMM_UPDATE, g, 1, X.ntr, batch)) != cudaSuccess) return e;
         ++ctx->launches;
       }
       g.j0 = jj;
-      if ((e = launch_gemm(ctx->stream, GEMM_TRSM, g, 1, X.ntr, batch)) != cudaSuccess) return e;
+      if ((e = launch_gemm(st, GEMM_TRSM, g, 1, X.ntr, batch)) != cudaSuccess) return e;
       ++ctx->launches;
     }
+  }
+  return cudaSuccess;
+}
+
+cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch) {
+  const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
+  if (G <= 1) return trsm_right_lt_stream(ctx, ctx->stream, X, L, W, wstride, batch);
+  cudaError_t e;
+  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
+  for (int gi = 0; gi < G; ++gi) {
+    const int b0 = (int)((int64_t)batch * gi / G), b1 = (int)((int64_t)batch * (gi + 1) / G);
+    cudaStream_t st = ctx->gstream[gi];
+    if ((e = cudaStreamWaitEvent(st, ctx->ev_fork, 0)) != cudaSuccess) return e;
+    TiledRect Xg{X.base + (size_t)b0 * X.batch_stride, X.ntr, X.ntc, X.batch_stride};
+    TiledSym Lg{L.base + (size_t)b0 * L.batch_stride, L.nt, L.batch_stride};
+    if ((e = trsm_right_lt_stream(ctx, st, Xg, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ctx->ev_join[gi], st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[gi], 0)) != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
@@ -326,6 +369,9 @@ extern "C" int lmm_ctx_create(int device, lmm_ctx** out) {
     return LMM_E_CUDA;
   }
   for (auto& e : ctx->ev) cudaEventCreate(&e);
+  for (auto& g : ctx->gstream) cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  for (auto& e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
@@ -341,6 +387,9 @@ extern "C" int lmm_ctx_destroy(lmm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
   for (auto& e : ctx->ev) cudaEventDestroy(e);
+  for (auto& g : ctx->gstream) cudaStreamDestroy(g);
+  cudaEventDestroy(ctx->ev_fork);
+  for (auto& e : ctx->ev_join) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return LMM_OK;
@@ -358,6 +407,9 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "outer_block") {
     if (value < 1 || value > 64) return ctx->fail(LMM_E_ARG, "outer_block must be in [1, 64]");
     ctx->outer_block = (int)value;
+  } else if (k == "streams") {
+    if (value < 1 || value > lmm_ctx::MAX_GROUPS) return ctx->fail(LMM_E_ARG, "streams must be in [1, 8]");
+    ctx->ngroups = (int)value;
   } else if (k == "gemm_impl") {
     if (value != 0.0) return ctx->fail(LMM_E_UNSUPPORTED, "only gemm_impl 0 exists");
   } else {

@@ -1,30 +1,58 @@
 // Diagonal-tile factorisation: the panel step (dpotf2) of the blocked Cholesky (K6), fused with
 // logdet accumulation (K7), non-PD detection and the triangular inverse W = inv(L_JJ) that turns
 // every panel TRSM and every triangular vector solve into tensor-core GEMMs / plain GEMVs.
-// One CTA per latent; the 128x128 tile lives in shared memory (column-major, ld = 129).
-// Latency-bound by design (it sits on the critical path of each tile column; batching over
-// latents keeps the SMs busy meanwhile).
+// One CTA (8 warps) per latent; the 128x128 tile lives in shared memory, column-major with
+// ld = 132 (conflict-free DMMA fragment loads: column stride = 8 banks).
+//   phase C: 16 steps of 8 columns: 8x8 diagonal block factored in registers (rsqrt pivots,
+//            redundantly by every row-owner thread -> no intra-block syncs), panel rows solved
+//            in registers, trailing update of the tile on the FP64 tensor pipe (m8n8k4 DMMA).
+//   phase W: in-place recursive inverse of the lower triangle: 8x8 diagonal blocks by
+//            substitution, then 4 doubling levels  W21 = -W22 (L21 W11)  as DMMA block products;
+//            the temporary L21*W11 lives in the (free) mirrored upper block.
+// Latency-bound by design (it sits on the critical path of each tile column; the host runs
+// several latent groups on separate streams so the other SMs keep doing trailing updates).
 #include "common.cuh"
 #include "kernels.h"
 
 namespace lmm {
 
-constexpr int LD = TILE + 1;
+constexpr int LD = 132;
 constexpr size_t POTRF_SMEM = (size_t)(TILE * LD + 2 * TILE + 32) * sizeof(double);
+
+__device__ __forceinline__ void dmma884p(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// C(8x8 at R0,N0) (+)= sign * sum over 8-wide k-blocks  A(R0, K0+8kk) * B(K0+8kk, N0)
+// A block element (r,k) at S[(K0+k)*LD + R0+r]; B block element (k,n) at S[(N0+n)*LD + K0+k].
+__device__ __forceinline__ void block_mma(const double* S, int R0, int KA0, int KB0, int N0, int nk, double neg, double& c0, double& c1,
+                                          int g, int t) {
+  for (int kk = 0; kk < nk; ++kk) {
+    const int ka = KA0 + 8 * kk, kb = KB0 + 8 * kk;
+    const double a0 = neg * S[(ka + t) * LD + R0 + g];
+    const double a1 = neg * S[(ka + 4 + t) * LD + R0 + g];
+    const double b0 = S[(N0 + g) * LD + kb + t];
+    const double b1 = S[(N0 + g) * LD + kb + 4 + t];
+    dmma884p(c0, c1, a0, b0);
+    dmma884p(c0, c1, a1, b1);
+  }
+}
 
 __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* __restrict__ Wbase, size_t w_batch_stride, int J,
                                                             double* __restrict__ logdet, int* __restrict__ info) {
   extern __shared__ __align__(16) double S[];  // S[c*LD + r]
   double* dinv = S + TILE * LD;               // 1 / L[r][r]
-  double* red = dinv + TILE;                  // reduction scratch (TILE doubles)
+  double* red = dinv + TILE;                  // reduction scratch
   __shared__ int fail_col;
 
   const int b = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   double* tile = L.tile(b, J, J);
   double* Wt = Wbase + (size_t)b * w_batch_stride + (size_t)J * TT;
 
   if (tid == 0) fail_col = 0x7fffffff;
+#pragma unroll 8
   for (int e = tid; e < TT; e += 256) {
     int r, c;
     tile_rc(e, r, c);
@@ -32,7 +60,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
   }
   __syncthreads();
 
-  // ---- blocked right-looking Cholesky, 8 columns per step
+  // ---- phase C
   for (int j0 = 0; j0 < TILE; j0 += 8) {
     const int r = tid;  // row owner (threads 0..127)
     double p[8];
@@ -49,26 +77,22 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     __syncthreads();
     if (active) {
       double dv[8];
-      // factor the 8x8 diagonal block in registers (redundantly per thread)
+      // right-looking 8x8 factor in registers (short critical path: rsqrt + 2 FMAs per column)
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        double piv = d[jj][jj];
-#pragma unroll
-        for (int k = 0; k < jj; ++k) piv = fma(-d[jj][k], d[jj][k], piv);
+        const double piv = d[jj][jj];
         if (!(piv > 0.0)) {
           if (r == j0) atomicMin(&fail_col, j0 + jj);
         }
-        const double l = sqrt(piv);
-        d[jj][jj] = l;
-        const double inv = 1.0 / l;
+        const double inv = rsqrt(piv);
         dv[jj] = inv;
+        d[jj][jj] = piv * inv;
 #pragma unroll
-        for (int i = jj + 1; i < 8; ++i) {
-          double v = d[i][jj];
+        for (int i = jj + 1; i < 8; ++i) d[i][jj] *= inv;
 #pragma unroll
-          for (int k = 0; k < jj; ++k) v = fma(-d[i][k], d[jj][k], v);
-          d[i][jj] = v * inv;
-        }
+        for (int j2 = jj + 1; j2 < 8; ++j2)
+#pragma unroll
+          for (int i = j2; i < 8; ++i) d[i][j2] = fma(-d[i][jj], d[j2][jj], d[i][j2]);
       }
       if (r >= j0 + 8) {
 #pragma unroll
@@ -88,98 +112,117 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
             if (ii == i && jj <= ii) v = d[ii][jj];
           p[jj] = v;
         }
-        dinv[r] = 0.0;
+        double di = 0.0;
 #pragma unroll
         for (int ii = 0; ii < 8; ++ii)
-          if (ii == i) dinv[r] = dv[ii];
+          if (ii == i) di = dv[ii];
+        dinv[r] = di;
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) S[(j0 + k) * LD + r] = p[k];
     }
     __syncthreads();
-    // trailing update of rows/cols [j0+8, 128): 4x4 strided register blocks, lower part only
-    const int n = TILE - j0 - 8;
-    if (n > 0) {
-      const int nq = n >> 2;  // n is a multiple of 8
-      const int base = j0 + 8;
-      for (int task = tid; task < nq * nq; task += 256) {
-        const int tr = task % nq, tc = task / nq;
-        double pr[4][8], pc[4][8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            pr[i][k] = S[(j0 + k) * LD + base + tr + i * nq];
-            pc[i][k] = S[(j0 + k) * LD + base + tc + i * nq];
-          }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int jx = 0; jx <= i; ++jx) {
-            if (i == jx && tr < tc) continue;
-            const int rr = base + tr + i * nq, cc = base + tc + jx * nq;
-            double v = S[cc * LD + rr];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v = fma(-pr[i][k], pc[jx][k], v);
-            S[cc * LD + rr] = v;
-          }
-      }
+    // trailing update of the lower 8x8 blocks of rows/cols [j0+8, 128) on the tensor pipe
+    const int nb = (TILE - j0 - 8) >> 3;
+    const int nblocks = nb * (nb + 1) / 2;
+    for (int idx = warp; idx < nblocks; idx += 8) {
+      int bi = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+      while ((bi + 1) * (bi + 2) / 2 <= idx) ++bi;
+      while (bi * (bi + 1) / 2 > idx) --bi;
+      const int bj = idx - bi * (bi + 1) / 2;
+      const int R0 = j0 + 8 + 8 * bi, C0 = j0 + 8 + 8 * bj;
+      double c0 = S[(C0 + 2 * t) * LD + R0 + g], c1 = S[(C0 + 2 * t + 1) * LD + R0 + g];
+      const double a0 = -S[(j0 + t) * LD + R0 + g], a1 = -S[(j0 + 4 + t) * LD + R0 + g];
+      const double b0 = S[(j0 + t) * LD + C0 + g], b1 = S[(j0 + 4 + t) * LD + C0 + g];
+      dmma884p(c0, c1, a0, b0);
+      dmma884p(c0, c1, a1, b1);
+      S[(C0 + 2 * t) * LD + R0 + g] = c0;
+      S[(C0 + 2 * t + 1) * LD + R0 + g] = c1;
     }
     __syncthreads();
   }
 
-  // ---- logdet and failure report
-  if (tid < TILE) red[tid] = log(S[tid * LD + tid]);
+  // ---- logdet and failure report (fixed reduction order)
+  if (tid < TILE) {
+    double v = log(S[tid * LD + tid]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+  }
   __syncthreads();
   if (tid == 0) {
-    double s = 0.0;
-    for (int i = 0; i < TILE; ++i) s += red[i];
-    logdet[b] += 2.0 * s;
+    logdet[b] += 2.0 * (((red[0] + red[1]) + red[2]) + red[3]);
     if (fail_col != 0x7fffffff && info[b] == 0) info[b] = J * TILE + fail_col + 1;
   }
 
   // ---- write L (lower, zero upper)
+#pragma unroll 8
   for (int e = tid; e < TT; e += 256) {
     int r, c;
     tile_rc(e, r, c);
     tile[e] = (r >= c) ? S[c * LD + r] : 0.0;
   }
-  __syncthreads();
 
-  // ---- W = inv(L): thread c owns column c; W[r][c] (r > c) is kept at S[r*LD + c] (the unused
-  // upper triangle, transposed); diagonal in dinv.  Rows are processed 4 at a time: the sums over
-  // k below the row block are 4 independent FMA chains, then a 4x4 triangular finish.
-  if (tid < TILE) {
-    const int c = tid;
-    const int c0 = c & ~31;  // warp-uniform start so that reads of L broadcast
-    for (int rb = (c0 & ~3); rb < TILE; rb += 4) {
-      double s[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int k = c0; k < rb; ++k) {
-        const double w = (k > c) ? S[k * LD + c] : ((k == c) ? dinv[c] : 0.0);
+  // ---- phase W level 0: invert the 16 diagonal 8x8 blocks in place (thread = one column)
+  {
+    double Lb[8][8];
+    const int blk = tid >> 3, col = tid & 7, o = blk * 8;
+    if (tid < TILE) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] = fma(S[k * LD + rb + i], w, s[i]);
-      }
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = rb + i;
-        // contributions from rows inside the block (k in [rb, rr))
-        double w_rr;
-#pragma unroll
-        for (int kk = 0; kk < i; ++kk) {
-          const int k = rb + kk;
-          const double w = (k > c) ? S[k * LD + c] : ((k == c) ? dinv[c] : 0.0);
-          s[i] = fma(S[k * LD + rr], w, s[i]);
-        }
-        w_rr = -s[i] * dinv[rr];
-        if (rr > c) S[rr * LD + c] = w_rr;
-      }
+        for (int k = 0; k < i; ++k) Lb[i][k] = S[(o + k) * LD + o + i];
     }
+    __syncthreads();
+    if (tid < TILE) {
+      double w[8];
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) {
+        double s = (rr == col) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < rr; ++k) s = fma(-Lb[rr][k], w[k], s);
+        w[rr] = s * dinv[o + rr];
+      }
+#pragma unroll
+      for (int rr = 0; rr < 8; ++rr) S[(o + col) * LD + o + rr] = w[rr];
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  // ---- phase W doubling levels: W21 = -W22 * (L21 * W11)
+  for (int s = 8; s < TILE; s <<= 1) {
+    const int sb = s >> 3;               // 8-blocks per side
+    const int npairs = TILE / (2 * s);
+    const int nout = npairs * sb * sb;   // output 8x8 blocks per phase
+    // T(i,j) = sum_{k=j}^{sb-1} L21(i,k) W11(k,j)   -> stored in the mirrored upper block (1,2)
+    for (int ob = warp; ob < nout; ob += 8) {
+      const int q = ob / (sb * sb), ij = ob % (sb * sb), i = ij % sb, j = ij / sb;
+      const int base = q * 2 * s;
+      double c0 = 0.0, c1 = 0.0;
+      // A = L21 block (rows base+s+8i, cols base+8k), B = W11 block (rows base+8k, cols base+8j)
+      block_mma(S, base + s + 8 * i, base + 8 * j, base + 8 * j, base + 8 * j, sb - j, 1.0, c0, c1, g, t);
+      const int TR = base + 8 * i, TC = base + s + 8 * j;
+      S[(TC + 2 * t) * LD + TR + g] = c0;
+      S[(TC + 2 * t + 1) * LD + TR + g] = c1;
+    }
+    __syncthreads();
+    // W21(i,j) = -sum_{k=0}^{i} W22(i,k) T(k,j)
+    for (int ob = warp; ob < nout; ob += 8) {
+      const int q = ob / (sb * sb), ij = ob % (sb * sb), i = ij % sb, j = ij / sb;
+      const int base = q * 2 * s;
+      double c0 = 0.0, c1 = 0.0;
+      // A = W22 block (rows base+s+8i, cols base+s+8k), B = T block (rows base+8k, cols base+s+8j)
+      block_mma(S, base + s + 8 * i, base + s, base, base + s + 8 * j, i + 1, -1.0, c0, c1, g, t);
+      const int WR = base + s + 8 * i, WC = base + 8 * j;
+      S[(WC + 2 * t) * LD + WR + g] = c0;
+      S[(WC + 2 * t + 1) * LD + WR + g] = c1;
+    }
+    __syncthreads();
+  }
+#pragma unroll 8
   for (int e = tid; e < TT; e += 256) {
     int r, c;
     tile_rc(e, r, c);
-    Wt[e] = (r > c) ? S[r * LD + c] : ((r == c) ? dinv[r] : 0.0);
+    Wt[e] = (r >= c) ? S[c * LD + r] : 0.0;
   }
 }
 
