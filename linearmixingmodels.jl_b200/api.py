@@ -620,9 +620,10 @@ def posterior(fx: FiniteGP, y, with_logpdf: bool = False):
 def mean_and_var(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
     """`mean_and_var(fx)`: src/oilmm.jl:57-76, src/ilmm.jl:122-129, src/independent_mogp.jl:50-57."""
     f = fx.f
-    ctx = _ctx_of(fx)
-    lib = ctx.lib
     owner = _post_owner(fx)
+    needs_device = owner is not None or isinstance(f, ILMM)
+    ctx = _ctx_of(fx) if needs_device else None
+    lib = ctx.lib if ctx else None
     x = fx.x
     reorder = None
     if isinstance(f, IndependentMOGP) and isinstance(x, MOInputIsotopicByFeatures):

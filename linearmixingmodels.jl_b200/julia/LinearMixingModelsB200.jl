@@ -1,0 +1,197 @@
+# LinearMixingModelsB200.jl -- the reference-side binding of liblmm.so (include/lmm.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  This is the shim a
+# maintainer loads next to LinearMixingModels.jl: it keeps the reference's exported types
+# (ILMM, OILMM, Orthogonal, IndependentMOGP; src/LinearMixingModels.jl:21-24) and overrides the
+# method *bodies* of the hot path with `ccall`s.  The Python host mirror
+# (linearmixingmodels.jl_b200/api.py) exercises exactly the same exports with the same buffer
+# layouts (column-major, by-outputs vectors), so every ccall below has a tested ctypes twin.
+module LinearMixingModelsB200
+
+using LinearAlgebra, Random
+using AbstractGPs, KernelFunctions, FillArrays
+using LinearMixingModels
+using LinearMixingModels: ILMM, OILMM, Orthogonal, IndependentMOGP, unpack, noise_var
+
+const liblmm = get(ENV, "LIBLMM", joinpath(@__DIR__, "..", "liblmm.so"))
+
+struct GpDesc            # lmm_gp_desc
+    kind::Int32
+    reserved::Int32
+    variance::Float64
+    inv_lengthscale::Float64
+    mean_const::Float64
+end
+
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+function ctx()
+    if CTX[] == C_NULL
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:lmm_ctx_create, liblmm), Cint, (Cint, Ptr{Ptr{Cvoid}}), 0, h)
+        rc == 0 || error("lmm_ctx_create failed ($rc): a CUDA device is required (no CPU fallback)")
+        CTX[] = h[]
+    end
+    return CTX[]
+end
+lasterr() = unsafe_string(ccall((:lmm_last_error, liblmm), Cstring, (Ptr{Cvoid},), ctx()))
+
+function check(rc::Integer)
+    rc == 0 && return nothing
+    rc > 0 && throw(PosDefException(rc))                                   # LAPACK info
+    rc == -2 && error("out dim of x != out dim of f.")                     # src/ilmm.jl:52
+    rc == -6 && throw(ArgumentError("`U` is not an orthogonal matrix"))    # src/orthogonal_matrix.jl:22
+    rc == -7 && throw(OutOfMemoryError())
+    (rc == -1 || rc == -3) && throw(ArgumentError(lasterr()))
+    error("liblmm error $rc: $(lasterr())")
+end
+
+# --- kernel / GP description ------------------------------------------------------------------
+kind(::SqExponentialKernel) = Int32(0)
+kind(::Matern32Kernel) = Int32(1)
+kind(::Matern52Kernel) = Int32(2)
+describe(k::KernelFunctions.SimpleKernel) = (kind(k), 1.0, 1.0)
+describe(k::ScaledKernel) = (d = describe(k.kernel); (d[1], d[2] * only(k.σ²), d[3]))
+function describe(k::TransformedKernel{<:Kernel,<:ScaleTransform})
+    d = describe(k.kernel)
+    return (d[1], d[2], d[3] * only(k.transform.s))
+end
+describe(k) = throw(ArgumentError("kernel $(typeof(k)) is not supported by liblmm (no CPU fallback)"))
+meanconst(::AbstractGPs.ZeroMean) = 0.0
+meanconst(m::AbstractGPs.ConstMean) = Float64(m.c)
+function GpDesc(f::GP)
+    k, v, s = describe(f.kernel)
+    return GpDesc(k, 0, v, s, meanconst(f.mean))
+end
+
+points(x::AbstractVector{<:Real}) = (collect(Float64, x), 1)
+points(x::ColVecs) = (Matrix{Float64}(x.X), size(x.X, 1))              # D x N column-major
+points(x::RowVecs) = (Matrix{Float64}(permutedims(x.X)), size(x.X, 2))
+
+# --- device-resident posterior -----------------------------------------------------------------
+mutable struct DevicePosterior
+    handle::Ptr{Cvoid}
+    function DevicePosterior(h)
+        p = new(h)
+        finalizer(q -> ccall((:lmm_post_free, liblmm), Cint, (Ptr{Cvoid},), q.handle), p)
+        return p
+    end
+end
+# A latent of the posterior OILMM: behaves as an AbstractGP whose (α, C, x, δ) live on the GPU.
+struct DeviceLatentPosterior{Tf<:GP} <: AbstractGPs.AbstractGP
+    owner::DevicePosterior
+    index::Int
+    prior::Tf
+end
+
+# --- logpdf(fx::FiniteGP{<:OILMM}, y)   replaces src/oilmm.jl:79-93 ------------------------------
+function AbstractGPs.logpdf(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    U = Matrix{Float64}(H.U); S = Vector{Float64}(diag(H.S)); yv = Vector{Float64}(y)
+    out = Ref{Float64}(0.0); il = Ref{Cint}(-1)
+    rc = ccall((:lmm_oilmm_logpdf, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64,
+         Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(x), D, U, S, size(U, 1), Float64(σ²), yv, fx.x.out_dim, out, C_NULL, il)
+    check(rc)
+    return out[]
+end
+
+# --- posterior(fx::FiniteGP{<:OILMM}, y)   replaces src/oilmm.jl:116-134 -------------------------
+function AbstractGPs.posterior(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    U = Matrix{Float64}(H.U); S = Vector{Float64}(diag(H.S)); yv = Vector{Float64}(y)
+    h = Ref{Ptr{Cvoid}}(C_NULL); il = Ref{Cint}(-1)
+    rc = ccall((:lmm_oilmm_posterior, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64,
+         Ptr{Float64}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(x), D, U, S, size(U, 1), Float64(σ²), yv, fx.x.out_dim, h, C_NULL, C_NULL, il)
+    check(rc)
+    owner = DevicePosterior(h[])
+    latents = [DeviceLatentPosterior(owner, i - 1, f) for (i, f) in enumerate(fs.fs)]
+    return ILMM(IndependentMOGP(latents), H)          # an OILMM whose latents are (device) posteriors
+end
+
+const PosteriorOILMM = ILMM{<:IndependentMOGP{<:Vector{<:DeviceLatentPosterior}},<:Orthogonal}
+
+# --- mean_and_var(post(x*, σ²))   replaces src/oilmm.jl:57-76 on posterior latents ---------------
+function AbstractGPs.mean_and_var(fx::FiniteGP{<:PosteriorOILMM})
+    fs, H, σ², x = unpack(fx)
+    X, _ = points(x)
+    n = length(x) * fx.x.out_dim
+    M = Vector{Float64}(undef, n); V = Vector{Float64}(undef, n)
+    rc = ccall((:lmm_post_mean_and_var, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Ptr{Float64}),
+        fs.fs[1].owner.handle, X, length(x), Float64(σ²), M, V)
+    check(rc)
+    return M, V
+end
+
+# --- logpdf(post(x*, σ²), y*)   (test/oilmm.jl:84) ----------------------------------------------
+function AbstractGPs.logpdf(fx::FiniteGP{<:PosteriorOILMM}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, _ = points(x)
+    out = Ref{Float64}(0.0); il = Ref{Cint}(-1)
+    rc = ccall((:lmm_post_logpdf, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        fs.fs[1].owner.handle, X, length(x), Float64(σ²), Vector{Float64}(y), out, il)
+    check(rc)
+    return out[]
+end
+
+# --- rand(rng, fx)   replaces src/oilmm.jl:40-54: normals drawn in the reference's order ----------
+function AbstractGPs.rand(rng::AbstractRNG, fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    m, p, N = length(descs), size(H, 1), length(x)
+    zl = randn(rng, N * m)          # latent 1..m, N draws each  (src/oilmm.jl:47)
+    zn = randn(rng, N * p)          # then the observation noise (src/oilmm.jl:53)
+    out = Vector{Float64}(undef, N * p); il = Ref{Cint}(-1)
+    rc = ccall((:lmm_oilmm_rand, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, m, X, N, D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), p, Float64(σ²), fx.x.out_dim, zl, zn, out, il)
+    check(rc)
+    return out
+end
+
+# --- general ILMM: logpdf replaces src/ilmm.jl:150-163 ------------------------------------------
+function AbstractGPs.logpdf(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    out = Ref{Float64}(0.0); info = Ref{Cint}(0)
+    rc = ccall((:lmm_ilmm_logpdf, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint, Cint,
+         Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(x), D, H, size(H, 1), Float64(σ²), Vector{Float64}(y), fx.x.out_dim, 0, out, info)
+    check(rc)
+    return out[]
+end
+
+# --- IndependentMOGP: logpdf replaces src/independent_mogp.jl:74-80 -----------------------------
+function AbstractGPs.logpdf(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOInputIsotopicByOutputs,<:Diagonal{<:Real,<:Fill}},
+                            y::AbstractVector{<:Real})
+    X, D = points(ft.x.x)
+    descs = GpDesc.(ft.f.fs)
+    out = Ref{Float64}(0.0); il = Ref{Cint}(-1)
+    rc = ccall((:lmm_imogp_logpdf, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Float64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(ft.x.x), D, Float64(ft.Σy[1]), Vector{Float64}(y), ft.x.out_dim, out, C_NULL, il)
+    check(rc)
+    return out[]
+end
+
+# PosteriorGP field access (α, C, δ) for one latent -- `lmm_post_export`
+function export_latent(f::DeviceLatentPosterior, N::Int)
+    L = Matrix{Float64}(undef, N, N); α = Vector{Float64}(undef, N); δ = Vector{Float64}(undef, N)
+    check(ccall((:lmm_post_export, liblmm), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                f.owner.handle, f.index, L, α, δ))
+    return (α = α, C = Cholesky(LowerTriangular(L)), δ = δ)
+end
+
+end # module

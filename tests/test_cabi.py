@@ -1,0 +1,111 @@
+"""CPU checks of the drop-in boundary: liblmm.so loads, exports every symbol include/lmm.h
+declares (and nothing is bound that the header does not declare), host-only entry points behave,
+and compute entry points fail loudly without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import lmm_b200 as lmm
+from lmm_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "lmm.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lmm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"liblmm.so does not export {n}"
+    assert sorted(_lib.SIGNATURES) == names  # the ctypes table covers the header exactly
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (lmm_[a-z0-9_]+)", out)))
+    assert exported == names
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(_lib.GpDesc) == 32
+    assert _lib.GpDesc.variance.offset == 8 and _lib.GpDesc.mean_const.offset == 24
+
+
+def test_version_and_host_only_entry_points():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.lmm_version()
+    U, _, _ = np.linalg.svd(np.random.default_rng(0).uniform(size=(5, 3)), full_matrices=False)
+    Uf = np.asfortranarray(U)
+    assert lib.lmm_orthogonal_validate(_lib.ptr(Uf), 5, 3) == 0
+    bad = np.asfortranarray(np.random.default_rng(1).uniform(size=(5, 3)))
+    assert lib.lmm_orthogonal_validate(_lib.ptr(bad), 5, 3) == _lib.LMM_E_NOT_ORTHOGONAL
+    # known answers of test/independent_mogp.jl:86-98 (1-based there)
+    out = np.zeros(6, dtype=np.int64)
+    assert lib.lmm_reorder_indices(3, 2, 0, out.ctypes.data_as(C.c_void_p)) == 0
+    np.testing.assert_array_equal(out + 1, [1, 4, 2, 5, 3, 6])
+    assert lib.lmm_reorder_indices(3, 2, 1, out.ctypes.data_as(C.c_void_p)) == 0
+    np.testing.assert_array_equal(out + 1, [1, 3, 5, 2, 4, 6])
+
+
+def test_host_mirror_types_and_errors():
+    """test/orthogonal_matrix.jl:1-15, test/ilmm.jl:55-72 (known answers on the host side)."""
+    rng = np.random.default_rng(2)
+    with pytest.raises(ValueError, match="not an orthogonal matrix"):
+        lmm.Orthogonal(rng.uniform(size=(3, 2)), np.ones(2))
+    U, S, _ = np.linalg.svd(rng.uniform(size=(3, 2)), full_matrices=False)
+    H = lmm.Orthogonal(U, S)
+    assert H.shape == (3, 2)
+    np.testing.assert_allclose(np.asarray(H), U @ np.diag(np.sqrt(S)))
+    fs = lmm.independent_mogp([lmm.GP(lmm.SEKernel()), lmm.GP(2.0, 0.5 * lmm.Matern32Kernel())])
+    f = lmm.ILMM(fs, H)
+    assert isinstance(f, lmm.OILMM) and lmm.get_latent_gp(f) is fs
+    assert not isinstance(lmm.ILMM(fs, np.asarray(H)), lmm.OILMM)
+    assert fs.fs[1].kernel.variance == 0.5 and fs.fs[1].mean_const == 2.0
+    assert lmm.with_lengthscale(lmm.SEKernel(), 4.0).inv_lengthscale == 0.25
+    x = lmm.MOInputIsotopicByOutputs(np.arange(4.0), 3)
+    fx = f(x, 2.0)
+    assert len(fx) == 12 and lmm.noise_var(fx) == 2.0  # noise_var(Diagonal(Fill(2, n))) == 2
+    assert lmm.reshape_y(np.arange(16.0), 8).shape == (2, 8) and lmm.reshape_y(np.arange(16.0), 2).shape == (8, 2)
+    lat, HH, s2, xx = lmm.unpack(fx)
+    assert lat is fs and HH is H and s2 == 2.0 and xx is x.x
+    with pytest.raises(RuntimeError, match="out dim of x != out dim of f."):
+        lmm.unpack(f(lmm.MOInputIsotopicByOutputs(np.arange(4.0), 2), 0.1))
+    with pytest.raises(TypeError):
+        lmm.unpack(f(lmm.MOInputIsotopicByFeatures(np.arange(4.0), 3), 0.1))
+    np.testing.assert_array_equal(lmm.indices_which_reorder_outputs_to_features(lmm.MOInputIsotopicByOutputs(np.arange(3.0), 2)) + 1,
+                                  [1, 4, 2, 5, 3, 6])
+    # prior marginals of an IndependentMOGP need no device
+    M, V = lmm.mean_and_var(fs(lmm.MOInputIsotopicByOutputs(np.arange(3.0), 2), 0.1))
+    np.testing.assert_allclose(M, [0, 0, 0, 2, 2, 2])
+    np.testing.assert_allclose(V, [1.1, 1.1, 1.1, 0.6, 0.6, 0.6])
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the loud-failure path is for CPU-only hosts")
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.lmm_ctx_create(0, C.byref(h)) == _lib.LMM_E_CUDA
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lmm.Context(0)
+    buf = C.create_string_buffer(128)
+    assert lib.lmm_comm_unique_id(C.cast(buf, C.c_void_p)) in (0, _lib.LMM_E_NCCL)
+
+
+def test_product_path_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, load or call it."""
+    pkg = os.path.join(ROOT, "linearmixingmodels.jl_b200")
+    pat = re.compile(r"(from|import)\s+oracle|lmm_oracle|oracle/")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".inc", ".jl")):
+                assert not pat.search(open(os.path.join(dirpath, fn)).read()), fn
