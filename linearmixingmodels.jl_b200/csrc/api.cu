@@ -411,7 +411,8 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
     if (value < 1 || value > lmm_ctx::MAX_GROUPS) return ctx->fail(LMM_E_ARG, "streams must be in [1, 8]");
     ctx->ngroups = (int)value;
   } else if (k == "gemm_impl") {
-    if (value != 0.0) return ctx->fail(LMM_E_UNSUPPORTED, "only gemm_impl 0 exists");
+    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0 or 1");
+    set_gemm_impl((int)value);
   } else {
     return ctx->fail(LMM_E_UNSUPPORTED, "unknown option " + k);
   }

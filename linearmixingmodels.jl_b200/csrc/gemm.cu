@@ -132,6 +132,151 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel(GemmArgs g) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2: TMA bulk copies + full/empty mbarrier ring, no CTA-wide barrier in the main loop.
+// One elected thread (warp 0, lane 0) is the producer on the side: per 16-column k-chunk it issues
+// two 16 KB cp.async.bulk copies (SASS UBLKCP) that complete on the stage's `full` mbarrier; each
+// of the 8 consumer warps waits on `full`, runs its 128 DMMAs and arrives on the stage's `empty`
+// mbarrier.  Warps therefore drift apart by up to a few chunks, so one warp's chunk-boundary bubble
+// (barrier wait + first LDS latency) is covered by the other warp of its SM sub-partition.
+// ------------------------------------------------------------------------------------------------
+constexpr int V2_STAGES = 6;
+constexpr size_t GEMM_V2_SMEM = (size_t)V2_STAGES * 2 * CHUNK * sizeof(double) + 2 * V2_STAGES * sizeof(uint64_t);
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(s_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 28)) __trap();  // never hang the GPU on a protocol bug
+  }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src),
+               "r"(bytes), "r"(s_u32(bar))
+               : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
+  extern __shared__ __align__(128) double smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)V2_STAGES * 2 * CHUNK);
+  uint64_t* empty = full + V2_STAGES;
+  const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
+  if (g.sym && I < J) return;
+
+  double* Ctile = g.C.tile(b, I, J);
+  const double* Asrc;
+  const double* Bsrc;
+  int nchunks;
+  if (MODE == GEMM_UPDATE) {
+    Asrc = g.A.tile(b, I, g.k0);
+    Bsrc = g.B.tile(b, J, g.k0);
+    nchunks = (g.k1 - g.k0) * 8;
+  } else {
+    Asrc = Ctile;
+    Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
+    nchunks = 8;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 1, wn = warp >> 1;
+  constexpr uint32_t CHUNK_BYTES = CHUNK * sizeof(double);
+
+  if (tid == 0) {
+    for (int s = 0; s < V2_STAGES; ++s) {
+      mb_init(&full[s], 1);
+      mb_init(&empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto produce = [&](int q) {
+    const int s = q % V2_STAGES;
+    double* sa = smem + (size_t)s * (2 * CHUNK);
+    mb_expect_tx(&full[s], 2 * CHUNK_BYTES);
+    bulk_load(sa, Asrc + (size_t)q * CHUNK, CHUNK_BYTES, &full[s]);
+    bulk_load(sa + CHUNK, Bsrc + (size_t)q * CHUNK, CHUNK_BYTES, &full[s]);
+  };
+  if (tid == 0) {
+    const int pre = nchunks < V2_STAGES ? nchunks : V2_STAGES;
+    for (int q = 0; q < pre; ++q) produce(q);
+  }
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int q = 0; q < nchunks; ++q) {
+    const int s = q % V2_STAGES;
+    mb_wait(&full[s], (uint32_t)((q / V2_STAGES) & 1));
+    const double* sa = smem + (size_t)s * (2 * CHUNK) + (wm * 8) * 32 + lane;
+    const double* sb = smem + (size_t)s * (2 * CHUNK) + CHUNK + (wn * 4) * 32 + lane;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      double a[8], bq[4];
+#pragma unroll
+      for (int mb = 0; mb < 8; ++mb) a[mb] = sa[ks * 512 + mb * 32];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) bq[nb] = sb[ks * 512 + nb * 32];
+#pragma unroll
+      for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bq[nb]);
+    }
+    __syncwarp();
+    if (lane == 0) mb_arrive(&empty[s]);
+    // producer duty: refill the stage consumed one iteration ago (its readers had a whole chunk
+    // of time to finish, so this wait is normally already satisfied)
+    if (tid == 0 && q >= 1) {
+      const int qn = q - 1 + V2_STAGES;
+      if (qn < nchunks) {
+        mb_wait(&empty[(q - 1) % V2_STAGES], (uint32_t)(((q - 1) / V2_STAGES) & 1));
+        produce(qn);
+      }
+    }
+  }
+
+  const int g4 = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int mb = 0; mb < 8; ++mb) {
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const int cg = wn * 8 + nb * 2 + (t4 >> 1);
+      const int off = (cg << 9) + ((wm * 8 + mb) << 5) + (g4 << 2) + ((t4 & 1) << 1);
+      double2* ptr = reinterpret_cast<double2*>(Ctile + off);
+      double2 v;
+      if (MODE == GEMM_UPDATE) {
+        v = *ptr;
+        v.x -= acc[mb][nb][0];
+        v.y -= acc[mb][nb][1];
+      } else {
+        v.x = acc[mb][nb][0];
+        v.y = acc[mb][nb][1];
+      }
+      *ptr = v;
+    }
+  }
+}
+
+static int g_gemm_impl = 1;
+void set_gemm_impl(int impl) { g_gemm_impl = impl; }
+
 cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch) {
   if (ncols <= 0 || nrows <= 0 || batch <= 0) return cudaSuccess;
   static bool configured = false;
@@ -140,10 +285,19 @@ cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols,
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tile_kernel<GEMM_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
+    if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
-  if (mode == GEMM_UPDATE)
+  if (g_gemm_impl == 1) {
+    if (mode == GEMM_UPDATE)
+      gemm_tile_kernel_v2<GEMM_UPDATE><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
+    else
+      gemm_tile_kernel_v2<GEMM_TRSM><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
+  } else if (mode == GEMM_UPDATE)
     gemm_tile_kernel<GEMM_UPDATE><<<grid, 256, GEMM_SMEM, st>>>(a);
   else
     gemm_tile_kernel<GEMM_TRSM><<<grid, 256, GEMM_SMEM, st>>>(a);

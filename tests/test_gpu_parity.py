@@ -131,6 +131,32 @@ def test_oilmm_mid_size_multi_tile(lmm):
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
 
 
+@pytest.mark.parametrize("impl,streams,outer", [(0, 1, 8), (1, 1, 3), (0, 4, 16), (1, 8, 1)])
+def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer):
+    """Both GEMM pipelines (cp.async ring / TMA bulk + mbarrier ring), any stream-group count and
+    any outer block width give the same factor (N = 1100: 9 tile columns, batch 3)."""
+    N, p, m, Ns = 1100, 5, 3, 70
+    x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=77, means=True)
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    ctx = lmm.default_context()
+    ctx.set_option("gemm_impl", impl)
+    ctx.set_option("streams", streams)
+    ctx.set_option("outer_block", outer)
+    try:
+        fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+        post, lp = lmm.posterior(fx, y, with_logpdf=True)
+        assert rel(lp, o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
+        M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
+        Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
+        np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+        np.testing.assert_allclose(V, Vr, rtol=RTOL)
+    finally:
+        ctx.set_option("gemm_impl", 1)
+        ctx.set_option("streams", 4)
+        ctx.set_option("outer_block", 8)
+
+
 def test_distance_form_option(lmm):
     x, xs, U, S, fs, y = make_problem(300, 4, 2, 5, seed=11)
     om = o.OILMMModel(fs, U, S)

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Multi-rank parity check (run under torchrun, one rank per GPU): OILMM logpdf / posterior /
+mean_and_var / rand / posterior-logpdf / sweep with latents sharded over the ranks and the
+in-library NCCL all-reduce, against the CPU oracle on identical inputs."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lmm_b200 as lmm  # noqa: E402
+from oracle import lmm_oracle as o  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ctx = lmm.Context(local)
+    lmm.set_default_context(ctx)
+    lmm.dist.init_context_distributed(ctx)
+    rng = np.random.default_rng(0)
+    N, p, m, Ns = 700, 8, 5, 33
+    x = np.sort(rng.uniform(0, 7, N))
+    xs = rng.uniform(0, 7, Ns)
+    U, S = o.orthogonal_from_seed(p, m, seed=1)
+    kinds = [o.SE, o.MATERN32, o.MATERN52, o.SE, o.MATERN32]
+    fs = [o.GP(o.Kernel(kinds[i], float(rng.uniform(0.5, 1.5)), float(rng.uniform(0.5, 2.0))), float(rng.normal())) for i in range(m)]
+    y = rng.standard_normal(p * N)
+    om = o.OILMMModel(fs, U, S)
+    names = {o.SE: lmm.SEKernel, o.MATERN32: lmm.Matern32Kernel, o.MATERN52: lmm.Matern52Kernel}
+    gps = [lmm.GP(g.mean_const, (g.kernel.variance * names[g.kernel.kind]()).compose(lmm.ScaleTransform(g.kernel.inv_lengthscale))) for g in fs]
+    f = lmm.ILMM(lmm.independent_mogp(gps), lmm.Orthogonal(U, S))
+    fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+    ref = o.oilmm_logpdf(om, x, 0.1, y)
+    got = lmm.logpdf(fx, y)
+    errs = {"logpdf": abs(got - ref) / abs(ref)}
+    post, lp = lmm.posterior(fx, y, with_logpdf=True)
+    errs["posterior_logpdf_same"] = abs(lp - got)
+    M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
+    opost = o.oilmm_posterior(om, x, 0.1, y)
+    Mr, Vr = o.oilmm_mean_and_var(opost, xs, 0.1)
+    errs["mean"] = float(np.max(np.abs(M - Mr) / (np.abs(Mr) + 1e-10)))
+    errs["var"] = float(np.max(np.abs(V - Vr) / np.abs(Vr)))
+    ys = np.random.default_rng(5).standard_normal(p * Ns)
+    errs["post_logpdf"] = abs(lmm.logpdf(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.2), ys) - o.oilmm_logpdf(opost, xs, 0.2, ys)) / abs(
+        o.oilmm_logpdf(opost, xs, 0.2, ys))
+    scales = np.array([0.7, 1.0, 1.6])
+    sw = lmm.logpdf_sweep(fx, y, scales)
+    for s, v in zip(scales, sw):
+        fs_s = [o.GP(o.Kernel(g.kernel.kind, g.kernel.variance, g.kernel.inv_lengthscale * s), g.mean_const) for g in fs]
+        r = o.oilmm_logpdf(o.OILMMModel(fs_s, U, S), x, 0.1, y)
+        errs[f"sweep_{s}"] = abs(v - r) / abs(r)
+    # rand (Matern latents at few points so that K + 1e-18 I is numerically PD)
+    xr = np.linspace(0, 10, 6)
+    fr = [o.GP(o.Kernel(o.MATERN32, 1.0, 1.0 + 0.3 * i), 0.1 * i) for i in range(m)]
+    gr = [lmm.GP(g.mean_const, lmm.Matern32Kernel().compose(lmm.ScaleTransform(g.kernel.inv_lengthscale))) for g in fr]
+    frx = lmm.ILMM(lmm.independent_mogp(gr), lmm.Orthogonal(U, S))(lmm.MOInputIsotopicByOutputs(xr, p), 0.1)
+    gq = np.random.default_rng(21)
+    zl, zn = gq.standard_normal(m * 6), gq.standard_normal(p * 6)
+    s = lmm.rand(np.random.default_rng(21), frx)
+    errs["rand"] = float(np.max(np.abs(s - o.oilmm_rand(o.OILMMModel(fr, U, S), xr, 0.1, zl, zn))))
+    worst = max(errs.values())
+    ok = worst < 1e-7 and max(errs[k] for k in ("logpdf", "mean", "var", "post_logpdf")) < 1e-9
+    print(f"rank {rank}/{world}: {'OK' if ok else 'FAIL'} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+    post.f.fs[0]._owner.free()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
