@@ -112,12 +112,19 @@ def fp64_peak_tflops():
         return 35.9, "fallback: cuBLAS DGEMM 8192^3 measured earlier on this pool"
 
 
-def ncu_traffic():
+def ncu_traffic(p, N, mloc):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the Cholesky launch sequence of
+    one step on one rank, from the committed ncu pass over a full C4 eval
+    (profiles/r01_launches_c4_summary.json: 64 latents); per-latent work is independent, so a rank
+    holding mloc latents moves mloc/64 of it.  null for any other problem size."""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_gemm_summary.json")) as fh:
-            return json.load(fh).get("dram_bytes_per_launch")
+        with open(os.path.join(ROOT, "profiles", "r01_launches_c4_summary.json")) as fh:
+            d = json.load(fh)
+        if p == 64 and N == 16384:
+            return d["cholesky_sequence"]["dram_bytes_per_step"] * mloc / 64.0
     except Exception:
-        return None
+        pass
+    return None
 
 
 def cpu_latent_eval(x, inv_ls_i, noise_i, delta, threads):
@@ -179,6 +186,7 @@ def main():
     ap.add_argument("--m", type=int, default=64)
     ap.add_argument("--N", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=0, help="latent groups on separate CUDA streams (0 = library default)")
     args = ap.parse_args()
     p, m, N = args.p, args.m, args.N
     cfg = {"p": p, "m": m, "N": N,
@@ -206,6 +214,8 @@ def main():
     lmm.set_default_context(ctx)
     if world > 1:
         lmm.dist.init_context_distributed(ctx)
+    if args.streams > 0:
+        ctx.set_option("streams", args.streams)
 
     x, U, S, inv_ls, y, s2 = workload(p, m, N)
     H = lmm.Orthogonal(U, S)
@@ -286,7 +296,7 @@ def main():
         "gpu_launches": int(launches.item()),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "batched blocked Cholesky (gemm_tile_kernel DMMA updates + potrf_tile_kernel + TRSM-as-GEMM)",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(p, N, mloc),
                      "peak_source": peak_src, "flops_per_rank_step": chol_flops,
                      "whole_eval_tflops": (m * (N ** 3 / 3.0 + 2.0 * N * N) + 4.0 * p * m * N) / (ms_per_step * 1e-3) / 1e12 / world},
         "stage_ms_per_step": {"kmat": kmat_ms / K, "cholesky": chol_ms / K, "solves": solve_ms / K},

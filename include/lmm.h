@@ -129,6 +129,17 @@ int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, cons
  * mean/var); for an IndependentMOGP posterior: src/independent_mogp.jl:50-57; ILMM: src/ilmm.jl:122-129. */
 int lmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean,
                           double* var);
+/* mean_and_cov(post(x*, σ²)) / cov: dense (p Ns) x (p Ns) column-major output, by outputs
+ * (src/ilmm.jl:132-139,147; src/independent_mogp.jl:60-63 + Σy).  mean is nullable. */
+int lmm_post_mean_and_cov(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean,
+                          double* cov);
+/* mean_and_cov(fx) on PRIOR latents mixed by H (p x m column-major; pass U*sqrt(S) for an OILMM,
+ * the identity for an IndependentMOGP): C = (H ⊗ I)(blockdiag K_a + latent_jitter I)(H ⊗ I)' + σ² I.
+ * latent_jitter is the FiniteGP default noise 1e-18 for ILMM/OILMM (src/ilmm.jl:115), 0 for an
+ * IndependentMOGP. */
+int lmm_prior_mean_and_cov(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* xs, int Ns,
+                           int D, const double* H, int p, double sigma2, double latent_jitter,
+                           int out_dim, double* mean, double* cov);
 /* logpdf(post(x*, σ²), y*)  (test/oilmm.jl:84): OILMM logpdf with PosteriorGP latents. */
 int lmm_post_logpdf(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys,
                     double* out_logpdf, int* info_latent);

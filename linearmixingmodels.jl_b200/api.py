@@ -31,7 +31,7 @@ __all__ = [
     "SEKernel", "SqExponentialKernel", "Matern32Kernel", "Matern52Kernel", "ScaleTransform", "with_lengthscale",
     "GP", "MOInputIsotopicByOutputs", "MOInputIsotopicByFeatures", "ColVecs", "RowVecs",
     "ILMM", "OILMM", "Orthogonal", "IndependentMOGP", "independent_mogp", "get_latent_gp",
-    "FiniteGP", "Normal", "logpdf", "posterior", "mean_and_var", "mean", "var", "marginals", "rand",
+    "FiniteGP", "Normal", "logpdf", "posterior", "mean_and_var", "mean", "var", "marginals", "rand", "cov", "mean_and_cov",
     "PosDefException", "Context", "default_context", "noise_var", "reshape_y", "unpack",
     "indices_which_reorder_outputs_to_features", "indices_which_reorder_features_to_outputs",
 ]
@@ -660,6 +660,49 @@ def mean_and_var(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
     if reorder is not None:
         M, V = M[reorder], V[reorder]
     return M, V
+
+
+def mean_and_cov(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
+    """`mean_and_cov(fx)`: src/ilmm.jl:132-139 (also the path `cov(fx::FiniteGP{<:OILMM})` takes),
+    src/independent_mogp.jl:60-63 + Σy.  Dense (p N*)² output -- meant for small N*."""
+    f = fx.f
+    ctx = _ctx_of(fx)
+    owner = _post_owner(fx)
+    x = fx.x
+    reorder = None
+    if isinstance(f, IndependentMOGP) and isinstance(x, MOInputIsotopicByFeatures):
+        reorder = indices_which_reorder_outputs_to_features(x)  # src/independent_mogp.jl:181-186
+        x = MOInputIsotopicByOutputs(x.x, x.out_dim)
+    elif not isinstance(x, MOInputIsotopicByOutputs):
+        raise TypeError("this method needs MOInput inputs")
+    pts = _points(x.x)
+    Ns, D = int(pts.shape[0]), int(pts.shape[1])
+    p = x.out_dim
+    if isinstance(f, ILMM) and f.H.shape[0] != p:
+        raise RuntimeError("out dim of x != out dim of f.")
+    M = np.zeros(p * Ns)
+    Cm = np.zeros((p * Ns, p * Ns), order="F")
+    if owner is not None:
+        rc = ctx.lib.lmm_post_mean_and_cov(owner.handle, ptr(pts), Ns, fx.sigma2, ptr(M), ptr(Cm))
+    else:
+        if isinstance(f, ILMM):
+            fs, H, jitter = f.f.fs, np.asfortranarray(np.asarray(f.H, dtype=np.float64)), 1e-18
+        elif isinstance(f, IndependentMOGP):
+            if len(f.fs) != p:
+                raise RuntimeError("out dim of x != out dim of f.")
+            fs, H, jitter = f.fs, np.asfortranarray(np.eye(p)), 0.0
+        else:
+            raise TypeError(f"mean_and_cov not defined for FiniteGP of {type(f).__name__}")
+        rc = ctx.lib.lmm_prior_mean_and_cov(ctx.handle, _descs(fs), len(fs), ptr(pts), Ns, D, ptr(H), p, fx.sigma2, jitter, p, ptr(M), ptr(Cm))
+    ctx.check(rc)
+    Cm = np.ascontiguousarray(Cm)
+    if reorder is not None:
+        M, Cm = M[reorder], Cm[np.ix_(reorder, reorder)]
+    return M, Cm
+
+
+def cov(fx: FiniteGP) -> np.ndarray:
+    return mean_and_cov(fx)[1]  # src/ilmm.jl:147
 
 
 def mean(fx: FiniteGP) -> np.ndarray:

@@ -74,6 +74,11 @@ struct lmm_ctx {
   int ngroups = 4;
   cudaStream_t gstream[MAX_GROUPS];
   cudaEvent_t ev_fork, ev_join[MAX_GROUPS];
+  // block-level look-ahead for small batches (ILMM: batch 1): panel stream (high priority) +
+  // trailing-update stream, chained by per-block events
+  cudaStream_t panel_stream = nullptr, update_stream = nullptr;
+  std::vector<cudaEvent_t> blk_ev;
+  int lookahead = 1;
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -228,9 +233,76 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
   return cudaSuccess;
 }
 
+// Block-level look-ahead (small batches: nothing else can hide the panel latency).  The wide
+// update of block column b is split along K: part A (all columns before block b-1) runs on the
+// update stream concurrently with the latency-bound panel steps of block b-1 on the high-priority
+// panel stream; part B (the columns of block b-1) follows on the panel stream.
+cudaError_t chol_factor_lookahead(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
+  const int nt = L.nt, ob = ctx->outer_block;
+  const int nblk = (nt + ob - 1) / ob;
+  cudaError_t e;
+  while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
+    cudaEvent_t ev;
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    ctx->blk_ev.push_back(ev);
+  }
+  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream;
+  cudaEvent_t* evI = ctx->blk_ev.data();          // inner(b) done on X
+  cudaEvent_t* evA = ctx->blk_ev.data() + nblk;   // part A(b) done on Y
+  GemmArgs g{};
+  g.A = operand(L); g.B = operand(L); g.C = operand(L);
+  g.W = W; g.w_batch_stride = wstride; g.sym = 1;
+  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  bool y_used = false;
+  for (int b = 0; b < nblk; ++b) {
+    const int s0 = b * ob, s1 = (s0 + ob < nt) ? s0 + ob : nt;
+    const int sp = (b >= 1) ? (b - 1) * ob : 0;  // first column of block b-1
+    if (b >= 2) {  // part A on Y: k in [0, sp)
+      if ((e = cudaStreamWaitEvent(Y, evI[b - 2], 0)) != cudaSuccess) return e;
+      g.i0 = s0; g.j0 = s0; g.k0 = 0; g.k1 = sp;
+      if ((e = launch_gemm(Y, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(evA[b], Y)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(X, evA[b], 0)) != cudaSuccess) return e;
+      ++ctx->launches;
+      ctx->timings[6] += 1;
+      y_used = true;
+    }
+    if (b >= 1) {  // part B on X: k in [sp, s0)
+      g.i0 = s0; g.j0 = s0; g.k0 = sp; g.k1 = s0;
+      if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
+      ++ctx->launches;
+      ctx->timings[6] += 1;
+    }
+    for (int jj = s0; jj < s1; ++jj) {
+      if (jj > s0) {
+        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+      if ((e = launch_potrf_tile(X, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
+      ++ctx->launches;
+      if (jj + 1 < nt) {
+        g.i0 = jj + 1; g.j0 = jj;
+        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+    }
+    if ((e = cudaEventRecord(evI[b], X)) != cudaSuccess) return e;
+  }
+  if ((e = cudaStreamWaitEvent(ctx->stream, evI[nblk - 1], 0)) != cudaSuccess) return e;
+  if (y_used) {
+    if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 // Fork the batch into latent groups on separate streams (joined back into ctx->stream).
 cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
   const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
+  if (ctx->lookahead && batch <= 2 && L.nt > 2 * ctx->outer_block) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
   if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info);
   cudaError_t e;
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
@@ -370,6 +442,12 @@ extern "C" int lmm_ctx_create(int device, lmm_ctx** out) {
   }
   for (auto& e : ctx->ev) cudaEventCreate(&e);
   for (auto& g : ctx->gstream) cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking);
+  {
+    int lo_pri = 0, hi_pri = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+    cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, hi_pri);
+    cudaStreamCreateWithPriority(&ctx->update_stream, cudaStreamNonBlocking, lo_pri);
+  }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   for (auto& e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaMemPool_t pool;
@@ -388,6 +466,9 @@ extern "C" int lmm_ctx_destroy(lmm_ctx* ctx) {
   if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& g : ctx->gstream) cudaStreamDestroy(g);
+  cudaStreamDestroy(ctx->panel_stream);
+  cudaStreamDestroy(ctx->update_stream);
+  for (auto& e : ctx->blk_ev) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_fork);
   for (auto& e : ctx->ev_join) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
@@ -410,6 +491,8 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "streams") {
     if (value < 1 || value > lmm_ctx::MAX_GROUPS) return ctx->fail(LMM_E_ARG, "streams must be in [1, 8]");
     ctx->ngroups = (int)value;
+  } else if (k == "lookahead") {
+    ctx->lookahead = value != 0.0;
   } else if (k == "gemm_impl") {
     if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0 or 1");
     set_gemm_impl((int)value);

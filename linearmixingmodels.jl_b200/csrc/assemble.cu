@@ -158,3 +158,66 @@ cudaError_t launch_gather_rows(cudaStream_t st, double* dst, const double* src, 
 }
 
 }  // namespace lmm
+
+namespace lmm {
+
+// Dense output covariance from independent latent covariances (TiledSym C, one per resident latent):
+//   out[(j,n) + (j2,n2)*pNs] = sum_a H[j,a] H[j2,a] C_a(n,n2)      (the caller adds σ² on the diagonal
+//   after the cross-rank reduction).  src/ilmm.jl:132-139 without kron(H, I): C = (H⊗I) C_lat (H⊗I)'.
+// grid (ceil(pNs/16), ceil(pNs/16)), block 16x16.
+__global__ void __launch_bounds__(256) mix_cov_kernel(TiledSym C, int nloc, int lat0, const double* __restrict__ H, int p, int Ns,
+                                                      double* __restrict__ out) {
+  const int dim = p * Ns;
+  const int row = blockIdx.x * 16 + threadIdx.x, col = blockIdx.y * 16 + threadIdx.y;
+  if (row >= dim || col >= dim) return;
+  const int j = row / Ns, n = row % Ns, j2 = col / Ns, n2 = col % Ns;
+  const int hi = n >= n2 ? n : n2, lo = n >= n2 ? n2 : n;
+  const size_t off = sym_tile_index(hi / TILE, lo / TILE) * TT + tile_elem(hi % TILE, lo % TILE);
+  double s = 0.0;
+  for (int a = 0; a < nloc; ++a)
+    s = fma(H[(size_t)(lat0 + a) * p + j] * H[(size_t)(lat0 + a) * p + j2], C.base[(size_t)a * C.batch_stride + off], s);
+  out[(size_t)col * dim + row] = s;
+}
+cudaError_t launch_mix_cov(cudaStream_t st, TiledSym C, int nloc, int lat0, const double* H, int p, int Ns, double* out) {
+  const int dim = p * Ns;
+  dim3 grid((unsigned)((dim + 15) / 16), (unsigned)((dim + 15) / 16)), block(16, 16);
+  mix_cov_kernel<<<grid, block, 0, st>>>(C, nloc, lat0, H, p, Ns, out);
+  return cudaGetLastError();
+}
+
+// Same from a joint latent covariance Cl (TiledSym over m*Ns, batch 1):
+//   out[(j,n),(j2,n2)] = sum_{a,b} H[j,a] H[j2,b] Cl[(a,n),(b,n2)]
+__global__ void __launch_bounds__(256) mix_cov_joint_kernel(TiledSym Cl, int m, const double* __restrict__ H, int p, int Ns,
+                                                            double* __restrict__ out) {
+  const int dim = p * Ns;
+  const int row = blockIdx.x * 16 + threadIdx.x, col = blockIdx.y * 16 + threadIdx.y;
+  if (row >= dim || col >= dim) return;
+  const int j = row / Ns, n = row % Ns, j2 = col / Ns, n2 = col % Ns;
+  double s = 0.0;
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b < m; ++b) {
+      const int r = a * Ns + n, c = b * Ns + n2;
+      const int hi = r >= c ? r : c, lo = r >= c ? c : r;
+      const double v = Cl.base[sym_tile_index(hi / TILE, lo / TILE) * TT + tile_elem(hi % TILE, lo % TILE)];
+      s = fma(H[(size_t)a * p + j] * H[(size_t)b * p + j2], v, s);
+    }
+  out[(size_t)col * dim + row] = s;
+}
+cudaError_t launch_mix_cov_joint(cudaStream_t st, TiledSym Cl, int m, const double* H, int p, int Ns, double* out) {
+  const int dim = p * Ns;
+  dim3 grid((unsigned)((dim + 15) / 16), (unsigned)((dim + 15) / 16)), block(16, 16);
+  mix_cov_joint_kernel<<<grid, block, 0, st>>>(Cl, m, H, p, Ns, out);
+  return cudaGetLastError();
+}
+
+// out[i + i*dim] += s
+__global__ void add_diag_kernel(double* out, int dim, double s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dim) out[(size_t)i * dim + i] += s;
+}
+cudaError_t launch_add_diag(cudaStream_t st, double* out, int dim, double s) {
+  add_diag_kernel<<<(dim + 255) / 256, 256, 0, st>>>(out, dim, s);
+  return cudaGetLastError();
+}
+
+}  // namespace lmm

@@ -63,17 +63,22 @@ struct LatentParams {
 
 // κ(d²)·variance -- KernelFunctions kappa for SE / Matern32 / Matern52.
 __device__ __forceinline__ double kappa_eval(int kind, double variance, double d2) {
+  // exp() underflows to exactly 0.0 below about -745.14; far-apart pairs (most of a kernel matrix
+  // whose inputs span many lengthscales) skip the transcendental and store the same 0.0.
   double v;
   if (kind == 0) {
+    if (d2 > 1500.0) return 0.0;
     v = exp(-d2 / 2.0);
   } else {
     double d = sqrt(d2);
     if (kind == 1) {
       double s = 1.7320508075688772 * d;  // sqrt(3)
+      if (s > 800.0) return 0.0;
       v = (1.0 + s) * exp(-s);
     } else {
       double s = 2.23606797749979 * d;  // sqrt(5)
-      v = (1.0 + s + 5.0 * d * d / 3.0) * exp(-s);
+      if (s > 800.0) return 0.0;
+      v = (1.0 + s + 5.0 * (d * d) / 3.0) * exp(-s);
     }
   }
   return variance * v;

@@ -85,3 +85,9 @@ cudaError_t launch_ilmm_predict(cudaStream_t st, TiledRect V, int Ns, int m, int
                                 const double* mlat, double sigma2, double* mean, double* var);
 cudaError_t launch_gather_rows(cudaStream_t st, double* dst, const double* src, const int* idx, size_t stride, int n);
 }  // namespace lmm
+
+namespace lmm {
+cudaError_t launch_mix_cov(cudaStream_t st, TiledSym C, int nloc, int lat0, const double* H, int p, int Ns, double* out);
+cudaError_t launch_mix_cov_joint(cudaStream_t st, TiledSym Cl, int m, const double* H, int p, int Ns, double* out);
+cudaError_t launch_add_diag(cudaStream_t st, double* out, int dim, double s);
+}  // namespace lmm

@@ -110,7 +110,7 @@ def kappa(kind: int, d2: np.ndarray) -> np.ndarray:
         return (1.0 + s) * np.exp(-s)
     if kind == MATERN52:
         s = math.sqrt(5.0) * d
-        return (1.0 + s + 5.0 * d * d / 3.0) * np.exp(-s)
+        return (1.0 + s + 5.0 * (d * d) / 3.0) * np.exp(-s)  # Julia: 5 * d^2 / 3
     raise ValueError(f"unsupported kernel kind {kind}")
 
 
@@ -329,6 +329,12 @@ def imogp_cov(fs, xs) -> np.ndarray:
     return sla.block_diag(*[gp_cov(f, xs) for f in fs])
 
 
+def imogp_mean_and_cov(fs, xs, sigma2: float) -> Tuple[np.ndarray, np.ndarray]:
+    """AbstractGPs generic ``mean_and_cov(fx)`` = (mean(f,x), cov(f,x) + Σy) on an IndependentMOGP."""
+    C = imogp_cov(fs, xs)
+    return np.concatenate([gp_mean(f, xs) for f in fs]), C + sigma2 * np.eye(C.shape[0])
+
+
 def imogp_rand(fs, xs, sigma2: float, z: np.ndarray) -> np.ndarray:
     """src/independent_mogp.jl:83-86 -- z holds N normals per latent, latent-major."""
     N = _as2d(xs).shape[0]
@@ -466,9 +472,9 @@ def _ilmm_latent_mean_and_cov(f, xs, form="gemm") -> Tuple[np.ndarray, np.ndarra
         mean = prior_mean + Ksx @ f.alpha
         V = _fwd(f.L, Ksx.T)
         cov = sla.block_diag(*[kernelmatrix(g.kernel, xs, form=form) for g in f.fs]) - V.T @ V
-    else:
-        mean = np.concatenate([np.full(Ns, g.mean_const) for g in f])
-        cov = _latent_prior_cov(f, xs, form)
+    else:  # independent latents: priors (GP) or per-latent posteriors (PosteriorGP), src/independent_mogp.jl:50-63
+        mean = np.concatenate([gp_mean(g, xs) for g in f])
+        cov = sla.block_diag(*[gp_cov(g, xs) for g in f])
     return mean, cov + 1e-18 * np.eye(cov.shape[0])
 
 

@@ -329,3 +329,58 @@ def test_device_resident_inputs(lmm):
     yd = torch.from_numpy(y).cuda()
     b = lmm.logpdf(f(lmm.MOInputIsotopicByOutputs(xd, 4), 0.1), yd)
     assert a == b
+
+
+def test_cov_and_mean_and_cov(lmm):
+    """`cov` / `mean_and_cov` (src/ilmm.jl:132-139,147; src/independent_mogp.jl:60-63): prior and
+    posterior, OILMM / general ILMM / IndependentMOGP -- the quantities test_utils.jl:50-59 compares."""
+    rng = np.random.default_rng(12)
+    N, Ns, p, m = 60, 9, 3, 2
+    x = np.sort(rng.uniform(0, 4, N))
+    xs = np.sort(rng.uniform(0, 4, Ns))
+    U, S = o.orthogonal_from_seed(p, m, seed=4)
+    fs = [o.GP(o.Kernel(o.SE), 0.3), o.GP(o.Kernel(o.MATERN32, 0.7, 1.3), -0.1)]
+    om = o.OILMMModel(fs, U, S)
+    H = om.H
+    y = rng.standard_normal(p * N)
+    gps = [to_lmm_gp(lmm, g) for g in fs]
+    xin, xsin = lmm.MOInputIsotopicByOutputs(x, p), lmm.MOInputIsotopicByOutputs(xs, p)
+    f_o = lmm.ILMM(lmm.independent_mogp(gps), lmm.Orthogonal(U, S))
+    f_i = lmm.ILMM(lmm.independent_mogp(gps), H)
+    # prior
+    Mr, Cr = o.ilmm_mean_and_cov(fs, H, xs, 0.1)
+    for f in (f_o, f_i):
+        M, C = lmm.mean_and_cov(f(xsin, 0.1))
+        np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(C, Cr, rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(np.diag(lmm.cov(f(xsin, 0.1))), lmm.var(f(xsin, 0.1)), rtol=1e-12)
+    # OILMM posterior
+    post = lmm.posterior(f_o(xin, 0.1), y)
+    opost = o.oilmm_posterior(om, x, 0.1, y)
+    Mr, Cr = o.ilmm_mean_and_cov(opost.fs, H, xs, 0.1)
+    M, C = lmm.mean_and_cov(post(xsin, 0.1))
+    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(C, Cr, rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(np.diag(C), lmm.var(post(xsin, 0.1)), rtol=1e-9)
+    # general ILMM posterior (joint)
+    posti = lmm.posterior(f_i(xin, 0.1), y)
+    Mr, Cr = o.ilmm_mean_and_cov(o.ilmm_posterior(fs, H, x, 0.1, y), H, xs, 0.1)
+    M, C = lmm.mean_and_cov(posti(xsin, 0.1))
+    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(C, Cr, rtol=1e-8, atol=1e-11)
+    # IndependentMOGP prior / posterior, by outputs and by features
+    fm = lmm.independent_mogp(gps)
+    xs2 = lmm.MOInputIsotopicByOutputs(xs, 2)
+    Mr, Cr = o.imogp_mean_and_cov(fs, xs, 0.2)
+    M, C = lmm.mean_and_cov(fm(xs2, 0.2))
+    np.testing.assert_allclose(M, Mr, rtol=RTOL)
+    np.testing.assert_allclose(C, Cr, rtol=RTOL, atol=1e-13)
+    y2 = rng.standard_normal(2 * N)
+    pm = lmm.posterior(fm(lmm.MOInputIsotopicByOutputs(x, 2), 0.1), y2)
+    Mr, Cr = o.imogp_mean_and_cov(o.imogp_posterior(fs, x, 0.1, y2), xs, 0.2)
+    M, C = lmm.mean_and_cov(pm(xs2, 0.2))
+    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(C, Cr, rtol=1e-8, atol=1e-11)
+    idx = o.indices_outputs_to_features(Ns, 2)
+    Mf, Cf = lmm.mean_and_cov(pm(lmm.MOInputIsotopicByFeatures(xs, 2), 0.2))
+    np.testing.assert_allclose(Cf, Cr[np.ix_(idx, idx)], rtol=1e-8, atol=1e-11)
