@@ -462,8 +462,9 @@ def ilmm_posterior(fs: Sequence[GP], H: np.ndarray, x, sigma2: float, y: np.ndar
     return ILMMPosterior(list(fs), H, np.asarray(x, dtype=np.float64), alpha, L)
 
 
-def _ilmm_latent_mean_and_cov(f, xs, form="gemm") -> Tuple[np.ndarray, np.ndarray]:
-    """``mean_and_cov(f(x_mo))`` for prior (list of GP) or joint posterior, incl. the 1e-18 noise."""
+def _ilmm_latent_mean_and_cov(f, xs, form="gemm", jitter: float = 1e-18) -> Tuple[np.ndarray, np.ndarray]:
+    """``mean_and_cov(f(x_mo, jitter))`` for prior (list of GP) or joint posterior; the default
+    jitter is the FiniteGP default noise 1e-18 (src/ilmm.jl:115)."""
     Ns = _as2d(xs).shape[0]
     if isinstance(f, ILMMPosterior):
         m = len(f.fs)
@@ -475,7 +476,7 @@ def _ilmm_latent_mean_and_cov(f, xs, form="gemm") -> Tuple[np.ndarray, np.ndarra
     else:  # independent latents: priors (GP) or per-latent posteriors (PosteriorGP), src/independent_mogp.jl:50-63
         mean = np.concatenate([gp_mean(g, xs) for g in f])
         cov = sla.block_diag(*[gp_cov(g, xs) for g in f])
-    return mean, cov + 1e-18 * np.eye(cov.shape[0])
+    return mean, cov + jitter * np.eye(cov.shape[0])
 
 
 def ilmm_mean_and_cov(f, H: np.ndarray, xs, sigma2: float) -> Tuple[np.ndarray, np.ndarray]:
@@ -497,6 +498,27 @@ def ilmm_rand(fs: Sequence[GP], H: np.ndarray, xs, sigma2: float, z_latent: np.n
     """src/ilmm.jl:78-87 -- latent jitter 1e-12, then ``vec(reshape(latent, N, m) * H') + sqrt(σ²) ε``."""
     lat = imogp_rand(fs, xs, 1e-12, z_latent).reshape(len(fs), -1)  # m x N
     return (np.asarray(H, dtype=np.float64) @ lat).reshape(-1) + math.sqrt(sigma2) * np.asarray(z_noise, dtype=np.float64)
+
+
+def ilmm_post_rand(post: ILMMPosterior, xs, sigma2: float, z_latent: np.ndarray, z_noise: np.ndarray) -> np.ndarray:
+    """src/ilmm.jl:78-87 on ``ILMM(PosteriorGP{IndependentMOGP}, H)``: latent = m* + chol(C* + 1e-12 I) z."""
+    mean, cov = _ilmm_latent_mean_and_cov(post, xs, jitter=1e-12)
+    lat = (mean + _chol_lower(cov) @ np.asarray(z_latent, dtype=np.float64)).reshape(len(post.fs), -1)
+    return (post.H @ lat).reshape(-1) + math.sqrt(sigma2) * np.asarray(z_noise, dtype=np.float64)
+
+
+def ilmm_post_logpdf(post: ILMMPosterior, xs, sigma2: float, ys: np.ndarray) -> float:
+    """src/ilmm.jl:150-163 on the posterior ILMM: logN(vec((TY*)') | m*, C* + ΣT ⊗ I) + regulariser."""
+    Ns = _as2d(xs).shape[0]
+    m = len(post.fs)
+    Y = reshape_y(ys, Ns)
+    T, ST = project_general(post.H, sigma2)
+    yproj = (T @ Y).reshape(-1)
+    mean, cov = _ilmm_latent_mean_and_cov(post, xs, jitter=0.0)
+    L = _chol_lower(cov + np.kron(ST, np.eye(Ns)))
+    z = _fwd(L, yproj - mean)
+    lml = -0.5 * (m * Ns * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(z @ z))
+    return lml + regulariser_general(post.H, sigma2, Y)
 
 
 # --------------------------------------------------------------------------------------------

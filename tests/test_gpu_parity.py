@@ -384,3 +384,25 @@ def test_cov_and_mean_and_cov(lmm):
     idx = o.indices_outputs_to_features(Ns, 2)
     Mf, Cf = lmm.mean_and_cov(pm(lmm.MOInputIsotopicByFeatures(xs, 2), 0.2))
     np.testing.assert_allclose(Cf, Cr[np.ix_(idx, idx)], rtol=1e-8, atol=1e-11)
+
+
+def test_ilmm_posterior_rand_and_logpdf(lmm):
+    """`rand(rng, p_i)` and `logpdf(p_i(x*, σ²), y*)` on a general-ILMM posterior (src/ilmm.jl:78-87,
+    150-163 with PosteriorGP{IndependentMOGP} latents; test/ilmm.jl:26-27, notebook `rand(rng, p_i)`)."""
+    rng = np.random.default_rng(14)
+    N, Ns, p, m = 40, 7, 3, 2
+    x = np.sort(rng.uniform(0, 6, N))
+    xs = np.sort(rng.uniform(0, 6, Ns))
+    H = rng.uniform(0, 1, (p, m))
+    fs = [o.GP(o.Kernel(o.MATERN32), 0.2), o.GP(o.Kernel(o.MATERN52, 0.8, 1.4), -0.3)]
+    y = rng.standard_normal(p * N)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), H)
+    post = lmm.posterior(f(lmm.MOInputIsotopicByOutputs(x, p), 0.1), y)
+    opost = o.ilmm_posterior(fs, H, x, 0.1, y)
+    pfx = post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1)
+    g = np.random.default_rng(31)
+    zl, zn = g.standard_normal(m * Ns), g.standard_normal(p * Ns)
+    s = lmm.rand(np.random.default_rng(31), pfx)
+    np.testing.assert_allclose(s, o.ilmm_post_rand(opost, xs, 0.1, zl, zn), rtol=1e-6, atol=1e-7)
+    ys = rng.standard_normal(p * Ns)
+    assert rel(lmm.logpdf(pfx, ys), o.ilmm_post_logpdf(opost, xs, 0.1, ys)) < RTOL
