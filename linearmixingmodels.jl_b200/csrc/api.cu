@@ -494,7 +494,7 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "lookahead") {
     ctx->lookahead = value != 0.0;
   } else if (k == "gemm_impl") {
-    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0 or 1");
+    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0, 1 or 2");
     set_gemm_impl((int)value);
   } else {
     return ctx->fail(LMM_E_UNSUPPORTED, "unknown option " + k);

@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel(GemmArgs g) {
 // mbarrier.  Warps therefore drift apart by up to a few chunks, so one warp's chunk-boundary bubble
 // (barrier wait + first LDS latency) is covered by the other warp of its SM sub-partition.
 // ------------------------------------------------------------------------------------------------
-constexpr int V2_STAGES = 6;
-constexpr size_t GEMM_V2_SMEM = (size_t)V2_STAGES * 2 * CHUNK * sizeof(double) + 2 * V2_STAGES * sizeof(uint64_t);
+// KC = k-columns per stage (16 or 32); the ring always holds 96 columns of A and of B (192 KB).
+constexpr size_t GEMM_V2_SMEM = (size_t)6 * 2 * CHUNK * sizeof(double) + 2 * 6 * sizeof(uint64_t);
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
@@ -171,10 +171,12 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                : "memory");
 }
 
-template <int MODE>
+template <int MODE, int KC>
 __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
+  constexpr int V2_STAGES = 96 / KC;
+  constexpr int SCHUNK = 128 * KC;  // doubles per operand per stage
   extern __shared__ __align__(128) double smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)V2_STAGES * 2 * CHUNK);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)6 * 2 * CHUNK);
   uint64_t* empty = full + V2_STAGES;
   const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
   if (g.sym && I < J) return;
@@ -186,15 +188,15 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   if (MODE == GEMM_UPDATE) {
     Asrc = g.A.tile(b, I, g.k0);
     Bsrc = g.B.tile(b, J, g.k0);
-    nchunks = (g.k1 - g.k0) * 8;
+    nchunks = (g.k1 - g.k0) * (128 / KC);
   } else {
     Asrc = Ctile;
     Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
-    nchunks = 8;
+    nchunks = 128 / KC;
   }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 1, wn = warp >> 1;
-  constexpr uint32_t CHUNK_BYTES = CHUNK * sizeof(double);
+  constexpr uint32_t CHUNK_BYTES = SCHUNK * sizeof(double);
 
   if (tid == 0) {
     for (int s = 0; s < V2_STAGES; ++s) {
@@ -206,10 +208,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   __syncthreads();
   auto produce = [&](int q) {
     const int s = q % V2_STAGES;
-    double* sa = smem + (size_t)s * (2 * CHUNK);
+    double* sa = smem + (size_t)s * (2 * SCHUNK);
     mb_expect_tx(&full[s], 2 * CHUNK_BYTES);
-    bulk_load(sa, Asrc + (size_t)q * CHUNK, CHUNK_BYTES, &full[s]);
-    bulk_load(sa + CHUNK, Bsrc + (size_t)q * CHUNK, CHUNK_BYTES, &full[s]);
+    bulk_load(sa, Asrc + (size_t)q * SCHUNK, CHUNK_BYTES, &full[s]);
+    bulk_load(sa + SCHUNK, Bsrc + (size_t)q * SCHUNK, CHUNK_BYTES, &full[s]);
   };
   if (tid == 0) {
     const int pre = nchunks < V2_STAGES ? nchunks : V2_STAGES;
@@ -225,10 +227,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   for (int q = 0; q < nchunks; ++q) {
     const int s = q % V2_STAGES;
     mb_wait(&full[s], (uint32_t)((q / V2_STAGES) & 1));
-    const double* sa = smem + (size_t)s * (2 * CHUNK) + (wm * 8) * 32 + lane;
-    const double* sb = smem + (size_t)s * (2 * CHUNK) + CHUNK + (wn * 4) * 32 + lane;
+    const double* sa = smem + (size_t)s * (2 * SCHUNK) + (wm * 8) * 32 + lane;
+    const double* sb = smem + (size_t)s * (2 * SCHUNK) + SCHUNK + (wn * 4) * 32 + lane;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int ks = 0; ks < KC / 4; ++ks) {
       double a[8], bq[4];
 #pragma unroll
       for (int mb = 0; mb < 8; ++mb) a[mb] = sa[ks * 512 + mb * 32];
@@ -274,29 +276,41 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   }
 }
 
-static int g_gemm_impl = 1;
+static int g_gemm_impl = 2;  // 0: v1 cp.async ring; 1: v2 (TMA bulk + mbarriers), 16-column stages; 2: v2, 32-column stages
 void set_gemm_impl(int impl) { g_gemm_impl = impl; }
 
 cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch) {
   if (ncols <= 0 || nrows <= 0 || batch <= 0) return cudaSuccess;
-  static bool configured = false;
+  static bool configured_dev[64] = {false};  // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel<GEMM_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tile_kernel<GEMM_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
+    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_UPDATE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
+    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_TRSM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_UPDATE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_TRSM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
   if (g_gemm_impl == 1) {
     if (mode == GEMM_UPDATE)
-      gemm_tile_kernel_v2<GEMM_UPDATE><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
+      gemm_tile_kernel_v2<GEMM_UPDATE, 16><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
     else
-      gemm_tile_kernel_v2<GEMM_TRSM><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
+      gemm_tile_kernel_v2<GEMM_TRSM, 16><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
+  } else if (g_gemm_impl == 2) {
+    if (mode == GEMM_UPDATE)
+      gemm_tile_kernel_v2<GEMM_UPDATE, 32><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
+    else
+      gemm_tile_kernel_v2<GEMM_TRSM, 32><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
   } else if (mode == GEMM_UPDATE)
     gemm_tile_kernel<GEMM_UPDATE><<<grid, 256, GEMM_SMEM, st>>>(a);
   else

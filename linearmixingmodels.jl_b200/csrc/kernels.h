@@ -35,7 +35,7 @@ struct GemmArgs {
 };
 enum { GEMM_UPDATE = 0, GEMM_TRSM = 1 };
 cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch);
-void set_gemm_impl(int impl);  // 0: cp.async ring + CTA barrier; 1: TMA bulk + full/empty mbarrier ring (default)
+void set_gemm_impl(int impl);  // 0: cp.async ring + CTA barrier; 1/2: TMA bulk + full/empty mbarrier ring, 16/32-column stages (2 = default)
 
 // ---- potrf.cu : factor diagonal tile (J,J) in place, W(J) = inv(L_JJ), logdet += 2*sum(log diag)
 cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int batch, double* logdet,

@@ -228,7 +228,10 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
 
 cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int batch, double* logdet,
                               int* info) {
-  static bool configured = false;
+  static bool configured_dev[64] = {false};  // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
     if (e != cudaSuccess) return e;

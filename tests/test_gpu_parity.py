@@ -131,7 +131,7 @@ def test_oilmm_mid_size_multi_tile(lmm):
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
 
 
-@pytest.mark.parametrize("impl,streams,outer", [(0, 1, 8), (1, 1, 3), (0, 4, 16), (1, 8, 1)])
+@pytest.mark.parametrize("impl,streams,outer", [(0, 1, 8), (1, 1, 3), (0, 4, 16), (1, 8, 1), (2, 2, 8), (2, 1, 5)])
 def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer):
     """Both GEMM pipelines (cp.async ring / TMA bulk + mbarrier ring), any stream-group count and
     any outer block width give the same factor (N = 1100: 9 tile columns, batch 3)."""
