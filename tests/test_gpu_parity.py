@@ -152,7 +152,7 @@ def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer):
         np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
         np.testing.assert_allclose(V, Vr, rtol=RTOL)
     finally:
-        ctx.set_option("gemm_impl", 1)
+        ctx.set_option("gemm_impl", 2)
         ctx.set_option("streams", 4)
         ctx.set_option("outer_block", 8)
 
