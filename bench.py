@@ -250,11 +250,11 @@ def main():
     if rank == 0:
         sampler.start()
     l0, h0, d0 = ctx.counters()
-    ev_ms, chol_ms, kmat_ms, solve_ms = 0.0, 0.0, 0.0, 0.0
+    ev_ms, chol_ms, kmat_ms, solve_ms, proj_ms = 0.0, 0.0, 0.0, 0.0, 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         lp, tm = step(fx_dev, yd)
-        ev_ms += tm[0]; kmat_ms += tm[1]; chol_ms += tm[2]; solve_ms += tm[3]
+        ev_ms += tm[0]; kmat_ms += tm[1]; chol_ms += tm[2]; solve_ms += tm[3]; proj_ms += tm[4]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
@@ -299,7 +299,7 @@ def main():
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(p, N, mloc),
                      "peak_source": peak_src, "flops_per_rank_step": chol_flops,
                      "whole_eval_tflops": (m * (N ** 3 / 3.0 + 2.0 * N * N) + 4.0 * p * m * N) / (ms_per_step * 1e-3) / 1e12 / world},
-        "stage_ms_per_step": {"kmat": kmat_ms / K, "cholesky": chol_ms / K, "solves": solve_ms / K},
+        "stage_ms_per_step": {"stage_in+project": proj_ms / K, "kmat": kmat_ms / K, "cholesky": chol_ms / K, "solves": solve_ms / K},
         "logpdf": lp,
     }
     if world == 1 and not args.no_cpu_baseline:

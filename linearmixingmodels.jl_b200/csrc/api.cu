@@ -657,8 +657,9 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
   // ---- projection + residual (K2/K3)
   CU(b_ty.alloc(ctx, (size_t)(mloc > 0 ? mloc : 1) * npad * sizeof(double)));
   CU(cudaMemsetAsync(b_ty.p, 0, (size_t)(mloc > 0 ? mloc : 1) * npad * sizeof(double), st));
-  const int nblk = (N + 31) / 32;
+  const int nblk = (N + 15) / 16;
   CU(b_resid_part.alloc(ctx, (size_t)nblk * sizeof(double)));
+  CU(cudaMemsetAsync(b_resid_part.p, 0, (size_t)nblk * sizeof(double), st));
   CU(b_resid.alloc(ctx, sizeof(double)));
   CU(b_terms.alloc(ctx, (size_t)(m + 1) * sizeof(double)));
   CU(cudaMemsetAsync(b_terms.p, 0, (size_t)(m + 1) * sizeof(double), st));
