@@ -63,7 +63,52 @@ __device__ __forceinline__ void stage_points(double* xa, double* xb, double* sa,
   __syncthreads();
 }
 
+// One 128x128 tile of kernel values.  Thread t owns the fixed tile row r(t) and walks the columns
+// c = 4*it + 2*(t&1) + {0,1}: its own scaled point / squared norm are hoisted into registers, the
+// column points are shared-memory broadcasts, and each iteration ends in one coalesced 16-byte
+// store at tile offset e = it*512 + 2*t (the k4-interleaved layout makes e linear in (it, t)).
+// SYM: diagonal entries get d² = 0 exactly and + noise; padding is the identity (SYM) or zero.
+template <bool SYM, int DS>
+__device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const double* xa, const double* xb, const double* sa,
+                                               const double* sb, int D, int r0, int c0, int Na, int Nb, const LatentParams& lp, int form) {
+  const int t = threadIdx.x;
+  const int r = (((2 * t) >> 5) & 15) * 8 + (((2 * t) >> 2) & 7);
+  const int gr = r0 + r;
+  const int dd = DS > 0 ? DS : D;
+  const double* ar = xa + (size_t)r * dd;
+  const double sar = sa[r];
+  const double a0 = ar[0];
+  for (int it = 0; it < 32; ++it) {
+    const int c = 4 * it + ((2 * t) & 3);
+    double2 v;
+    double* vv = reinterpret_cast<double*>(&v);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int gc = c0 + c + q;
+      double val;
+      if (gr >= Na || gc >= Nb) {
+        val = (SYM && gr == gc) ? 1.0 : 0.0;
+      } else if (SYM && gr == gc) {
+        val = kappa_eval(lp.kind, lp.variance, 0.0) + lp.noise;
+      } else {
+        double d2;
+        if (DS == 1 && form == 0) {
+          const double tt = sar + sb[c + q];
+          d2 = fma(-2.0, a0 * xb[c + q], tt);
+          d2 = d2 > 0.0 ? d2 : 0.0;
+        } else {
+          d2 = sqdist(ar, xb + (size_t)(c + q) * dd, dd, sar, sb[c + q], form);
+        }
+        val = kappa_eval(lp.kind, lp.variance, d2);
+      }
+      vv[q] = val;
+    }
+    *reinterpret_cast<double2*>(tile + it * 512 + 2 * t) = v;
+  }
+}
+
 // grid: (lower tiles, batch).  Writes K_b + noise_b*I (identity on the padding) into L tiles.
+template <int DS>
 __global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const double* __restrict__ xpad, int N, int D,
                                                        const LatentParams* __restrict__ params, int form) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -83,34 +128,12 @@ __global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const doubl
   const LatentParams lp = params[b];
 
   stage_points(xa, xb, sa, sb, xpad + (size_t)I * TILE * D, xpad + (size_t)J * TILE * D, D, lp.inv_ls, &bar);
-
-  double* tile = out.tile(b, I, J);
-  const int r0 = I * TILE, c0 = J * TILE;
-  for (int e = 2 * threadIdx.x; e < TT; e += 2 * blockDim.x) {
-    int r, c;
-    tile_rc(e, r, c);  // (r, c) and (r, c+1)
-    double2 v;
-    double* vv = reinterpret_cast<double*>(&v);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int gr = r0 + r, gc = c0 + c + q;
-      double val;
-      if (gr >= N || gc >= N) {
-        val = (gr == gc) ? 1.0 : 0.0;
-      } else if (gr == gc) {
-        val = kappa_eval(lp.kind, lp.variance, 0.0) + lp.noise;
-      } else {
-        double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)(c + q) * D, D, sa[r], sb[c + q], form);
-        val = kappa_eval(lp.kind, lp.variance, d2);
-      }
-      vv[q] = val;
-    }
-    *reinterpret_cast<double2*>(tile + e) = v;
-  }
+  kmat_tile_body<true, DS>(out.tile(b, I, J), xa, xb, sa, sb, D, I * TILE, J * TILE, N, N, lp, form);
 }
 
 // grid: (ntr*ntc, batch).  Rows = points of xa_pad (e.g. x*), cols = points of xb_pad (train x).
 // Padding rows/cols are zero.
+template <int DS>
 __global__ void __launch_bounds__(256) kmat_cross_kernel(TiledRect out, const double* __restrict__ xa_pad, int Na,
                                                          const double* __restrict__ xb_pad, int Nb, int D,
                                                          const LatentParams* __restrict__ params, int form) {
@@ -125,26 +148,7 @@ __global__ void __launch_bounds__(256) kmat_cross_kernel(TiledRect out, const do
   const int R = blockIdx.x / out.ntc, J = blockIdx.x % out.ntc;
   const LatentParams lp = params[b];
   stage_points(xa, xb, sa, sb, xa_pad + (size_t)R * TILE * D, xb_pad + (size_t)J * TILE * D, D, lp.inv_ls, &bar);
-
-  double* tile = out.tile(b, R, J);
-  const int r0 = R * TILE, c0 = J * TILE;
-  for (int e = 2 * threadIdx.x; e < TT; e += 2 * blockDim.x) {
-    int r, c;
-    tile_rc(e, r, c);
-    double2 v;
-    double* vv = reinterpret_cast<double*>(&v);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int gr = r0 + r, gc = c0 + c + q;
-      double val = 0.0;
-      if (gr < Na && gc < Nb) {
-        double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)(c + q) * D, D, sa[r], sb[c + q], form);
-        val = kappa_eval(lp.kind, lp.variance, d2);
-      }
-      vv[q] = val;
-    }
-    *reinterpret_cast<double2*>(tile + e) = v;
-  }
+  kmat_tile_body<false, DS>(out.tile(b, R, J), xa, xb, sa, sb, D, R * TILE, J * TILE, Na, Nb, lp, form);
 }
 
 static size_t kmat_smem(int D) { return (size_t)(2 * TILE * D + 2 * TILE) * sizeof(double); }
@@ -153,11 +157,14 @@ cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const doub
                             const LatentParams* params, int form) {
   size_t sm = kmat_smem(D);
   if (sm > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kmat_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaError_t e = cudaFuncSetAttribute(kmat_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
   }
   dim3 grid((unsigned)sym_tiles(out.nt), (unsigned)batch);
-  kmat_sym_kernel<<<grid, 256, sm, st>>>(out, xpad, N, D, params, form);
+  if (D == 1)
+    kmat_sym_kernel<1><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form);
+  else
+    kmat_sym_kernel<0><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form);
   return cudaGetLastError();
 }
 
@@ -165,11 +172,14 @@ cudaError_t launch_kmat_cross(cudaStream_t st, TiledRect out, int batch, const d
                               int Nb, int D, const LatentParams* params, int form) {
   size_t sm = kmat_smem(D);
   if (sm > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kmat_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaError_t e = cudaFuncSetAttribute(kmat_cross_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
   }
   dim3 grid((unsigned)(out.ntr * out.ntc), (unsigned)batch);
-  kmat_cross_kernel<<<grid, 256, sm, st>>>(out, xa_pad, Na, xb_pad, Nb, D, params, form);
+  if (D == 1)
+    kmat_cross_kernel<1><<<grid, 256, sm, st>>>(out, xa_pad, Na, xb_pad, Nb, D, params, form);
+  else
+    kmat_cross_kernel<0><<<grid, 256, sm, st>>>(out, xa_pad, Na, xb_pad, Nb, D, params, form);
   return cudaGetLastError();
 }
 
