@@ -141,6 +141,11 @@ int lmm_post_mean_and_cov(lmm_post* post, const double* xs, int Ns, double sigma
 int lmm_prior_mean_and_cov(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* xs, int Ns,
                            int D, const double* H, int p, double sigma2, double latent_jitter,
                            int out_dim, double* mean, double* cov);
+/* posterior(post(x2, σ²), y2): sequential conditioning of an OILMM / IndependentMOGP posterior
+ * (src/oilmm.jl:116-134 / src/independent_mogp.jl:119-126 with PosteriorGP latents).  Returns a new
+ * handle over the union of the inputs; the old handle stays valid. */
+int lmm_post_condition(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys,
+                       lmm_post** out_post, int* info_latent);
 /* logpdf(post(x*, σ²), y*)  (test/oilmm.jl:84): OILMM logpdf with PosteriorGP latents. */
 int lmm_post_logpdf(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys,
                     double* out_logpdf, int* info_latent);

@@ -577,8 +577,6 @@ def posterior(fx: FiniteGP, y, with_logpdf: bool = False):
     f = fx.f
     ctx = _ctx_of(fx)
     lib = ctx.lib
-    if _post_owner(fx) is not None:
-        raise NotImplementedError("conditioning a posterior again (sequential conditioning) is a SURVEY §8f item")
     _require_by_outputs(fx)
     pts = _points(fx.x.x)
     N, D = int(pts.shape[0]), int(pts.shape[1])
@@ -586,6 +584,22 @@ def posterior(fx: FiniteGP, y, with_logpdf: bool = False):
     out = C.c_double()
     il = C.c_int(-1)
     lp = C.byref(out) if with_logpdf else None
+    owner0 = _post_owner(fx)
+    if owner0 is not None:
+        # sequential conditioning: posterior(post(x2, σ²), y2)
+        if isinstance(f, ILMM) and f.H.shape[0] != fx.x.out_dim:
+            raise RuntimeError("out dim of x != out dim of f.")
+        lat = f.f if isinstance(f, ILMM) else f
+        if not isinstance(lat, IndependentMOGP):
+            raise NotImplementedError("sequential conditioning of a general-ILMM posterior is not built")
+        yv = _yvec(y, N * fx.x.out_dim)
+        logp = logpdf(fx, y) if with_logpdf else None
+        rc = lib.lmm_post_condition(owner0.handle, ptr(pts), N, fx.sigma2, ptr(yv), C.byref(h), C.byref(il))
+        ctx.check(rc, il.value)
+        owner = _PostHandle(ctx, h, owner0.N + N)
+        newlat = IndependentMOGP([PosteriorGP(owner, i, g.prior) for i, g in enumerate(lat.fs)])
+        post = ILMM(newlat, f.H) if isinstance(f, ILMM) else newlat
+        return (post, logp) if with_logpdf else post
     if isinstance(f, ILMM):
         lat, H, s2, _ = unpack(fx)
         if not isinstance(lat, IndependentMOGP):

@@ -63,6 +63,7 @@ struct lmm_ctx {
   std::string err;
   int distance_form = 0;
   int outer_block = 8;
+  bool outer_block_user = false;
   int nranks = 1, rank = 0;
   void* comm = nullptr;
   int64_t launches = 0, h2d = 0, d2h = 0;
@@ -238,7 +239,9 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
 // update stream concurrently with the latency-bound panel steps of block b-1 on the high-priority
 // panel stream; part B (the columns of block b-1) follows on the panel stream.
 cudaError_t chol_factor_lookahead(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
-  const int nt = L.nt, ob = ctx->outer_block;
+  const int nt = L.nt;
+  // the panel chain is the critical path here: narrower blocks for smaller matrices (measured)
+  const int ob = ctx->outer_block_user ? ctx->outer_block : (nt <= 40 ? 3 : nt <= 96 ? 6 : 8);
   const int nblk = (nt + ob - 1) / ob;
   cudaError_t e;
   while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
@@ -302,7 +305,7 @@ cudaError_t chol_factor_lookahead(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
 // Fork the batch into latent groups on separate streams (joined back into ctx->stream).
 cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
   const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
-  if (ctx->lookahead && batch <= 2 && L.nt > 2 * ctx->outer_block) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
+  if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
   if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info);
   cudaError_t e;
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
@@ -410,6 +413,7 @@ struct lmm_post {
   double* d_delta = nullptr; // [batch][Npad]
   LatentParams* d_params = nullptr;
   double* d_H = nullptr;
+  double* d_noise_vec = nullptr;  // [nloc][Npad] per-point training noise (sequentially conditioned posteriors), else null
   size_t bytes = 0;
   int big_n = 0, big_nt = 0;  // ILMM joint dimension mN and its tile count
 
@@ -488,6 +492,7 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "outer_block") {
     if (value < 1 || value > 64) return ctx->fail(LMM_E_ARG, "outer_block must be in [1, 64]");
     ctx->outer_block = (int)value;
+    ctx->outer_block_user = true;
   } else if (k == "streams") {
     if (value < 1 || value > lmm_ctx::MAX_GROUPS) return ctx->fail(LMM_E_ARG, "streams must be in [1, 8]");
     ctx->ngroups = (int)value;
@@ -911,7 +916,7 @@ extern "C" int lmm_post_free(lmm_post* post) {
   lmm_ctx* ctx = post->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {post->d_xpad, post->d_L, post->d_W, post->d_alpha, post->d_delta, post->d_params, post->d_H};
+  void* ptrs[] = {post->d_xpad, post->d_L, post->d_W, post->d_alpha, post->d_delta, post->d_params, post->d_H, post->d_noise_vec};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, ctx->stream);
   cudaStreamSynchronize(ctx->stream);

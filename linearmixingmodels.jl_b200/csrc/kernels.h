@@ -6,8 +6,9 @@
 namespace lmm {
 
 // ---- kmat.cu
+// noise_vec (nullable): per-point diagonal noise [batch][noise_stride] overriding params[b].noise
 cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const double* xpad, int N, int D,
-                            const LatentParams* params, int form);
+                            const LatentParams* params, int form, const double* noise_vec = nullptr, size_t noise_stride = 0);
 cudaError_t launch_kmat_cross(cudaStream_t st, TiledRect out, int batch, const double* xa_pad, int Na, const double* xb_pad,
                               int Nb, int D, const LatentParams* params, int form);
 

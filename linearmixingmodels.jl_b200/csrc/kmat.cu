@@ -70,7 +70,8 @@ __device__ __forceinline__ void stage_points(double* xa, double* xb, double* sa,
 // SYM: diagonal entries get d² = 0 exactly and + noise; padding is the identity (SYM) or zero.
 template <bool SYM, int DS>
 __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const double* xa, const double* xb, const double* sa,
-                                               const double* sb, int D, int r0, int c0, int Na, int Nb, const LatentParams& lp, int form) {
+                                               const double* sb, int D, int r0, int c0, int Na, int Nb, const LatentParams& lp, int form,
+                                               const double* __restrict__ noise_vec = nullptr) {
   const int t = threadIdx.x;
   const int r = (((2 * t) >> 5) & 15) * 8 + (((2 * t) >> 2) & 7);
   const int gr = r0 + r;
@@ -89,7 +90,7 @@ __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const 
       if (gr >= Na || gc >= Nb) {
         val = (SYM && gr == gc) ? 1.0 : 0.0;
       } else if (SYM && gr == gc) {
-        val = kappa_eval(lp.kind, lp.variance, 0.0) + lp.noise;
+        val = kappa_eval(lp.kind, lp.variance, 0.0) + (noise_vec ? noise_vec[gr] : lp.noise);
       } else {
         double d2;
         if (DS == 1 && form == 0) {
@@ -110,7 +111,8 @@ __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const 
 // grid: (lower tiles, batch).  Writes K_b + noise_b*I (identity on the padding) into L tiles.
 template <int DS>
 __global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const double* __restrict__ xpad, int N, int D,
-                                                       const LatentParams* __restrict__ params, int form) {
+                                                       const LatentParams* __restrict__ params, int form,
+                                                       const double* __restrict__ noise_vec, size_t noise_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* xa = reinterpret_cast<double*>(smem_raw);
   double* xb = xa + TILE * D;
@@ -128,7 +130,8 @@ __global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const doubl
   const LatentParams lp = params[b];
 
   stage_points(xa, xb, sa, sb, xpad + (size_t)I * TILE * D, xpad + (size_t)J * TILE * D, D, lp.inv_ls, &bar);
-  kmat_tile_body<true, DS>(out.tile(b, I, J), xa, xb, sa, sb, D, I * TILE, J * TILE, N, N, lp, form);
+  kmat_tile_body<true, DS>(out.tile(b, I, J), xa, xb, sa, sb, D, I * TILE, J * TILE, N, N, lp, form,
+                           noise_vec ? noise_vec + (size_t)b * noise_stride : nullptr);
 }
 
 // grid: (ntr*ntc, batch).  Rows = points of xa_pad (e.g. x*), cols = points of xb_pad (train x).
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(256) kmat_cross_kernel(TiledRect out, const do
 static size_t kmat_smem(int D) { return (size_t)(2 * TILE * D + 2 * TILE) * sizeof(double); }
 
 cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const double* xpad, int N, int D,
-                            const LatentParams* params, int form) {
+                            const LatentParams* params, int form, const double* noise_vec, size_t noise_stride) {
   size_t sm = kmat_smem(D);
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kmat_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -162,9 +165,9 @@ cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const doub
   }
   dim3 grid((unsigned)sym_tiles(out.nt), (unsigned)batch);
   if (D == 1)
-    kmat_sym_kernel<1><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form);
+    kmat_sym_kernel<1><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form, noise_vec, noise_stride);
   else
-    kmat_sym_kernel<0><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form);
+    kmat_sym_kernel<0><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form, noise_vec, noise_stride);
   return cudaGetLastError();
 }
 

@@ -199,6 +199,27 @@ def gp_cov(f, xs) -> np.ndarray:
     return kernelmatrix(f.kernel, xs)
 
 
+def gp_cross_cov(f, xa, xb) -> np.ndarray:
+    """AbstractGPs ``cov(f, x, x')``: prior kernel matrix, or K(x,x') - V_x' V_x' for a PosteriorGP."""
+    if isinstance(f, PosteriorGP):
+        Va = _fwd(f.L, kernelmatrix(f.prior.kernel, f.x, xa, form=f.form))
+        Vb = _fwd(f.L, kernelmatrix(f.prior.kernel, f.x, xb, form=f.form))
+        return kernelmatrix(f.prior.kernel, xa, xb, form=f.form) - Va.T @ Vb
+    return kernelmatrix(f.kernel, xa, xb)
+
+
+def gp_condition_again_marginals(post: "PosteriorGP", x2, noise2: float, y2: np.ndarray, xt) -> Tuple[np.ndarray, np.ndarray]:
+    """Marginals at xt of ``posterior(post(x2, noise2), y2)`` by the textbook Gaussian update applied
+    to the FIRST posterior (independent of the union-of-data route the library takes)."""
+    C22 = gp_cov(post, x2)
+    C22[np.diag_indices_from(C22)] += noise2
+    L = _chol_lower(C22)
+    Ct2 = gp_cross_cov(post, xt, x2)
+    a = _bwd(L, _fwd(L, np.asarray(y2, dtype=np.float64) - gp_mean(post, x2)))
+    V = _fwd(L, Ct2.T)
+    return gp_mean(post, xt) + Ct2 @ a, gp_var(post, xt) - np.sum(V * V, axis=0)
+
+
 def finite_marginals(f, xs, noise: float = 1e-18) -> Tuple[np.ndarray, np.ndarray]:
     """``mean_and_var(f(x, σ²))`` = (m(x), diag K + σ²); default FiniteGP noise is 1e-18."""
     return gp_mean(f, xs), gp_var(f, xs) + noise

@@ -406,3 +406,57 @@ def test_ilmm_posterior_rand_and_logpdf(lmm):
     np.testing.assert_allclose(s, o.ilmm_post_rand(opost, xs, 0.1, zl, zn), rtol=1e-6, atol=1e-7)
     ys = rng.standard_normal(p * Ns)
     assert rel(lmm.logpdf(pfx, ys), o.ilmm_post_logpdf(opost, xs, 0.1, ys)) < RTOL
+
+
+def test_sequential_conditioning(lmm):
+    """posterior(post(x2, σ²), y2): OILMM and IndependentMOGP posteriors conditioned a
+    second (and third) time agree with the textbook update of the first posterior, and with
+    conditioning once on all the data."""
+    rng = np.random.default_rng(17)
+    N1, N2, N3, Nt, p, m = 90, 37, 5, 11, 4, 2
+    x1, x2, x3 = np.sort(rng.uniform(0, 6, N1)), rng.uniform(0, 6, N2), rng.uniform(0, 6, N3)
+    xt = rng.uniform(0, 6, Nt)
+    U, S = o.orthogonal_from_seed(p, m, seed=6)
+    fs = [o.GP(o.Kernel(o.SE, 1.0, 1.2), 0.2), o.GP(o.Kernel(o.MATERN52, 0.6, 0.9), -0.4)]
+    om = o.OILMMModel(fs, U, S)
+    y1, y2, y3 = rng.standard_normal(p * N1), rng.standard_normal(p * N2), rng.standard_normal(p * N3)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    mo = lambda x: lmm.MOInputIsotopicByOutputs(x, p)
+    post1 = lmm.posterior(f(mo(x1), 0.1), y1)
+    post2 = lmm.posterior(post1(mo(x2), 0.3), y2)
+    assert isinstance(post2, lmm.OILMM)
+    M, V = lmm.mean_and_var(post2(mo(xt), 0.1))
+    # oracle: latent-wise textbook update of the first posterior, then the OILMM mixing
+    op1 = o.oilmm_posterior(om, x1, 0.1, y1)
+    T, ST2 = o.project_orthogonal(U, S, 0.3)
+    Ty2 = T @ o.reshape_y(y2, N2)
+    ML, VL = zip(*[o.gp_condition_again_marginals(op1.fs[i], x2, ST2[i], Ty2[i], xt) for i in range(m)])
+    H = om.H
+    Mr = (H @ np.stack(ML)).reshape(-1)
+    Vr = ((H * H) @ (np.stack(VL) + 1e-18) + 0.1).reshape(-1)
+    np.testing.assert_allclose(M, Mr, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(V, Vr, rtol=1e-8)
+    # same noise both times == conditioning once on the union (by-outputs concatenation per output)
+    post2b = lmm.posterior(post1(mo(x2), 0.1), y2)
+    xu = np.concatenate([x1, x2])
+    yu = np.concatenate([np.concatenate([y1.reshape(p, N1)[j], y2.reshape(p, N2)[j]]) for j in range(p)])
+    postu = lmm.posterior(f(mo(xu), 0.1), yu)
+    Ma, Va = lmm.mean_and_var(post2b(mo(xt), 0.1))
+    Mb, Vb = lmm.mean_and_var(postu(mo(xt), 0.1))
+    np.testing.assert_allclose(Ma, Mb, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(Va, Vb, rtol=1e-9)
+    # a third conditioning step keeps the per-point noise of the first two
+    post3 = lmm.posterior(post2(mo(x3), 0.05), y3)
+    M3, V3 = lmm.mean_and_var(post3(mo(xt), 0.1))
+    assert M3.shape == (p * Nt,) and np.all(V3 > 0.1) and np.all(V3 <= V + 1e-12)
+    # IndependentMOGP
+    fm = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    ya, yb = rng.standard_normal(m * N1), rng.standard_normal(m * N2)
+    pa = lmm.posterior(fm(lmm.MOInputIsotopicByOutputs(x1, m), 0.1), ya)
+    pb = lmm.posterior(pa(lmm.MOInputIsotopicByOutputs(x2, m), 0.2), yb)
+    Mi, Vi = lmm.mean_and_var(pb(lmm.MOInputIsotopicByOutputs(xt, m), 0.1))
+    oa = o.imogp_posterior(fs, x1, 0.1, ya)
+    for i in range(m):
+        mr, vr = o.gp_condition_again_marginals(oa[i], x2, 0.2, yb.reshape(m, N2)[i], xt)
+        np.testing.assert_allclose(Mi[i * Nt:(i + 1) * Nt], mr, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(Vi[i * Nt:(i + 1) * Nt], vr + 0.1, rtol=1e-8)
