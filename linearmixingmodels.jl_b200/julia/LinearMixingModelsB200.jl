@@ -186,6 +186,58 @@ function AbstractGPs.logpdf(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOI
     return out[]
 end
 
+# --- mean_and_cov / cov(post(x*, σ²))   replaces src/ilmm.jl:132-139,147 on posterior latents -----
+function AbstractGPs.mean_and_cov(fx::FiniteGP{<:PosteriorOILMM})
+    fs, H, σ², x = unpack(fx)
+    X, _ = points(x)
+    n = length(x) * fx.x.out_dim
+    M = Vector{Float64}(undef, n); C = Matrix{Float64}(undef, n, n)
+    check(ccall((:lmm_post_mean_and_cov, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Ptr{Float64}),
+        fs.fs[1].owner.handle, X, length(x), Float64(σ²), M, C))
+    return M, C
+end
+AbstractGPs.cov(fx::FiniteGP{<:PosteriorOILMM}) = mean_and_cov(fx)[2]
+
+# --- mean_and_cov on prior latents (OILMM and general ILMM): H passed explicitly -------------------
+function AbstractGPs.mean_and_cov(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    Hm = Matrix{Float64}(collect(H))            # U*sqrt(S) for an Orthogonal
+    n = length(x) * fx.x.out_dim
+    M = Vector{Float64}(undef, n); C = Matrix{Float64}(undef, n, n)
+    check(ccall((:lmm_prior_mean_and_cov, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Float64, Cint, Ptr{Float64}, Ptr{Float64}),
+        ctx(), descs, length(descs), X, length(x), D, Hm, size(Hm, 1), Float64(σ²), 1e-18, fx.x.out_dim, M, C))
+    return M, C
+end
+
+# --- posterior(post(x2, σ²), y2): sequential conditioning ------------------------------------------
+function AbstractGPs.posterior(fx::FiniteGP{<:PosteriorOILMM}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, _ = points(x)
+    h = Ref{Ptr{Cvoid}}(C_NULL); il = Ref{Cint}(-1)
+    check(ccall((:lmm_post_condition, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Ptr{Ptr{Cvoid}}, Ptr{Cint}),
+        fs.fs[1].owner.handle, X, length(x), Float64(σ²), Vector{Float64}(y), h, il))
+    owner = DevicePosterior(h[])
+    return ILMM(IndependentMOGP([DeviceLatentPosterior(owner, f.index, f.prior) for f in fs.fs]), H)
+end
+
+# --- rand(rng, post(x*, σ²)) ------------------------------------------------------------------------
+function AbstractGPs.rand(rng::AbstractRNG, fx::FiniteGP{<:PosteriorOILMM})
+    fs, H, σ², x = unpack(fx)
+    X, _ = points(x)
+    m, p, N = length(fs.fs), size(H, 1), length(x)
+    zl = randn(rng, N * m); zn = randn(rng, N * p)
+    out = Vector{Float64}(undef, N * p); il = Ref{Cint}(-1)
+    check(ccall((:lmm_post_rand, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        fs.fs[1].owner.handle, X, N, Float64(σ²), zl, zn, out, il))
+    return out
+end
+
 # PosteriorGP field access (α, C, δ) for one latent -- `lmm_post_export`
 function export_latent(f::DeviceLatentPosterior, N::Int)
     L = Matrix{Float64}(undef, N, N); α = Vector{Float64}(undef, N); δ = Vector{Float64}(undef, N)

@@ -1,0 +1,60 @@
+"""Golden vectors (tests/golden/c1_oilmm.npz, made by tests/golden/make_golden.py from the oracle
+with an extended-precision cross-check): the oracle must keep reproducing them (CPU), and the CUDA
+path must match them (GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lmm_oracle as o
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_oilmm.npz"))
+FS = [o.GP(o.Kernel(o.SE)), o.GP(o.Kernel(o.MATERN32))]
+FS_I = [o.GP(o.Kernel(o.MATERN32), 30.0), o.GP(o.Kernel(o.SE, 0.5), 10.0)]
+
+
+def test_oracle_reproduces_golden():
+    model = o.OILMMModel(FS, G["U"], G["S"])
+    terms, reg = o.oilmm_logpdf_terms(model, G["x"], 0.1, G["y"])
+    np.testing.assert_allclose(terms, G["lml_terms"], rtol=1e-13)
+    assert float(np.sum(terms) + reg) == pytest.approx(float(G["logpdf"]), rel=1e-13)
+    assert float(G["logpdf"]) == pytest.approx(float(G["logpdf_longdouble"]), rel=1e-11)
+    post = o.oilmm_posterior(model, G["x"], 0.1, G["y"])
+    M, V = o.oilmm_mean_and_var(post, G["xs"], 0.1)
+    np.testing.assert_allclose(M, G["post_mean"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(V, G["post_var"], rtol=1e-11)
+    assert o.oilmm_logpdf(post, G["xs"], 0.1, G["ys"]) == pytest.approx(float(G["post_logpdf"]), rel=1e-12)
+    assert o.imogp_logpdf(FS_I, G["x"], 0.1, G["imogp_y"]) == pytest.approx(float(G["imogp_logpdf"]), rel=1e-13)
+    assert o.ilmm_logpdf(FS, G["ilmm_H"], G["x"], 0.1, G["y"]) == pytest.approx(float(G["ilmm_logpdf"]), rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_golden():
+    import lmm_b200 as lmm
+
+    p = 3
+    mo = lambda x, q=p: lmm.MOInputIsotopicByOutputs(x, q)
+    gps = [lmm.GP(lmm.SEKernel()), lmm.GP(lmm.Matern32Kernel())]
+    f = lmm.ILMM(lmm.independent_mogp(gps), lmm.Orthogonal(G["U"], G["S"]))
+    fx = f(mo(G["x"]), 0.1)
+    terms = lmm.logpdf_terms(fx, G["y"])
+    np.testing.assert_allclose(terms[:2], G["lml_terms"], rtol=1e-9)
+    assert abs(lmm.logpdf(fx, G["y"]) - float(G["logpdf"])) <= 1e-9 * abs(float(G["logpdf"]))
+    post = lmm.posterior(fx, G["y"])
+    M, V = lmm.mean_and_var(post(mo(G["xs"]), 0.1))
+    np.testing.assert_allclose(M, G["post_mean"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(V, G["post_var"], rtol=1e-9)
+    got = lmm.logpdf(post(mo(G["xs"]), 0.1), G["ys"])
+    assert abs(got - float(G["post_logpdf"])) <= 1e-9 * abs(float(G["post_logpdf"]))
+    fi = lmm.independent_mogp([lmm.GP(30.0, lmm.Matern32Kernel()), lmm.GP(10.0, 0.5 * lmm.SEKernel())])
+    fxi = fi(mo(G["x"], 2), 0.1)
+    assert abs(lmm.logpdf(fxi, G["imogp_y"]) - float(G["imogp_logpdf"])) <= 1e-9 * abs(float(G["imogp_logpdf"]))
+    Mi, Vi = lmm.mean_and_var(lmm.posterior(fxi, G["imogp_y"])(mo(G["xs"], 2), 0.1))
+    np.testing.assert_allclose(Mi, G["imogp_post_mean"], rtol=1e-9)
+    np.testing.assert_allclose(Vi, G["imogp_post_var"], rtol=1e-9)
+    fg = lmm.ILMM(lmm.independent_mogp(gps), G["ilmm_H"])
+    fxg = fg(mo(G["x"]), 0.1)
+    assert abs(lmm.logpdf(fxg, G["y"]) - float(G["ilmm_logpdf"])) <= 1e-9 * abs(float(G["ilmm_logpdf"]))
+    Mg, Vg = lmm.mean_and_var(lmm.posterior(fxg, G["y"])(mo(G["xs"]), 0.1))
+    np.testing.assert_allclose(Mg, G["ilmm_post_mean"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(Vg, G["ilmm_post_var"], rtol=1e-9)
