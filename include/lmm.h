@@ -125,6 +125,19 @@ int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, cons
                            const double* y, int out_dim, const double* inv_lengthscale_scales,
                            int n_sweep, double* out_logpdfs, int* info_latent);
 
+/* rrule of logpdf (`Zygote.gradient(logpdf, fx, y)` at test/oilmm.jl:31-32,
+ * test/independent_mogp.jl:65-66 needs a ChainRulesCore.rrule around the opaque ccall): value and
+ * gradients w.r.t. each latent's (variance, inv_lengthscale, mean_const) -- grad_latents is m x 3
+ * row-major --, the observation noise σ² and, optionally, y (p*N by outputs).  All outputs nullable.
+ * G_i = (α_i α_i' - C_i^{-1})/2 comes from a batched potri on the tensor pipe. */
+int lmm_oilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N,
+                          int D, const double* U, const double* S, int p, double sigma2,
+                          const double* y, int out_dim, double* out_logpdf, double* grad_latents,
+                          double* grad_sigma2, double* grad_y, int* info_latent);
+int lmm_imogp_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
+                          double sigma2, const double* y, int out_dim, double* out_logpdf,
+                          double* grad_latents, double* grad_sigma2, double* grad_y, int* info_latent);
+
 /* ---- posterior handle: the OILMM/ILMM/IndependentMOGP whose latents are PosteriorGPs -------- */
 /* mean_and_var(post(x*, σ²))  src/oilmm.jl:57-76 on PosteriorGP latents (AbstractGPs posterior
  * mean/var); for an IndependentMOGP posterior: src/independent_mogp.jl:50-57; ILMM: src/ilmm.jl:122-129. */

@@ -788,6 +788,39 @@ def _rand_one(rng, fx: FiniteGP) -> np.ndarray:
     raise TypeError(f"rand not defined for FiniteGP of {type(f).__name__}")
 
 
+def logpdf_and_gradient(fx: FiniteGP, y, with_grad_y: bool = False):
+    """Value and gradient of `logpdf(fx, y)` for an OILMM or IndependentMOGP prior -- the pullback a
+    ChainRulesCore `rrule` around the ccall returns (test/oilmm.jl:31-32 `gradient(logpdf, fx, y)`).
+    Returns (logpdf, grads) with grads = {"variance": (m,), "inv_lengthscale": (m,), "mean_const": (m,),
+    "sigma2": float[, "y": (p*N,)]}."""
+    f = fx.f
+    ctx = _ctx_of(fx)
+    _require_by_outputs(fx)
+    pts = _points(fx.x.x)
+    N, D = int(pts.shape[0]), int(pts.shape[1])
+    out, gs2, il = C.c_double(), C.c_double(), C.c_int(-1)
+    yv = _yvec(y, N * fx.x.out_dim)
+    gy = np.zeros(N * fx.x.out_dim) if with_grad_y else None
+    if isinstance(f, ILMM) and isinstance(f.H, Orthogonal) and isinstance(f.f, IndependentMOGP):
+        lat, H = f.f, f.H
+        m = len(lat.fs)
+        gl = np.zeros((m, 3))
+        rc = ctx.lib.lmm_oilmm_logpdf_grad(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H.U), ptr(H.S), H.shape[0], fx.sigma2, ptr(yv),
+                                           fx.x.out_dim, C.byref(out), ptr(gl), C.byref(gs2), ptr(gy), C.byref(il))
+    elif isinstance(f, IndependentMOGP):
+        m = len(f.fs)
+        gl = np.zeros((m, 3))
+        rc = ctx.lib.lmm_imogp_logpdf_grad(ctx.handle, _descs(f.fs), m, ptr(pts), N, D, fx.sigma2, ptr(yv), fx.x.out_dim, C.byref(out),
+                                           ptr(gl), C.byref(gs2), ptr(gy), C.byref(il))
+    else:
+        raise TypeError("logpdf_and_gradient is built for OILMM and IndependentMOGP priors")
+    ctx.check(rc, il.value)
+    grads = {"variance": gl[:, 0].copy(), "inv_lengthscale": gl[:, 1].copy(), "mean_const": gl[:, 2].copy(), "sigma2": gs2.value}
+    if with_grad_y:
+        grads["y"] = gy
+    return out.value, grads
+
+
 def logpdf_sweep(fx: FiniteGP, y, inv_lengthscale_scales) -> np.ndarray:
     """BASELINE config 5: OILMM logpdf for a batch of lengthscale settings in one call."""
     lat, H, s2, _ = unpack(fx)

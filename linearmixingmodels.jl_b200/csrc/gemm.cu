@@ -41,15 +41,18 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel(GemmArgs g) {
   extern __shared__ __align__(128) double smem[];
   const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
   if (g.sym && I < J) return;
+  if (g.upper && I > J) return;
+  const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;  // first k-tile of this CTA
+  if (MODE == GEMM_UPDATE && kb >= g.k1) return;
 
   double* Ctile = g.C.tile(b, I, J);
   const double* Asrc;
   const double* Bsrc;
   int nchunks;
   if (MODE == GEMM_UPDATE) {
-    Asrc = g.A.tile(b, I, g.k0);
-    Bsrc = g.B.tile(b, J, g.k0);
-    nchunks = (g.k1 - g.k0) * 8;
+    Asrc = g.A.tile(b, I, kb);
+    Bsrc = g.B.tile(b, J, kb);
+    nchunks = (g.k1 - kb) * 8;
   } else {
     Asrc = Ctile;
     Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
@@ -180,15 +183,18 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   uint64_t* empty = full + V2_STAGES;
   const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
   if (g.sym && I < J) return;
+  if (g.upper && I > J) return;
+  const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;  // first k-tile of this CTA
+  if (MODE == GEMM_UPDATE && kb >= g.k1) return;
 
   double* Ctile = g.C.tile(b, I, J);
   const double* Asrc;
   const double* Bsrc;
   int nchunks;
   if (MODE == GEMM_UPDATE) {
-    Asrc = g.A.tile(b, I, g.k0);
-    Bsrc = g.B.tile(b, J, g.k0);
-    nchunks = (g.k1 - g.k0) * (128 / KC);
+    Asrc = g.A.tile(b, I, kb);
+    Bsrc = g.B.tile(b, J, kb);
+    nchunks = (g.k1 - kb) * (128 / KC);
   } else {
     Asrc = Ctile;
     Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;

@@ -1,0 +1,173 @@
+// Fused kernel-gradient reduction for the logpdf rrule (reference call sites
+// test/oilmm.jl:31-32, test/ilmm.jl:31-32, test/independent_mogp.jl:65-66 `gradient(logpdf, fx, y)`).
+// With G = d lml / dC = (αα' - C^{-1})/2 the hyper-parameter gradients of one latent are
+//   d/d variance = <G, κ>,  d/d inv_lengthscale = <G, dK/ds>,  d/d noise = tr(G),
+// contracted tile by tile: the kernel values and their lengthscale derivatives are recomputed in
+// registers from the staged inputs (never stored), NegCinv = -C^{-1} comes from the batched
+// `potri` (triangular TRSM sweep + SYRK on the DMMA kernel).  HBM-bound: one read of C^{-1}.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace lmm {
+
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// κ and dK/ds (both already multiplied by the variance where appropriate): returns κ (unscaled by variance)
+__device__ __forceinline__ void kappa_and_ds(int kind, double d2, double inv_ls, double& kap, double& dkds) {
+  if (kind == 0) {
+    if (d2 > 1500.0) { kap = 0.0; dkds = 0.0; return; }
+    kap = exp(-d2 / 2.0);
+    dkds = -kap * d2 / inv_ls;
+  } else {
+    const double d = sqrt(d2);
+    if (kind == 1) {
+      const double s = 1.7320508075688772 * d;
+      if (s > 800.0) { kap = 0.0; dkds = 0.0; return; }
+      const double e = exp(-s);
+      kap = (1.0 + s) * e;
+      dkds = -3.0 * d2 * e / inv_ls;
+    } else {
+      const double s = 2.23606797749979 * d;
+      if (s > 800.0) { kap = 0.0; dkds = 0.0; return; }
+      const double e = exp(-s);
+      kap = (1.0 + s + 5.0 * (d * d) / 3.0) * e;
+      dkds = -(5.0 / 3.0) * d2 * (1.0 + s) * e / inv_ls;
+    }
+  }
+}
+
+// grid (lower tiles, batch).  partial[(b*ntiles + tile)*3 + {0,1,2}] = {<G,κ>, <G,dK/ds>/variance.., tr G}
+__global__ void __launch_bounds__(256) kgrad_kernel(TiledSym negCinv, const double* __restrict__ xpad, int N, int D,
+                                                    const LatentParams* __restrict__ params, const double* __restrict__ alpha,
+                                                    size_t alpha_stride, int form, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double sm[];
+  double* xa = sm;                 // [128*D] scaled
+  double* xb = xa + TILE * D;
+  double* sa = xb + TILE * D;
+  double* sb = sa + TILE;
+  double* aa = sb + TILE;          // alpha rows
+  double* ab = aa + TILE;          // alpha cols
+  __shared__ double red[3][256];
+
+  const int b = blockIdx.y, tl = blockIdx.x, t = threadIdx.x;
+  int I = (int)((sqrt(8.0 * (double)tl + 1.0) - 1.0) * 0.5);
+  while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tl) ++I;
+  while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
+  const int J = tl - (int)((size_t)I * (I + 1) / 2);
+  const LatentParams lp = params[b];
+  for (int i = t; i < TILE * D; i += 256) {
+    xa[i] = xpad[(size_t)I * TILE * D + i] * lp.inv_ls;
+    xb[i] = xpad[(size_t)J * TILE * D + i] * lp.inv_ls;
+  }
+  if (t < TILE) {
+    aa[t] = alpha[(size_t)b * alpha_stride + I * TILE + t];
+    ab[t] = alpha[(size_t)b * alpha_stride + J * TILE + t];
+  }
+  __syncthreads();
+  for (int i = t; i < 2 * TILE; i += 256) {
+    const double* v = (i < TILE) ? xa + (size_t)i * D : xb + (size_t)(i - TILE) * D;
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) s = fma(v[k], v[k], s);
+    if (i < TILE) sa[i] = s; else sb[i - TILE] = s;
+  }
+  __syncthreads();
+
+  const double* tile = negCinv.tile(b, I, J);
+  const int r = (((2 * t) >> 5) & 15) * 8 + (((2 * t) >> 2) & 7);
+  const int gr = I * TILE + r;
+  double gv = 0.0, gs = 0.0, gn = 0.0;
+  for (int it = 0; it < 32; ++it) {
+    const int c = 4 * it + ((2 * t) & 3);
+    const double2 nc = *reinterpret_cast<const double2*>(tile + it * 512 + 2 * t);
+    const double ncv[2] = {nc.x, nc.y};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int cc = c + q, gc = J * TILE + cc;
+      if (gr >= N || gc >= N) continue;
+      if (I == J && cc > r) continue;  // lower triangle only; off-diagonal entries count twice
+      const double G = 0.5 * (aa[r] * ab[cc] + ncv[q]);
+      if (gr == gc) {
+        gn += G;
+        gv = fma(G, 1.0, gv);  // κ(0) = 1, dK/ds = 0 on the diagonal
+      } else {
+        const double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)cc * D, D, sa[r], sb[cc], form);
+        double kap, dk;
+        kappa_and_ds(lp.kind, d2, lp.inv_ls, kap, dk);
+        gv = fma(2.0 * G, kap, gv);
+        gs = fma(2.0 * G, dk, gs);
+      }
+    }
+  }
+  red[0][t] = gv; red[1][t] = gs; red[2][t] = gn;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) {
+      red[0][t] += red[0][t + w];
+      red[1][t] += red[1][t + w];
+      red[2][t] += red[2][t + w];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    double* out = partial + ((size_t)b * gridDim.x + tl) * 3;
+    out[0] = red[0][0];
+    out[1] = red[1][0] * lp.variance;  // dK/ds carries the variance
+    out[2] = red[2][0];
+  }
+}
+
+cudaError_t launch_kgrad(cudaStream_t st, TiledSym negCinv, int batch, const double* xpad, int N, int D, const LatentParams* params,
+                         const double* alpha, size_t alpha_stride, int form, double* partial) {
+  const size_t smem = (size_t)(2 * TILE * D + 4 * TILE) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((unsigned)sym_tiles(negCinv.nt), (unsigned)batch);
+  kgrad_kernel<<<grid, 256, smem, st>>>(negCinv, xpad, N, D, params, alpha, alpha_stride, form, partial);
+  return cudaGetLastError();
+}
+
+// out[b*4 + {0,1,2}] = fixed-order sums of the tile partials; out[b*4+3] = sum(alpha_b) (d/d mean)
+__global__ void __launch_bounds__(256) kgrad_finish_kernel(const double* __restrict__ partial, int ntiles_, const double* __restrict__ alpha,
+                                                           size_t alpha_stride, int N, double* __restrict__ out) {
+  __shared__ double red[4][256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int i = t; i < ntiles_; i += 256) {
+    const double* p = partial + ((size_t)b * ntiles_ + i) * 3;
+    s0 += p[0]; s1 += p[1]; s2 += p[2];
+  }
+  for (int i = t; i < N; i += 256) s3 += alpha[(size_t)b * alpha_stride + i];
+  red[0][t] = s0; red[1][t] = s1; red[2][t] = s2; red[3][t] = s3;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w)
+      for (int k = 0; k < 4; ++k) red[k][t] += red[k][t + w];
+    __syncthreads();
+  }
+  if (t < 4) out[(size_t)b * 4 + t] = red[t][0];
+}
+cudaError_t launch_kgrad_finish(cudaStream_t st, const double* partial, int ntiles_, int batch, const double* alpha, size_t alpha_stride,
+                                int N, double* out) {
+  kgrad_finish_kernel<<<batch, 256, 0, st>>>(partial, ntiles_, alpha, alpha_stride, N, out);
+  return cudaGetLastError();
+}
+
+// X (rectangular tiles, nt x nt per latent) <- identity
+__global__ void __launch_bounds__(256) rect_identity_kernel(TiledRect X) {
+  const int b = blockIdx.y, R = blockIdx.x / X.ntc, J = blockIdx.x % X.ntc;
+  double* tile = X.tile(b, R, J);
+  for (int e = threadIdx.x; e < TT; e += 256) {
+    int r, c;
+    tile_rc(e, r, c);
+    tile[e] = (R == J && r == c) ? 1.0 : 0.0;
+  }
+}
+cudaError_t launch_rect_identity(cudaStream_t st, TiledRect X, int batch) {
+  dim3 grid((unsigned)(X.ntr * X.ntc), (unsigned)batch);
+  rect_identity_kernel<<<grid, 256, 0, st>>>(X);
+  return cudaGetLastError();
+}
+
+}  // namespace lmm

@@ -33,6 +33,8 @@ struct GemmArgs {
   int i0, j0;             // tile (I, J) = (i0 + blockIdx.y, j0 + blockIdx.x)
   int k0, k1;             // UPDATE: k-tile range
   int sym;                // skip tiles with I < J
+  int upper;              // skip tiles with I > J (upper-triangular X, e.g. L^{-T})
+  int k_from_row;         // UPDATE: k range starts at max(k0, I) (A(I,k) = 0 for k < I)
 };
 enum { GEMM_UPDATE = 0, GEMM_TRSM = 1 };
 cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch);
@@ -67,7 +69,7 @@ cudaError_t launch_tile_from_dense(cudaStream_t st, TiledSym L, int batch, const
 // resid_partial[blk] = sum over the block's columns of |Y - Q (P Y)|^2
 cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const double* T, int m, int lat0, int mloc,
                            const double* means, double* ty, size_t ty_stride, const double* P, const double* Q,
-                           double* resid_partial, int* nblocks_out);
+                           double* resid_partial, int* nblocks_out, double* resid_out = nullptr);
 cudaError_t launch_sum_partials(cudaStream_t st, const double* partial, int n, double* out);
 // back-projection: mean[j*Ns+n] = sum_i H[j, lat0+i] ML[i][n]; var = sum_i H^2 (VL + jitter) (+ sigma2 if add_noise)
 cudaError_t launch_backproject(cudaStream_t st, const double* H, int p, int m, int lat0, int mloc, const double* ML,
@@ -91,4 +93,13 @@ namespace lmm {
 cudaError_t launch_mix_cov(cudaStream_t st, TiledSym C, int nloc, int lat0, const double* H, int p, int Ns, double* out);
 cudaError_t launch_mix_cov_joint(cudaStream_t st, TiledSym Cl, int m, const double* H, int p, int Ns, double* out);
 cudaError_t launch_add_diag(cudaStream_t st, double* out, int dim, double s);
+}  // namespace lmm
+
+namespace lmm {
+// ---- grad.cu
+cudaError_t launch_kgrad(cudaStream_t st, TiledSym negCinv, int batch, const double* xpad, int N, int D, const LatentParams* params,
+                         const double* alpha, size_t alpha_stride, int form, double* partial);
+cudaError_t launch_kgrad_finish(cudaStream_t st, const double* partial, int ntiles_, int batch, const double* alpha, size_t alpha_stride,
+                                int N, double* out);
+cudaError_t launch_rect_identity(cudaStream_t st, TiledRect X, int batch);
 }  // namespace lmm

@@ -46,7 +46,7 @@ template <int NT>
 __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__ y, int N, int p, const double* __restrict__ T, int m,
                                                       int lat0, int mloc, const double* __restrict__ means, double* __restrict__ ty,
                                                       size_t ty_stride, const double* __restrict__ P, const double* __restrict__ Q,
-                                                      double* __restrict__ resid_partial) {
+                                                      double* __restrict__ resid_partial, double* __restrict__ resid_out) {
   constexpr int NB = 16 * NT;
   extern __shared__ __align__(16) double sm[];
   double* Ys = sm;            // [p][NB]
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__
         for (int q = 0; q < NT; ++q) {
           const double r = Ys[(r0 + i) * NB + n0 + q] - acc[i][q];
           ss = fma(r, r, ss);
+          if (resid_out && nb0 + n0 + q < N) resid_out[(size_t)(r0 + i) * N + nb0 + n0 + q] = r;
         }
   }
   red[t] = ss;
@@ -129,7 +130,7 @@ int project_block_cols(int p, int m) {
 
 cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const double* T, int m, int lat0, int mloc,
                            const double* means, double* ty, size_t ty_stride, const double* P, const double* Q,
-                           double* resid_partial, int* nblocks_out) {
+                           double* resid_partial, int* nblocks_out, double* resid_out) {
   const int nbcols = project_block_cols(p, m);
   if (nbcols == 0) return cudaErrorInvalidValue;
   const int nblocks = (N + nbcols - 1) / nbcols;
@@ -140,7 +141,7 @@ cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const
   do {                                                                                                                    \
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(project_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                       \
-    project_kernel<NT_><<<nblocks, 256, smem, st>>>(y, N, p, T, m, lat0, mloc, means, ty, ty_stride, P, Q, resid_partial);       \
+    project_kernel<NT_><<<nblocks, 256, smem, st>>>(y, N, p, T, m, lat0, mloc, means, ty, ty_stride, P, Q, resid_partial, resid_out); \
   } while (0)
   if (nbcols == 64) LMM_LAUNCH_PROJECT(4);
   else if (nbcols == 32) LMM_LAUNCH_PROJECT(2);

@@ -238,6 +238,32 @@ function AbstractGPs.rand(rng::AbstractRNG, fx::FiniteGP{<:PosteriorOILMM})
     return out
 end
 
+# --- rrule for logpdf (keeps `Zygote.gradient(logpdf, fx, y)` working: test/oilmm.jl:31-32) ---------
+# The ccall is opaque to AD, so the pullback comes from `lmm_oilmm_logpdf_grad` (batched potri +
+# fused kernel-gradient reduction).  Tangents are returned for y, σ² and, per latent, the kernel
+# variance / inverse lengthscale / constant mean; mapping them back onto the nested kernel structs
+# (ScaledKernel.σ², ScaleTransform.s, ConstMean.c) is mechanical and omitted here.
+using ChainRulesCore
+function ChainRulesCore.rrule(::typeof(AbstractGPs.logpdf), fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}},
+                              y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs); m = length(descs)
+    out = Ref{Float64}(0.0); gs2 = Ref{Float64}(0.0); il = Ref{Cint}(-1)
+    gl = Matrix{Float64}(undef, 3, m)            # column i = (d/dvariance, d/dinv_lengthscale, d/dmean) of latent i
+    gy = Vector{Float64}(undef, length(y))
+    check(ccall((:lmm_oilmm_logpdf_grad, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, m, X, length(x), D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), size(H, 1), Float64(σ²),
+        Vector{Float64}(y), fx.x.out_dim, out, gl, gs2, gy, il))
+    function logpdf_pullback(Δ)
+        Σy_tangent = Tangent{typeof(fx.Σy)}(; diag = Tangent{typeof(fx.Σy.diag)}(; value = Δ * gs2[]))
+        return NoTangent(), Tangent{typeof(fx)}(; Σy = Σy_tangent), Δ .* gy
+    end
+    return out[], logpdf_pullback
+end
+
 # PosteriorGP field access (α, C, δ) for one latent -- `lmm_post_export`
 function export_latent(f::DeviceLatentPosterior, N::Int)
     L = Matrix{Float64}(undef, N, N); α = Vector{Float64}(undef, N); δ = Vector{Float64}(undef, N)

@@ -584,6 +584,55 @@ def dense_mogp_posterior_mean_and_var(fs, H, x, sigma2, y, xs, sigma2_pred) -> T
 
 
 # --------------------------------------------------------------------------------------------
+# Gradients of the logpdf (for the rrule; checked against central finite differences in tests)
+# --------------------------------------------------------------------------------------------
+def _dkernel_ds(k: Kernel, x) -> np.ndarray:
+    """d/d(inv_lengthscale) of kernelmatrix(k, x) (direct-difference distances; analytic)."""
+    xs = _as2d(x) * k.inv_lengthscale
+    d2 = pairwise_sqdist(xs, form="direct")
+    s = k.inv_lengthscale
+    if k.kind == SE:
+        return k.variance * (-np.exp(-d2 / 2.0) * d2 / s)
+    d = np.sqrt(d2)
+    if k.kind == MATERN32:
+        return k.variance * (-3.0 * d2 * np.exp(-math.sqrt(3.0) * d) / s)
+    return k.variance * (-(5.0 / 3.0) * d2 * (1.0 + math.sqrt(5.0) * d) * np.exp(-math.sqrt(5.0) * d) / s)
+
+
+def gp_logpdf_grad(f: GP, x, noise: float, y: np.ndarray):
+    """(lml, d/dvariance, d/dinv_lengthscale, d/dmean, d/dnoise, d/dy) with G = (αα' - C⁻¹)/2."""
+    C = kernelmatrix(f.kernel, x)
+    n = C.shape[0]
+    K = C.copy()
+    C[np.diag_indices_from(C)] += noise
+    L = _chol_lower(C)
+    delta = np.asarray(y, dtype=np.float64) - f.mean_const
+    alpha = _bwd(L, _fwd(L, delta))
+    Cinv = _bwd(L, _fwd(L, np.eye(n)))
+    G = 0.5 * (np.outer(alpha, alpha) - Cinv)
+    lml = -0.5 * (n * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(delta @ alpha))
+    return (lml, float(np.sum(G * K)) / f.kernel.variance, float(np.sum(G * _dkernel_ds(f.kernel, x))), float(np.sum(alpha)),
+            float(np.trace(G)), -alpha)
+
+
+def oilmm_logpdf_grad(model: OILMMModel, x, sigma2: float, y: np.ndarray):
+    """Analytic gradient of src/oilmm.jl:79-93 w.r.t. latent hyper-parameters, σ² and y."""
+    N = _as2d(x).shape[0]
+    Y = reshape_y(y, N)
+    p, m = model.U.shape
+    T, ST = project_orthogonal(model.U, model.S, sigma2)
+    Ty = T @ Y
+    parts = [gp_logpdf_grad(f, x, ST[i], Ty[i]) for i, f in enumerate(model.fs)]
+    R = (np.eye(p) - model.U @ model.U.T) @ Y
+    resid = float(np.sum(R * R))
+    lp = sum(q[0] for q in parts) + regulariser_orthogonal(model.U, model.S, sigma2, Y)
+    g_sigma2 = sum(q[4] / model.S[i] for i, q in enumerate(parts)) - 0.5 * (N * (p - m) / sigma2 - resid / sigma2 ** 2)
+    g_y = sum(np.outer(T[i], q[5]) for i, q in enumerate(parts)) - R / sigma2
+    return lp, {"variance": np.array([q[1] for q in parts]), "inv_lengthscale": np.array([q[2] for q in parts]),
+                "mean_const": np.array([q[3] for q in parts]), "sigma2": float(g_sigma2), "y": g_y.reshape(-1)}
+
+
+# --------------------------------------------------------------------------------------------
 # Synthetic workloads shared by tests and bench (SURVEY.md §8d): identical bytes for oracle and GPU
 # --------------------------------------------------------------------------------------------
 def orthogonal_from_seed(p: int, m: int, seed: int = 1) -> Tuple[np.ndarray, np.ndarray]:

@@ -460,3 +460,29 @@ def test_sequential_conditioning(lmm):
         mr, vr = o.gp_condition_again_marginals(oa[i], x2, 0.2, yb.reshape(m, N2)[i], xt)
         np.testing.assert_allclose(Mi[i * Nt:(i + 1) * Nt], mr, rtol=1e-8, atol=1e-10)
         np.testing.assert_allclose(Vi[i * Nt:(i + 1) * Nt], vr + 0.1, rtol=1e-8)
+
+
+@pytest.mark.parametrize("N,p,m", [(60, 4, 3), (700, 6, 3)])
+def test_logpdf_gradient(lmm, N, p, m):
+    """rrule of logpdf: value + gradients w.r.t. kernel hyper-parameters, σ² and y from
+    the batched potri + fused kernel-gradient reduction, against the oracle's analytic gradient."""
+    x, xs, U, S, fs, y = make_problem(N, p, m, 1, seed=61 + N, means=True)
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    lp, g = lmm.logpdf_and_gradient(f(lmm.MOInputIsotopicByOutputs(x, p), 0.15), y, with_grad_y=True)
+    lpr, gr = o.oilmm_logpdf_grad(om, x, 0.15, y)
+    assert rel(lp, lpr) < RTOL
+    for k in ("variance", "inv_lengthscale", "mean_const"):
+        np.testing.assert_allclose(g[k], gr[k], rtol=1e-7, atol=1e-8)
+    assert rel(g["sigma2"], gr["sigma2"]) < 1e-7
+    np.testing.assert_allclose(g["y"], gr["y"], rtol=1e-7, atol=1e-9)
+    # IndependentMOGP
+    fi = lmm.independent_mogp([to_lmm_gp(lmm, gg) for gg in fs])
+    yi = np.random.default_rng(3).standard_normal(m * N)
+    lpi, gi = lmm.logpdf_and_gradient(fi(lmm.MOInputIsotopicByOutputs(x, m), 0.15), yi, with_grad_y=True)
+    parts = [o.gp_logpdf_grad(fs[i], x, 0.15, yi.reshape(m, N)[i]) for i in range(m)]
+    assert rel(lpi, sum(q[0] for q in parts)) < RTOL
+    np.testing.assert_allclose(gi["variance"], [q[1] for q in parts], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(gi["inv_lengthscale"], [q[2] for q in parts], rtol=1e-7, atol=1e-8)
+    assert rel(gi["sigma2"], sum(q[4] for q in parts)) < 1e-7
+    np.testing.assert_allclose(gi["y"], np.concatenate([q[5] for q in parts]), rtol=1e-7, atol=1e-9)

@@ -173,3 +173,41 @@ def test_multidim_inputs_colvecs():
     a = o.gp_logpdf(f, X, 0.1, y, form="gemm")
     b = o.gp_logpdf(f, X, 0.1, y, form="direct")
     assert a == pytest.approx(b, rel=1e-12)
+
+
+def test_oracle_gradient_matches_finite_differences():
+    """The analytic logpdf gradient (used to check the CUDA rrule) against central differences."""
+    rng = np.random.default_rng(9)
+    N, p, m = 25, 4, 3
+    x = np.sort(rng.uniform(0, 4, N))
+    U, S = o.orthogonal_from_seed(p, m, seed=5)
+    fs = [o.GP(o.Kernel(o.SE, 0.9, 1.2), 0.3), o.GP(o.Kernel(o.MATERN32, 1.3, 0.8), -0.2), o.GP(o.Kernel(o.MATERN52, 0.7, 1.5), 0.1)]
+    y = rng.standard_normal(p * N)
+    lp, g = o.oilmm_logpdf_grad(o.OILMMModel(fs, U, S), x, 0.2, y)
+    assert lp == pytest.approx(o.oilmm_logpdf(o.OILMMModel(fs, U, S), x, 0.2, y), rel=1e-12)
+
+    def f_at(i, field, h):
+        k = fs[i].kernel
+        kw = dict(kind=k.kind, variance=k.variance, inv_lengthscale=k.inv_lengthscale)
+        mean = fs[i].mean_const
+        if field == "mean_const":
+            mean += h
+        else:
+            kw[field] += h
+        fs2 = list(fs)
+        fs2[i] = o.GP(o.Kernel(**kw), mean)
+        return o.oilmm_logpdf(o.OILMMModel(fs2, U, S), x, 0.2, y, form="direct")
+
+    h = 1e-6
+    for i in range(m):
+        for field in ("variance", "inv_lengthscale", "mean_const"):
+            fd = (f_at(i, field, h) - f_at(i, field, -h)) / (2 * h)
+            assert g[field][i] == pytest.approx(fd, rel=2e-6, abs=1e-7)
+    model = o.OILMMModel(fs, U, S)
+    fd = (o.oilmm_logpdf(model, x, 0.2 + h, y) - o.oilmm_logpdf(model, x, 0.2 - h, y)) / (2 * h)
+    assert g["sigma2"] == pytest.approx(fd, rel=2e-6)
+    for j in (0, 17, p * N - 1):
+        e = np.zeros(p * N)
+        e[j] = h
+        fd = (o.oilmm_logpdf(model, x, 0.2, y + e) - o.oilmm_logpdf(model, x, 0.2, y - e)) / (2 * h)
+        assert g["y"][j] == pytest.approx(fd, rel=2e-6, abs=1e-8)

@@ -63,6 +63,10 @@ def main():
     print(json.dumps({"config": "C3 OILMM p=64 m=16 N=8192 Matern52", "eval_plus_marginals_wall_ms": t * 1e3, "logpdf_posterior_ms": tm[0],
                       "kmat_ms": tm[1], "chol_ms": tm[2], "solves_ms": tm[3], "chol_tflops": m * N ** 3 / 3 / (tm[2] * 1e-3) / 1e12,
                       "marginals_Ns1024_ms": tp * 1e3, "marginals_tflops": m * (N * N * Ns) / tp / 1e12}), flush=True)
+    # ---- gradient (rrule) at the C3 shape: value + d/d(hyper-parameters, σ², y)
+    t, (lp, g) = timed(lambda: lmm.logpdf_and_gradient(fx, y, with_grad_y=True), reps=2)
+    print(json.dumps({"config": "C3 shape: logpdf + gradient (batched potri + fused kernel-gradient reduction)", "wall_ms": t * 1e3,
+                      "tflops": m * N ** 3 / t / 1e12, "note": "N^3 flop per latent = potrf + triangular TRSM + SYRK"}), flush=True)
     # ---- C5 slice on one GPU: p=256, m=16 of 128 latents, N=8192, 4 of 32 lengthscales
     N, p, m, nsw = 8192, 256, 16, 4
     x = np.sort(rng.uniform(0, N / 100.0, N))
