@@ -27,7 +27,25 @@ __device__ __forceinline__ void dmma884p(double& d0, double& d1, double a, doubl
 // A block element (r,k) at S[(K0+k)*LD + R0+r]; B block element (k,n) at S[(N0+n)*LD + K0+k].
 __device__ __forceinline__ void block_mma(const double* S, int R0, int KA0, int KB0, int N0, int nk, double neg, double& c0, double& c1,
                                           int g, int t) {
-  for (int kk = 0; kk < nk; ++kk) {
+  // two independent accumulator chains (even / odd k-blocks) hide the DMMA latency
+  double e0 = 0.0, e1 = 0.0;
+  int kk = 0;
+  for (; kk + 1 < nk; kk += 2) {
+    const int ka = KA0 + 8 * kk, kb = KB0 + 8 * kk;
+    const double a0 = neg * S[(ka + t) * LD + R0 + g];
+    const double a1 = neg * S[(ka + 4 + t) * LD + R0 + g];
+    const double b0 = S[(N0 + g) * LD + kb + t];
+    const double b1 = S[(N0 + g) * LD + kb + 4 + t];
+    const double a2 = neg * S[(ka + 8 + t) * LD + R0 + g];
+    const double a3 = neg * S[(ka + 12 + t) * LD + R0 + g];
+    const double b2 = S[(N0 + g) * LD + kb + 8 + t];
+    const double b3 = S[(N0 + g) * LD + kb + 12 + t];
+    dmma884p(c0, c1, a0, b0);
+    dmma884p(e0, e1, a2, b2);
+    dmma884p(c0, c1, a1, b1);
+    dmma884p(e0, e1, a3, b3);
+  }
+  if (kk < nk) {
     const int ka = KA0 + 8 * kk, kb = KB0 + 8 * kk;
     const double a0 = neg * S[(ka + t) * LD + R0 + g];
     const double a1 = neg * S[(ka + 4 + t) * LD + R0 + g];
@@ -36,6 +54,8 @@ __device__ __forceinline__ void block_mma(const double* S, int R0, int KA0, int 
     dmma884p(c0, c1, a0, b0);
     dmma884p(c0, c1, a1, b1);
   }
+  c0 += e0;
+  c1 += e1;
 }
 
 __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* __restrict__ Wbase, size_t w_batch_stride, int J,
@@ -44,6 +64,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
   double* dinv = S + TILE * LD;               // 1 / L[r][r]
   double* red = dinv + TILE;                  // reduction scratch
   __shared__ int fail_col;
+  __shared__ unsigned char tri_bi[120], tri_bj[120];  // packed lower-triangular block order (row by row)
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -52,6 +73,12 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
   double* Wt = Wbase + (size_t)b * w_batch_stride + (size_t)J * TT;
 
   if (tid == 0) fail_col = 0x7fffffff;
+  if (tid < 120) {
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= tid) ++bi;
+    tri_bi[tid] = (unsigned char)bi;
+    tri_bj[tid] = (unsigned char)(tid - bi * (bi + 1) / 2);
+  }
 #pragma unroll 8
   for (int e = tid; e < TT; e += 256) {
     int r, c;
@@ -125,19 +152,35 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     // trailing update of the lower 8x8 blocks of rows/cols [j0+8, 128) on the tensor pipe
     const int nb = (TILE - j0 - 8) >> 3;
     const int nblocks = nb * (nb + 1) / 2;
-    for (int idx = warp; idx < nblocks; idx += 8) {
-      int bi = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
-      while ((bi + 1) * (bi + 2) / 2 <= idx) ++bi;
-      while (bi * (bi + 1) / 2 > idx) --bi;
-      const int bj = idx - bi * (bi + 1) / 2;
-      const int R0 = j0 + 8 + 8 * bi, C0 = j0 + 8 + 8 * bj;
-      double c0 = S[(C0 + 2 * t) * LD + R0 + g], c1 = S[(C0 + 2 * t + 1) * LD + R0 + g];
-      const double a0 = -S[(j0 + t) * LD + R0 + g], a1 = -S[(j0 + 4 + t) * LD + R0 + g];
-      const double b0 = S[(j0 + t) * LD + C0 + g], b1 = S[(j0 + 4 + t) * LD + C0 + g];
-      dmma884p(c0, c1, a0, b0);
-      dmma884p(c0, c1, a1, b1);
-      S[(C0 + 2 * t) * LD + R0 + g] = c0;
-      S[(C0 + 2 * t + 1) * LD + R0 + g] = c1;
+    for (int base = warp; base < nblocks; base += 32) {  // 4 independent blocks per pass
+      double c0[4], c1[4], a0[4], a1[4], b0[4], b1[4];
+      int R0[4], C0[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + 8 * u;
+        if (idx < nblocks) {
+          R0[u] = j0 + 8 + 8 * tri_bi[idx];
+          C0[u] = j0 + 8 + 8 * tri_bj[idx];
+          c0[u] = S[(C0[u] + 2 * t) * LD + R0[u] + g];
+          c1[u] = S[(C0[u] + 2 * t + 1) * LD + R0[u] + g];
+          a0[u] = -S[(j0 + t) * LD + R0[u] + g];
+          a1[u] = -S[(j0 + 4 + t) * LD + R0[u] + g];
+          b0[u] = S[(j0 + t) * LD + C0[u] + g];
+          b1[u] = S[(j0 + 4 + t) * LD + C0[u] + g];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (base + 8 * u < nblocks) dmma884p(c0[u], c1[u], a0[u], b0[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (base + 8 * u < nblocks) dmma884p(c0[u], c1[u], a1[u], b1[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (base + 8 * u < nblocks) {
+          S[(C0[u] + 2 * t) * LD + R0[u] + g] = c0[u];
+          S[(C0[u] + 2 * t + 1) * LD + R0[u] + g] = c1[u];
+        }
     }
     __syncthreads();
   }
@@ -189,13 +232,13 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     __syncthreads();
   }
   // ---- phase W doubling levels: W21 = -W22 * (L21 * W11)
-  for (int s = 8; s < TILE; s <<= 1) {
-    const int sb = s >> 3;               // 8-blocks per side
+  for (int s = 8, lg = 0; s < TILE; s <<= 1, ++lg) {
+    const int sb = s >> 3;               // 8-blocks per side (= 1 << lg)
     const int npairs = TILE / (2 * s);
     const int nout = npairs * sb * sb;   // output 8x8 blocks per phase
     // T(i,j) = sum_{k=j}^{sb-1} L21(i,k) W11(k,j)   -> stored in the mirrored upper block (1,2)
     for (int ob = warp; ob < nout; ob += 8) {
-      const int q = ob / (sb * sb), ij = ob % (sb * sb), i = ij % sb, j = ij / sb;
+      const int q = ob >> (2 * lg), ij = ob & (sb * sb - 1), i = ij & (sb - 1), j = ij >> lg;
       const int base = q * 2 * s;
       double c0 = 0.0, c1 = 0.0;
       // A = L21 block (rows base+s+8i, cols base+8k), B = W11 block (rows base+8k, cols base+8j)
@@ -207,7 +250,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     __syncthreads();
     // W21(i,j) = -sum_{k=0}^{i} W22(i,k) T(k,j)
     for (int ob = warp; ob < nout; ob += 8) {
-      const int q = ob / (sb * sb), ij = ob % (sb * sb), i = ij % sb, j = ij / sb;
+      const int q = ob >> (2 * lg), ij = ob & (sb * sb - 1), i = ij & (sb - 1), j = ij >> lg;
       const int base = q * 2 * s;
       double c0 = 0.0, c1 = 0.0;
       // A = W22 block (rows base+s+8i, cols base+s+8k), B = T block (rows base+8k, cols base+s+8j)
