@@ -16,8 +16,31 @@
 
 namespace lmm {
 
+#ifdef LMM_POTRF_TIMING
+__device__ long long g_potrf_clk[16];
+#define PT(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_potrf_clk[k] = clock64(); } while (0)
+#else
+#define PT(k) do { } while (0)
+#endif
+
 constexpr int LD = 132;
 constexpr size_t POTRF_SMEM = (size_t)(TILE * LD + 2 * TILE + 32) * sizeof(double);
+
+// 1/sqrt(x) for x > 0 in the normal range: MUFU.RSQ64H seed + two Newton-Raphson steps (quadratic
+// convergence: ~2^-20 -> 2^-40 -> full double precision); non-positive / NaN pivots are reported
+// separately by the caller, so no special-case handling is needed on the critical path.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
 
 __device__ __forceinline__ void dmma884p(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -72,6 +95,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
   double* tile = L.tile(b, J, J);
   double* Wt = Wbase + (size_t)b * w_batch_stride + (size_t)J * TT;
 
+  PT(0);
   if (tid == 0) fail_col = 0x7fffffff;
   if (tid < 120) {
     int bi = 0;
@@ -79,7 +103,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     tri_bi[tid] = (unsigned char)bi;
     tri_bj[tid] = (unsigned char)(tid - bi * (bi + 1) / 2);
   }
-#pragma unroll 8
+#pragma unroll 16
   for (int e = tid; e < TT; e += 256) {
     int r, c;
     tile_rc(e, r, c);
@@ -87,6 +111,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
   }
   __syncthreads();
 
+  PT(1);
   // ---- phase C
   for (int j0 = 0; j0 < TILE; j0 += 8) {
     const int r = tid;  // row owner (threads 0..127)
@@ -111,7 +136,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
         if (!(piv > 0.0)) {
           if (r == j0) atomicMin(&fail_col, j0 + jj);
         }
-        const double inv = rsqrt(piv);
+        const double inv = fast_rsqrt(piv);
         dv[jj] = inv;
         d[jj][jj] = piv * inv;
 #pragma unroll
@@ -149,41 +174,46 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
       for (int k = 0; k < 8; ++k) S[(j0 + k) * LD + r] = p[k];
     }
     __syncthreads();
+    if (j0 == 0) PT(2);
     // trailing update of the lower 8x8 blocks of rows/cols [j0+8, 128) on the tensor pipe
     const int nb = (TILE - j0 - 8) >> 3;
     const int nblocks = nb * (nb + 1) / 2;
-    for (int base = warp; base < nblocks; base += 32) {  // 4 independent blocks per pass
+    for (int base = warp; base < nblocks; base += 32) {  // 4 independent blocks per pass, branch-free
       double c0[4], c1[4], a0[4], a1[4], b0[4], b1[4];
       int R0[4], C0[4];
+      bool valid[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int idx = base + 8 * u;
-        if (idx < nblocks) {
-          R0[u] = j0 + 8 + 8 * tri_bi[idx];
-          C0[u] = j0 + 8 + 8 * tri_bj[idx];
-          c0[u] = S[(C0[u] + 2 * t) * LD + R0[u] + g];
-          c1[u] = S[(C0[u] + 2 * t + 1) * LD + R0[u] + g];
-          a0[u] = -S[(j0 + t) * LD + R0[u] + g];
-          a1[u] = -S[(j0 + 4 + t) * LD + R0[u] + g];
-          b0[u] = S[(j0 + t) * LD + C0[u] + g];
-          b1[u] = S[(j0 + 4 + t) * LD + C0[u] + g];
-        }
+        valid[u] = base + 8 * u < nblocks;
+        const int idx = valid[u] ? base + 8 * u : nblocks - 1;  // out-of-range slots recompute a real block, never store
+        R0[u] = j0 + 8 + 8 * tri_bi[idx];
+        C0[u] = j0 + 8 + 8 * tri_bj[idx];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (base + 8 * u < nblocks) dmma884p(c0[u], c1[u], a0[u], b0[u]);
+      for (int u = 0; u < 4; ++u) {
+        c0[u] = S[(C0[u] + 2 * t) * LD + R0[u] + g];
+        c1[u] = S[(C0[u] + 2 * t + 1) * LD + R0[u] + g];
+        a0[u] = -S[(j0 + t) * LD + R0[u] + g];
+        a1[u] = -S[(j0 + 4 + t) * LD + R0[u] + g];
+        b0[u] = S[(j0 + t) * LD + C0[u] + g];
+        b1[u] = S[(j0 + 4 + t) * LD + C0[u] + g];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma884p(c0[u], c1[u], a0[u], b0[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dmma884p(c0[u], c1[u], a1[u], b1[u]);
+      __syncwarp();  // all lanes have read the C blocks of this pass before anyone overwrites them
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        if (base + 8 * u < nblocks) dmma884p(c0[u], c1[u], a1[u], b1[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (base + 8 * u < nblocks) {
+        if (valid[u]) {
           S[(C0[u] + 2 * t) * LD + R0[u] + g] = c0[u];
           S[(C0[u] + 2 * t + 1) * LD + R0[u] + g] = c1[u];
         }
     }
     __syncthreads();
+    if (j0 == 0) PT(3);
   }
+  PT(4);
 
   // ---- logdet and failure report (fixed reduction order)
   if (tid < TILE) {
@@ -198,6 +228,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     if (fail_col != 0x7fffffff && info[b] == 0) info[b] = J * TILE + fail_col + 1;
   }
 
+  PT(5);
   // ---- write L (lower, zero upper)
 #pragma unroll 8
   for (int e = tid; e < TT; e += 256) {
@@ -206,6 +237,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     tile[e] = (r >= c) ? S[c * LD + r] : 0.0;
   }
 
+  PT(6);
   // ---- phase W level 0: invert the 16 diagonal 8x8 blocks in place (thread = one column)
   {
     double Lb[8][8];
@@ -231,6 +263,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     }
     __syncthreads();
   }
+  PT(7);
   // ---- phase W doubling levels: W21 = -W22 * (L21 * W11)
   for (int s = 8, lg = 0; s < TILE; s <<= 1, ++lg) {
     const int sb = s >> 3;               // 8-blocks per side (= 1 << lg)
@@ -261,12 +294,14 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
     }
     __syncthreads();
   }
+  PT(8);
 #pragma unroll 8
   for (int e = tid; e < TT; e += 256) {
     int r, c;
     tile_rc(e, r, c);
     Wt[e] = (r >= c) ? S[c * LD + r] : 0.0;
   }
+  PT(9);
 }
 
 cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int batch, double* logdet,
