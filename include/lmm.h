@@ -128,12 +128,14 @@ int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, cons
 /* rrule of logpdf (`Zygote.gradient(logpdf, fx, y)` at test/oilmm.jl:31-32,
  * test/independent_mogp.jl:65-66 needs a ChainRulesCore.rrule around the opaque ccall): value and
  * gradients w.r.t. each latent's (variance, inv_lengthscale, mean_const) -- grad_latents is m x 3
- * row-major --, the observation noise σ² and, optionally, y (p*N by outputs).  All outputs nullable.
- * G_i = (α_i α_i' - C_i^{-1})/2 comes from a batched potri on the tensor pipe. */
+ * row-major --, the observation noise σ², y (p*N by outputs) and the mixing matrix fields U (p x m
+ * column-major, the unconstrained Euclidean gradient of the reference's expressions) and S (m).
+ * All outputs nullable.  G_i = (α_i α_i' - C_i^{-1})/2 comes from a batched potri on the tensor pipe. */
 int lmm_oilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N,
                           int D, const double* U, const double* S, int p, double sigma2,
                           const double* y, int out_dim, double* out_logpdf, double* grad_latents,
-                          double* grad_sigma2, double* grad_y, int* info_latent);
+                          double* grad_sigma2, double* grad_y, double* grad_U, double* grad_S,
+                          int* info_latent);
 int lmm_imogp_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
                           double sigma2, const double* y, int out_dim, double* out_logpdf,
                           double* grad_latents, double* grad_sigma2, double* grad_y, int* info_latent);

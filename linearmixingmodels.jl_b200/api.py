@@ -792,7 +792,7 @@ def logpdf_and_gradient(fx: FiniteGP, y, with_grad_y: bool = False):
     """Value and gradient of `logpdf(fx, y)` for an OILMM or IndependentMOGP prior -- the pullback a
     ChainRulesCore `rrule` around the ccall returns (test/oilmm.jl:31-32 `gradient(logpdf, fx, y)`).
     Returns (logpdf, grads) with grads = {"variance": (m,), "inv_lengthscale": (m,), "mean_const": (m,),
-    "sigma2": float[, "y": (p*N,)]}."""
+    "sigma2": float[, "y": (p*N,)][, "U": (p, m), "S": (m,) for an OILMM]}."""
     f = fx.f
     ctx = _ctx_of(fx)
     _require_by_outputs(fx)
@@ -805,8 +805,10 @@ def logpdf_and_gradient(fx: FiniteGP, y, with_grad_y: bool = False):
         lat, H = f.f, f.H
         m = len(lat.fs)
         gl = np.zeros((m, 3))
+        gU = np.zeros(H.shape, order="F")
+        gS = np.zeros(m)
         rc = ctx.lib.lmm_oilmm_logpdf_grad(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H.U), ptr(H.S), H.shape[0], fx.sigma2, ptr(yv),
-                                           fx.x.out_dim, C.byref(out), ptr(gl), C.byref(gs2), ptr(gy), C.byref(il))
+                                           fx.x.out_dim, C.byref(out), ptr(gl), C.byref(gs2), ptr(gy), ptr(gU), ptr(gS), C.byref(il))
     elif isinstance(f, IndependentMOGP):
         m = len(f.fs)
         gl = np.zeros((m, 3))
@@ -818,6 +820,8 @@ def logpdf_and_gradient(fx: FiniteGP, y, with_grad_y: bool = False):
     grads = {"variance": gl[:, 0].copy(), "inv_lengthscale": gl[:, 1].copy(), "mean_const": gl[:, 2].copy(), "sigma2": gs2.value}
     if with_grad_y:
         grads["y"] = gy
+    if isinstance(f, ILMM):
+        grads["U"], grads["S"] = np.ascontiguousarray(gU), gS
     return out.value, grads
 
 

@@ -69,7 +69,10 @@ cudaError_t launch_tile_from_dense(cudaStream_t st, TiledSym L, int batch, const
 // resid_partial[blk] = sum over the block's columns of |Y - Q (P Y)|^2
 cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const double* T, int m, int lat0, int mloc,
                            const double* means, double* ty, size_t ty_stride, const double* P, const double* Q,
-                           double* resid_partial, int* nblocks_out, double* resid_out = nullptr);
+                           double* resid_partial, int* nblocks_out, double* resid_out = nullptr, double* z_out = nullptr);
+// out (ra x rb, column-major) += scale * A B'  with A: ra x N, B: rb x N stored row by row (strides lda, ldb)
+cudaError_t launch_abt(cudaStream_t st, const double* A, size_t lda, int ra, const double* B, size_t ldb, int rb, int N, double scale,
+                       double* out);
 cudaError_t launch_sum_partials(cudaStream_t st, const double* partial, int n, double* out);
 // back-projection: mean[j*Ns+n] = sum_i H[j, lat0+i] ML[i][n]; var = sum_i H^2 (VL + jitter) (+ sigma2 if add_noise)
 cudaError_t launch_backproject(cudaStream_t st, const double* H, int p, int m, int lat0, int mloc, const double* ML,

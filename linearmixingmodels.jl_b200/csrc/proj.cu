@@ -46,7 +46,7 @@ template <int NT>
 __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__ y, int N, int p, const double* __restrict__ T, int m,
                                                       int lat0, int mloc, const double* __restrict__ means, double* __restrict__ ty,
                                                       size_t ty_stride, const double* __restrict__ P, const double* __restrict__ Q,
-                                                      double* __restrict__ resid_partial, double* __restrict__ resid_out) {
+                                                      double* __restrict__ resid_partial, double* __restrict__ resid_out, double* __restrict__ z_out) {
   constexpr int NB = 16 * NT;
   extern __shared__ __align__(16) double sm[];
   double* Ys = sm;            // [p][NB]
@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__
     for (int i = 0; i < 4; ++i)
       if (r0 + i < m)
 #pragma unroll
-        for (int q = 0; q < NT; ++q) Zs[(r0 + i) * NB + n0 + q] = acc[i][q];
+        for (int q = 0; q < NT; ++q) {
+          Zs[(r0 + i) * NB + n0 + q] = acc[i][q];
+          if (z_out && nb0 + n0 + q < N) z_out[(size_t)(r0 + i) * N + nb0 + n0 + q] = acc[i][q];
+        }
   }
   __syncthreads();
   // R = Y - Q Z (p x NB), summed squares
@@ -130,7 +133,7 @@ int project_block_cols(int p, int m) {
 
 cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const double* T, int m, int lat0, int mloc,
                            const double* means, double* ty, size_t ty_stride, const double* P, const double* Q,
-                           double* resid_partial, int* nblocks_out, double* resid_out) {
+                           double* resid_partial, int* nblocks_out, double* resid_out, double* z_out) {
   const int nbcols = project_block_cols(p, m);
   if (nbcols == 0) return cudaErrorInvalidValue;
   const int nblocks = (N + nbcols - 1) / nbcols;
@@ -141,7 +144,7 @@ cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const
   do {                                                                                                                    \
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(project_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                       \
-    project_kernel<NT_><<<nblocks, 256, smem, st>>>(y, N, p, T, m, lat0, mloc, means, ty, ty_stride, P, Q, resid_partial, resid_out); \
+    project_kernel<NT_><<<nblocks, 256, smem, st>>>(y, N, p, T, m, lat0, mloc, means, ty, ty_stride, P, Q, resid_partial, resid_out, z_out); \
   } while (0)
   if (nbcols == 64) LMM_LAUNCH_PROJECT(4);
   else if (nbcols == 32) LMM_LAUNCH_PROJECT(2);
@@ -188,6 +191,32 @@ cudaError_t launch_backproject(cudaStream_t st, const double* H, int p, int m, i
                                double* mean, double* var) {
   dim3 grid((unsigned)((Ns + 255) / 256), (unsigned)p);
   backproject_kernel<<<grid, 256, 0, st>>>(H, p, m, lat0, mloc, ML, VL, lat_stride, Ns, jitter, sigma2, add_noise, mean, var);
+  return cudaGetLastError();
+}
+
+// out[i + j*ra] (+)= scale * sum_n A[i*lda + n] * B[j*ldb + n]   (A: ra x N, B: rb x N, rows contiguous)
+// grid (ra, rb): one CTA per output entry, fixed-order block reduction.
+__global__ void __launch_bounds__(256) abt_kernel(const double* __restrict__ A, size_t lda, const double* __restrict__ B, size_t ldb, int N,
+                                                  double scale, double* __restrict__ out, int ra) {
+  __shared__ double red[256];
+  const int i = blockIdx.x, j = blockIdx.y, t = threadIdx.x;
+  const double* a = A + (size_t)i * lda;
+  const double* b = B + (size_t)j * ldb;
+  double s = 0.0;
+  for (int n = t; n < N; n += 256) s = fma(a[n], b[n], s);
+  red[t] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) red[t] += red[t + w];
+    __syncthreads();
+  }
+  if (t == 0) out[(size_t)j * ra + i] += scale * red[0];
+}
+cudaError_t launch_abt(cudaStream_t st, const double* A, size_t lda, int ra, const double* B, size_t ldb, int rb, int N, double scale,
+                       double* out) {
+  if (ra <= 0 || rb <= 0) return cudaSuccess;
+  dim3 grid((unsigned)ra, (unsigned)rb);
+  abt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, N, scale, out, ra);
   return cudaGetLastError();
 }
 

@@ -628,8 +628,13 @@ def oilmm_logpdf_grad(model: OILMMModel, x, sigma2: float, y: np.ndarray):
     lp = sum(q[0] for q in parts) + regulariser_orthogonal(model.U, model.S, sigma2, Y)
     g_sigma2 = sum(q[4] / model.S[i] for i, q in enumerate(parts)) - 0.5 * (N * (p - m) / sigma2 - resid / sigma2 ** 2)
     g_y = sum(np.outer(T[i], q[5]) for i, q in enumerate(parts)) - R / sigma2
+    # mixing matrix: δ_i = U_i'Y/sqrt(S_i) - m_i, ν_i = σ²/S_i, regulariser -(n logdet S + |(I-UU')Y|²/σ²)/2
+    S = model.S
+    g_S = np.array([-(q[5] @ Ty[i]) / (2 * S[i]) - q[4] * sigma2 / S[i] ** 2 - N / (2 * S[i]) for i, q in enumerate(parts)])
+    Z = model.U.T @ Y
+    g_U = np.stack([Y @ q[5] / math.sqrt(S[i]) for i, q in enumerate(parts)], axis=1) + (R @ Z.T + Y @ (R.T @ model.U)) / sigma2
     return lp, {"variance": np.array([q[1] for q in parts]), "inv_lengthscale": np.array([q[2] for q in parts]),
-                "mean_const": np.array([q[3] for q in parts]), "sigma2": float(g_sigma2), "y": g_y.reshape(-1)}
+                "mean_const": np.array([q[3] for q in parts]), "sigma2": float(g_sigma2), "y": g_y.reshape(-1), "U": g_U, "S": g_S}
 
 
 # --------------------------------------------------------------------------------------------

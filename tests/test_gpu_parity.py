@@ -476,6 +476,8 @@ def test_logpdf_gradient(lmm, N, p, m):
         np.testing.assert_allclose(g[k], gr[k], rtol=1e-7, atol=1e-8)
     assert rel(g["sigma2"], gr["sigma2"]) < 1e-7
     np.testing.assert_allclose(g["y"], gr["y"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(g["S"], gr["S"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(g["U"], gr["U"], rtol=1e-7, atol=1e-7)
     # IndependentMOGP
     fi = lmm.independent_mogp([to_lmm_gp(lmm, gg) for gg in fs])
     yi = np.random.default_rng(3).standard_normal(m * N)

@@ -211,3 +211,16 @@ def test_oracle_gradient_matches_finite_differences():
         e[j] = h
         fd = (o.oilmm_logpdf(model, x, 0.2, y + e) - o.oilmm_logpdf(model, x, 0.2, y - e)) / (2 * h)
         assert g["y"][j] == pytest.approx(fd, rel=2e-6, abs=1e-8)
+    # mixing matrix fields (unconstrained Euclidean derivatives of the reference's expressions)
+    for i in range(m):
+        Sp, Sm = S.copy(), S.copy()
+        Sp[i] += h
+        Sm[i] -= h
+        fd = (o.oilmm_logpdf(o.OILMMModel(fs, U, Sp), x, 0.2, y) - o.oilmm_logpdf(o.OILMMModel(fs, U, Sm), x, 0.2, y)) / (2 * h)
+        assert g["S"][i] == pytest.approx(fd, rel=2e-6)
+    for (j, i) in ((0, 0), (2, 1), (3, 2)):
+        Up, Um = U.copy(), U.copy()
+        Up[j, i] += h
+        Um[j, i] -= h
+        fd = (o.oilmm_logpdf(o.OILMMModel(fs, Up, S), x, 0.2, y) - o.oilmm_logpdf(o.OILMMModel(fs, Um, S), x, 0.2, y)) / (2 * h)
+        assert g["U"][j, i] == pytest.approx(fd, rel=5e-6, abs=1e-6)
