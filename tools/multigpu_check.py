@@ -63,8 +63,30 @@ def main():
     zl, zn = gq.standard_normal(m * 6), gq.standard_normal(p * 6)
     s = lmm.rand(np.random.default_rng(21), frx)
     errs["rand"] = float(np.max(np.abs(s - o.oilmm_rand(o.OILMMModel(fr, U, S), xr, 0.1, zl, zn))))
+    # dense covariance, sequential conditioning and the logpdf gradient across ranks
+    xc = np.sort(rng.uniform(0, 7, 9))
+    Mc, Cc = lmm.mean_and_cov(post(lmm.MOInputIsotopicByOutputs(xc, p), 0.1))
+    Mcr, Ccr = o.ilmm_mean_and_cov(opost.fs, om.H, xc, 0.1)
+    errs["cov"] = float(np.max(np.abs(Cc - Ccr)) / np.max(np.abs(Ccr)))
+    errs["cov_mean"] = float(np.max(np.abs(Mc - Mcr)))
+    x2 = rng.uniform(0, 7, 21)
+    y2 = rng.standard_normal(p * 21)
+    post2 = lmm.posterior(post(lmm.MOInputIsotopicByOutputs(x2, p), 0.1), y2)
+    xu = np.concatenate([x, x2])
+    yu = np.concatenate([np.concatenate([y.reshape(p, N)[j], y2.reshape(p, 21)[j]]) for j in range(p)])
+    Mu, Vu = o.oilmm_mean_and_var(o.oilmm_posterior(om, xu, 0.1, yu), xs, 0.1)
+    M2, V2 = lmm.mean_and_var(post2(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
+    errs["cond_mean"] = float(np.max(np.abs(M2 - Mu) / (np.abs(Mu) + 1e-8)))
+    errs["cond_var"] = float(np.max(np.abs(V2 - Vu) / np.abs(Vu)))
+    lpg, g = lmm.logpdf_and_gradient(fx, y, with_grad_y=True)
+    lpr, gr = o.oilmm_logpdf_grad(om, x, 0.1, y)
+    errs["grad_value"] = abs(lpg - lpr) / abs(lpr)
+    for k in ("variance", "inv_lengthscale", "mean_const", "y", "S", "U"):
+        errs["grad_" + k] = float(np.max(np.abs(g[k] - gr[k])) / (np.max(np.abs(gr[k])) + 1e-12))
+    errs["grad_sigma2"] = abs(g["sigma2"] - gr["sigma2"]) / abs(gr["sigma2"])
+    post2.f.fs[0]._owner.free()
     worst = max(errs.values())
-    ok = worst < 1e-7 and max(errs[k] for k in ("logpdf", "mean", "var", "post_logpdf")) < 1e-9
+    ok = worst < 1e-6 and max(errs[k] for k in ("logpdf", "mean", "var", "post_logpdf", "grad_value")) < 1e-9
     print(f"rank {rank}/{world}: {'OK' if ok else 'FAIL'} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
     post.f.fs[0]._owner.free()
     dist.barrier()
