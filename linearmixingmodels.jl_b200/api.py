@@ -499,8 +499,14 @@ def _require_by_outputs(fx: FiniteGP):
         raise TypeError("this method needs MOInputIsotopicByOutputs inputs (src/ilmm.jl:45)")
 
 
-def logpdf(fx: FiniteGP, y) -> float:
-    """`logpdf(fx, y)`: src/oilmm.jl:79-93, src/ilmm.jl:150-163, src/independent_mogp.jl:74-80,222-229."""
+def logpdf(fx: FiniteGP, y):
+    """`logpdf(fx, y)`: src/oilmm.jl:79-93, src/ilmm.jl:150-163, src/independent_mogp.jl:74-80,222-229.
+    A matrix `Y` (one sample per column, as returned by `rand(rng, fx, n)`) gives the vector of
+    per-column logpdfs (AbstractGPs `logpdf(fx, Y::AbstractMatrix)`)."""
+    if not _is_device_tensor(y):
+        ya = np.asarray(y)
+        if ya.ndim == 2:
+            return np.array([_logpdf_impl(fx, np.ascontiguousarray(ya[:, k]))[0] for k in range(ya.shape[1])])
     return _logpdf_impl(fx, y)[0]
 
 

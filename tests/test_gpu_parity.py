@@ -259,7 +259,10 @@ def test_rand_prior_and_posterior(lmm):
     s = lmm.rand(np.random.default_rng(21), fx)
     assert s.shape == (p * N,)
     np.testing.assert_allclose(s, o.oilmm_rand(om, x, 0.1, zl, zn), rtol=1e-7, atol=1e-8)
-    assert lmm.rand(np.random.default_rng(1), fx, 3).shape == (p * N, 3)
+    Ys = lmm.rand(np.random.default_rng(1), fx, 3)
+    assert Ys.shape == (p * N, 3)
+    lps = lmm.logpdf(fx, Ys)  # AbstractGPs logpdf(fx, Y::AbstractMatrix): one value per column
+    assert lps.shape == (3,) and rel(lps[1], o.oilmm_logpdf(om, x, 0.1, Ys[:, 1])) < RTOL
     # general ILMM
     Hm = om.H
     fi = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), Hm)
