@@ -734,8 +734,9 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
       CU(cudaGetLastError());
       ++ctx->launches;
       CU(cudaEventRecord(ctx->ev[5], st));
-      if (c0 + chunk < mloc || true) {
-        // accumulate stage timings per chunk (needs a sync; cheap relative to a chunk's factorisation)
+      {
+        // accumulate stage timings per chunk: the stage events are reused by the next chunk, so they
+        // are read here (one host sync per chunk; negligible next to a chunk's factorisation)
         CU(cudaEventSynchronize(ctx->ev[5]));
         float a = 0, bq = 0, c = 0;
         cudaEventElapsedTime(&a, ctx->ev[2], ctx->ev[3]);
@@ -779,7 +780,11 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
     *out.logpdf = s + hterms[m];
   }
   if (keep) {
-    lmm_post* P = new lmm_post();
+    DevBuf b_H;
+    CU(b_H.alloc(ctx, (size_t)p * m * sizeof(double)));
+    CU(copy_in(ctx, b_H.as<double>(), Hhost, (size_t)p * m));
+    CU(cudaStreamSynchronize(st));
+    lmm_post* P = new lmm_post();  // nothing below can fail: ownership of the device buffers moves to P
     P->ctx = ctx; P->kind = kind; P->m = m; P->p = p; P->N = N; P->D = D; P->nt = nt; P->lo = lo; P->hi = hi;
     P->descs.assign(latents, latents + m);
     P->noise = pr.noise;
@@ -787,10 +792,6 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
     if (Uhost) P->U.assign(Uhost, Uhost + (size_t)p * m);
     if (Shost) P->S.assign(Shost, Shost + m);
     P->sigma2 = sigma2;
-    DevBuf b_H;
-    CU(b_H.alloc(ctx, (size_t)p * m * sizeof(double)));
-    CU(copy_in(ctx, b_H.as<double>(), Hhost, (size_t)p * m));
-    CU(cudaStreamSynchronize(st));
     P->bytes = (size_t)mloc * (per_lat + 2 * npad * sizeof(double)) + npad * D * sizeof(double);
     P->d_xpad = (double*)b_x.detach();
     P->d_L = (double*)b_L.detach();
