@@ -20,7 +20,8 @@
  *    cudaPointerGetAttributes) -- bench.py's HBM-resident timing uses that.  The library never
  *    retains a caller pointer after return.
  *  - Calls are synchronous and thread-safe per context (one mutex per lmm_ctx; cudaSetDevice on
- *    entry).  There is no CPU fallback: without a CUDA device every compute entry returns
+ *    entry).  A posterior handle belongs to the context that created it: free every lmm_post
+ *    before destroying its lmm_ctx.  There is no CPU fallback: without a CUDA device every compute entry returns
  *    LMM_E_CUDA.
  */
 #ifndef LMM_H_

@@ -465,7 +465,7 @@ def test_sequential_conditioning(lmm):
         np.testing.assert_allclose(Vi[i * Nt:(i + 1) * Nt], vr + 0.1, rtol=1e-8)
 
 
-@pytest.mark.parametrize("N,p,m", [(60, 4, 3), (700, 6, 3)])
+@pytest.mark.parametrize("N,p,m", [(60, 4, 3), (700, 6, 3), (1300, 4, 2)])
 def test_logpdf_gradient(lmm, N, p, m):
     """rrule of logpdf: value + gradients w.r.t. kernel hyper-parameters, σ² and y from
     the batched potri + fused kernel-gradient reduction, against the oracle's analytic gradient."""
