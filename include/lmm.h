@@ -188,6 +188,11 @@ int lmm_imogp_posterior(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double
 /* rand src/independent_mogp.jl:83-86. */
 int lmm_imogp_rand(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
                    double sigma2, int out_dim, const double* z, double* out, int* info_latent);
+/* cov(f::IndependentMOGP, x, y): prior cross-covariance, dense (m*Na) x (m*Nb) column-major block
+ * diagonal, both inputs by outputs  src/independent_mogp.jl:66-71 (by-features variants :188-215
+ * permute rows / columns with lmm_reorder_indices). */
+int lmm_imogp_cross_cov(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* xa, int Na,
+                        const double* xb, int Nb, int D, double* out);
 /* indices_which_reorder_{outputs_to_features,features_to_outputs}  src/independent_mogp.jl:135-145
  * (0-based; direction 0 = outputs->features, 1 = features->outputs). */
 int lmm_reorder_indices(int N, int p, int direction, int64_t* out);

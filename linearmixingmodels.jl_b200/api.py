@@ -721,8 +721,31 @@ def mean_and_cov(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
     return M, Cm
 
 
-def cov(fx: FiniteGP) -> np.ndarray:
-    return mean_and_cov(fx)[1]  # src/ilmm.jl:147
+def cov(*args) -> np.ndarray:
+    """`cov(fx)` (src/ilmm.jl:147) or, for an IndependentMOGP prior, the process cross-covariance
+    `cov(f, x, y)` between two isotopic inputs in any by-outputs / by-features combination
+    (src/independent_mogp.jl:60-71, 181-215; test/independent_mogp.jl:135-141)."""
+    if len(args) == 1:
+        return mean_and_cov(args[0])[1]
+    f, x = args[0], args[1]
+    y = args[2] if len(args) > 2 else x
+    if not isinstance(f, IndependentMOGP) or any(isinstance(g, PosteriorGP) for g in f.fs):
+        raise TypeError("cov(f, x[, y]) is built for IndependentMOGP priors")
+    for z in (x, y):
+        if not isinstance(z, (MOInputIsotopicByOutputs, MOInputIsotopicByFeatures)) or z.out_dim != len(f.fs):
+            raise TypeError("cov(f, x, y) needs isotopic multi-output inputs with out_dim == number of outputs")
+    ctx = default_context()
+    pa, pb = _points(x.x), _points(y.x)
+    m, Na, Nb = len(f.fs), int(pa.shape[0]), int(pb.shape[0])
+    out = np.zeros((m * Na, m * Nb), order="F")
+    rc = ctx.lib.lmm_imogp_cross_cov(ctx.handle, _descs(f.fs), m, ptr(pa), Na, ptr(pb), Nb, int(pa.shape[1]), ptr(out))
+    ctx.check(rc)
+    out = np.ascontiguousarray(out)
+    if isinstance(x, MOInputIsotopicByFeatures):
+        out = out[indices_which_reorder_outputs_to_features(x), :]
+    if isinstance(y, MOInputIsotopicByFeatures):
+        out = out[:, indices_which_reorder_outputs_to_features(y)]
+    return out
 
 
 def mean(fx: FiniteGP) -> np.ndarray:

@@ -106,3 +106,7 @@ cudaError_t launch_kgrad_finish(cudaStream_t st, const double* partial, int ntil
                                 int N, double* out);
 cudaError_t launch_rect_identity(cudaStream_t st, TiledRect X, int batch);
 }  // namespace lmm
+
+namespace lmm {
+cudaError_t launch_untile_rect_blockdiag(cudaStream_t st, TiledRect A, int batch, int Na, int Nb, double* dense, size_t ld);
+}  // namespace lmm

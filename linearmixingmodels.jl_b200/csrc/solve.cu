@@ -254,4 +254,21 @@ cudaError_t launch_tile_from_dense(cudaStream_t st, TiledSym L, int batch, const
   return cudaGetLastError();
 }
 
+// grid (ntr*ntc, batch): dense block-diagonal scatter of rectangular tiled matrices:
+// dense[(b*Na + r) + (b*Nb + c) * ld] = A_b(r, c)   for r < Na, c < Nb   (dense pre-zeroed)
+__global__ void __launch_bounds__(256) untile_rect_blockdiag_kernel(TiledRect A, int Na, int Nb, double* __restrict__ dense, size_t ld) {
+  const int b = blockIdx.y, R = blockIdx.x / A.ntc, J = blockIdx.x % A.ntc;
+  const double* tile = A.tile(b, R, J);
+  for (int idx = threadIdx.x; idx < TT; idx += 256) {
+    const int r = idx & 127, c = idx >> 7;
+    const int gr = R * TILE + r, gc = J * TILE + c;
+    if (gr < Na && gc < Nb) dense[((size_t)b * Nb + gc) * ld + (size_t)b * Na + gr] = tile[tile_elem(r, c)];
+  }
+}
+cudaError_t launch_untile_rect_blockdiag(cudaStream_t st, TiledRect A, int batch, int Na, int Nb, double* dense, size_t ld) {
+  dim3 grid((unsigned)(A.ntr * A.ntc), (unsigned)batch);
+  untile_rect_blockdiag_kernel<<<grid, 256, 0, st>>>(A, Na, Nb, dense, ld);
+  return cudaGetLastError();
+}
+
 }  // namespace lmm

@@ -491,3 +491,21 @@ def test_logpdf_gradient(lmm, N, p, m):
     np.testing.assert_allclose(gi["inv_lengthscale"], [q[2] for q in parts], rtol=1e-7, atol=1e-8)
     assert rel(gi["sigma2"], sum(q[4] for q in parts)) < 1e-7
     np.testing.assert_allclose(gi["y"], np.concatenate([q[5] for q in parts]), rtol=1e-7, atol=1e-9)
+
+
+def test_imogp_process_cov_mixed_orderings(lmm):
+    """cov(f, x, y) with by-outputs / by-features inputs in all four combinations
+    (src/independent_mogp.jl:60-71,181-215; test/independent_mogp.jl:135-141)."""
+    rng = np.random.default_rng(19)
+    xa, xb = rng.uniform(0, 3, 5), rng.uniform(0, 3, 140)
+    fs = [o.GP(o.Kernel(o.SE, 0.5)), o.GP(o.Kernel(o.MATERN32, 1.0, 1.4)), o.GP(o.Kernel(o.MATERN52))]
+    f = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    import scipy.linalg as sla2
+    ref = sla2.block_diag(*[o.kernelmatrix(g.kernel, xa, xb) for g in fs])
+    ia, ib = o.indices_outputs_to_features(5, 3), o.indices_outputs_to_features(140, 3)
+    O, F = lmm.MOInputIsotopicByOutputs, lmm.MOInputIsotopicByFeatures
+    np.testing.assert_allclose(lmm.cov(f, O(xa, 3), O(xb, 3)), ref, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(lmm.cov(f, F(xa, 3), O(xb, 3)), ref[ia, :], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(lmm.cov(f, O(xa, 3), F(xb, 3)), ref[:, ib], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(lmm.cov(f, F(xa, 3), F(xb, 3)), ref[np.ix_(ia, ib)], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(lmm.cov(f, F(xa, 3)), sla2.block_diag(*[o.kernelmatrix(g.kernel, xa) for g in fs])[np.ix_(ia, ia)], rtol=1e-13, atol=1e-15)
