@@ -165,6 +165,11 @@ int lmm_post_condition(lmm_post* post, const double* xs, int Ns, double sigma2, 
 /* logpdf(post(x*, σ²), y*)  (test/oilmm.jl:84): OILMM logpdf with PosteriorGP latents. */
 int lmm_post_logpdf(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys,
                     double* out_logpdf, int* info_latent);
+/* rrule of logpdf(post(x*, σ²), y*) (`gradient(logpdf, po, y_test)` at test/oilmm.jl:32, test/ilmm.jl:32,
+ * test/independent_mogp.jl:66): value and gradients w.r.t. σ² and y* (p*Ns by outputs); the posterior's
+ * own data (α, C, x) and kernel hyper-parameters are held fixed.  All outputs nullable. */
+int lmm_post_logpdf_grad(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys,
+                         double* out_logpdf, double* grad_sigma2, double* grad_y, int* info_latent);
 /* rand(rng, post(x*, σ²))  src/oilmm.jl:40-54 with PosteriorGP latents. */
 int lmm_post_rand(lmm_post* post, const double* xs, int Ns, double sigma2, const double* z_latent,
                   const double* z_noise, double* out, int* info_latent);
@@ -216,6 +221,17 @@ int lmm_ilmm_prior_mean_and_var(lmm_ctx* ctx, const lmm_gp_desc* latents, int m,
 int lmm_ilmm_rand(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
                   const double* H, int p, double sigma2, int out_dim, const double* z_latent,
                   const double* z_noise, double* out, int* info_latent);
+
+/* rrule of the general-ILMM logpdf (`gradient(logpdf, ilmmx, y_train)` at
+ * test/ilmm.jl:31): value and gradients of the projected form src/ilmm.jl:150-163 (through `project`
+ * :61-68 and `regulariser` :171-181) w.r.t. each latent's (variance, inv_lengthscale, mean_const) --
+ * grad_latents m x 3 row-major --, σ², y (p*N by outputs) and the dense mixing matrix H (p x m
+ * column-major).  All outputs nullable.  G = (αα' - C^{-1})/2 over the joint (mN x mN) matrix comes
+ * from a potri on the tensor pipe; the chain through T, ΣT is host arithmetic on m x p matrices. */
+int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
+                         const double* H, int p, double sigma2, const double* y, int out_dim,
+                         double* out_logpdf, double* grad_latents, double* grad_sigma2, double* grad_y,
+                         double* grad_H, int* info);
 
 /* ---- batched blocked Cholesky primitive: the `cholesky(Symmetric(C))` / dpotrf call site ---- */
 /* A: batch matrices, each N x N column-major (lower triangle read).  L_out (nullable): same

@@ -67,6 +67,7 @@ SIGNATURES = {
     "lmm_prior_mean_and_cov": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp]),
     "lmm_post_condition": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, C.POINTER(_vp), _ip]),
     "lmm_post_logpdf": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, _dp, _ip]),
+    "lmm_post_logpdf_grad": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, _dp, _dp, _vp, _ip]),
     "lmm_post_rand": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _ip]),
     "lmm_post_export": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "lmm_post_info": (C.c_int, [_vp, _ip, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "lmm_ilmm_posterior": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_double, _vp, C.c_int, C.POINTER(_vp), _dp, _ip]),
     "lmm_ilmm_prior_mean_and_var": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _vp, _vp]),
     "lmm_ilmm_rand": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _vp, _vp, _vp, _ip]),
+    "lmm_ilmm_logpdf_grad": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_double, _vp, C.c_int, _dp, _vp, _dp, _vp, _vp, _ip]),
     "lmm_potrf_batched": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "lmm_potrf_bench": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_int, _vp, _dp, _dp]),
 }

@@ -818,8 +818,9 @@ def _rand_one(rng, fx: FiniteGP) -> np.ndarray:
 
 
 def logpdf_and_gradient(fx: FiniteGP, y, with_grad_y: bool = False):
-    """Value and gradient of `logpdf(fx, y)` for an OILMM or IndependentMOGP prior -- the pullback a
-    ChainRulesCore `rrule` around the ccall returns (test/oilmm.jl:31-32 `gradient(logpdf, fx, y)`).
+    """Value and gradient of `logpdf(fx, y)` for an OILMM, general ILMM or IndependentMOGP prior -- the pullback
+    a ChainRulesCore `rrule` around the ccall returns (test/oilmm.jl:31-32, test/ilmm.jl:31 `gradient(logpdf, fx, y)`).
+    A general ILMM returns "H" (p, m) instead of "U"/"S".
     Returns (logpdf, grads) with grads = {"variance": (m,), "inv_lengthscale": (m,), "mean_const": (m,),
     "sigma2": float[, "y": (p*N,)][, "U": (p, m), "S": (m,) for an OILMM]}."""
     f = fx.f
@@ -830,6 +831,17 @@ def logpdf_and_gradient(fx: FiniteGP, y, with_grad_y: bool = False):
     out, gs2, il = C.c_double(), C.c_double(), C.c_int(-1)
     yv = _yvec(y, N * fx.x.out_dim)
     gy = np.zeros(N * fx.x.out_dim) if with_grad_y else None
+    owner = _post_owner(fx)
+    if owner is not None:
+        # logpdf(post(x*, σ²), y*): gradient w.r.t. σ² and y* (test/oilmm.jl:32 `gradient(logpdf, po, y_test)`)
+        if isinstance(f, ILMM) and f.H.shape[0] != fx.x.out_dim:
+            raise RuntimeError("out dim of x != out dim of f.")
+        rc = ctx.lib.lmm_post_logpdf_grad(owner.handle, ptr(pts), N, fx.sigma2, ptr(yv), C.byref(out), C.byref(gs2), ptr(gy), C.byref(il))
+        ctx.check(rc, il.value)
+        grads = {"sigma2": gs2.value}
+        if with_grad_y:
+            grads["y"] = gy
+        return out.value, grads
     if isinstance(f, ILMM) and isinstance(f.H, Orthogonal) and isinstance(f.f, IndependentMOGP):
         lat, H = f.f, f.H
         m = len(lat.fs)
@@ -843,8 +855,22 @@ def logpdf_and_gradient(fx: FiniteGP, y, with_grad_y: bool = False):
         gl = np.zeros((m, 3))
         rc = ctx.lib.lmm_imogp_logpdf_grad(ctx.handle, _descs(f.fs), m, ptr(pts), N, D, fx.sigma2, ptr(yv), fx.x.out_dim, C.byref(out),
                                            ptr(gl), C.byref(gs2), ptr(gy), C.byref(il))
+    elif isinstance(f, ILMM) and isinstance(f.f, IndependentMOGP):  # general mixing matrix, src/ilmm.jl:150-163
+        lat = f.f
+        m = len(lat.fs)
+        Hm = as_f64(np.asarray(f.H), "F")
+        gl = np.zeros((m, 3))
+        gH = np.zeros(Hm.shape, order="F")
+        rc = ctx.lib.lmm_ilmm_logpdf_grad(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(Hm), Hm.shape[0], fx.sigma2, ptr(yv),
+                                          fx.x.out_dim, C.byref(out), ptr(gl), C.byref(gs2), ptr(gy), ptr(gH), C.byref(il))
+        ctx.check(rc, il.value)
+        grads = {"variance": gl[:, 0].copy(), "inv_lengthscale": gl[:, 1].copy(), "mean_const": gl[:, 2].copy(), "sigma2": gs2.value,
+                 "H": np.ascontiguousarray(gH)}
+        if with_grad_y:
+            grads["y"] = gy
+        return out.value, grads
     else:
-        raise TypeError("logpdf_and_gradient is built for OILMM and IndependentMOGP priors")
+        raise TypeError("logpdf_and_gradient is built for OILMM, ILMM and IndependentMOGP priors")
     ctx.check(rc, il.value)
     grads = {"variance": gl[:, 0].copy(), "inv_lengthscale": gl[:, 1].copy(), "mean_const": gl[:, 2].copy(), "sigma2": gs2.value}
     if with_grad_y:

@@ -373,6 +373,35 @@ cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W
   return cudaSuccess;
 }
 
+// X <- X L^{-T} for an upper-triangular X given as full rectangular tiles (zero tiles skipped).
+cudaError_t trsm_right_lt_upper(lmm_ctx* ctx, cudaStream_t st, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch) {
+  const int nt = L.nt, ob = ctx->outer_block;
+  GemmArgs g{};
+  g.A = operand(X); g.B = operand(L); g.C = operand(X);
+  g.W = W; g.w_batch_stride = wstride;
+  g.sym = 0; g.upper = 1; g.k_from_row = 1; g.i0 = 0;
+  cudaError_t e;
+  for (int s0 = 0; s0 < nt; s0 += ob) {
+    const int s1 = (s0 + ob < nt) ? s0 + ob : nt;
+    if (s0 > 0) {
+      g.j0 = s0; g.k0 = 0; g.k1 = s0;
+      if ((e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, s0, batch)) != cudaSuccess) return e;  // rows < s0 have k < s0 terms
+      ++ctx->launches;
+    }
+    for (int jj = s0; jj < s1; ++jj) {
+      if (jj > s0) {
+        g.j0 = jj; g.k0 = s0; g.k1 = jj;
+        if ((e = launch_gemm(st, GEMM_UPDATE, g, 1, jj, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+      g.j0 = jj;
+      if ((e = launch_gemm(st, GEMM_TRSM, g, 1, jj + 1, batch)) != cudaSuccess) return e;
+      ++ctx->launches;
+    }
+  }
+  return cudaSuccess;
+}
+
 size_t factor_bytes_per_latent(int nt) { return (sym_tiles(nt) + (size_t)nt) * TT * sizeof(double); }
 
 void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const double* noise, int lo, int hi, double ls_scale = 1.0) {

@@ -170,4 +170,154 @@ cudaError_t launch_rect_identity(cudaStream_t st, TiledRect X, int batch) {
   return cudaGetLastError();
 }
 
+
+// ---- general-ILMM gradient: the joint (mN x mN) matrix C = blockdiag(K_a) + ΣT ⊗ I -----------------
+// Latent blocks start at multiples of N, not of the tile size, so elements are addressed one by one.
+__device__ __forceinline__ double sym_get(const double* __restrict__ base, int r, int c) {  // r >= c
+  return base[sym_tile_index(r / TILE, c / TILE) * TT + tile_elem(r % TILE, c % TILE)];
+}
+
+// grid (chunks of the lower triangle of one N x N latent block, m).  x is [N][D] (unpadded), alpha the
+// joint vector (latent a at a*N).  partial[(a*nchunks + chunk)*2 + {0,1}] = {<G_aa, κ>, <G_aa, dK_a/ds>}.
+__global__ void __launch_bounds__(256) kgrad_block_kernel(TiledSym negCinv, const double* __restrict__ x, int N, int D,
+                                                          const LatentParams* __restrict__ params, const double* __restrict__ alpha,
+                                                          int form, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double sm[];
+  double* xa = sm;
+  double* xb = xa + TILE * D;
+  double* sa = xb + TILE * D;
+  double* sb = sa + TILE;
+  double* aa = sb + TILE;
+  double* ab = aa + TILE;
+  __shared__ double red[2][256];
+  const int a = blockIdx.y, tl = blockIdx.x, t = threadIdx.x;
+  int I = (int)((sqrt(8.0 * (double)tl + 1.0) - 1.0) * 0.5);
+  while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tl) ++I;
+  while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
+  const int J = tl - (int)((size_t)I * (I + 1) / 2);
+  const LatentParams lp = params[a];
+  for (int i = t; i < TILE * D; i += 256) {
+    const int ra = I * TILE + i / D, rb = J * TILE + i / D;
+    xa[i] = ra < N ? x[(size_t)ra * D + i % D] * lp.inv_ls : 0.0;
+    xb[i] = rb < N ? x[(size_t)rb * D + i % D] * lp.inv_ls : 0.0;
+  }
+  if (t < TILE) {
+    aa[t] = (I * TILE + t < N) ? alpha[(size_t)a * N + I * TILE + t] : 0.0;
+    ab[t] = (J * TILE + t < N) ? alpha[(size_t)a * N + J * TILE + t] : 0.0;
+  }
+  __syncthreads();
+  for (int i = t; i < 2 * TILE; i += 256) {
+    const double* v = (i < TILE) ? xa + (size_t)i * D : xb + (size_t)(i - TILE) * D;
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) s = fma(v[k], v[k], s);
+    if (i < TILE) sa[i] = s; else sb[i - TILE] = s;
+  }
+  __syncthreads();
+  const double* base = negCinv.base;
+  double gv = 0.0, gs = 0.0;
+  for (int e = t; e < TT; e += 256) {
+    const int c = ((e >> 9) << 2) + (e & 3), r = (e >> 2) & 127;
+    const int gr = I * TILE + r, gc = J * TILE + c;
+    if (gr >= N || gc >= N || gc > gr) continue;
+    const double G = 0.5 * (aa[r] * ab[c] + sym_get(base, a * N + gr, a * N + gc));
+    if (gr == gc) {
+      gv += G;
+    } else {
+      const double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)c * D, D, sa[r], sb[c], form);
+      double kap, dk;
+      kappa_and_ds(lp.kind, d2, lp.inv_ls, kap, dk);
+      gv = fma(2.0 * G, kap, gv);
+      gs = fma(2.0 * G, dk, gs);
+    }
+  }
+  red[0][t] = gv; red[1][t] = gs;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) {
+      red[0][t] += red[0][t + w];
+      red[1][t] += red[1][t + w];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    double* out = partial + ((size_t)a * gridDim.x + tl) * 2;
+    out[0] = red[0][0];
+    out[1] = red[1][0] * lp.variance;
+  }
+}
+
+// out[a*3 + {0,1,2}] = {Σ chunks <G,κ>, Σ chunks <G,dK/ds>, Σ_n α[a*N+n]} in a fixed order.
+__global__ void __launch_bounds__(256) kgrad_block_finish_kernel(const double* __restrict__ partial, int nchunks,
+                                                                 const double* __restrict__ alpha, int N, double* __restrict__ out) {
+  __shared__ double red[3][256];
+  const int a = blockIdx.x, t = threadIdx.x;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int i = t; i < nchunks; i += 256) {
+    s0 += partial[((size_t)a * nchunks + i) * 2];
+    s1 += partial[((size_t)a * nchunks + i) * 2 + 1];
+  }
+  for (int i = t; i < N; i += 256) s2 += alpha[(size_t)a * N + i];
+  red[0][t] = s0; red[1][t] = s1; red[2][t] = s2;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w)
+      for (int k = 0; k < 3; ++k) red[k][t] += red[k][t + w];
+    __syncthreads();
+  }
+  if (t < 3) out[(size_t)a * 3 + t] = red[t][0];
+}
+
+// B[a,b] = Σ_n G[(a,n),(b,n)] = Σ_n (α_a[n] α_b[n] - C^{-1}[(a,n),(b,n)])/2  (m x m, symmetric): d lml / dΣT.
+__global__ void __launch_bounds__(256) block_trace_kernel(TiledSym negCinv, const double* __restrict__ alpha, int N, int m,
+                                                          double* __restrict__ B) {
+  __shared__ double red[256];
+  const int a = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  if (b > a) return;
+  double s = 0.0;
+  for (int n = t; n < N; n += 256) s += 0.5 * (alpha[(size_t)a * N + n] * alpha[(size_t)b * N + n] + sym_get(negCinv.base, a * N + n, b * N + n));
+  red[t] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) red[t] += red[t + w];
+    __syncthreads();
+  }
+  if (t == 0) {
+    B[(size_t)b * m + a] = red[0];
+    B[(size_t)a * m + b] = red[0];
+  }
+}
+
+cudaError_t launch_kgrad_joint(cudaStream_t st, TiledSym negCinv, const double* x, int N, int D, const LatentParams* params, int m,
+                               const double* alpha, int form, double* partial, double* out3, double* B) {
+  const size_t smem = (size_t)(2 * TILE * D + 4 * TILE) * sizeof(double);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kgrad_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int ntn = (N + TILE - 1) / TILE;
+  const int nchunks = (int)sym_tiles(ntn);
+  dim3 grid((unsigned)nchunks, (unsigned)m);
+  kgrad_block_kernel<<<grid, 256, smem, st>>>(negCinv, x, N, D, params, alpha, form, partial);
+  kgrad_block_finish_kernel<<<m, 256, 0, st>>>(partial, nchunks, alpha, N, out3);
+  dim3 g2((unsigned)m, (unsigned)m);
+  block_trace_kernel<<<g2, 256, 0, st>>>(negCinv, alpha, N, m, B);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_block_trace(cudaStream_t st, TiledSym negCinv, const double* alpha, int N, int m, double* B) {
+  dim3 g2((unsigned)m, (unsigned)m);
+  block_trace_kernel<<<g2, 256, 0, st>>>(negCinv, alpha, N, m, B);
+  return cudaGetLastError();
+}
+
+// v[i] = a[i] * sa - b[i]
+__global__ void scale_sub_kernel(double* __restrict__ v, const double* __restrict__ a, double sa, const double* __restrict__ b, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = a[i] * sa - b[i];
+}
+cudaError_t launch_scale_sub(cudaStream_t st, double* v, const double* a, double sa, const double* b, size_t n) {
+  scale_sub_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, a, sa, b, n);
+  return cudaGetLastError();
+}
+
 }  // namespace lmm

@@ -105,6 +105,14 @@ cudaError_t launch_kgrad(cudaStream_t st, TiledSym negCinv, int batch, const dou
 cudaError_t launch_kgrad_finish(cudaStream_t st, const double* partial, int ntiles_, int batch, const double* alpha, size_t alpha_stride,
                                 int N, double* out);
 cudaError_t launch_rect_identity(cudaStream_t st, TiledRect X, int batch);
+// general ILMM: contraction of G = (αα' - C^{-1})/2 over the joint (mN) matrix (batch 1, negCinv = -C^{-1}):
+// out3[a*3+{0,1,2}] = {<G_aa,κ_a>, <G_aa,dK_a/ds>, Σ_n α_a}; B (m x m) = block traces (d lml / dΣT).
+// partial: m * sym_tiles(ceil(N/128)) * 2 doubles of scratch.  x is [N][D] unpadded.
+cudaError_t launch_kgrad_joint(cudaStream_t st, TiledSym negCinv, const double* x, int N, int D, const LatentParams* params, int m,
+                               const double* alpha, int form, double* partial, double* out3, double* B);
+// B (m x m) = block traces of G over a joint (m*N) matrix whose latent blocks start at multiples of N
+cudaError_t launch_block_trace(cudaStream_t st, TiledSym negCinv, const double* alpha, int N, int m, double* B);
+cudaError_t launch_scale_sub(cudaStream_t st, double* v, const double* a, double sa, const double* b, size_t n);
 }  // namespace lmm
 
 namespace lmm {

@@ -637,6 +637,135 @@ def oilmm_logpdf_grad(model: OILMMModel, x, sigma2: float, y: np.ndarray):
                 "mean_const": np.array([q[3] for q in parts]), "sigma2": float(g_sigma2), "y": g_y.reshape(-1), "U": g_U, "S": g_S}
 
 
+def ilmm_logpdf_grad(fs: Sequence[GP], H: np.ndarray, x, sigma2: float, y: np.ndarray):
+    """Analytic gradient of src/ilmm.jl:150-163 (projected form incl. `project` :61-68 and
+    `regulariser` :171-181) w.r.t. latent hyper-parameters, σ², y and the dense mixing matrix H
+    (what ``Zygote.gradient(logpdf, ilmmx, y)`` differentiates, test/ilmm.jl:31).
+
+    With δ = vec((TY)') - μ, α = C⁻¹δ, G = (αα' - C⁻¹)/2 over the joint (mN) matrix
+    C = blockdiag(K_a) + ΣT ⊗ I:  ∂/∂θ_a = <G_aa, ∂K_a/∂θ>,  ∂/∂ΣT[a,b] = Σ_n G[(a,n),(b,n)],
+    ∂/∂(TY) = -A (A = α as m x N); the chain through T = M⁻¹H'/σ², M = H'H/σ² + 1e-9 I and
+    ΣT = σ² T T' is done on the small matrices."""
+    N = _as2d(x).shape[0]
+    H = np.asarray(H, dtype=np.float64)
+    p, m = H.shape
+    Y = reshape_y(y, N)
+    M = H.T @ H / sigma2 + 1e-9 * np.eye(m)
+    W = np.linalg.inv(M)
+    T = W @ H.T / sigma2
+    ST = sigma2 * (T @ T.T)
+    Z = T @ Y
+    K = _latent_prior_cov(fs, x, "direct")
+    C = K + np.kron(ST, np.eye(N))
+    mean = np.concatenate([np.full(N, f.mean_const) for f in fs])
+    L = _chol_lower(C)
+    delta = Z.reshape(-1) - mean
+    alpha = _bwd(L, _fwd(L, delta))
+    Cinv = _bwd(L, _fwd(L, np.eye(m * N)))
+    G = 0.5 * (np.outer(alpha, alpha) - Cinv)
+    R = Y - H @ Z
+    resid = float(np.sum(R * R))
+    _, logdet_ST = np.linalg.slogdet(ST)
+    lml = -0.5 * (m * N * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(delta @ alpha))
+    reg = -(N * ((p - m) * LOG2PI + (p * math.log(sigma2) - logdet_ST)) + resid / sigma2) / 2.0
+    A = alpha.reshape(m, N)
+    g_var = np.zeros(m)
+    g_s = np.zeros(m)
+    for a, f in enumerate(fs):
+        Gaa = G[a * N:(a + 1) * N, a * N:(a + 1) * N]
+        g_var[a] = float(np.sum(Gaa * kernelmatrix(f.kernel, x, form="direct"))) / f.kernel.variance
+        g_s[a] = float(np.sum(Gaa * _dkernel_ds(f.kernel, x)))
+    B = np.array([[float(np.trace(G[a * N:(a + 1) * N, b * N:(b + 1) * N])) for b in range(m)] for a in range(m)])
+    # direct cotangents
+    HtR = H.T @ R
+    Vm = HtR / sigma2 - A                       # m x N
+    bar_T = Vm @ Y.T                            # -A Y' + H'R Y'/σ²
+    bar_H = R @ Z.T / sigma2
+    bar_ST = B + 0.5 * N * np.linalg.inv(ST)
+    g_y = T.T @ Vm - R / sigma2
+    g_sigma2 = -0.5 * (N * p / sigma2 - resid / sigma2 ** 2)
+    # ΣT = σ² T T'
+    g_sigma2 += float(np.sum(bar_ST * (T @ T.T)))
+    bar_T = bar_T + sigma2 * (bar_ST + bar_ST.T) @ T
+    # T = W H'/σ²
+    g_sigma2 -= float(np.sum(bar_T * T)) / sigma2
+    bar_H = bar_H + bar_T.T @ W / sigma2
+    Zm = bar_T @ H / sigma2
+    bar_M = -W @ Zm @ W
+    bar_H = bar_H + H @ (bar_M + bar_M.T) / sigma2
+    g_sigma2 -= float(np.sum(bar_M * (H.T @ H))) / sigma2 ** 2
+    return lml + reg, {"variance": g_var, "inv_lengthscale": g_s, "mean_const": A.sum(axis=1), "sigma2": float(g_sigma2),
+                       "y": g_y.reshape(-1), "H": bar_H}
+
+
+def oilmm_post_logpdf_grad(model: OILMMModel, xs, sigma2: float, ys: np.ndarray):
+    """Gradient of ``logpdf(post(x*, σ²), y*)`` (test/oilmm.jl:32 `gradient(logpdf, po, y_test)`) w.r.t. σ² and
+    y*, the posterior's data (α, C, x) and hyper-parameters held fixed.  ``model.fs`` are PosteriorGPs
+    (OILMM) -- pass ``U = I, S = 1`` for an IndependentMOGP posterior (no regulariser: p == m)."""
+    Ns = _as2d(xs).shape[0]
+    Y = reshape_y(ys, Ns)
+    p, m = model.U.shape
+    T, ST = project_orthogonal(model.U, model.S, sigma2)
+    Ty = T @ Y
+    lp, g_s2, g_y = 0.0, 0.0, np.zeros((p, Ns))
+    for i, f in enumerate(model.fs):
+        C = gp_cov(f, xs) + ST[i] * np.eye(Ns)
+        L = _chol_lower(C)
+        delta = Ty[i] - gp_mean(f, xs)
+        alpha = _bwd(L, _fwd(L, delta))
+        Li = _fwd(L, np.eye(Ns))
+        lp += -0.5 * (Ns * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(delta @ alpha))
+        g_s2 += 0.5 * (float(alpha @ alpha) - float(np.sum(Li * Li))) / model.S[i]
+        g_y -= np.outer(T[i], alpha)
+    if p > m:
+        R = (np.eye(p) - model.U @ model.U.T) @ Y
+        resid = float(np.sum(R * R))
+        lp += regulariser_orthogonal(model.U, model.S, sigma2, Y)
+        g_s2 += -0.5 * (Ns * (p - m) / sigma2 - resid / sigma2 ** 2)
+        g_y -= R / sigma2
+    else:
+        lp += -0.5 * Ns * float(np.sum(np.log(model.S)))
+    return lp, {"sigma2": float(g_s2), "y": g_y.reshape(-1)}
+
+
+def ilmm_post_logpdf_grad(post: ILMMPosterior, xs, sigma2: float, ys: np.ndarray):
+    """Same for a general-ILMM posterior (test/ilmm.jl:32): σ² enters through `project` (T, ΣT) and the
+    regulariser; the joint latent posterior (m*, C*) is held fixed."""
+    Ns = _as2d(xs).shape[0]
+    H = post.H
+    p, m = H.shape
+    Y = reshape_y(ys, Ns)
+    M = H.T @ H / sigma2 + 1e-9 * np.eye(m)
+    W = np.linalg.inv(M)
+    T = W @ H.T / sigma2
+    ST = sigma2 * (T @ T.T)
+    Z = T @ Y
+    mean, cov = _ilmm_latent_mean_and_cov(post, xs, jitter=0.0)
+    C = cov + np.kron(ST, np.eye(Ns))
+    L = _chol_lower(C)
+    delta = Z.reshape(-1) - mean
+    alpha = _bwd(L, _fwd(L, delta))
+    Cinv = _bwd(L, _fwd(L, np.eye(m * Ns)))
+    G = 0.5 * (np.outer(alpha, alpha) - Cinv)
+    R = Y - H @ Z
+    resid = float(np.sum(R * R))
+    _, logdet_ST = np.linalg.slogdet(ST)
+    lp = -0.5 * (m * Ns * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(delta @ alpha))
+    lp += -(Ns * ((p - m) * LOG2PI + (p * math.log(sigma2) - logdet_ST)) + resid / sigma2) / 2.0
+    A = alpha.reshape(m, Ns)
+    B = np.array([[float(np.trace(G[a * Ns:(a + 1) * Ns, b * Ns:(b + 1) * Ns])) for b in range(m)] for a in range(m)])
+    Vm = H.T @ R / sigma2 - A
+    bar_T = Vm @ Y.T
+    bar_ST = B + 0.5 * Ns * np.linalg.inv(ST)
+    g_y = T.T @ Vm - R / sigma2
+    g_s2 = -0.5 * (Ns * p / sigma2 - resid / sigma2 ** 2) + float(np.sum(bar_ST * (T @ T.T)))
+    bar_T = bar_T + sigma2 * (bar_ST + bar_ST.T) @ T
+    g_s2 -= float(np.sum(bar_T * T)) / sigma2
+    bar_M = -W @ (bar_T @ H / sigma2) @ W
+    g_s2 -= float(np.sum(bar_M * (H.T @ H))) / sigma2 ** 2
+    return lp, {"sigma2": float(g_s2), "y": g_y.reshape(-1)}
+
+
 # --------------------------------------------------------------------------------------------
 # Synthetic workloads shared by tests and bench (SURVEY.md §8d): identical bytes for oracle and GPU
 # --------------------------------------------------------------------------------------------

@@ -493,6 +493,58 @@ def test_logpdf_gradient(lmm, N, p, m):
     np.testing.assert_allclose(gi["y"], np.concatenate([q[5] for q in parts]), rtol=1e-7, atol=1e-9)
 
 
+@pytest.mark.parametrize("N,p,m,D", [(40, 4, 3, 1), (150, 5, 2, 2), (300, 6, 3, 1)])
+def test_ilmm_logpdf_gradient(lmm, N, p, m, D):
+    """rrule of the general-ILMM logpdf (test/ilmm.jl:31 `gradient(logpdf, ilmmx, y_train)`): joint potri +
+    block-wise kernel-gradient contraction + host chain through `project`, against the oracle's analytic
+    gradient (itself checked against finite differences on CPU)."""
+    x, xs, U, S, fs, y = make_problem(N, p, m, 1, seed=71 + N, D=D, means=True)
+    H = np.random.default_rng(N).uniform(0.0, 1.0, (p, m))
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), H)
+    xin = x if D == 1 else lmm.ColVecs(x.T)
+    lp, g = lmm.logpdf_and_gradient(f(lmm.MOInputIsotopicByOutputs(xin, p), 0.2), y, with_grad_y=True)
+    lpr, gr = o.ilmm_logpdf_grad(fs, H, x, 0.2, y)
+    assert rel(lp, lpr) < RTOL
+    for k in ("variance", "inv_lengthscale", "mean_const"):
+        np.testing.assert_allclose(g[k], gr[k], rtol=1e-7, atol=1e-8)
+    assert rel(g["sigma2"], gr["sigma2"]) < 1e-7
+    np.testing.assert_allclose(g["y"], gr["y"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(g["H"], gr["H"], rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("N,Ns,p,m", [(50, 7, 4, 3), (300, 140, 5, 2)])
+def test_posterior_logpdf_gradient(lmm, N, Ns, p, m):
+    """`gradient(logpdf, po, y_test)` (test/oilmm.jl:32, test/ilmm.jl:32, test/independent_mogp.jl:66): value and
+    gradient w.r.t. σ² and y* of the posterior-predictive logpdf for all three model kinds."""
+    x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=83 + N, means=True)
+    rng = np.random.default_rng(N)
+    ys = rng.standard_normal(p * Ns)
+    lat = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    O = lmm.MOInputIsotopicByOutputs
+    # OILMM
+    po = lmm.posterior(lmm.ILMM(lat, lmm.Orthogonal(U, S))(O(x, p), 0.1), y)
+    lp, g = lmm.logpdf_and_gradient(po(O(xs, p), 0.2), ys, with_grad_y=True)
+    lpr, gr = o.oilmm_post_logpdf_grad(o.oilmm_posterior(o.OILMMModel(fs, U, S), x, 0.1, y), xs, 0.2, ys)
+    assert rel(lp, lpr) < RTOL
+    assert rel(g["sigma2"], gr["sigma2"]) < 1e-7
+    np.testing.assert_allclose(g["y"], gr["y"], rtol=1e-7, atol=1e-9)
+    # IndependentMOGP
+    pi = lmm.posterior(lat(O(x, m), 0.1), y[: m * N])
+    lp, g = lmm.logpdf_and_gradient(pi(O(xs, m), 0.2), ys[: m * Ns], with_grad_y=True)
+    lpr, gr = o.oilmm_post_logpdf_grad(o.OILMMModel(o.imogp_posterior(fs, x, 0.1, y[: m * N]), np.eye(m), np.ones(m)), xs, 0.2, ys[: m * Ns])
+    assert rel(lp, lpr) < RTOL
+    assert rel(g["sigma2"], gr["sigma2"]) < 1e-7
+    np.testing.assert_allclose(g["y"], gr["y"], rtol=1e-7, atol=1e-9)
+    # general ILMM
+    H = rng.uniform(0.0, 1.0, (p, m))
+    pl = lmm.posterior(lmm.ILMM(lat, H)(O(x, p), 0.1), y)
+    lp, g = lmm.logpdf_and_gradient(pl(O(xs, p), 0.2), ys, with_grad_y=True)
+    lpr, gr = o.ilmm_post_logpdf_grad(o.ilmm_posterior(fs, H, x, 0.1, y), xs, 0.2, ys)
+    assert rel(lp, lpr) < 1e-8
+    assert rel(g["sigma2"], gr["sigma2"]) < 1e-6
+    np.testing.assert_allclose(g["y"], gr["y"], rtol=1e-6, atol=1e-8)
+
+
 def test_imogp_process_cov_mixed_orderings(lmm):
     """cov(f, x, y) with by-outputs / by-features inputs in all four combinations
     (src/independent_mogp.jl:60-71,181-215; test/independent_mogp.jl:135-141)."""

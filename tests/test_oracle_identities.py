@@ -224,3 +224,74 @@ def test_oracle_gradient_matches_finite_differences():
         Um[j, i] -= h
         fd = (o.oilmm_logpdf(o.OILMMModel(fs, Up, S), x, 0.2, y) - o.oilmm_logpdf(o.OILMMModel(fs, Um, S), x, 0.2, y)) / (2 * h)
         assert g["U"][j, i] == pytest.approx(fd, rel=5e-6, abs=1e-6)
+
+
+def test_oracle_ilmm_gradient_matches_finite_differences():
+    """Analytic gradient of the general-ILMM logpdf (src/ilmm.jl:150-163 through `project` and
+    `regulariser`; the oracle for lmm_ilmm_logpdf_grad) against central differences."""
+    rng = np.random.default_rng(3)
+    N, p, m = 17, 4, 3
+    x = np.sort(rng.uniform(0, 4, N))
+    H = rng.uniform(0, 1, (p, m))
+    y = rng.standard_normal(p * N)
+    s2 = 0.3
+    par = np.array([[1.3, 0.7, 0.2], [0.8, 1.4, -0.5], [1.1, 0.9, 1.0]])
+    kinds = [o.SE, o.MATERN32, o.MATERN52]
+
+    def mk(q):
+        return [o.GP(o.Kernel(kinds[i], q[i, 0], q[i, 1]), q[i, 2]) for i in range(m)]
+
+    def f(q=par, Hm=H, s=s2, yy=y):
+        return o.ilmm_logpdf(mk(q), Hm, x, s, yy, form="direct")
+
+    lp, g = o.ilmm_logpdf_grad(mk(par), H, x, s2, y)
+    assert lp == pytest.approx(f(), rel=1e-12)
+    h = 1e-6
+    for i in range(m):
+        for c, field in enumerate(("variance", "inv_lengthscale", "mean_const")):
+            qp, qm = par.copy(), par.copy()
+            qp[i, c] += h
+            qm[i, c] -= h
+            assert g[field][i] == pytest.approx((f(q=qp) - f(q=qm)) / (2 * h), rel=5e-6, abs=1e-6)
+    assert g["sigma2"] == pytest.approx((f(s=s2 + h) - f(s=s2 - h)) / (2 * h), rel=5e-6)
+    for j in (0, 23, p * N - 1):
+        e = np.zeros(p * N)
+        e[j] = h
+        assert g["y"][j] == pytest.approx((f(yy=y + e) - f(yy=y - e)) / (2 * h), rel=5e-6, abs=1e-7)
+    for j in range(p):
+        for i in range(m):
+            Hp, Hm_ = H.copy(), H.copy()
+            Hp[j, i] += h
+            Hm_[j, i] -= h
+            assert g["H"][j, i] == pytest.approx((f(Hm=Hp) - f(Hm=Hm_)) / (2 * h), rel=5e-6, abs=1e-6)
+
+
+def test_oracle_posterior_logpdf_gradient_matches_finite_differences():
+    """d/dσ² and d/dy* of logpdf(post(x*, σ²), y*) for OILMM, IndependentMOGP and general-ILMM posteriors."""
+    rng = np.random.default_rng(5)
+    N, p, m, Ns = 20, 4, 3, 6
+    x = np.sort(rng.uniform(0, 4, N))
+    xs = rng.uniform(0, 4, Ns)
+    U, S = o.orthogonal_from_seed(p, m, seed=2)
+    fs = [o.GP(o.Kernel(o.SE, 0.9, 1.2), 0.3), o.GP(o.Kernel(o.MATERN32, 1.3, 0.8), -0.2), o.GP(o.Kernel(o.MATERN52, 0.7, 1.5), 0.1)]
+    y, ys = rng.standard_normal(p * N), rng.standard_normal(p * Ns)
+    h = 1e-6
+    e = np.zeros(p * Ns)
+    e[7] = h
+    post = o.oilmm_posterior(o.OILMMModel(fs, U, S), x, 0.1, y)
+    lp, g = o.oilmm_post_logpdf_grad(post, xs, 0.2, ys)
+    assert lp == pytest.approx(o.oilmm_logpdf(post, xs, 0.2, ys), rel=1e-12)
+    assert g["sigma2"] == pytest.approx((o.oilmm_logpdf(post, xs, 0.2 + h, ys) - o.oilmm_logpdf(post, xs, 0.2 - h, ys)) / (2 * h), rel=5e-6)
+    assert g["y"][7] == pytest.approx((o.oilmm_logpdf(post, xs, 0.2, ys + e) - o.oilmm_logpdf(post, xs, 0.2, ys - e)) / (2 * h), rel=5e-6)
+    posts = o.imogp_posterior(fs, x, 0.1, y[: m * N])
+    yi = ys[: m * Ns]
+    ref = lambda s2: sum(o.finite_logpdf(posts[i], xs, s2, yi.reshape(m, Ns)[i]) for i in range(m))
+    lp, g = o.oilmm_post_logpdf_grad(o.OILMMModel(posts, np.eye(m), np.ones(m)), xs, 0.2, yi)
+    assert lp == pytest.approx(ref(0.2), rel=1e-12)
+    assert g["sigma2"] == pytest.approx((ref(0.2 + h) - ref(0.2 - h)) / (2 * h), rel=5e-6)
+    H = rng.uniform(0, 1, (p, m))
+    ip = o.ilmm_posterior(fs, H, x, 0.1, y)
+    lp, g = o.ilmm_post_logpdf_grad(ip, xs, 0.2, ys)
+    assert lp == pytest.approx(o.ilmm_post_logpdf(ip, xs, 0.2, ys), rel=1e-12)
+    assert g["sigma2"] == pytest.approx((o.ilmm_post_logpdf(ip, xs, 0.2 + h, ys) - o.ilmm_post_logpdf(ip, xs, 0.2 - h, ys)) / (2 * h), rel=5e-6)
+    assert g["y"][7] == pytest.approx((o.ilmm_post_logpdf(ip, xs, 0.2, ys + e) - o.ilmm_post_logpdf(ip, xs, 0.2, ys - e)) / (2 * h), rel=5e-6)
