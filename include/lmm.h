@@ -157,9 +157,9 @@ int lmm_post_mean_and_cov(lmm_post* post, const double* xs, int Ns, double sigma
 int lmm_prior_mean_and_cov(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* xs, int Ns,
                            int D, const double* H, int p, double sigma2, double latent_jitter,
                            int out_dim, double* mean, double* cov);
-/* posterior(post(x2, σ²), y2): sequential conditioning of an OILMM / IndependentMOGP posterior
- * (src/oilmm.jl:116-134 / src/independent_mogp.jl:119-126 with PosteriorGP latents).  Returns a new
- * handle over the union of the inputs; the old handle stays valid. */
+/* posterior(post(x2, σ²), y2): sequential conditioning of an OILMM / IndependentMOGP / general-ILMM
+ * posterior (src/oilmm.jl:116-134 / src/independent_mogp.jl:119-126 / src/ilmm.jl:184-198 with PosteriorGP
+ * latents).  Returns a new handle over the union of the inputs; the old handle stays valid. */
 int lmm_post_condition(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys,
                        lmm_post** out_post, int* info_latent);
 /* logpdf(post(x*, σ²), y*)  (test/oilmm.jl:84): OILMM logpdf with PosteriorGP latents. */
@@ -178,6 +178,11 @@ int lmm_post_rand(lmm_post* post, const double* xs, int Ns, double sigma2, const
  * not resident on this rank. */
 int lmm_post_export(lmm_post* post, int i, double* L, double* alpha, double* delta);
 int lmm_post_info(lmm_post* post, int* kind, int* m, int* p, int* N, int* D, int64_t* device_bytes);
+/* Serialisable posterior: the handle's metadata followed by its device arrays verbatim
+ * (tiled factors, α, δ, inputs), little-endian Float64.  A loaded handle answers every lmm_post_* call
+ * bit-identically to the saved one; no recomputation.  Each rank saves / loads its own shard. */
+int lmm_post_save(lmm_post* post, const char* path);
+int lmm_post_load(lmm_ctx* ctx, const char* path, lmm_post** out_post);
 int lmm_post_free(lmm_post* post);
 
 /* ---- IndependentMOGP: src/independent_mogp.jl ---------------------------------------------- */
@@ -190,6 +195,18 @@ int lmm_imogp_logpdf(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x
 int lmm_imogp_posterior(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
                         double sigma2, const double* y, int out_dim, lmm_post** out_post,
                         double* out_logpdf, int* info_latent);
+/* IndependentMOGP with non-isotropic observation noise (AbstractGPs generic FiniteGP path; the
+ * reference's fast methods dispatch on Σy::Diagonal{<:Real,<:Fill} only, src/independent_mogp.jl:44-46;
+ * test/independent_mogp.jl:72-75 exercises `f(x_train_mo, Σy)` with a dense Σy).
+ * LMM_NOISE_DIAG: Sigma_y is the m*N vector of per-observation variances (by outputs) -- the latents
+ * stay independent; LMM_NOISE_DENSE: Sigma_y is (mN x mN) column-major -- one joint factor of
+ * blockdiag(K_a) + Σy, the returned handle behaves like an ILMM posterior with identity mixing.
+ * out_post / out_logpdf nullable (not both). */
+#define LMM_NOISE_DIAG 1
+#define LMM_NOISE_DENSE 2
+int lmm_imogp_posterior_noise(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
+                              const double* Sigma_y, int noise_kind, const double* y, int out_dim,
+                              lmm_post** out_post, double* out_logpdf, int* info_latent);
 /* rand src/independent_mogp.jl:83-86. */
 int lmm_imogp_rand(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
                    double sigma2, int out_dim, const double* z, double* out, int* info_latent);

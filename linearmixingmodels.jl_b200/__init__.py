@@ -16,6 +16,8 @@ from .api import (  # noqa: F401
     potrf_batched,
     set_default_context,
     set_ilmm_form,
+    save_posterior,
+    load_posterior,
 )
 from . import _lib, api, dist  # noqa: F401
 

@@ -71,9 +71,12 @@ SIGNATURES = {
     "lmm_post_rand": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _ip]),
     "lmm_post_export": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp]),
     "lmm_post_info": (C.c_int, [_vp, _ip, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
+    "lmm_post_save": (C.c_int, [_vp, C.c_char_p]),
+    "lmm_post_load": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "lmm_post_free": (C.c_int, [_vp]),
     "lmm_imogp_logpdf": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_double, _vp, C.c_int, _dp, _vp, _ip]),
     "lmm_imogp_posterior": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_double, _vp, C.c_int, C.POINTER(_vp), _dp, _ip]),
+    "lmm_imogp_posterior_noise": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, C.POINTER(_vp), _dp, _ip]),
     "lmm_imogp_rand": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_double, C.c_int, _vp, _vp, _ip]),
     "lmm_imogp_cross_cov": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "lmm_reorder_indices": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp]),

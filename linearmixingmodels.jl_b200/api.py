@@ -17,6 +17,7 @@ liblmm on the GPU; nothing here computes on the CPU beyond argument marshalling.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 import weakref
 from dataclasses import dataclass
@@ -419,13 +420,25 @@ class Normal:
 
 
 class FiniteGP:
-    """`f(x, σ²)`; only isotropic scalar noise (`Diagonal(Fill(σ², n))`) reaches the fast paths."""
+    """`f(x, σ²)` -- AbstractGPs: a scalar gives `Diagonal(Fill(σ², n))` (the reference's fast paths), a vector
+    `Diagonal(v)`, a matrix a dense Σy.  Non-scalar noise is only defined for an IndependentMOGP (the
+    AbstractGPs generic FiniteGP path, test/independent_mogp.jl:72-75); ILMM / OILMM methods dispatch on
+    scalar noise only (src/ilmm.jl:45) and raise TypeError otherwise, as the reference's MethodError does."""
 
     def __init__(self, f: AbstractGP, x, sigma2=1e-18):
         self.f, self.x = f, x
-        if not isinstance(sigma2, (int, float, np.floating)):
-            raise TypeError("only scalar observation noise is supported on this path (src/ilmm.jl:45)")
-        self.sigma2 = float(sigma2)
+        self.noise = None  # ndarray (1-D: diagonal, 2-D: dense), in the ordering of `x`
+        if isinstance(sigma2, (int, float, np.floating)):
+            self.sigma2 = float(sigma2)
+        else:
+            a = np.asarray(sigma2, dtype=np.float64)
+            n = len(x)
+            if a.ndim not in (1, 2) or a.shape[0] != n or (a.ndim == 2 and a.shape[1] != n):
+                raise ValueError("observation noise must be a scalar, a length-n vector or an n x n matrix")
+            if isinstance(f, ILMM):
+                raise TypeError("ILMM / OILMM methods need scalar observation noise (src/ilmm.jl:45)")
+            self.noise = a
+            self.sigma2 = 0.0
 
     def __len__(self):
         return len(self.x)
@@ -481,6 +494,8 @@ def _ctx_of(fx: FiniteGP) -> Context:
             owner = lat._owner
     elif isinstance(f, IndependentMOGP) and isinstance(f.fs[0], PosteriorGP):
         owner = f.fs[0]._owner
+    elif isinstance(f, _JointPosterior):
+        owner = f._owner
     return owner.ctx if owner is not None else default_context()
 
 
@@ -492,6 +507,20 @@ def _post_owner(fx: FiniteGP) -> Optional[_PostHandle]:
     if isinstance(lat, _JointPosterior):
         return lat._owner
     return None
+
+
+def _noise_by_outputs(fx: FiniteGP):
+    """(kind, Σy in by-outputs order) for a FiniteGP with non-scalar noise: kind 1 diagonal, 2 dense
+    (src/independent_mogp.jl:149-151 `reorder_by_outputs(Σy, x)`)."""
+    a = fx.noise
+    if isinstance(fx.x, MOInputIsotopicByFeatures):
+        idx = indices_which_reorder_features_to_outputs(fx.x)
+        a = a[idx] if a.ndim == 1 else a[np.ix_(idx, idx)]
+    return (1, np.ascontiguousarray(a)) if a.ndim == 1 else (2, np.asfortranarray(a))
+
+
+def _add_noise_to_var(fx: FiniteGP, V: np.ndarray) -> np.ndarray:
+    return V if fx.noise is None else V + (fx.noise if fx.noise.ndim == 1 else np.diag(fx.noise))
 
 
 def _require_by_outputs(fx: FiniteGP):
@@ -526,10 +555,20 @@ def _logpdf_impl(fx: FiniteGP, y):
         # src/independent_mogp.jl:222-229
         xo = MOInputIsotopicByOutputs(fx.x.x, fx.x.out_dim)
         idx = indices_which_reorder_features_to_outputs(fx.x)
-        return _logpdf_impl(FiniteGP(f, xo, fx.sigma2), np.asarray(y, dtype=np.float64)[idx])
+        noise = fx.sigma2 if fx.noise is None else _noise_by_outputs(fx)[1]
+        return _logpdf_impl(FiniteGP(f, xo, noise), np.asarray(y, dtype=np.float64)[idx])
     _require_by_outputs(fx)
     pts = _points(fx.x.x)
     N, D = int(pts.shape[0]), int(pts.shape[1])
+    if fx.noise is not None:
+        if owner is not None or not isinstance(f, IndependentMOGP):
+            raise NotImplementedError("non-scalar observation noise is built for IndependentMOGP priors")
+        kind, Sy = _noise_by_outputs(fx)
+        yv = _yvec(y, N * fx.x.out_dim)
+        rc = lib.lmm_imogp_posterior_noise(ctx.handle, _descs(f.fs), len(f.fs), ptr(pts), N, D, ptr(Sy), kind, ptr(yv), fx.x.out_dim, None,
+                                           C.byref(out), C.byref(il))
+        ctx.check(rc, il.value)
+        return out.value, None
     if owner is not None:
         if isinstance(f, ILMM) and f.H.shape[0] != fx.x.out_dim:
             raise RuntimeError("out dim of x != out dim of f.")
@@ -583,6 +622,12 @@ def posterior(fx: FiniteGP, y, with_logpdf: bool = False):
     f = fx.f
     ctx = _ctx_of(fx)
     lib = ctx.lib
+    if isinstance(f, IndependentMOGP) and isinstance(fx.x, MOInputIsotopicByFeatures):
+        # AbstractGPs generic posterior on by-features inputs == the by-outputs posterior of the reordered data
+        xo = MOInputIsotopicByOutputs(fx.x.x, fx.x.out_dim)
+        idx = indices_which_reorder_features_to_outputs(fx.x)
+        noise = fx.sigma2 if fx.noise is None else _noise_by_outputs(fx)[1]
+        return posterior(FiniteGP(f, xo, noise), np.asarray(y, dtype=np.float64)[idx], with_logpdf)
     _require_by_outputs(fx)
     pts = _points(fx.x.x)
     N, D = int(pts.shape[0]), int(pts.shape[1])
@@ -591,17 +636,35 @@ def posterior(fx: FiniteGP, y, with_logpdf: bool = False):
     il = C.c_int(-1)
     lp = C.byref(out) if with_logpdf else None
     owner0 = _post_owner(fx)
+    if fx.noise is not None:
+        if owner0 is not None or not isinstance(f, IndependentMOGP):
+            raise NotImplementedError("non-scalar observation noise is built for IndependentMOGP priors")
+        kind, Sy = _noise_by_outputs(fx)
+        m = len(f.fs)
+        yv = _yvec(y, N * fx.x.out_dim)
+        rc = lib.lmm_imogp_posterior_noise(ctx.handle, _descs(f.fs), m, ptr(pts), N, D, ptr(Sy), kind, ptr(yv), fx.x.out_dim, C.byref(h), lp,
+                                           C.byref(il))
+        ctx.check(rc, il.value)
+        if kind == 1:
+            owner = _PostHandle(ctx, h, N)
+            post = IndependentMOGP([PosteriorGP(owner, i, g) for i, g in enumerate(f.fs)])
+        else:  # dense Σy couples the outputs: one joint PosteriorGP{IndependentMOGP}
+            post = _JointPosterior(_PostHandle(ctx, h, N, joint_n=m * N), f)
+        return (post, out.value) if with_logpdf else post
     if owner0 is not None:
         # sequential conditioning: posterior(post(x2, σ²), y2)
         if isinstance(f, ILMM) and f.H.shape[0] != fx.x.out_dim:
             raise RuntimeError("out dim of x != out dim of f.")
         lat = f.f if isinstance(f, ILMM) else f
-        if not isinstance(lat, IndependentMOGP):
-            raise NotImplementedError("sequential conditioning of a general-ILMM posterior is not built")
         yv = _yvec(y, N * fx.x.out_dim)
         logp = logpdf(fx, y) if with_logpdf else None
         rc = lib.lmm_post_condition(owner0.handle, ptr(pts), N, fx.sigma2, ptr(yv), C.byref(h), C.byref(il))
         ctx.check(rc, il.value)
+        if isinstance(lat, _JointPosterior):  # general ILMM: src/ilmm.jl:184-198 on PosteriorGP{IndependentMOGP} latents
+            m = len(lat.prior.fs)
+            owner = _PostHandle(ctx, h, owner0.N + N, joint_n=m * (owner0.N + N))
+            post = ILMM(_JointPosterior(owner, lat.prior), f.H)
+            return (post, logp) if with_logpdf else post
         owner = _PostHandle(ctx, h, owner0.N + N)
         newlat = IndependentMOGP([PosteriorGP(owner, i, g.prior) for i, g in enumerate(lat.fs)])
         post = ILMM(newlat, f.H) if isinstance(f, ILMM) else newlat
@@ -646,7 +709,7 @@ def mean_and_var(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
     lib = ctx.lib if ctx else None
     x = fx.x
     reorder = None
-    if isinstance(f, IndependentMOGP) and isinstance(x, MOInputIsotopicByFeatures):
+    if isinstance(f, (IndependentMOGP, _JointPosterior)) and isinstance(x, MOInputIsotopicByFeatures):
         reorder = indices_which_reorder_outputs_to_features(x)  # src/independent_mogp.jl:169-179
         x = MOInputIsotopicByOutputs(x.x, x.out_dim)
     elif not isinstance(x, MOInputIsotopicByOutputs):
@@ -679,7 +742,7 @@ def mean_and_var(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
         raise TypeError(f"mean_and_var not defined for FiniteGP of {type(f).__name__}")
     if reorder is not None:
         M, V = M[reorder], V[reorder]
-    return M, V
+    return M, _add_noise_to_var(fx, V)
 
 
 def mean_and_cov(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
@@ -690,7 +753,7 @@ def mean_and_cov(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
     owner = _post_owner(fx)
     x = fx.x
     reorder = None
-    if isinstance(f, IndependentMOGP) and isinstance(x, MOInputIsotopicByFeatures):
+    if isinstance(f, (IndependentMOGP, _JointPosterior)) and isinstance(x, MOInputIsotopicByFeatures):
         reorder = indices_which_reorder_outputs_to_features(x)  # src/independent_mogp.jl:181-186
         x = MOInputIsotopicByOutputs(x.x, x.out_dim)
     elif not isinstance(x, MOInputIsotopicByOutputs):
@@ -718,6 +781,8 @@ def mean_and_cov(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
     Cm = np.ascontiguousarray(Cm)
     if reorder is not None:
         M, Cm = M[reorder], Cm[np.ix_(reorder, reorder)]
+    if fx.noise is not None:
+        Cm = Cm + (np.diag(fx.noise) if fx.noise.ndim == 1 else fx.noise)
     return M, Cm
 
 
@@ -779,7 +844,7 @@ def _rand_one(rng, fx: FiniteGP) -> np.ndarray:
     ctx = _ctx_of(fx)
     lib = ctx.lib
     owner = _post_owner(fx)
-    by_features = isinstance(f, IndependentMOGP) and isinstance(fx.x, MOInputIsotopicByFeatures)
+    by_features = isinstance(f, (IndependentMOGP, _JointPosterior)) and isinstance(fx.x, MOInputIsotopicByFeatures)
     if not by_features:
         _require_by_outputs(fx)
     pts = _points(fx.x.x)
@@ -787,6 +852,18 @@ def _rand_one(rng, fx: FiniteGP) -> np.ndarray:
     p = fx.x.out_dim
     il = C.c_int(-1)
     out = np.zeros(p * N)
+    if fx.noise is not None:
+        # AbstractGPs generic `rand(rng, fx) = m + cholesky(K + Σy).U' z`: covariance and factor on the device
+        M, Cm = mean_and_cov(fx)
+        L, _, info = potrf_batched(Cm, ctx)
+        if info[0] > 0:
+            raise PosDefException(int(info[0]))
+        return M + L[0] @ rng.standard_normal(p * N)
+    if isinstance(f, _JointPosterior):
+        z = rng.standard_normal(p * N)
+        rc = lib.lmm_post_rand(owner.handle, ptr(pts), N, fx.sigma2, ptr(z), None, ptr(out), C.byref(il))
+        ctx.check(rc, il.value)
+        return out.reshape(p, N).T.reshape(-1).copy() if by_features else out
     if isinstance(f, ILMM):
         if f.H.shape[0] != p:
             raise RuntimeError("out dim of x != out dim of f.")
@@ -914,3 +991,35 @@ def potrf_batched(A: np.ndarray, ctx: Optional[Context] = None):
     if rc < 0:
         ctx.check(rc)
     return np.transpose(L, (0, 2, 1)), logdet, info
+
+
+def save_posterior(post, path: str) -> None:
+    """Write a posterior (as returned by `posterior`) to `path`: metadata + device arrays verbatim (lmm_post_save)."""
+    owner = _post_owner(FiniteGP(post, MOInputIsotopicByOutputs(np.zeros(1), 1)))
+    if owner is None:
+        raise TypeError("save_posterior needs a posterior returned by `posterior`")
+    owner.ctx.check(owner.ctx.lib.lmm_post_save(owner.handle, os.fsencode(path)))
+
+
+def load_posterior(path: str, prior, ctx: Optional[Context] = None):
+    """Restore a posterior saved by `save_posterior`.  `prior` is the model it was conditioned from (ILMM / OILMM /
+    IndependentMOGP): it supplies the host-side wrappers, every number comes from the file."""
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    ctx.check(ctx.lib.lmm_post_load(ctx.handle, os.fsencode(path), C.byref(h)))
+    kind, m, p, N, D = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    nbytes = C.c_int64()
+    ctx.check(ctx.lib.lmm_post_info(h, C.byref(kind), C.byref(m), C.byref(p), C.byref(N), C.byref(D), C.byref(nbytes)))
+    lat = prior.f if isinstance(prior, ILMM) else prior
+    if isinstance(lat, _JointPosterior):
+        lat = lat.prior
+    priors = [g.prior if isinstance(g, PosteriorGP) else g for g in lat.fs]
+    if len(priors) != m.value:
+        ctx.lib.lmm_post_free(h)
+        raise ValueError("the prior model does not match the saved posterior")
+    if kind.value in (2, 3):  # joint factor: general ILMM / IndependentMOGP under a dense Σy
+        joint = _JointPosterior(_PostHandle(ctx, h, N.value, joint_n=m.value * N.value), IndependentMOGP(priors))
+        return ILMM(joint, prior.H) if kind.value == 2 else joint
+    owner = _PostHandle(ctx, h, N.value)
+    newlat = IndependentMOGP([PosteriorGP(owner, i, g) for i, g in enumerate(priors)])
+    return ILMM(newlat, prior.H) if kind.value == 0 else newlat

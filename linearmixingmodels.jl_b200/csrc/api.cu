@@ -422,7 +422,9 @@ void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const doub
 // ------------------------------------------------------------------------------------------------
 // posterior handle
 // ------------------------------------------------------------------------------------------------
-enum { POST_OILMM = 0, POST_IMOGP = 1, POST_ILMM = 2 };
+// POST_JOINT: IndependentMOGP conditioned under a dense Σy (AbstractGPs generic path): one joint (mN) factor like
+// POST_ILMM, identity mixing, no projection.
+enum { POST_OILMM = 0, POST_IMOGP = 1, POST_ILMM = 2, POST_JOINT = 3 };
 
 struct lmm_post {
   lmm_ctx* ctx = nullptr;
@@ -443,13 +445,15 @@ struct lmm_post {
   LatentParams* d_params = nullptr;
   double* d_H = nullptr;
   double* d_noise_vec = nullptr;  // [nloc][Npad] per-point training noise (sequentially conditioned posteriors), else null
+  double* d_Ept = nullptr;        // POST_ILMM: [N][m*m] per-point projected noise blocks ΣT (extended by sequential conditioning)
   size_t bytes = 0;
   int big_n = 0, big_nt = 0;  // ILMM joint dimension mN and its tile count
 
   int nloc() const { return hi - lo; }
   size_t npad() const { return (size_t)nt * TILE; }
-  TiledSym Lsym() const { return TiledSym{d_L, kind == POST_ILMM ? big_nt : nt, sym_tiles(kind == POST_ILMM ? big_nt : nt) * TT}; }
-  size_t wstride() const { return (size_t)(kind == POST_ILMM ? big_nt : nt) * TT; }
+  bool joint() const { return kind == POST_ILMM || kind == POST_JOINT; }
+  TiledSym Lsym() const { return TiledSym{d_L, joint() ? big_nt : nt, sym_tiles(joint() ? big_nt : nt) * TT}; }
+  size_t wstride() const { return (size_t)(joint() ? big_nt : nt) * TT; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -644,7 +648,8 @@ struct RunOut {
 // The shared driver for OILMM (src/oilmm.jl:79-93, 116-134) and IndependentMOGP
 // (src/independent_mogp.jl:74-80, 119-126).
 int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const double* x, int N, int D, int p, double sigma2,
-                const double* y, const Projection& pr, const double* Hhost, const double* Uhost, const double* Shost, RunOut out) {
+                const double* y, const Projection& pr, const double* Hhost, const double* Uhost, const double* Shost, RunOut out,
+                const double* noise_vec = nullptr /* per-point noise, m*N by outputs (IndependentMOGP with Σy = Diagonal(v)) */) {
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   for (double& t : ctx->timings) t = 0.0;
@@ -723,7 +728,18 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
     if (fit < 1) fit = 1;
     if ((size_t)chunk > fit) chunk = (int)fit;
   }
-  DevBuf b_L, b_W, b_alpha, b_r, b_z, b_logdet, b_quad, b_info;
+  DevBuf b_L, b_W, b_alpha, b_r, b_z, b_logdet, b_quad, b_info, b_nv;
+  if (noise_vec) {
+    const int nl = mloc > 0 ? mloc : 1;
+    CU(b_nv.alloc(ctx, (size_t)nl * npad * sizeof(double)));
+    CU(cudaMemsetAsync(b_nv.p, 0, (size_t)nl * npad * sizeof(double), st));
+    if (mloc > 0) {
+      const bool dev = is_device_ptr(noise_vec);
+      if (!dev) ctx->h2d += (int64_t)((size_t)mloc * N * sizeof(double));
+      CU(cudaMemcpy2DAsync(b_nv.p, npad * sizeof(double), noise_vec + (size_t)lo * N, (size_t)N * sizeof(double), (size_t)N * sizeof(double),
+                           (size_t)mloc, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    }
+  }
   std::vector<int> hinfo(mloc > 0 ? mloc : 1, 0);
   float ms_kmat = 0, ms_chol = 0, ms_solve = 0;
   if (mloc > 0) {
@@ -745,7 +761,8 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
       const LatentParams* dp = b_params.as<LatentParams>() + c0;
       double* delta = b_ty.as<double>() + (size_t)c0 * npad;
       CU(cudaEventRecord(ctx->ev[2], st));
-      CU(launch_kmat_sym(st, L, nb, b_x.as<double>(), N, D, dp, ctx->distance_form));
+      CU(launch_kmat_sym(st, L, nb, b_x.as<double>(), N, D, dp, ctx->distance_form,
+                         noise_vec ? b_nv.as<double>() + (size_t)c0 * npad : nullptr, npad));
       ++ctx->launches;
       CU(cudaEventRecord(ctx->ev[3], st));
       CU(chol_factor(ctx, L, W, wstride, nb, b_logdet.as<double>() + c0, b_info.as<int>() + c0));
@@ -829,6 +846,7 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
     P->d_delta = (double*)b_ty.detach();
     P->d_params = (LatentParams*)b_params.detach();
     P->d_H = (double*)b_H.detach();
+    if (noise_vec) P->d_noise_vec = (double*)b_nv.detach();
     *out.post = P;
   }
   return LMM_OK;
@@ -946,7 +964,8 @@ extern "C" int lmm_post_free(lmm_post* post) {
   lmm_ctx* ctx = post->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {post->d_xpad, post->d_L, post->d_W, post->d_alpha, post->d_delta, post->d_params, post->d_H, post->d_noise_vec};
+  void* ptrs[] = {post->d_xpad, post->d_L, post->d_W, post->d_alpha, post->d_delta, post->d_params, post->d_H, post->d_noise_vec,
+                  post->d_Ept};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
@@ -971,8 +990,8 @@ extern "C" int lmm_post_export(lmm_post* post, int i, double* Lout, double* alph
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   int b, n;
-  if (post->kind == POST_ILMM) {
-    if (i != 0) return ctx->fail(LMM_E_ARG, "an ILMM posterior has one joint factor (i = 0)");
+  if (post->joint()) {
+    if (i != 0) return ctx->fail(LMM_E_ARG, "a joint posterior has one factor (i = 0)");
     b = 0;
     n = post->big_n;
   } else {
@@ -980,7 +999,7 @@ extern "C" int lmm_post_export(lmm_post* post, int i, double* Lout, double* alph
     b = i - post->lo;
     n = post->N;
   }
-  const size_t vstride = post->kind == POST_ILMM ? (size_t)post->big_nt * TILE : post->npad();
+  const size_t vstride = post->joint() ? (size_t)post->big_nt * TILE : post->npad();
   if (Lout) {
     DevBuf dense;
     CU(dense.alloc(ctx, (size_t)n * n * sizeof(double)));
@@ -1042,7 +1061,7 @@ extern "C" int lmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, d
   lmm_ctx* ctx = post->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  if (post->kind == POST_ILMM) return ilmm_post_mean_and_var(post, xs, Ns, sigma2, mean, var);
+  if (post->joint()) return ilmm_post_mean_and_var(post, xs, Ns, sigma2, mean, var);
   cudaStream_t st = ctx->stream;
   for (double& t : ctx->timings) t = 0.0;
   const int nts = ntiles(Ns), nloc = post->nloc(), p = post->p, m = post->m;

@@ -25,6 +25,8 @@ __device__ __forceinline__ double kernel_pair(const LatentParams& lp, const doub
 
 // mode 0 (projected): dim = m*N, val = [a==b] k_a(i,j) + E[a,b] [i==j]      (E = ΣT, m x m col-major)
 // mode 1 (dense):     dim = q*N, val = sum_l Hm[a,l] Hm[b,l] k_l(i,j) + E0 [a==b][i==j]   (Hm: q x m col-major)
+// mode 2 (dense Σy):  dim = m*N, val = [a==b] k_a(i,j) + E[gr, gc]          (E = Σy, dim x dim col-major)
+// mode 3 (per point): dim = m*N, val = [a==b] k_a(i,j) + E[i][a,b] [i==j]   (E: N blocks of m x m col-major)
 __global__ void __launch_bounds__(256) assemble_ilmm_kernel(TiledSym out, const double* __restrict__ x, int N, int D,
                                                             const LatentParams* __restrict__ params, int m, int q,
                                                             const double* __restrict__ E, const double* __restrict__ Hm, int mode,
@@ -47,9 +49,11 @@ __global__ void __launch_bounds__(256) assemble_ilmm_kernel(TiledSym out, const 
       const int a = gr / N, i = gr % N, b = gc / N, j = gc % N;
       const double* xi = x + (size_t)i * D;
       const double* xj = x + (size_t)j * D;
-      if (mode == 0) {
+      if (mode == 0 || mode == 3) {
         val = (a == b) ? kernel_pair(params[a], xi, xj, D, form, i == j) : 0.0;
-        if (i == j) val += E[(size_t)b * m + a];
+        if (i == j) val += E[(mode == 3 ? (size_t)i * m * m : 0) + (size_t)b * m + a];
+      } else if (mode == 2) {
+        val = ((a == b) ? kernel_pair(params[a], xi, xj, D, form, i == j) : 0.0) + E[(size_t)gc * dim + gr];
       } else {
         val = 0.0;
         for (int l = 0; l < m; ++l)

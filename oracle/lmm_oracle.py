@@ -542,6 +542,62 @@ def ilmm_post_logpdf(post: ILMMPosterior, xs, sigma2: float, ys: np.ndarray) -> 
     return lml + regulariser_general(post.H, sigma2, Y)
 
 
+def ilmm_condition_again_mean_and_var(post: ILMMPosterior, x2, sigma2_2: float, y2: np.ndarray, xt, sigma2_pred: float):
+    """``mean_and_var(posterior(post(x2, σ2²), y2)(xt, σ²))`` for a general-ILMM posterior by the textbook
+    update of the joint latent posterior (src/ilmm.jl:184-198 applied to PosteriorGP{IndependentMOGP} latents):
+    the latent posterior GP is conditioned on vec((T2 Y2)') at x2 with noise ΣT2 ⊗ I, then mixed (src/ilmm.jl:122-129)."""
+    N2, Nt = _as2d(x2).shape[0], _as2d(xt).shape[0]
+    m = len(post.fs)
+    H = post.H
+    T2, ST2 = project_general(H, sigma2_2)
+    Y2 = reshape_y(y2, N2)
+    # joint latent posterior over [x2; xt] in latent-major order per block
+    xa = np.concatenate([_as2d(x2), _as2d(xt)], axis=0)
+    Na = N2 + Nt
+    mean, cov = _ilmm_latent_mean_and_cov(post, xa if xa.shape[1] > 1 else xa[:, 0], jitter=0.0)
+    i2 = np.concatenate([a * Na + np.arange(N2) for a in range(m)])
+    it = np.concatenate([a * Na + N2 + np.arange(Nt) for a in range(m)])
+    C22 = cov[np.ix_(i2, i2)] + np.kron(ST2, np.eye(N2))
+    Ct2 = cov[np.ix_(it, i2)]
+    L = _chol_lower(C22)
+    d = (T2 @ Y2).reshape(-1) - mean[i2]
+    mt = mean[it] + Ct2 @ _bwd(L, _fwd(L, d))
+    V = _fwd(L, Ct2.T)
+    Ctt = cov[np.ix_(it, it)] - V.T @ V + 1e-18 * np.eye(m * Nt)
+    Hf = np.kron(H, np.eye(Nt))
+    return Hf @ mt, np.diag(Hf @ Ctt @ Hf.T) + sigma2_pred
+
+
+def _noise_matrix(Sigma, n: int) -> np.ndarray:
+    S = np.asarray(Sigma, dtype=np.float64)
+    return np.diag(S) if S.ndim == 1 else S
+
+
+def imogp_logpdf_noise(fs: Sequence[GP], x, Sigma_y, y: np.ndarray) -> float:
+    """AbstractGPs generic ``logpdf(f(x_mo, Σy), y)`` for an IndependentMOGP with Σy a vector (``Diagonal(v)``) or a dense
+    matrix (test/independent_mogp.jl:72-75): MVN with mean(f, x), cov(f, x) + Σy (src/independent_mogp.jl:50-63)."""
+    N = _as2d(x).shape[0]
+    C = imogp_cov(fs, x) + _noise_matrix(Sigma_y, len(fs) * N)
+    L = _chol_lower(C)
+    z = _fwd(L, np.asarray(y, dtype=np.float64) - np.concatenate([gp_mean(f, x) for f in fs]))
+    return -0.5 * (len(y) * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(z @ z))
+
+
+def imogp_posterior_noise_mean_and_cov(fs: Sequence[GP], x, Sigma_y, y: np.ndarray, xs, sigma2_pred: float):
+    """AbstractGPs generic posterior of an IndependentMOGP under a vector / dense Σy, evaluated at (xs, σ²):
+    textbook conditioning with the block-diagonal prior (src/independent_mogp.jl:60-71)."""
+    N, Ns = _as2d(x).shape[0], _as2d(xs).shape[0]
+    C = imogp_cov(fs, x) + _noise_matrix(Sigma_y, len(fs) * N)
+    L = _chol_lower(C)
+    delta = np.asarray(y, dtype=np.float64) - np.concatenate([gp_mean(f, x) for f in fs])
+    alpha = _bwd(L, _fwd(L, delta))
+    Ksx = sla.block_diag(*[kernelmatrix(f.kernel, xs, x) for f in fs])
+    mean = np.concatenate([gp_mean(f, xs) for f in fs]) + Ksx @ alpha
+    V = _fwd(L, Ksx.T)
+    cov = imogp_cov(fs, xs) - V.T @ V + sigma2_pred * np.eye(len(fs) * Ns)
+    return mean, cov
+
+
 # --------------------------------------------------------------------------------------------
 # Independent dense check: GP(LinearMixingModelKernel(kernels, H')) (test/ilmm.jl:5)
 # --------------------------------------------------------------------------------------------

@@ -545,6 +545,108 @@ def test_posterior_logpdf_gradient(lmm, N, Ns, p, m):
     np.testing.assert_allclose(g["y"], gr["y"], rtol=1e-6, atol=1e-8)
 
 
+@pytest.mark.parametrize("N1,N2,Nt,p,m", [(12, 9, 5, 4, 3), (150, 140, 33, 5, 2)])
+def test_ilmm_sequential_conditioning(lmm, N1, N2, Nt, p, m):
+    """posterior(post(x2, σ2²), y2) on a general-ILMM posterior (src/ilmm.jl:184-198 with PosteriorGP{IndependentMOGP}
+    latents) against the textbook update of the joint latent posterior, and against the posterior on the union."""
+    rng = np.random.default_rng(N1)
+    x1, x2, xt = np.sort(rng.uniform(0, 4, N1)), rng.uniform(0, 4, N2), rng.uniform(0, 4, Nt)
+    _, _, _, _, fs, _ = make_problem(N1, p, m, 1, seed=5, means=True)
+    H = rng.uniform(0, 1, (p, m))
+    y1, y2 = rng.standard_normal(p * N1), rng.standard_normal(p * N2)
+    O = lmm.MOInputIsotopicByOutputs
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), H)
+    p1 = lmm.posterior(f(O(x1, p), 0.1), y1)
+    p2, lp2 = lmm.posterior(p1(O(x2, p), 0.2), y2, with_logpdf=True)
+    M, V = lmm.mean_and_var(p2(O(xt, p), 0.15))
+    op = o.ilmm_posterior(fs, H, x1, 0.1, y1)
+    Mr, Vr = o.ilmm_condition_again_mean_and_var(op, x2, 0.2, y2, xt, 0.15)
+    np.testing.assert_allclose(M, Mr, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(V, Vr, rtol=1e-8)
+    assert rel(lp2, o.ilmm_post_logpdf(op, x2, 0.2, y2)) < 1e-8
+    # a third conditioning step keeps working (per-point noise blocks are extended again)
+    p3 = lmm.posterior(p2(O(xt, p), 0.3), rng.standard_normal(p * Nt))
+    M3, V3 = lmm.mean_and_var(p3(O(xt, p), 0.1))
+    assert np.all(np.isfinite(M3)) and np.all(V3 > 0.1) and np.all(V3 < V + 1.0)
+
+
+@pytest.mark.parametrize("N,Ns,m", [(9, 4, 2), (140, 37, 3)])
+def test_imogp_vector_and_dense_noise(lmm, N, Ns, m):
+    """f(x_mo, v::Vector) and f(x_mo, Σy::Matrix) on an IndependentMOGP: the AbstractGPs generic FiniteGP path
+    (test/independent_mogp.jl:72-75; by-features reordering of a Diagonal Σy src/independent_mogp.jl:149-159)."""
+    rng = np.random.default_rng(7 * N)
+    x, xs = np.sort(rng.uniform(0, 4, N)), rng.uniform(0, 4, Ns)
+    _, _, _, _, fs, _ = make_problem(N, m, m, 1, seed=9, means=True)
+    f = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    y, ys = rng.standard_normal(m * N), rng.standard_normal(m * Ns)
+    O, F = lmm.MOInputIsotopicByOutputs, lmm.MOInputIsotopicByFeatures
+    v = rng.uniform(0.05, 0.5, m * N)
+    A = rng.standard_normal((m * N, m * N))
+    Sy = A.T @ A / (m * N) + 0.1 * np.eye(m * N)
+    for Sig in (v, Sy):
+        fx = f(O(x, m), Sig)
+        assert rel(lmm.logpdf(fx, y), o.imogp_logpdf_noise(fs, x, Sig, y)) < RTOL
+        post, lp = lmm.posterior(fx, y, with_logpdf=True)
+        assert rel(lp, o.imogp_logpdf_noise(fs, x, Sig, y)) < RTOL
+        Mr, Cr = o.imogp_posterior_noise_mean_and_cov(fs, x, Sig, y, xs, 0.2)
+        M, V = lmm.mean_and_var(post(O(xs, m), 0.2))
+        np.testing.assert_allclose(M, Mr, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(V, np.diag(Cr), rtol=1e-8)
+        M2, C2 = lmm.mean_and_cov(post(O(xs, m), 0.2))
+        np.testing.assert_allclose(C2, Cr, rtol=1e-7, atol=1e-9)
+        # logpdf(post(x*, σ²), y*) == MVN(y*; mean*, cov* + σ² I)
+        L = np.linalg.cholesky(Cr)
+        z = sla.solve_triangular(L, ys - Mr, lower=True)
+        ref = -0.5 * (m * Ns * o.LOG2PI + 2 * np.sum(np.log(np.diag(L))) + z @ z)
+        assert rel(lmm.logpdf(post(O(xs, m), 0.2), ys), ref) < 1e-8
+        assert lmm.rand(np.random.default_rng(0), post(O(xs, m), 0.2)).shape == (m * Ns,)
+        assert lmm.rand(np.random.default_rng(0), fx).shape == (m * N,)
+        # prior marginals under the same noise: var = k(x,x) + diag(Σy)
+        Mp, Vp = lmm.mean_and_var(fx)
+        np.testing.assert_allclose(Vp, np.concatenate([np.full(N, g.kernel.variance) for g in fs]) + (Sig if Sig.ndim == 1 else np.diag(Sig)), rtol=1e-13)
+    # by-features inputs: Σy given in by-features order
+    idx = o.indices_outputs_to_features(N, m)
+    assert rel(lmm.logpdf(f(F(x, m), v[idx]), y[idx]), o.imogp_logpdf_noise(fs, x, v, y)) < RTOL
+    assert rel(lmm.logpdf(f(F(x, m), Sy[np.ix_(idx, idx)]), y[idx]), o.imogp_logpdf_noise(fs, x, Sy, y)) < RTOL
+    pf = lmm.posterior(f(F(x, m), v[idx]), y[idx])
+    Mf, Vf = lmm.mean_and_var(pf(F(xs, m), 0.2))
+    Mr, Cr = o.imogp_posterior_noise_mean_and_cov(fs, x, v, y, xs, 0.2)
+    ids = o.indices_outputs_to_features(Ns, m)
+    np.testing.assert_allclose(Mf, Mr[ids], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(Vf, np.diag(Cr)[ids], rtol=1e-8)
+    # ILMM / OILMM methods keep rejecting non-scalar noise (src/ilmm.jl:45 dispatch)
+    with pytest.raises(TypeError):
+        lmm.ILMM(f, np.eye(m))(O(x, m), v)
+
+
+def test_posterior_save_load_round_trip(lmm, tmp_path):
+    """Serialisable posterior: a handle restored from its file answers bit-identically, for the
+    per-latent kinds (OILMM, IndependentMOGP), the joint kind (general ILMM) and a sequentially conditioned one."""
+    N, Ns, p, m = 260, 40, 5, 3
+    x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=101, means=True)
+    O = lmm.MOInputIsotopicByOutputs
+    lat = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    H = np.random.default_rng(2).uniform(0, 1, (p, m))
+    models = [(lmm.ILMM(lat, lmm.Orthogonal(U, S)), p), (lat, m), (lmm.ILMM(lat, H), p)]
+    for k, (model, pp) in enumerate(models):
+        post = lmm.posterior(model(O(x, pp), 0.1), y[: pp * N])
+        if k != 1:
+            post = lmm.posterior(post(O(xs, pp), 0.2), y[: pp * Ns])  # also a conditioned-again handle
+        path = str(tmp_path / f"post{k}.lmm")
+        lmm.save_posterior(post, path)
+        back = lmm.load_posterior(path, model)
+        M0, V0 = lmm.mean_and_var(post(O(xs, pp), 0.1))
+        M1, V1 = lmm.mean_and_var(back(O(xs, pp), 0.1))
+        assert np.array_equal(M0, M1) and np.array_equal(V0, V1)
+        assert lmm.logpdf(post(O(xs, pp), 0.1), y[: pp * Ns]) == lmm.logpdf(back(O(xs, pp), 0.1), y[: pp * Ns])
+        again = lmm.posterior(back(O(xs, pp), 0.3), y[: pp * Ns])  # a loaded handle can be conditioned further
+        assert np.all(np.isfinite(lmm.mean(again(O(xs, pp), 0.1))))
+    with open(str(tmp_path / "bad.lmm"), "wb") as fh:
+        fh.write(b"not a posterior")
+    with pytest.raises(Exception):
+        lmm.load_posterior(str(tmp_path / "bad.lmm"), lat)
+
+
 def test_imogp_process_cov_mixed_orderings(lmm):
     """cov(f, x, y) with by-outputs / by-features inputs in all four combinations
     (src/independent_mogp.jl:60-71,181-215; test/independent_mogp.jl:135-141)."""
