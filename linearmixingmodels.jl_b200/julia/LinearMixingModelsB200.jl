@@ -265,6 +265,65 @@ function ChainRulesCore.rrule(::typeof(AbstractGPs.logpdf), fx::FiniteGP{<:OILMM
     return out[], logpdf_pullback
 end
 
+# --- rrule for the general-ILMM logpdf (test/ilmm.jl:31 `gradient(logpdf, ilmmx, y_train)`) -------
+function ChainRulesCore.rrule(::typeof(AbstractGPs.logpdf), fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}},
+                              y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs); m = length(descs)
+    out = Ref{Float64}(0.0); gs2 = Ref{Float64}(0.0); info = Ref{Cint}(0)
+    gl = Matrix{Float64}(undef, 3, m); gy = Vector{Float64}(undef, length(y)); gH = similar(H)
+    check(ccall((:lmm_ilmm_logpdf_grad, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, m, X, length(x), D, H, size(H, 1), Float64(σ²), Vector{Float64}(y), fx.x.out_dim, out, gl, gs2, gy, gH, info))
+    function logpdf_pullback(Δ)
+        Σy_tangent = Tangent{typeof(fx.Σy)}(; diag = Tangent{typeof(fx.Σy.diag)}(; value = Δ * gs2[]))
+        f_tangent = Tangent{typeof(fx.f)}(; H = Δ .* gH)
+        return NoTangent(), Tangent{typeof(fx)}(; f = f_tangent, Σy = Σy_tangent), Δ .* gy
+    end
+    return out[], logpdf_pullback
+end
+
+# --- rrule for logpdf(post(x*, σ²), y*) (test/oilmm.jl:32 `gradient(logpdf, po, y_test)`): tangents for σ² and y* ---
+function ChainRulesCore.rrule(::typeof(AbstractGPs.logpdf), fx::FiniteGP{<:PosteriorOILMM}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, _ = points(x)
+    out = Ref{Float64}(0.0); gs2 = Ref{Float64}(0.0); il = Ref{Cint}(-1)
+    gy = Vector{Float64}(undef, length(y))
+    check(ccall((:lmm_post_logpdf_grad, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        fs.fs[1].owner.handle, X, length(x), Float64(σ²), Vector{Float64}(y), out, gs2, gy, il))
+    function logpdf_pullback(Δ)
+        Σy_tangent = Tangent{typeof(fx.Σy)}(; diag = Tangent{typeof(fx.Σy.diag)}(; value = Δ * gs2[]))
+        return NoTangent(), Tangent{typeof(fx)}(; Σy = Σy_tangent), Δ .* gy
+    end
+    return out[], logpdf_pullback
+end
+
+# --- IndependentMOGP with Σy = Diagonal(v) or a dense Σy (AbstractGPs generic FiniteGP path,
+#     test/independent_mogp.jl:72-75; by-features callers reorder Σy first, src/independent_mogp.jl:149-159) ---
+noise_arg(Σy::Diagonal) = (Vector{Float64}(Σy.diag), Cint(1))      # LMM_NOISE_DIAG
+noise_arg(Σy::AbstractMatrix) = (Matrix{Float64}(Σy), Cint(2))     # LMM_NOISE_DENSE
+function AbstractGPs.logpdf(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOInputIsotopicByOutputs}, y::AbstractVector{<:Real})
+    X, D = points(ft.x.x)
+    descs = GpDesc.(ft.f.fs)
+    Σ, kind = noise_arg(ft.Σy)
+    out = Ref{Float64}(0.0); il = Ref{Cint}(-1)
+    check(ccall((:lmm_imogp_posterior_noise, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(ft.x.x), D, Σ, kind, Vector{Float64}(y), ft.x.out_dim, C_NULL, out, il))
+    return out[]
+end
+
+# --- serialisable posterior: the on-disk form of a DevicePosterior -----------------------------------
+save_posterior(p::DevicePosterior, path::AbstractString) = check(ccall((:lmm_post_save, liblmm), Cint, (Ptr{Cvoid}, Cstring), p.handle, path))
+function load_posterior(path::AbstractString)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:lmm_post_load, liblmm), Cint, (Ptr{Cvoid}, Cstring, Ptr{Ptr{Cvoid}}), ctx(), path, h))
+    return DevicePosterior(h[])
+end
+
 # PosteriorGP field access (α, C, δ) for one latent -- `lmm_post_export`
 function export_latent(f::DeviceLatentPosterior, N::Int)
     L = Matrix{Float64}(undef, N, N); α = Vector{Float64}(undef, N); δ = Vector{Float64}(undef, N)
