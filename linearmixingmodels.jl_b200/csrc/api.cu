@@ -79,7 +79,7 @@ struct lmm_ctx {
   // trailing-update stream, chained by per-block events
   cudaStream_t panel_stream = nullptr, update_stream = nullptr;
   std::vector<cudaEvent_t> blk_ev;
-  int lookahead = 1;
+  int lookahead = 2;  // 0 off, 1 left-looking K-split, 2 right-looking (default)
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -302,9 +302,81 @@ cudaError_t chol_factor_lookahead(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
   return cudaSuccess;
 }
 
+// Right-looking block schedule with look-ahead (small batches).  After block column kb is factored on the
+// high-priority panel stream X, its update of the NEXT block column runs on X (so the next panel can start at
+// once) while its update of everything further right runs as one large GEMM on the low-priority stream Y:
+//   X: [wait Y(kb-2)] update(kb-1 -> kb), panel(kb)            Y: [wait X(kb)] update(kb -> kb+2 .. end)
+// The Y launches have thousands of tiles (no tail effect, unlike the wide left-looking update of one block
+// column) and keep every SM busy while the latency-bound panel steps run beside them; each C tile is
+// read-modify-written once per block column of L (K = `ob` tiles per launch).
+cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
+  const int nt = L.nt;
+  // the panel chain is the critical path: narrow blocks for small matrices, wider ones (fewer read-modify-write
+  // passes over the trailing matrix) once the trailing GEMMs dominate (measured: tools/bench_batch1.py)
+  const int ob = ctx->outer_block_user ? ctx->outer_block : (nt <= 32 ? 1 : nt <= 72 ? 2 : nt <= 112 ? 3 : 4);
+  const int nblk = (nt + ob - 1) / ob;
+  cudaError_t e;
+  while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
+    cudaEvent_t ev;
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    ctx->blk_ev.push_back(ev);
+  }
+  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream;
+  cudaEvent_t* evX = ctx->blk_ev.data();          // panel(b) done on X
+  cudaEvent_t* evY = ctx->blk_ev.data() + nblk;   // trailing update from block b done on Y
+  GemmArgs g{};
+  g.A = operand(L); g.B = operand(L); g.C = operand(L);
+  g.W = W; g.w_batch_stride = wstride; g.sym = 1;
+  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  for (int b = 0; b < nblk; ++b) {
+    const int s0 = b * ob, s1 = (s0 + ob < nt) ? s0 + ob : nt;
+    if (b >= 1) {
+      // every earlier update of this block column (Y launches up to b-2) must have landed
+      if (b >= 2 && (e = cudaStreamWaitEvent(X, evY[b - 2], 0)) != cudaSuccess) return e;
+      g.i0 = s0; g.j0 = s0; g.k0 = s0 - ob; g.k1 = s0;
+      if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
+      ++ctx->launches;
+      ctx->timings[6] += 1;
+    }
+    for (int jj = s0; jj < s1; ++jj) {
+      if (jj > s0) {
+        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+      if ((e = launch_potrf_tile(X, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
+      ++ctx->launches;
+      if (jj + 1 < nt) {
+        g.i0 = jj + 1; g.j0 = jj;
+        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+    }
+    if ((e = cudaEventRecord(evX[b], X)) != cudaSuccess) return e;
+    const int s2 = s1 + ob;  // first column of block b+2
+    if (s2 < nt) {
+      if ((e = cudaStreamWaitEvent(Y, evX[b], 0)) != cudaSuccess) return e;
+      g.i0 = s2; g.j0 = s2; g.k0 = s0; g.k1 = s1;
+      if ((e = launch_gemm(Y, GEMM_UPDATE, g, nt - s2, nt - s2, batch)) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
+      ++ctx->launches;
+      ctx->timings[6] += 1;
+    } else if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) {  // no trailing launch left: keep the event chain defined
+      return e;
+    }
+  }
+  if ((e = cudaStreamWaitEvent(ctx->stream, evX[nblk - 1], 0)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
 // Fork the batch into latent groups on separate streams (joined back into ctx->stream).
 cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
   const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
+  if (ctx->lookahead == 2 && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
   if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
   if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info);
   cudaError_t e;
@@ -523,14 +595,20 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
     if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_ARG, "distance_form must be 0 or 1");
     ctx->distance_form = (int)value;
   } else if (k == "outer_block") {
-    if (value < 1 || value > 64) return ctx->fail(LMM_E_ARG, "outer_block must be in [1, 64]");
+    if (value == 0.0) {  // back to the built-in choice
+      ctx->outer_block = 8;
+      ctx->outer_block_user = false;
+      return LMM_OK;
+    }
+    if (value < 1 || value > 64) return ctx->fail(LMM_E_ARG, "outer_block must be in [1, 64] (0 = automatic)");
     ctx->outer_block = (int)value;
     ctx->outer_block_user = true;
   } else if (k == "streams") {
     if (value < 1 || value > lmm_ctx::MAX_GROUPS) return ctx->fail(LMM_E_ARG, "streams must be in [1, 8]");
     ctx->ngroups = (int)value;
   } else if (k == "lookahead") {
-    ctx->lookahead = value != 0.0;
+    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "lookahead must be 0, 1 (left-looking, K-split) or 2 (right-looking)");
+    ctx->lookahead = (int)value;
   } else if (k == "gemm_impl") {
     if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0, 1 or 2");
     set_gemm_impl((int)value);

@@ -54,7 +54,7 @@ def rel(a, b):
     return abs(a - b) / max(abs(b), 1e-300)
 
 
-@pytest.mark.parametrize("N,batch", [(50, 2), (128, 1), (300, 3), (1000, 2)])
+@pytest.mark.parametrize("N,batch", [(50, 2), (128, 1), (300, 3), (1000, 2), (2000, 1), (1700, 2)])
 def test_potrf_batched_matches_lapack(lmm, N, batch):
     rng = np.random.default_rng(N)
     A = rng.standard_normal((batch, N, N))
@@ -66,6 +66,28 @@ def test_potrf_batched_matches_lapack(lmm, N, batch):
         np.testing.assert_allclose(L[b], Lr, rtol=1e-10, atol=1e-12)
         assert rel(logdet[b], 2 * np.sum(np.log(np.diag(Lr)))) < 1e-11 or abs(logdet[b]) < 1e-9
         assert np.all(np.triu(L[b], 1) == 0.0)
+
+
+def test_potrf_small_batch_schedules(lmm):
+    """Batch-1 schedules (plain, left-looking K-split look-ahead, right-looking look-ahead) at several block
+    widths all reproduce LAPACK's factor."""
+    rng = np.random.default_rng(5)
+    N = 2300
+    A = rng.standard_normal((N, N))
+    A = A @ A.T / N + np.eye(N)
+    Lr = sla.cholesky(A, lower=True)
+    ctx = lmm.default_context()
+    try:
+        for la, ob in ((0, 0), (1, 0), (1, 5), (2, 0), (2, 1), (2, 3), (2, 7)):
+            ctx.set_option("lookahead", la)
+            ctx.set_option("outer_block", ob)
+            L, logdet, info = lmm.potrf_batched(A)
+            assert info[0] == 0
+            np.testing.assert_allclose(L[0], Lr, rtol=1e-10, atol=1e-12, err_msg=f"lookahead={la} outer_block={ob}")
+            assert rel(logdet[0], 2 * np.sum(np.log(np.diag(Lr)))) < 1e-11
+    finally:
+        ctx.set_option("lookahead", 2)
+        ctx.set_option("outer_block", 0)
 
 
 def test_potrf_reports_non_pd(lmm):
