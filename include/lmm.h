@@ -68,7 +68,10 @@ const char* lmm_version(void);
 /* Tunables: "distance_form" (0 = Distances.jl gemm form [default], 1 = direct differences),
  * "outer_block" (tile columns per outer Cholesky step, default 8; 0 = automatic), "streams" (latent groups
  * factored concurrently on separate CUDA streams, default 4, 1..8), "lookahead" (block-level look-ahead for batches <= 2: 0 off, 1 left-looking with the
- * wide update split along K, 2 right-looking with the next block column on the panel stream [default]), "gemm_impl" (0 = cp.async ring + CTA barrier; 1 / 2 =
+ * wide update split along K, 2 right-looking with the next block column on the panel stream [default]), "partition_ilmm" (1: the joint factor of a general ILMM
+ * -- one large matrix, factored by every rank of the communicator on identical inputs -- is partitioned row-cyclically
+ * over the ranks, one ncclAllGather of the current block column per step; every rank must make the same call; default 0),
+ * "gemm_impl" (0 = cp.async ring + CTA barrier; 1 / 2 =
  * TMA bulk copies + full/empty mbarrier ring with 16- / 32-column stages; default 2). */
 int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value);
 /* Counters since context creation: kernels launched by this library, bytes copied H2D / D2H. */

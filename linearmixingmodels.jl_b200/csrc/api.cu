@@ -28,6 +28,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclId*) = nullptr;
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
@@ -45,6 +46,7 @@ static NcclApi& nccl_api() {
     api.GetUniqueId = (int (*)(NcclId*))dlsym(api.handle, "ncclGetUniqueId");
     api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
     api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllGather");
     api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
     api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
     api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
@@ -80,6 +82,12 @@ struct lmm_ctx {
   cudaStream_t panel_stream = nullptr, update_stream = nullptr;
   std::vector<cudaEvent_t> blk_ev;
   int lookahead = 2;  // 0 off, 1 left-looking K-split, 2 right-looking (default)
+  // one large factor (general ILMM, batch 1) partitioned row-cyclically over the ranks of the communicator
+  int partition_ilmm = 0;
+  int partition_now = 0;  // set by the callers whose factorisation is replicated on every rank (ILMM joint factor)
+  int dist_error = 0;  // NCCL failure inside the partitioned schedule (reported by the caller)
+  void* xbuf = nullptr;  // exchange buffers of the row-cyclic schedule (send | all-gathered), grown on demand
+  size_t xbuf_bytes = 0;
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -373,9 +381,108 @@ cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t
   return cudaSuccess;
 }
 
+// Row-cyclic multi-GPU factorisation of ONE large matrix (north star: "ILMM runs on one GPU unless its blocked
+// Cholesky is explicitly row-cyclic partitioned").  Every rank holds the whole packed-lower matrix and runs the same
+// right-looking schedule; rank r owns the tile rows I = r (mod G) of the TRAILING matrix and applies the updates to
+// those rows only.  Before block column b is factored its tiles are exchanged (pack own rows -> ncclAllGather over
+// NVLink -> unpack the others' rows); the latency-bound panel (diagonal-tile factor, TRSM-as-GEMM of all rows, 2-3 %
+// of the flops) is then computed redundantly by every rank, so the finished columns of L are complete everywhere and
+// nothing downstream (solves, predictions, logdet) needs a collective.  Per block: one all-gather of (nt - s0) * ob
+// tiles; the trailing GEMMs -- 97 % of the work -- are split G ways.
+cudaError_t chol_factor_rowcyclic(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, double* logdet, int* info) {
+  const int nt = L.nt, G = ctx->nranks, me = ctx->rank;
+  const int ob = ctx->outer_block_user ? ctx->outer_block : (nt <= 72 ? 2 : nt <= 112 ? 3 : 4);
+  const int nblk = (nt + ob - 1) / ob;
+  cudaError_t e;
+  while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
+    cudaEvent_t ev;
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    ctx->blk_ev.push_back(ev);
+  }
+  // exchange buffers: [send: slots*ob tiles][recv: G*slots*ob tiles], sized for the first (largest) exchange
+  const int max_slots = (nt + G - 1) / G;
+  const size_t send_elems = (size_t)max_slots * ob * TT, need = (send_elems * (size_t)(G + 1)) * sizeof(double);
+  if (ctx->xbuf_bytes < need) {
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
+    ctx->xbuf = nullptr;
+    ctx->xbuf_bytes = 0;
+    if ((e = cudaMalloc(&ctx->xbuf, need)) != cudaSuccess) return e;
+    ctx->xbuf_bytes = need;
+  }
+  double* sendb = (double*)ctx->xbuf;
+  double* recvb = sendb + send_elems;
+  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream;
+  cudaEvent_t* evX = ctx->blk_ev.data();
+  cudaEvent_t* evY = ctx->blk_ev.data() + nblk;
+  GemmArgs g{};
+  g.A = operand(L); g.B = operand(L); g.C = operand(L);
+  g.W = W; g.w_batch_stride = wstride; g.sym = 1;
+  auto first_own = [&](int s) { return s + (((me - s % G) % G) + G) % G; };
+  auto own_count = [&](int s) { const int f = first_own(s); return f >= nt ? 0 : (nt - 1 - f) / G + 1; };
+  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  for (int b = 0; b < nblk; ++b) {
+    const int s0 = b * ob, s1 = (s0 + ob < nt) ? s0 + ob : nt;
+    if (b >= 1) {
+      if (b >= 2 && (e = cudaStreamWaitEvent(X, evY[b - 2], 0)) != cudaSuccess) return e;
+      // own rows of block column b: update with block b-1 ...
+      const int cnt = own_count(s0);
+      if (cnt > 0) {
+        g.row_step = G; g.i0 = first_own(s0); g.j0 = s0; g.k0 = s0 - ob; g.k1 = s0;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, cnt, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+        ctx->timings[6] += 1;
+      }
+      // ... then exchange the block column so that every rank can factor it
+      const int slots = (nt - s0 + G - 1) / G;
+      if ((e = launch_rowcyclic_pack(X, L, s0, s1, G, me, slots, sendb)) != cudaSuccess) return e;
+      const size_t cntel = (size_t)slots * (s1 - s0) * TT;
+      if (nccl_api().AllGather(sendb, recvb, cntel, NCCL_DOUBLE, ctx->comm, X) != 0) {
+        ctx->dist_error = 1;
+        return cudaErrorUnknown;
+      }
+      if ((e = launch_rowcyclic_unpack(X, L, s0, s1, G, me, slots, recvb)) != cudaSuccess) return e;
+      ctx->launches += 2;
+    }
+    g.row_step = 1;
+    for (int jj = s0; jj < s1; ++jj) {  // the panel: every rank, all rows
+      if (jj > s0) {
+        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+      if ((e = launch_potrf_tile(X, L, W, wstride, jj, 1, logdet, info)) != cudaSuccess) return e;
+      ++ctx->launches;
+      if (jj + 1 < nt) {
+        g.i0 = jj + 1; g.j0 = jj;
+        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, nt - jj - 1, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+    }
+    if ((e = cudaEventRecord(evX[b], X)) != cudaSuccess) return e;
+    const int s2 = s1 + ob;
+    const int cnt2 = s2 < nt ? own_count(s2) : 0;
+    if (cnt2 > 0) {
+      if ((e = cudaStreamWaitEvent(Y, evX[b], 0)) != cudaSuccess) return e;
+      g.row_step = G; g.i0 = first_own(s2); g.j0 = s2; g.k0 = s0; g.k1 = s1;
+      if ((e = launch_gemm(Y, GEMM_UPDATE, g, nt - s2, cnt2, 1)) != cudaSuccess) return e;
+      ++ctx->launches;
+      ctx->timings[6] += 1;
+    }
+    if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
+  }
+  if ((e = cudaStreamWaitEvent(ctx->stream, evX[nblk - 1], 0)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
 // Fork the batch into latent groups on separate streams (joined back into ctx->stream).
 cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
   const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
+  if (ctx->partition_ilmm && ctx->partition_now && batch == 1 && ctx->comm && ctx->nranks > 1 && L.nt >= 2 * ctx->nranks && nccl_api().AllGather)
+    return chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
   if (ctx->lookahead == 2 && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
   if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
   if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info);
@@ -473,6 +580,14 @@ cudaError_t trsm_right_lt_upper(lmm_ctx* ctx, cudaStream_t st, TiledRect X, Tile
   }
   return cudaSuccess;
 }
+
+// Marks a factorisation that every rank of the communicator performs on identical inputs (the joint ILMM factor,
+// the batch-1 potrf primitive): with the "partition_ilmm" option such a call runs the row-cyclic multi-GPU schedule.
+struct PartitionScope {
+  lmm_ctx* c;
+  explicit PartitionScope(lmm_ctx* ctx) : c(ctx) { c->partition_now = 1; }
+  ~PartitionScope() { c->partition_now = 0; }
+};
 
 size_t factor_bytes_per_latent(int nt) { return (sym_tiles(nt) + (size_t)nt) * TT * sizeof(double); }
 
@@ -575,6 +690,7 @@ extern "C" int lmm_ctx_destroy(lmm_ctx* ctx) {
   if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& g : ctx->gstream) cudaStreamDestroy(g);
+  if (ctx->xbuf) cudaFree(ctx->xbuf);
   cudaStreamDestroy(ctx->panel_stream);
   cudaStreamDestroy(ctx->update_stream);
   for (auto& e : ctx->blk_ev) cudaEventDestroy(e);
@@ -609,6 +725,8 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "lookahead") {
     if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "lookahead must be 0, 1 (left-looking, K-split) or 2 (right-looking)");
     ctx->lookahead = (int)value;
+  } else if (k == "partition_ilmm") {
+    ctx->partition_ilmm = value != 0.0;
   } else if (k == "gemm_impl") {
     if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0, 1 or 2");
     set_gemm_impl((int)value);
@@ -1263,7 +1381,10 @@ extern "C" int lmm_potrf_batched(lmm_ctx* ctx, const double* A, int N, int batch
   CU(launch_tile_from_dense(st, L, batch, dA, N));
   ++ctx->launches;
   CU(cudaEventRecord(ctx->ev[0], st));
-  CU(chol_factor(ctx, L, b_W.as<double>(), (size_t)nt * TT, batch, b_logdet.as<double>(), b_info.as<int>()));
+  {
+    PartitionScope scope(ctx);
+    CU(chol_factor(ctx, L, b_W.as<double>(), (size_t)nt * TT, batch, b_logdet.as<double>(), b_info.as<int>()));
+  }
   CU(cudaEventRecord(ctx->ev[1], st));
   std::vector<int> hinfo(batch, 0);
   CU(copy_out(ctx, hinfo.data(), b_info.p, (size_t)batch * sizeof(int)));
@@ -1327,7 +1448,10 @@ extern "C" int lmm_potrf_bench(lmm_ctx* ctx, const lmm_gp_desc* desc, const doub
   CU(launch_kmat_sym(st, L, batch, b_x.as<double>(), N, D, b_params.as<LatentParams>(), ctx->distance_form));
   ++ctx->launches;
   CU(cudaEventRecord(ctx->ev[1], st));
-  CU(chol_factor(ctx, L, b_W.as<double>(), (size_t)nt * TT, batch, b_logdet.as<double>(), b_info.as<int>()));
+  {
+    PartitionScope scope(ctx);
+    CU(chol_factor(ctx, L, b_W.as<double>(), (size_t)nt * TT, batch, b_logdet.as<double>(), b_info.as<int>()));
+  }
   CU(cudaEventRecord(ctx->ev[2], st));
   std::vector<int> hinfo(batch, 0);
   CU(copy_out(ctx, hinfo.data(), b_info.p, (size_t)batch * sizeof(int)));

@@ -39,7 +39,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 template <int MODE>
 __global__ void __launch_bounds__(256, 1) gemm_tile_kernel(GemmArgs g) {
   extern __shared__ __align__(128) double smem[];
-  const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
+  const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y * (g.row_step > 0 ? g.row_step : 1), b = blockIdx.z;
   if (g.sym && I < J) return;
   if (g.upper && I > J) return;
   const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;  // first k-tile of this CTA
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   extern __shared__ __align__(128) double smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)6 * 2 * CHUNK);
   uint64_t* empty = full + V2_STAGES;
-  const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
+  const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y * (g.row_step > 0 ? g.row_step : 1), b = blockIdx.z;
   if (g.sym && I < J) return;
   if (g.upper && I > J) return;
   const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;  // first k-tile of this CTA

@@ -35,6 +35,8 @@ struct GemmArgs {
   int sym;                // skip tiles with I < J
   int upper;              // skip tiles with I > J (upper-triangular X, e.g. L^{-T})
   int k_from_row;         // UPDATE: k range starts at max(k0, I) (A(I,k) = 0 for k < I)
+  int row_step;           // tile row I = i0 + blockIdx.y * row_step (0 or 1: consecutive rows; G: the rows one rank of a
+                          // row-cyclic partition owns)
 };
 enum { GEMM_UPDATE = 0, GEMM_TRSM = 1 };
 cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch);
@@ -63,6 +65,11 @@ cudaError_t launch_lower_gemv(cudaStream_t st, TiledSym L, const double* z, size
 cudaError_t launch_untile_lower(cudaStream_t st, TiledSym L, int b, double* dense, int N);
 // tile: dense N x N col-major (lower read, mirrored) -> tiles (identity on padding)
 cudaError_t launch_tile_from_dense(cudaStream_t st, TiledSym L, int batch, const double* dense, int N);
+// Row-cyclic exchange of one block column [s0, s1) of a packed-lower matrix (batch 1): rank r owns tile rows
+// I = r (mod G).  pack: own rows I >= s0 -> buf[q][ob tiles] (q = index among the own rows); unpack: every other
+// rank's rows from an all-gathered buffer [G][slots][ob tiles] back into the matrix.
+cudaError_t launch_rowcyclic_pack(cudaStream_t st, TiledSym L, int s0, int s1, int G, int rank, int slots, double* buf);
+cudaError_t launch_rowcyclic_unpack(cudaStream_t st, TiledSym L, int s0, int s1, int G, int rank, int slots, const double* all);
 
 // ---- proj.cu
 // Ty[i][n] = sum_j T[i + lat0][j] Y[j][n] - mean_i  (i < mloc), written to ty[i*ty_stride + n], zero padding to ty_stride
