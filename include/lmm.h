@@ -259,6 +259,12 @@ int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const 
  * info (nullable): batch ints, 0 or 1-based failing pivot.  Returns max(info). */
 int lmm_potrf_batched(lmm_ctx* ctx, const double* A, int N, int batch, double* L_out,
                       double* logdet_out, int* info);
+/* AbstractGPs generic FiniteGP verbs on an explicit mean (n) and covariance (n x n column-major, lower read):
+ * logpdf(fx, y) when y / out_logpdf are given, rand(rng, fx) = mean + C.U' z when z / out_sample are given
+ * (either pair nullable).  Serves FiniteGPs outside the fast paths, e.g. a posterior evaluated under a vector
+ * or dense Σy (test/independent_mogp.jl:120-133); the dense factor and solves run on the device. */
+int lmm_mvn_logpdf_rand(lmm_ctx* ctx, const double* mean, const double* cov, int n, const double* y,
+                        double* out_logpdf, const double* z, double* out_sample, int* info);
 /* Same factorisation run on synthetic SPD matrices generated on the device (kernel-matrix build
  * of `desc` at x plus `noise` on the diagonal), nothing copied back but logdet: the kernel-level
  * benchmark used for roofline numbers.  out_ms receives the CUDA-event time of the factorisation

@@ -551,6 +551,14 @@ def _logpdf_impl(fx: FiniteGP, y):
     out = C.c_double()
     il = C.c_int(-1)
     owner = _post_owner(fx)
+    if fx.noise is not None and (owner is not None or not isinstance(f, IndependentMOGP)):
+        # AbstractGPs generic `logpdf(fx, y)` on (mean, cov + Σy), e.g. a posterior evaluated under a vector / dense Σy
+        M, Cm = mean_and_cov(fx)
+        yv = _yvec(y, M.shape[0])
+        Cf = np.asfortranarray(Cm)
+        rc = lib.lmm_mvn_logpdf_rand(ctx.handle, ptr(M), ptr(Cf), M.shape[0], ptr(yv), C.byref(out), None, None, C.byref(il))
+        ctx.check(rc)
+        return out.value, None
     if isinstance(f, IndependentMOGP) and isinstance(fx.x, MOInputIsotopicByFeatures):
         # src/independent_mogp.jl:222-229
         xo = MOInputIsotopicByOutputs(fx.x.x, fx.x.out_dim)
@@ -561,8 +569,6 @@ def _logpdf_impl(fx: FiniteGP, y):
     pts = _points(fx.x.x)
     N, D = int(pts.shape[0]), int(pts.shape[1])
     if fx.noise is not None:
-        if owner is not None or not isinstance(f, IndependentMOGP):
-            raise NotImplementedError("non-scalar observation noise is built for IndependentMOGP priors")
         kind, Sy = _noise_by_outputs(fx)
         yv = _yvec(y, N * fx.x.out_dim)
         rc = lib.lmm_imogp_posterior_noise(ctx.handle, _descs(f.fs), len(f.fs), ptr(pts), N, D, ptr(Sy), kind, ptr(yv), fx.x.out_dim, None,
@@ -855,10 +861,10 @@ def _rand_one(rng, fx: FiniteGP) -> np.ndarray:
     if fx.noise is not None:
         # AbstractGPs generic `rand(rng, fx) = m + cholesky(K + Σy).U' z`: covariance and factor on the device
         M, Cm = mean_and_cov(fx)
-        L, _, info = potrf_batched(Cm, ctx)
-        if info[0] > 0:
-            raise PosDefException(int(info[0]))
-        return M + L[0] @ rng.standard_normal(p * N)
+        Cf, z = np.asfortranarray(Cm), rng.standard_normal(p * N)
+        rc = lib.lmm_mvn_logpdf_rand(ctx.handle, ptr(M), ptr(Cf), p * N, None, None, ptr(z), ptr(out), C.byref(il))
+        ctx.check(rc)
+        return out
     if isinstance(f, _JointPosterior):
         z = rng.standard_normal(p * N)
         rc = lib.lmm_post_rand(owner.handle, ptr(pts), N, fx.sigma2, ptr(z), None, ptr(out), C.byref(il))
