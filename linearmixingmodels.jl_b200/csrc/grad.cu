@@ -13,25 +13,22 @@ namespace lmm {
 __device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // κ and dK/ds (both already multiplied by the variance where appropriate): returns κ (unscaled by variance)
-__device__ __forceinline__ void kappa_and_ds(int kind, double d2, double inv_ls, double& kap, double& dkds) {
+__device__ __forceinline__ void kappa_and_ds(int kind, double d2, double rinv_ls, double& kap, double& dkds) {
   if (kind == 0) {
-    if (d2 > 1500.0) { kap = 0.0; dkds = 0.0; return; }
-    kap = exp(-d2 / 2.0);
-    dkds = -kap * d2 / inv_ls;
+    kap = exp_nonpos(-0.5 * d2);
+    dkds = -kap * d2 * rinv_ls;
   } else {
     const double d = sqrt(d2);
     if (kind == 1) {
       const double s = 1.7320508075688772 * d;
-      if (s > 800.0) { kap = 0.0; dkds = 0.0; return; }
-      const double e = exp(-s);
+      const double e = exp_nonpos(-s);
       kap = (1.0 + s) * e;
-      dkds = -3.0 * d2 * e / inv_ls;
+      dkds = -3.0 * d2 * e * rinv_ls;
     } else {
       const double s = 2.23606797749979 * d;
-      if (s > 800.0) { kap = 0.0; dkds = 0.0; return; }
-      const double e = exp(-s);
-      kap = (1.0 + s + 5.0 * (d * d) / 3.0) * e;
-      dkds = -(5.0 / 3.0) * d2 * (1.0 + s) * e / inv_ls;
+      const double e = exp_nonpos(-s);
+      kap = (1.0 + s + (d * d) * 1.6666666666666667) * e;
+      dkds = -(5.0 / 3.0) * d2 * (1.0 + s) * e * rinv_ls;
     }
   }
 }
@@ -55,6 +52,7 @@ __global__ void __launch_bounds__(256) kgrad_kernel(TiledSym negCinv, const doub
   while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
   const int J = tl - (int)((size_t)I * (I + 1) / 2);
   const LatentParams lp = params[b];
+  const double rinv_ls = 1.0 / lp.inv_ls;
   for (int i = t; i < TILE * D; i += 256) {
     xa[i] = xpad[(size_t)I * TILE * D + i] * lp.inv_ls;
     xb[i] = xpad[(size_t)J * TILE * D + i] * lp.inv_ls;
@@ -92,7 +90,7 @@ __global__ void __launch_bounds__(256) kgrad_kernel(TiledSym negCinv, const doub
       } else {
         const double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)cc * D, D, sa[r], sb[cc], form);
         double kap, dk;
-        kappa_and_ds(lp.kind, d2, lp.inv_ls, kap, dk);
+        kappa_and_ds(lp.kind, d2, rinv_ls, kap, dk);
         gv = fma(2.0 * G, kap, gv);
         gs = fma(2.0 * G, dk, gs);
       }
@@ -196,6 +194,7 @@ __global__ void __launch_bounds__(256) kgrad_block_kernel(TiledSym negCinv, cons
   while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
   const int J = tl - (int)((size_t)I * (I + 1) / 2);
   const LatentParams lp = params[a];
+  const double rinv_ls = 1.0 / lp.inv_ls;
   for (int i = t; i < TILE * D; i += 256) {
     const int ra = I * TILE + i / D, rb = J * TILE + i / D;
     xa[i] = ra < N ? x[(size_t)ra * D + i % D] * lp.inv_ls : 0.0;
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(256) kgrad_block_kernel(TiledSym negCinv, cons
     } else {
       const double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)c * D, D, sa[r], sb[c], form);
       double kap, dk;
-      kappa_and_ds(lp.kind, d2, lp.inv_ls, kap, dk);
+      kappa_and_ds(lp.kind, d2, rinv_ls, kap, dk);
       gv = fma(2.0 * G, kap, gv);
       gs = fma(2.0 * G, dk, gs);
     }
