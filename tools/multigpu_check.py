@@ -84,6 +84,17 @@ def main():
     for k in ("variance", "inv_lengthscale", "mean_const", "y", "S", "U"):
         errs["grad_" + k] = float(np.max(np.abs(g[k] - gr[k])) / (np.max(np.abs(gr[k])) + 1e-12))
     errs["grad_sigma2"] = abs(g["sigma2"] - gr["sigma2"]) / abs(gr["sigma2"])
+    # posterior-predictive logpdf gradient and a per-observation-noise IndependentMOGP across ranks
+    lpp, gp_ = lmm.logpdf_and_gradient(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.2), ys, with_grad_y=True)
+    lppr, gpr = o.oilmm_post_logpdf_grad(opost, xs, 0.2, ys)
+    errs["postgrad_value"] = abs(lpp - lppr) / abs(lppr)
+    errs["postgrad_sigma2"] = abs(gp_["sigma2"] - gpr["sigma2"]) / abs(gpr["sigma2"])
+    errs["postgrad_y"] = float(np.max(np.abs(gp_["y"] - gpr["y"])) / np.max(np.abs(gpr["y"])))
+    fi = lmm.independent_mogp(gps)
+    vn = np.random.default_rng(8).uniform(0.05, 0.5, m * N)
+    yi = y[: m * N]
+    errs["imogp_vector_noise"] = abs(lmm.logpdf(fi(lmm.MOInputIsotopicByOutputs(x, m), vn), yi) - o.imogp_logpdf_noise(fs, x, vn, yi)) / abs(
+        o.imogp_logpdf_noise(fs, x, vn, yi))
     post2.f.fs[0]._owner.free()
     worst = max(errs.values())
     ok = worst < 1e-6 and max(errs[k] for k in ("logpdf", "mean", "var", "post_logpdf", "grad_value")) < 1e-9
