@@ -109,3 +109,32 @@ def test_product_path_does_not_import_oracle():
         for fn in files:
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".inc", ".jl")):
                 assert not pat.search(open(os.path.join(dirpath, fn)).read()), fn
+
+
+C_CLIENT = os.path.join(ROOT, "examples", "c_client")
+
+
+def _build_c_client():
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_client.c"),
+                    "-L" + os.path.dirname(_lib.LIB_PATH), "-llmm", "-lm", "-Wl,-rpath,$ORIGIN/../linearmixingmodels.jl_b200", "-o", C_CLIENT],
+                   check=True)
+
+
+def test_header_is_valid_c_and_plain_c_client_links():
+    """include/lmm.h compiles as C99 and a program that includes nothing but it links against liblmm.so; without a
+    GPU the client reports the missing device (exit code 77): there is no CPU fallback to fall into."""
+    _build_c_client()
+    r = subprocess.run([C_CLIENT], capture_output=True, text=True)
+    import torch
+
+    if not torch.cuda.is_available():
+        assert r.returncode == 77 and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_client_runs_on_gpu(tmp_path):
+    """The drop-in boundary without Python in the call path: examples/c_client.c (BASELINE config 1 through the C ABI)."""
+    _build_c_client()
+    r = subprocess.run([C_CLIENT, str(tmp_path / "post.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "c_client ok" in r.stdout
