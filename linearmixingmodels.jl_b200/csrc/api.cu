@@ -29,6 +29,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommSplit)(void*, int, int, void**, void*) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
@@ -47,6 +48,7 @@ static NcclApi& nccl_api() {
     api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
     api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
     api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+    api.CommSplit = (int (*)(void*, int, int, void**, void*))dlsym(api.handle, "ncclCommSplit");
     api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
     api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
     api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
@@ -68,6 +70,14 @@ struct lmm_ctx {
   bool outer_block_user = false;
   int nranks = 1, rank = 0;
   void* comm = nullptr;
+  void* comm_small = nullptr;  // few-CTA communicator for the small, latency-critical exchanges on the panel chain
+  int nccl_small_ctas = 0;  // 0: NCCL's own choice
+  int profile_partition = 0;  // option "profile_partition": per-phase CUDA-event times of the row-cyclic schedule on stderr
+  void* comm2 = nullptr;  // second communicator (ncclCommSplit): the large exchanges of the partitioned factorisation, which
+                          // overlap the panel chain's small ones on another stream
+  cudaStream_t xchg_stream = nullptr;
+  void* xbuf2 = nullptr;
+  size_t xbuf2_bytes = 0;
   int64_t launches = 0, h2d = 0, d2h = 0;
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[8];
@@ -436,13 +446,13 @@ cudaError_t chol_factor_rowcyclic(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
       }
       // ... then exchange the block column so that every rank can factor it
       const int slots = (nt - s0 + G - 1) / G;
-      if ((e = launch_rowcyclic_pack(X, L, s0, s1, G, me, slots, sendb)) != cudaSuccess) return e;
+      if ((e = launch_rowcyclic_pack(X, L, s0, s1, s0, nt, G, me, slots, sendb)) != cudaSuccess) return e;
       const size_t cntel = (size_t)slots * (s1 - s0) * TT;
-      if (nccl_api().AllGather(sendb, recvb, cntel, NCCL_DOUBLE, ctx->comm, X) != 0) {
+      if (nccl_api().AllGather(sendb, recvb, cntel, NCCL_DOUBLE, ctx->comm_small ? ctx->comm_small : ctx->comm, X) != 0) {
         ctx->dist_error = 1;
         return cudaErrorUnknown;
       }
-      if ((e = launch_rowcyclic_unpack(X, L, s0, s1, G, me, slots, recvb)) != cudaSuccess) return e;
+      if ((e = launch_rowcyclic_unpack(X, L, s0, s1, s0, nt, G, me, slots, recvb)) != cudaSuccess) return e;
       ctx->launches += 2;
     }
     g.row_step = 1;
@@ -478,11 +488,176 @@ cudaError_t chol_factor_rowcyclic(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
   return cudaSuccess;
 }
 
+// Second row-cyclic schedule ("partition_ilmm" = 2): the panel's TRSM is distributed as well and the large exchange leaves
+// the critical path.  Per block column b = [s0, s1), next block [s1, s2):
+//   X (panel stream, communicator 1): update(b-1 -> b) on own rows; all-gather of the DIAGONAL block rows [s0, s1) (<= ob
+//     tile rows); diagonal block factored redundantly; TRSM of the OWN rows >= s1; all-gather of the NEXT block's rows
+//     [s1, s2) of the finished panel -- all the next update(b -> b+1) needs besides the own rows.
+//   Z (exchange stream, communicator 2): all-gather of the rows >= s2 of the finished panel -- the bulk of the data --
+//     concurrently with the next panel; it only gates
+//   Y (update stream): update(b -> b+2..end) on own rows.
+// Everything on the panel chain is small (<= 2 ob tile rows exchanged, 1/G of the TRSM and update waves).
+cudaError_t chol_factor_rowcyclic2(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, double* logdet, int* info) {
+  const int nt = L.nt, G = ctx->nranks, me = ctx->rank;
+  const int ob = ctx->outer_block_user ? ctx->outer_block : (nt <= 72 ? 2 : nt <= 160 ? 3 : 4);
+  const int nblk = (nt + ob - 1) / ob;
+  cudaError_t e;
+  while ((int)ctx->blk_ev.size() < 3 * nblk + 3) {
+    cudaEvent_t ev;
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    ctx->blk_ev.push_back(ev);
+  }
+  auto grow = [&](void*& buf, size_t& have, size_t need) -> cudaError_t {
+    if (have >= need) return cudaSuccess;
+    if (buf) cudaFree(buf);
+    buf = nullptr;
+    have = 0;
+    cudaError_t ee = cudaMalloc(&buf, need);
+    if (ee == cudaSuccess) have = need;
+    return ee;
+  };
+  // small exchanges (<= ob rows): [send | recv]; large ones: sized for the first block
+  const int small_slots = (2 * ob + G - 1) / G;
+  const size_t small_send = (size_t)small_slots * ob * TT;
+  if ((e = grow(ctx->xbuf, ctx->xbuf_bytes, small_send * (size_t)(G + 1) * sizeof(double))) != cudaSuccess) return e;
+  const int big_slots0 = (nt + G - 1) / G;
+  const size_t big_send = (size_t)big_slots0 * ob * TT;
+  if ((e = grow(ctx->xbuf2, ctx->xbuf2_bytes, big_send * (size_t)(G + 1) * sizeof(double))) != cudaSuccess) return e;
+  double* ssend = (double*)ctx->xbuf;
+  double* srecv = ssend + small_send;
+  double* bsend = (double*)ctx->xbuf2;
+  double* brecv = bsend + big_send;
+  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream, Z = ctx->xchg_stream;
+  cudaEvent_t* evX = ctx->blk_ev.data();
+  cudaEvent_t* evY = evX + nblk;
+  cudaEvent_t* evZ = evY + nblk;
+  GemmArgs g{};
+  g.A = operand(L); g.B = operand(L); g.C = operand(L);
+  g.W = W; g.w_batch_stride = wstride; g.sym = 1;
+  auto first_own = [&](int s) { return s + (((me - s % G) % G) + G) % G; };
+  auto own_count = [&](int s) { const int f = first_own(s); return f >= nt ? 0 : (nt - 1 - f) / G + 1; };
+  auto gather = [&](cudaStream_t st, void* comm, int s0, int s1, int ra, int rb, double* sendb, double* recvb) -> cudaError_t {
+    if (rb <= ra) return cudaSuccess;
+    const int slots = (rb - ra + G - 1) / G;
+    cudaError_t ee;
+    if ((ee = launch_rowcyclic_pack(st, L, s0, s1, ra, rb, G, me, slots, sendb)) != cudaSuccess) return ee;
+    if (nccl_api().AllGather(sendb, recvb, (size_t)slots * (s1 - s0) * TT, NCCL_DOUBLE, comm, st) != 0) {
+      ctx->dist_error = 1;
+      return cudaErrorUnknown;
+    }
+    if ((ee = launch_rowcyclic_unpack(st, L, s0, s1, ra, rb, G, me, slots, recvb)) != cudaSuccess) return ee;
+    ctx->launches += 2;
+    return cudaSuccess;
+  };
+  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(Z, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  // optional phase profile of the panel chain: [0] wait for the trailing update, [1] own-row update, [2] exchange,
+  // [3] redundant diagonal / next-block rows, [4] own-row TRSM
+  std::vector<cudaEvent_t> pev;
+  const bool prof = ctx->profile_partition != 0;
+  auto mark = [&]() {
+    if (!prof) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, X);
+    pev.push_back(ev);
+  };
+  for (int b = 0; b < nblk; ++b) {
+    const int s0 = b * ob, s1 = (s0 + ob < nt) ? s0 + ob : nt, s2 = (s1 + ob < nt) ? s1 + ob : nt;
+    mark();
+    if (b >= 2 && (e = cudaStreamWaitEvent(X, evY[b - 2], 0)) != cudaSuccess) return e;
+    mark();
+    if (b >= 1) {
+      const int cnt = own_count(s0);
+      if (cnt > 0) {  // own rows of block column b <- block b-1 (B operand rows [s0, s1) arrived with the previous panel)
+        g.row_step = G; g.i0 = first_own(s0); g.j0 = s0; g.k0 = s0 - ob; g.k1 = s0;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, cnt, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+        ctx->timings[6] += 1;
+      }
+      mark();
+      // the diagonal block AND the next block's rows, in one small exchange
+      if ((e = gather(X, ctx->comm_small ? ctx->comm_small : ctx->comm, s0, s1, s0, s2, ssend, srecv)) != cudaSuccess) return e;
+    }
+    if (b == 0) mark();
+    mark();
+    g.row_step = 1;
+    for (int jj = s0; jj < s1; ++jj) {  // diagonal block and the next block's rows [s1, s2): every rank
+      if (jj > s0) {
+        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, s2 - jj, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+      if ((e = launch_potrf_tile(X, L, W, wstride, jj, 1, logdet, info)) != cudaSuccess) return e;
+      ++ctx->launches;
+      if (jj + 1 < s2) {
+        g.i0 = jj + 1; g.j0 = jj;
+        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, s2 - jj - 1, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+    }
+    mark();
+    const int cnt1 = s2 < nt ? own_count(s2) : 0;
+    if (cnt1 > 0) {  // own rows below: in-block updates + TRSM, column by column
+      g.row_step = G; g.i0 = first_own(s2);
+      for (int jj = s0; jj < s1; ++jj) {
+        if (jj > s0) {
+          g.j0 = jj; g.k0 = s0; g.k1 = jj;
+          if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, cnt1, 1)) != cudaSuccess) return e;
+          ++ctx->launches;
+        }
+        g.j0 = jj;
+        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, cnt1, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+    }
+    mark();
+    if ((e = cudaEventRecord(evX[b], X)) != cudaSuccess) return e;
+    if (s2 < nt) {
+      // the bulk of the panel travels beside the next panel's work and only gates the trailing update
+      if ((e = cudaStreamWaitEvent(Z, evX[b], 0)) != cudaSuccess) return e;
+      if ((e = gather(Z, ctx->comm2, s0, s1, s2, nt, bsend, brecv)) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(evZ[b], Z)) != cudaSuccess) return e;
+      const int cnt2 = own_count(s2);
+      if (cnt2 > 0) {
+        if ((e = cudaStreamWaitEvent(Y, evZ[b], 0)) != cudaSuccess) return e;
+        g.row_step = G; g.i0 = first_own(s2); g.j0 = s2; g.k0 = s0; g.k1 = s1;
+        if ((e = launch_gemm(Y, GEMM_UPDATE, g, nt - s2, cnt2, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+        ctx->timings[6] += 1;
+      }
+    }
+    if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
+  }
+  if ((e = cudaStreamWaitEvent(ctx->stream, evX[nblk - 1], 0)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_join[1], Z)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0)) != cudaSuccess) return e;
+  if (prof) {
+    cudaStreamSynchronize(X);
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int b = 0; b < nblk; ++b)
+      for (int k = 0; k < 5; ++k) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pev[(size_t)b * 6 + k], pev[(size_t)b * 6 + k + 1]);
+        acc[k] += ms;
+      }
+    fprintf(stderr, "[liblmm rank %d] row-cyclic chain, nt=%d ob=%d: wait_trailing %.2f ms, own_update %.2f, exchange %.2f, "
+                    "diag+next rows %.2f, own TRSM %.2f\n", me, nt, ob, acc[0], acc[1], acc[2], acc[3], acc[4]);
+    for (cudaEvent_t ev : pev) cudaEventDestroy(ev);
+  }
+  return cudaSuccess;
+}
+
 // Fork the batch into latent groups on separate streams (joined back into ctx->stream).
 cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
   const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
   if (ctx->partition_ilmm && ctx->partition_now && batch == 1 && ctx->comm && ctx->nranks > 1 && L.nt >= 2 * ctx->nranks && nccl_api().AllGather)
-    return chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
+    return (ctx->partition_ilmm == 2 && ctx->comm2) ? chol_factor_rowcyclic2(ctx, L, W, wstride, logdet, info)
+                                                    : chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
   if (ctx->lookahead == 2 && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
   if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
   if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info);
@@ -671,6 +846,7 @@ extern "C" int lmm_ctx_create(int device, lmm_ctx** out) {
     cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
     cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, hi_pri);
     cudaStreamCreateWithPriority(&ctx->update_stream, cudaStreamNonBlocking, lo_pri);
+    cudaStreamCreateWithPriority(&ctx->xchg_stream, cudaStreamNonBlocking, hi_pri);
   }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   for (auto& e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -687,7 +863,11 @@ extern "C" int lmm_ctx_destroy(lmm_ctx* ctx) {
   if (!ctx) return LMM_E_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm_small && nccl_api().ok) nccl_api().CommDestroy(ctx->comm_small);
+  if (ctx->comm2 && nccl_api().ok) nccl_api().CommDestroy(ctx->comm2);
   if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
+  if (ctx->xbuf2) cudaFree(ctx->xbuf2);
+  cudaStreamDestroy(ctx->xchg_stream);
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& g : ctx->gstream) cudaStreamDestroy(g);
   if (ctx->xbuf) cudaFree(ctx->xbuf);
@@ -725,8 +905,17 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "lookahead") {
     if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "lookahead must be 0, 1 (left-looking, K-split) or 2 (right-looking)");
     ctx->lookahead = (int)value;
+  } else if (k == "nccl_small_ctas") {  // takes effect at lmm_comm_init
+    if (value < 0 || value > 32) return ctx->fail(LMM_E_ARG, "nccl_small_ctas must be in [0, 32]");
+    ctx->nccl_small_ctas = (int)value;
+  } else if (k == "profile_partition") {
+    ctx->profile_partition = value != 0.0;
   } else if (k == "partition_ilmm") {
-    ctx->partition_ilmm = value != 0.0;
+    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "partition_ilmm must be 0, 1 or 2");
+    ctx->partition_ilmm = (int)value;
+  } else if (k == "gemm_small") {
+    if (value < 0 || value > 4096) return ctx->fail(LMM_E_ARG, "gemm_small must be in [0, 4096]");
+    set_gemm_small_threshold((int)value);
   } else if (k == "gemm_impl") {
     if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0, 1 or 2");
     set_gemm_impl((int)value);
@@ -782,6 +971,22 @@ extern "C" int lmm_comm_init(lmm_ctx* ctx, const void* unique_id_128_bytes, int 
   if (r != 0) return ctx->fail(LMM_E_NCCL, std::string("ncclCommInitRank: ") + (api.GetErrorString ? api.GetErrorString(r) : "?"));
   ctx->nranks = nranks;
   ctx->rank = rank;
+  // Communicators of the partitioned factorisation (optional: without them it uses the main one).  Their exchanges sit on
+  // the panel chain while the trailing GEMMs hold every SM (one 192 KB CTA each), so an NCCL kernel waits for as many
+  // SMs to drain as it has CTAs: cap them (ncclConfig_t minCTAs / maxCTAs; the prefix of the struct as of NCCL 2.18).
+  if (api.CommSplit && nranks > 1) {
+    struct { size_t size; unsigned magic; unsigned version; int blocking, cgaClusterSize, minCTAs, maxCTAs; const char* netName; int splitShare; } cfg;
+    const int UNDEF = -2147483647 - 1;
+    auto split = [&](void** out, int max_ctas) {
+      cfg = {sizeof(cfg), 0xcafebeefu, 21800u, UNDEF, UNDEF, 1, max_ctas, nullptr, UNDEF};
+      if (api.CommSplit(ctx->comm, 0, rank, out, &cfg) != 0) {
+        *out = nullptr;
+        if (api.CommSplit(ctx->comm, 0, rank, out, nullptr) != 0) *out = nullptr;
+      }
+    };
+    if (ctx->nccl_small_ctas > 0) split(&ctx->comm_small, ctx->nccl_small_ctas);
+    if (api.CommSplit(ctx->comm, 0, rank, &ctx->comm2, nullptr) != 0) ctx->comm2 = nullptr;
+  }
   return LMM_OK;
 }
 

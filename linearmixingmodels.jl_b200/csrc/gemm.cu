@@ -282,6 +282,90 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   }
 }
 
+// Latency-optimised variant for SMALL grids (the panel chain of a batch-1 / partitioned factorisation: a handful of
+// tiles whose 17 us per k-tile on one SM sit on the critical path).  One 128x128 tile is split into 4 row slices of 32
+// rows, one CTA each (4x the SMs per tile, a quarter of the time); no shared memory at all: in the k4-interleaved tile
+// layout every m8n8k4 fragment is 32 contiguous doubles in lane order, so each warp loads its A / B fragments with
+// coalesced 256-byte accesses straight from L2 (the 8 warps of a CTA share the A rows through L1).  Warp w owns columns
+// [16w, 16w+16) of the slice: 4 x 2 fragments, 8 DMMAs per k4-step.  TRSM is in place: a CTA only reads its own rows of
+// C(I,J), and a CTA barrier separates its last read from its first write.
+template <int MODE>
+__global__ void __launch_bounds__(256) gemm_direct_kernel(GemmArgs g) {
+  constexpr int SPLIT = 4;
+  const int J = g.j0 + (int)(blockIdx.x / SPLIT), slice = (int)(blockIdx.x % SPLIT);
+  const int I = g.i0 + blockIdx.y * (g.row_step > 0 ? g.row_step : 1), b = blockIdx.z;
+  if (g.sym && I < J) return;
+  if (g.upper && I > J) return;
+  const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;
+  if (MODE == GEMM_UPDATE && kb >= g.k1) return;
+  double* Ctile = g.C.tile(b, I, J);
+  const double* Asrc;
+  const double* Bsrc;
+  int nsteps;
+  if (MODE == GEMM_UPDATE) {
+    Asrc = g.A.tile(b, I, kb);
+    Bsrc = g.B.tile(b, J, kb);
+    nsteps = (g.k1 - kb) * 32;
+  } else {
+    Asrc = Ctile;
+    Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
+    nsteps = 32;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* pa = Asrc + (slice * 4) * 32 + lane;   // row blocks slice*4 .. slice*4+3
+  const double* pb = Bsrc + (warp * 2) * 32 + lane;    // column blocks warp*2, warp*2+1
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double a[4], bq[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = pa[i * 32];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) bq[j] = pb[j * 32];
+#pragma unroll 4
+  for (int q = 0; q < nsteps; ++q) {
+    double an[4], bn[2];
+    const int qn = (q + 1 < nsteps) ? q + 1 : q;  // prefetch the next k4-step (512 doubles further: tiles of one row panel are contiguous)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) an[i] = pa[(size_t)qn * 512 + i * 32];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) bn[j] = pb[(size_t)qn * 512 + j * 32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = an[i];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) bq[j] = bn[j];
+  }
+  if (MODE == GEMM_TRSM) __syncthreads();  // every warp of this CTA has finished reading its rows of C(I,J)
+  const int g4 = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int cg = warp * 4 + j * 2 + (t4 >> 1);
+      const int off = (cg << 9) + ((slice * 4 + i) << 5) + (g4 << 2) + ((t4 & 1) << 1);
+      double2* ptr = reinterpret_cast<double2*>(Ctile + off);
+      double2 v;
+      if (MODE == GEMM_UPDATE) {
+        v = *ptr;
+        v.x -= acc[i][j][0];
+        v.y -= acc[i][j][1];
+      } else {
+        v.x = acc[i][j][0];
+        v.y = acc[i][j][1];
+      }
+      *ptr = v;
+    }
+}
+
+static int g_gemm_small = 74;  // grids of at most this many tiles take the latency-optimised kernel (0 = never)
+void set_gemm_small_threshold(int tiles) { g_gemm_small = tiles; }
+
 static int g_gemm_impl = 2;  // 0: v1 cp.async ring; 1: v2 (TMA bulk + mbarriers), 16-column stages; 2: v2, 32-column stages
 void set_gemm_impl(int impl) { g_gemm_impl = impl; }
 
@@ -305,6 +389,14 @@ cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols,
     e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_TRSM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
+  }
+  if ((long long)ncols * nrows * batch <= g_gemm_small) {
+    dim3 gs((unsigned)ncols * 4, (unsigned)nrows, (unsigned)batch);
+    if (mode == GEMM_UPDATE)
+      gemm_direct_kernel<GEMM_UPDATE><<<gs, 256, 0, st>>>(a);
+    else
+      gemm_direct_kernel<GEMM_TRSM><<<gs, 256, 0, st>>>(a);
+    return cudaGetLastError();
   }
   dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
   if (g_gemm_impl == 1) {

@@ -40,6 +40,7 @@ struct GemmArgs {
 };
 enum { GEMM_UPDATE = 0, GEMM_TRSM = 1 };
 cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch);
+void set_gemm_small_threshold(int tiles);  // grids of <= tiles tiles use the latency-optimised direct kernel (default 74; 0 = off)
 void set_gemm_impl(int impl);  // 0: cp.async ring + CTA barrier; 1/2: TMA bulk + full/empty mbarrier ring, 16/32-column stages (2 = default)
 
 // ---- potrf.cu : factor diagonal tile (J,J) in place, W(J) = inv(L_JJ), logdet += 2*sum(log diag)
@@ -65,11 +66,12 @@ cudaError_t launch_lower_gemv(cudaStream_t st, TiledSym L, const double* z, size
 cudaError_t launch_untile_lower(cudaStream_t st, TiledSym L, int b, double* dense, int N);
 // tile: dense N x N col-major (lower read, mirrored) -> tiles (identity on padding)
 cudaError_t launch_tile_from_dense(cudaStream_t st, TiledSym L, int batch, const double* dense, int N);
-// Row-cyclic exchange of one block column [s0, s1) of a packed-lower matrix (batch 1): rank r owns tile rows
-// I = r (mod G).  pack: own rows I >= s0 -> buf[q][ob tiles] (q = index among the own rows); unpack: every other
-// rank's rows from an all-gathered buffer [G][slots][ob tiles] back into the matrix.
-cudaError_t launch_rowcyclic_pack(cudaStream_t st, TiledSym L, int s0, int s1, int G, int rank, int slots, double* buf);
-cudaError_t launch_rowcyclic_unpack(cudaStream_t st, TiledSym L, int s0, int s1, int G, int rank, int slots, const double* all);
+// Row-cyclic exchange of tile rows [ra, rb) of one block column [s0, s1) of a packed-lower matrix (batch 1): rank r
+// owns tile rows I = r (mod G).  pack: own rows -> buf[q][ob tiles] (q = index among the own rows >= ra); unpack: every
+// other rank's rows from an all-gathered buffer [G][slots][ob tiles] back into the matrix.
+cudaError_t launch_rowcyclic_pack(cudaStream_t st, TiledSym L, int s0, int s1, int ra, int rb, int G, int rank, int slots, double* buf);
+cudaError_t launch_rowcyclic_unpack(cudaStream_t st, TiledSym L, int s0, int s1, int ra, int rb, int G, int rank, int slots,
+                                    const double* all);
 
 // ---- proj.cu
 // Ty[i][n] = sum_j T[i + lat0][j] Y[j][n] - mean_i  (i < mloc), written to ty[i*ty_stride + n], zero padding to ty_stride

@@ -273,15 +273,16 @@ cudaError_t launch_untile_rect_blockdiag(cudaStream_t st, TiledRect A, int batch
 
 
 // ---- row-cyclic block-column exchange (multi-GPU Cholesky of one large factor) ---------------------
-// grid (slots, ob): one CTA copies one tile (16384 doubles, 128-bit accesses).
-__global__ void __launch_bounds__(256) rowcyclic_copy_kernel(TiledSym L, int s0, int s1, int G, int rank_lo, int rank_hi, int skip_rank,
-                                                             int slots, double* __restrict__ buf, int to_buf) {
+// Tile rows [ra, rb) of block column [s0, s1); rank r owns the rows I = r (mod G).  Slot q of rank r is its q-th
+// own row >= ra.  grid (slots, ob): one CTA copies one tile (16384 doubles, 128-bit accesses).
+__global__ void __launch_bounds__(256) rowcyclic_copy_kernel(TiledSym L, int s0, int s1, int ra, int rb, int G, int rank_lo, int rank_hi,
+                                                             int skip_rank, int slots, double* __restrict__ buf, int to_buf) {
   const int ob = s1 - s0, q = blockIdx.x, c = blockIdx.y;
   for (int r = rank_lo; r < rank_hi; ++r) {
     if (r == skip_rank) continue;
-    int first = s0 + ((r - s0 % G) % G + G) % G;  // first tile row >= s0 owned by rank r
+    const int first = ra + ((r - ra % G) % G + G) % G;  // first tile row >= ra owned by rank r
     const int I = first + q * G;
-    if (I >= L.nt) continue;
+    if (I >= rb) continue;
     const int J = s0 + c;
     if (J > I) continue;  // above the diagonal inside the block
     double2* t = reinterpret_cast<double2*>(L.tile(0, I, J));
@@ -292,14 +293,15 @@ __global__ void __launch_bounds__(256) rowcyclic_copy_kernel(TiledSym L, int s0,
     }
   }
 }
-cudaError_t launch_rowcyclic_pack(cudaStream_t st, TiledSym L, int s0, int s1, int G, int rank, int slots, double* buf) {
+cudaError_t launch_rowcyclic_pack(cudaStream_t st, TiledSym L, int s0, int s1, int ra, int rb, int G, int rank, int slots, double* buf) {
   dim3 grid((unsigned)slots, (unsigned)(s1 - s0));
-  rowcyclic_copy_kernel<<<grid, 256, 0, st>>>(L, s0, s1, G, rank, rank + 1, -1, slots, buf, 1);
+  rowcyclic_copy_kernel<<<grid, 256, 0, st>>>(L, s0, s1, ra, rb, G, rank, rank + 1, -1, slots, buf, 1);
   return cudaGetLastError();
 }
-cudaError_t launch_rowcyclic_unpack(cudaStream_t st, TiledSym L, int s0, int s1, int G, int rank, int slots, const double* all) {
+cudaError_t launch_rowcyclic_unpack(cudaStream_t st, TiledSym L, int s0, int s1, int ra, int rb, int G, int rank, int slots,
+                                    const double* all) {
   dim3 grid((unsigned)slots, (unsigned)(s1 - s0));
-  rowcyclic_copy_kernel<<<grid, 256, 0, st>>>(L, s0, s1, G, 0, G, rank, slots, const_cast<double*>(all), 0);
+  rowcyclic_copy_kernel<<<grid, 256, 0, st>>>(L, s0, s1, ra, rb, G, 0, G, rank, slots, const_cast<double*>(all), 0);
   return cudaGetLastError();
 }
 

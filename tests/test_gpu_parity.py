@@ -153,10 +153,12 @@ def test_oilmm_mid_size_multi_tile(lmm):
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
 
 
-@pytest.mark.parametrize("impl,streams,outer", [(0, 1, 8), (1, 1, 3), (0, 4, 16), (1, 8, 1), (2, 2, 8), (2, 1, 5)])
-def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer):
-    """Both GEMM pipelines (cp.async ring / TMA bulk + mbarrier ring), any stream-group count and
-    any outer block width give the same factor (N = 1100: 9 tile columns, batch 3)."""
+@pytest.mark.parametrize("impl,streams,outer,small", [(0, 1, 8, 74), (1, 1, 3, 74), (0, 4, 16, 0), (1, 8, 1, 0), (2, 2, 8, 0), (2, 1, 5, 74),
+                                                      (2, 4, 8, 4096)])
+def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer, small):
+    """Both GEMM pipelines (cp.async ring / TMA bulk + mbarrier ring), the latency-optimised direct kernel for small grids
+    (off / default threshold / everywhere), any stream-group count and any outer block width give the same factor
+    (N = 1100: 9 tile columns, batch 3)."""
     N, p, m, Ns = 1100, 5, 3, 70
     x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=77, means=True)
     om = o.OILMMModel(fs, U, S)
@@ -165,6 +167,7 @@ def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer):
     ctx.set_option("gemm_impl", impl)
     ctx.set_option("streams", streams)
     ctx.set_option("outer_block", outer)
+    ctx.set_option("gemm_small", small)
     try:
         fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
         post, lp = lmm.posterior(fx, y, with_logpdf=True)
@@ -176,7 +179,8 @@ def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer):
     finally:
         ctx.set_option("gemm_impl", 2)
         ctx.set_option("streams", 4)
-        ctx.set_option("outer_block", 8)
+        ctx.set_option("outer_block", 0)
+        ctx.set_option("gemm_small", 74)
 
 
 def test_distance_form_option(lmm):

@@ -34,14 +34,14 @@ def main():
     A = rng.standard_normal((N, N))
     A = A @ A.T / N + np.eye(N)
     Lr = sla.cholesky(A, lower=True)
-    for ob in (0, 1, 3):
-        ctx.set_option("partition_ilmm", 1)
+    for part, ob in ((1, 0), (1, 1), (1, 3), (2, 0), (2, 1), (2, 3), (2, 5)):
+        ctx.set_option("partition_ilmm", part)
         ctx.set_option("outer_block", ob)
         L, logdet, info = lmm.potrf_batched(A)
         err = float(np.max(np.abs(L[0] - Lr)))
         good = info[0] == 0 and err < 1e-11 and abs(logdet[0] - 2 * np.sum(np.log(np.diag(Lr)))) < 1e-8
         ok &= bool(good)
-        print(f"rank {rank}: potrf N={N} outer_block={ob} partitioned max|L-L_lapack|={err:.2e} {'OK' if good else 'FAIL'}", flush=True)
+        print(f"rank {rank}: potrf N={N} schedule={part} outer_block={ob} partitioned max|L-L_lapack|={err:.2e} {'OK' if good else 'FAIL'}", flush=True)
     ctx.set_option("outer_block", 0)
     # ---- parity 2: general ILMM logpdf + posterior + marginals + conditioning + gradient with the partitioned factor
     Nn, p, m, Ns = 900, 6, 3, 40
@@ -55,7 +55,7 @@ def main():
     f = lmm.ILMM(lmm.independent_mogp(gps), H)
     O = lmm.MOInputIsotopicByOutputs
     res = {}
-    for part in (0, 1):
+    for part in (0, 2):
         ctx.set_option("partition_ilmm", part)
         post, lp = lmm.posterior(f(O(x, p), 0.1), y, with_logpdf=True)
         M, V = lmm.mean_and_var(post(O(xs, p), 0.1))
@@ -64,6 +64,7 @@ def main():
         post.f._owner.free()
     ref = o.ilmm_logpdf(fs, H, x, 0.1, y)
     Mr, Vr = o.ilmm_mean_and_var(o.ilmm_posterior(fs, H, x, 0.1, y), H, xs, 0.1)
+    res[1] = res[2]
     e_lp = abs(res[1][0] - ref) / abs(ref)
     e_m = float(np.max(np.abs(res[1][1] - Mr) / (np.abs(Mr) + 1e-9)))
     e_v = float(np.max(np.abs(res[1][2] - Vr) / np.abs(Vr)))
@@ -75,16 +76,18 @@ def main():
     # ---- timings: batch-1 Cholesky, single-GPU schedule vs row-cyclic partition (max over ranks)
     for Nb in sizes:
         out = {"N": Nb, "ranks": world}
-        for part in (0, 1):
+        for part in (0, 1, 2):
             ctx.set_option("partition_ilmm", part)
             dist.barrier()
             ms, _, ld = run(ctx, Nb, 1, reps=3)
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            out["partitioned_ms" if part else "single_gpu_ms"] = round(float(t.item()), 3)
-            out["logdet_part" if part else "logdet_single"] = ld
-        out["speedup"] = round(out["single_gpu_ms"] / out["partitioned_ms"], 3)
-        out["tflops_partitioned"] = round(Nb ** 3 / 3.0 / (out["partitioned_ms"] * 1e-3) / 1e12, 2)
+            key = ["single_gpu", "rowcyclic1", "rowcyclic2"][part]
+            out[key + "_ms"] = round(float(t.item()), 3)
+            out[key + "_logdet"] = ld
+        out["speedup1"] = round(out["single_gpu_ms"] / out["rowcyclic1_ms"], 3)
+        out["speedup2"] = round(out["single_gpu_ms"] / out["rowcyclic2_ms"], 3)
+        out["tflops_rowcyclic2"] = round(Nb ** 3 / 3.0 / (out["rowcyclic2_ms"] * 1e-3) / 1e12, 2)
         if rank == 0:
             print(json.dumps(out), flush=True)
     ctx.set_option("partition_ilmm", 0)
