@@ -320,6 +320,22 @@ cudaError_t chol_factor_lookahead(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
   return cudaSuccess;
 }
 
+// Trailing update of the columns >= s2 (tile rows first_row, first_row + row_step, ... < nt) by the k-tiles [k0, k1): ONE
+// launch.  (Chunking it into launches of <= 132 CTAs, to keep a few SMs free for the panel chain on the other stream, was
+// measured and is much slower -- N=16384: 48 -> 68 ms, N=8192: 8.5 -> 10.3 ms: every launch boundary costs a pipeline
+// fill and a tail, while a single launch keeps the block scheduler streaming CTAs.)
+cudaError_t launch_trailing(lmm_ctx* ctx, cudaStream_t st, GemmArgs g, int s2, int nt, int first_row, int row_step, int k0, int k1,
+                            int batch) {
+  const int nrows = first_row >= nt ? 0 : (nt - 1 - first_row) / row_step + 1;
+  if (nrows <= 0) return cudaSuccess;
+  g.i0 = first_row; g.j0 = s2; g.k0 = k0; g.k1 = k1; g.row_step = row_step;
+  cudaError_t e = launch_gemm(st, GEMM_UPDATE, g, nt - s2, nrows, batch);
+  if (e != cudaSuccess) return e;
+  ++ctx->launches;
+  ctx->timings[6] += 1;
+  return cudaSuccess;
+}
+
 // Right-looking block schedule with look-ahead (small batches).  After block column kb is factored on the
 // high-priority panel stream X, its update of the NEXT block column runs on X (so the next panel can start at
 // once) while its update of everything further right runs as one large GEMM on the low-priority stream Y:
@@ -376,11 +392,8 @@ cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t
     const int s2 = s1 + ob;  // first column of block b+2
     if (s2 < nt) {
       if ((e = cudaStreamWaitEvent(Y, evX[b], 0)) != cudaSuccess) return e;
-      g.i0 = s2; g.j0 = s2; g.k0 = s0; g.k1 = s1;
-      if ((e = launch_gemm(Y, GEMM_UPDATE, g, nt - s2, nt - s2, batch)) != cudaSuccess) return e;
+      if ((e = launch_trailing(ctx, Y, g, s2, nt, s2, 1, s0, s1, batch)) != cudaSuccess) return e;
       if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
-      ++ctx->launches;
-      ctx->timings[6] += 1;
     } else if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) {  // no trailing launch left: keep the event chain defined
       return e;
     }
@@ -475,10 +488,7 @@ cudaError_t chol_factor_rowcyclic(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
     const int cnt2 = s2 < nt ? own_count(s2) : 0;
     if (cnt2 > 0) {
       if ((e = cudaStreamWaitEvent(Y, evX[b], 0)) != cudaSuccess) return e;
-      g.row_step = G; g.i0 = first_own(s2); g.j0 = s2; g.k0 = s0; g.k1 = s1;
-      if ((e = launch_gemm(Y, GEMM_UPDATE, g, nt - s2, cnt2, 1)) != cudaSuccess) return e;
-      ++ctx->launches;
-      ctx->timings[6] += 1;
+      if ((e = launch_trailing(ctx, Y, g, s2, nt, first_own(s2), G, s0, s1, 1)) != cudaSuccess) return e;
     }
     if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
   }
@@ -623,10 +633,7 @@ cudaError_t chol_factor_rowcyclic2(lmm_ctx* ctx, TiledSym L, double* W, size_t w
       const int cnt2 = own_count(s2);
       if (cnt2 > 0) {
         if ((e = cudaStreamWaitEvent(Y, evZ[b], 0)) != cudaSuccess) return e;
-        g.row_step = G; g.i0 = first_own(s2); g.j0 = s2; g.k0 = s0; g.k1 = s1;
-        if ((e = launch_gemm(Y, GEMM_UPDATE, g, nt - s2, cnt2, 1)) != cudaSuccess) return e;
-        ++ctx->launches;
-        ctx->timings[6] += 1;
+        if ((e = launch_trailing(ctx, Y, g, s2, nt, first_own(s2), G, s0, s1, 1)) != cudaSuccess) return e;
       }
     }
     if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;

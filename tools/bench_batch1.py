@@ -16,7 +16,7 @@ if __name__ == "__main__":
     cfgs = arg(1, "4096x1,8192x1,16384x1,8192x2")
     las = [int(v) for v in arg(2, "2").split(",")]
     obs = [int(v) for v in arg(3, "0,1,2,3,4").split(",")]
-    smalls = [int(v) for v in arg(4, "0,74,160").split(",")]
+    smalls = [int(v) for v in arg(4, "74").split(",")]
     for cfg in cfgs.split(","):
         N, batch = [int(v) for v in cfg.split("x")]
         for la in las:
