@@ -79,6 +79,26 @@ __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const 
   const double* ar = xa + (size_t)r * dd;
   const double sar = sa[r];
   const double a0 = ar[0];
+  // interior off-diagonal tiles (almost all of them): no bounds / diagonal predicates in the element loop
+  if (DS == 1 && form == 0 && r0 + TILE <= Na && c0 + TILE <= Nb && !(SYM && r0 == c0)) {
+    const int cb = (2 * t) & 3;
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+      const int c = 4 * it + cb;
+      const double2 xb2 = *reinterpret_cast<const double2*>(xb + c);
+      const double2 sb2 = *reinterpret_cast<const double2*>(sb + c);
+      // the same arithmetic as the general path: one rounded product (Distances.jl's K=1 GEMM), then |a|²+|b|² - 2ab
+      double d0 = fma(-2.0, a0 * xb2.x, sar + sb2.x);
+      double d1 = fma(-2.0, a0 * xb2.y, sar + sb2.y);
+      d0 = d0 > 0.0 ? d0 : 0.0;
+      d1 = d1 > 0.0 ? d1 : 0.0;
+      double2 v;
+      v.x = kappa_eval(lp.kind, lp.variance, d0);
+      v.y = kappa_eval(lp.kind, lp.variance, d1);
+      *reinterpret_cast<double2*>(tile + it * 512 + 2 * t) = v;
+    }
+    return;
+  }
   for (int it = 0; it < 32; ++it) {
     const int c = 4 * it + ((2 * t) & 3);
     double2 v;
