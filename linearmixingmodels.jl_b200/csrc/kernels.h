@@ -127,3 +127,16 @@ cudaError_t launch_scale_sub(cudaStream_t st, double* v, const double* a, double
 namespace lmm {
 cudaError_t launch_untile_rect_blockdiag(cudaStream_t st, TiledRect A, int batch, int Na, int Nb, double* dense, size_t ld);
 }  // namespace lmm
+
+namespace lmm {
+// ---- misc.cu : small elementwise / bookkeeping kernels of the host drivers
+cudaError_t launch_lml_terms(cudaStream_t st, double* terms, int slot0, int nb, const double* logdet, const double* quad, int n, double log2pi);
+cudaError_t launch_regulariser(cudaStream_t st, double* slot, double c0, const double* resid, double sigma2);
+cudaError_t launch_add_scalar(cudaStream_t st, double* v, size_t n, double s);
+cudaError_t launch_copy_add(cudaStream_t st, int nlat, double* out, size_t stride_out, const double* in, size_t stride_in, int n, double s);
+cudaError_t launch_add_mean(cudaStream_t st, int nlat, double* v, size_t stride, int n, const LatentParams* params);
+cudaError_t launch_axpy(cudaStream_t st, double* y, const double* x, size_t n, double a);
+cudaError_t launch_fill_noise(cudaStream_t st, int nlat, double* nv, size_t stride, int n_old, int n_new, const double* old_vec, size_t old_stride,
+                              const LatentParams* old_params, const double* new_noise);
+cudaError_t launch_repeat_block(cudaStream_t st, double* dst, const double* E, int mm, size_t total);
+}  // namespace lmm

@@ -14,7 +14,7 @@ import numpy as np
 
 
 def shard_range(m: int, nranks: int, rank: int) -> Tuple[int, int]:
-    """Latents [lo, hi) owned by `rank` -- must match liblmm's shard_range (csrc/api.cu)."""
+    """Latents [lo, hi) owned by `rank` -- must match liblmm's shard_range (csrc/api.cu, `shard_range`)."""
     return (m * rank) // nranks, (m * (rank + 1)) // nranks
 
 
