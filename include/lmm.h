@@ -48,13 +48,18 @@ extern "C" {
 #define LMM_KERNEL_MATERN32 1
 #define LMM_KERNEL_MATERN52 2
 
-/* One latent `GP(mean_const, variance * (base_kernel ∘ ScaleTransform(inv_lengthscale)))`. */
+/* One latent `GP(mean_const, variance * (base_kernel ∘ ScaleTransform(inv_lengthscale) [∘ ARDTransform(ard)]))`.
+ * Inputs are multiplied by inv_lengthscale (and, per dimension, by ard[k]) BEFORE distances are taken
+ * (KernelFunctions semantics). */
+#define LMM_MAX_ARD 8
 typedef struct lmm_gp_desc {
   int32_t kind;           /* LMM_KERNEL_*                                   */
   int32_t reserved;       /* must be 0                                      */
   double variance;        /* ScaledKernel σ² (1.0 for a plain kernel)       */
   double inv_lengthscale; /* ScaleTransform s (1.0 for a plain kernel)      */
   double mean_const;      /* ZeroMean -> 0.0; ConstMean(c) -> c             */
+  const double* ard;      /* ARDTransform v: D positive per-dimension multipliers (D <= LMM_MAX_ARD), or NULL;
+                             read during the call only (posterior handles keep their own copy)           */
 } lmm_gp_desc;
 
 typedef struct lmm_ctx lmm_ctx;   /* owns device, stream, memory pool, optional NCCL communicator */

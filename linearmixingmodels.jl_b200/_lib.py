@@ -35,6 +35,7 @@ class GpDesc(C.Structure):
         ("variance", C.c_double),
         ("inv_lengthscale", C.c_double),
         ("mean_const", C.c_double),
+        ("ard", C.c_void_p),  # const double*: D per-dimension multipliers (ARDTransform) or NULL
     ]
 
 

@@ -29,7 +29,7 @@ from . import _lib
 from ._lib import GpDesc, PosDefException, as_f64, ptr
 
 __all__ = [
-    "SEKernel", "SqExponentialKernel", "Matern32Kernel", "Matern52Kernel", "ScaleTransform", "with_lengthscale",
+    "SEKernel", "SqExponentialKernel", "Matern32Kernel", "Matern52Kernel", "ScaleTransform", "ARDTransform", "with_lengthscale",
     "GP", "MOInputIsotopicByOutputs", "MOInputIsotopicByFeatures", "ColVecs", "RowVecs",
     "ILMM", "OILMM", "Orthogonal", "IndependentMOGP", "independent_mogp", "get_latent_gp",
     "FiniteGP", "Normal", "logpdf", "posterior", "mean_and_var", "mean", "var", "marginals", "rand", "cov", "mean_and_cov",
@@ -143,16 +143,24 @@ class Kernel:
     kind: int
     variance: float = 1.0
     inv_lengthscale: float = 1.0
+    ard: Optional[tuple] = None  # ARDTransform multipliers (one per input dimension)
 
     def __rmul__(self, s):  # `0.5 * SEKernel()` -> ScaledKernel
         if not (isinstance(s, (int, float)) and s > 0):
             raise TypeError("kernel scale must be a positive real")
-        return Kernel(self.kind, self.variance * float(s), self.inv_lengthscale)
+        return Kernel(self.kind, self.variance * float(s), self.inv_lengthscale, self.ard)
 
     __mul__ = __rmul__
 
-    def compose(self, t: "ScaleTransform") -> "Kernel":  # `k ∘ ScaleTransform(s)`
-        return Kernel(self.kind, self.variance, self.inv_lengthscale * t.s)
+    def compose(self, t) -> "Kernel":  # `k ∘ ScaleTransform(s)` / `k ∘ ARDTransform(v)`: inputs are scaled before distances
+        if isinstance(t, ARDTransform):
+            v = tuple(float(a) for a in t.v)
+            if self.ard is not None:
+                if len(self.ard) != len(v):
+                    raise ValueError("ARDTransform dimensions do not match")
+                v = tuple(a * b for a, b in zip(self.ard, v))
+            return Kernel(self.kind, self.variance, self.inv_lengthscale, v)
+        return Kernel(self.kind, self.variance, self.inv_lengthscale * t.s, self.ard)
 
     __matmul__ = compose
 
@@ -160,6 +168,13 @@ class Kernel:
 @dataclass(frozen=True)
 class ScaleTransform:
     s: float
+
+
+class ARDTransform:
+    """KernelFunctions `ARDTransform(v)`: x -> v .* x (one positive multiplier per input dimension, D <= 8)."""
+
+    def __init__(self, v):
+        self.v = tuple(float(a) for a in np.asarray(v, dtype=np.float64).reshape(-1))
 
 
 def SEKernel() -> Kernel:
@@ -466,9 +481,16 @@ def unpack(fx: FiniteGP):
 
 def _descs(fs: Sequence[GP]):
     arr = (GpDesc * len(fs))()
+    keep = []  # the ARD arrays must outlive the call; they ride on the ctypes array
     for i, f in enumerate(fs):
         g = f.prior if isinstance(f, PosteriorGP) else f
-        arr[i] = GpDesc(g.kernel.kind, 0, g.kernel.variance, g.kernel.inv_lengthscale, g.mean_const)
+        ard = None
+        if g.kernel.ard is not None:
+            a = np.ascontiguousarray(g.kernel.ard, dtype=np.float64)
+            keep.append(a)
+            ard = a.ctypes.data
+        arr[i] = GpDesc(g.kernel.kind, 0, g.kernel.variance, g.kernel.inv_lengthscale, g.mean_const, ard)
+    arr._keep = keep
     return arr
 
 

@@ -53,27 +53,36 @@ void shard_range(const lmm_ctx* ctx, int m, int& lo, int& hi) {
   hi = (int)(((int64_t)m * (ctx->rank + 1)) / ctx->nranks);
 }
 
-int check_descs(lmm_ctx* ctx, const lmm_gp_desc* d, int m) {
+int check_descs(lmm_ctx* ctx, const lmm_gp_desc* d, int m, int D) {
   for (int i = 0; i < m; ++i) {
     if (d[i].kind < 0 || d[i].kind > 2) return ctx->fail(LMM_E_UNSUPPORTED, "unsupported kernel kind (only SE, Matern32, Matern52)");
     if (!(d[i].variance > 0.0) || !(d[i].inv_lengthscale > 0.0)) return ctx->fail(LMM_E_ARG, "kernel variance and inv_lengthscale must be positive");
+    if (d[i].ard) {
+      if (D > LMM_MAX_ARD) return ctx->fail(LMM_E_UNSUPPORTED, "ARDTransform is supported for input dimension D <= 8");
+      for (int k = 0; k < D; ++k)
+        if (!(d[i].ard[k] > 0.0)) return ctx->fail(LMM_E_ARG, "ARD multipliers must be positive");
+    }
   }
   return LMM_OK;
 }
 
 size_t factor_bytes_per_latent(int nt) { return (sym_tiles(nt) + (size_t)nt) * TT * sizeof(double); }
 
-void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const double* noise, int lo, int hi, double ls_scale) {
+// Device-side description of one latent (noise = what is added on the diagonal of its kernel matrix).
+void set_params(LatentParams& q, const lmm_gp_desc& d, double noise, double ls_scale, int D) {
+  q.kind = d.kind;
+  q.ard_dim = d.ard ? D : 0;
+  q.variance = d.variance;
+  q.inv_ls = d.inv_lengthscale * ls_scale;
+  q.noise = noise;
+  q.mean = d.mean_const;
+  static_assert(MAX_ARD == LMM_MAX_ARD, "device and ABI limits must agree");
+  for (int k = 0; k < MAX_ARD; ++k) q.ard[k] = (d.ard && k < D) ? d.ard[k] : 1.0;
+}
+
+void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const double* noise, int lo, int hi, int D, double ls_scale) {
   hp.resize(hi - lo);
-  for (int i = lo; i < hi; ++i) {
-    LatentParams& q = hp[i - lo];
-    q.kind = d[i].kind;
-    q.pad = 0;
-    q.variance = d[i].variance;
-    q.inv_ls = d[i].inv_lengthscale * ls_scale;
-    q.noise = noise[i];
-    q.mean = d[i].mean_const;
-  }
+  for (int i = lo; i < hi; ++i) set_params(hp[i - lo], d[i], noise[i], ls_scale, D);
 }
 
 }  // namespace lmm_host

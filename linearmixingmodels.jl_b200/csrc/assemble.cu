@@ -15,8 +15,9 @@ __device__ __forceinline__ double kernel_pair(const LatentParams& lp, const doub
   double a[64], b[64];
   double sa = 0.0, sb = 0.0;
   for (int k = 0; k < D; ++k) {
-    a[k] = xa[k] * lp.inv_ls;
-    b[k] = xb[k] * lp.inv_ls;
+    const double s = input_scale(&lp, k);
+    a[k] = xa[k] * s;
+    b[k] = xb[k] * s;
     sa = fma(a[k], a[k], sa);
     sb = fma(b[k], b[k], sb);
   }

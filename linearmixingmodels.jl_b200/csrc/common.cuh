@@ -52,14 +52,19 @@ struct TiledRect {
 };
 
 // Per-latent kernel parameters on the device.
+constexpr int MAX_ARD = 8;  // == LMM_MAX_ARD of include/lmm.h
 struct LatentParams {
   int kind;
-  int pad;
+  int ard_dim;  // 0: isotropic ScaleTransform only; D (<= MAX_ARD): inputs are also multiplied by ard[0..D) (ARDTransform)
   double variance;
   double inv_ls;
   double noise;  // added on the diagonal (ΣT_i for OILMM, σ² for IndependentMOGP)
   double mean;
+  double ard[MAX_ARD];
 };
+// Multiplier of input dimension k: KernelFunctions `k ∘ ScaleTransform(s)` / `k ∘ ARDTransform(v)` scale the inputs
+// BEFORE pairwise distances are taken.  p points at global memory (no dynamically indexed register copy).
+__device__ __forceinline__ double input_scale(const LatentParams* p, int k) { return p->ard_dim ? p->inv_ls * p->ard[k] : p->inv_ls; }
 
 // exp(x) for x <= 0, <= 1 ulp (checked against expl on 2e7 points, tools/microbench/exp_check.c): Cody-Waite
 // reduction x = n ln2 + r with the round-to-nearest shift trick, degree-11 near-minimax polynomial on |r| <= ln2/2

@@ -54,8 +54,9 @@ __global__ void __launch_bounds__(256) kgrad_kernel(TiledSym negCinv, const doub
   const LatentParams lp = params[b];
   const double rinv_ls = 1.0 / lp.inv_ls;
   for (int i = t; i < TILE * D; i += 256) {
-    xa[i] = xpad[(size_t)I * TILE * D + i] * lp.inv_ls;
-    xb[i] = xpad[(size_t)J * TILE * D + i] * lp.inv_ls;
+    const double s = input_scale(params + b, i % D);
+    xa[i] = xpad[(size_t)I * TILE * D + i] * s;
+    xb[i] = xpad[(size_t)J * TILE * D + i] * s;
   }
   if (t < TILE) {
     aa[t] = alpha[(size_t)b * alpha_stride + I * TILE + t];
@@ -197,8 +198,9 @@ __global__ void __launch_bounds__(256) kgrad_block_kernel(TiledSym negCinv, cons
   const double rinv_ls = 1.0 / lp.inv_ls;
   for (int i = t; i < TILE * D; i += 256) {
     const int ra = I * TILE + i / D, rb = J * TILE + i / D;
-    xa[i] = ra < N ? x[(size_t)ra * D + i % D] * lp.inv_ls : 0.0;
-    xb[i] = rb < N ? x[(size_t)rb * D + i % D] * lp.inv_ls : 0.0;
+    const double s = input_scale(params + a, i % D);
+    xa[i] = ra < N ? x[(size_t)ra * D + i % D] * s : 0.0;
+    xb[i] = rb < N ? x[(size_t)rb * D + i % D] * s : 0.0;
   }
   if (t < TILE) {
     aa[t] = (I * TILE + t < N) ? alpha[(size_t)a * N + I * TILE + t] : 0.0;

@@ -625,7 +625,7 @@ extern "C" int lmm_potrf_bench(lmm_ctx* ctx, const lmm_gp_desc* desc, const doub
   if (!ctx) return LMM_E_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!desc || !x || N <= 0 || D <= 0 || batch <= 0) return ctx->fail(LMM_E_ARG, "null pointer or non-positive size");
-  int rc = check_descs(ctx, desc, 1);
+  int rc = check_descs(ctx, desc, 1, D);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -638,8 +638,7 @@ extern "C" int lmm_potrf_bench(lmm_ctx* ctx, const lmm_gp_desc* desc, const doub
   CU(copy_in(ctx, b_x.as<double>(), x, (size_t)N * D));
   std::vector<LatentParams> hp(batch);
   for (int b = 0; b < batch; ++b) {
-    hp[b].kind = desc->kind; hp[b].pad = 0; hp[b].variance = desc->variance; hp[b].inv_ls = desc->inv_lengthscale;
-    hp[b].noise = noise; hp[b].mean = desc->mean_const;
+    set_params(hp[b], *desc, noise, 1.0, D);
   }
   CU(b_params.alloc(ctx, hp.size() * sizeof(LatentParams)));
   CU(cudaMemcpyAsync(b_params.p, hp.data(), hp.size() * sizeof(LatentParams), cudaMemcpyHostToDevice, st));

@@ -109,7 +109,7 @@ extern "C" int lmm_post_condition(lmm_post* post, const double* xs, int Ns, doub
   }
   lmm_post* P = new lmm_post();
   P->ctx = ctx; P->kind = post->kind; P->m = m; P->p = p; P->N = N2; P->D = D; P->nt = nt2; P->lo = lo; P->hi = post->hi;
-  P->descs = post->descs; P->noise = post->noise; P->H = post->H; P->U = post->U; P->S = post->S; P->sigma2 = sigma2;
+  P->adopt_descs(post->descs.data(), m, D); P->noise = post->noise; P->H = post->H; P->U = post->U; P->S = post->S; P->sigma2 = sigma2;
   P->bytes = (size_t)nloc * (factor_bytes_per_latent(nt2) + 3 * npad2 * sizeof(double)) + npad2 * D * sizeof(double);
   P->d_xpad = (double*)b_x.detach();
   P->d_L = (double*)b_L.detach();
@@ -176,7 +176,7 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
   for (int i = lo; i < hi; ++i) hmeans[i - lo] = latents[i].mean_const;
   CU(b_means.alloc(ctx, (size_t)nl * sizeof(double)));
   CU(copy_in(ctx, b_means.as<double>(), hmeans.data(), (size_t)nl));
-  if ((rc = upload_params(ctx, b_params, latents, pr.noise.data(), lo, hi))) return rc;
+  if ((rc = upload_params(ctx, b_params, latents, pr.noise.data(), lo, hi, D))) return rc;
   CU(b_ty.alloc(ctx, (size_t)nl * npad * sizeof(double)));
   CU(cudaMemsetAsync(b_ty.p, 0, (size_t)nl * npad * sizeof(double), st));
   const int nblk = (N + 15) / 16;
@@ -433,7 +433,7 @@ extern "C" int lmm_imogp_cross_cov(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, c
   if (!ctx) return LMM_E_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!fs || !xa || !xb || !out || m <= 0 || Na <= 0 || Nb <= 0 || D <= 0 || D > 64) return ctx->fail(LMM_E_ARG, "bad argument");
-  int rc = check_descs(ctx, fs, m);
+  int rc = check_descs(ctx, fs, m, D);
   if (rc) return rc;
   if ((int64_t)m * Na > 46000 || (int64_t)m * Nb > 46000) return ctx->fail(LMM_E_UNSUPPORTED, "dense covariance output too large");
   CU(cudaSetDevice(ctx->device));
@@ -442,7 +442,7 @@ extern "C" int lmm_imogp_cross_cov(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, c
   if ((rc = stage_xpad(ctx, b_xa, xa, Na, D))) return rc;
   if ((rc = stage_xpad(ctx, b_xb, xb, Nb, D))) return rc;
   std::vector<double> noise(m, 0.0);
-  if ((rc = upload_params(ctx, b_params, fs, noise.data(), 0, m))) return rc;
+  if ((rc = upload_params(ctx, b_params, fs, noise.data(), 0, m, D))) return rc;
   const int nta = ntiles(Na), ntb = ntiles(Nb);
   CU(b_V.alloc(ctx, (size_t)m * nta * ntb * TT * sizeof(double)));
   TiledRect V{b_V.as<double>(), nta, ntb, (size_t)nta * ntb * TT};
@@ -495,7 +495,7 @@ extern "C" int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, in
     d_y = b_y.as<double>();
   }
   std::vector<double> noise0(m, 0.0);
-  if ((rc = upload_params(ctx, b_params, latents, noise0.data(), 0, m))) return rc;
+  if ((rc = upload_params(ctx, b_params, latents, noise0.data(), 0, m, D))) return rc;
   std::vector<double> Hh(H, H + (size_t)p * m), Ht((size_t)m * p), Tt((size_t)p * m);
   for (int a = 0; a < m; ++a)
     for (int j = 0; j < p; ++j) {

@@ -226,7 +226,7 @@ lmm_post* joint_make_post(lmm_ctx* ctx, JointBuild& J, int kind, const lmm_gp_de
                           DevBuf& Ept) {
   lmm_post* P = new lmm_post();
   P->ctx = ctx; P->kind = kind; P->m = J.m; P->p = p; P->N = J.N; P->D = J.D; P->nt = ntiles(J.N); P->lo = 0; P->hi = J.m;
-  P->descs.assign(latents, latents + J.m);
+  P->adopt_descs(latents, J.m, J.D);
   P->noise.assign(J.m, 0.0);
   P->H.assign(Hhost, Hhost + (size_t)p * J.m);
   P->sigma2 = sigma2;
@@ -272,7 +272,7 @@ int ilmm_run(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, i
     d_y = b_y.as<double>();
   }
   std::vector<double> noise0(m, 0.0);
-  if ((rc = upload_params(ctx, J.params, latents, noise0.data(), 0, m))) return rc;
+  if ((rc = upload_params(ctx, J.params, latents, noise0.data(), 0, m, D))) return rc;
   CU(J.H.alloc(ctx, (size_t)p * m * sizeof(double)));
   CU(copy_in(ctx, J.H.as<double>(), H, (size_t)p * m));
   CU(J.delta.alloc(ctx, J.bpad * sizeof(double)));
@@ -465,7 +465,7 @@ extern "C" int lmm_prior_mean_and_cov(lmm_ctx* ctx, const lmm_gp_desc* latents, 
   DevBuf b_xs, b_params, b_C, b_H, b_cov, b_mean;
   if ((rc = stage_xpad(ctx, b_xs, xs, Ns, D))) return rc;
   std::vector<double> noise(m, latent_jitter);
-  if ((rc = upload_params(ctx, b_params, latents, noise.data(), lo, hi))) return rc;
+  if ((rc = upload_params(ctx, b_params, latents, noise.data(), lo, hi, D))) return rc;
   CU(b_C.alloc(ctx, (size_t)(nloc > 0 ? nloc : 1) * sym_tiles(nts) * TT * sizeof(double)));
   TiledSym C{b_C.as<double>(), nts, sym_tiles(nts) * TT};
   if (nloc > 0) {

@@ -154,7 +154,8 @@ struct lmm_post {
   int kind = POST_OILMM;
   int m = 0, p = 0, N = 0, D = 1, nt = 0;
   int lo = 0, hi = 0;  // resident latents [lo, hi)
-  std::vector<lmm_gp_desc> descs;
+  std::vector<lmm_gp_desc> descs;  // descs[i].ard points into ard_store (or is NULL)
+  std::vector<double> ard_store;   // m x D copies of the callers' ARD vectors
   std::vector<double> noise;  // per latent (all m)
   std::vector<double> H;      // p x m column-major (U sqrt(S) for OILMM)
   std::vector<double> U, S;
@@ -172,6 +173,16 @@ struct lmm_post {
   size_t bytes = 0;
   int big_n = 0, big_nt = 0;  // ILMM joint dimension mN and its tile count
 
+  // deep copy of the latent descriptions (the caller's ARD arrays are only valid during its call)
+  void adopt_descs(const lmm_gp_desc* d, int m_, int D_) {
+    descs.assign(d, d + m_);
+    ard_store.assign((size_t)m_ * D_, 0.0);
+    for (int i = 0; i < m_; ++i)
+      if (d[i].ard) {
+        for (int k = 0; k < D_; ++k) ard_store[(size_t)i * D_ + k] = d[i].ard[k];
+        descs[i].ard = ard_store.data() + (size_t)i * D_;
+      }
+  }
   int nloc() const { return hi - lo; }
   size_t npad() const { return (size_t)nt * TILE; }
   bool joint() const { return kind == POST_ILMM || kind == POST_JOINT; }
@@ -228,14 +239,15 @@ bool is_device_ptr(const void* p);
 cudaError_t copy_in(lmm_ctx* ctx, double* dst, const double* src, size_t n);
 cudaError_t copy_out(lmm_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 void shard_range(const lmm_ctx* ctx, int m, int& lo, int& hi);
-int check_descs(lmm_ctx* ctx, const lmm_gp_desc* d, int m);
+int check_descs(lmm_ctx* ctx, const lmm_gp_desc* d, int m, int D);
+void set_params(LatentParams& q, const lmm_gp_desc& d, double noise, double ls_scale, int D);
 size_t factor_bytes_per_latent(int nt);
-void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const double* noise, int lo, int hi, double ls_scale = 1.0);
+void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const double* noise, int lo, int hi, int D, double ls_scale = 1.0);
 int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const double* x, int N, int D, int p, double sigma2, const double* y, const Projection& pr, const double* Hhost, const double* Uhost, const double* Shost, RunOut out, const double* noise_vec = nullptr);
 int oilmm_projection(lmm_ctx* ctx, const double* U, const double* S, int p, int m, double sigma2, int N, Projection& pr, std::vector<double>& H);
 int check_common(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const void* x, int N, int D, int p, int out_dim);
 int post_latent_marginals(lmm_post* post, const double* d_xspad, int Ns, int nts, double* d_ML, double* d_VL);
-int upload_params(lmm_ctx* ctx, DevBuf& buf, const lmm_gp_desc* descs, const double* noise_all, int lo, int hi);
+int upload_params(lmm_ctx* ctx, DevBuf& buf, const lmm_gp_desc* descs, const double* noise_all, int lo, int hi, int D);
 int stage_latent_vectors(lmm_ctx* ctx, DevBuf& buf, const double* z, int N, size_t npad, int lo, int hi);
 int report_info(lmm_ctx* ctx, const std::vector<int>& hinfo, int lo, int nmax, int* info_latent);
 int prior_latent_samples(lmm_ctx* ctx, const lmm_gp_desc* descs, const double* noise_all, int lo, int hi, const double* d_xpad, int N, int D, const double* d_z, double* d_X, int* info_latent);

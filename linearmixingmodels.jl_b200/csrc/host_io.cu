@@ -10,7 +10,7 @@
 // ------------------------------------------------------------------------------------------------
 namespace lmm_host {
 struct PostFileHeader {
-  char magic[8];  // "LMMPOST1"
+  char magic[8];  // "LMMPOST2"
   int32_t kind, m, p, N, D, nt, lo, hi, big_n, big_nt, has_U, has_noise_vec, has_Ept, reserved;
   double sigma2;
   uint64_t n_x, n_L, n_W, n_alpha, n_delta, n_params, n_H, n_noise_vec, n_Ept;  // element counts (doubles; params: structs)
@@ -67,7 +67,7 @@ extern "C" int lmm_post_save(lmm_post* post, const char* path) {
   FILE* f = fopen(path, "wb");
   if (!f) return ctx->fail(LMM_E_ARG, std::string("cannot open ") + path + " for writing");
   PostFileHeader h{};
-  memcpy(h.magic, "LMMPOST1", 8);
+  memcpy(h.magic, "LMMPOST2", 8);
   h.kind = post->kind; h.m = post->m; h.p = post->p; h.N = post->N; h.D = post->D; h.nt = post->nt; h.lo = post->lo; h.hi = post->hi;
   h.big_n = post->big_n; h.big_nt = post->big_nt; h.has_U = post->U.empty() ? 0 : 1;
   h.has_noise_vec = post->d_noise_vec ? 1 : 0; h.has_Ept = post->d_Ept ? 1 : 0;
@@ -77,6 +77,9 @@ extern "C" int lmm_post_save(lmm_post* post, const char* path) {
   bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(post->descs.data(), sizeof(lmm_gp_desc), post->m, f) == (size_t)post->m &&
             fwrite(post->noise.data(), sizeof(double), post->m, f) == (size_t)post->m &&
             fwrite(post->H.data(), sizeof(double), post->H.size(), f) == post->H.size();
+  // the descriptions hold host pointers (ARD vectors): the file carries the vectors and re-points on load (a non-null
+  // pointer in the raw desc only marks "this latent has one")
+  if (ok) ok = fwrite(post->ard_store.data(), sizeof(double), post->ard_store.size(), f) == post->ard_store.size();
   if (ok && h.has_U)
     ok = fwrite(post->U.data(), sizeof(double), post->U.size(), f) == post->U.size() &&
          fwrite(post->S.data(), sizeof(double), post->S.size(), f) == post->S.size();
@@ -103,7 +106,7 @@ extern "C" int lmm_post_load(lmm_ctx* ctx, const char* path, lmm_post** out_post
     fclose(f);
     return ctx->fail(LMM_E_ARG, msg);
   };
-  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "LMMPOST1", 8) != 0) return bail("not a liblmm posterior file");
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "LMMPOST2", 8) != 0) return bail("not a liblmm posterior file");
   if (h.kind < POST_OILMM || h.kind > POST_JOINT || h.m <= 0 || h.p <= 0 || h.N <= 0 || h.D <= 0 || h.lo < 0 || h.hi < h.lo || h.hi > h.m)
     return bail("corrupt posterior header");
   lmm_post* P = new lmm_post();
@@ -112,6 +115,12 @@ extern "C" int lmm_post_load(lmm_ctx* ctx, const char* path, lmm_post** out_post
   P->descs.resize(h.m); P->noise.resize(h.m); P->H.resize((size_t)h.p * h.m);
   bool ok = fread(P->descs.data(), sizeof(lmm_gp_desc), h.m, f) == (size_t)h.m && fread(P->noise.data(), sizeof(double), h.m, f) == (size_t)h.m &&
             fread(P->H.data(), sizeof(double), P->H.size(), f) == P->H.size();
+  if (ok) {
+    P->ard_store.resize((size_t)h.m * h.D);
+    ok = fread(P->ard_store.data(), sizeof(double), P->ard_store.size(), f) == P->ard_store.size();
+    for (int i = 0; ok && i < h.m; ++i)
+      if (P->descs[i].ard) P->descs[i].ard = P->ard_store.data() + (size_t)i * h.D;
+  }
   if (ok && h.has_U) {
     P->U.resize((size_t)h.p * h.m); P->S.resize(h.m);
     ok = fread(P->U.data(), sizeof(double), P->U.size(), f) == P->U.size() && fread(P->S.data(), sizeof(double), P->S.size(), f) == P->S.size();

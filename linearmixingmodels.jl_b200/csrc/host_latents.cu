@@ -49,7 +49,7 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
   CU(b_means.alloc(ctx, hmeans.size() * sizeof(double)));
   CU(copy_in(ctx, b_means.as<double>(), hmeans.data(), hmeans.size()));
   std::vector<LatentParams> hparams;
-  fill_params(hparams, latents, pr.noise.data(), lo, hi);
+  fill_params(hparams, latents, pr.noise.data(), lo, hi, D);
   DevBuf b_params;
   CU(b_params.alloc(ctx, (hparams.size() + 1) * sizeof(LatentParams)));
   if (mloc > 0) {
@@ -193,7 +193,7 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
     CU(cudaStreamSynchronize(st));
     lmm_post* P = new lmm_post();  // nothing below can fail: ownership of the device buffers moves to P
     P->ctx = ctx; P->kind = kind; P->m = m; P->p = p; P->N = N; P->D = D; P->nt = nt; P->lo = lo; P->hi = hi;
-    P->descs.assign(latents, latents + m);
+    P->adopt_descs(latents, m, D);
     P->noise = pr.noise;
     P->H.assign(Hhost, Hhost + (size_t)p * m);
     if (Uhost) P->U.assign(Uhost, Uhost + (size_t)p * m);
@@ -245,7 +245,7 @@ int check_common(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const void* x,
   if (!latents || !x || m <= 0 || N <= 0 || D <= 0 || p <= 0) return ctx->fail(LMM_E_ARG, "null pointer or non-positive size");
   if (D > 64) return ctx->fail(LMM_E_UNSUPPORTED, "input dimension D > 64 is not supported");
   if (out_dim != p) return ctx->fail(LMM_E_OUT_DIM, "out dim of x != out dim of f.");
-  return check_descs(ctx, latents, m);
+  return check_descs(ctx, latents, m, D);
 }
 
 }  // namespace lmm_host

@@ -5,9 +5,9 @@
 namespace lmm_host {
 
 // Upload LatentParams for latents [lo, hi) of `descs` with per-latent noise values.
-int upload_params(lmm_ctx* ctx, DevBuf& buf, const lmm_gp_desc* descs, const double* noise_all, int lo, int hi) {
+int upload_params(lmm_ctx* ctx, DevBuf& buf, const lmm_gp_desc* descs, const double* noise_all, int lo, int hi, int D) {
   std::vector<LatentParams> hp;
-  fill_params(hp, descs, noise_all, lo, hi);
+  fill_params(hp, descs, noise_all, lo, hi, D);
   CU(buf.alloc(ctx, (hp.size() + 1) * sizeof(LatentParams)));
   if (!hp.empty()) {
     ctx->h2d += (int64_t)(hp.size() * sizeof(LatentParams));
@@ -55,7 +55,7 @@ int prior_latent_samples(lmm_ctx* ctx, const lmm_gp_desc* descs, const double* n
   const size_t npad = (size_t)nt * TILE;
   if (nloc == 0) return LMM_OK;
   DevBuf b_params, b_L, b_W, b_logdet, b_info;
-  int rc = upload_params(ctx, b_params, descs, noise_all, lo, hi);
+  int rc = upload_params(ctx, b_params, descs, noise_all, lo, hi, D);
   if (rc) return rc;
   size_t fr = 0, tot = 0;
   CU(cudaMemGetInfo(&fr, &tot));
@@ -216,7 +216,7 @@ int build_predictive(lmm_post* post, const double* xs, int Ns, const std::vector
   P.nspad = (size_t)P.nts * TILE;
   int rc = stage_xpad(ctx, P.xs, xs, Ns, post->D);
   if (rc) return rc;
-  if ((rc = upload_params(ctx, P.params, post->descs.data(), noise_all.data(), post->lo, post->hi))) return rc;
+  if ((rc = upload_params(ctx, P.params, post->descs.data(), noise_all.data(), post->lo, post->hi, post->D))) return rc;
   const int nl = nloc > 0 ? nloc : 1;
   CU(P.ML.alloc(ctx, (size_t)nl * P.nspad * sizeof(double)));
   CU(P.C.alloc(ctx, (size_t)nl * sym_tiles(P.nts) * TT * sizeof(double)));
@@ -569,9 +569,7 @@ extern "C" int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, 
     for (int u = ulo; u < uhi; ++u) {
       const int s = u / m, i = u % m;
       LatentParams& q = hp[u - ulo];
-      q.kind = latents[i].kind; q.pad = 0; q.variance = latents[i].variance;
-      q.inv_ls = latents[i].inv_lengthscale * inv_lengthscale_scales[s];
-      q.noise = pr.noise[i]; q.mean = latents[i].mean_const;
+      set_params(q, latents[i], pr.noise[i], inv_lengthscale_scales[s], D);
       hidx[u - ulo] = i;
     }
     CU(b_params.alloc(ctx, (size_t)nu * sizeof(LatentParams)));

@@ -34,10 +34,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Stage the two point tiles (rows of xpad, D doubles per point) and scale them by inv_ls.
+// Stage the two point tiles (rows of xpad, D doubles per point) and scale them (ScaleTransform / ARDTransform).
 // smem layout: xa[128*D] | xb[128*D] | sa[128] | sb[128]
 __device__ __forceinline__ void stage_points(double* xa, double* xb, double* sa, double* sb, const double* ga, const double* gb,
-                                             int D, double inv_ls, uint64_t* bar) {
+                                             int D, const LatentParams* gp, uint64_t* bar) {
   const uint32_t bytes = (uint32_t)(TILE * D * sizeof(double));
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
@@ -50,8 +50,9 @@ __device__ __forceinline__ void stage_points(double* xa, double* xb, double* sa,
   }
   mbar_wait(bar, 0);
   for (int i = threadIdx.x; i < TILE * D; i += blockDim.x) {
-    xa[i] *= inv_ls;
-    xb[i] *= inv_ls;
+    const double s = input_scale(gp, i % D);
+    xa[i] *= s;
+    xb[i] *= s;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * TILE; i += blockDim.x) {
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const doubl
   const int J = t - (int)((size_t)I * (I + 1) / 2);
   const LatentParams lp = params[b];
 
-  stage_points(xa, xb, sa, sb, xpad + (size_t)I * TILE * D, xpad + (size_t)J * TILE * D, D, lp.inv_ls, &bar);
+  stage_points(xa, xb, sa, sb, xpad + (size_t)I * TILE * D, xpad + (size_t)J * TILE * D, D, params + b, &bar);
   kmat_tile_body<true, DS>(out.tile(b, I, J), xa, xb, sa, sb, D, I * TILE, J * TILE, N, N, lp, form,
                            noise_vec ? noise_vec + (size_t)b * noise_stride : nullptr);
 }
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256) kmat_cross_kernel(TiledRect out, const do
   const int b = blockIdx.y;
   const int R = blockIdx.x / out.ntc, J = blockIdx.x % out.ntc;
   const LatentParams lp = params[b];
-  stage_points(xa, xb, sa, sb, xa_pad + (size_t)R * TILE * D, xb_pad + (size_t)J * TILE * D, D, lp.inv_ls, &bar);
+  stage_points(xa, xb, sa, sb, xa_pad + (size_t)R * TILE * D, xb_pad + (size_t)J * TILE * D, D, params + b, &bar);
   kmat_tile_body<false, DS>(out.tile(b, R, J), xa, xb, sa, sb, D, R * TILE, J * TILE, Na, Nb, lp, form);
 }
 

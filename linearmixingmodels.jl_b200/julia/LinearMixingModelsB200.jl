@@ -21,6 +21,7 @@ struct GpDesc            # lmm_gp_desc
     variance::Float64
     inv_lengthscale::Float64
     mean_const::Float64
+    ard::Ptr{Float64}    # ARDTransform multipliers (D values, kept alive by the caller with GC.@preserve) or C_NULL
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
@@ -60,7 +61,7 @@ meanconst(::AbstractGPs.ZeroMean) = 0.0
 meanconst(m::AbstractGPs.ConstMean) = Float64(m.c)
 function GpDesc(f::GP)
     k, v, s = describe(f.kernel)
-    return GpDesc(k, 0, v, s, meanconst(f.mean))
+    return GpDesc(k, 0, v, s, meanconst(f.mean), C_NULL)   # `k ∘ ARDTransform(v)`: pass pointer(v) under GC.@preserve
 end
 
 points(x::AbstractVector{<:Real}) = (collect(Float64, x), 1)

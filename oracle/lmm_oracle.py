@@ -51,6 +51,7 @@ class Kernel:
     kind: int = SE
     variance: float = 1.0
     inv_lengthscale: float = 1.0
+    ard: Optional[tuple] = None  # KernelFunctions ``ARDTransform(v)``: x -> v .* x, composed with the ScaleTransform
 
 
 @dataclass(frozen=True)
@@ -116,8 +117,9 @@ def kappa(kind: int, d2: np.ndarray) -> np.ndarray:
 
 def kernelmatrix(k: Kernel, x: np.ndarray, x2: Optional[np.ndarray] = None, *, form: str = "gemm") -> np.ndarray:
     """``kernelmatrix(k, x[, x2])`` = ``variance * map(κ, pairwise(metric, s*x, s*x2))``."""
-    xs = _as2d(x) * k.inv_lengthscale
-    x2s = None if x2 is None else _as2d(x2) * k.inv_lengthscale
+    sc = k.inv_lengthscale if k.ard is None else k.inv_lengthscale * np.asarray(k.ard, dtype=np.float64)[None, :]
+    xs = _as2d(x) * sc
+    x2s = None if x2 is None else _as2d(x2) * sc
     return k.variance * kappa(k.kind, pairwise_sqdist(xs, x2s, form=form))
 
 
@@ -644,7 +646,8 @@ def dense_mogp_posterior_mean_and_var(fs, H, x, sigma2, y, xs, sigma2_pred) -> T
 # --------------------------------------------------------------------------------------------
 def _dkernel_ds(k: Kernel, x) -> np.ndarray:
     """d/d(inv_lengthscale) of kernelmatrix(k, x) (direct-difference distances; analytic)."""
-    xs = _as2d(x) * k.inv_lengthscale
+    sc = k.inv_lengthscale if k.ard is None else k.inv_lengthscale * np.asarray(k.ard, dtype=np.float64)[None, :]
+    xs = _as2d(x) * sc
     d2 = pairwise_sqdist(xs, form="direct")
     s = k.inv_lengthscale
     if k.kind == SE:

@@ -34,8 +34,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert C.sizeof(_lib.GpDesc) == 32
-    assert _lib.GpDesc.variance.offset == 8 and _lib.GpDesc.mean_const.offset == 24
+    assert C.sizeof(_lib.GpDesc) == 40
+    assert _lib.GpDesc.variance.offset == 8 and _lib.GpDesc.mean_const.offset == 24 and _lib.GpDesc.ard.offset == 32
 
 
 def test_version_and_host_only_entry_points():

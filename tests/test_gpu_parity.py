@@ -28,6 +28,8 @@ def to_lmm_gp(lmm, g: o.GP):
     k = g.kernel.variance * k if g.kernel.variance != 1.0 else k
     if g.kernel.inv_lengthscale != 1.0:
         k = k.compose(lmm.ScaleTransform(g.kernel.inv_lengthscale))
+    if g.kernel.ard is not None:
+        k = k.compose(lmm.ARDTransform(g.kernel.ard))
     return lmm.GP(g.mean_const, k)
 
 
@@ -671,6 +673,71 @@ def test_posterior_save_load_round_trip(lmm, tmp_path):
         fh.write(b"not a posterior")
     with pytest.raises(Exception):
         lmm.load_posterior(str(tmp_path / "bad.lmm"), lat)
+
+
+def test_ard_transform(lmm, tmp_path):
+    """`k ∘ ARDTransform(v)` (KernelFunctions: x -> v .* x before distances) on D = 3 inputs through every
+    kernel-evaluating path: OILMM logpdf / posterior / marginals / gradient, general ILMM (joint assembly + cross covariance),
+    sequential conditioning and a save / load round trip (the handle keeps its own copy of the ARD vectors)."""
+    N, Ns, p, m, D = 300, 37, 5, 3, 3
+    rng = np.random.default_rng(17)
+    x, xs = rng.uniform(0, 3, (N, D)), rng.uniform(0, 3, (Ns, D))
+    U, S = o.orthogonal_from_seed(p, m, seed=3)
+    fs = [o.GP(o.Kernel(o.SE, 0.9, 1.2, (0.5, 1.5, 1.0)), 0.3), o.GP(o.Kernel(o.MATERN32, 1.3, 0.8, (1.2, 0.7, 2.0)), -0.2),
+          o.GP(o.Kernel(o.MATERN52, 0.7, 1.1))]  # the third latent has no ARD
+    y, ys = rng.standard_normal(p * N), rng.standard_normal(p * Ns)
+    O = lmm.MOInputIsotopicByOutputs
+    lat = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lat, lmm.Orthogonal(U, S))
+    fx = f(O(lmm.RowVecs(x), p), 0.1)
+    post, lp = lmm.posterior(fx, y, with_logpdf=True)
+    assert rel(lp, o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
+    opost = o.oilmm_posterior(om, x, 0.1, y)
+    M, V = lmm.mean_and_var(post(O(lmm.RowVecs(xs), p), 0.1))
+    Mr, Vr = o.oilmm_mean_and_var(opost, xs, 0.1)
+    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(V, Vr, rtol=RTOL)
+    lpg, g = lmm.logpdf_and_gradient(fx, y, with_grad_y=True)
+    lpr, gr = o.oilmm_logpdf_grad(om, x, 0.1, y)
+    for k in ("variance", "inv_lengthscale", "mean_const"):
+        np.testing.assert_allclose(g[k], gr[k], rtol=1e-7, atol=1e-8)
+    assert rel(g["sigma2"], gr["sigma2"]) < 1e-7
+    # save / load keeps the ARD vectors; the reloaded handle can be conditioned again
+    path = str(tmp_path / "ard.lmm")
+    lmm.save_posterior(post, path)
+    back = lmm.load_posterior(path, f)
+    M1, V1 = lmm.mean_and_var(back(O(lmm.RowVecs(xs), p), 0.1))
+    assert np.array_equal(M, M1) and np.array_equal(V, V1)
+    post2 = lmm.posterior(back(O(lmm.RowVecs(xs), p), 0.2), ys)
+    # compare with the textbook per-latent update of the first posterior
+    T, ST2 = o.project_orthogonal(U, S, 0.2)
+    xt = rng.uniform(0, 3, (9, D))
+    M2, V2 = lmm.mean_and_var(post2(O(lmm.RowVecs(xt), p), 0.1))
+    ML, VL = [], []
+    for i in range(m):
+        mr, vr = o.gp_condition_again_marginals(opost.fs[i], xs, ST2[i], (T @ ys.reshape(p, Ns))[i], xt)
+        ML.append(mr)
+        VL.append(vr + 1e-18)
+    H = om.H
+    np.testing.assert_allclose(M2, (H @ np.stack(ML)).reshape(-1), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(V2, ((H * H) @ np.stack(VL) + 0.1).reshape(-1), rtol=1e-8)
+    # general ILMM: joint assembly and block-diagonal cross covariance evaluate the same kernels
+    Hd = rng.uniform(0, 1, (p, m))
+    fi = lmm.ILMM(lat, Hd)(O(lmm.RowVecs(x), p), 0.1)
+    assert rel(lmm.logpdf(fi, y), o.ilmm_logpdf(fs, Hd, x, 0.1, y)) < RTOL
+    pi = lmm.posterior(fi, y)
+    Mi, Vi = lmm.mean_and_var(pi(O(lmm.RowVecs(xs), p), 0.1))
+    Mir, Vir = o.ilmm_mean_and_var(o.ilmm_posterior(fs, Hd, x, 0.1, y), Hd, xs, 0.1)
+    np.testing.assert_allclose(Mi, Mir, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(Vi, Vir, rtol=1e-8)
+    lpi, gi = lmm.logpdf_and_gradient(fi, y)
+    _, gir = o.ilmm_logpdf_grad(fs, Hd, x, 0.1, y)
+    np.testing.assert_allclose(gi["inv_lengthscale"], gir["inv_lengthscale"], rtol=1e-7, atol=1e-8)
+    # D > 8 with ARD is rejected loudly, never routed elsewhere
+    big = lmm.GP(lmm.SEKernel().compose(lmm.ARDTransform(np.ones(9))))
+    with pytest.raises(ValueError, match="ARDTransform"):
+        lmm.logpdf(lmm.independent_mogp([big])(O(lmm.RowVecs(rng.uniform(0, 1, (5, 9))), 1), 0.1), np.zeros(5))
 
 
 def test_imogp_process_cov_mixed_orderings(lmm):
