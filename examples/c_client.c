@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
   double n1 = sqrt(U[3] * U[3] + U[4] * U[4] + U[5] * U[5]);
   for (int j = 0; j < P; ++j) U[3 + j] /= n1;
   if (lmm_orthogonal_validate(U, P, M) != LMM_OK) { printf("U not orthogonal\n"); return 1; }
-  lmm_gp_desc lat[M] = {{LMM_KERNEL_SE, 0, 1.0, 1.0, 0.0, NULL}, {LMM_KERNEL_MATERN32, 0, 0.8, 1.3, 0.2, NULL}};
+  lmm_gp_desc lat[M] = {{LMM_KERNEL_SE, 0, 1.0, 1.0, 0.0, NULL, 0.0}, {LMM_KERNEL_MATERN32, 0, 0.8, 1.3, 0.2, NULL, 0.0}};
   const double sigma2 = 0.1;
   int il = -1, fails = 0;
 

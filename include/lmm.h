@@ -43,10 +43,13 @@ extern "C" {
 #define LMM_E_NOT_ORTHOGONAL (-6) /* "`U` is not an orthogonal matrix" src/orthogonal_matrix.jl:22 */
 #define LMM_E_OOM (-7)            /* device memory exhausted                                  */
 
-/* Base kernels (KernelFunctions.jl): SEKernel, Matern32Kernel, Matern52Kernel. */
+/* Base kernels (KernelFunctions.jl): SEKernel, Matern32Kernel, Matern52Kernel, ExponentialKernel (= Matern12Kernel,
+ * κ(d) = exp(-d)) and RationalQuadraticKernel(α) (κ(d²) = (1 + d²/(2α))^(-α), α in `param`). */
 #define LMM_KERNEL_SE 0
 #define LMM_KERNEL_MATERN32 1
 #define LMM_KERNEL_MATERN52 2
+#define LMM_KERNEL_EXPONENTIAL 3
+#define LMM_KERNEL_RATIONAL_QUADRATIC 4
 
 /* One latent `GP(mean_const, variance * (base_kernel ∘ ScaleTransform(inv_lengthscale) [∘ ARDTransform(ard)]))`.
  * Inputs are multiplied by inv_lengthscale (and, per dimension, by ard[k]) BEFORE distances are taken
@@ -60,6 +63,7 @@ typedef struct lmm_gp_desc {
   double mean_const;      /* ZeroMean -> 0.0; ConstMean(c) -> c             */
   const double* ard;      /* ARDTransform v: D positive per-dimension multipliers (D <= LMM_MAX_ARD), or NULL;
                              read during the call only (posterior handles keep their own copy)           */
+  double param;           /* shape parameter of the base kernel: α of RationalQuadraticKernel; else ignored */
 } lmm_gp_desc;
 
 typedef struct lmm_ctx lmm_ctx;   /* owns device, stream, memory pool, optional NCCL communicator */

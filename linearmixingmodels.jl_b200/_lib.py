@@ -36,6 +36,7 @@ class GpDesc(C.Structure):
         ("inv_lengthscale", C.c_double),
         ("mean_const", C.c_double),
         ("ard", C.c_void_p),  # const double*: D per-dimension multipliers (ARDTransform) or NULL
+        ("param", C.c_double),  # α of RationalQuadraticKernel
     ]
 
 

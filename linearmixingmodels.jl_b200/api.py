@@ -29,7 +29,7 @@ from . import _lib
 from ._lib import GpDesc, PosDefException, as_f64, ptr
 
 __all__ = [
-    "SEKernel", "SqExponentialKernel", "Matern32Kernel", "Matern52Kernel", "ScaleTransform", "ARDTransform", "with_lengthscale",
+    "SEKernel", "SqExponentialKernel", "Matern32Kernel", "Matern52Kernel", "ExponentialKernel", "Matern12Kernel", "RationalQuadraticKernel", "ScaleTransform", "ARDTransform", "with_lengthscale",
     "GP", "MOInputIsotopicByOutputs", "MOInputIsotopicByFeatures", "ColVecs", "RowVecs",
     "ILMM", "OILMM", "Orthogonal", "IndependentMOGP", "independent_mogp", "get_latent_gp",
     "FiniteGP", "Normal", "logpdf", "posterior", "mean_and_var", "mean", "var", "marginals", "rand", "cov", "mean_and_cov",
@@ -144,11 +144,12 @@ class Kernel:
     variance: float = 1.0
     inv_lengthscale: float = 1.0
     ard: Optional[tuple] = None  # ARDTransform multipliers (one per input dimension)
+    param: float = 1.0  # shape parameter of the base kernel (α of RationalQuadraticKernel)
 
     def __rmul__(self, s):  # `0.5 * SEKernel()` -> ScaledKernel
         if not (isinstance(s, (int, float)) and s > 0):
             raise TypeError("kernel scale must be a positive real")
-        return Kernel(self.kind, self.variance * float(s), self.inv_lengthscale, self.ard)
+        return Kernel(self.kind, self.variance * float(s), self.inv_lengthscale, self.ard, self.param)
 
     __mul__ = __rmul__
 
@@ -159,8 +160,8 @@ class Kernel:
                 if len(self.ard) != len(v):
                     raise ValueError("ARDTransform dimensions do not match")
                 v = tuple(a * b for a, b in zip(self.ard, v))
-            return Kernel(self.kind, self.variance, self.inv_lengthscale, v)
-        return Kernel(self.kind, self.variance, self.inv_lengthscale * t.s, self.ard)
+            return Kernel(self.kind, self.variance, self.inv_lengthscale, v, self.param)
+        return Kernel(self.kind, self.variance, self.inv_lengthscale * t.s, self.ard, self.param)
 
     __matmul__ = compose
 
@@ -190,6 +191,19 @@ def Matern32Kernel() -> Kernel:
 
 def Matern52Kernel() -> Kernel:
     return Kernel(2)
+
+
+def ExponentialKernel() -> Kernel:  # KernelFunctions: ExponentialKernel == Matern12Kernel, κ(d) = exp(-d)
+    return Kernel(3)
+
+
+Matern12Kernel = ExponentialKernel
+
+
+def RationalQuadraticKernel(alpha: float = 2.0) -> Kernel:  # κ(d²) = (1 + d²/(2α))^(-α)
+    if not alpha > 0:
+        raise ValueError("RationalQuadraticKernel needs α > 0")
+    return Kernel(4, param=float(alpha))
 
 
 def with_lengthscale(k: Kernel, l: float) -> Kernel:
@@ -489,7 +503,7 @@ def _descs(fs: Sequence[GP]):
             a = np.ascontiguousarray(g.kernel.ard, dtype=np.float64)
             keep.append(a)
             ard = a.ctypes.data
-        arr[i] = GpDesc(g.kernel.kind, 0, g.kernel.variance, g.kernel.inv_lengthscale, g.mean_const, ard)
+        arr[i] = GpDesc(g.kernel.kind, 0, g.kernel.variance, g.kernel.inv_lengthscale, g.mean_const, ard, g.kernel.param)
     arr._keep = keep
     return arr
 

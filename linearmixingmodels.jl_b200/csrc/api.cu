@@ -55,7 +55,9 @@ void shard_range(const lmm_ctx* ctx, int m, int& lo, int& hi) {
 
 int check_descs(lmm_ctx* ctx, const lmm_gp_desc* d, int m, int D) {
   for (int i = 0; i < m; ++i) {
-    if (d[i].kind < 0 || d[i].kind > 2) return ctx->fail(LMM_E_UNSUPPORTED, "unsupported kernel kind (only SE, Matern32, Matern52)");
+    if (d[i].kind < 0 || d[i].kind > LMM_KERNEL_RATIONAL_QUADRATIC)
+      return ctx->fail(LMM_E_UNSUPPORTED, "unsupported kernel kind (SE, Matern32, Matern52, Exponential, RationalQuadratic)");
+    if (d[i].kind == LMM_KERNEL_RATIONAL_QUADRATIC && !(d[i].param > 0.0)) return ctx->fail(LMM_E_ARG, "RationalQuadraticKernel needs α > 0 in `param`");
     if (!(d[i].variance > 0.0) || !(d[i].inv_lengthscale > 0.0)) return ctx->fail(LMM_E_ARG, "kernel variance and inv_lengthscale must be positive");
     if (d[i].ard) {
       if (D > LMM_MAX_ARD) return ctx->fail(LMM_E_UNSUPPORTED, "ARDTransform is supported for input dimension D <= 8");
@@ -76,6 +78,7 @@ void set_params(LatentParams& q, const lmm_gp_desc& d, double noise, double ls_s
   q.inv_ls = d.inv_lengthscale * ls_scale;
   q.noise = noise;
   q.mean = d.mean_const;
+  q.param = d.param;
   static_assert(MAX_ARD == LMM_MAX_ARD, "device and ABI limits must agree");
   for (int k = 0; k < MAX_ARD; ++k) q.ard[k] = (d.ard && k < D) ? d.ard[k] : 1.0;
 }

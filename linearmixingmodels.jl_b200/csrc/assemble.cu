@@ -11,7 +11,7 @@ namespace lmm {
 
 __device__ __forceinline__ double kernel_pair(const LatentParams& lp, const double* __restrict__ xa, const double* __restrict__ xb,
                                               int D, int form, bool same_point) {
-  if (same_point) return kappa_eval(lp.kind, lp.variance, 0.0);
+  if (same_point) return kappa_eval(lp.kind, lp.variance, 0.0, lp.param);
   double a[64], b[64];
   double sa = 0.0, sb = 0.0;
   for (int k = 0; k < D; ++k) {
@@ -21,7 +21,7 @@ __device__ __forceinline__ double kernel_pair(const LatentParams& lp, const doub
     sa = fma(a[k], a[k], sa);
     sb = fma(b[k], b[k], sb);
   }
-  return kappa_eval(lp.kind, lp.variance, sqdist(a, b, D, sa, sb, form));
+  return kappa_eval(lp.kind, lp.variance, sqdist(a, b, D, sa, sb, form), lp.param);
 }
 
 // mode 0 (projected): dim = m*N, val = [a==b] k_a(i,j) + E[a,b] [i==j]      (E = ΣT, m x m col-major)

@@ -60,6 +60,7 @@ struct LatentParams {
   double inv_ls;
   double noise;  // added on the diagonal (ΣT_i for OILMM, σ² for IndependentMOGP)
   double mean;
+  double param;  // α of the RationalQuadraticKernel
   double ard[MAX_ARD];
 };
 // Multiplier of input dimension k: KernelFunctions `k ∘ ScaleTransform(s)` / `k ∘ ARDTransform(v)` scale the inputs
@@ -95,19 +96,23 @@ __device__ __forceinline__ double exp_nonpos(double x) {
 }
 
 // κ(d²)·variance -- KernelFunctions kappa for SE / Matern32 / Matern52.
-__device__ __forceinline__ double kappa_eval(int kind, double variance, double d2) {
+__device__ __forceinline__ double kappa_eval(int kind, double variance, double d2, double param = 1.0) {
   // far-apart pairs (most of a kernel matrix whose inputs span many lengthscales) underflow to exactly 0.0
   double v;
   if (kind == 0) {
     v = exp_nonpos(-0.5 * d2);
+  } else if (kind == 4) {
+    v = pow(1.0 + d2 / (2.0 * param), -param);  // RationalQuadraticKernel(α)
   } else {
     double d = sqrt(d2);
     if (kind == 1) {
       double s = 1.7320508075688772 * d;  // sqrt(3)
       v = (1.0 + s) * exp_nonpos(-s);
-    } else {
+    } else if (kind == 2) {
       double s = 2.23606797749979 * d;  // sqrt(5)
       v = (1.0 + s + (d * d) * 1.6666666666666667) * exp_nonpos(-s);
+    } else {
+      v = exp_nonpos(-d);  // ExponentialKernel = Matern12Kernel
     }
   }
   return variance * v;

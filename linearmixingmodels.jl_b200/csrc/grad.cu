@@ -13,10 +13,14 @@ namespace lmm {
 __device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // κ and dK/ds (both already multiplied by the variance where appropriate): returns κ (unscaled by variance)
-__device__ __forceinline__ void kappa_and_ds(int kind, double d2, double rinv_ls, double& kap, double& dkds) {
+__device__ __forceinline__ void kappa_and_ds(int kind, double d2, double rinv_ls, double& kap, double& dkds, double param = 1.0) {
   if (kind == 0) {
     kap = exp_nonpos(-0.5 * d2);
     dkds = -kap * d2 * rinv_ls;
+  } else if (kind == 4) {  // (1 + d²/2α)^(-α);  d/ds = -(d²/s) (1 + d²/2α)^(-α-1)
+    const double base = 1.0 + d2 / (2.0 * param);
+    kap = pow(base, -param);
+    dkds = -d2 * rinv_ls * kap / base;
   } else {
     const double d = sqrt(d2);
     if (kind == 1) {
@@ -24,11 +28,14 @@ __device__ __forceinline__ void kappa_and_ds(int kind, double d2, double rinv_ls
       const double e = exp_nonpos(-s);
       kap = (1.0 + s) * e;
       dkds = -3.0 * d2 * e * rinv_ls;
-    } else {
+    } else if (kind == 2) {
       const double s = 2.23606797749979 * d;
       const double e = exp_nonpos(-s);
       kap = (1.0 + s + (d * d) * 1.6666666666666667) * e;
       dkds = -(5.0 / 3.0) * d2 * (1.0 + s) * e * rinv_ls;
+    } else {  // exp(-d);  d/ds = -(d/s) exp(-d)
+      kap = exp_nonpos(-d);
+      dkds = -d * kap * rinv_ls;
     }
   }
 }
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(256) kgrad_kernel(TiledSym negCinv, const doub
       } else {
         const double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)cc * D, D, sa[r], sb[cc], form);
         double kap, dk;
-        kappa_and_ds(lp.kind, d2, rinv_ls, kap, dk);
+        kappa_and_ds(lp.kind, d2, rinv_ls, kap, dk, lp.param);
         gv = fma(2.0 * G, kap, gv);
         gs = fma(2.0 * G, dk, gs);
       }
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(256) kgrad_block_kernel(TiledSym negCinv, cons
     } else {
       const double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)c * D, D, sa[r], sb[c], form);
       double kap, dk;
-      kappa_and_ds(lp.kind, d2, rinv_ls, kap, dk);
+      kappa_and_ds(lp.kind, d2, rinv_ls, kap, dk, lp.param);
       gv = fma(2.0 * G, kap, gv);
       gs = fma(2.0 * G, dk, gs);
     }

@@ -94,8 +94,8 @@ __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const 
       d0 = d0 > 0.0 ? d0 : 0.0;
       d1 = d1 > 0.0 ? d1 : 0.0;
       double2 v;
-      v.x = kappa_eval(lp.kind, lp.variance, d0);
-      v.y = kappa_eval(lp.kind, lp.variance, d1);
+      v.x = kappa_eval(lp.kind, lp.variance, d0, lp.param);
+      v.y = kappa_eval(lp.kind, lp.variance, d1, lp.param);
       *reinterpret_cast<double2*>(tile + it * 512 + 2 * t) = v;
     }
     return;
@@ -111,7 +111,7 @@ __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const 
       if (gr >= Na || gc >= Nb) {
         val = (SYM && gr == gc) ? 1.0 : 0.0;
       } else if (SYM && gr == gc) {
-        val = kappa_eval(lp.kind, lp.variance, 0.0) + (noise_vec ? noise_vec[gr] : lp.noise);
+        val = kappa_eval(lp.kind, lp.variance, 0.0, lp.param) + (noise_vec ? noise_vec[gr] : lp.noise);
       } else {
         double d2;
         if (DS == 1 && form == 0) {
@@ -121,7 +121,7 @@ __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const 
         } else {
           d2 = sqdist(ar, xb + (size_t)(c + q) * dd, dd, sar, sb[c + q], form);
         }
-        val = kappa_eval(lp.kind, lp.variance, d2);
+        val = kappa_eval(lp.kind, lp.variance, d2, lp.param);
       }
       vv[q] = val;
     }

@@ -22,6 +22,7 @@ struct GpDesc            # lmm_gp_desc
     inv_lengthscale::Float64
     mean_const::Float64
     ard::Ptr{Float64}    # ARDTransform multipliers (D values, kept alive by the caller with GC.@preserve) or C_NULL
+    param::Float64       # α of RationalQuadraticKernel
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
@@ -50,6 +51,10 @@ end
 kind(::SqExponentialKernel) = Int32(0)
 kind(::Matern32Kernel) = Int32(1)
 kind(::Matern52Kernel) = Int32(2)
+kind(::ExponentialKernel) = Int32(3)          # == Matern12Kernel
+kind(::RationalQuadraticKernel) = Int32(4)    # α travels in GpDesc.param
+shape(k) = 1.0
+shape(k::RationalQuadraticKernel) = Float64(only(k.α))
 describe(k::KernelFunctions.SimpleKernel) = (kind(k), 1.0, 1.0)
 describe(k::ScaledKernel) = (d = describe(k.kernel); (d[1], d[2] * only(k.σ²), d[3]))
 function describe(k::TransformedKernel{<:Kernel,<:ScaleTransform})
@@ -61,7 +66,7 @@ meanconst(::AbstractGPs.ZeroMean) = 0.0
 meanconst(m::AbstractGPs.ConstMean) = Float64(m.c)
 function GpDesc(f::GP)
     k, v, s = describe(f.kernel)
-    return GpDesc(k, 0, v, s, meanconst(f.mean), C_NULL)   # `k ∘ ARDTransform(v)`: pass pointer(v) under GC.@preserve
+    return GpDesc(k, 0, v, s, meanconst(f.mean), C_NULL, 1.0)   # `k ∘ ARDTransform(v)`: pass pointer(v) under GC.@preserve
 end
 
 points(x::AbstractVector{<:Real}) = (collect(Float64, x), 1)

@@ -32,8 +32,9 @@ import scipy.linalg as sla
 
 LOG2PI = math.log(2.0 * math.pi)
 
-SE, MATERN32, MATERN52 = 0, 1, 2
-KERNEL_NAMES = {SE: "SEKernel", MATERN32: "Matern32Kernel", MATERN52: "Matern52Kernel"}
+SE, MATERN32, MATERN52, EXPONENTIAL, RATQUAD = 0, 1, 2, 3, 4
+KERNEL_NAMES = {SE: "SEKernel", MATERN32: "Matern32Kernel", MATERN52: "Matern52Kernel", EXPONENTIAL: "ExponentialKernel",
+                RATQUAD: "RationalQuadraticKernel"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -52,6 +53,7 @@ class Kernel:
     variance: float = 1.0
     inv_lengthscale: float = 1.0
     ard: Optional[tuple] = None  # KernelFunctions ``ARDTransform(v)``: x -> v .* x, composed with the ScaleTransform
+    param: float = 1.0  # α of RationalQuadraticKernel
 
 
 @dataclass(frozen=True)
@@ -97,7 +99,7 @@ def pairwise_sqdist(a: np.ndarray, b: Optional[np.ndarray] = None, *, form: str 
     return d2
 
 
-def kappa(kind: int, d2: np.ndarray) -> np.ndarray:
+def kappa(kind: int, d2: np.ndarray, param: float = 1.0) -> np.ndarray:
     """Base kernel as a function of the squared distance (KernelFunctions ``kappa``).
 
     SE: exp(-d²/2) on SqEuclidean; Matern32: (1+√3 d)exp(-√3 d); Matern52:
@@ -112,6 +114,10 @@ def kappa(kind: int, d2: np.ndarray) -> np.ndarray:
     if kind == MATERN52:
         s = math.sqrt(5.0) * d
         return (1.0 + s + 5.0 * (d * d) / 3.0) * np.exp(-s)  # Julia: 5 * d^2 / 3
+    if kind == EXPONENTIAL:  # KernelFunctions ExponentialKernel (= Matern12Kernel): exp(-d), metric Euclidean
+        return np.exp(-d)
+    if kind == RATQUAD:  # RationalQuadraticKernel(α): (1 + d²/(2α))^(-α), metric SqEuclidean
+        return (1.0 + d2 / (2.0 * param)) ** (-param)
     raise ValueError(f"unsupported kernel kind {kind}")
 
 
@@ -120,7 +126,7 @@ def kernelmatrix(k: Kernel, x: np.ndarray, x2: Optional[np.ndarray] = None, *, f
     sc = k.inv_lengthscale if k.ard is None else k.inv_lengthscale * np.asarray(k.ard, dtype=np.float64)[None, :]
     xs = _as2d(x) * sc
     x2s = None if x2 is None else _as2d(x2) * sc
-    return k.variance * kappa(k.kind, pairwise_sqdist(xs, x2s, form=form))
+    return k.variance * kappa(k.kind, pairwise_sqdist(xs, x2s, form=form), k.param)
 
 
 def kernelmatrix_diag(k: Kernel, x: np.ndarray) -> np.ndarray:
@@ -655,7 +661,12 @@ def _dkernel_ds(k: Kernel, x) -> np.ndarray:
     d = np.sqrt(d2)
     if k.kind == MATERN32:
         return k.variance * (-3.0 * d2 * np.exp(-math.sqrt(3.0) * d) / s)
-    return k.variance * (-(5.0 / 3.0) * d2 * (1.0 + math.sqrt(5.0) * d) * np.exp(-math.sqrt(5.0) * d) / s)
+    if k.kind == MATERN52:
+        return k.variance * (-(5.0 / 3.0) * d2 * (1.0 + math.sqrt(5.0) * d) * np.exp(-math.sqrt(5.0) * d) / s)
+    if k.kind == EXPONENTIAL:
+        return k.variance * (-d * np.exp(-d) / s)
+    base = 1.0 + d2 / (2.0 * k.param)
+    return k.variance * (-(d2 / s) * base ** (-k.param - 1.0))
 
 
 def gp_logpdf_grad(f: GP, x, noise: float, y: np.ndarray):

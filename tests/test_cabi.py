@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert C.sizeof(_lib.GpDesc) == 40
+    assert C.sizeof(_lib.GpDesc) == 48
     assert _lib.GpDesc.variance.offset == 8 and _lib.GpDesc.mean_const.offset == 24 and _lib.GpDesc.ard.offset == 32
 
 

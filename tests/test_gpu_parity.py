@@ -20,11 +20,11 @@ def lmm():
     return lmm_b200
 
 
-KMAP = {o.SE: "SEKernel", o.MATERN32: "Matern32Kernel", o.MATERN52: "Matern52Kernel"}
+KMAP = {o.SE: "SEKernel", o.MATERN32: "Matern32Kernel", o.MATERN52: "Matern52Kernel", o.EXPONENTIAL: "ExponentialKernel"}
 
 
 def to_lmm_gp(lmm, g: o.GP):
-    k = getattr(lmm, KMAP[g.kernel.kind])()
+    k = lmm.RationalQuadraticKernel(g.kernel.param) if g.kernel.kind == o.RATQUAD else getattr(lmm, KMAP[g.kernel.kind])()
     k = g.kernel.variance * k if g.kernel.variance != 1.0 else k
     if g.kernel.inv_lengthscale != 1.0:
         k = k.compose(lmm.ScaleTransform(g.kernel.inv_lengthscale))
@@ -738,6 +738,40 @@ def test_ard_transform(lmm, tmp_path):
     big = lmm.GP(lmm.SEKernel().compose(lmm.ARDTransform(np.ones(9))))
     with pytest.raises(ValueError, match="ARDTransform"):
         lmm.logpdf(lmm.independent_mogp([big])(O(lmm.RowVecs(rng.uniform(0, 1, (5, 9))), 1), 0.1), np.zeros(5))
+
+
+@pytest.mark.parametrize("D", [1, 2])
+def test_exponential_and_rational_quadratic_kernels(lmm, D):
+    """ExponentialKernel (= Matern12Kernel) and RationalQuadraticKernel(α) latents: OILMM logpdf, posterior marginals and the
+    logpdf gradient, and the general-ILMM joint assembly, against the oracle."""
+    N, Ns, p, m = 260, 40, 4, 3
+    rng = np.random.default_rng(23 + D)
+    x = np.sort(rng.uniform(0, 4, N)) if D == 1 else rng.uniform(0, 3, (N, D))
+    xs = rng.uniform(0, 4, Ns) if D == 1 else rng.uniform(0, 3, (Ns, D))
+    U, S = o.orthogonal_from_seed(p, m, seed=5)
+    ard = None if D == 1 else (0.8, 1.3)
+    fs = [o.GP(o.Kernel(o.EXPONENTIAL, 0.9, 1.2, ard), 0.3), o.GP(o.Kernel(o.RATQUAD, 1.3, 0.8, None, 1.7), -0.2),
+          o.GP(o.Kernel(o.RATQUAD, 0.7, 1.1, ard, 0.6))]
+    y = rng.standard_normal(p * N)
+    O = lmm.MOInputIsotopicByOutputs
+    wrap = (lambda a: a) if D == 1 else lmm.RowVecs
+    lat = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    om = o.OILMMModel(fs, U, S)
+    fx = lmm.ILMM(lat, lmm.Orthogonal(U, S))(O(wrap(x), p), 0.1)
+    post, lp = lmm.posterior(fx, y, with_logpdf=True)
+    assert rel(lp, o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
+    M, V = lmm.mean_and_var(post(O(wrap(xs), p), 0.1))
+    Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
+    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    np.testing.assert_allclose(V, Vr, rtol=RTOL)
+    _, g = lmm.logpdf_and_gradient(fx, y)
+    _, gr = o.oilmm_logpdf_grad(om, x, 0.1, y)
+    for k in ("variance", "inv_lengthscale", "mean_const"):
+        np.testing.assert_allclose(g[k], gr[k], rtol=1e-7, atol=1e-8)
+    Hd = rng.uniform(0, 1, (p, m))
+    assert rel(lmm.logpdf(lmm.ILMM(lat, Hd)(O(wrap(x), p), 0.1), y), o.ilmm_logpdf(fs, Hd, x, 0.1, y)) < RTOL
+    with pytest.raises(ValueError):
+        lmm.RationalQuadraticKernel(0.0)
 
 
 def test_imogp_process_cov_mixed_orderings(lmm):

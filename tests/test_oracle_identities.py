@@ -295,3 +295,22 @@ def test_oracle_posterior_logpdf_gradient_matches_finite_differences():
     assert lp == pytest.approx(o.ilmm_post_logpdf(ip, xs, 0.2, ys), rel=1e-12)
     assert g["sigma2"] == pytest.approx((o.ilmm_post_logpdf(ip, xs, 0.2 + h, ys) - o.ilmm_post_logpdf(ip, xs, 0.2 - h, ys)) / (2 * h), rel=5e-6)
     assert g["y"][7] == pytest.approx((o.ilmm_post_logpdf(ip, xs, 0.2, ys + e) - o.ilmm_post_logpdf(ip, xs, 0.2, ys - e)) / (2 * h), rel=5e-6)
+
+
+def test_oracle_exponential_and_rational_quadratic_kernels():
+    """ExponentialKernel (= Matern12Kernel, exp(-d)) and RationalQuadraticKernel(α) ((1 + d²/2α)^(-α)), with an ARDTransform:
+    known values, and the lengthscale derivative against central differences."""
+    x = np.array([[0.0, 0.0], [3.0, 4.0]])
+    assert o.kernelmatrix(o.Kernel(o.EXPONENTIAL), x)[0, 1] == pytest.approx(math.exp(-5.0), rel=1e-15)
+    assert o.kernelmatrix(o.Kernel(o.RATQUAD, param=2.0), x)[0, 1] == pytest.approx((1 + 25.0 / 4.0) ** -2.0, rel=1e-15)
+    assert o.kernelmatrix(o.Kernel(o.EXPONENTIAL, 2.0, 0.5, (2.0, 1.0)), x)[0, 1] == pytest.approx(2.0 * math.exp(-math.sqrt(9.0 + 4.0)), rel=1e-15)
+    rng = np.random.default_rng(4)
+    X = rng.uniform(0, 2, (12, 2))
+    y = rng.standard_normal(12)
+    h = 1e-6
+    for k in (o.Kernel(o.EXPONENTIAL, 0.8, 1.3, (0.7, 1.4)), o.Kernel(o.RATQUAD, 1.2, 0.9, None, 1.7)):
+        _, _, gs, _, _, _ = o.gp_logpdf_grad(o.GP(k, 0.1), X, 0.2, y)
+        kp = o.Kernel(k.kind, k.variance, k.inv_lengthscale + h, k.ard, k.param)
+        km = o.Kernel(k.kind, k.variance, k.inv_lengthscale - h, k.ard, k.param)
+        fd = (o.gp_logpdf(o.GP(kp, 0.1), X, 0.2, y, form="direct") - o.gp_logpdf(o.GP(km, 0.1), X, 0.2, y, form="direct")) / (2 * h)
+        assert gs == pytest.approx(fd, rel=2e-6, abs=1e-8)

@@ -17,7 +17,7 @@ from lmm_b200._lib import GpDesc, ptr  # noqa: E402
 def run(ctx, N, batch, reps=2):
     rng = np.random.default_rng(0)
     x = np.sort(rng.uniform(0, N / 100.0, N))
-    d = GpDesc(0, 0, 1.0, 1.0, 0.0, None)
+    d = GpDesc(0, 0, 1.0, 1.0, 0.0, None, 1.0)
     logdet = np.zeros(batch)
     a, c = C.c_double(), C.c_double()
     best = 1e30
