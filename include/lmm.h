@@ -74,14 +74,24 @@ int lmm_ctx_create(int device, lmm_ctx** out);
 int lmm_ctx_destroy(lmm_ctx* ctx);
 const char* lmm_last_error(lmm_ctx* ctx);
 const char* lmm_version(void);
-/* Tunables: "distance_form" (0 = Distances.jl gemm form [default], 1 = direct differences),
- * "outer_block" (tile columns per outer Cholesky step, default 8; 0 = automatic), "streams" (latent groups
- * factored concurrently on separate CUDA streams, default 4, 1..8), "lookahead" (block-level look-ahead for batches <= 2: 0 off, 1 left-looking with the
- * wide update split along K, 2 right-looking with the next block column on the panel stream [default]), "partition_ilmm" (1: the joint factor of a general ILMM
- * -- one large matrix, factored by every rank of the communicator on identical inputs -- is partitioned row-cyclically
- * over the ranks, one ncclAllGather of the current block column per step; every rank must make the same call; default 0),
- * "gemm_impl" (0 = cp.async ring + CTA barrier; 1 / 2 =
- * TMA bulk copies + full/empty mbarrier ring with 16- / 32-column stages; default 2). */
+/* Tunables (key, value):
+ *   "distance_form"   0 = Distances.jl form |a|²+|b|²-2a·b clamped at 0 [default], 1 = direct differences
+ *   "outer_block"     tile columns per outer Cholesky step (default 8 for batched work, 1-4 by size for the
+ *                     look-ahead schedules); 0 = back to automatic
+ *   "streams"         latent groups factored concurrently on separate CUDA streams (default 4, 1..8)
+ *   "lookahead"       schedule for batches <= 2: 0 plain, 1 left-looking with the wide update split along K,
+ *                     2 right-looking with the next block column on the panel stream [default]
+ *   "partition_ilmm"  the joint factor of a general ILMM (one large matrix, factored by every rank of the
+ *                     communicator on identical inputs) is partitioned row-cyclically over the ranks: 1 = one
+ *                     ncclAllGather of the current block column per step, panels redundant; 2 = the panel TRSM
+ *                     distributed too, bulk exchange on a second communicator / stream.  Every rank must make
+ *                     the same calls.  Default 0 (replicas).
+ *   "profile_partition"  1: per-phase CUDA-event times of schedule 2 on stderr
+ *   "nccl_small_ctas" CTA cap of the panel-chain communicator (takes effect at lmm_comm_init; 0 = NCCL's choice)
+ *   "gemm_impl"       0 = cp.async ring + CTA barrier; 1 / 2 = TMA bulk copies + full/empty mbarrier ring with
+ *                     16- / 32-column stages (default 2)          [process-wide]
+ *   "gemm_small"      grids of at most this many tiles use the latency-optimised direct kernel (default 74,
+ *                     0 = never)                                  [process-wide] */
 int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value);
 /* Counters since context creation: kernels launched by this library, bytes copied H2D / D2H. */
 int lmm_ctx_counters(lmm_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
