@@ -58,3 +58,40 @@ def test_cuda_path_matches_golden():
     Mg, Vg = lmm.mean_and_var(lmm.posterior(fxg, G["y"])(mo(G["xs"]), 0.1))
     np.testing.assert_allclose(Mg, G["ilmm_post_mean"], rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(Vg, G["ilmm_post_var"], rtol=1e-9)
+
+
+# ---- 40-digit truth (tests/golden/c1_truth_mp.npz, made by make_golden_mp.py with mpmath straight from the dense multi-output
+# GP definition the reference's tests use as ground truth; shares no code with the oracle)
+T = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_truth_mp.npz"))
+
+
+def test_oracle_matches_extended_precision_truth():
+    model = o.OILMMModel(FS, G["U"], G["S"])
+    assert o.oilmm_logpdf(model, G["x"], 0.1, G["y"]) == pytest.approx(float(T["logpdf"]), rel=1e-13)
+    M, V = o.oilmm_mean_and_var(o.oilmm_posterior(model, G["x"], 0.1, G["y"]), G["xs"], 0.1)
+    np.testing.assert_allclose(M, T["post_mean"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(V, T["post_var"], rtol=1e-11)
+    _, g = o.oilmm_logpdf_grad(model, G["x"], 0.1, G["y"])
+    assert g["sigma2"] == pytest.approx(float(T["dlogpdf_dsigma2"]), rel=1e-10)
+    assert g["inv_lengthscale"][0] == pytest.approx(float(T["dlogpdf_dinv_lengthscale0"]), rel=1e-10)
+    assert g["variance"][0] == pytest.approx(float(T["dlogpdf_dvariance0"]), rel=1e-10)
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_extended_precision_truth():
+    """The B200 path against the 40-digit values: logpdf, posterior means and variances to 1e-9 relative (the north star's
+    tolerance), the logpdf gradient to 1e-8."""
+    import lmm_b200 as lmm
+
+    mo = lambda x: lmm.MOInputIsotopicByOutputs(x, 3)
+    f = lmm.ILMM(lmm.independent_mogp([lmm.GP(lmm.SEKernel()), lmm.GP(lmm.Matern32Kernel())]), lmm.Orthogonal(G["U"], G["S"]))
+    fx = f(mo(G["x"]), 0.1)
+    lp = lmm.logpdf(fx, G["y"])
+    assert abs(lp - float(T["logpdf"])) <= 1e-9 * abs(float(T["logpdf"]))
+    M, V = lmm.mean_and_var(lmm.posterior(fx, G["y"])(mo(G["xs"]), 0.1))
+    np.testing.assert_allclose(M, T["post_mean"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(V, T["post_var"], rtol=1e-9)
+    _, g = lmm.logpdf_and_gradient(fx, G["y"])
+    assert abs(g["sigma2"] - float(T["dlogpdf_dsigma2"])) <= 1e-8 * abs(float(T["dlogpdf_dsigma2"]))
+    assert abs(g["inv_lengthscale"][0] - float(T["dlogpdf_dinv_lengthscale0"])) <= 1e-8 * abs(float(T["dlogpdf_dinv_lengthscale0"]))
+    assert abs(g["variance"][0] - float(T["dlogpdf_dvariance0"])) <= 1e-8 * abs(float(T["dlogpdf_dvariance0"]))
