@@ -272,6 +272,15 @@ int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const 
                          double* out_logpdf, double* grad_latents, double* grad_sigma2, double* grad_y,
                          double* grad_H, int* info);
 
+/* Heterotopic / missing-data ILMM (unsupported in the reference, examples/oilmm_and_ilmm.ipynb:112).
+ * Entries of y (host memory) that are NaN are unobserved; exact inference on the observed entries of the dense model
+ * y ~ N((H ⊗ I) m, Σ_l (h_l h_l') ⊗ K_l + σ² I) -- the model the reference's tests use as the ILMM's ground truth
+ * (test/ilmm.jl:5).  Pass U*sqrt(S) as H for an OILMM.  The returned handle answers lmm_post_mean_and_var (all p outputs
+ * at x*), lmm_post_info and lmm_post_free.  out_post / out_logpdf nullable (not both); n_observed nullable. */
+int lmm_ilmm_masked_posterior(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
+                              const double* H, int p, double sigma2, const double* y, int out_dim,
+                              lmm_post** out_post, double* out_logpdf, int* n_observed, int* info);
+
 /* ---- batched blocked Cholesky primitive: the `cholesky(Symmetric(C))` / dpotrf call site ---- */
 /* A: batch matrices, each N x N column-major (lower triangle read).  L_out (nullable): same
  * shape, lower factor with zero upper part.  logdet_out (nullable): batch doubles = 2 Σ log L_jj.

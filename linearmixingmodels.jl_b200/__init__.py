@@ -18,6 +18,8 @@ from .api import (  # noqa: F401
     set_ilmm_form,
     save_posterior,
     load_posterior,
+    posterior_missing,
+    logpdf_missing,
 )
 from . import _lib, api, dist  # noqa: F401
 

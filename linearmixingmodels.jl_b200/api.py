@@ -530,7 +530,7 @@ def _ctx_of(fx: FiniteGP) -> Context:
             owner = lat._owner
     elif isinstance(f, IndependentMOGP) and isinstance(f.fs[0], PosteriorGP):
         owner = f.fs[0]._owner
-    elif isinstance(f, _JointPosterior):
+    elif isinstance(f, (_JointPosterior, _MissingDataPosterior)):
         owner = f._owner
     return owner.ctx if owner is not None else default_context()
 
@@ -540,7 +540,7 @@ def _post_owner(fx: FiniteGP) -> Optional[_PostHandle]:
     lat = f.f if isinstance(f, ILMM) else f
     if isinstance(lat, IndependentMOGP) and isinstance(lat.fs[0], PosteriorGP):
         return lat.fs[0]._owner
-    if isinstance(lat, _JointPosterior):
+    if isinstance(lat, (_JointPosterior, _MissingDataPosterior)):
         return lat._owner
     return None
 
@@ -1065,3 +1065,50 @@ def load_posterior(path: str, prior, ctx: Optional[Context] = None):
     owner = _PostHandle(ctx, h, N.value)
     newlat = IndependentMOGP([PosteriorGP(owner, i, g) for i, g in enumerate(priors)])
     return ILMM(newlat, prior.H) if kind.value == 0 else newlat
+
+
+class _MissingDataPosterior(AbstractGP):
+    """Posterior of an ILMM / OILMM conditioned on a partially observed y (NaN = missing): `mean_and_var` / `mean` / `var` /
+    `marginals` at new inputs for all outputs."""
+
+    def __init__(self, owner: _PostHandle, prior: ILMM, n_observed: int):
+        self._owner, self.prior, self.n_observed = owner, prior, n_observed
+
+
+def posterior_missing(fx: FiniteGP, y, with_logpdf: bool = False):
+    """Heterotopic / missing-data conditioning (the reference leaves it unsupported): entries of `y` that are NaN
+    are unobserved.  Exact inference on the observed entries of the dense multi-output model; works for `ILMM(fs, H)` with a
+    dense H or an `Orthogonal` H.  Returns a posterior whose FiniteGPs answer `mean_and_var` / `mean` / `var` / `marginals`."""
+    lat, H, s2, _ = unpack(fx)
+    if not isinstance(lat, IndependentMOGP) or any(isinstance(g, PosteriorGP) for g in lat.fs):
+        raise TypeError("posterior_missing needs an ILMM / OILMM over prior latents")
+    ctx = default_context()
+    pts = _points(fx.x.x)
+    N, D = int(pts.shape[0]), int(pts.shape[1])
+    Hm = as_f64(np.asarray(H), "F")
+    p, m = Hm.shape
+    yv = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    if yv.shape[0] != N * p:
+        raise ValueError("length of y does not match the inputs")
+    h, out, nobs, info = C.c_void_p(), C.c_double(), C.c_int(0), C.c_int(0)
+    rc = ctx.lib.lmm_ilmm_masked_posterior(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(Hm), p, s2, ptr(yv), fx.x.out_dim, C.byref(h),
+                                           C.byref(out), C.byref(nobs), C.byref(info))
+    ctx.check(rc)
+    post = _MissingDataPosterior(_PostHandle(ctx, h, N, joint_n=nobs.value), fx.f, nobs.value)
+    return (post, out.value) if with_logpdf else post
+
+
+def logpdf_missing(fx: FiniteGP, y) -> float:
+    """logpdf of the observed (non-NaN) entries of `y` under the ILMM / OILMM `fx` (dense model)."""
+    lat, H, s2, _ = unpack(fx)
+    ctx = default_context()
+    pts = _points(fx.x.x)
+    N, D = int(pts.shape[0]), int(pts.shape[1])
+    Hm = as_f64(np.asarray(H), "F")
+    p, m = Hm.shape
+    yv = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+    out, info = C.c_double(), C.c_int(0)
+    rc = ctx.lib.lmm_ilmm_masked_posterior(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(Hm), p, s2, ptr(yv), fx.x.out_dim, None,
+                                           C.byref(out), None, C.byref(info))
+    ctx.check(rc)
+    return out.value

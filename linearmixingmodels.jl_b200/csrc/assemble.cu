@@ -150,6 +150,69 @@ cudaError_t launch_ilmm_predict(cudaStream_t st, TiledRect V, int Ns, int m, int
   return cudaGetLastError();
 }
 
+// Heterotopic / missing-data dense model: rows and columns run over the OBSERVED entries obs[k] = j*N + i (output j at
+// input i, by outputs) of y ~ N((H ⊗ I) m, Σ_l (h_l h_l') ⊗ K_l + σ² I).   val = Σ_l H[a,l] H[b,l] k_l(x_i, x_j) + σ² [r == c].
+__global__ void __launch_bounds__(256) assemble_masked_kernel(TiledSym out, const int* __restrict__ obs, int nobs,
+                                                              const double* __restrict__ x, int N, int D,
+                                                              const LatentParams* __restrict__ params, int m, int p,
+                                                              const double* __restrict__ Hm, double sigma2, int form) {
+  const int tl = blockIdx.x;
+  int I = (int)((sqrt(8.0 * (double)tl + 1.0) - 1.0) * 0.5);
+  while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tl) ++I;
+  while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
+  const int J = tl - (int)((size_t)I * (I + 1) / 2);
+  double* tile = out.tile(0, I, J);
+  for (int e = threadIdx.x; e < TT; e += 256) {
+    int r, c;
+    tile_rc(e, r, c);
+    const int gr = I * TILE + r, gc = J * TILE + c;
+    double val;
+    if (gr >= nobs || gc >= nobs) {
+      val = (gr == gc) ? 1.0 : 0.0;
+    } else {
+      const int oa = obs[gr], ob = obs[gc];
+      const int a = oa / N, i = oa % N, b = ob / N, j = ob % N;
+      val = 0.0;
+      for (int l = 0; l < m; ++l)
+        val = fma(Hm[(size_t)l * p + a] * Hm[(size_t)l * p + b], kernel_pair(params[l], x + (size_t)i * D, x + (size_t)j * D, D, form, i == j), val);
+      if (gr == gc) val += sigma2;
+    }
+    tile[e] = val;
+  }
+}
+cudaError_t launch_assemble_masked(cudaStream_t st, TiledSym out, const int* obs, int nobs, const double* x, int N, int D,
+                                   const LatentParams* params, int m, int p, const double* Hm, double sigma2, int form) {
+  assemble_masked_kernel<<<(unsigned)sym_tiles(out.nt), 256, 0, st>>>(out, obs, nobs, x, N, D, params, m, p, Hm, sigma2, form);
+  return cudaGetLastError();
+}
+
+// Cross covariance of the dense model between ALL outputs at x* (rows (j, n), by outputs, p*Ns) and the observed entries
+// (columns k over obs): Σ_l H[j,l] H[b_k,l] k_l(x*_n, x_{i_k}).
+__global__ void __launch_bounds__(256) assemble_masked_cross_kernel(TiledRect out, const double* __restrict__ xs, int Ns,
+                                                                    const int* __restrict__ obs, int nobs, const double* __restrict__ x,
+                                                                    int N, int D, const LatentParams* __restrict__ params, int m, int p,
+                                                                    const double* __restrict__ Hm, int form) {
+  const int Rt = blockIdx.x / out.ntc, Jt = blockIdx.x % out.ntc;
+  double* tile = out.tile(0, Rt, Jt);
+  for (int e = threadIdx.x; e < TT; e += 256) {
+    int r, c;
+    tile_rc(e, r, c);
+    const int gr = Rt * TILE + r, gc = Jt * TILE + c;
+    double val = 0.0;
+    if (gr < p * Ns && gc < nobs) {
+      const int j = gr / Ns, n = gr % Ns, ob = obs[gc], b = ob / N, i = ob % N;
+      for (int l = 0; l < m; ++l)
+        val = fma(Hm[(size_t)l * p + j] * Hm[(size_t)l * p + b], kernel_pair(params[l], xs + (size_t)n * D, x + (size_t)i * D, D, form, false), val);
+    }
+    tile[e] = val;
+  }
+}
+cudaError_t launch_assemble_masked_cross(cudaStream_t st, TiledRect out, const double* xs, int Ns, const int* obs, int nobs, const double* x,
+                                         int N, int D, const LatentParams* params, int m, int p, const double* Hm, int form) {
+  assemble_masked_cross_kernel<<<(unsigned)(out.ntr * out.ntc), 256, 0, st>>>(out, xs, Ns, obs, nobs, x, N, D, params, m, p, Hm, form);
+  return cudaGetLastError();
+}
+
 // Gather rows: dst[u][:] = src[idx[u]][:]  (delta replication for the hyper-parameter sweep)
 __global__ void gather_rows_kernel(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ idx, size_t stride) {
   const int u = blockIdx.y;

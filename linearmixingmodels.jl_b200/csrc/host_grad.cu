@@ -16,6 +16,7 @@ extern "C" int lmm_post_condition(lmm_post* post, const double* xs, int Ns, doub
   lmm_ctx* ctx = post->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
+  if (post->kind == POST_MASKED) return ctx->fail(LMM_E_UNSUPPORTED, "a missing-data posterior offers mean_and_var only");
   if (post->joint()) return ilmm_post_condition(post, xs, Ns, sigma2, ys, out_post, info_latent);
   cudaStream_t st = ctx->stream;
   const int m = post->m, p = post->p, D = post->D, N1 = post->N, N2 = N1 + Ns, lo = post->lo, nloc = post->nloc();

@@ -501,6 +501,7 @@ extern "C" int lmm_post_mean_and_cov(lmm_post* post, const double* xs, int Ns, d
   CU(b_cov.alloc(ctx, (size_t)dim * dim * sizeof(double)));
   CU(b_mean.alloc(ctx, 2 * (size_t)dim * sizeof(double)));
   CU(cudaMemsetAsync(b_mean.p, 0, 2 * (size_t)dim * sizeof(double), st));
+  if (post->kind == POST_MASKED) return ctx->fail(LMM_E_UNSUPPORTED, "a missing-data posterior offers mean_and_var only");
   if (post->joint()) {
     // joint latent posterior: C_lat = blockdiag(K**) + 1e-18 I - V V',  V = Kc L^{-T}
     const int N = post->N, D = post->D, bnt = post->big_nt, ntr = ntiles(m * Ns);
@@ -869,3 +870,168 @@ extern "C" int lmm_imogp_posterior_noise(lmm_ctx* ctx, const lmm_gp_desc* fs, in
   if (info_latent && rc <= 0) *info_latent = -1;
   return rc;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Heterotopic / missing-data ILMM (the reference leaves it unsupported,
+// examples/oilmm_and_ilmm.ipynb:112).  Entries of y that are NaN are unobserved.  Exact inference on the observed entries
+// of the dense multi-output model  y ~ N((H ⊗ I) m, Σ_l (h_l h_l') ⊗ K_l + σ² I)  (the model the reference's tests use as
+// the ground truth of the ILMM, test/ilmm.jl:5): one factor of the (n_obs x n_obs) covariance, assembled straight into the
+// factor tiles from the index list of observed entries.  With nothing missing it equals the ILMM's dense form.
+// ------------------------------------------------------------------------------------------------
+extern "C" int lmm_ilmm_masked_posterior(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D, const double* H,
+                                         int p, double sigma2, const double* y, int out_dim, lmm_post** out_post, double* out_logpdf,
+                                         int* n_observed, int* info) {
+  if (!ctx) return LMM_E_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (out_post) *out_post = nullptr;
+  int rc = check_common(ctx, latents, m, x, N, D, p, out_dim);
+  if (rc) return rc;
+  if (!H || !y || (!out_post && !out_logpdf)) return ctx->fail(LMM_E_ARG, "null pointer");
+  if (!(sigma2 > 0.0)) return ctx->fail(LMM_E_ARG, "noise variance must be positive");
+  if (is_device_ptr(y) || is_device_ptr(H)) return ctx->fail(LMM_E_UNSUPPORTED, "the missing-data path takes host y and H (the mask is read on the host)");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  for (double& t : ctx->timings) t = 0.0;
+  // observed entries and centred observations (host: a scan of p*N doubles)
+  std::vector<int> obs;
+  std::vector<double> delta;
+  std::vector<double> hm(p, 0.0);
+  for (int j = 0; j < p; ++j)
+    for (int a = 0; a < m; ++a) hm[j] += H[(size_t)a * p + j] * latents[a].mean_const;
+  for (int j = 0; j < p; ++j)
+    for (int i = 0; i < N; ++i) {
+      const double v = y[(size_t)j * N + i];
+      if (v == v) {  // not NaN
+        obs.push_back(j * N + i);
+        delta.push_back(v - hm[j]);
+      }
+    }
+  const int nobs = (int)obs.size();
+  if (n_observed) *n_observed = nobs;
+  if (nobs == 0) return ctx->fail(LMM_E_ARG, "every observation is missing");
+  if (nobs > (1 << 20)) return ctx->fail(LMM_E_UNSUPPORTED, "joint dimension too large");
+  JointBuild J;
+  J.m = m; J.q = p; J.N = N; J.D = D;
+  J.big = nobs; J.bnt = ntiles(nobs); J.bpad = (size_t)J.bnt * TILE;
+  CU(cudaEventRecord(ctx->ev[0], st));
+  DevBuf b_obs;
+  CU(J.x.alloc(ctx, (size_t)N * D * sizeof(double)));
+  CU(copy_in(ctx, J.x.as<double>(), x, (size_t)N * D));
+  std::vector<double> noise0(m, 0.0);
+  if ((rc = upload_params(ctx, J.params, latents, noise0.data(), 0, m, D))) return rc;
+  CU(J.H.alloc(ctx, (size_t)p * m * sizeof(double)));
+  CU(copy_in(ctx, J.H.as<double>(), H, (size_t)p * m));
+  CU(b_obs.alloc(ctx, (size_t)nobs * sizeof(int)));
+  ctx->h2d += (int64_t)((size_t)nobs * sizeof(int));
+  CU(cudaMemcpyAsync(b_obs.p, obs.data(), (size_t)nobs * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(J.delta.alloc(ctx, J.bpad * sizeof(double)));
+  CU(cudaMemsetAsync(J.delta.p, 0, J.bpad * sizeof(double), st));
+  CU(copy_in(ctx, J.delta.as<double>(), delta.data(), (size_t)nobs));
+  // factor storage + assembly + factor + solves (joint_factor assembles through launch_assemble_ilmm: do it here instead)
+  CU(J.L.alloc(ctx, sym_tiles(J.bnt) * TT * sizeof(double)));
+  CU(J.W.alloc(ctx, (size_t)J.bnt * TT * sizeof(double)));
+  CU(J.logdet.alloc(ctx, sizeof(double)));
+  CU(J.info.alloc(ctx, sizeof(int)));
+  CU(J.quad.alloc(ctx, sizeof(double)));
+  CU(cudaMemsetAsync(J.logdet.p, 0, sizeof(double), st));
+  CU(cudaMemsetAsync(J.info.p, 0, sizeof(int), st));
+  TiledSym L{J.L.as<double>(), J.bnt, sym_tiles(J.bnt) * TT};
+  const size_t wstride = (size_t)J.bnt * TT;
+  CU(cudaEventRecord(ctx->ev[1], st));
+  CU(launch_assemble_masked(st, L, b_obs.as<int>(), nobs, J.x.as<double>(), N, D, J.params.as<LatentParams>(), m, p, J.H.as<double>(), sigma2,
+                            ctx->distance_form));
+  ++ctx->launches;
+  CU(cudaEventRecord(ctx->ev[2], st));
+  {
+    PartitionScope scope(ctx);
+    CU(chol_factor(ctx, L, J.W.as<double>(), wstride, 1, J.logdet.as<double>(), J.info.as<int>()));
+  }
+  CU(cudaEventRecord(ctx->ev[3], st));
+  DevBuf b_r, b_z;
+  CU(b_r.alloc(ctx, J.bpad * sizeof(double)));
+  CU(b_z.alloc(ctx, J.bpad * sizeof(double)));
+  CU(cudaMemcpyAsync(b_r.p, J.delta.p, J.bpad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CU(launch_fwd_solve(st, L, J.W.as<double>(), wstride, b_r.as<double>(), b_z.as<double>(), J.bpad, 1, &ctx->launches));
+  CU(launch_sumsq(st, b_z.as<double>(), J.bpad, (int)J.bpad, 1, J.quad.as<double>()));
+  ++ctx->launches;
+  if (out_post) {
+    CU(J.alpha.alloc(ctx, J.bpad * sizeof(double)));
+    CU(cudaMemcpyAsync(b_r.p, b_z.p, J.bpad * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(launch_bwd_solve(st, L, J.W.as<double>(), wstride, b_r.as<double>(), J.alpha.as<double>(), J.bpad, 1, &ctx->launches));
+  }
+  int hinfo = 0;
+  CU(copy_out(ctx, &J.hlogdet, J.logdet.p, sizeof(double)));
+  CU(copy_out(ctx, &J.hquad, J.quad.p, sizeof(double)));
+  CU(copy_out(ctx, &hinfo, J.info.p, sizeof(int)));
+  CU(cudaEventRecord(ctx->ev[4], st));
+  CU(cudaStreamSynchronize(st));
+  {
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[4]);
+    cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&d, ctx->ev[3], ctx->ev[4]);
+    ctx->timings[0] = a; ctx->timings[1] = b; ctx->timings[2] = c; ctx->timings[3] = d;
+  }
+  if (hinfo > 0) {
+    if (info) *info = hinfo > nobs ? nobs : hinfo;
+    ctx->err = "PosDefException: the covariance of the observed entries is not positive definite";
+    return hinfo > nobs ? nobs : hinfo;
+  }
+  if (info) *info = 0;
+  if (out_logpdf) *out_logpdf = -((double)nobs * LOG2PI + J.hlogdet + J.hquad) / 2.0;
+  if (out_post) {
+    DevBuf none;
+    lmm_post* P = joint_make_post(ctx, J, POST_MASKED, latents, H, p, sigma2, none);
+    P->d_obs = (int*)b_obs.detach();
+    P->bytes += (size_t)nobs * sizeof(int);
+    *out_post = P;
+  }
+  return LMM_OK;
+}
+
+namespace lmm_host {
+// mean_and_var(post(x*, σ²)) of the missing-data posterior: all p outputs at x*.
+//   mean = (H m)_j + K_{*,obs} α ;  var = Σ_l H[j,l]² k_l(x*,x*) - rowsumsq(K_{*,obs} L^{-T}) + σ²
+int masked_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean, double* var) {
+  lmm_ctx* ctx = post->ctx;
+  cudaStream_t st = ctx->stream;
+  const int m = post->m, p = post->p, N = post->N, D = post->D, bnt = post->big_nt, nobs = post->big_n;
+  const int64_t rows64 = (int64_t)p * Ns;
+  if (rows64 > (1 << 22)) return ctx->fail(LMM_E_UNSUPPORTED, "too many prediction points");
+  const int rows = (int)rows64, ntr = ntiles(rows);
+  DevBuf b_xs, b_V, b_m, b_v, b_zero;
+  CU(b_xs.alloc(ctx, (size_t)Ns * D * sizeof(double)));
+  CU(copy_in(ctx, b_xs.as<double>(), xs, (size_t)Ns * D));
+  CU(b_V.alloc(ctx, (size_t)ntr * bnt * TT * sizeof(double)));
+  TiledRect V{b_V.as<double>(), ntr, bnt, (size_t)ntr * bnt * TT};
+  CU(launch_assemble_masked_cross(st, V, b_xs.as<double>(), Ns, post->d_obs, nobs, post->d_xpad, N, D, post->d_params, m, p, post->d_H,
+                                  ctx->distance_form));
+  // a zeroed LatentParams turns rect_gemv / rect_rowsumsq into plain K α and -rowsumsq
+  CU(b_zero.alloc(ctx, sizeof(LatentParams)));
+  CU(cudaMemsetAsync(b_zero.p, 0, sizeof(LatentParams), st));
+  CU(b_m.alloc(ctx, (size_t)ntr * TILE * sizeof(double)));
+  CU(b_v.alloc(ctx, (size_t)ntr * TILE * sizeof(double)));
+  CU(launch_rect_gemv(st, V, post->d_alpha, (size_t)bnt * TILE, b_m.as<double>(), (size_t)ntr * TILE, b_zero.as<LatentParams>(), 0, 1));
+  CU(trsm_right_lt(ctx, V, post->Lsym(), post->d_W, post->wstride(), 1));
+  CU(launch_rect_rowsumsq(st, V, b_v.as<double>(), (size_t)ntr * TILE, b_zero.as<LatentParams>(), 1));
+  ctx->launches += 3;
+  CU(copy_out(ctx, mean, b_m.p, (size_t)rows * sizeof(double)));
+  CU(copy_out(ctx, var, b_v.p, (size_t)rows * sizeof(double)));
+  CU(cudaStreamSynchronize(st));
+  // prior mean and variance of output j (constants along n): Σ_l H[j,l] m_l and Σ_l H[j,l]² variance_l
+  for (int j = 0; j < p; ++j) {
+    double pm = 0.0, pv = 0.0;
+    for (int l = 0; l < m; ++l) {
+      const double h = post->H[(size_t)l * p + j];
+      pm += h * post->descs[l].mean_const;
+      pv += h * h * post->descs[l].variance;
+    }
+    for (int n = 0; n < Ns; ++n) {
+      mean[(size_t)j * Ns + n] += pm;
+      var[(size_t)j * Ns + n] += pv + sigma2;
+    }
+  }
+  return LMM_OK;
+}
+}  // namespace lmm_host

@@ -147,7 +147,8 @@ struct PartitionScope {
 
 // POST_JOINT: IndependentMOGP conditioned under a dense Σy (AbstractGPs generic path): one joint (mN) factor like
 // POST_ILMM, identity mixing, no projection.
-enum { POST_OILMM = 0, POST_IMOGP = 1, POST_ILMM = 2, POST_JOINT = 3 };
+// POST_MASKED: heterotopic / missing-data dense model -- one factor over the observed entries (d_obs), any mixing matrix.
+enum { POST_OILMM = 0, POST_IMOGP = 1, POST_ILMM = 2, POST_JOINT = 3, POST_MASKED = 4 };
 
 struct lmm_post {
   lmm_ctx* ctx = nullptr;
@@ -169,6 +170,7 @@ struct lmm_post {
   LatentParams* d_params = nullptr;
   double* d_H = nullptr;
   double* d_noise_vec = nullptr;  // [nloc][Npad] per-point training noise (sequentially conditioned posteriors), else null
+  int* d_obs = nullptr;           // POST_MASKED: observed entries j*N + i (big_n of them)
   double* d_Ept = nullptr;        // POST_ILMM: [N][m*m] per-point projected noise blocks ΣT (extended by sequential conditioning)
   size_t bytes = 0;
   int big_n = 0, big_nt = 0;  // ILMM joint dimension mN and its tile count
@@ -185,7 +187,7 @@ struct lmm_post {
   }
   int nloc() const { return hi - lo; }
   size_t npad() const { return (size_t)nt * TILE; }
-  bool joint() const { return kind == POST_ILMM || kind == POST_JOINT; }
+  bool joint() const { return kind == POST_ILMM || kind == POST_JOINT || kind == POST_MASKED; }
   TiledSym Lsym() const { return TiledSym{d_L, joint() ? big_nt : nt, sym_tiles(joint() ? big_nt : nt) * TT}; }
   size_t wstride() const { return (size_t)(joint() ? big_nt : nt) * TT; }
 };
@@ -273,4 +275,7 @@ cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W
 cudaError_t trsm_right_lt_upper(lmm_ctx* ctx, cudaStream_t st, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch);
 
 }  // namespace lmm_host
+namespace lmm_host {
+int masked_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean, double* var);
+}
 using namespace lmm_host;

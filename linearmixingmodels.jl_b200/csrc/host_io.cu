@@ -64,6 +64,7 @@ extern "C" int lmm_post_save(lmm_post* post, const char* path) {
   lmm_ctx* ctx = post->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
+  if (post->kind == POST_MASKED) return ctx->fail(LMM_E_UNSUPPORTED, "a missing-data posterior cannot be saved yet");
   FILE* f = fopen(path, "wb");
   if (!f) return ctx->fail(LMM_E_ARG, std::string("cannot open ") + path + " for writing");
   PostFileHeader h{};
@@ -107,7 +108,7 @@ extern "C" int lmm_post_load(lmm_ctx* ctx, const char* path, lmm_post** out_post
     return ctx->fail(LMM_E_ARG, msg);
   };
   if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "LMMPOST2", 8) != 0) return bail("not a liblmm posterior file");
-  if (h.kind < POST_OILMM || h.kind > POST_JOINT || h.m <= 0 || h.p <= 0 || h.N <= 0 || h.D <= 0 || h.lo < 0 || h.hi < h.lo || h.hi > h.m)
+  if (h.kind < POST_OILMM || h.kind > POST_JOINT /* POST_MASKED is never written */ || h.m <= 0 || h.p <= 0 || h.N <= 0 || h.D <= 0 || h.lo < 0 || h.hi < h.lo || h.hi > h.m)
     return bail("corrupt posterior header");
   lmm_post* P = new lmm_post();
   P->ctx = ctx; P->kind = h.kind; P->m = h.m; P->p = h.p; P->N = h.N; P->D = h.D; P->nt = h.nt; P->lo = h.lo; P->hi = h.hi;

@@ -326,7 +326,7 @@ extern "C" int lmm_post_free(lmm_post* post) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   cudaSetDevice(ctx->device);
   void* ptrs[] = {post->d_xpad, post->d_L, post->d_W, post->d_alpha, post->d_delta, post->d_params, post->d_H, post->d_noise_vec,
-                  post->d_Ept};
+                  post->d_Ept, post->d_obs};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
@@ -419,6 +419,7 @@ extern "C" int lmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, d
   lmm_ctx* ctx = post->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
+  if (post->kind == POST_MASKED) return masked_post_mean_and_var(post, xs, Ns, sigma2, mean, var);
   if (post->joint()) return ilmm_post_mean_and_var(post, xs, Ns, sigma2, mean, var);
   cudaStream_t st = ctx->stream;
   for (double& t : ctx->timings) t = 0.0;

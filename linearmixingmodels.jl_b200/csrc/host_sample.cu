@@ -272,6 +272,7 @@ extern "C" int lmm_post_rand(lmm_post* post, const double* xs, int Ns, double si
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
   if (post->kind != POST_IMOGP && post->kind != POST_JOINT && !z_noise) return ctx->fail(LMM_E_ARG, "null pointer");
+  if (post->kind == POST_MASKED) return ctx->fail(LMM_E_UNSUPPORTED, "a missing-data posterior offers mean_and_var only");
   if (post->joint()) return ilmm_post_rand(post, xs, Ns, sigma2, z_latent, z_noise, out, info_latent);
   cudaStream_t st = ctx->stream;
   // OILMM: latents sampled at the default FiniteGP noise 1e-18 (src/oilmm.jl:47); IndependentMOGP: σ²
@@ -304,6 +305,7 @@ int post_logpdf_impl(lmm_post* post, const double* xs, int Ns, double sigma2, co
                      double* grad_y, int* info_latent) {
   lmm_ctx* ctx = post->ctx;
   CU(cudaSetDevice(ctx->device));
+  if (post->kind == POST_MASKED) return ctx->fail(LMM_E_UNSUPPORTED, "a missing-data posterior offers mean_and_var only");
   if (post->joint()) return ilmm_post_logpdf(post, xs, Ns, sigma2, ys, out_logpdf, grad_sigma2, grad_y, info_latent);
   const bool want_grad = grad_sigma2 || grad_y;
   cudaStream_t st = ctx->stream;

@@ -99,6 +99,11 @@ cudaError_t launch_assemble_cross_blockdiag(cudaStream_t st, TiledRect out, cons
 cudaError_t launch_ilmm_predict(cudaStream_t st, TiledRect V, int Ns, int m, int p, const double* H, const LatentParams* params,
                                 const double* mlat, double sigma2, double* mean, double* var);
 cudaError_t launch_gather_rows(cudaStream_t st, double* dst, const double* src, const int* idx, size_t stride, int n);
+// heterotopic / missing-data dense model over the observed entries obs[k] = j*N + i
+cudaError_t launch_assemble_masked(cudaStream_t st, TiledSym out, const int* obs, int nobs, const double* x, int N, int D,
+                                   const LatentParams* params, int m, int p, const double* Hm, double sigma2, int form);
+cudaError_t launch_assemble_masked_cross(cudaStream_t st, TiledRect out, const double* xs, int Ns, const int* obs, int nobs, const double* x,
+                                         int N, int D, const LatentParams* params, int m, int p, const double* Hm, int form);
 }  // namespace lmm
 
 namespace lmm {

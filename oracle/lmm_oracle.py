@@ -647,6 +647,31 @@ def dense_mogp_posterior_mean_and_var(fs, H, x, sigma2, y, xs, sigma2_pred) -> T
     return mean, var
 
 
+def missing_data_logpdf(fs: Sequence[GP], H: np.ndarray, x, sigma2: float, y: np.ndarray) -> float:
+    """Heterotopic / missing-data ILMM (unsupported in the reference): entries of ``y`` that are NaN are
+    unobserved; exact MVN logpdf of the observed entries under the dense model (test/ilmm.jl:5's ground-truth GP)."""
+    y = np.asarray(y, dtype=np.float64)
+    obs = np.flatnonzero(~np.isnan(y))
+    C = dense_mogp_cov(fs, H, x)[np.ix_(obs, obs)] + sigma2 * np.eye(len(obs))
+    L = _chol_lower(C)
+    z = _fwd(L, y[obs] - dense_mogp_mean(fs, H, x)[obs])
+    return -0.5 * (len(obs) * LOG2PI + 2.0 * float(np.sum(np.log(np.diag(L)))) + float(z @ z))
+
+
+def missing_data_posterior_mean_and_var(fs, H, x, sigma2, y, xs, sigma2_pred) -> Tuple[np.ndarray, np.ndarray]:
+    """Posterior marginals of ALL outputs at xs given the observed (non-NaN) entries of y: textbook conditioning of the dense model."""
+    y = np.asarray(y, dtype=np.float64)
+    obs = np.flatnonzero(~np.isnan(y))
+    C = dense_mogp_cov(fs, H, x)[np.ix_(obs, obs)] + sigma2 * np.eye(len(obs))
+    L = _chol_lower(C)
+    alpha = _bwd(L, _fwd(L, y[obs] - dense_mogp_mean(fs, H, x)[obs]))
+    Ksx = dense_mogp_cov(fs, H, xs, x)[:, obs]
+    V = _fwd(L, Ksx.T)
+    mean = dense_mogp_mean(fs, H, xs) + Ksx @ alpha
+    var = np.diag(dense_mogp_cov(fs, H, xs)) - np.sum(V * V, axis=0) + sigma2_pred
+    return mean, var
+
+
 # --------------------------------------------------------------------------------------------
 # Gradients of the logpdf (for the rrule; checked against central finite differences in tests)
 # --------------------------------------------------------------------------------------------

@@ -774,6 +774,38 @@ def test_exponential_and_rational_quadratic_kernels(lmm, D):
         lmm.RationalQuadraticKernel(0.0)
 
 
+@pytest.mark.parametrize("N,Ns,p,m,frac", [(30, 6, 3, 2, 0.3), (300, 45, 5, 3, 0.4), (260, 33, 4, 4, 0.0)])
+def test_missing_data_ilmm(lmm, N, Ns, p, m, frac):
+    """Heterotopic / missing-data conditioning: NaN entries of y are unobserved; logpdf of the observed entries and
+    posterior marginals of all outputs against textbook conditioning of the dense multi-output GP; with nothing missing the
+    result equals the ILMM's own dense form."""
+    rng = np.random.default_rng(N + 1)
+    x, xs = np.sort(rng.uniform(0, 5, N)), rng.uniform(0, 5, Ns)
+    _, _, U, S, fs, y = make_problem(N, p, m, 1, seed=7 + N, means=True)
+    ym = y.copy()
+    ym[rng.uniform(size=p * N) < frac] = np.nan
+    if frac > 0:
+        ym[: N // 2] = np.nan  # half of output 1 missing in one block
+    O = lmm.MOInputIsotopicByOutputs
+    lat = lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs])
+    for Hobj, Hd in ((np.random.default_rng(3).uniform(0, 1, (p, m)), None), (lmm.Orthogonal(U, S), U * np.sqrt(S)[None, :])):
+        Hd = np.asarray(Hobj) if Hd is None else Hd
+        fx = lmm.ILMM(lat, Hobj)(O(x, p), 0.1)
+        post, lp = lmm.posterior_missing(fx, ym, with_logpdf=True)
+        assert post.n_observed == int(np.sum(~np.isnan(ym)))
+        assert rel(lp, o.missing_data_logpdf(fs, Hd, x, 0.1, ym)) < RTOL
+        assert rel(lmm.logpdf_missing(fx, ym), lp) < 1e-14
+        M, V = lmm.mean_and_var(post(O(xs, p), 0.2))
+        Mr, Vr = o.missing_data_posterior_mean_and_var(fs, Hd, x, 0.1, ym, xs, 0.2)
+        np.testing.assert_allclose(M, Mr, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(V, Vr, rtol=1e-8)
+        assert len(lmm.marginals(post(O(xs, p), 0.2))) == p * Ns
+    if frac == 0.0:  # nothing missing: the dense form of the ILMM itself
+        assert rel(lp, o.dense_mogp_logpdf(fs, Hd, x, 0.1, y)) < RTOL
+    with pytest.raises(ValueError):
+        lmm.posterior_missing(fx, np.full(p * N, np.nan))
+
+
 def test_imogp_process_cov_mixed_orderings(lmm):
     """cov(f, x, y) with by-outputs / by-features inputs in all four combinations
     (src/independent_mogp.jl:60-71,181-215; test/independent_mogp.jl:135-141)."""
