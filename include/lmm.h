@@ -153,15 +153,17 @@ int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, cons
  * gradients w.r.t. each latent's (variance, inv_lengthscale, mean_const) -- grad_latents is m x 3
  * row-major --, the observation noise σ², y (p*N by outputs) and the mixing matrix fields U (p x m
  * column-major, the unconstrained Euclidean gradient of the reference's expressions) and S (m).
- * All outputs nullable.  G_i = (α_i α_i' - C_i^{-1})/2 comes from a batched potri on the tensor pipe. */
+ * grad_ard (m x D row-major) receives the gradient w.r.t. each latent's ARD multipliers (zeros for latents without an
+ * ARDTransform).  All outputs nullable.  G_i = (α_i α_i' - C_i^{-1})/2 comes from a batched potri on the tensor pipe. */
 int lmm_oilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N,
                           int D, const double* U, const double* S, int p, double sigma2,
                           const double* y, int out_dim, double* out_logpdf, double* grad_latents,
-                          double* grad_sigma2, double* grad_y, double* grad_U, double* grad_S,
+                          double* grad_ard, double* grad_sigma2, double* grad_y, double* grad_U, double* grad_S,
                           int* info_latent);
 int lmm_imogp_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D,
                           double sigma2, const double* y, int out_dim, double* out_logpdf,
-                          double* grad_latents, double* grad_sigma2, double* grad_y, int* info_latent);
+                          double* grad_latents, double* grad_ard, double* grad_sigma2, double* grad_y,
+                          int* info_latent);
 
 /* ---- posterior handle: the OILMM/ILMM/IndependentMOGP whose latents are PosteriorGPs -------- */
 /* mean_and_var(post(x*, σ²))  src/oilmm.jl:57-76 on PosteriorGP latents (AbstractGPs posterior
@@ -269,8 +271,8 @@ int lmm_ilmm_rand(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double*
  * from a potri on the tensor pipe; the chain through T, ΣT is host arithmetic on m x p matrices. */
 int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
                          const double* H, int p, double sigma2, const double* y, int out_dim,
-                         double* out_logpdf, double* grad_latents, double* grad_sigma2, double* grad_y,
-                         double* grad_H, int* info);
+                         double* out_logpdf, double* grad_latents, double* grad_ard, double* grad_sigma2,
+                         double* grad_y, double* grad_H, int* info);
 
 /* Heterotopic / missing-data ILMM (unsupported in the reference, examples/oilmm_and_ilmm.ipynb:112).
  * Entries of y (host memory) that are NaN are unobserved; exact inference on the observed entries of the dense model

@@ -967,31 +967,35 @@ def logpdf_and_gradient(fx: FiniteGP, y, with_grad_y: bool = False):
         gl = np.zeros((m, 3))
         gU = np.zeros(H.shape, order="F")
         gS = np.zeros(m)
+        ga = np.zeros((m, D))
         rc = ctx.lib.lmm_oilmm_logpdf_grad(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H.U), ptr(H.S), H.shape[0], fx.sigma2, ptr(yv),
-                                           fx.x.out_dim, C.byref(out), ptr(gl), C.byref(gs2), ptr(gy), ptr(gU), ptr(gS), C.byref(il))
+                                           fx.x.out_dim, C.byref(out), ptr(gl), ptr(ga), C.byref(gs2), ptr(gy), ptr(gU), ptr(gS), C.byref(il))
     elif isinstance(f, IndependentMOGP):
         m = len(f.fs)
         gl = np.zeros((m, 3))
+        ga = np.zeros((m, D))
         rc = ctx.lib.lmm_imogp_logpdf_grad(ctx.handle, _descs(f.fs), m, ptr(pts), N, D, fx.sigma2, ptr(yv), fx.x.out_dim, C.byref(out),
-                                           ptr(gl), C.byref(gs2), ptr(gy), C.byref(il))
+                                           ptr(gl), ptr(ga), C.byref(gs2), ptr(gy), C.byref(il))
     elif isinstance(f, ILMM) and isinstance(f.f, IndependentMOGP):  # general mixing matrix, src/ilmm.jl:150-163
         lat = f.f
         m = len(lat.fs)
         Hm = as_f64(np.asarray(f.H), "F")
         gl = np.zeros((m, 3))
         gH = np.zeros(Hm.shape, order="F")
+        ga = np.zeros((m, D))
         rc = ctx.lib.lmm_ilmm_logpdf_grad(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(Hm), Hm.shape[0], fx.sigma2, ptr(yv),
-                                          fx.x.out_dim, C.byref(out), ptr(gl), C.byref(gs2), ptr(gy), ptr(gH), C.byref(il))
+                                          fx.x.out_dim, C.byref(out), ptr(gl), ptr(ga), C.byref(gs2), ptr(gy), ptr(gH), C.byref(il))
         ctx.check(rc, il.value)
         grads = {"variance": gl[:, 0].copy(), "inv_lengthscale": gl[:, 1].copy(), "mean_const": gl[:, 2].copy(), "sigma2": gs2.value,
-                 "H": np.ascontiguousarray(gH)}
+                 "H": np.ascontiguousarray(gH), "ard": ga}
         if with_grad_y:
             grads["y"] = gy
         return out.value, grads
     else:
         raise TypeError("logpdf_and_gradient is built for OILMM, ILMM and IndependentMOGP priors")
     ctx.check(rc, il.value)
-    grads = {"variance": gl[:, 0].copy(), "inv_lengthscale": gl[:, 1].copy(), "mean_const": gl[:, 2].copy(), "sigma2": gs2.value}
+    grads = {"variance": gl[:, 0].copy(), "inv_lengthscale": gl[:, 1].copy(), "mean_const": gl[:, 2].copy(), "sigma2": gs2.value,
+             "ard": ga}  # (m, D): d/d ARDTransform multipliers, zeros for latents without one
     if with_grad_y:
         grads["y"] = gy
     if isinstance(f, ILMM):

@@ -318,6 +318,110 @@ cudaError_t launch_block_trace(cudaStream_t st, TiledSym negCinv, const double* 
   return cudaGetLastError();
 }
 
+// ---- gradient w.r.t. the ARD multipliers (only launched when a latent has an ARDTransform and the caller asks) ------
+// dK/d a_k = variance κ'(d²) 2 u_k² / a_k with u = scaled coordinate difference; κ'(d²) 2 = (dK/ds per unit variance) s / d².
+// One generic kernel for both storages: per-latent factors (mat_batch_stride = tile storage of one latent, off_per_lat = 0)
+// and the joint ILMM matrix (mat_batch_stride = 0, off_per_lat = N).  grid (chunks of the lower triangle, latents).
+__global__ void __launch_bounds__(256) kgrad_ard_kernel(const double* __restrict__ mat_base, size_t mat_batch_stride, int off_per_lat,
+                                                        const double* __restrict__ x, int N, int D,
+                                                        const LatentParams* __restrict__ params, const double* __restrict__ alpha,
+                                                        size_t alpha_stride, int form, double* __restrict__ partial) {
+  extern __shared__ __align__(16) double sm[];
+  double* xa = sm;
+  double* xb = xa + TILE * D;
+  double* sa = xb + TILE * D;
+  double* sb = sa + TILE;
+  double* aa = sb + TILE;
+  double* ab = aa + TILE;
+  __shared__ double red[MAX_ARD][256];
+  const int lat = blockIdx.y, tl = blockIdx.x, t = threadIdx.x;
+  double ga[MAX_ARD];
+#pragma unroll
+  for (int k = 0; k < MAX_ARD; ++k) ga[k] = 0.0;
+  const LatentParams lp = params[lat];
+  if (lp.ard_dim > 0) {  // block-uniform
+    int I = (int)((sqrt(8.0 * (double)tl + 1.0) - 1.0) * 0.5);
+    while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tl) ++I;
+    while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
+    const int J = tl - (int)((size_t)I * (I + 1) / 2);
+    const double* base = mat_base + (size_t)lat * mat_batch_stride;
+    const int off = lat * off_per_lat;
+    const double* al = alpha + (size_t)lat * alpha_stride;
+    const double rinv_ls = 1.0 / lp.inv_ls;
+    for (int i = t; i < TILE * D; i += 256) {
+      const int ra = I * TILE + i / D, rb = J * TILE + i / D;
+      const double s = input_scale(params + lat, i % D);
+      xa[i] = ra < N ? x[(size_t)ra * D + i % D] * s : 0.0;
+      xb[i] = rb < N ? x[(size_t)rb * D + i % D] * s : 0.0;
+    }
+    if (t < TILE) {
+      aa[t] = (I * TILE + t < N) ? al[I * TILE + t] : 0.0;
+      ab[t] = (J * TILE + t < N) ? al[J * TILE + t] : 0.0;
+    }
+    __syncthreads();
+    for (int i = t; i < 2 * TILE; i += 256) {
+      const double* v = (i < TILE) ? xa + (size_t)i * D : xb + (size_t)(i - TILE) * D;
+      double s = 0.0;
+      for (int k = 0; k < D; ++k) s = fma(v[k], v[k], s);
+      if (i < TILE) sa[i] = s; else sb[i - TILE] = s;
+    }
+    __syncthreads();
+    for (int e = t; e < TT; e += 256) {
+      const int c = ((e >> 9) << 2) + (e & 3), r = (e >> 2) & 127;
+      const int gr = I * TILE + r, gc = J * TILE + c;
+      if (gr >= N || gc >= N || gc >= gr) continue;  // strictly lower: the diagonal does not depend on the inputs
+      const double d2 = sqdist(xa + (size_t)r * D, xb + (size_t)c * D, D, sa[r], sb[c], form);
+      if (!(d2 > 0.0)) continue;
+      const double G = 0.5 * (aa[r] * ab[c] + sym_get(base, off + gr, off + gc));
+      double kap, dk;
+      kappa_and_ds(lp.kind, d2, rinv_ls, kap, dk, lp.param);
+      const double w = 2.0 * G * dk * lp.inv_ls / d2;
+#pragma unroll
+      for (int k = 0; k < MAX_ARD; ++k)
+        if (k < D) {
+          const double u = xa[(size_t)r * D + k] - xb[(size_t)c * D + k];
+          ga[k] = fma(w, u * u, ga[k]);
+        }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAX_ARD; ++k) red[k][t] = ga[k];
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w)
+#pragma unroll
+      for (int k = 0; k < MAX_ARD; ++k) red[k][t] += red[k][t + w];
+    __syncthreads();
+  }
+  if (t < MAX_ARD) partial[((size_t)lat * gridDim.x + tl) * MAX_ARD + t] = red[t][0] * lp.variance / (lp.ard_dim > 0 ? params[lat].ard[t] : 1.0);
+}
+// out[lat*MAX_ARD + k] = Σ chunks (fixed order)
+__global__ void __launch_bounds__(256) kgrad_ard_finish_kernel(const double* __restrict__ partial, int nchunks, double* __restrict__ out) {
+  __shared__ double red[256];
+  const int lat = blockIdx.x, k = blockIdx.y, t = threadIdx.x;
+  double s = 0.0;
+  for (int i = t; i < nchunks; i += 256) s += partial[((size_t)lat * nchunks + i) * MAX_ARD + k];
+  red[t] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (t < w) red[t] += red[t + w];
+    __syncthreads();
+  }
+  if (t == 0) out[(size_t)lat * MAX_ARD + k] = red[0];
+}
+cudaError_t launch_kgrad_ard(cudaStream_t st, const double* mat_base, size_t mat_batch_stride, int off_per_lat, const double* x, int N, int D,
+                             const LatentParams* params, int nlat, const double* alpha, size_t alpha_stride, int form, double* partial,
+                             double* out) {
+  const size_t smem = (size_t)(2 * TILE * D + 4 * TILE) * sizeof(double);
+  const int ntn = (N + TILE - 1) / TILE;
+  const int nchunks = (int)sym_tiles(ntn);
+  dim3 grid((unsigned)nchunks, (unsigned)nlat);
+  kgrad_ard_kernel<<<grid, 256, smem, st>>>(mat_base, mat_batch_stride, off_per_lat, x, N, D, params, alpha, alpha_stride, form, partial);
+  dim3 g2((unsigned)nlat, (unsigned)MAX_ARD);
+  kgrad_ard_finish_kernel<<<g2, 256, 0, st>>>(partial, nchunks, out);
+  return cudaGetLastError();
+}
+
 // v[i] = a[i] * sa - b[i]
 __global__ void scale_sub_kernel(double* __restrict__ v, const double* __restrict__ a, double sa, const double* __restrict__ b, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

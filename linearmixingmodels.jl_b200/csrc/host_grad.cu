@@ -142,6 +142,7 @@ struct GradOut {
   double* grad_U = nullptr;  // p x m column-major (OILMM only, nullable)
   double* grad_S = nullptr;  // m (OILMM only, nullable)
   const double* Yhost_or_dev = nullptr;
+  double* grad_ard = nullptr;  // m x D row-major: d/d ARD multiplier (zeros for latents without an ARDTransform; nullable)
 };
 
 int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m, const double* x, int N, int D, int p, double sigma2,
@@ -207,7 +208,16 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
   double* d_vec = b_vec.as<double>();
   if (do_reg) CU(cudaMemcpyAsync(d_vec + 5 * m, b_resid.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
 
-  DevBuf b_L, b_W, b_X, b_alpha, b_r, b_z, b_logdet, b_quad, b_info, b_gpart, b_g4, b_gy;
+  DevBuf b_L, b_W, b_X, b_alpha, b_r, b_z, b_logdet, b_quad, b_info, b_gpart, b_g4, b_gy, b_apart, b_gard;
+  bool want_ard = false;
+  if (out.grad_ard) {
+    for (int i = 0; i < m; ++i) want_ard |= latents[i].ard != nullptr;
+    for (size_t i = 0; i < (size_t)m * D; ++i) out.grad_ard[i] = 0.0;
+  }
+  if (want_ard) {
+    CU(b_gard.alloc(ctx, (size_t)m * MAX_ARD * sizeof(double)));
+    CU(cudaMemsetAsync(b_gard.p, 0, (size_t)m * MAX_ARD * sizeof(double), st));
+  }
   std::vector<int> hinfo(nl, 0);
   std::vector<double> hg4((size_t)nl * 4, 0.0);
   if (mloc > 0) {
@@ -229,6 +239,7 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
     CU(b_info.alloc(ctx, (size_t)mloc * sizeof(int)));
     CU(b_gpart.alloc(ctx, (size_t)chunk * ntl * 3 * sizeof(double)));
     CU(b_g4.alloc(ctx, (size_t)mloc * 4 * sizeof(double)));
+    if (want_ard) CU(b_apart.alloc(ctx, (size_t)chunk * ntl * MAX_ARD * sizeof(double)));
     CU(cudaMemsetAsync(b_logdet.p, 0, (size_t)mloc * sizeof(double), st));
     CU(cudaMemsetAsync(b_info.p, 0, (size_t)mloc * sizeof(int), st));
     for (int c0 = 0; c0 < mloc; c0 += chunk) {
@@ -259,6 +270,11 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
       CU(launch_kgrad(st, L, nb, b_x.as<double>(), N, D, dp, alpha, npad, ctx->distance_form, b_gpart.as<double>()));
       CU(launch_kgrad_finish(st, b_gpart.as<double>(), ntl, nb, alpha, npad, N, b_g4.as<double>() + (size_t)c0 * 4));
       ctx->launches += 8;
+      if (want_ard) {
+        CU(launch_kgrad_ard(st, L.base, L.batch_stride, 0, b_x.as<double>(), N, D, dp, nb, alpha, npad, ctx->distance_form,
+                            b_apart.as<double>(), b_gard.as<double>() + (size_t)(lo + c0) * MAX_ARD));
+        ctx->launches += 2;
+      }
     }
     std::vector<double> hquad(mloc, 0.0);
     CU(copy_out(ctx, hinfo.data(), b_info.p, (size_t)mloc * sizeof(int)));
@@ -279,6 +295,18 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
     CU(copy_in(ctx, b_hv.as<double>(), hv.data(), nvec));
     CU(launch_axpy(st, d_vec, b_hv.as<double>(), nvec, 1.0));
     CU(cudaStreamSynchronize(st));
+  }
+  std::vector<double> hgard;
+  if (want_ard) {
+    if (multi) {
+      int r = nccl_api().AllReduce(b_gard.p, b_gard.p, (size_t)m * MAX_ARD, NCCL_DOUBLE, NCCL_SUM, ctx->comm, st);
+      if (r != 0) return ctx->fail(LMM_E_NCCL, "ncclAllReduce failed");
+    }
+    hgard.resize((size_t)m * MAX_ARD);
+    CU(copy_out(ctx, hgard.data(), b_gard.p, hgard.size() * sizeof(double)));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < m; ++i)
+      for (int k = 0; k < D && k < MAX_ARD; ++k) out.grad_ard[(size_t)i * D + k] = latents[i].ard ? hgard[(size_t)i * MAX_ARD + k] : 0.0;
   }
   // d/dy: -sum_i T[i,:]' α_i  (- R/σ² from the regulariser on rank 0)
   if (out.grad_y) {
@@ -390,8 +418,8 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
 
 extern "C" int lmm_oilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D, const double* U,
                                      const double* S, int p, double sigma2, const double* y, int out_dim, double* out_logpdf,
-                                     double* grad_latents, double* grad_sigma2, double* grad_y, double* grad_U, double* grad_S,
-                                     int* info_latent) {
+                                     double* grad_latents, double* grad_ard, double* grad_sigma2, double* grad_y, double* grad_U,
+                                     double* grad_S, int* info_latent) {
   if (!ctx) return LMM_E_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   int rc = check_common(ctx, latents, m, x, N, D, p, out_dim);
@@ -404,12 +432,13 @@ extern "C" int lmm_oilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, i
   GradOut out{out_logpdf, grad_latents, grad_sigma2, grad_y, info_latent};
   out.grad_U = grad_U;
   out.grad_S = grad_S;
+  out.grad_ard = grad_ard;
   return latents_grad_run(ctx, true, latents, m, x, N, D, p, sigma2, y, pr, S, out);
 }
 
 extern "C" int lmm_imogp_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const double* x, int N, int D, double sigma2,
-                                     const double* y, int out_dim, double* out_logpdf, double* grad_latents, double* grad_sigma2,
-                                     double* grad_y, int* info_latent) {
+                                     const double* y, int out_dim, double* out_logpdf, double* grad_latents, double* grad_ard,
+                                     double* grad_sigma2, double* grad_y, int* info_latent) {
   if (!ctx) return LMM_E_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   int rc = check_common(ctx, fs, m, x, N, D, m, out_dim);
@@ -422,6 +451,7 @@ extern "C" int lmm_imogp_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* fs, int m,
   pr.noise.assign(m, sigma2);
   pr.has_reg = false;
   GradOut out{out_logpdf, grad_latents, grad_sigma2, grad_y, info_latent};
+  out.grad_ard = grad_ard;
   return latents_grad_run(ctx, false, fs, m, x, N, D, m, sigma2, y, pr, nullptr, out);
 }
 // ------------------------------------------------------------------------------------------------
@@ -469,7 +499,7 @@ extern "C" int lmm_imogp_cross_cov(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, c
 
 extern "C" int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D, const double* H,
                                     int p, double sigma2, const double* y, int out_dim, double* out_logpdf, double* grad_latents,
-                                    double* grad_sigma2, double* grad_y, double* grad_H, int* info) {
+                                    double* grad_ard, double* grad_sigma2, double* grad_y, double* grad_H, int* info) {
   if (!ctx) return LMM_E_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   int rc = check_common(ctx, latents, m, x, N, D, p, out_dim);
@@ -575,6 +605,22 @@ extern "C" int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, in
   CU(launch_kgrad_joint(st, L, b_x.as<double>(), N, D, b_params.as<LatentParams>(), m, b_alpha.as<double>(), ctx->distance_form,
                         b_gpart.as<double>(), b_g3.as<double>(), b_B.as<double>()));
   ctx->launches += 6;
+  bool want_ard = false;
+  DevBuf b_apart, b_gard;
+  std::vector<double> hgard;
+  if (grad_ard) {
+    for (int a = 0; a < m; ++a) want_ard |= latents[a].ard != nullptr;
+    for (size_t i = 0; i < (size_t)m * D; ++i) grad_ard[i] = 0.0;
+  }
+  if (want_ard) {
+    CU(b_apart.alloc(ctx, (size_t)m * nchunks * MAX_ARD * sizeof(double)));
+    CU(b_gard.alloc(ctx, (size_t)m * MAX_ARD * sizeof(double)));
+    CU(launch_kgrad_ard(st, L.base, 0, N, b_x.as<double>(), N, D, b_params.as<LatentParams>(), m, b_alpha.as<double>(), (size_t)N,
+                        ctx->distance_form, b_apart.as<double>(), b_gard.as<double>()));
+    ctx->launches += 2;
+    hgard.resize((size_t)m * MAX_ARD);
+    CU(copy_out(ctx, hgard.data(), b_gard.p, hgard.size() * sizeof(double)));
+  }
   // V = H'R/σ² - A ;  dT(direct) = V Y' ;  dH(direct) = R Z'/σ² ;  dy = T'V - R/σ²
   CU(b_HtR.alloc(ctx, (size_t)m * N * sizeof(double)));
   CU(launch_project(st, b_R.as<double>(), N, p, b_Ht.as<double>(), m, 0, m, b_zero.as<double>(), b_HtR.as<double>(), (size_t)N, nullptr,
@@ -623,6 +669,9 @@ extern "C" int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, in
   }
   if (info) *info = 0;
   if (out_logpdf) *out_logpdf = -((double)big * LOG2PI + hlogdet + hquad) / 2.0 - (gp.pr.reg_c0 + hres / sigma2) / 2.0;
+  if (want_ard)
+    for (int a = 0; a < m; ++a)
+      for (int k = 0; k < D && k < MAX_ARD; ++k) grad_ard[(size_t)a * D + k] = latents[a].ard ? hgard[(size_t)a * MAX_ARD + k] : 0.0;
   if (grad_latents)
     for (int a = 0; a < m; ++a) {
       grad_latents[(size_t)a * 3 + 0] = g3[(size_t)a * 3 + 0];

@@ -126,6 +126,11 @@ cudaError_t launch_kgrad_joint(cudaStream_t st, TiledSym negCinv, const double* 
                                const double* alpha, int form, double* partial, double* out3, double* B);
 // B (m x m) = block traces of G over a joint (m*N) matrix whose latent blocks start at multiples of N
 cudaError_t launch_block_trace(cudaStream_t st, TiledSym negCinv, const double* alpha, int N, int m, double* B);
+// gradient w.r.t. the ARD multipliers: out[lat*8 + k]; partial: nlat * sym_tiles(ceil(N/128)) * 8 doubles of scratch.
+// Per-latent factors: mat_batch_stride = doubles per latent, off_per_lat = 0; joint ILMM matrix: 0 and N.  D <= 8.
+cudaError_t launch_kgrad_ard(cudaStream_t st, const double* mat_base, size_t mat_batch_stride, int off_per_lat, const double* x, int N, int D,
+                             const LatentParams* params, int nlat, const double* alpha, size_t alpha_stride, int form, double* partial,
+                             double* out);
 cudaError_t launch_scale_sub(cudaStream_t st, double* v, const double* a, double sa, const double* b, size_t n);
 }  // namespace lmm
 

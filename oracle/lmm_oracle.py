@@ -694,6 +694,33 @@ def _dkernel_ds(k: Kernel, x) -> np.ndarray:
     return k.variance * (-(d2 / s) * base ** (-k.param - 1.0))
 
 
+def _dkernel_dard(k: Kernel, x) -> List[np.ndarray]:
+    """d/d(ard_j) of kernelmatrix(k, x): dK/ds * (s / d²) * u_j² / ard_j with u = scaled coordinate differences (analytic)."""
+    X = _as2d(x)
+    if k.ard is None:
+        return []
+    a = np.asarray(k.ard, dtype=np.float64)
+    xs = X * (k.inv_lengthscale * a[None, :])
+    d2 = pairwise_sqdist(xs, form="direct")
+    dKds = _dkernel_ds(k, x)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = np.where(d2 > 0, dKds * k.inv_lengthscale / d2, 0.0)
+    return [w * (xs[:, j][:, None] - xs[:, j][None, :]) ** 2 / a[j] for j in range(X.shape[1])]
+
+
+def gp_logpdf_grad_ard(f: GP, x, noise: float, y: np.ndarray) -> np.ndarray:
+    """d lml / d(ARD multipliers) of one latent (zeros if it has no ARDTransform)."""
+    X = _as2d(x)
+    if f.kernel.ard is None:
+        return np.zeros(X.shape[1])
+    C = kernelmatrix(f.kernel, x)
+    C[np.diag_indices_from(C)] += noise
+    L = _chol_lower(C)
+    alpha = _bwd(L, _fwd(L, np.asarray(y, dtype=np.float64) - f.mean_const))
+    G = 0.5 * (np.outer(alpha, alpha) - _bwd(L, _fwd(L, np.eye(C.shape[0]))))
+    return np.array([float(np.sum(G * dK)) for dK in _dkernel_dard(f.kernel, x)])
+
+
 def gp_logpdf_grad(f: GP, x, noise: float, y: np.ndarray):
     """(lml, d/dvariance, d/dinv_lengthscale, d/dmean, d/dnoise, d/dy) with G = (αα' - C⁻¹)/2."""
     C = kernelmatrix(f.kernel, x)
@@ -766,10 +793,13 @@ def ilmm_logpdf_grad(fs: Sequence[GP], H: np.ndarray, x, sigma2: float, y: np.nd
     A = alpha.reshape(m, N)
     g_var = np.zeros(m)
     g_s = np.zeros(m)
+    g_ard = np.zeros((m, _as2d(x).shape[1]))
     for a, f in enumerate(fs):
         Gaa = G[a * N:(a + 1) * N, a * N:(a + 1) * N]
         g_var[a] = float(np.sum(Gaa * kernelmatrix(f.kernel, x, form="direct"))) / f.kernel.variance
         g_s[a] = float(np.sum(Gaa * _dkernel_ds(f.kernel, x)))
+        for j, dK in enumerate(_dkernel_dard(f.kernel, x)):
+            g_ard[a, j] = float(np.sum(Gaa * dK))
     B = np.array([[float(np.trace(G[a * N:(a + 1) * N, b * N:(b + 1) * N])) for b in range(m)] for a in range(m)])
     # direct cotangents
     HtR = H.T @ R
@@ -790,7 +820,7 @@ def ilmm_logpdf_grad(fs: Sequence[GP], H: np.ndarray, x, sigma2: float, y: np.nd
     bar_H = bar_H + H @ (bar_M + bar_M.T) / sigma2
     g_sigma2 -= float(np.sum(bar_M * (H.T @ H))) / sigma2 ** 2
     return lml + reg, {"variance": g_var, "inv_lengthscale": g_s, "mean_const": A.sum(axis=1), "sigma2": float(g_sigma2),
-                       "y": g_y.reshape(-1), "H": bar_H}
+                       "y": g_y.reshape(-1), "H": bar_H, "ard": g_ard}
 
 
 def oilmm_post_logpdf_grad(model: OILMMModel, xs, sigma2: float, ys: np.ndarray):

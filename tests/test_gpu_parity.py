@@ -703,6 +703,10 @@ def test_ard_transform(lmm, tmp_path):
     for k in ("variance", "inv_lengthscale", "mean_const"):
         np.testing.assert_allclose(g[k], gr[k], rtol=1e-7, atol=1e-8)
     assert rel(g["sigma2"], gr["sigma2"]) < 1e-7
+    T, ST1 = o.project_orthogonal(U, S, 0.1)
+    ard_ref = np.stack([o.gp_logpdf_grad_ard(fs[i], x, ST1[i], (T @ y.reshape(p, N))[i]) for i in range(m)])
+    np.testing.assert_allclose(g["ard"], ard_ref, rtol=1e-7, atol=1e-8)
+    assert np.all(g["ard"][2] == 0.0)  # the latent without an ARDTransform
     # save / load keeps the ARD vectors; the reloaded handle can be conditioned again
     path = str(tmp_path / "ard.lmm")
     lmm.save_posterior(post, path)
@@ -734,6 +738,7 @@ def test_ard_transform(lmm, tmp_path):
     lpi, gi = lmm.logpdf_and_gradient(fi, y)
     _, gir = o.ilmm_logpdf_grad(fs, Hd, x, 0.1, y)
     np.testing.assert_allclose(gi["inv_lengthscale"], gir["inv_lengthscale"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(gi["ard"], gir["ard"], rtol=1e-7, atol=1e-8)
     # D > 8 with ARD is rejected loudly, never routed elsewhere
     big = lmm.GP(lmm.SEKernel().compose(lmm.ARDTransform(np.ones(9))))
     with pytest.raises(ValueError, match="ARDTransform"):

@@ -314,3 +314,20 @@ def test_oracle_exponential_and_rational_quadratic_kernels():
         km = o.Kernel(k.kind, k.variance, k.inv_lengthscale - h, k.ard, k.param)
         fd = (o.gp_logpdf(o.GP(kp, 0.1), X, 0.2, y, form="direct") - o.gp_logpdf(o.GP(km, 0.1), X, 0.2, y, form="direct")) / (2 * h)
         assert gs == pytest.approx(fd, rel=2e-6, abs=1e-8)
+
+
+def test_oracle_ard_gradient_matches_finite_differences():
+    rng = np.random.default_rng(11)
+    X = rng.uniform(0, 2, (14, 3))
+    y = rng.standard_normal(14)
+    h = 1e-6
+    for kind, param in ((o.SE, 1.0), (o.MATERN32, 1.0), (o.MATERN52, 1.0), (o.EXPONENTIAL, 1.0), (o.RATQUAD, 1.4)):
+        ard = (0.7, 1.3, 2.1)
+        g = o.gp_logpdf_grad_ard(o.GP(o.Kernel(kind, 0.9, 1.1, ard, param), 0.2), X, 0.15, y)
+        for j in range(3):
+            ap, am = list(ard), list(ard)
+            ap[j] += h
+            am[j] -= h
+            fd = (o.gp_logpdf(o.GP(o.Kernel(kind, 0.9, 1.1, tuple(ap), param), 0.2), X, 0.15, y, form="direct")
+                  - o.gp_logpdf(o.GP(o.Kernel(kind, 0.9, 1.1, tuple(am), param), 0.2), X, 0.15, y, form="direct")) / (2 * h)
+            assert g[j] == pytest.approx(fd, rel=5e-6, abs=1e-8)
