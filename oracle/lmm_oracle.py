@@ -10,7 +10,9 @@ reference's own tests hold no golden logpdf / mean / var numbers (SURVEY.md §8c
 known answers (permutations, ``noise_var``, ``reshape_y``, ``Orthogonal`` validation).  This file
 is a NumPy/SciPy Float64 restatement (LAPACK ``dpotrf``/``dtrtrs`` through OpenBLAS -- the routine
 family Julia's ``cholesky`` and ``\\`` reach) pinned by exactly those identities and known answers
-(``tests/test_oracle_identities.py``) and by a long-double/dense cross-check.
+(``tests/test_oracle_identities.py``), by a long-double/dense cross-check and by 40-digit mpmath values of BASELINE
+config 1 computed from the dense multi-output-GP definition with no shared code (``tests/golden/make_golden_mp.py``,
+``tests/golden/c1_truth_mp.npz``: logpdf, posterior marginals, three logpdf derivatives).
 
 Every function cites the reference lines it follows (paths relative to /root/reference).  The
 arithmetic of AbstractGPs 0.3.x / KernelFunctions 0.10.x / Distances 0.10.x is not vendored in the
