@@ -224,28 +224,50 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
     for (int q = 0; q < pre; ++q) produce(q);
   }
 
+  // Accumulators: 64 doubles per thread in both modes.  UPDATE: warps 2(M) x 4(N), warp tile 64 x 32 = acc[8][4].  TRSM:
+  // W(J) is LOWER triangular, so output column block nb only needs the k-blocks <= nb -- a 2 x 4 warp grid would leave the
+  // warps of the low column groups idle, so the TRSM uses 8(M) x 1(N) warps, warp tile 16 x 128 = acc[2][16] (the same
+  // storage, viewed differently), and every warp skips the same zero blocks: 120 of 256 block products.
   double acc[8][4][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double (*acct)[16][2] = reinterpret_cast<double (*)[16][2]>(&acc[0][0][0]);  // TRSM view: [2][16][2]
 
   for (int q = 0; q < nchunks; ++q) {
     const int s = q % V2_STAGES;
     mb_wait(&full[s], (uint32_t)((q / V2_STAGES) & 1));
-    const double* sa = smem + (size_t)s * (2 * SCHUNK) + (wm * 8) * 32 + lane;
-    const double* sb = smem + (size_t)s * (2 * SCHUNK) + SCHUNK + (wn * 4) * 32 + lane;
+    if constexpr (MODE == GEMM_TRSM) {
+      const double* sa = smem + (size_t)s * (2 * SCHUNK) + (warp * 2) * 32 + lane;
+      const double* sb = smem + (size_t)s * (2 * SCHUNK) + SCHUNK + lane;
 #pragma unroll
-    for (int ks = 0; ks < KC / 4; ++ks) {
-      double a[8], bq[4];
+      for (int ks = 0; ks < KC / 4; ++ks) {
+        const int kb8 = (q * (KC / 4) + ks) >> 1;  // the 8-column block of W this k4-step belongs to
+        const double a0 = sa[ks * 512], a1 = sa[ks * 512 + 32];
 #pragma unroll
-      for (int mb = 0; mb < 8; ++mb) a[mb] = sa[ks * 512 + mb * 32];
+        for (int nb = 0; nb < 16; ++nb)
+          if (nb >= kb8) {  // warp-uniform: W(n, k) = 0 for k > n
+            const double bq = sb[ks * 512 + nb * 32];
+            dmma884(acct[0][nb][0], acct[0][nb][1], a0, bq);
+            dmma884(acct[1][nb][0], acct[1][nb][1], a1, bq);
+          }
+      }
+    } else {
+      const double* sa = smem + (size_t)s * (2 * SCHUNK) + (wm * 8) * 32 + lane;
+      const double* sb = smem + (size_t)s * (2 * SCHUNK) + SCHUNK + (wn * 4) * 32 + lane;
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb) bq[nb] = sb[ks * 512 + nb * 32];
+      for (int ks = 0; ks < KC / 4; ++ks) {
+        double a[8], bq[4];
 #pragma unroll
-      for (int mb = 0; mb < 8; ++mb)
+        for (int mb = 0; mb < 8; ++mb) a[mb] = sa[ks * 512 + mb * 32];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bq[nb]);
+        for (int nb = 0; nb < 4; ++nb) bq[nb] = sb[ks * 512 + nb * 32];
+#pragma unroll
+        for (int mb = 0; mb < 8; ++mb)
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bq[nb]);
+      }
     }
     __syncwarp();
     if (lane == 0) mb_arrive(&empty[s]);
@@ -261,23 +283,34 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   }
 
   const int g4 = lane >> 2, t4 = lane & 3;
+  if constexpr (MODE == GEMM_TRSM) {
+    // in place: the whole tile C(I,J) went through the stage ring above (every chunk consumed by every warp), so a CTA
+    // barrier is all that separates the last read from the first write
+    __syncthreads();
 #pragma unroll
-  for (int mb = 0; mb < 8; ++mb) {
+    for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) {
-      const int cg = wn * 8 + nb * 2 + (t4 >> 1);
-      const int off = (cg << 9) + ((wm * 8 + mb) << 5) + (g4 << 2) + ((t4 & 1) << 1);
-      double2* ptr = reinterpret_cast<double2*>(Ctile + off);
-      double2 v;
-      if (MODE == GEMM_UPDATE) {
-        v = *ptr;
+      for (int nb = 0; nb < 16; ++nb) {
+        const int cg = nb * 2 + (t4 >> 1);
+        const int off = (cg << 9) + ((warp * 2 + mb) << 5) + (g4 << 2) + ((t4 & 1) << 1);
+        double2 v;
+        v.x = acct[mb][nb][0];
+        v.y = acct[mb][nb][1];
+        *reinterpret_cast<double2*>(Ctile + off) = v;
+      }
+  } else {
+#pragma unroll
+    for (int mb = 0; mb < 8; ++mb) {
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const int cg = wn * 8 + nb * 2 + (t4 >> 1);
+        const int off = (cg << 9) + ((wm * 8 + mb) << 5) + (g4 << 2) + ((t4 & 1) << 1);
+        double2* ptr = reinterpret_cast<double2*>(Ctile + off);
+        double2 v = *ptr;
         v.x -= acc[mb][nb][0];
         v.y -= acc[mb][nb][1];
-      } else {
-        v.x = acc[mb][nb][0];
-        v.y = acc[mb][nb][1];
+        *ptr = v;
       }
-      *ptr = v;
     }
   }
 }
