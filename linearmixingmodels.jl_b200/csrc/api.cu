@@ -188,6 +188,12 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "gemm_small") {
     if (value < 0 || value > 4096) return ctx->fail(LMM_E_ARG, "gemm_small must be in [0, 4096]");
     set_gemm_small_threshold((int)value);
+  } else if (k == "potrf_impl") {
+    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_UNSUPPORTED, "potrf_impl must be 0 or 1");
+    set_potrf_impl((int)value);
+  } else if (k == "gemm_direct") {
+    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_direct must be 0, 1 or 2");
+    set_gemm_direct((int)value);
   } else if (k == "gemm_impl") {
     if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0, 1 or 2");
     set_gemm_impl((int)value);

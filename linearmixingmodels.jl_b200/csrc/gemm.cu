@@ -396,8 +396,107 @@ __global__ void __launch_bounds__(256) gemm_direct_kernel(GemmArgs g) {
     }
 }
 
+// Second-generation direct kernel: the same no-shared-memory scheme, with (a) the fragments of the next PF k4-steps in
+// flight while the current ones feed the tensor pipe (a register ring: the plain kernel waits one L2 round trip per
+// k4-step), (b) RB = 4 or 2 row blocks per CTA (a tile split over 4 or 8 SMs), and (c) in TRSM mode the zero blocks of the
+// lower-triangular W(J) skipped: warp w owns column blocks w and 15-w, i.e. 2(w+1) + 2(16-w) = 34 of 64 block-steps.
+template <int MODE, int RB, int PF>
+__global__ void __launch_bounds__(256) gemm_direct2_kernel(GemmArgs g) {
+  constexpr int SPLIT = 16 / RB;
+  const int J = g.j0 + (int)(blockIdx.x / SPLIT), slice = (int)(blockIdx.x % SPLIT);
+  const int I = g.i0 + blockIdx.y * (g.row_step > 0 ? g.row_step : 1), b = blockIdx.z;
+  if (g.sym && I < J) return;
+  if (g.upper && I > J) return;
+  const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;
+  if (MODE == GEMM_UPDATE && kb >= g.k1) return;
+  double* Ctile = g.C.tile(b, I, J);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* Asrc;
+  const double* Bsrc;
+  int nsteps, nb0, nb1, lim0;
+  if (MODE == GEMM_UPDATE) {
+    Asrc = g.A.tile(b, I, kb);
+    Bsrc = g.B.tile(b, J, kb);
+    nsteps = (g.k1 - kb) * 32;
+    nb0 = warp * 2;
+    nb1 = warp * 2 + 1;
+    lim0 = nsteps;
+  } else {
+    Asrc = Ctile;
+    Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
+    nb0 = warp;             // W^T block (k8, nb) is zero for k8 > nb: column block nb needs k4-steps q < 2 (nb + 1)
+    nb1 = 15 - warp;
+    lim0 = 2 * (nb0 + 1);
+    nsteps = 2 * (nb1 + 1);
+  }
+  const double* pa = Asrc + (slice * RB) * 32 + lane;
+  const double* pb0 = Bsrc + nb0 * 32 + lane;
+  const double* pb1 = Bsrc + nb1 * 32 + lane;
+  double acc[RB][2][2];
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double ra[PF][RB], rb[PF][2];
+#pragma unroll
+  for (int u = 0; u < PF; ++u) {
+    const int q = u < nsteps ? u : nsteps - 1;
+#pragma unroll
+    for (int i = 0; i < RB; ++i) ra[u][i] = pa[(size_t)q * 512 + i * 32];
+    rb[u][0] = pb0[(size_t)q * 512];
+    rb[u][1] = pb1[(size_t)q * 512];
+  }
+  for (int q0 = 0; q0 < nsteps; q0 += PF) {  // nsteps is even; PF steps per trip, the tail of the last trip is predicated off
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int q = q0 + u;
+      double a[RB], bq[2];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) a[i] = ra[u][i];
+      bq[0] = rb[u][0];
+      bq[1] = rb[u][1];
+      const int qn = (q + PF < nsteps) ? q + PF : nsteps - 1;
+#pragma unroll
+      for (int i = 0; i < RB; ++i) ra[u][i] = pa[(size_t)qn * 512 + i * 32];
+      rb[u][0] = pb0[(size_t)qn * 512];
+      rb[u][1] = pb1[(size_t)qn * 512];
+      if (q < nsteps) {
+        if (MODE == GEMM_UPDATE || q < lim0) {
+#pragma unroll
+          for (int i = 0; i < RB; ++i) dmma884(acc[i][0][0], acc[i][0][1], a[i], bq[0]);
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) dmma884(acc[i][1][0], acc[i][1][1], a[i], bq[1]);
+      }
+    }
+  }
+  if (MODE == GEMM_TRSM) __syncthreads();  // every warp of this CTA has finished reading its rows of C(I,J)
+  const int g4 = lane >> 2, t4 = lane & 3;
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int cg = (j == 0 ? nb0 : nb1) * 2 + (t4 >> 1);
+      const int off = (cg << 9) + ((slice * RB + i) << 5) + (g4 << 2) + ((t4 & 1) << 1);
+      double2* ptr = reinterpret_cast<double2*>(Ctile + off);
+      double2 v;
+      if (MODE == GEMM_UPDATE) {
+        v = *ptr;
+        v.x -= acc[i][j][0];
+        v.y -= acc[i][j][1];
+      } else {
+        v.x = acc[i][j][0];
+        v.y = acc[i][j][1];
+      }
+      *ptr = v;
+    }
+}
+
 static int g_gemm_small = 74;  // grids of at most this many tiles take the latency-optimised kernel (0 = never)
 void set_gemm_small_threshold(int tiles) { g_gemm_small = tiles; }
+
+static int g_gemm_direct = 2;  // 0: plain direct kernel (4 slices, one step of prefetch); 1: register-ring prefetch, 4 slices; 2: ring, 8 slices
+void set_gemm_direct(int v) { g_gemm_direct = v; }
 
 static int g_gemm_impl = 2;  // 0: v1 cp.async ring; 1: v2 (TMA bulk + mbarriers), 16-column stages; 2: v2, 32-column stages
 void set_gemm_impl(int impl) { g_gemm_impl = impl; }
@@ -424,8 +523,19 @@ cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols,
     configured = true;
   }
   if ((long long)ncols * nrows * batch <= g_gemm_small) {
-    dim3 gs((unsigned)ncols * 4, (unsigned)nrows, (unsigned)batch);
-    if (mode == GEMM_UPDATE)
+    const int split = g_gemm_direct == 2 ? 8 : 4;
+    dim3 gs((unsigned)ncols * split, (unsigned)nrows, (unsigned)batch);
+    if (g_gemm_direct == 2) {
+      if (mode == GEMM_UPDATE)
+        gemm_direct2_kernel<GEMM_UPDATE, 2, 8><<<gs, 256, 0, st>>>(a);
+      else
+        gemm_direct2_kernel<GEMM_TRSM, 2, 8><<<gs, 256, 0, st>>>(a);
+    } else if (g_gemm_direct == 1) {
+      if (mode == GEMM_UPDATE)
+        gemm_direct2_kernel<GEMM_UPDATE, 4, 6><<<gs, 256, 0, st>>>(a);
+      else
+        gemm_direct2_kernel<GEMM_TRSM, 4, 6><<<gs, 256, 0, st>>>(a);
+    } else if (mode == GEMM_UPDATE)
       gemm_direct_kernel<GEMM_UPDATE><<<gs, 256, 0, st>>>(a);
     else
       gemm_direct_kernel<GEMM_TRSM><<<gs, 256, 0, st>>>(a);

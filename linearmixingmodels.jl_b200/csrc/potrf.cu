@@ -303,6 +303,339 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
   PT(9);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Second-generation diagonal-tile kernel (default).  Same results (L, W = inv(L), logdet, info), about half the cycles:
+//   * LEFT-looking inside the tile.  The first kernel's right-looking trailing update re-reads and re-writes every 8x8
+//     block of the tile once per panel step (6 loads + 2 stores per pair of DMMAs: shared-memory-bandwidth bound, a third
+//     of its cycles); here the column block about to be factored is brought up to date in one go,
+//     C(bi, bj) -= sum_{k<bj} L(bi, k) L(bj, k)^T, accumulators in registers, 3 loads per pair of DMMAs, one
+//     read-modify-write per block, by all 8 warps (two blocks of the column per warp sharing the B fragments);
+//   * the pivot chain of each 8x8 diagonal block runs on reciprocals (LDL^T style): next pivot = fma(-u^2, 1/piv, d),
+//     one MUFU.RCP64H + 3 dependent FMAs + 1 per column; the rsqrt that scales the stored column is computed beside the
+//     chain, not on it.  The row owners of the diagonal block take the common path (no divergent branch on the critical
+//     warp) and the non-positive-pivot report leaves the pivot loop;
+//   * the two 64x64 diagonal halves of W are built one block row at a time, by warps 4-7, WHILE warps 0-3 run the
+//     (row-owner, 128-thread) panel step of the next 8 columns:  W_ii = inv(L_ii),  W_ij = -W_ii * sum_{k=j}^{i-1} L_ik W_kj
+//     needs only rows of L that are already final, and restricted to its own half a block row costs less than a panel
+//     step.  W lives transposed in the free upper triangle of the tile (W(r,c) at S[r*LD+c], its diagonal in dinv[]),
+//     so L stays intact underneath.  The off-diagonal half W21 = -W22 (L21 W11) follows the last panel step as two fully
+//     unrolled DMMA stages on all 8 warps;
+//   * tile load and both stores move 16 B per thread-access.
+// Measured (tools/microbench/potrf_phases.cu, B200): 47 us -> see DESIGN.md.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);  // seed is good to ~2^-20 (tools/microbench/rsqrt_check.cu); cubic step -> 2^-60
+  return fma(y, fma(e, e, e), y);
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// element (rr, cc) of the lower-triangular 8x8 block W_oo in the mirrored storage
+__device__ __forceinline__ double wdiag(const double* S, const double* dinv, int o, int rr, int cc) {
+  double v = 0.0;
+  if (rr > cc) v = S[(o + rr) * LD + o + cc];
+  if (rr == cc) v = dinv[o + rr];
+  return v;
+}
+
+// Block row i of W restricted to the block columns [jmin, i), by `nw` warps (this warp = wl) sharing the named barrier
+// `bar_id`.  Deliberately light on the FP64 pipe (one block at a time per warp, two accumulator chains): the pipe is
+// shared with the panel warps, whose dependent chain is the critical path -- denser DMMA issue here was measured to slow
+// the whole step down.
+__device__ __forceinline__ void w_block_row(double* S, const double* dinv, int i, int jmin, int wl, int nw, int lane, int bar_id) {
+  const int g = lane >> 2, t = lane & 3, o = 8 * i;
+  if (wl == nw - 1 && lane < 8) {  // W_ii by substitution, one thread per column
+    double Lb[8][8], w[8];
+    const int col = lane;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int k = 0; k < a; ++k) Lb[a][k] = S[(o + k) * LD + o + a];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      double s = (rr == col) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < rr; ++k) s = fma(-Lb[rr][k], w[k], s);
+      w[rr] = s * dinv[o + rr];
+    }
+#pragma unroll
+    for (int rr = 1; rr < 8; ++rr)
+      if (rr > col) S[(o + rr) * LD + o + col] = w[rr];
+  }
+  __syncwarp();
+  // T_j = sum_{k=j}^{i-1} L_ik W_kj, parked where W_ij will live
+  for (int j = jmin + wl; j < i; j += nw) {
+    const int oj = 8 * j;
+    double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+    {
+      const double a0 = S[(oj + t) * LD + o + g];
+      const double a1 = S[(oj + 4 + t) * LD + o + g];
+      const double b0 = wdiag(S, dinv, oj, t, g);
+      const double b1 = wdiag(S, dinv, oj, 4 + t, g);
+      dmma884p(c0, c1, a0, b0);
+      dmma884p(e0, e1, a1, b1);
+    }
+    for (int k = j + 1; k < i; ++k) {
+      const int ok = 8 * k;
+      const double a0 = S[(ok + t) * LD + o + g];
+      const double a1 = S[(ok + 4 + t) * LD + o + g];
+      const double b0 = S[(ok + t) * LD + oj + g];
+      const double b1 = S[(ok + 4 + t) * LD + oj + g];
+      dmma884p(c0, c1, a0, b0);
+      dmma884p(e0, e1, a1, b1);
+    }
+    S[(o + g) * LD + oj + 2 * t] = c0 + e0;
+    S[(o + g) * LD + oj + 2 * t + 1] = c1 + e1;
+  }
+  named_bar(bar_id, nw * 32);  // W_ii (and every T_j) visible to the warps of this group
+  const double wa0 = wdiag(S, dinv, o, g, t);
+  const double wa1 = wdiag(S, dinv, o, g, 4 + t);
+  for (int j = jmin + wl; j < i; j += nw) {
+    const int oj = 8 * j;
+    double c0 = 0.0, c1 = 0.0;
+    const double b0 = S[(o + t) * LD + oj + g];
+    const double b1 = S[(o + 4 + t) * LD + oj + g];
+    dmma884p(c0, c1, wa0, b0);
+    dmma884p(c0, c1, wa1, b1);
+    __syncwarp();  // every lane has read T_j before it is overwritten
+    S[(o + g) * LD + oj + 2 * t] = -c0;
+    S[(o + g) * LD + oj + 2 * t + 1] = -c1;
+  }
+}
+
+// The off-diagonal half of W once both 64x64 diagonal halves are inverted: W21 = -W22 (L21 W11), 8 warps, everything
+// unrolled (no branches between the loads and the DMMAs: this phase has the pipe to itself and is meant to fill it).
+//   stage A: warp w owns block row i = 8 + w:    T_ij = sum_{k=j}^{7} L_ik W_kj      (A fragments shared along the row)
+//   stage B: warp w owns block column j = w:     W_ij = -sum_{k=8}^{i} W_ik T_kj     (B fragments shared along the column)
+__device__ __forceinline__ void w_lower_left(double* S, const double* dinv, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  {
+    const int o = 64 + 8 * warp;
+    double c0[8], c1[8], e0[8], e1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c0[j] = c1[j] = e0[j] = e1[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ok = 8 * k;
+      const double a0 = S[(ok + t) * LD + o + g];
+      const double a1 = S[(ok + 4 + t) * LD + o + g];
+#pragma unroll
+      for (int j = 0; j <= k; ++j) {
+        const int oj = 8 * j;
+        double b0, b1;
+        if (j == k) {
+          b0 = wdiag(S, dinv, oj, t, g);
+          b1 = wdiag(S, dinv, oj, 4 + t, g);
+        } else {
+          b0 = S[(ok + t) * LD + oj + g];
+          b1 = S[(ok + 4 + t) * LD + oj + g];
+        }
+        dmma884p(c0[j], c1[j], a0, b0);
+        dmma884p(e0[j], e1[j], a1, b1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      S[(o + g) * LD + 8 * j + 2 * t] = c0[j] + e0[j];
+      S[(o + g) * LD + 8 * j + 2 * t + 1] = c1[j] + e1[j];
+    }
+  }
+  __syncthreads();
+  {
+    const int oj = 8 * warp;
+    double c0[8], c1[8], e0[8], e1[8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) c0[ii] = c1[ii] = e0[ii] = e1[ii] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int ok = 64 + 8 * kk;
+      const double b0 = S[(ok + t) * LD + oj + g];
+      const double b1 = S[(ok + 4 + t) * LD + oj + g];
+#pragma unroll
+      for (int ii = kk; ii < 8; ++ii) {
+        const int o = 64 + 8 * ii;
+        double a0, a1;
+        if (ii == kk) {
+          a0 = wdiag(S, dinv, o, g, t);
+          a1 = wdiag(S, dinv, o, g, 4 + t);
+        } else {
+          a0 = S[(o + g) * LD + ok + t];
+          a1 = S[(o + g) * LD + ok + 4 + t];
+        }
+        dmma884p(c0[ii], c1[ii], a0, b0);
+        dmma884p(e0[ii], e1[ii], a1, b1);
+      }
+    }
+    __syncthreads();  // every T block has been read by every warp that needs it
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const int o = 64 + 8 * ii;
+      S[(o + g) * LD + oj + 2 * t] = -(c0[ii] + e0[ii]);
+      S[(o + g) * LD + oj + 2 * t + 1] = -(c1[ii] + e1[ii]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double* __restrict__ Wbase, size_t w_batch_stride, int J,
+                                                             double* __restrict__ logdet, int* __restrict__ info) {
+  extern __shared__ __align__(16) double S[];  // S[c*LD + r]: L in the lower triangle, W^T strictly above the diagonal
+  double* dinv = S + TILE * LD;               // 1 / L[r][r] = W[r][r]
+  double* red = dinv + TILE;
+  __shared__ int fail_col;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double* tile = L.tile(b, J, J);
+  double* Wt = Wbase + (size_t)b * w_batch_stride + (size_t)J * TT;
+
+  PT(0);
+  if (tid == 0) fail_col = 0x7fffffff;
+#pragma unroll 16
+  for (int e2 = tid; e2 < TT / 2; e2 += 256) {
+    const double2 v = reinterpret_cast<const double2*>(tile)[e2];
+    int r, c;
+    tile_rc(2 * e2, r, c);
+    S[c * LD + r] = v.x;
+    S[(c + 1) * LD + r] = v.y;
+  }
+  __syncthreads();
+
+  PT(1);
+  for (int j0 = 0; j0 < TILE; j0 += 8) {
+    const int bj = j0 >> 3;
+    if (bj > 0) {
+      // left-looking update of column block bj: block rows bi0 = bj + warp and bi0 + 8
+      const int bi0 = bj + warp;
+      if (bi0 < 16) {
+        const bool two = bi0 + 8 < 16;
+        const int R0 = 8 * bi0, R1 = two ? R0 + 64 : R0;
+        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;  // block 0: two chains
+        double u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;  // block 1
+        // fragments of trip k + 1 are in flight while the DMMAs of trip k issue
+        double bb0 = S[t * LD + j0 + g], bb1 = S[(4 + t) * LD + j0 + g];
+        double a00 = S[t * LD + R0 + g], a01 = S[(4 + t) * LD + R0 + g];
+        double a10 = S[t * LD + R1 + g], a11 = S[(4 + t) * LD + R1 + g];
+        for (int k = 0; k < bj; ++k) {
+          const int cn = 8 * (k + 1 < bj ? k + 1 : k);
+          const double nb0 = S[(cn + t) * LD + j0 + g];
+          const double nb1 = S[(cn + 4 + t) * LD + j0 + g];
+          const double n00 = S[(cn + t) * LD + R0 + g];
+          const double n01 = S[(cn + 4 + t) * LD + R0 + g];
+          const double n10 = S[(cn + t) * LD + R1 + g];
+          const double n11 = S[(cn + 4 + t) * LD + R1 + g];
+          dmma884p(p0, p1, a00, bb0);
+          dmma884p(q0, q1, a01, bb1);
+          dmma884p(u0, u1, a10, bb0);
+          dmma884p(v0, v1, a11, bb1);
+          bb0 = nb0; bb1 = nb1; a00 = n00; a01 = n01; a10 = n10; a11 = n11;
+        }
+        double* c0p = &S[(j0 + 2 * t) * LD + R0 + g];
+        c0p[0] -= p0 + q0;
+        c0p[LD] -= p1 + q1;
+        if (two) {
+          double* c1p = &S[(j0 + 2 * t) * LD + R1 + g];
+          c1p[0] -= u0 + v0;
+          c1p[LD] -= u1 + v1;
+        }
+      }
+      __syncthreads();  // the column block is up to date for its row owners
+    }
+    if (j0 == 8) PT(2);
+    if (warp < 4) {
+      const int r = tid;  // row owner
+      double p[8];
+      double d[8][8];
+      const bool active = r >= j0;
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int k = 0; k <= i; ++k) d[i][k] = S[(j0 + k) * LD + (j0 + i)];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p[k] = S[(j0 + k) * LD + r];
+      }
+      named_bar(1, 128);  // every row owner has read the diagonal block before its rows are overwritten
+      if (active) {
+        double dv[8], tm[8][8];
+        int failj = 8;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const double piv = d[jj][jj];
+          if (!(piv > 0.0) && failj == 8) failj = jj;
+          const double rc = fast_rcp(piv);
+          dv[jj] = fast_rsqrt(piv);
+#pragma unroll
+          for (int j2 = jj + 1; j2 < 8; ++j2) {
+            d[j2][j2] = fma(-(d[j2][jj] * d[j2][jj]), rc, d[j2][j2]);  // the pivot chain: one FMA behind the reciprocal
+            tm[j2][jj] = d[j2][jj] * rc;
+#pragma unroll
+            for (int i = j2 + 1; i < 8; ++i) d[i][j2] = fma(-d[i][jj], tm[j2][jj], d[i][j2]);
+          }
+        }
+        // every row, the 8 rows of the diagonal block included (their entries right of the diagonal are never stored):
+        // u_j = a_j - sum_{k<j} u_k (u_jk / piv_k),  L_rj = u_j / sqrt(piv_j)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          double v = p[jj];
+#pragma unroll
+          for (int k = 0; k < jj; ++k) v = fma(-p[k], tm[jj][k], v);
+          p[jj] = v;
+        }
+        const int within = r - j0;  // >= 8 below the diagonal block
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k <= within) S[(j0 + k) * LD + r] = p[k] * dv[k];
+        if (r == j0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dinv[j0 + k] = dv[k];
+          if (failj < 8) atomicMin(&fail_col, j0 + failj);
+        }
+      }
+    } else if (j0 > 0) {
+      w_block_row(S, dinv, bj - 1, bj - 1 < 8 ? 0 : 8, warp - 4, 4, lane, 2);
+    }
+    __syncthreads();
+    if (j0 == 8) PT(3);
+  }
+  PT(4);
+  w_block_row(S, dinv, 15, 8, warp, 8, lane, 0);  // ends the inversion of the lower-right 64x64 half
+  w_lower_left(S, dinv, warp, lane);
+
+  if (tid < TILE) {
+    double v = log(S[tid * LD + tid]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+  }
+  __syncthreads();
+  PT(5);
+  if (tid == 0) {
+    logdet[b] += 2.0 * (((red[0] + red[1]) + red[2]) + red[3]);
+    if (fail_col != 0x7fffffff && info[b] == 0) info[b] = J * TILE + fail_col + 1;
+  }
+  PT(6);
+  PT(7);
+#pragma unroll 8
+  for (int e2 = tid; e2 < TT / 2; e2 += 256) {
+    int r, c;
+    tile_rc(2 * e2, r, c);
+    double2 l, w;
+    l.x = (r >= c) ? S[c * LD + r] : 0.0;
+    l.y = (r >= c + 1) ? S[(c + 1) * LD + r] : 0.0;
+    const double2 wt = *reinterpret_cast<const double2*>(&S[r * LD + c]);  // 16-byte aligned: LD and c are even
+    w.x = (r > c) ? wt.x : (r == c ? dinv[r] : 0.0);
+    w.y = (r > c + 1) ? wt.y : (r == c + 1 ? dinv[r] : 0.0);
+    reinterpret_cast<double2*>(tile)[e2] = l;
+    reinterpret_cast<double2*>(Wt)[e2] = w;
+  }
+  PT(8);
+  PT(9);
+}
+
+static int g_potrf_impl = 1;  // 0: first-generation kernel (right-looking, W after L); 1: left-looking, W rows overlapped
+void set_potrf_impl(int v) { g_potrf_impl = v; }
+
 cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int batch, double* logdet,
                               int* info) {
   static bool configured_dev[64] = {false};  // function attributes are per device
@@ -312,9 +645,14 @@ cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_b
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(potrf_tile_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
+    if (e != cudaSuccess) return e;
     configured = true;
   }
-  potrf_tile_kernel<<<batch, 256, POTRF_SMEM, st>>>(L, W, w_batch_stride, J, logdet, info);
+  if (g_potrf_impl == 1)
+    potrf_tile_kernel2<<<batch, 256, POTRF_SMEM, st>>>(L, W, w_batch_stride, J, logdet, info);
+  else
+    potrf_tile_kernel<<<batch, 256, POTRF_SMEM, st>>>(L, W, w_batch_stride, J, logdet, info);
   return cudaGetLastError();
 }
 

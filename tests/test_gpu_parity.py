@@ -92,11 +92,21 @@ def test_potrf_small_batch_schedules(lmm):
         ctx.set_option("outer_block", 0)
 
 
-def test_potrf_reports_non_pd(lmm):
+@pytest.mark.parametrize("potrf_impl", [0, 1])
+def test_potrf_reports_non_pd(lmm, potrf_impl):
+    """LAPACK `info` semantics (1-based index of the first non-positive pivot), every diagonal-tile kernel; the pivot sits
+    in the second tile and in the middle of an 8-column panel step."""
     A = np.eye(200)
     A[150, 150] = -1.0
-    L, logdet, info = lmm.potrf_batched(np.stack([np.eye(200), A]))
-    assert info[0] == 0 and info[1] == 151
+    B = np.eye(200)
+    B[5, 5] = 0.0
+    ctx = lmm.default_context()
+    ctx.set_option("potrf_impl", potrf_impl)
+    try:
+        L, logdet, info = lmm.potrf_batched(np.stack([np.eye(200), A, B]))
+    finally:
+        ctx.set_option("potrf_impl", 1)
+    assert info[0] == 0 and info[1] == 151 and info[2] == 6
 
 
 @pytest.mark.parametrize(
@@ -183,6 +193,46 @@ def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer, small)
         ctx.set_option("streams", 4)
         ctx.set_option("outer_block", 0)
         ctx.set_option("gemm_small", 74)
+
+
+@pytest.mark.parametrize("potrf_impl,direct,small,lookahead", [(0, 0, 74, 2), (1, 1, 4096, 2), (1, 2, 4096, 2), (0, 2, 4096, 0), (1, 0, 0, 1),
+                                                                (1, 1, 4096, 1), (1, 2, 74, 2), (1, 0, 4096, 0)])
+def test_panel_kernel_variants_agree(lmm, potrf_impl, direct, small, lookahead):
+    """Both diagonal-tile kernels (inverse after the factor / inverse block rows overlapped with the panel steps) and the three
+    direct-GEMM variants (plain / register-ring prefetch with 4 or 8 slices per tile, zero blocks of W skipped) give the
+    same factor: batched OILMM (N = 1100, batch 3) and a single general-ILMM factor (batch 1, right-looking schedule)."""
+    N, p, m, Ns = 1100, 5, 3, 70
+    x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=78, means=True)
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    ctx = lmm.default_context()
+    ctx.set_option("potrf_impl", potrf_impl)
+    ctx.set_option("gemm_direct", direct)
+    ctx.set_option("gemm_small", small)
+    ctx.set_option("lookahead", lookahead)
+    try:
+        fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+        post, lp = lmm.posterior(fx, y, with_logpdf=True)
+        assert rel(lp, o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
+        M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
+        Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
+        np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+        np.testing.assert_allclose(V, Vr, rtol=RTOL)
+        # general ILMM: one (mN x mN) factor, batch 1
+        rng = np.random.default_rng(5)
+        N2, p2, m2 = 500, 4, 3
+        x2 = np.sort(rng.uniform(0, 6, N2))
+        H = rng.uniform(0, 1, (p2, m2))
+        fs2 = [o.GP(o.Kernel(o.SE, 1.0, 1.3)), o.GP(o.Kernel(o.MATERN32)), o.GP(o.Kernel(o.MATERN52, 0.7, 0.8))]
+        y2 = rng.standard_normal(N2 * p2)
+        f2 = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs2]), H)
+        lp2 = lmm.logpdf(f2(lmm.MOInputIsotopicByOutputs(x2, p2), 0.05), y2)
+        assert rel(lp2, o.ilmm_logpdf(fs2, H, x2, 0.05, y2)) < RTOL
+    finally:
+        ctx.set_option("potrf_impl", 1)
+        ctx.set_option("gemm_direct", 2)
+        ctx.set_option("gemm_small", 74)
+        ctx.set_option("lookahead", 2)
 
 
 def test_distance_form_option(lmm):
