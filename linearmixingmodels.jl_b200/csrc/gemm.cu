@@ -437,6 +437,17 @@ __global__ void __launch_bounds__(256) gemm_direct2_kernel(GemmArgs g) {
   for (int i = 0; i < RB; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  double2 cv[RB][2];  // UPDATE: the C fragments travel with the first operand fragments, not after the last DMMA
+  if (MODE == GEMM_UPDATE) {
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int cg = (j == 0 ? nb0 : nb1) * 2 + (t4 >> 1);
+        cv[i][j] = *reinterpret_cast<const double2*>(Ctile + (cg << 9) + ((slice * RB + i) << 5) + (g4 << 2) + ((t4 & 1) << 1));
+      }
+  }
   double ra[PF][RB], rb[PF][2];
 #pragma unroll
   for (int u = 0; u < PF; ++u) {
@@ -471,7 +482,6 @@ __global__ void __launch_bounds__(256) gemm_direct2_kernel(GemmArgs g) {
     }
   }
   if (MODE == GEMM_TRSM) __syncthreads();  // every warp of this CTA has finished reading its rows of C(I,J)
-  const int g4 = lane >> 2, t4 = lane & 3;
 #pragma unroll
   for (int i = 0; i < RB; ++i)
 #pragma unroll
@@ -481,7 +491,7 @@ __global__ void __launch_bounds__(256) gemm_direct2_kernel(GemmArgs g) {
       double2* ptr = reinterpret_cast<double2*>(Ctile + off);
       double2 v;
       if (MODE == GEMM_UPDATE) {
-        v = *ptr;
+        v = cv[i][j];
         v.x -= acc[i][j][0];
         v.y -= acc[i][j][1];
       } else {

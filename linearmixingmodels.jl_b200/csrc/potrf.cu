@@ -18,9 +18,16 @@ namespace lmm {
 
 #ifdef LMM_POTRF_TIMING
 __device__ long long g_potrf_clk[16];
+__device__ long long g_potrf_acc[8];  // per-step sums: [0] column update, [1] panel (warp 0), [2] its wait at the step barrier, [3] W block row (warp 4)
 #define PT(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_potrf_clk[k] = clock64(); } while (0)
+#define ACC_DECL long long acc_t0 = 0
+#define ACC_START(tidsel) do { if (blockIdx.x == 0 && threadIdx.x == (tidsel)) acc_t0 = clock64(); } while (0)
+#define ACC_STOP(tidsel, k) do { if (blockIdx.x == 0 && threadIdx.x == (tidsel)) g_potrf_acc[k] += clock64() - acc_t0; } while (0)
 #else
 #define PT(k) do { } while (0)
+#define ACC_DECL do { } while (0)
+#define ACC_START(tidsel) do { } while (0)
+#define ACC_STOP(tidsel, k) do { } while (0)
 #endif
 
 constexpr int LD = 132;
@@ -502,46 +509,67 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double*
   __syncthreads();
 
   PT(1);
+  ACC_DECL;
   for (int j0 = 0; j0 < TILE; j0 += 8) {
     const int bj = j0 >> 3;
+    ACC_START(0);
     if (bj > 0) {
-      // left-looking update of column block bj: block rows bi0 = bj + warp and bi0 + 8
+      // left-looking update of column block bj: block rows bi0 = bj + warp and bi0 + 8.  A dependent DMMA costs ~100
+      // cycles, so chain length is what matters: a warp with two blocks runs 4 chains of bj DMMAs; a warp with one block
+      // (always the case once bj >= 8, when the chains are longest) splits k in two halves, 4 chains of bj/2.
       const int bi0 = bj + warp;
       if (bi0 < 16) {
         const bool two = bi0 + 8 < 16;
         const int R0 = 8 * bi0, R1 = two ? R0 + 64 : R0;
-        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;  // block 0: two chains
-        double u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;  // block 1
+        const int trips = two ? bj : (bj + 1) >> 1;
+        const int koff = two ? 0 : 8 * trips;  // column offset of the second pair of chains
+        const int klast = 8 * (bj - 1);
+        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;  // block 0 (first half of k)
+        double u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;  // block 1, or block 0's second half of k
         // fragments of trip k + 1 are in flight while the DMMAs of trip k issue
+        int c2 = koff < klast ? koff : klast;
         double bb0 = S[t * LD + j0 + g], bb1 = S[(4 + t) * LD + j0 + g];
         double a00 = S[t * LD + R0 + g], a01 = S[(4 + t) * LD + R0 + g];
-        double a10 = S[t * LD + R1 + g], a11 = S[(4 + t) * LD + R1 + g];
-        for (int k = 0; k < bj; ++k) {
-          const int cn = 8 * (k + 1 < bj ? k + 1 : k);
+        double bb2 = S[(c2 + t) * LD + j0 + g], bb3 = S[(c2 + 4 + t) * LD + j0 + g];
+        double a10 = S[(c2 + t) * LD + R1 + g], a11 = S[(c2 + 4 + t) * LD + R1 + g];
+        for (int k = 0; k < trips; ++k) {
+          const int cn = 8 * (k + 1 < trips ? k + 1 : k);
+          const int c2n = cn + koff < klast ? cn + koff : klast;
           const double nb0 = S[(cn + t) * LD + j0 + g];
           const double nb1 = S[(cn + 4 + t) * LD + j0 + g];
           const double n00 = S[(cn + t) * LD + R0 + g];
           const double n01 = S[(cn + 4 + t) * LD + R0 + g];
-          const double n10 = S[(cn + t) * LD + R1 + g];
-          const double n11 = S[(cn + 4 + t) * LD + R1 + g];
+          const double nb2 = S[(c2n + t) * LD + j0 + g];
+          const double nb3 = S[(c2n + 4 + t) * LD + j0 + g];
+          const double n10 = S[(c2n + t) * LD + R1 + g];
+          const double n11 = S[(c2n + 4 + t) * LD + R1 + g];
           dmma884p(p0, p1, a00, bb0);
           dmma884p(q0, q1, a01, bb1);
-          dmma884p(u0, u1, a10, bb0);
-          dmma884p(v0, v1, a11, bb1);
-          bb0 = nb0; bb1 = nb1; a00 = n00; a01 = n01; a10 = n10; a11 = n11;
+          if (two || 8 * k + koff <= klast) {  // warp-uniform; false only for the odd trip out of a split k range
+            dmma884p(u0, u1, a10, bb2);
+            dmma884p(v0, v1, a11, bb3);
+          }
+          bb0 = nb0; bb1 = nb1; a00 = n00; a01 = n01;
+          bb2 = nb2; bb3 = nb3; a10 = n10; a11 = n11;
         }
         double* c0p = &S[(j0 + 2 * t) * LD + R0 + g];
-        c0p[0] -= p0 + q0;
-        c0p[LD] -= p1 + q1;
         if (two) {
+          c0p[0] -= p0 + q0;
+          c0p[LD] -= p1 + q1;
           double* c1p = &S[(j0 + 2 * t) * LD + R1 + g];
           c1p[0] -= u0 + v0;
           c1p[LD] -= u1 + v1;
+        } else {
+          c0p[0] -= (p0 + q0) + (u0 + v0);
+          c0p[LD] -= (p1 + q1) + (u1 + v1);
         }
       }
       __syncthreads();  // the column block is up to date for its row owners
     }
+    ACC_STOP(0, 0);
     if (j0 == 8) PT(2);
+    ACC_START(0);
+    ACC_START(128);
     if (warp < 4) {
       const int r = tid;  // row owner
       double p[8];
@@ -595,7 +623,11 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double*
     } else if (j0 > 0) {
       w_block_row(S, dinv, bj - 1, bj - 1 < 8 ? 0 : 8, warp - 4, 4, lane, 2);
     }
+    ACC_STOP(0, 1);
+    ACC_STOP(128, 3);
+    ACC_START(0);
     __syncthreads();
+    ACC_STOP(0, 2);
     if (j0 == 8) PT(3);
   }
   PT(4);

@@ -31,6 +31,11 @@ int main() {
       printf("impl %d rep %d: %.1f us total; phase cycles:", impl, rep, ms * 1e3);
       for (int k = 0; k < 9; ++k) printf(" %lld", clk[k + 1] - clk[k]);
       printf(" (sum %lld)\n", clk[9] - clk[0]);
+      if (impl == 1) {
+        long long acc[8]; cudaMemcpyFromSymbol(acc, g_potrf_acc, sizeof acc);
+        printf("    step sums: column update %lld | panel (warp 0) %lld | warp 0 waiting at the step barrier %lld | W block rows (warp 4) %lld\n", acc[0], acc[1], acc[2], acc[3]);
+        long long z[8] = {0}; cudaMemcpyToSymbol(g_potrf_acc, z, sizeof z);
+      }
     }
     outL[impl].resize(h.size()); outW[impl].resize(h.size());
     cudaMemcpy(outL[impl].data(), dL, h.size() * 8, cudaMemcpyDeviceToHost);
