@@ -91,7 +91,12 @@ const char* lmm_version(void);
  *   "gemm_impl"       0 = cp.async ring + CTA barrier; 1 / 2 = TMA bulk copies + full/empty mbarrier ring with
  *                     16- / 32-column stages (default 2)          [process-wide]
  *   "gemm_small"      grids of at most this many tiles use the latency-optimised direct kernel (default 74,
- *                     0 = never)                                  [process-wide] */
+ *                     0 = never)                                  [process-wide]
+ *   "gemm_direct"     variant of that direct kernel: 0 = plain (4 slices per tile, one step of prefetch), 1 / 2 =
+ *                     register-ring prefetch with 4 / 8 slices per tile and the zero blocks of the triangular
+ *                     inverse skipped (default 2)                 [process-wide]
+ *   "potrf_impl"      diagonal-tile kernel: 0 = first generation (right-looking, inverse after the factor),
+ *                     1 = left-looking with the inverse built beside the panel steps (default) [process-wide] */
 int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value);
 /* Counters since context creation: kernels launched by this library, bytes copied H2D / D2H. */
 int lmm_ctx_counters(lmm_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
