@@ -143,43 +143,87 @@ cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t
   // passes over the trailing matrix) once the trailing GEMMs dominate (measured: tools/bench_batch1.py)
   const int ob = ctx->outer_block_user ? ctx->outer_block : (nt <= 32 ? 1 : nt <= 72 ? 2 : nt <= 112 ? 3 : 4);
   const int nblk = (nt + ob - 1) / ob;
+  // "panel_split": only the DIAGONAL tile of the next column is updated on the panel stream before its factorisation;
+  // the rest of that column -- needed by the TRSM that follows the diagonal-tile kernel, not by the kernel itself -- is
+  // updated on a second high-priority stream X2 meanwhile.
+  const bool split = ctx->panel_split != 0;
   cudaError_t e;
-  while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
+  while ((int)ctx->blk_ev.size() < 2 * nblk + 2 + 2 * nt + 2) {
     cudaEvent_t ev;
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     ctx->blk_ev.push_back(ev);
   }
-  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream;
+  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream, X2 = ctx->xchg_stream;
   cudaEvent_t* evX = ctx->blk_ev.data();          // panel(b) done on X
   cudaEvent_t* evY = ctx->blk_ev.data() + nblk;   // trailing update from block b done on Y
+  cudaEvent_t* evT = ctx->blk_ev.data() + 2 * nblk + 2;  // split: TRSM of column j done on X
+  cudaEvent_t* evU = evT + nt;                           // split: rest-of-column update(s) up to column j done on X2
+  int last_u = -1;                                       // latest evU that X has not waited for yet
   GemmArgs g{};
   g.A = operand(L); g.B = operand(L); g.C = operand(L);
   g.W = W; g.w_batch_stride = wstride; g.sym = 1;
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  if (split && (e = cudaStreamWaitEvent(X2, ctx->ev_fork, 0)) != cudaSuccess) return e;
   for (int b = 0; b < nblk; ++b) {
     const int s0 = b * ob, s1 = (s0 + ob < nt) ? s0 + ob : nt;
     if (b >= 1) {
       // every earlier update of this block column (Y launches up to b-2) must have landed
       if (b >= 2 && (e = cudaStreamWaitEvent(X, evY[b - 2], 0)) != cudaSuccess) return e;
-      g.i0 = s0; g.j0 = s0; g.k0 = s0 - ob; g.k1 = s0;
-      if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
-      ++ctx->launches;
+      g.k0 = s0 - ob; g.k1 = s0;
+      if (!split) {
+        g.i0 = s0; g.j0 = s0;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+      } else {
+        g.i0 = s0; g.j0 = s0;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, 1, batch)) != cudaSuccess) return e;
+        ++ctx->launches;
+        if (s0 + 1 < nt) {  // all other tiles of the block columns (the symmetric-skip leaves row s0 to the launch above)
+          if (b >= 2 && (e = cudaStreamWaitEvent(X2, evY[b - 2], 0)) != cudaSuccess) return e;
+          if ((e = cudaStreamWaitEvent(X2, evT[s0 - 1], 0)) != cudaSuccess) return e;
+          g.i0 = s0 + 1; g.j0 = s0;
+          if ((e = launch_gemm(X2, GEMM_UPDATE, g, s1 - s0, nt - s0 - 1, batch)) != cudaSuccess) return e;
+          ++ctx->launches;
+          if ((e = cudaEventRecord(evU[s0], X2)) != cudaSuccess) return e;
+          last_u = s0;
+        }
+      }
       ctx->timings[6] += 1;
     }
     for (int jj = s0; jj < s1; ++jj) {
       if (jj > s0) {
-        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
-        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
-        ++ctx->launches;
+        g.k0 = s0; g.k1 = jj;
+        if (!split) {
+          g.i0 = jj; g.j0 = jj;
+          if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
+          ++ctx->launches;
+        } else {
+          g.i0 = jj; g.j0 = jj;
+          if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, 1, batch)) != cudaSuccess) return e;
+          ++ctx->launches;
+          if (jj + 1 < nt) {
+            if ((e = cudaStreamWaitEvent(X2, evT[jj - 1], 0)) != cudaSuccess) return e;
+            g.i0 = jj + 1; g.j0 = jj;
+            if ((e = launch_gemm(X2, GEMM_UPDATE, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
+            ++ctx->launches;
+            if ((e = cudaEventRecord(evU[jj], X2)) != cudaSuccess) return e;
+            last_u = jj;
+          }
+        }
       }
       if ((e = launch_potrf_tile(X, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
       ++ctx->launches;
       if (jj + 1 < nt) {
+        if (split && last_u >= 0) {
+          if ((e = cudaStreamWaitEvent(X, evU[last_u], 0)) != cudaSuccess) return e;
+          last_u = -1;
+        }
         g.i0 = jj + 1; g.j0 = jj;
         if ((e = launch_gemm(X, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
         ++ctx->launches;
+        if (split && (e = cudaEventRecord(evT[jj], X)) != cudaSuccess) return e;
       }
     }
     if ((e = cudaEventRecord(evX[b], X)) != cudaSuccess) return e;
@@ -195,6 +239,10 @@ cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t
   if ((e = cudaStreamWaitEvent(ctx->stream, evX[nblk - 1], 0)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
+  if (split) {  // every X2 launch is followed by a TRSM on X that waited for it; joined explicitly all the same
+    if ((e = cudaEventRecord(ctx->ev_join[1], X2)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0)) != cudaSuccess) return e;
+  }
   return cudaSuccess;
 }
 

@@ -78,6 +78,7 @@ struct lmm_ctx {
   cudaStream_t panel_stream = nullptr, update_stream = nullptr;
   std::vector<cudaEvent_t> blk_ev;
   int lookahead = 2;  // 0 off, 1 left-looking K-split, 2 right-looking (default)
+  int panel_split = 0;  // right-looking schedule: next column's diagonal tile on the panel stream, the rest of it on a second one
   // one large factor (general ILMM, batch 1) partitioned row-cyclically over the ranks of the communicator
   int partition_ilmm = 0;
   int partition_now = 0;  // set by the callers whose factorisation is replicated on every rank (ILMM joint factor)
