@@ -321,7 +321,7 @@ def main():
         "e2e": {"value": 1e3 / (e2e_ms / K), "unit": UNIT, "h2d_bytes_per_step": int((hh1 - hh0) / K), "d2h_bytes_per_step": int((dh1 - dh0) / K)},
         "gpu_launches": int(launches.item()),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "batched blocked Cholesky (gemm_tile_kernel DMMA updates + potrf_tile_kernel + TRSM-as-GEMM)",
+        "roofline": {"bound": "tensor", "kernel": "batched blocked Cholesky (gemm_tile_kernel_v2 DMMA updates + TRSM-as-GEMM + potrf_tile_kernel2)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(p, N, mloc),
                      "peak_source": peak_src, "flops_per_rank_step": chol_flops,
                      "whole_eval_tflops": (m * (N ** 3 / 3.0 + 2.0 * N * N) + 4.0 * p * m * N) / (ms_per_step * 1e-3) / 1e12 / world},
