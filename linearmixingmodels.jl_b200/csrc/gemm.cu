@@ -228,11 +228,28 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   // W(J) is LOWER triangular, so output column block nb only needs the k-blocks <= nb -- a 2 x 4 warp grid would leave the
   // warps of the low column groups idle, so the TRSM uses 8(M) x 1(N) warps, warp tile 16 x 128 = acc[2][16] (the same
   // storage, viewed differently), and every warp skips the same zero blocks: 120 of 256 block products.
+  // UPDATE starts its accumulators from C(I,J) and feeds NEGATED B fragments (one sign flip per fragment, 4 per 32 DMMAs),
+  // so the tile's read latency hides behind the first TMA stage and the epilogue is a store: the CTA retires -- and the
+  // SM's next tile starts -- one L2/HBM round trip earlier than with a read-modify-write at the end.
+  const int g4 = lane >> 2, t4 = lane & 3;
   double acc[8][4][2];
+  if constexpr (MODE == GEMM_UPDATE) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+    for (int mb = 0; mb < 8; ++mb)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int nb = 0; nb < 4; ++nb) {
+        const int cg = wn * 8 + nb * 2 + (t4 >> 1);
+        const int off = (cg << 9) + ((wm * 8 + mb) << 5) + (g4 << 2) + ((t4 & 1) << 1);
+        const double2 v = *reinterpret_cast<const double2*>(Ctile + off);
+        acc[mb][nb][0] = v.x;
+        acc[mb][nb][1] = v.y;
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
   double (*acct)[16][2] = reinterpret_cast<double (*)[16][2]>(&acc[0][0][0]);  // TRSM view: [2][16][2]
 
   for (int q = 0; q < nchunks; ++q) {
@@ -262,7 +279,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
 #pragma unroll
         for (int mb = 0; mb < 8; ++mb) a[mb] = sa[ks * 512 + mb * 32];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) bq[nb] = sb[ks * 512 + nb * 32];
+        for (int nb = 0; nb < 4; ++nb) bq[nb] = -sb[ks * 512 + nb * 32];
 #pragma unroll
         for (int mb = 0; mb < 8; ++mb)
 #pragma unroll
@@ -282,7 +299,6 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
     }
   }
 
-  const int g4 = lane >> 2, t4 = lane & 3;
   if constexpr (MODE == GEMM_TRSM) {
     // in place: the whole tile C(I,J) went through the stage ring above (every chunk consumed by every warp), so a CTA
     // barrier is all that separates the last read from the first write
@@ -305,11 +321,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
       for (int nb = 0; nb < 4; ++nb) {
         const int cg = wn * 8 + nb * 2 + (t4 >> 1);
         const int off = (cg << 9) + ((wm * 8 + mb) << 5) + (g4 << 2) + ((t4 & 1) << 1);
-        double2* ptr = reinterpret_cast<double2*>(Ctile + off);
-        double2 v = *ptr;
-        v.x -= acc[mb][nb][0];
-        v.y -= acc[mb][nb][1];
-        *ptr = v;
+        double2 v;
+        v.x = acc[mb][nb][0];
+        v.y = acc[mb][nb][1];
+        *reinterpret_cast<double2*>(Ctile + off) = v;
       }
     }
   }
