@@ -15,10 +15,9 @@ if __name__ == "__main__":
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     for N in Ns:
         for potrf_impl, direct, split in ((0, 0, 0), (0, 2, 0), (1, 0, 0), (1, 2, 0), (1, 2, 1)):
-            if True:
-                ctx.set_option("potrf_impl", potrf_impl)
-                ctx.set_option("gemm_direct", direct)
-                ctx.set_option("panel_split", split)
-                ms, _, ld = run(ctx, N, batch, reps=3)
-                print(json.dumps({"N": N, "batch": batch, "potrf_impl": potrf_impl, "gemm_direct": direct, "panel_split": split, "chol_ms": round(ms, 3),
-                                  "tflops": round(batch * N ** 3 / 3.0 / (ms * 1e-3) / 1e12, 2), "logdet0": ld}), flush=True)
+            ctx.set_option("potrf_impl", potrf_impl)
+            ctx.set_option("gemm_direct", direct)
+            ctx.set_option("panel_split", split)
+            ms, _, ld = run(ctx, N, batch, reps=3)
+            print(json.dumps({"N": N, "batch": batch, "potrf_impl": potrf_impl, "gemm_direct": direct, "panel_split": split, "chol_ms": round(ms, 3),
+                              "tflops": round(batch * N ** 3 / 3.0 / (ms * 1e-3) / 1e12, 2), "logdet0": ld}), flush=True)
