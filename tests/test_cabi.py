@@ -33,6 +33,17 @@ def test_library_exports_every_declared_symbol():
     assert exported == names
 
 
+def test_documented_options_match_the_library():
+    """Every tunable include/lmm.h documents is accepted by lmm_ctx_set_option's dispatcher and vice versa (the header is
+    the only place a caller of the C ABI learns about them)."""
+    hdr = open(os.path.join(ROOT, "include", "lmm.h")).read()
+    block = hdr[hdr.index("Tunables (key, value)"):hdr.index("int lmm_ctx_set_option")]
+    documented = set(re.findall(r'^ \*   "([a-z_]+)"', block, flags=re.M))
+    src = open(os.path.join(ROOT, "linearmixingmodels.jl_b200", "csrc", "api.cu")).read()
+    accepted = set(re.findall(r'k == "([a-z_]+)"', src))
+    assert documented == accepted, (sorted(documented - accepted), sorted(accepted - documented))
+
+
 def test_struct_layout_matches_header():
     assert C.sizeof(_lib.GpDesc) == 48
     assert _lib.GpDesc.variance.offset == 8 and _lib.GpDesc.mean_const.offset == 24 and _lib.GpDesc.ard.offset == 32
