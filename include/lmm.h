@@ -85,6 +85,11 @@ const char* lmm_version(void);
  *                     updated on the panel stream, the rest of the column on a second high-priority stream (two
  *                     more cross-stream events per column: measured 1-3 % slower up to N=8192, 0.7 % faster at
  *                     N=16384).  Default 0.
+ *   "pdl"             programmatic dependent launch along the batch-1 panel chain: the diagonal-tile kernel and the
+ *                     small direct GEMMs are launched with programmatic stream serialisation, wait on
+ *                     `griddepcontrol.wait` before their first read and release their successor before their
+ *                     final stores (N=2048: -12 %, 4096: -5 %, 8192: -3 %).  Default 1; 0 = plain launches.
+ *                                                                 [process-wide]
  *   "partition_ilmm"  the joint factor of a general ILMM (one large matrix, factored by every rank of the
  *                     communicator on identical inputs) is partitioned row-cyclically over the ranks: 1 = one
  *                     ncclAllGather of the current block column per step, panels redundant; 2 = the panel TRSM

@@ -177,6 +177,8 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "lookahead") {
     if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "lookahead must be 0, 1 (left-looking, K-split) or 2 (right-looking)");
     ctx->lookahead = (int)value;
+  } else if (k == "pdl") {
+    set_pdl(value != 0.0);
   } else if (k == "panel_split") {
     ctx->panel_split = value != 0.0;
   } else if (k == "nccl_small_ctas") {  // takes effect at lmm_comm_init

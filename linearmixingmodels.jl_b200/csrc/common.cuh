@@ -136,4 +136,25 @@ __device__ __forceinline__ double sqdist(const double* a, const double* b, int D
   return d2;
 }
 
+// Programmatic dependent launch (the panel chain of a batch-1 factorisation is three dependent small kernels per tile
+// column): a kernel launched with launch_pdl() may be scheduled as soon as its predecessor in the stream executes
+// pdl_trigger(); it must execute pdl_wait() before touching anything the predecessor wrote (pdl_wait returns when the
+// predecessor grid has completed and its writes are visible).  Both are no-ops for a plain <<<>>> launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace lmm

@@ -426,6 +426,7 @@ __global__ void __launch_bounds__(256) gemm_direct2_kernel(GemmArgs g) {
   if (MODE == GEMM_UPDATE && kb >= g.k1) return;
   double* Ctile = g.C.tile(b, I, J);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();  // everything below reads what the previous kernel of the panel chain wrote
   const double* Asrc;
   const double* Bsrc;
   int nsteps, nb0, nb1, lim0;
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(256) gemm_direct2_kernel(GemmArgs g) {
       }
     }
   }
+  pdl_trigger();  // the next kernel of the chain may be scheduled while this one stores
   if (MODE == GEMM_TRSM) __syncthreads();  // every warp of this CTA has finished reading its rows of C(I,J)
 #pragma unroll
   for (int i = 0; i < RB; ++i)
@@ -519,6 +521,10 @@ __global__ void __launch_bounds__(256) gemm_direct2_kernel(GemmArgs g) {
 
 static int g_gemm_small = 74;  // grids of at most this many tiles take the latency-optimised kernel (0 = never)
 void set_gemm_small_threshold(int tiles) { g_gemm_small = tiles; }
+
+static bool g_pdl = true;   // programmatic dependent launch along the panel chain (direct kernels + diagonal-tile kernel)
+void set_pdl(int v) { g_pdl = v != 0; }
+bool pdl_enabled() { return g_pdl; }
 
 static int g_gemm_direct = 2;  // 0: plain direct kernel (4 slices, one step of prefetch); 1: register-ring prefetch, 4 slices; 2: ring, 8 slices
 void set_gemm_direct(int v) { g_gemm_direct = v; }
@@ -552,9 +558,9 @@ cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols,
     dim3 gs((unsigned)ncols * split, (unsigned)nrows, (unsigned)batch);
     if (g_gemm_direct == 2) {
       if (mode == GEMM_UPDATE)
-        gemm_direct2_kernel<GEMM_UPDATE, 2, 8><<<gs, 256, 0, st>>>(a);
+        return launch_pdl(g_pdl, gemm_direct2_kernel<GEMM_UPDATE, 2, 8>, gs, dim3(256), 0, st, a);
       else
-        gemm_direct2_kernel<GEMM_TRSM, 2, 8><<<gs, 256, 0, st>>>(a);
+        return launch_pdl(g_pdl, gemm_direct2_kernel<GEMM_TRSM, 2, 8>, gs, dim3(256), 0, st, a);
     } else if (g_gemm_direct == 1) {
       if (mode == GEMM_UPDATE)
         gemm_direct2_kernel<GEMM_UPDATE, 4, 6><<<gs, 256, 0, st>>>(a);

@@ -41,6 +41,8 @@ struct GemmArgs {
 enum { GEMM_UPDATE = 0, GEMM_TRSM = 1 };
 cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch);
 void set_gemm_small_threshold(int tiles);  // grids of <= tiles tiles use the latency-optimised direct kernel (default 74; 0 = off)
+void set_pdl(int v);       // 1: programmatic dependent launch along the batch-1 panel chain (default 1)
+bool pdl_enabled();
 void set_gemm_direct(int v);  // direct-kernel variant: 0 plain, 1 register-ring prefetch with 4 slices per tile, 2 with 8 slices
 void set_gemm_impl(int impl);  // 0: cp.async ring + CTA barrier; 1/2: TMA bulk + full/empty mbarrier ring, 16/32-column stages (2 = default)
 

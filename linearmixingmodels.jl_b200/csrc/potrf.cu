@@ -498,6 +498,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double*
 
   PT(0);
   if (tid == 0) fail_col = 0x7fffffff;
+  pdl_wait();  // the tile was written by the previous kernel of the panel chain
 #pragma unroll 16
   for (int e2 = tid; e2 < TT / 2; e2 += 256) {
     const double2 v = reinterpret_cast<const double2*>(tile)[e2];
@@ -647,6 +648,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double*
     if (fail_col != 0x7fffffff && info[b] == 0) info[b] = J * TILE + fail_col + 1;
   }
   PT(6);
+  pdl_trigger();  // the column's TRSM may be scheduled while L and W are stored
   PT(7);
 #pragma unroll 8
   for (int e2 = tid; e2 < TT / 2; e2 += 256) {
@@ -682,7 +684,7 @@ cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_b
     configured = true;
   }
   if (g_potrf_impl == 1)
-    potrf_tile_kernel2<<<batch, 256, POTRF_SMEM, st>>>(L, W, w_batch_stride, J, logdet, info);
+    return launch_pdl(pdl_enabled(), potrf_tile_kernel2, dim3(batch), dim3(256), POTRF_SMEM, st, L, W, w_batch_stride, J, logdet, info);
   else
     potrf_tile_kernel<<<batch, 256, POTRF_SMEM, st>>>(L, W, w_batch_stride, J, logdet, info);
   return cudaGetLastError();

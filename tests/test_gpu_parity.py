@@ -80,18 +80,21 @@ def test_potrf_small_batch_schedules(lmm):
     Lr = sla.cholesky(A, lower=True)
     ctx = lmm.default_context()
     try:
-        for la, ob, split in ((0, 0, 0), (1, 0, 0), (1, 5, 0), (2, 0, 0), (2, 1, 0), (2, 3, 0), (2, 7, 0), (2, 0, 1), (2, 1, 1), (2, 3, 1), (2, 18, 1)):
+        for la, ob, split, pdl in ((0, 0, 0, 0), (1, 0, 0, 0), (1, 5, 0, 0), (2, 0, 0, 0), (2, 1, 0, 0), (2, 3, 0, 0), (2, 7, 0, 0), (2, 0, 1, 0),
+                                   (2, 1, 1, 0), (2, 3, 1, 0), (2, 18, 1, 0), (2, 0, 0, 1), (2, 1, 0, 1), (2, 3, 1, 1), (0, 0, 0, 1), (1, 2, 0, 1)):
             ctx.set_option("lookahead", la)
             ctx.set_option("outer_block", ob)
             ctx.set_option("panel_split", split)
+            ctx.set_option("pdl", pdl)
             L, logdet, info = lmm.potrf_batched(A)
             assert info[0] == 0
-            np.testing.assert_allclose(L[0], Lr, rtol=1e-10, atol=1e-12, err_msg=f"lookahead={la} outer_block={ob} panel_split={split}")
+            np.testing.assert_allclose(L[0], Lr, rtol=1e-10, atol=1e-12, err_msg=f"lookahead={la} outer_block={ob} panel_split={split} pdl={pdl}")
             assert rel(logdet[0], 2 * np.sum(np.log(np.diag(Lr)))) < 1e-11
     finally:
         ctx.set_option("lookahead", 2)
         ctx.set_option("outer_block", 0)
         ctx.set_option("panel_split", 0)
+        ctx.set_option("pdl", 1)
 
 
 @pytest.mark.parametrize("potrf_impl", [0, 1])
