@@ -322,6 +322,138 @@ function AbstractGPs.logpdf(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOI
     return out[]
 end
 
+# --- mean_and_var on PRIOR latents   replaces src/oilmm.jl:57-76 (OILMM) and src/ilmm.jl:108-130 (general H) ---------
+function AbstractGPs.mean_and_var(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    n = length(x) * fx.x.out_dim
+    M = Vector{Float64}(undef, n); V = Vector{Float64}(undef, n)
+    check(ccall((:lmm_oilmm_prior_mean_and_var, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Ptr{Float64}, Ptr{Float64}),
+        ctx(), descs, length(descs), X, length(x), D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), size(H, 1), Float64(σ²),
+        fx.x.out_dim, M, V))
+    return M, V
+end
+function AbstractGPs.mean_and_var(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    n = length(x) * fx.x.out_dim
+    M = Vector{Float64}(undef, n); V = Vector{Float64}(undef, n)
+    check(ccall((:lmm_ilmm_prior_mean_and_var, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Cint, Ptr{Float64}, Ptr{Float64}),
+        ctx(), descs, length(descs), X, length(x), D, H, size(H, 1), Float64(σ²), fx.x.out_dim, M, V))
+    return M, V
+end
+AbstractGPs.mean(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}}) = mean_and_var(fx)[1]     # src/ilmm.jl:142
+AbstractGPs.var(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}}) = mean_and_var(fx)[2]      # src/ilmm.jl:145
+AbstractGPs.mean(fx::FiniteGP{<:PosteriorOILMM}) = mean_and_var(fx)[1]
+AbstractGPs.var(fx::FiniteGP{<:PosteriorOILMM}) = mean_and_var(fx)[2]
+
+# --- general ILMM: posterior replaces src/ilmm.jl:184-198 (one (mN)² factor; POST_ILMM handle) and rand src/ilmm.jl:78-87 ---
+const PosteriorILMM = ILMM{<:IndependentMOGP{<:Vector{<:DeviceLatentPosterior}},<:Matrix{Float64}}
+function AbstractGPs.posterior(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    h = Ref{Ptr{Cvoid}}(C_NULL); info = Ref{Cint}(0)
+    check(ccall((:lmm_ilmm_posterior, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
+         Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(x), D, H, size(H, 1), Float64(σ²), Vector{Float64}(y), fx.x.out_dim, h, C_NULL, info))
+    owner = DevicePosterior(h[])
+    return ILMM(IndependentMOGP([DeviceLatentPosterior(owner, i - 1, f) for (i, f) in enumerate(fs.fs)]), H)
+end
+# every lmm_post_* entry point dispatches on the handle's kind, so the posterior methods above serve both aliases
+for f in (:mean_and_var, :mean_and_cov, :cov, :mean, :var)
+    @eval AbstractGPs.$f(fx::FiniteGP{<:PosteriorILMM}) = invoke(AbstractGPs.$f, Tuple{FiniteGP{<:PosteriorOILMM}}, fx)
+end
+function AbstractGPs.rand(rng::AbstractRNG, fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    m, p, N = length(descs), size(H, 1), length(x)
+    zl = randn(rng, N * m); zn = randn(rng, N * p)       # latent draws (src/ilmm.jl:84), then the noise (:86)
+    out = Vector{Float64}(undef, N * p); il = Ref{Cint}(-1)
+    check(ccall((:lmm_ilmm_rand, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Cint,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, m, X, N, D, H, p, Float64(σ²), fx.x.out_dim, zl, zn, out, il))
+    return out
+end
+# rand(rng, fx, n) / rand(fx) (src/ilmm.jl:90-106): columns are independent draws in the reference's order
+AbstractGPs.rand(rng::AbstractRNG, fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, n::Int) = hcat((rand(rng, fx) for _ in 1:n)...)
+AbstractGPs.rand(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}}) = rand(Random.GLOBAL_RNG, fx)
+
+# --- IndependentMOGP: posterior replaces src/independent_mogp.jl:119-126, rand :85-98 ------------------------------
+function AbstractGPs.posterior(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOInputIsotopicByOutputs,<:Diagonal{<:Real,<:Fill}},
+                               y::AbstractVector{<:Real})
+    X, D = points(ft.x.x)
+    descs = GpDesc.(ft.f.fs)
+    h = Ref{Ptr{Cvoid}}(C_NULL); il = Ref{Cint}(-1)
+    check(ccall((:lmm_imogp_posterior, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Float64, Ptr{Float64}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(ft.x.x), D, Float64(ft.Σy[1]), Vector{Float64}(y), ft.x.out_dim, h, C_NULL, il))
+    owner = DevicePosterior(h[])
+    return IndependentMOGP([DeviceLatentPosterior(owner, i - 1, f) for (i, f) in enumerate(ft.f.fs)])
+end
+function AbstractGPs.rand(rng::AbstractRNG, ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOInputIsotopicByOutputs,<:Diagonal{<:Real,<:Fill}})
+    X, D = points(ft.x.x)
+    descs = GpDesc.(ft.f.fs)
+    N = length(ft.x.x); m = length(descs)
+    z = randn(rng, N * m); out = Vector{Float64}(undef, N * m); il = Ref{Cint}(-1)
+    check(ccall((:lmm_imogp_rand, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, m, X, N, D, Float64(ft.Σy[1]), ft.x.out_dim, z, out, il))
+    return out
+end
+# by-features inputs (src/independent_mogp.jl:134-229): the permutation the reference builds with
+# `vec(reshape(1:pN, N, p)')` comes from lmm_reorder_indices; y is permuted, the by-outputs method called, results permuted back
+function reorder(N::Int, p::Int, direction::Int)
+    idx = Vector{Int64}(undef, N * p)
+    check(ccall((:lmm_reorder_indices, liblmm), Cint, (Cint, Cint, Cint, Ptr{Int64}), N, p, direction, idx))
+    return idx .+ 1
+end
+
+# --- hyper-parameter sweep (BASELINE config 5): n_sweep logpdfs of the same data, every latent's inverse lengthscale scaled ---
+function logpdf_sweep(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real}, scales::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    out = Vector{Float64}(undef, length(scales)); il = Ref{Cint}(-1)
+    check(ccall((:lmm_oilmm_logpdf_sweep, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
+         Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(x), D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), size(H, 1), Float64(σ²),
+        Vector{Float64}(y), fx.x.out_dim, Vector{Float64}(scales), length(scales), out, il))
+    return out
+end
+
+# --- missing data (not in the reference, examples/oilmm_and_ilmm.ipynb:112): NaN entries of y are unobserved ---------
+function posterior_missing(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs = GpDesc.(fs.fs)
+    Hm = Matrix{Float64}(collect(H))
+    h = Ref{Ptr{Cvoid}}(C_NULL); lp = Ref{Float64}(0.0); nobs = Ref{Cint}(0); info = Ref{Cint}(0)
+    check(ccall((:lmm_ilmm_masked_posterior, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
+         Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(x), D, Hm, size(Hm, 1), Float64(σ²), Vector{Float64}(y), fx.x.out_dim, h, lp, nobs, info))
+    return DevicePosterior(h[]), lp[], Int(nobs[])
+end
+
+# --- tunables and teardown ------------------------------------------------------------------------------------------
+set_option(key::AbstractString, value::Real) = check(ccall((:lmm_ctx_set_option, liblmm), Cint, (Ptr{Cvoid}, Cstring, Float64), ctx(), key, Float64(value)))
+version() = unsafe_string(ccall((:lmm_version, liblmm), Cstring, ()))
+function __init__()
+    atexit() do
+        CTX[] == C_NULL || ccall((:lmm_ctx_destroy, liblmm), Cint, (Ptr{Cvoid},), CTX[])
+        CTX[] = C_NULL
+    end
+end
+
 # --- serialisable posterior: the on-disk form of a DevicePosterior -----------------------------------
 save_posterior(p::DevicePosterior, path::AbstractString) = check(ccall((:lmm_post_save, liblmm), Cint, (Ptr{Cvoid}, Cstring), p.handle, path))
 function load_posterior(path::AbstractString)

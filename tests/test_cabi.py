@@ -44,6 +44,79 @@ def test_documented_options_match_the_library():
     assert documented == accepted, (sorted(documented - accepted), sorted(accepted - documented))
 
 
+def _split_top(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_shim_ccalls_match_the_header():
+    """The Julia shim cannot be executed here (no Julia), so its ccall signatures are checked mechanically against
+    include/lmm.h: same symbol, same number of arguments, pointer / int / double / string in the same positions, and one
+    value passed per declared argument."""
+    hdr = open(os.path.join(ROOT, "include", "lmm.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(lmm_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", hdr):
+        args = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        kinds = []
+        for a in args:
+            if a in ("void", ""):
+                continue
+            if "*" in a:
+                kinds.append("str" if re.match(r"const\s+char\s*\*", a) else "ptr")
+            elif re.match(r"(const\s+)?double\b", a):
+                kinds.append("double")
+            else:
+                kinds.append("int")
+        protos[m.group(1)] = kinds
+    jl = open(os.path.join(ROOT, "linearmixingmodels.jl_b200", "julia", "LinearMixingModelsB200.jl")).read()
+    jl = re.sub(r"#=.*?=#", "", jl, flags=re.S)
+    jl = "\n".join(line.split("#")[0] if not line.lstrip().startswith("#") else "" for line in jl.split("\n"))
+    seen = set()
+    for m in re.finditer(r"ccall\(\(:(lmm_[a-z0-9_]+), liblmm\),", jl):
+        name = m.group(1)
+        assert name in protos, f"{name} is not declared in lmm.h"
+        # take the balanced argument list of this ccall
+        i = m.start() + len("ccall(")
+        depth, j = 1, i
+        while depth:
+            ch = jl[j]
+            depth += ch in "({["
+            depth -= ch in ")}]"
+            j += 1
+        parts = _split_top(jl[i:j - 1])
+        types = _split_top(parts[2].strip()[1:-1]) if parts[2].strip() != "()" else []
+        values = parts[3:]
+        kinds = []
+        for t in types:
+            if t.startswith("Ptr{"):
+                kinds.append("ptr")
+            elif t == "Cstring":
+                kinds.append("str")
+            elif t == "Float64":
+                kinds.append("double")
+            elif t in ("Cint", "Int32"):
+                kinds.append("int")
+            else:
+                raise AssertionError(f"{name}: unexpected ccall type {t}")
+        assert kinds == protos[name], f"{name}: shim {kinds} vs header {protos[name]}"
+        assert len(values) == len(kinds), f"{name}: {len(values)} values for {len(kinds)} declared arguments"
+        seen.add(name)
+    assert len(seen) >= 25
+
+
 def test_struct_layout_matches_header():
     assert C.sizeof(_lib.GpDesc) == 48
     assert _lib.GpDesc.variance.offset == 8 and _lib.GpDesc.mean_const.offset == 24 and _lib.GpDesc.ard.offset == 32
