@@ -12,7 +12,9 @@ is a NumPy/SciPy Float64 restatement (LAPACK ``dpotrf``/``dtrtrs`` through OpenB
 family Julia's ``cholesky`` and ``\\`` reach) pinned by exactly those identities and known answers
 (``tests/test_oracle_identities.py``), by a long-double/dense cross-check and by 40-digit mpmath values of BASELINE
 config 1 computed from the dense multi-output-GP definition with no shared code (``tests/golden/make_golden_mp.py``,
-``tests/golden/c1_truth_mp.npz``: logpdf, posterior marginals, three logpdf derivatives).
+``tests/golden/c1_truth_mp.npz``: logpdf, posterior marginals, three logpdf derivatives) and of a general ILMM with
+2-D inputs, ARD, Matern52 / Exponential / RationalQuadratic latents and constant means (``make_golden_mp2.py``,
+``c2_truth_mp.npz``).
 
 Every function cites the reference lines it follows (paths relative to /root/reference).  The
 arithmetic of AbstractGPs 0.3.x / KernelFunctions 0.10.x / Distances 0.10.x is not vendored in the

@@ -95,3 +95,32 @@ def test_cuda_path_matches_extended_precision_truth():
     assert abs(g["sigma2"] - float(T["dlogpdf_dsigma2"])) <= 1e-8 * abs(float(T["dlogpdf_dsigma2"]))
     assert abs(g["inv_lengthscale"][0] - float(T["dlogpdf_dinv_lengthscale0"])) <= 1e-8 * abs(float(T["dlogpdf_dinv_lengthscale0"]))
     assert abs(g["variance"][0] - float(T["dlogpdf_dvariance0"])) <= 1e-8 * abs(float(T["dlogpdf_dvariance0"]))
+
+
+# ---- second 40-digit truth (tests/golden/c2_truth_mp.npz, make_golden_mp2.py): a general ILMM with a dense non-orthogonal H,
+# 2-D inputs, an ARDTransform, Matern52 / Exponential / RationalQuadratic latents and constant means
+T2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_truth_mp.npz"))
+
+
+def _c2_latents():
+    return [o.GP(o.Kernel(o.MATERN52, 1.2, 0.9, ard=tuple(T2["ard0"])), 0.5), o.GP(o.Kernel(o.EXPONENTIAL, 0.8, 1.4), -1.0),
+            o.GP(o.Kernel(o.RATQUAD, 1.0, 0.6, param=1.7), 0.0)]
+
+
+def test_oracle_general_ilmm_matches_extended_precision_truth():
+    """The oracle's dense multi-output GP (what test/ilmm.jl compares the ILMM with) reproduces the 40-digit values to
+    rounding; its restatement of the reference's projected ILMM (src/ilmm.jl:61-68,150-198) agrees to the size of the
+    reference's own 1e-9 regulariser in `project` -- that offset belongs to the reference's algorithm, not to the oracle."""
+    fs, x, xs, H, y, s2 = _c2_latents(), T2["x"], T2["xs"], T2["H"], T2["y"], float(T2["sigma2"])
+    assert o.dense_mogp_logpdf(fs, H, x, s2, y) == pytest.approx(float(T2["logpdf"]), rel=1e-13)
+    M, V = o.dense_mogp_posterior_mean_and_var(fs, H, x, s2, y, xs, s2)
+    np.testing.assert_allclose(M, T2["post_mean"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(V, T2["post_var"], rtol=1e-11)
+    assert o.ilmm_logpdf(fs, H, x, s2, y) == pytest.approx(float(T2["logpdf"]), rel=1e-9)
+    M2, V2 = o.ilmm_mean_and_var(o.ilmm_posterior(fs, H, x, s2, y), H, xs, s2)
+    np.testing.assert_allclose(M2, T2["post_mean"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(V2, T2["post_var"], rtol=1e-8)
+    _, g = o.ilmm_logpdf_grad(fs, H, x, s2, y)
+    assert g["sigma2"] == pytest.approx(float(T2["dlogpdf_dsigma2"]), rel=1e-8)
+    assert g["ard"][0][1] == pytest.approx(float(T2["dlogpdf_dard0_1"]), rel=1e-7)
+    assert g["H"][1, 2] == pytest.approx(float(T2["dlogpdf_dH12"]), rel=1e-7)
