@@ -3,12 +3,16 @@
 // every panel TRSM and every triangular vector solve into tensor-core GEMMs / plain GEMVs.
 // One CTA (8 warps) per latent; the 128x128 tile lives in shared memory, column-major with
 // ld = 132 (conflict-free DMMA fragment loads: column stride = 8 banks).
+//
+// Two kernels.  potrf_tile_kernel (first generation, "potrf_impl" = 0):
 //   phase C: 16 steps of 8 columns: 8x8 diagonal block factored in registers (rsqrt pivots,
 //            redundantly by every row-owner thread -> no intra-block syncs), panel rows solved
 //            in registers, trailing update of the tile on the FP64 tensor pipe (m8n8k4 DMMA).
 //   phase W: in-place recursive inverse of the lower triangle: 8x8 diagonal blocks by
 //            substitution, then 4 doubling levels  W21 = -W22 (L21 W11)  as DMMA block products;
 //            the temporary L21*W11 lives in the (free) mirrored upper block.
+// potrf_tile_kernel2 (default): left-looking column updates, reciprocal pivot chain, W built beside
+// the panel steps -- described above its definition.
 // Latency-bound by design (it sits on the critical path of each tile column; the host runs
 // several latent groups on separate streams so the other SMs keep doing trailing updates).
 #include "common.cuh"
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* 
 //     so L stays intact underneath.  The off-diagonal half W21 = -W22 (L21 W11) follows the last panel step as two fully
 //     unrolled DMMA stages on all 8 warps;
 //   * tile load and both stores move 16 B per thread-access.
-// Measured (tools/microbench/potrf_phases.cu, B200): 47 us -> see DESIGN.md.
+// Measured (tools/microbench/potrf_phases.cu, B200): 47.1 us -> 36.9 us per tile (profiles/r01_panel_chain.md).
 __device__ __forceinline__ double fast_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
