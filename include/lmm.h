@@ -184,6 +184,11 @@ int lmm_imogp_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* fs, int m, const doub
  * mean/var); for an IndependentMOGP posterior: src/independent_mogp.jl:50-57; ILMM: src/ilmm.jl:122-129. */
 int lmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean,
                           double* var);
+/* mean_and_var(get_latent_gp(post).fs[i](x*, σ²)): ONE PosteriorGP latent (global index i, resident on this rank)
+ * evaluated on its own -- the per-latent call src/oilmm.jl:61 makes; AbstractGPs FiniteGP{<:PosteriorGP}:
+ * mean = m_i + K(x*,x) α_i, var = k(x*,x*) - colsumsq(C.U'^{-1} K(x,x*)) + σ².  mean / var: Ns doubles. */
+int lmm_post_latent_mean_and_var(lmm_post* post, int i, const double* xs, int Ns, double sigma2,
+                                 double* mean, double* var);
 /* mean_and_cov(post(x*, σ²)) / cov: dense (p Ns) x (p Ns) column-major output, by outputs
  * (src/ilmm.jl:132-139,147; src/independent_mogp.jl:60-63 + Σy).  mean is nullable. */
 int lmm_post_mean_and_cov(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean,

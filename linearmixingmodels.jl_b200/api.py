@@ -745,6 +745,18 @@ def posterior(fx: FiniteGP, y, with_logpdf: bool = False):
 def mean_and_var(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
     """`mean_and_var(fx)`: src/oilmm.jl:57-76, src/ilmm.jl:122-129, src/independent_mogp.jl:50-57."""
     f = fx.f
+    if isinstance(f, PosteriorGP):
+        # one latent of a posterior on its own, `mean_and_var(get_latent_gp(post).fs[i](x*, σ²))` -- the per-latent
+        # call src/oilmm.jl:61 makes (AbstractGPs FiniteGP{<:PosteriorGP})
+        pts = _points(fx.x)
+        Ns = int(pts.shape[0])
+        M, V = np.zeros(Ns), np.zeros(Ns)
+        c = f._owner.ctx
+        c.check(c.lib.lmm_post_latent_mean_and_var(f._owner.handle, f.index, ptr(pts), Ns, fx.sigma2, ptr(M), ptr(V)))
+        return M, V
+    if isinstance(f, GP):  # AbstractGPs `mean_and_var(f(x, σ²))` for a prior GP: (m(x), diag K + σ²)
+        Ns = _npoints(fx.x)
+        return np.full(Ns, f.mean_const), np.full(Ns, f.kernel.variance + fx.sigma2)
     owner = _post_owner(fx)
     needs_device = owner is not None or isinstance(f, ILMM)
     ctx = _ctx_of(fx) if needs_device else None

@@ -380,12 +380,13 @@ namespace lmm_host {
 
 // Latent posterior marginals at xs for the resident latents: ML/VL [nloc][nspad] on the device.
 // mean*_i = m_i + K(x*,x) α_i ; var*_i = k(x*,x*) - colsumsq(L_i^{-1} K(x,x*))   (AbstractGPs)
-int post_latent_marginals(lmm_post* post, const double* d_xspad, int Ns, int nts, double* d_ML, double* d_VL) {
+// `first` / `count` select a sub-range of the resident latents (default: all of them); d_ML / d_VL rows are relative to it.
+int post_latent_marginals(lmm_post* post, const double* d_xspad, int Ns, int nts, double* d_ML, double* d_VL, int first, int count) {
   lmm_ctx* ctx = post->ctx;
   cudaStream_t st = ctx->stream;
-  const int nloc = post->nloc(), nt = post->nt;
+  const int nloc = count < 0 ? post->nloc() - first : count, nt = post->nt;
   const size_t nspad = (size_t)nts * TILE;
-  if (nloc == 0) return LMM_OK;
+  if (nloc <= 0) return LMM_OK;
   const size_t per_lat = (size_t)nts * nt * TT * sizeof(double);
   size_t fr = 0, tot = 0;
   CU(cudaMemGetInfo(&fr, &tot));
@@ -398,11 +399,12 @@ int post_latent_marginals(lmm_post* post, const double* d_xspad, int Ns, int nts
   for (int c0 = 0; c0 < nloc; c0 += chunk) {
     const int nb = (c0 + chunk <= nloc) ? chunk : nloc - c0;
     TiledRect V{b_V.as<double>(), nts, nt, (size_t)nts * nt * TT};
-    TiledSym Lc{L.base + (size_t)c0 * L.batch_stride, nt, L.batch_stride};
-    const double* Wc = post->d_W + (size_t)c0 * post->wstride();
-    const LatentParams* dp = post->d_params + c0;
+    const int g0 = first + c0;  // index among the resident latents
+    TiledSym Lc{L.base + (size_t)g0 * L.batch_stride, nt, L.batch_stride};
+    const double* Wc = post->d_W + (size_t)g0 * post->wstride();
+    const LatentParams* dp = post->d_params + g0;
     CU(launch_kmat_cross(st, V, nb, d_xspad, Ns, post->d_xpad, post->N, post->D, dp, ctx->distance_form));
-    CU(launch_rect_gemv(st, V, post->d_alpha + (size_t)c0 * post->npad(), post->npad(), d_ML + (size_t)c0 * nspad, nspad, dp, 1, nb));
+    CU(launch_rect_gemv(st, V, post->d_alpha + (size_t)g0 * post->npad(), post->npad(), d_ML + (size_t)c0 * nspad, nspad, dp, 1, nb));
     ctx->launches += 2;
     CU(trsm_right_lt(ctx, V, Lc, Wc, post->wstride(), nb));
     CU(launch_rect_rowsumsq(st, V, d_VL + (size_t)c0 * nspad, nspad, dp, nb));
@@ -469,6 +471,34 @@ extern "C" int lmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, d
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
   ctx->timings[0] = ms;
   ctx->timings[5] = ms;
+  return LMM_OK;
+}
+
+// mean_and_var(post.f.fs[i](x*, σ²)): one PosteriorGP latent evaluated on its own (AbstractGPs FiniteGP{<:PosteriorGP}
+// mean_and_var = (m_i + K*x α_i, k** - colsumsq(L_i^{-1} K x*) + σ²)); src/oilmm.jl:61 calls exactly this per latent.
+extern "C" int lmm_post_latent_mean_and_var(lmm_post* post, int i, const double* xs, int Ns, double sigma2, double* mean, double* var) {
+  if (!post || !xs || Ns <= 0 || !mean || !var) return LMM_E_ARG;
+  lmm_ctx* ctx = post->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  if (post->joint()) return ctx->fail(LMM_E_UNSUPPORTED, "a joint posterior has no independent latent posteriors");
+  if (i < post->lo || i >= post->hi) return ctx->fail(LMM_E_ARG, "latent not resident on this rank");
+  cudaStream_t st = ctx->stream;
+  const int nts = ntiles(Ns);
+  const size_t nspad = (size_t)nts * TILE;
+  DevBuf b_xs, b_ML, b_VL;
+  CU(b_xs.alloc(ctx, nspad * post->D * sizeof(double)));
+  CU(cudaMemsetAsync(b_xs.p, 0, nspad * post->D * sizeof(double), st));
+  CU(copy_in(ctx, b_xs.as<double>(), xs, (size_t)Ns * post->D));
+  CU(b_ML.alloc(ctx, nspad * sizeof(double)));
+  CU(b_VL.alloc(ctx, nspad * sizeof(double)));
+  int rc = post_latent_marginals(post, b_xs.as<double>(), Ns, nts, b_ML.as<double>(), b_VL.as<double>(), i - post->lo, 1);
+  if (rc) return rc;
+  CU(launch_add_scalar(st, b_VL.as<double>(), (size_t)Ns, sigma2));
+  ++ctx->launches;
+  CU(copy_out(ctx, mean, b_ML.p, (size_t)Ns * sizeof(double)));
+  CU(copy_out(ctx, var, b_VL.p, (size_t)Ns * sizeof(double)));
+  CU(cudaStreamSynchronize(st));
   return LMM_OK;
 }
 

@@ -6,6 +6,8 @@ import os
 import numpy as np
 import pytest
 
+from _tol import assert_isapprox
+
 from oracle import lmm_oracle as o
 
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_oilmm.npz"))
@@ -42,7 +44,7 @@ def test_cuda_path_matches_golden():
     assert abs(lmm.logpdf(fx, G["y"]) - float(G["logpdf"])) <= 1e-9 * abs(float(G["logpdf"]))
     post = lmm.posterior(fx, G["y"])
     M, V = lmm.mean_and_var(post(mo(G["xs"]), 0.1))
-    np.testing.assert_allclose(M, G["post_mean"], rtol=1e-9, atol=1e-11)
+    assert_isapprox(M, G["post_mean"], 1e-9)
     np.testing.assert_allclose(V, G["post_var"], rtol=1e-9)
     got = lmm.logpdf(post(mo(G["xs"]), 0.1), G["ys"])
     assert abs(got - float(G["post_logpdf"])) <= 1e-9 * abs(float(G["post_logpdf"]))
@@ -56,7 +58,7 @@ def test_cuda_path_matches_golden():
     fxg = fg(mo(G["x"]), 0.1)
     assert abs(lmm.logpdf(fxg, G["y"]) - float(G["ilmm_logpdf"])) <= 1e-9 * abs(float(G["ilmm_logpdf"]))
     Mg, Vg = lmm.mean_and_var(lmm.posterior(fxg, G["y"])(mo(G["xs"]), 0.1))
-    np.testing.assert_allclose(Mg, G["ilmm_post_mean"], rtol=1e-9, atol=1e-11)
+    assert_isapprox(Mg, G["ilmm_post_mean"], 1e-9)
     np.testing.assert_allclose(Vg, G["ilmm_post_var"], rtol=1e-9)
 
 
@@ -89,7 +91,7 @@ def test_cuda_path_matches_extended_precision_truth():
     lp = lmm.logpdf(fx, G["y"])
     assert abs(lp - float(T["logpdf"])) <= 1e-9 * abs(float(T["logpdf"]))
     M, V = lmm.mean_and_var(lmm.posterior(fx, G["y"])(mo(G["xs"]), 0.1))
-    np.testing.assert_allclose(M, T["post_mean"], rtol=1e-9, atol=1e-11)
+    assert_isapprox(M, T["post_mean"], 1e-9)
     np.testing.assert_allclose(V, T["post_var"], rtol=1e-9)
     _, g = lmm.logpdf_and_gradient(fx, G["y"])
     assert abs(g["sigma2"] - float(T["dlogpdf_dsigma2"])) <= 1e-8 * abs(float(T["dlogpdf_dsigma2"]))

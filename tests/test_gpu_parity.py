@@ -6,6 +6,7 @@ import pytest
 import scipy.linalg as sla
 
 from oracle import lmm_oracle as o
+from _tol import assert_isapprox, relnorm
 
 pytestmark = pytest.mark.gpu
 
@@ -139,17 +140,17 @@ def test_oilmm_logpdf_posterior_marginals(lmm, N, p, m, Ns, D, means):
     M, V = lmm.mean_and_var(post(xsin, s2))
     opost = o.oilmm_posterior(om, x, s2, y)
     Mr, Vr = o.oilmm_mean_and_var(opost, xs, s2)
-    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    assert_isapprox(M, Mr, RTOL)
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
     # PosteriorGP fields (α, C, δ)
     g0 = post.f.fs[m - 1]
-    np.testing.assert_allclose(g0.alpha, opost.fs[m - 1].alpha, rtol=1e-7, atol=1e-9)
+    assert_isapprox(g0.alpha, opost.fs[m - 1].alpha, RTOL)
     np.testing.assert_allclose(g0.delta, opost.fs[m - 1].delta, rtol=1e-12, atol=1e-13)
-    np.testing.assert_allclose(g0.C, opost.fs[m - 1].L, rtol=1e-8, atol=1e-10)
+    assert_isapprox(g0.C, opost.fs[m - 1].L, RTOL)
     # prior marginals
     Mp, Vp = lmm.mean_and_var(f(xsin, s2))
     Mpr, Vpr = o.oilmm_mean_and_var(om, xs, s2)
-    np.testing.assert_allclose(Mp, Mpr, rtol=RTOL, atol=1e-12)
+    assert_isapprox(Mp, Mpr, RTOL)
     np.testing.assert_allclose(Vp, Vpr, rtol=RTOL)
     marg = lmm.marginals(post(xsin, s2))
     assert len(marg) == p * Ns and abs(marg[0].sigma ** 2 - V[0]) < 1e-12
@@ -166,7 +167,7 @@ def test_oilmm_mid_size_multi_tile(lmm):
     post = lmm.posterior(fx, y)
     M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
     Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
-    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    assert_isapprox(M, Mr, RTOL)
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
 
 
@@ -191,7 +192,7 @@ def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer, small)
         assert rel(lp, o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
         M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
         Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
-        np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+        assert_isapprox(M, Mr, RTOL)
         np.testing.assert_allclose(V, Vr, rtol=RTOL)
     finally:
         ctx.set_option("gemm_impl", 2)
@@ -221,7 +222,7 @@ def test_panel_kernel_variants_agree(lmm, potrf_impl, direct, small, lookahead):
         assert rel(lp, o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
         M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
         Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
-        np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+        assert_isapprox(M, Mr, RTOL)
         np.testing.assert_allclose(V, Vr, rtol=RTOL)
         # general ILMM: one (mN x mN) factor, batch 1
         rng = np.random.default_rng(5)
@@ -318,11 +319,11 @@ def test_ilmm_posterior_marginals(lmm):
     assert rel(lp, o.ilmm_logpdf(fs, H, x, 0.1, y)) < RTOL
     M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
     Mr, Vr = o.ilmm_mean_and_var(o.ilmm_posterior(fs, H, x, 0.1, y), H, xs, 0.1)
-    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    assert_isapprox(M, Mr, RTOL)
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
     Mp, Vp = lmm.mean_and_var(f(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
     Mpr, Vpr = o.ilmm_mean_and_var(fs, H, xs, 0.1)
-    np.testing.assert_allclose(Mp, Mpr, rtol=RTOL, atol=1e-12)
+    assert_isapprox(Mp, Mpr, RTOL)
     np.testing.assert_allclose(Vp, Vpr, rtol=RTOL)
 
 
@@ -437,7 +438,7 @@ def test_cov_and_mean_and_cov(lmm):
     Mr, Cr = o.ilmm_mean_and_cov(fs, H, xs, 0.1)
     for f in (f_o, f_i):
         M, C = lmm.mean_and_cov(f(xsin, 0.1))
-        np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-12)
+        assert_isapprox(M, Mr, RTOL)
         np.testing.assert_allclose(C, Cr, rtol=RTOL, atol=1e-12)
         np.testing.assert_allclose(np.diag(lmm.cov(f(xsin, 0.1))), lmm.var(f(xsin, 0.1)), rtol=1e-12)
     # OILMM posterior
@@ -445,14 +446,14 @@ def test_cov_and_mean_and_cov(lmm):
     opost = o.oilmm_posterior(om, x, 0.1, y)
     Mr, Cr = o.ilmm_mean_and_cov(opost.fs, H, xs, 0.1)
     M, C = lmm.mean_and_cov(post(xsin, 0.1))
-    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-11)
+    assert_isapprox(M, Mr, RTOL)
     np.testing.assert_allclose(C, Cr, rtol=1e-8, atol=1e-11)
     np.testing.assert_allclose(np.diag(C), lmm.var(post(xsin, 0.1)), rtol=1e-9)
     # general ILMM posterior (joint)
     posti = lmm.posterior(f_i(xin, 0.1), y)
     Mr, Cr = o.ilmm_mean_and_cov(o.ilmm_posterior(fs, H, x, 0.1, y), H, xs, 0.1)
     M, C = lmm.mean_and_cov(posti(xsin, 0.1))
-    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    assert_isapprox(M, Mr, RTOL)
     np.testing.assert_allclose(C, Cr, rtol=1e-8, atol=1e-11)
     # IndependentMOGP prior / posterior, by outputs and by features
     fm = lmm.independent_mogp(gps)
@@ -465,7 +466,7 @@ def test_cov_and_mean_and_cov(lmm):
     pm = lmm.posterior(fm(lmm.MOInputIsotopicByOutputs(x, 2), 0.1), y2)
     Mr, Cr = o.imogp_mean_and_cov(o.imogp_posterior(fs, x, 0.1, y2), xs, 0.2)
     M, C = lmm.mean_and_cov(pm(xs2, 0.2))
-    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-11)
+    assert_isapprox(M, Mr, RTOL)
     np.testing.assert_allclose(C, Cr, rtol=1e-8, atol=1e-11)
     idx = o.indices_outputs_to_features(Ns, 2)
     Mf, Cf = lmm.mean_and_cov(pm(lmm.MOInputIsotopicByFeatures(xs, 2), 0.2))
@@ -751,7 +752,7 @@ def test_ard_transform(lmm, tmp_path):
     opost = o.oilmm_posterior(om, x, 0.1, y)
     M, V = lmm.mean_and_var(post(O(lmm.RowVecs(xs), p), 0.1))
     Mr, Vr = o.oilmm_mean_and_var(opost, xs, 0.1)
-    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    assert_isapprox(M, Mr, RTOL)
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
     lpg, g = lmm.logpdf_and_gradient(fx, y, with_grad_y=True)
     lpr, gr = o.oilmm_logpdf_grad(om, x, 0.1, y)
@@ -822,7 +823,7 @@ def test_exponential_and_rational_quadratic_kernels(lmm, D):
     assert rel(lp, o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
     M, V = lmm.mean_and_var(post(O(wrap(xs), p), 0.1))
     Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
-    np.testing.assert_allclose(M, Mr, rtol=RTOL, atol=1e-10)
+    assert_isapprox(M, Mr, RTOL)
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
     _, g = lmm.logpdf_and_gradient(fx, y)
     _, gr = o.oilmm_logpdf_grad(om, x, 0.1, y)

@@ -28,6 +28,16 @@ def test_cuda_general_ilmm_matches_extended_precision_truth():
     M, V = lmm.mean_and_var(lmm.posterior(fx, y)(O(lmm.RowVecs(xs), p), s2))
     np.testing.assert_allclose(M, T2["post_mean"], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(V, T2["post_var"], rtol=1e-8)
+    # against the oracle's restatement of the SAME (projected, 1e-9-jittered) algorithm the north star's 1e-9 holds
+    from oracle import lmm_oracle as o
+    from _tol import assert_isapprox
+
+    fs = [o.GP(o.Kernel(o.MATERN52, 1.2, 0.9, ard=tuple(T2["ard0"])), 0.5), o.GP(o.Kernel(o.EXPONENTIAL, 0.8, 1.4), -1.0),
+          o.GP(o.Kernel(o.RATQUAD, 1.0, 0.6, param=1.7), 0.0)]
+    assert abs(lp - o.ilmm_logpdf(fs, H, x, s2, y)) <= 1e-9 * abs(lp)
+    Mo, Vo = o.ilmm_mean_and_var(o.ilmm_posterior(fs, H, x, s2, y), H, xs, s2)
+    assert_isapprox(M, Mo, 1e-9, "general-ILMM posterior mean vs projected oracle")
+    assert_isapprox(V, Vo, 1e-9, "general-ILMM posterior var vs projected oracle")
     _, g = lmm.logpdf_and_gradient(fx, y)
     assert abs(g["sigma2"] - float(T2["dlogpdf_dsigma2"])) <= 1e-7 * abs(float(T2["dlogpdf_dsigma2"]))
     assert abs(g["ard"][0][1] - float(T2["dlogpdf_dard0_1"])) <= 1e-6 * abs(float(T2["dlogpdf_dard0_1"]))
