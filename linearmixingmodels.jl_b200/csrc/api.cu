@@ -1,5 +1,7 @@
 // liblmm C ABI (include/lmm.h): contexts, communicators, options and the host-only entry points; the shared host
 // helpers (pointer classification, staged copies, shard ranges).  See host_internal.h for the file map.
+#include <algorithm>
+
 #include "host_internal.h"
 
 // NCCL through dlopen: no link-time dependency; picks up the libnccl.so.2 already loaded by the host process (torch
@@ -275,21 +277,54 @@ extern "C" int lmm_comm_init(lmm_ctx* ctx, const void* unique_id_128_bytes, int 
 // ------------------------------------------------------------------------------------------------
 // Orthogonal validation (host): src/orthogonal_matrix.jl:21-23  isapprox(U'U, I)
 // ------------------------------------------------------------------------------------------------
+// Largest |eigenvalue| of a symmetric n x n matrix (= its operator 2-norm): cyclic Jacobi rotations on the host.
+// n = m (number of latents), so O(n³) per sweep is negligible; converges quadratically, 6-10 sweeps.
+static double sym_opnorm(std::vector<double> A, int n) {
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int a = 0; a < n; ++a)
+      for (int b = 0; b < n; ++b) (a == b ? diag : off) += A[(size_t)a * n + b] * A[(size_t)a * n + b];
+    if (off <= 1e-32 * (diag + off) || off == 0.0) break;
+    for (int pI = 0; pI < n - 1; ++pI)
+      for (int q = pI + 1; q < n; ++q) {
+        const double apq = A[(size_t)pI * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[(size_t)q * n + q] - A[(size_t)pI * n + pI]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < n; ++k) {  // columns p, q
+          const double akp = A[(size_t)k * n + pI], akq = A[(size_t)k * n + q];
+          A[(size_t)k * n + pI] = c * akp - sn * akq;
+          A[(size_t)k * n + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < n; ++k) {  // rows p, q
+          const double apk = A[(size_t)pI * n + k], aqk = A[(size_t)q * n + k];
+          A[(size_t)pI * n + k] = c * apk - sn * aqk;
+          A[(size_t)q * n + k] = sn * apk + c * aqk;
+        }
+      }
+  }
+  double mx = 0.0;
+  for (int a = 0; a < n; ++a) mx = std::max(mx, std::fabs(A[(size_t)a * n + a]));
+  return mx;
+}
+
+// Julia: `isapprox(U'U, I)` against a UniformScaling uses the OPERATOR 2-norm with |I| = 1
+// (LinearAlgebra: norm(A - J) <= max(atol, rtol * max(norm(A), |λ|)), norm = opnorm, rtol = sqrt(eps)).
 extern "C" int lmm_orthogonal_validate(const double* U, int p, int m) {
   if (!U || p <= 0 || m <= 0) return LMM_E_ARG;
-  // |U'U - I|_F <= sqrt(eps) * max(|U'U|_F, |I|_F)
-  double diff2 = 0.0, g2 = 0.0;
+  std::vector<double> G((size_t)m * m), Dm((size_t)m * m);
   for (int a = 0; a < m; ++a)
-    for (int b = 0; b < m; ++b) {
+    for (int b = 0; b <= a; ++b) {
       double s = 0.0;
       for (int j = 0; j < p; ++j) s += U[(size_t)a * p + j] * U[(size_t)b * p + j];
-      g2 += s * s;
-      const double d = s - (a == b ? 1.0 : 0.0);
-      diff2 += d * d;
+      if (!std::isfinite(s)) return LMM_E_NOT_ORTHOGONAL;
+      G[(size_t)a * m + b] = G[(size_t)b * m + a] = s;
+      Dm[(size_t)a * m + b] = Dm[(size_t)b * m + a] = s - (a == b ? 1.0 : 0.0);
     }
   const double rtol = 1.4901161193847656e-08;  // sqrt(eps(Float64))
-  const double nrm = std::max(std::sqrt(g2), std::sqrt((double)m));
-  if (!(std::sqrt(diff2) <= rtol * nrm)) return LMM_E_NOT_ORTHOGONAL;
+  const double nrm = std::max(sym_opnorm(G, m), 1.0);
+  if (!(sym_opnorm(Dm, m) <= rtol * nrm)) return LMM_E_NOT_ORTHOGONAL;
   return LMM_OK;
 }
 

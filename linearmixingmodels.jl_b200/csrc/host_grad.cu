@@ -102,11 +102,9 @@ extern "C" int lmm_post_condition(lmm_post* post, const double* xs, int Ns, doub
   CU(b_H.alloc(ctx, (size_t)p * m * sizeof(double)));
   CU(cudaMemcpyAsync(b_H.p, post->d_H, (size_t)p * m * sizeof(double), cudaMemcpyDeviceToDevice, st));
   CU(cudaStreamSynchronize(st));
-  if (nloc > 0) {
+  {
     std::vector<int> hi(hinfo.begin(), hinfo.begin() + nloc);
-    if ((rc = report_info(ctx, hi, lo, N2, info_latent))) return rc;
-  } else if (info_latent) {
-    *info_latent = -1;
+    if ((rc = report_info(ctx, hi, lo, N2, info_latent))) return rc;  // collective: also the ranks without latents
   }
   lmm_post* P = new lmm_post();
   P->ctx = ctx; P->kind = post->kind; P->m = m; P->p = p; P->N = N2; P->D = D; P->nt = nt2; P->lo = lo; P->hi = post->hi;
@@ -370,11 +368,9 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
   ctx->timings[0] = ms;
-  if (mloc > 0) {
+  {
     std::vector<int> hi2(hinfo.begin(), hinfo.begin() + mloc);
-    if ((rc = report_info(ctx, hi2, lo, N, out.info_latent))) return rc;
-  } else if (out.info_latent) {
-    *out.info_latent = -1;
+    if ((rc = report_info(ctx, hi2, lo, N, out.info_latent))) return rc;  // collective: also the ranks without latents
   }
   const double resid = hv[(size_t)5 * m];
   double reg = 0.0, dreg = 0.0;

@@ -41,7 +41,7 @@ struct NcclApi {
   bool ok = false;
 };
 NcclApi& nccl_api();
-constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0, NCCL_MIN = 3;  // ncclFloat64, ncclSum, ncclMin
 
 // ------------------------------------------------------------------------------------------------
 // context

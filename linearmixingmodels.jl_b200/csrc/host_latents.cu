@@ -169,17 +169,11 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
     cudaEventElapsedTime(&prj, ctx->ev[0], ctx->ev[1]);
     ctx->timings[0] = tot; ctx->timings[1] = ms_kmat; ctx->timings[2] = ms_chol; ctx->timings[3] = ms_solve; ctx->timings[4] = prj;
   }
-  for (int i = 0; i < mloc; ++i) {
-    if (hinfo[i] > 0) {
-      int pivot = hinfo[i] > N ? N : hinfo[i];
-      if (out.info_latent) *out.info_latent = lo + i;
-      char buf[128];
-      snprintf(buf, sizeof buf, "PosDefException: latent %d is not positive definite (pivot %d)", lo + i, pivot);
-      ctx->err = buf;
-      return pivot;
-    }
+  {
+    // collective verdict: every rank returns the same PosDef code / latent, none emits a value
+    const int rc_info = report_info(ctx, std::vector<int>(hinfo.begin(), hinfo.begin() + mloc), lo, N, out.info_latent);
+    if (rc_info) return rc_info;
   }
-  if (out.info_latent) *out.info_latent = -1;
   if (out.lml_terms) memcpy(out.lml_terms, hterms.data(), (size_t)(m + 1) * sizeof(double));
   if (out.logpdf) {
     double s = 0.0;

@@ -31,16 +31,40 @@ int stage_latent_vectors(lmm_ctx* ctx, DevBuf& buf, const double* z, int N, size
   return LMM_OK;
 }
 
+// PosDef report for a set of sharded factorizations.  hinfo holds this rank's LAPACK-style info words for the units
+// lo, lo + 1, ...  With a communicator the verdict is made COLLECTIVE: one MIN all-reduce of a single double that encodes
+// (first failing unit, pivot), so that every rank returns the same code and the same info_latent and no rank goes on with a
+// value summed from a failed factorisation's garbage (rank-local PosDef status desynchronised the ranks, and a
+// return between the factorisation and a later collective left the other ranks hanging in NCCL).  EVERY rank of the
+// communicator must therefore reach this call, also one that owns no unit (hinfo empty), and callers must not return a
+// rank-local PosDef code before it.
 int report_info(lmm_ctx* ctx, const std::vector<int>& hinfo, int lo, int nmax, int* info_latent) {
+  constexpr double NONE = 1e300;
+  double key = NONE;  // unit * 2^31 + pivot of the first failing local unit
   for (size_t i = 0; i < hinfo.size(); ++i)
     if (hinfo[i] > 0) {
-      int pivot = hinfo[i] > nmax ? nmax : hinfo[i];
-      if (info_latent) *info_latent = lo + (int)i;
-      char buf[128];
-      snprintf(buf, sizeof buf, "PosDefException: latent %d is not positive definite (pivot %d)", lo + (int)i, pivot);
-      ctx->err = buf;
-      return pivot;
+      const int pivot = hinfo[i] > nmax ? nmax : hinfo[i];
+      key = (double)(lo + (int)i) * 2147483648.0 + (double)pivot;
+      break;
     }
+  if (ctx->comm && ctx->nranks > 1) {
+    DevBuf b_key;
+    CU(b_key.alloc(ctx, sizeof(double)));
+    CU(cudaMemcpyAsync(b_key.p, &key, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int r = nccl_api().AllReduce(b_key.p, b_key.p, 1, NCCL_DOUBLE, NCCL_MIN, ctx->comm, ctx->stream);
+    if (r != 0) return ctx->fail(LMM_E_NCCL, "ncclAllReduce failed");
+    CU(cudaMemcpyAsync(&key, b_key.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (key < NONE) {
+    const int unit = (int)std::floor(key / 2147483648.0);
+    const int pivot = (int)(key - (double)unit * 2147483648.0);
+    if (info_latent) *info_latent = unit;
+    char buf[128];
+    snprintf(buf, sizeof buf, "PosDefException: latent %d is not positive definite (pivot %d)", unit, pivot);
+    ctx->err = buf;
+    return pivot;
+  }
   if (info_latent) *info_latent = -1;
   return LMM_OK;
 }
@@ -53,7 +77,7 @@ int prior_latent_samples(lmm_ctx* ctx, const lmm_gp_desc* descs, const double* n
   cudaStream_t st = ctx->stream;
   const int nloc = hi - lo, nt = ntiles(N);
   const size_t npad = (size_t)nt * TILE;
-  if (nloc == 0) return LMM_OK;
+  if (nloc == 0) return report_info(ctx, std::vector<int>(), lo, N, info_latent);  // collective: every rank takes part
   DevBuf b_params, b_L, b_W, b_logdet, b_info;
   int rc = upload_params(ctx, b_params, descs, noise_all, lo, hi, D);
   if (rc) return rc;
@@ -225,7 +249,7 @@ int build_predictive(lmm_post* post, const double* xs, int Ns, const std::vector
   CU(P.info.alloc(ctx, (size_t)nl * sizeof(int)));
   CU(cudaMemsetAsync(P.logdet.p, 0, (size_t)nl * sizeof(double), st));
   CU(cudaMemsetAsync(P.info.p, 0, (size_t)nl * sizeof(int), st));
-  if (nloc == 0) return LMM_OK;
+  if (nloc == 0) return factor ? report_info(ctx, std::vector<int>(), post->lo, Ns, info_latent) : LMM_OK;  // collective
   const size_t per_lat = (size_t)P.nts * nt * TT * sizeof(double);
   size_t fr = 0, tot = 0;
   CU(cudaMemGetInfo(&fr, &tot));
@@ -603,12 +627,19 @@ extern "C" int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, 
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
   ctx->timings[0] = ms;
-  for (int u = 0; u < nu; ++u)
-    if (hinfo[u] > 0) {
-      if (info_latent) *info_latent = (ulo + u) % m;
-      ctx->err = "PosDefException in hyper-parameter sweep";
-      return hinfo[u] > N ? N : hinfo[u];
+  {
+    int unit = -1;
+    const int rc_info = report_info(ctx, std::vector<int>(hinfo.begin(), hinfo.begin() + nu), ulo, N, &unit);  // collective
+    if (rc_info) {
+      if (info_latent) *info_latent = unit >= 0 ? unit % m : -1;
+      if (rc_info > 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "PosDefException in hyper-parameter sweep: latent %d at sweep point %d (pivot %d)", unit % m, unit / m, rc_info);
+        ctx->err = buf;
+      }
+      return rc_info;
     }
+  }
   if (info_latent) *info_latent = -1;
   for (int s = 0; s < n_sweep; ++s) {
     double acc = 0.0;

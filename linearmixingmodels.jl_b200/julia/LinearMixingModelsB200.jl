@@ -54,19 +54,38 @@ kind(::Matern52Kernel) = Int32(2)
 kind(::ExponentialKernel) = Int32(3)          # == Matern12Kernel
 kind(::RationalQuadraticKernel) = Int32(4)    # α travels in GpDesc.param
 shape(k) = 1.0
-shape(k::RationalQuadraticKernel) = Float64(only(k.α))
-describe(k::KernelFunctions.SimpleKernel) = (kind(k), 1.0, 1.0)
-describe(k::ScaledKernel) = (d = describe(k.kernel); (d[1], d[2] * only(k.σ²), d[3]))
+shape(k::RationalQuadraticKernel) = Float64(only(k.α))   # KernelFunctions default α = 2
+# describe(k) -> (kind, variance, inv_lengthscale, shape parameter, ARD multipliers or nothing)
+describe(k::KernelFunctions.SimpleKernel) = (kind(k), 1.0, 1.0, shape(k), nothing)
+describe(k::ScaledKernel) = (d = describe(k.kernel); (d[1], d[2] * only(k.σ²), d[3], d[4], d[5]))
 function describe(k::TransformedKernel{<:Kernel,<:ScaleTransform})
     d = describe(k.kernel)
-    return (d[1], d[2], d[3] * only(k.transform.s))
+    return (d[1], d[2], d[3] * only(k.transform.s), d[4], d[5])
+end
+# `k ∘ ARDTransform(v)`: inputs are multiplied by v per dimension before distances are taken -> GpDesc.ard
+function describe(k::TransformedKernel{<:Kernel,<:ARDTransform})
+    d = describe(k.kernel)
+    v = Vector{Float64}(k.transform.v)
+    length(v) <= 8 || throw(ArgumentError("ARDTransform with more than 8 dimensions is not supported by liblmm"))
+    return (d[1], d[2], d[3], d[4], d[5] === nothing ? v : d[5] .* v)
 end
 describe(k) = throw(ArgumentError("kernel $(typeof(k)) is not supported by liblmm (no CPU fallback)"))
 meanconst(::AbstractGPs.ZeroMean) = 0.0
 meanconst(m::AbstractGPs.ConstMean) = Float64(m.c)
-function GpDesc(f::GP)
-    k, v, s = describe(f.kernel)
-    return GpDesc(k, 0, v, s, meanconst(f.mean), C_NULL, 1.0)   # `k ∘ ARDTransform(v)`: pass pointer(v) under GC.@preserve
+# The C descriptors of a vector of latents plus the objects that must stay rooted while the library reads them (the ARD
+# vectors GpDesc.ard points into): every ccall that takes `descs` runs under `GC.@preserve keep`.
+function gpdescs(fs::AbstractVector)
+    keep = Vector{Vector{Float64}}()
+    descs = map(fs) do f
+        k, v, s, a, ard = describe(f.kernel)
+        p = C_NULL
+        if ard !== nothing
+            push!(keep, ard)
+            p = pointer(ard)
+        end
+        GpDesc(k, 0, v, s, meanconst(f.mean), p, a)
+    end
+    return Vector{GpDesc}(descs), keep
 end
 
 points(x::AbstractVector{<:Real}) = (collect(Float64, x), 1)
@@ -93,10 +112,10 @@ end
 function AbstractGPs.logpdf(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     U = Matrix{Float64}(H.U); S = Vector{Float64}(diag(H.S)); yv = Vector{Float64}(y)
     out = Ref{Float64}(0.0); il = Ref{Cint}(-1)
-    rc = ccall((:lmm_oilmm_logpdf, liblmm), Cint,
+    rc = GC.@preserve keep ccall((:lmm_oilmm_logpdf, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64,
          Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(x), D, U, S, size(U, 1), Float64(σ²), yv, fx.x.out_dim, out, C_NULL, il)
@@ -108,10 +127,10 @@ end
 function AbstractGPs.posterior(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     U = Matrix{Float64}(H.U); S = Vector{Float64}(diag(H.S)); yv = Vector{Float64}(y)
     h = Ref{Ptr{Cvoid}}(C_NULL); il = Ref{Cint}(-1)
-    rc = ccall((:lmm_oilmm_posterior, liblmm), Cint,
+    rc = GC.@preserve keep ccall((:lmm_oilmm_posterior, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64,
          Ptr{Float64}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(x), D, U, S, size(U, 1), Float64(σ²), yv, fx.x.out_dim, h, C_NULL, C_NULL, il)
@@ -152,12 +171,12 @@ end
 function AbstractGPs.rand(rng::AbstractRNG, fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     m, p, N = length(descs), size(H, 1), length(x)
     zl = randn(rng, N * m)          # latent 1..m, N draws each  (src/oilmm.jl:47)
     zn = randn(rng, N * p)          # then the observation noise (src/oilmm.jl:53)
     out = Vector{Float64}(undef, N * p); il = Ref{Cint}(-1)
-    rc = ccall((:lmm_oilmm_rand, liblmm), Cint,
+    rc = GC.@preserve keep ccall((:lmm_oilmm_rand, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint,
          Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, m, X, N, D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), p, Float64(σ²), fx.x.out_dim, zl, zn, out, il)
@@ -169,9 +188,9 @@ end
 function AbstractGPs.logpdf(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}}, y::AbstractVector{<:Real})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     out = Ref{Float64}(0.0); info = Ref{Cint}(0)
-    rc = ccall((:lmm_ilmm_logpdf, liblmm), Cint,
+    rc = GC.@preserve keep ccall((:lmm_ilmm_logpdf, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint, Cint,
          Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(x), D, H, size(H, 1), Float64(σ²), Vector{Float64}(y), fx.x.out_dim, 0, out, info)
@@ -183,9 +202,9 @@ end
 function AbstractGPs.logpdf(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOInputIsotopicByOutputs,<:Diagonal{<:Real,<:Fill}},
                             y::AbstractVector{<:Real})
     X, D = points(ft.x.x)
-    descs = GpDesc.(ft.f.fs)
+    descs, keep = gpdescs(ft.f.fs)
     out = Ref{Float64}(0.0); il = Ref{Cint}(-1)
-    rc = ccall((:lmm_imogp_logpdf, liblmm), Cint,
+    rc = GC.@preserve keep ccall((:lmm_imogp_logpdf, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Float64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(ft.x.x), D, Float64(ft.Σy[1]), Vector{Float64}(y), ft.x.out_dim, out, C_NULL, il)
     check(rc)
@@ -209,11 +228,11 @@ AbstractGPs.cov(fx::FiniteGP{<:PosteriorOILMM}) = mean_and_cov(fx)[2]
 function AbstractGPs.mean_and_cov(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     Hm = Matrix{Float64}(collect(H))            # U*sqrt(S) for an Orthogonal
     n = length(x) * fx.x.out_dim
     M = Vector{Float64}(undef, n); C = Matrix{Float64}(undef, n, n)
-    check(ccall((:lmm_prior_mean_and_cov, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_prior_mean_and_cov, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Float64, Cint, Ptr{Float64}, Ptr{Float64}),
         ctx(), descs, length(descs), X, length(x), D, Hm, size(Hm, 1), Float64(σ²), 1e-18, fx.x.out_dim, M, C))
     return M, C
@@ -254,16 +273,16 @@ function ChainRulesCore.rrule(::typeof(AbstractGPs.logpdf), fx::FiniteGP{<:OILMM
                               y::AbstractVector{<:Real})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs); m = length(descs)
+    descs, keep = gpdescs(fs.fs); m = length(descs)
     out = Ref{Float64}(0.0); gs2 = Ref{Float64}(0.0); il = Ref{Cint}(-1)
     gl = Matrix{Float64}(undef, 3, m)            # column i = (d/dvariance, d/dinv_lengthscale, d/dmean) of latent i
     gy = Vector{Float64}(undef, length(y))
     gU = Matrix{Float64}(undef, size(H, 1), m); gS = Vector{Float64}(undef, m)   # tangents of H.U and H.S.diag
-    check(ccall((:lmm_oilmm_logpdf_grad, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_oilmm_logpdf_grad, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
          Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, m, X, length(x), D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), size(H, 1), Float64(σ²),
-        Vector{Float64}(y), fx.x.out_dim, out, gl, C_NULL #= grad_ard: m x D when ARDTransforms are described =#, gs2, gy, gU, gS, il))
+        Vector{Float64}(y), fx.x.out_dim, out, gl, C_NULL #= grad_ard (m x D, row-major): pass a Matrix{Float64}(undef, D, m) to receive d/d ARD multipliers =#, gs2, gy, gU, gS, il))
     function logpdf_pullback(Δ)
         Σy_tangent = Tangent{typeof(fx.Σy)}(; diag = Tangent{typeof(fx.Σy.diag)}(; value = Δ * gs2[]))
         return NoTangent(), Tangent{typeof(fx)}(; Σy = Σy_tangent), Δ .* gy
@@ -276,10 +295,10 @@ function ChainRulesCore.rrule(::typeof(AbstractGPs.logpdf), fx::FiniteGP{<:ILMM{
                               y::AbstractVector{<:Real})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs); m = length(descs)
+    descs, keep = gpdescs(fs.fs); m = length(descs)
     out = Ref{Float64}(0.0); gs2 = Ref{Float64}(0.0); info = Ref{Cint}(0)
     gl = Matrix{Float64}(undef, 3, m); gy = Vector{Float64}(undef, length(y)); gH = similar(H)
-    check(ccall((:lmm_ilmm_logpdf_grad, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_ilmm_logpdf_grad, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
          Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, m, X, length(x), D, H, size(H, 1), Float64(σ²), Vector{Float64}(y), fx.x.out_dim, out, gl, C_NULL, gs2, gy, gH, info))
@@ -313,10 +332,10 @@ noise_arg(Σy::Diagonal) = (Vector{Float64}(Σy.diag), Cint(1))      # LMM_NOISE
 noise_arg(Σy::AbstractMatrix) = (Matrix{Float64}(Σy), Cint(2))     # LMM_NOISE_DENSE
 function AbstractGPs.logpdf(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOInputIsotopicByOutputs}, y::AbstractVector{<:Real})
     X, D = points(ft.x.x)
-    descs = GpDesc.(ft.f.fs)
+    descs, keep = gpdescs(ft.f.fs)
     Σ, kind = noise_arg(ft.Σy)
     out = Ref{Float64}(0.0); il = Ref{Cint}(-1)
-    check(ccall((:lmm_imogp_posterior_noise, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_imogp_posterior_noise, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(ft.x.x), D, Σ, kind, Vector{Float64}(y), ft.x.out_dim, C_NULL, out, il))
     return out[]
@@ -326,10 +345,10 @@ end
 function AbstractGPs.mean_and_var(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     n = length(x) * fx.x.out_dim
     M = Vector{Float64}(undef, n); V = Vector{Float64}(undef, n)
-    check(ccall((:lmm_oilmm_prior_mean_and_var, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_oilmm_prior_mean_and_var, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Cint, Ptr{Float64}, Ptr{Float64}),
         ctx(), descs, length(descs), X, length(x), D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), size(H, 1), Float64(σ²),
         fx.x.out_dim, M, V))
@@ -338,10 +357,10 @@ end
 function AbstractGPs.mean_and_var(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     n = length(x) * fx.x.out_dim
     M = Vector{Float64}(undef, n); V = Vector{Float64}(undef, n)
-    check(ccall((:lmm_ilmm_prior_mean_and_var, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_ilmm_prior_mean_and_var, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Cint, Ptr{Float64}, Ptr{Float64}),
         ctx(), descs, length(descs), X, length(x), D, H, size(H, 1), Float64(σ²), fx.x.out_dim, M, V))
     return M, V
@@ -356,9 +375,9 @@ const PosteriorILMM = ILMM{<:IndependentMOGP{<:Vector{<:DeviceLatentPosterior}},
 function AbstractGPs.posterior(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}}, y::AbstractVector{<:Real})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     h = Ref{Ptr{Cvoid}}(C_NULL); info = Ref{Cint}(0)
-    check(ccall((:lmm_ilmm_posterior, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_ilmm_posterior, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
          Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(x), D, H, size(H, 1), Float64(σ²), Vector{Float64}(y), fx.x.out_dim, h, C_NULL, info))
@@ -372,11 +391,11 @@ end
 function AbstractGPs.rand(rng::AbstractRNG, fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}},<:Matrix{Float64}}})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     m, p, N = length(descs), size(H, 1), length(x)
     zl = randn(rng, N * m); zn = randn(rng, N * p)       # latent draws (src/ilmm.jl:84), then the noise (:86)
     out = Vector{Float64}(undef, N * p); il = Ref{Cint}(-1)
-    check(ccall((:lmm_ilmm_rand, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_ilmm_rand, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Cint,
          Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, m, X, N, D, H, p, Float64(σ²), fx.x.out_dim, zl, zn, out, il))
@@ -390,9 +409,9 @@ AbstractGPs.rand(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}}) = rand
 function AbstractGPs.posterior(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOInputIsotopicByOutputs,<:Diagonal{<:Real,<:Fill}},
                                y::AbstractVector{<:Real})
     X, D = points(ft.x.x)
-    descs = GpDesc.(ft.f.fs)
+    descs, keep = gpdescs(ft.f.fs)
     h = Ref{Ptr{Cvoid}}(C_NULL); il = Ref{Cint}(-1)
-    check(ccall((:lmm_imogp_posterior, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_imogp_posterior, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Float64, Ptr{Float64}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(ft.x.x), D, Float64(ft.Σy[1]), Vector{Float64}(y), ft.x.out_dim, h, C_NULL, il))
     owner = DevicePosterior(h[])
@@ -400,10 +419,10 @@ function AbstractGPs.posterior(ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:
 end
 function AbstractGPs.rand(rng::AbstractRNG, ft::FiniteGP{<:IndependentMOGP{<:Vector{<:GP}},<:MOInputIsotopicByOutputs,<:Diagonal{<:Real,<:Fill}})
     X, D = points(ft.x.x)
-    descs = GpDesc.(ft.f.fs)
+    descs, keep = gpdescs(ft.f.fs)
     N = length(ft.x.x); m = length(descs)
     z = randn(rng, N * m); out = Vector{Float64}(undef, N * m); il = Ref{Cint}(-1)
-    check(ccall((:lmm_imogp_rand, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_imogp_rand, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, m, X, N, D, Float64(ft.Σy[1]), ft.x.out_dim, z, out, il))
     return out
@@ -420,9 +439,9 @@ end
 function logpdf_sweep(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real}, scales::AbstractVector{<:Real})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     out = Vector{Float64}(undef, length(scales)); il = Ref{Cint}(-1)
-    check(ccall((:lmm_oilmm_logpdf_sweep, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_oilmm_logpdf_sweep, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
          Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(x), D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), size(H, 1), Float64(σ²),
@@ -434,10 +453,10 @@ end
 function posterior_missing(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real})
     fs, H, σ², x = unpack(fx)
     X, D = points(x)
-    descs = GpDesc.(fs.fs)
+    descs, keep = gpdescs(fs.fs)
     Hm = Matrix{Float64}(collect(H))
     h = Ref{Ptr{Cvoid}}(C_NULL); lp = Ref{Float64}(0.0); nobs = Ref{Cint}(0); info = Ref{Cint}(0)
-    check(ccall((:lmm_ilmm_masked_posterior, liblmm), Cint,
+    check(GC.@preserve keep ccall((:lmm_ilmm_masked_posterior, liblmm), Cint,
         (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
          Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}, Ptr{Cint}),
         ctx(), descs, length(descs), X, length(x), D, Hm, size(Hm, 1), Float64(σ²), Vector{Float64}(y), fx.x.out_dim, h, lp, nobs, info))
@@ -445,7 +464,7 @@ function posterior_missing(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}
 end
 
 # --- tunables and teardown ------------------------------------------------------------------------------------------
-set_option(key::AbstractString, value::Real) = check(ccall((:lmm_ctx_set_option, liblmm), Cint, (Ptr{Cvoid}, Cstring, Float64), ctx(), key, Float64(value)))
+set_option(key::AbstractString, value::Real) = check(GC.@preserve keep ccall((:lmm_ctx_set_option, liblmm), Cint, (Ptr{Cvoid}, Cstring, Float64), ctx(), key, Float64(value)))
 version() = unsafe_string(ccall((:lmm_version, liblmm), Cstring, ()))
 function __init__()
     atexit() do

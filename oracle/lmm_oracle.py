@@ -260,13 +260,13 @@ def finite_rand(f, xs, noise: float, z: np.ndarray) -> np.ndarray:
 # LinearMixingModels: Orthogonal, project, regulariser (src/orthogonal_matrix.jl, src/oilmm.jl, src/ilmm.jl)
 # --------------------------------------------------------------------------------------------
 def validate_orthogonal(U: np.ndarray) -> None:
-    """src/orthogonal_matrix.jl:21-23 -- ``isapprox(U'U, I)`` (Frobenius norm, rtol=sqrt(eps))."""
+    """src/orthogonal_matrix.jl:21-23 -- ``isapprox(U'U, I)``.  Against a ``UniformScaling`` Julia's ``isapprox`` uses the
+    operator 2-norm with ``|I| = 1``: ``opnorm(U'U - I) <= sqrt(eps) * max(opnorm(U'U), 1)``."""
     U = np.asarray(U, dtype=np.float64)
     m = U.shape[1]
     G = U.T @ U
-    eye = np.eye(m)
     rtol = math.sqrt(np.finfo(np.float64).eps)
-    if not np.linalg.norm(G - eye) <= rtol * max(np.linalg.norm(G), np.linalg.norm(eye)):
+    if not (np.all(np.isfinite(G)) and np.linalg.norm(G - np.eye(m), 2) <= rtol * max(np.linalg.norm(G, 2), 1.0)):
         raise ValueError("`U` is not an orthogonal matrix")
 
 

@@ -222,3 +222,43 @@ def test_plain_c_client_runs_on_gpu(tmp_path):
     r = subprocess.run([C_CLIENT, str(tmp_path / "post.bin")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "c_client ok" in r.stdout
+
+
+@pytest.mark.parametrize("eps,ok", [(0.5e-8, True), (1.3e-8, True), (1.7e-8, False), (3e-8, False)])
+def test_orthogonal_validate_uses_the_operator_norm(eps, ok):
+    """Julia's `isapprox(U'U, I)` against a UniformScaling compares OPERATOR 2-norms with |I| = 1
+    (src/orthogonal_matrix.jl:21-23): a rank-one deviation eps*v*v' of U'U must be rejected as soon as eps exceeds
+    sqrt(eps(Float64)) = 1.49e-8 -- a Frobenius test with |I|_F = sqrt(m) would accept it up to sqrt(m) times that
+    (ADVICE r01).  Library and oracle must agree on both sides of the threshold."""
+    from oracle import lmm_oracle as o
+
+    p, m = 24, 16
+    rng = np.random.default_rng(3)
+    Q, _ = np.linalg.qr(rng.standard_normal((p, m)))
+    v = rng.standard_normal(m)
+    v /= np.linalg.norm(v)
+    U = np.asfortranarray(Q @ (np.eye(m) + 0.5 * eps * np.outer(v, v)))  # U'U = I + eps vv' + O(eps²)
+    rc = _lib.load().lmm_orthogonal_validate(_lib.ptr(U), p, m)
+    assert (rc == 0) == ok
+    if ok:
+        o.validate_orthogonal(U)
+    else:
+        with pytest.raises(ValueError):
+            o.validate_orthogonal(U)
+
+
+def test_julia_shim_describes_shape_parameter_and_ard():
+    """the shim used to pass param = 1.0 and ard = C_NULL for every kernel (RationalQuadraticKernel's default
+    α = 2 evaluated with α = 1, ARDTransform rejected).  Mechanical check of the source (Julia cannot run here): `describe`
+    carries the shape parameter and the ARD vector, `gpdescs` stores `pointer(ard)` and every ccall that takes the
+    descriptors runs under `GC.@preserve keep`."""
+    jl = open(os.path.join(ROOT, "linearmixingmodels.jl_b200", "julia", "LinearMixingModelsB200.jl")).read()
+    assert "describe(k::TransformedKernel{<:Kernel,<:ARDTransform})" in jl
+    assert "describe(k::KernelFunctions.SimpleKernel) = (kind(k), 1.0, 1.0, shape(k), nothing)" in jl
+    assert "p = pointer(ard)" in jl and "GpDesc(k, 0, v, s, meanconst(f.mean), p, a)" in jl
+    assert "GpDesc.(" not in jl  # no call site builds descriptors without the keep-alive list any more
+    for fn_src in re.split(r"(?m)^(?=function )", jl):
+        if "= gpdescs(" in fn_src and not fn_src.startswith("function gpdescs"):
+            n_desc_calls = len(re.findall(r"ccall\(\(:lmm_[a-z0-9_]+, liblmm\), Cint,\s*\(Ptr\{Cvoid\}, Ptr\{GpDesc\}", fn_src))
+            assert n_desc_calls >= 1
+            assert fn_src.count("GC.@preserve keep ccall(") >= n_desc_calls, fn_src[:80]
