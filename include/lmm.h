@@ -104,6 +104,12 @@ const char* lmm_version(void);
  *   "gemm_direct"     variant of that direct kernel: 0 = plain (4 slices per tile, one step of prefetch), 1 / 2 =
  *                     register-ring prefetch with 4 / 8 slices per tile and the zero blocks of the triangular
  *                     inverse skipped (default 2)                 [process-wide]
+ *   "condition_update" lmm_post_condition on an OILMM / IndependentMOGP posterior: 1 = block-Cholesky update of each latent's
+ *                     factor, L21 = K21 L11^{-T}, L22 = chol(K22 + Σ2 - L21 L21'), O(N² N₂) (default, what AbstractGPs does);
+ *                     0 = re-factorise the union of the inputs, O((N + N₂)³)
+ *   "solve_impl"      triangular vector solves (z = L^{-1} r, a = L^{-T} z): 1 = ONE persistent launch per direction, tile rows /
+ *                     columns chained through ready flags in global memory (default); 0 = one launch per tile column
+ *                                                                 [process-wide]
  *   "potrf_impl"      diagonal-tile kernel: 0 = first generation (right-looking, inverse after the factor),
  *                     1 = left-looking with the inverse built beside the panel steps (default) [process-wide] */
 int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value);
@@ -202,7 +208,9 @@ int lmm_prior_mean_and_cov(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, cons
                            int out_dim, double* mean, double* cov);
 /* posterior(post(x2, σ²), y2): sequential conditioning of an OILMM / IndependentMOGP / general-ILMM
  * posterior (src/oilmm.jl:116-134 / src/independent_mogp.jl:119-126 / src/ilmm.jl:184-198 with PosteriorGP
- * latents).  Returns a new handle over the union of the inputs; the old handle stays valid. */
+ * latents).  Returns a new handle over the union of the inputs; the old handle stays valid.  Per-latent posteriors extend
+ * the old factor by a block-Cholesky update (cost O(N² N₂), see option "condition_update"); a joint (general-ILMM) posterior
+ * re-factorises the union. */
 int lmm_post_condition(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys,
                        lmm_post** out_post, int* info_latent);
 /* logpdf(post(x*, σ²), y*)  (test/oilmm.jl:84): OILMM logpdf with PosteriorGP latents. */

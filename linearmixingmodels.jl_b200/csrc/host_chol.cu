@@ -8,8 +8,12 @@ namespace lmm_host {
 // For every block column [s0, s1): one wide trailing update against all previous columns
 // (K = s0 tiles, output written once), then per tile column: narrow update inside the block,
 // diagonal-tile factor (+ inverse, logdet, info), panel TRSM as a GEMM with the inverse.
+// jstart > 0 EXTENDS a factor (block-Cholesky update, AbstractGPs' sequential conditioning): the tile rows < jstart of L
+// and W(J), J < jstart, are already final; only the tile rows >= jstart are computed -- for the columns J < jstart that
+// is L(I,J) = (A(I,J) - sum_{k<J} L(I,k) L(J,k)') W(J)' (no diagonal-tile step), from column jstart on the ordinary
+// factorisation of the Schur complement.  Cost O(N² N₂) instead of O((N + N₂)³).
 cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double* W, size_t wstride, int batch, double* logdet,
-                               int* info) {
+                               int* info, int jstart = 0) {
   const int nt = L.nt, ob = ctx->outer_block;
   GemmArgs g{};
   g.A = operand(L);
@@ -22,23 +26,28 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
   for (int s0 = 0; s0 < nt; s0 += ob) {
     const int s1 = (s0 + ob < nt) ? s0 + ob : nt;
     if (s0 > 0) {
-      g.i0 = s0; g.j0 = s0; g.k0 = 0; g.k1 = s0;
-      if ((e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
+      const int r0 = s0 > jstart ? s0 : jstart;  // first tile row that still has to be computed
+      g.i0 = r0; g.j0 = s0; g.k0 = 0; g.k1 = s0;
+      if ((e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, nt - r0, batch)) != cudaSuccess) return e;
       ++ctx->launches;
       ctx->timings[6] += 1;
     }
     for (int jj = s0; jj < s1; ++jj) {
+      const int r0 = jj > jstart ? jj : jstart;
       if (jj > s0) {
-        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
-        if ((e = launch_gemm(st, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
+        g.i0 = r0; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+        if ((e = launch_gemm(st, GEMM_UPDATE, g, 1, nt - r0, batch)) != cudaSuccess) return e;
         ++ctx->launches;
         ctx->timings[6] += 1;
       }
-      if ((e = launch_potrf_tile(st, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
-      ++ctx->launches;
-      if (jj + 1 < nt) {
-        g.i0 = jj + 1; g.j0 = jj;
-        if ((e = launch_gemm(st, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
+      if (jj >= jstart) {
+        if ((e = launch_potrf_tile(st, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+      const int t0 = jj + 1 > jstart ? jj + 1 : jstart;  // rows of column jj below the diagonal tile that are not final yet
+      if (t0 < nt) {
+        g.i0 = t0; g.j0 = jj;
+        if ((e = launch_gemm(st, GEMM_TRSM, g, 1, nt - t0, batch)) != cudaSuccess) return e;
         ++ctx->launches;
       }
     }
@@ -501,15 +510,18 @@ cudaError_t chol_factor_rowcyclic2(lmm_ctx* ctx, TiledSym L, double* W, size_t w
   return cudaSuccess;
 }
 
-// Fork the batch into latent groups on separate streams (joined back into ctx->stream).
-cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
+// Fork the batch into latent groups on separate streams (joined back into ctx->stream).  jstart > 0: extend a factor whose
+// tile rows < jstart are final (see chol_factor_stream).
+cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info, int jstart) {
   const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
-  if (ctx->partition_ilmm && ctx->partition_now && batch == 1 && ctx->comm && ctx->nranks > 1 && L.nt >= 2 * ctx->nranks && nccl_api().AllGather)
-    return (ctx->partition_ilmm == 2 && ctx->comm2) ? chol_factor_rowcyclic2(ctx, L, W, wstride, logdet, info)
-                                                    : chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
-  if (ctx->lookahead == 2 && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
-  if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
-  if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info);
+  if (jstart == 0) {  // the look-ahead / partitioned schedules factor from scratch only
+    if (ctx->partition_ilmm && ctx->partition_now && batch == 1 && ctx->comm && ctx->nranks > 1 && L.nt >= 2 * ctx->nranks && nccl_api().AllGather)
+      return (ctx->partition_ilmm == 2 && ctx->comm2) ? chol_factor_rowcyclic2(ctx, L, W, wstride, logdet, info)
+                                                      : chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
+    if (ctx->lookahead == 2 && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
+    if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
+  }
+  if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info, jstart);
   cudaError_t e;
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
   for (int gi = 0; gi < G; ++gi) {
@@ -517,7 +529,7 @@ cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int
     cudaStream_t st = ctx->gstream[gi];
     if ((e = cudaStreamWaitEvent(st, ctx->ev_fork, 0)) != cudaSuccess) return e;
     TiledSym Lg{L.base + (size_t)b0 * L.batch_stride, L.nt, L.batch_stride};
-    if ((e = chol_factor_stream(ctx, st, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0, logdet + b0, info + b0)) != cudaSuccess) return e;
+    if ((e = chol_factor_stream(ctx, st, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0, logdet + b0, info + b0, jstart)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ctx->ev_join[gi], st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[gi], 0)) != cudaSuccess) return e;
   }

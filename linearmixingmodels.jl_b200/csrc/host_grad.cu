@@ -4,9 +4,10 @@
 
 // ------------------------------------------------------------------------------------------------
 // Sequential conditioning: posterior(post(x2, σ²), y2) on an OILMM / IndependentMOGP posterior
-// (src/oilmm.jl:116-134 / src/independent_mogp.jl:119-126 applied to PosteriorGP latents; AbstractGPs
-// extends the factor by a block update -- here the equivalent exact GP identity is used: each
-// latent's prior is conditioned on the union [x; x2] with per-point noise [Σ1_i .. ; Σ2_i ..]).
+// (src/oilmm.jl:116-134 / src/independent_mogp.jl:119-126 applied to PosteriorGP latents).  Each latent's prior is
+// conditioned on the union [x; x2] with per-point noise [Σ1_i .. ; Σ2_i ..] -- the exact-GP identity "posterior of a
+// posterior = prior conditioned on the union" -- and, as AbstractGPs does, the existing factor is EXTENDED by a block
+// Cholesky update (O(N² N₂)) instead of re-factorising the union (O((N + N₂)³); option "condition_update" = 0).
 // ------------------------------------------------------------------------------------------------
 
 extern "C" int lmm_post_condition(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys, lmm_post** out_post,
@@ -90,9 +91,23 @@ extern "C" int lmm_post_condition(lmm_post* post, const double* xs, int Ns, doub
     CU(cudaMemsetAsync(b_info.p, 0, (size_t)nloc * sizeof(int), st));
     TiledSym L{b_L.as<double>(), nt2, sym_tiles(nt2) * TT};
     const size_t wstride = (size_t)nt2 * TT;
-    CU(launch_kmat_sym(st, L, nloc, b_x.as<double>(), N2, D, b_params.as<LatentParams>(), ctx->distance_form, b_nv.as<double>(), npad2));
+    // Block-Cholesky update (what AbstractGPs does when a FiniteGP{<:PosteriorGP} is conditioned again, SURVEY App. A.2;
+    // exercised at test/oilmm.jl:20-26): the tile rows of the old factor that lie entirely above the new points are final
+    // -- L = [L11 0; L21 L22], L21 = K21 L11^{-T}, L22 = chol(K22 + Σ2 - L21 L21') -- so they are copied, and only the tile
+    // rows from jstart = floor(N1 / 128) on are built and factored (the last, partly filled old tile row is recomputed
+    // together with the new rows: its old rows come out bit-identical, a row of a TRSM / update depends on that row only).
+    const int jstart = ctx->condition_update ? N1 / TILE : 0;
+    if (jstart > 0) {
+      const size_t pre_l = sym_tiles(jstart) * TT, pre_w = (size_t)jstart * TT;
+      const size_t ls1 = sym_tiles(post->nt) * TT, ws1 = (size_t)post->nt * TT, ls2 = sym_tiles(nt2) * TT;
+      for (int i = 0; i < nloc; ++i) {
+        CU(cudaMemcpyAsync(b_L.as<double>() + (size_t)i * ls2, post->d_L + (size_t)i * ls1, pre_l * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(b_W.as<double>() + (size_t)i * wstride, post->d_W + (size_t)i * ws1, pre_w * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    CU(launch_kmat_sym(st, L, nloc, b_x.as<double>(), N2, D, b_params.as<LatentParams>(), ctx->distance_form, b_nv.as<double>(), npad2, jstart));
     ++ctx->launches;
-    CU(chol_factor(ctx, L, b_W.as<double>(), wstride, nloc, b_logdet.as<double>(), b_info.as<int>()));
+    CU(chol_factor(ctx, L, b_W.as<double>(), wstride, nloc, b_logdet.as<double>(), b_info.as<int>(), jstart));
     CU(cudaMemcpyAsync(b_r.p, b_delta.p, (size_t)nloc * npad2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CU(launch_fwd_solve(st, L, b_W.as<double>(), wstride, b_r.as<double>(), b_z.as<double>(), npad2, nloc, &ctx->launches));
     CU(cudaMemcpyAsync(b_r.p, b_z.p, (size_t)nloc * npad2 * sizeof(double), cudaMemcpyDeviceToDevice, st));

@@ -81,6 +81,7 @@ struct lmm_ctx {
   int panel_split = 0;  // right-looking schedule: next column's diagonal tile on the panel stream, the rest of it on a second one
   // one large factor (general ILMM, batch 1) partitioned row-cyclically over the ranks of the communicator
   int partition_ilmm = 0;
+  int condition_update = 1;  // sequential conditioning of per-latent posteriors: 1 = block-Cholesky update of the factor, 0 = re-factorise the union
   int partition_now = 0;  // set by the callers whose factorisation is replicated on every rank (ILMM joint factor)
   int dist_error = 0;  // NCCL failure inside the partitioned schedule (reported by the caller)
   void* xbuf = nullptr;  // exchange buffers of the row-cyclic schedule (send | all-gathered), grown on demand
@@ -271,7 +272,7 @@ int ilmm_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double sigm
 int ilmm_post_rand(lmm_post* post, const double* xs, int Ns, double sigma2, const double* z_latent, const double* z_noise, double* out, int* info);
 int ilmm_post_logpdf(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys, double* out_logpdf, double* grad_sigma2, double* grad_y, int* info);
 int ilmm_post_condition(lmm_post* post, const double* xs, int Ns, double sigma2, const double* ys, lmm_post** out_post, int* info);
-cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info);
+cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info, int jstart = 0);
 cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch);
 cudaError_t trsm_right_lt_upper(lmm_ctx* ctx, cudaStream_t st, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch);
 

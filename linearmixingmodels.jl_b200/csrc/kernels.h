@@ -7,8 +7,9 @@ namespace lmm {
 
 // ---- kmat.cu
 // noise_vec (nullable): per-point diagonal noise [batch][noise_stride] overriding params[b].noise
+// row0: only the tile rows I >= row0 are built (the rows above belong to a factor that is being extended)
 cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const double* xpad, int N, int D,
-                            const LatentParams* params, int form, const double* noise_vec = nullptr, size_t noise_stride = 0);
+                            const LatentParams* params, int form, const double* noise_vec = nullptr, size_t noise_stride = 0, int row0 = 0);
 cudaError_t launch_kmat_cross(cudaStream_t st, TiledRect out, int batch, const double* xa_pad, int Na, const double* xb_pad,
                               int Nb, int D, const LatentParams* params, int form);
 
@@ -57,6 +58,7 @@ cudaError_t launch_fwd_solve(cudaStream_t st, TiledSym L, const double* W, size_
                              size_t vec_stride, int batch, int64_t* launches);
 cudaError_t launch_bwd_solve(cudaStream_t st, TiledSym L, const double* W, size_t w_batch_stride, double* rvec, double* avec,
                              size_t vec_stride, int batch, int64_t* launches);
+void set_solve_impl(int v);  // 1: persistent sweep kernels, one launch per direction (default); 0: one launch per tile column
 // out[b] = sum_i v[b][i]^2 (fixed order)
 cudaError_t launch_sumsq(cudaStream_t st, const double* v, size_t stride, int n, int batch, double* out);
 // y[b][R*128 + r] = add[b] + sum_J T(R,J) x[b][J*128 + :]   over a rectangular tiled matrix

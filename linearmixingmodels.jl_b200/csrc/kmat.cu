@@ -134,7 +134,7 @@ __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const 
 template <int DS>
 __global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const double* __restrict__ xpad, int N, int D,
                                                        const LatentParams* __restrict__ params, int form,
-                                                       const double* __restrict__ noise_vec, size_t noise_stride) {
+                                                       const double* __restrict__ noise_vec, size_t noise_stride, int tile0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* xa = reinterpret_cast<double*>(smem_raw);
   double* xb = xa + TILE * D;
@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const doubl
   __shared__ __align__(8) uint64_t bar;
 
   const int b = blockIdx.y;
-  // linear lower-tile index -> (I, J)
-  const int t = blockIdx.x;
+  // linear lower-tile index -> (I, J); tile0 = first tile of the first row built (rows below a prefix that is already
+  // factored: sequential conditioning extends a factor instead of rebuilding it)
+  const int t = blockIdx.x + tile0;
   int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
   while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)t) ++I;
   while ((size_t)I * (I + 1) / 2 > (size_t)t) --I;
@@ -179,17 +180,19 @@ __global__ void __launch_bounds__(256) kmat_cross_kernel(TiledRect out, const do
 static size_t kmat_smem(int D) { return (size_t)(2 * TILE * D + 2 * TILE) * sizeof(double); }
 
 cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const double* xpad, int N, int D,
-                            const LatentParams* params, int form, const double* noise_vec, size_t noise_stride) {
+                            const LatentParams* params, int form, const double* noise_vec, size_t noise_stride, int row0) {
   size_t sm = kmat_smem(D);
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kmat_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
   }
-  dim3 grid((unsigned)sym_tiles(out.nt), (unsigned)batch);
+  const int tile0 = (int)sym_tiles(row0);  // row-panel-major order: the tiles of rows >= row0 are the tail of the list
+  if (row0 >= out.nt) return cudaSuccess;
+  dim3 grid((unsigned)(sym_tiles(out.nt) - tile0), (unsigned)batch);
   if (D == 1)
-    kmat_sym_kernel<1><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form, noise_vec, noise_stride);
+    kmat_sym_kernel<1><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form, noise_vec, noise_stride, tile0);
   else
-    kmat_sym_kernel<0><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form, noise_vec, noise_stride);
+    kmat_sym_kernel<0><<<grid, 256, sm, st>>>(out, xpad, N, D, params, form, noise_vec, noise_stride, tile0);
   return cudaGetLastError();
 }
 

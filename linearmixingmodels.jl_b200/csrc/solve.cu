@@ -101,8 +101,225 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(TiledSym L, const double*
   if (t < TILE) r[k * TILE + t] -= ys[t];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent sweeps: ONE launch per direction instead of nt dependent launches (at 8 latents per
+// GPU the 128 launches per direction were launch-latency bound, 41 % of HBM peak).
+//
+// Forward, left-looking by tile ROW: CTA (I, b) owns z_I of latent b,
+//     z_I = W_I (rhs_I - sum_{K<I} L(I,K) z_K),
+// streams its row panel L(I, 0:I) -- one contiguous run of HBM, each tile read exactly once -- and consumes z_K as soon
+// as CTA (K, b) has published it (a per-(b, K) ready flag in global memory: st.release.gpu by the producer after its
+// CTA barrier + fence, ld.acquire.gpu by one polling lane of the consumer).  Backward, by tile COLUMN: CTA (J, b) owns
+//     a_J = W_J^T (rhs_J - sum_{I>J} L(I,J)^T a_I),   I = nt-1 ... J+1 (the order in which the a_I appear).
+// Dependencies only point to CTAs with a LOWER linear block index (rows ascending / columns descending, latent index
+// fastest), which the hardware dispatches first, so a resident CTA never waits for one that cannot be scheduled; a
+// bounded wait (10 s on %globaltimer) traps instead of hanging the GPU should that ever be violated.
+// The tile loads do not depend on the flags: they are issued one 16-value chunk ahead (register double buffer) so a
+// CTA that is waiting for z_K already has the first part of tile (I, K) in flight.  Summation order is fixed (per
+// thread: K ascending; then lane / warp reduction trees) -> bit-reproducible run to run.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_ready(const int* flag) {
+  if (ld_acquire_gpu(flag) != 0) return;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned ns = 32;
+  while (ld_acquire_gpu(flag) == 0) {
+    __nanosleep(ns);
+    if (ns < 512) ns <<= 1;
+    if (globaltimer_ns() - t0 > 10000000000ull) __trap();  // never hang the GPU on a scheduling assumption
+  }
+}
+// Warp 0 of the CTA: wait for vector block `blk` of latent-vector `v` and stage it (128 doubles) into xs.
+__device__ __forceinline__ void stage_ready_block(const int* flag, const double* __restrict__ v, double* xs, int lane) {
+  if (lane == 0) wait_ready(flag);
+  __syncwarp();
+  const double2* src = reinterpret_cast<const double2*>(v) + lane * 2;
+  const double2 p0 = __ldcg(src), p1 = __ldcg(src + 1);  // L2: written by another SM during this kernel
+  reinterpret_cast<double2*>(xs)[lane * 2] = p0;
+  reinterpret_cast<double2*>(xs)[lane * 2 + 1] = p1;
+}
+// All threads stored their part of the solution block; publish it.
+__device__ __forceinline__ void publish_block(int* flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release_gpu(flag, 1);
+  }
+}
+
+constexpr int SW_CH = 16;  // tile elements per thread per chunk (a 128x128 tile = 4 chunks of 16 for 256 threads)
+
+// grid nt*batch (linear index = I*batch + b), 256 threads.
+__global__ void __launch_bounds__(256, 3) fwd_sweep_kernel(TiledSym L, const double* __restrict__ W, size_t w_batch_stride,
+                                                           const double* __restrict__ rhs, double* __restrict__ sol, size_t vec_stride,
+                                                           int* __restrict__ flags, int batch) {
+  __shared__ __align__(16) double xs[2][TILE];
+  __shared__ double ys[TILE];
+  const int I = blockIdx.x / batch, b = blockIdx.x % batch, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nt = L.nt;
+  const double* row = L.tile(b, I, 0);  // tiles (I, 0..I-1) are contiguous
+  double* zb = sol + (size_t)b * vec_stride;
+  int* fl = flags + (size_t)b * nt;
+  double a0 = 0.0, a1 = 0.0;
+  double buf[SW_CH];
+  if (I > 0) {
+#pragma unroll
+    for (int u = 0; u < SW_CH; ++u) buf[u] = row[u * 256 + t];
+  }
+  for (int K = 0; K < I; ++K) {
+    if (warp == 0) stage_ready_block(fl + K, zb + (size_t)K * TILE, xs[K & 1], lane);
+    __syncthreads();
+    const double* xk = xs[K & 1];
+    const double* tile = row + (size_t)K * TT;
+#pragma unroll
+    for (int c = 0; c < 64 / SW_CH; ++c) {
+      double nxt[SW_CH];
+      const bool more = (c + 1 < 64 / SW_CH) || (K + 1 < I);
+      const double* np = tile + (c + 1) * SW_CH * 256 + t;  // chunk c+1 of this tile == chunk 0 of the next one when c = 3
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < SW_CH; ++u) nxt[u] = np[u * 256];
+      }
+#pragma unroll
+      for (int u = 0; u < SW_CH; u += 2) {
+        const double x = xk[((c * SW_CH + u) >> 1) * 4 + (t & 3)];
+        a0 = fma(buf[u], x, a0);
+        a1 = fma(buf[u + 1], x, a1);
+      }
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < SW_CH; ++u) buf[u] = nxt[u];
+      }
+    }
+  }
+  // r_I = rhs_I - (row sums) ;  z_I = W_I r_I
+  tile_gemv_n_finish(a0, a1, ys);
+  __syncthreads();
+  double* rs = xs[0];
+  if (t < TILE) rs[t] = rhs[(size_t)b * vec_stride + (size_t)I * TILE + t] - ys[t];
+  __syncthreads();
+  a0 = a1 = 0.0;
+  tile_gemv_n_acc(W + (size_t)b * w_batch_stride + (size_t)I * TT, rs, a0, a1);
+  tile_gemv_n_finish(a0, a1, ys);
+  __syncthreads();
+  if (t < TILE) zb[(size_t)I * TILE + t] = ys[t];
+  publish_block(fl + I);
+}
+
+// Per-thread partial sums of y = T^T x over one tile: thread t holds, for j = 0..31, the column c = 4j + (t&3) restricted
+// to its rows rlo = warp*8 + (t>>2)&7 and rlo + 64.  acc[j] += T(rlo, c) x[rlo] + T(rlo+64, c) x[rlo+64].
+__device__ __forceinline__ void gemv_t_reduce_store(const double (&acc)[32], double* part, double* ys) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    double v = acc[j];
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (lane < 4) part[warp * TILE + j * 4 + lane] = v;
+  }
+  __syncthreads();
+  if (t < TILE) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w * TILE + t];
+    ys[t] = s;
+  }
+  __syncthreads();
+}
+
+constexpr int SW_CHB = 8;  // the backward sweep carries 32 accumulators per thread: a shallower prefetch keeps it at 128 registers without spills
+// grid nt*batch (linear index = (nt-1-J)*batch + b), 256 threads.
+__global__ void __launch_bounds__(256, 2) bwd_sweep_kernel(TiledSym L, const double* __restrict__ W, size_t w_batch_stride,
+                                                           const double* __restrict__ rhs, double* __restrict__ sol, size_t vec_stride,
+                                                           int* __restrict__ flags, int batch) {
+  __shared__ __align__(16) double xs[2][TILE];
+  __shared__ double ys[TILE];
+  __shared__ double part[8 * TILE];
+  const int nt = L.nt;
+  const int J = nt - 1 - (int)(blockIdx.x / batch), b = blockIdx.x % batch, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int rlo = warp * 8 + ((t >> 2) & 7);
+  double* ab = sol + (size_t)b * vec_stride;
+  int* fl = flags + (size_t)b * nt;
+  double acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+  double buf[SW_CHB];
+  if (J < nt - 1) {
+    const double* tile = L.tile(b, nt - 1, J);
+#pragma unroll
+    for (int u = 0; u < SW_CHB; ++u) buf[u] = tile[u * 256 + t];
+  }
+  int par = 0;
+  for (int I = nt - 1; I > J; --I, par ^= 1) {
+    if (warp == 0) stage_ready_block(fl + I, ab + (size_t)I * TILE, xs[par], lane);
+    __syncthreads();
+    const double x0 = xs[par][rlo], x1 = xs[par][rlo + 64];
+    const double* tile = L.tile(b, I, J);
+    const double* tnext = (I - 1 > J) ? L.tile(b, I - 1, J) : tile;
+#pragma unroll
+    for (int c = 0; c < 64 / SW_CHB; ++c) {
+      double nxt[SW_CHB];
+      const bool more = (c + 1 < 64 / SW_CHB) || (I - 1 > J);
+      const double* np = (c + 1 < 64 / SW_CHB) ? tile + (c + 1) * SW_CHB * 256 + t : tnext + t;
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < SW_CHB; ++u) nxt[u] = np[u * 256];
+      }
+#pragma unroll
+      for (int u = 0; u < SW_CHB; u += 2) {
+        const int j = (c * SW_CHB + u) >> 1;
+        acc[j] = fma(buf[u], x0, acc[j]);
+        acc[j] = fma(buf[u + 1], x1, acc[j]);
+      }
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < SW_CHB; ++u) buf[u] = nxt[u];
+      }
+    }
+  }
+  gemv_t_reduce_store(acc, part, ys);
+  // r_J = rhs_J - (column sums) ;  a_J = W_J^T r_J
+  double* rs = xs[0];
+  if (t < TILE) rs[t] = rhs[(size_t)b * vec_stride + (size_t)J * TILE + t] - ys[t];
+  __syncthreads();
+  tile_gemv_t(W + (size_t)b * w_batch_stride + (size_t)J * TT, rs, ys, part);
+  if (t < TILE) ab[(size_t)J * TILE + t] = ys[t];
+  publish_block(fl + J);
+}
+
+static int g_solve_impl = 1;  // 1: persistent sweeps (default); 0: one launch per tile column
+void set_solve_impl(int v) { g_solve_impl = v; }
+
+static cudaError_t sweep_flags(cudaStream_t st, int n, int** out) {
+  cudaError_t e = cudaMallocAsync((void**)out, (size_t)n * sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  return cudaMemsetAsync(*out, 0, (size_t)n * sizeof(int), st);
+}
+
+// rvec is the right-hand side; it is left untouched by the persistent sweeps (the stepwise kernels consume it).
 cudaError_t launch_fwd_solve(cudaStream_t st, TiledSym L, const double* W, size_t w_batch_stride, double* rvec, double* zvec,
                              size_t vec_stride, int batch, int64_t* launches) {
+  if (g_solve_impl == 1) {
+    int* flags = nullptr;
+    cudaError_t e = sweep_flags(st, L.nt * batch, &flags);
+    if (e != cudaSuccess) return e;
+    fwd_sweep_kernel<<<(unsigned)(L.nt * batch), 256, 0, st>>>(L, W, w_batch_stride, rvec, zvec, vec_stride, flags, batch);
+    if (launches) ++*launches;
+    e = cudaGetLastError();
+    cudaFreeAsync(flags, st);
+    return e;
+  }
   for (int J = 0; J < L.nt; ++J) {
     dim3 grid((unsigned)(L.nt - J), (unsigned)batch);
     fwd_step_kernel<<<grid, 256, 0, st>>>(L, W, w_batch_stride, rvec, zvec, vec_stride, J);
@@ -113,6 +330,16 @@ cudaError_t launch_fwd_solve(cudaStream_t st, TiledSym L, const double* W, size_
 
 cudaError_t launch_bwd_solve(cudaStream_t st, TiledSym L, const double* W, size_t w_batch_stride, double* rvec, double* avec,
                              size_t vec_stride, int batch, int64_t* launches) {
+  if (g_solve_impl == 1) {
+    int* flags = nullptr;
+    cudaError_t e = sweep_flags(st, L.nt * batch, &flags);
+    if (e != cudaSuccess) return e;
+    bwd_sweep_kernel<<<(unsigned)(L.nt * batch), 256, 0, st>>>(L, W, w_batch_stride, rvec, avec, vec_stride, flags, batch);
+    if (launches) ++*launches;
+    e = cudaGetLastError();
+    cudaFreeAsync(flags, st);
+    return e;
+  }
   for (int J = L.nt - 1; J >= 0; --J) {
     dim3 grid((unsigned)(J + 1), (unsigned)batch);
     bwd_step_kernel<<<grid, 256, 0, st>>>(L, W, w_batch_stride, rvec, avec, vec_stride, J);
