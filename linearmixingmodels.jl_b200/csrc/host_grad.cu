@@ -235,11 +235,8 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
   std::vector<double> hg4((size_t)nl * 4, 0.0);
   if (mloc > 0) {
     const size_t per_lat = factor_bytes_per_latent(nt) + (size_t)nt * nt * TT * sizeof(double) + 6 * npad * sizeof(double);
-    size_t fr = 0, tot = 0;
-    CU(cudaMemGetInfo(&fr, &tot));
-    size_t fit = (size_t)((double)fr * 0.8) / per_lat;
-    if (fit < 1) fit = 1;
-    const int chunk = (size_t)mloc < fit ? mloc : (int)fit;
+    int chunk = 0;
+    CU(mem_fit(ctx, per_lat, mloc, &chunk));
     const int ntl = (int)sym_tiles(nt);
     CU(b_L.alloc(ctx, (size_t)chunk * sym_tiles(nt) * TT * sizeof(double)));
     CU(b_W.alloc(ctx, (size_t)chunk * nt * TT * sizeof(double)));

@@ -65,6 +65,7 @@ struct lmm_ctx {
   void* xbuf2 = nullptr;
   size_t xbuf2_bytes = 0;
   int64_t launches = 0, h2d = 0, d2h = 0;
+  size_t total_mem = 0;  // device memory size, queried once (mem_fit)
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[8];
   // latent groups run their (latency-bound) panel steps on separate streams so that one group's
@@ -136,6 +137,27 @@ struct DevBuf {
 };
 
 inline int ntiles(int n) { return (n + TILE - 1) / TILE; }
+
+// How many of `units` work items of `per_unit` bytes fit into 80 % of the free device memory (>= 1).  cudaMemGetInfo
+// synchronises with the device and costs ~0.5 ms -- as much as a whole small-N eval -- so requests below 2 % of the
+// device's memory skip it (an allocation that does not fit after all still fails cleanly with LMM_E_OOM).
+inline cudaError_t mem_fit(lmm_ctx* ctx, size_t per_unit, int units, int* chunk) {
+  size_t fr = 0, tot = 0;
+  cudaError_t e;
+  if (ctx->total_mem == 0) {
+    if ((e = cudaMemGetInfo(&fr, &tot)) != cudaSuccess) return e;
+    ctx->total_mem = tot;
+  }
+  if ((double)per_unit * (double)units <= 0.02 * (double)ctx->total_mem) {
+    *chunk = units;
+    return cudaSuccess;
+  }
+  if ((e = cudaMemGetInfo(&fr, &tot)) != cudaSuccess) return e;
+  size_t fit = (size_t)((double)fr * 0.8) / (per_unit ? per_unit : 1);
+  if (fit < 1) fit = 1;
+  *chunk = (size_t)units < fit ? units : (int)fit;
+  return cudaSuccess;
+}
 
 // Marks a factorisation that every rank of the communicator performs on identical inputs (the joint ILMM factor,
 // the batch-1 potrf primitive): with the "partition_ilmm" option such a call runs the row-cyclic multi-GPU schedule.

@@ -83,14 +83,7 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
   // ---- factor storage: all local latents when a posterior is kept, else a streamed arena
   const size_t per_lat = factor_bytes_per_latent(nt);
   int chunk = mloc;
-  if (!keep && mloc > 0) {
-    size_t fr = 0, tot = 0;
-    CU(cudaMemGetInfo(&fr, &tot));
-    size_t budget = (size_t)((double)fr * 0.80);
-    size_t fit = budget / (per_lat + 6 * npad * sizeof(double));
-    if (fit < 1) fit = 1;
-    if ((size_t)chunk > fit) chunk = (int)fit;
-  }
+  if (!keep && mloc > 0) CU(mem_fit(ctx, per_lat + 6 * npad * sizeof(double), mloc, &chunk));
   DevBuf b_L, b_W, b_alpha, b_r, b_z, b_logdet, b_quad, b_info, b_nv;
   if (noise_vec) {
     const int nl = mloc > 0 ? mloc : 1;
@@ -382,11 +375,8 @@ int post_latent_marginals(lmm_post* post, const double* d_xspad, int Ns, int nts
   const size_t nspad = (size_t)nts * TILE;
   if (nloc <= 0) return LMM_OK;
   const size_t per_lat = (size_t)nts * nt * TT * sizeof(double);
-  size_t fr = 0, tot = 0;
-  CU(cudaMemGetInfo(&fr, &tot));
-  size_t fit = (size_t)((double)fr * 0.8) / per_lat;
-  if (fit < 1) fit = 1;
-  const int chunk = (size_t)nloc < fit ? nloc : (int)fit;
+  int chunk = 0;
+  CU(mem_fit(ctx, per_lat, nloc, &chunk));
   DevBuf b_V;
   CU(b_V.alloc(ctx, (size_t)chunk * per_lat));
   const TiledSym L = post->Lsym();

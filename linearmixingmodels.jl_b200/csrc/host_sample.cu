@@ -81,11 +81,8 @@ int prior_latent_samples(lmm_ctx* ctx, const lmm_gp_desc* descs, const double* n
   DevBuf b_params, b_L, b_W, b_logdet, b_info;
   int rc = upload_params(ctx, b_params, descs, noise_all, lo, hi, D);
   if (rc) return rc;
-  size_t fr = 0, tot = 0;
-  CU(cudaMemGetInfo(&fr, &tot));
-  size_t fit = (size_t)((double)fr * 0.8) / factor_bytes_per_latent(nt);
-  if (fit < 1) fit = 1;
-  const int chunk = (size_t)nloc < fit ? nloc : (int)fit;
+  int chunk = 0;
+  CU(mem_fit(ctx, factor_bytes_per_latent(nt), nloc, &chunk));
   CU(b_L.alloc(ctx, (size_t)chunk * sym_tiles(nt) * TT * sizeof(double)));
   CU(b_W.alloc(ctx, (size_t)chunk * nt * TT * sizeof(double)));
   CU(b_logdet.alloc(ctx, (size_t)nloc * sizeof(double)));
@@ -251,11 +248,8 @@ int build_predictive(lmm_post* post, const double* xs, int Ns, const std::vector
   CU(cudaMemsetAsync(P.info.p, 0, (size_t)nl * sizeof(int), st));
   if (nloc == 0) return factor ? report_info(ctx, std::vector<int>(), post->lo, Ns, info_latent) : LMM_OK;  // collective
   const size_t per_lat = (size_t)P.nts * nt * TT * sizeof(double);
-  size_t fr = 0, tot = 0;
-  CU(cudaMemGetInfo(&fr, &tot));
-  size_t fit = (size_t)((double)fr * 0.8) / per_lat;
-  if (fit < 1) fit = 1;
-  const int chunk = (size_t)nloc < fit ? nloc : (int)fit;
+  int chunk = 0;
+  CU(mem_fit(ctx, per_lat, nloc, &chunk));
   CU(P.V.alloc(ctx, (size_t)chunk * per_lat));
   const TiledSym L = post->Lsym();
   TiledSym Call{P.C.as<double>(), P.nts, sym_tiles(P.nts) * TT};
@@ -429,11 +423,8 @@ int post_logpdf_impl(lmm_post* post, const double* xs, int Ns, double sigma2, co
       if (grad_sigma2) {
         // tr(C^{-1}) = |L^{-T}|_F²: triangular TRSM sweep on an identity, chunked by free memory
         const size_t per_lat = (size_t)P.nts * P.nts * TT * sizeof(double);
-        size_t fr = 0, totm = 0;
-        CU(cudaMemGetInfo(&fr, &totm));
-        size_t fit = (size_t)((double)fr * 0.8) / per_lat;
-        if (fit < 1) fit = 1;
-        const int chunk = (size_t)nloc < fit ? nloc : (int)fit;
+        int chunk = 0;
+        CU(mem_fit(ctx, per_lat, nloc, &chunk));
         CU(b_X.alloc(ctx, (size_t)chunk * per_lat));
         for (int c0 = 0; c0 < nloc; c0 += chunk) {
           const int nb = (c0 + chunk <= nloc) ? chunk : nloc - c0;
@@ -575,11 +566,8 @@ extern "C" int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, 
   }
   std::vector<int> hinfo(nu > 0 ? nu : 1, 0);
   if (nu > 0) {
-    size_t fr = 0, tot = 0;
-    CU(cudaMemGetInfo(&fr, &tot));
-    size_t fit = (size_t)((double)fr * 0.8) / (factor_bytes_per_latent(nt) + 4 * npad * sizeof(double));
-    if (fit < 1) fit = 1;
-    const int chunk = (size_t)nu < fit ? nu : (int)fit;
+    int chunk = 0;
+    CU(mem_fit(ctx, (factor_bytes_per_latent(nt) + 4 * npad * sizeof(double)), nu, &chunk));
     DevBuf b_L, b_W, b_r, b_z, b_logdet, b_quad, b_info, b_params, b_idx;
     CU(b_L.alloc(ctx, (size_t)chunk * sym_tiles(nt) * TT * sizeof(double)));
     CU(b_W.alloc(ctx, (size_t)chunk * nt * TT * sizeof(double)));
