@@ -104,6 +104,8 @@ const char* lmm_version(void);
  *   "gemm_direct"     variant of that direct kernel: 0 = plain (4 slices per tile, one step of prefetch), 1 / 2 =
  *                     register-ring prefetch with 4 / 8 slices per tile and the zero blocks of the triangular
  *                     inverse skipped (default 2)                 [process-wide]
+ *   "project_impl"    projection + regulariser residual (T*Y, (I - UU')Y): 1 = FP64 tensor-core (DMMA) kernel with the column
+ *                     block / row split sized to the SM count (default); 0 = register-tiled scalar-FMA kernel  [process-wide]
  *   "condition_update" lmm_post_condition on an OILMM / IndependentMOGP posterior: 1 = block-Cholesky update of each latent's
  *                     factor, L21 = K21 L11^{-T}, L22 = chol(K22 + Σ2 - L21 L21'), O(N² N₂) (default, what AbstractGPs does);
  *                     0 = re-factorise the union of the inputs, O((N + N₂)³)

@@ -194,6 +194,9 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "gemm_small") {
     if (value < 0 || value > 4096) return ctx->fail(LMM_E_ARG, "gemm_small must be in [0, 4096]");
     set_gemm_small_threshold((int)value);
+  } else if (k == "project_impl") {
+    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_UNSUPPORTED, "project_impl must be 0 or 1");
+    set_project_impl((int)value);
   } else if (k == "condition_update") {
     if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_UNSUPPORTED, "condition_update must be 0 or 1");
     ctx->condition_update = (int)value;

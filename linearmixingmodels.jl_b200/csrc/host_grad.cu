@@ -61,7 +61,7 @@ extern "C" int lmm_post_condition(lmm_post* post, const double* xs, int Ns, doub
   CU(copy_in(ctx, b_noise_new.as<double>(), hnoise.data(), (size_t)nl));
   CU(b_delta.alloc(ctx, (size_t)nl * npad2 * sizeof(double)));
   CU(cudaMemsetAsync(b_delta.p, 0, (size_t)nl * npad2 * sizeof(double), st));
-  CU(b_part.alloc(ctx, (size_t)((Ns + 15) / 16) * sizeof(double)));
+  CU(b_part.alloc(ctx, (size_t)project_max_partials(Ns) * sizeof(double)));
   if (nloc > 0) {
     CU(cudaMemcpy2DAsync(b_delta.p, npad2 * sizeof(double), post->d_delta, npad1 * sizeof(double), (size_t)N1 * sizeof(double),
                          (size_t)nloc, cudaMemcpyDeviceToDevice, st));
@@ -194,7 +194,7 @@ int latents_grad_run(lmm_ctx* ctx, bool orth, const lmm_gp_desc* latents, int m,
   if ((rc = upload_params(ctx, b_params, latents, pr.noise.data(), lo, hi, D))) return rc;
   CU(b_ty.alloc(ctx, (size_t)nl * npad * sizeof(double)));
   CU(cudaMemsetAsync(b_ty.p, 0, (size_t)nl * npad * sizeof(double), st));
-  const int nblk = (N + 15) / 16;
+  const int nblk = project_max_partials(N);
   CU(b_part.alloc(ctx, (size_t)nblk * sizeof(double)));
   CU(cudaMemsetAsync(b_part.p, 0, (size_t)nblk * sizeof(double), st));
   CU(b_resid.alloc(ctx, sizeof(double)));
@@ -557,7 +557,7 @@ extern "C" int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, in
   CU(cudaMemsetAsync(b_zero.p, 0, (size_t)m * sizeof(double), st));
   CU(b_delta.alloc(ctx, bpad * sizeof(double)));
   CU(cudaMemsetAsync(b_delta.p, 0, bpad * sizeof(double), st));
-  const int nblk = (N + 15) / 16;
+  const int nblk = project_max_partials(N);
   CU(b_part.alloc(ctx, (size_t)nblk * sizeof(double)));
   CU(cudaMemsetAsync(b_part.p, 0, (size_t)nblk * sizeof(double), st));
   CU(b_resid.alloc(ctx, sizeof(double)));

@@ -287,7 +287,7 @@ int ilmm_run(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, i
     for (int i = 0; i < m; ++i) hmeans[i] = latents[i].mean_const;
     CU(b_means.alloc(ctx, (size_t)m * sizeof(double)));
     CU(copy_in(ctx, b_means.as<double>(), hmeans.data(), (size_t)m));
-    const int nblk = (N + 15) / 16;
+    const int nblk = project_max_partials(N);
     CU(b_part.alloc(ctx, (size_t)nblk * sizeof(double)));
     CU(cudaMemsetAsync(b_part.p, 0, (size_t)nblk * sizeof(double), st));
     CU(b_resid.alloc(ctx, sizeof(double)));
@@ -671,7 +671,7 @@ int ilmm_post_logpdf(lmm_post* post, const double* xs, int Ns, double sigma2, co
   CU(copy_in(ctx, b_means.as<double>(), hmeans.data(), (size_t)m));
   CU(b_delta.alloc(ctx, bpad * sizeof(double)));
   CU(cudaMemsetAsync(b_delta.p, 0, bpad * sizeof(double), st));
-  const int nblk = (Ns + 15) / 16;
+  const int nblk = project_max_partials(Ns);
   CU(b_part.alloc(ctx, (size_t)nblk * sizeof(double)));
   CU(cudaMemsetAsync(b_part.p, 0, (size_t)nblk * sizeof(double), st));
   CU(b_resid.alloc(ctx, sizeof(double)));
@@ -816,7 +816,7 @@ int ilmm_post_condition(lmm_post* post, const double* xs, int Ns, double sigma2,
   for (int i = 0; i < m; ++i) hmeans[i] = post->descs[i].mean_const;
   CU(b_means.alloc(ctx, (size_t)m * sizeof(double)));
   CU(copy_in(ctx, b_means.as<double>(), hmeans.data(), (size_t)m));
-  CU(b_part.alloc(ctx, (size_t)((Ns + 15) / 16) * sizeof(double)));
+  CU(b_part.alloc(ctx, (size_t)project_max_partials(Ns) * sizeof(double)));
   CU(launch_project(st, d_y, Ns, p, b_T.as<double>(), m, 0, m, b_means.as<double>(), J.delta.as<double>() + N1, (size_t)N2, nullptr, nullptr,
                     b_part.as<double>(), nullptr));
   ++ctx->launches;

@@ -60,7 +60,7 @@ int latents_run(lmm_ctx* ctx, int kind, const lmm_gp_desc* latents, int m, const
   // ---- projection + residual (K2/K3)
   CU(b_ty.alloc(ctx, (size_t)(mloc > 0 ? mloc : 1) * npad * sizeof(double)));
   CU(cudaMemsetAsync(b_ty.p, 0, (size_t)(mloc > 0 ? mloc : 1) * npad * sizeof(double), st));
-  const int nblk = (N + 15) / 16;
+  const int nblk = project_max_partials(N);
   CU(b_resid_part.alloc(ctx, (size_t)nblk * sizeof(double)));
   CU(cudaMemsetAsync(b_resid_part.p, 0, (size_t)nblk * sizeof(double), st));
   CU(b_resid.alloc(ctx, sizeof(double)));

@@ -364,7 +364,7 @@ int post_logpdf_impl(lmm_post* post, const double* xs, int Ns, double sigma2, co
   CU(cudaMemsetAsync(b_zero.p, 0, (size_t)nl * sizeof(double), st));
   CU(b_ty.alloc(ctx, (size_t)nl * P.nspad * sizeof(double)));
   CU(cudaMemsetAsync(b_ty.p, 0, (size_t)nl * P.nspad * sizeof(double), st));
-  const int nblk = (Ns + 15) / 16;
+  const int nblk = project_max_partials(Ns);
   CU(b_part.alloc(ctx, (size_t)nblk * sizeof(double)));
   CU(cudaMemsetAsync(b_part.p, 0, (size_t)nblk * sizeof(double), st));
   CU(b_resid.alloc(ctx, sizeof(double)));
@@ -549,7 +549,7 @@ extern "C" int lmm_oilmm_logpdf_sweep(lmm_ctx* ctx, const lmm_gp_desc* latents, 
   CU(copy_in(ctx, b_means.as<double>(), hmeans.data(), (size_t)m));
   CU(b_ty.alloc(ctx, (size_t)m * npad * sizeof(double)));
   CU(cudaMemsetAsync(b_ty.p, 0, (size_t)m * npad * sizeof(double), st));
-  const int nblk = (N + 15) / 16;
+  const int nblk = project_max_partials(N);
   CU(b_part.alloc(ctx, (size_t)nblk * sizeof(double)));
   CU(cudaMemsetAsync(b_part.p, 0, (size_t)nblk * sizeof(double), st));
   CU(b_resid.alloc(ctx, sizeof(double)));

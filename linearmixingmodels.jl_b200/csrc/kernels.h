@@ -82,6 +82,8 @@ cudaError_t launch_rowcyclic_unpack(cudaStream_t st, TiledSym L, int s0, int s1,
 // ---- proj.cu
 // Ty[i][n] = sum_j T[i + lat0][j] Y[j][n] - mean_i  (i < mloc), written to ty[i*ty_stride + n], zero padding to ty_stride
 // resid_partial[blk] = sum over the block's columns of |Y - Q (P Y)|^2
+void set_project_impl(int v);      // 1: DMMA projection kernel (default); 0: register-tiled scalar-FMA kernel
+int project_max_partials(int N);  // size of the resid_partial buffer launch_project may write (callers zero it and sum that many)
 cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const double* T, int m, int lat0, int mloc,
                            const double* means, double* ty, size_t ty_stride, const double* P, const double* Q,
                            double* resid_partial, int* nblocks_out, double* resid_out = nullptr, double* z_out = nullptr);

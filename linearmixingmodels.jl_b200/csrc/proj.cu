@@ -5,11 +5,18 @@
 // src/ilmm.jl:157-158, :179-180 (`Y .- H*T*Y`).
 // Y is never transposed or copied: the by-outputs vector y IS the N x p column-major matrix, so
 // row j of Y is the contiguous run y[j*N ...] and every global access below is coalesced along n.
-// The projection is a skinny GEMM (m x p times p x N); at p = m = 64 its arithmetic intensity is
-// 4pmN / (8(p+m)N) = 16 flop/B, above the B200 FP64 balance (37 TFLOP/s / 6.5 TB/s = 5.7 flop/B), so
-// it is FP64-pipe bound, not HBM bound: the kernel is a register-tiled (4 x NT per thread)
-// shared-memory GEMM -- Y block staged once in smem and reused by the three products T*Y, P*Y and
-// Q*(P*Y); the residual never forms (I - UU') (O(pmN), not O(p²N)).
+//
+// The projection is three skinny GEMMs over one block of columns of Y -- T*Y, Z = P*Y and Y - Q*Z (the residual
+// never forms I - UU': O(pmN), not O(p²N)) -- i.e. 6pmN flop against 8(p+m)N bytes: 3pm/(4(p+m)) flop/B = 24 at
+// p = m = 64, 14.5 at the reference's notebook shape (p = 600, m = 20), above the B200 FP64 balance of
+// 37 TFLOP/s / 6.5 TB/s = 5.7 flop/B.  It is therefore FP64-pipe bound, and like every other true contraction in this
+// library it runs on the FP64 tensor cores: project_dmma_kernel stages the Y block once in shared memory (cp.async),
+// keeps Z in shared memory, and issues mma.m8n8k4.f64 (DMMA) for all three products.  Floor at C4: 4.0e8 flop /
+// 37 TFLOP/s = 10.8 us, i.e. at most 16.8 MB / 10.8 us = 1.55 TB/s = 24 % of the HBM peak whatever the kernel does.
+// The grid is sized for the SM count, not for the tile: the column block shrinks from 64 to 8 columns until there are
+// >= 148 CTAs, and at small N (the notebook's N = 552: 69 blocks of 8 columns) the p rows of the residual are split over
+// up to 4 CTAs per column block (each recomputes the small Z), where the round-1 kernel ran 18 CTAs on 148 SMs.
+// project_kernel (round 1: register-tiled scalar-FMA GEMM) is kept selectable ("project_impl" = 0) as the cross-check.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -124,6 +131,195 @@ __global__ void __launch_bounds__(256) project_kernel(const double* __restrict__
   if (t == 0) resid_partial[blockIdx.x] = red[0];
 }
 
+// ------------------------------------------------------------------------------------------------
+// DMMA projection kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884q(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+struct ProjArgs {
+  const double* y; int N, p;
+  const double* T; int m, lat0, mloc;
+  const double* means; double* ty; size_t ty_stride;
+  const double* P; const double* Q;
+  double* resid_partial; double* resid_out; double* z_out;
+  int psplit;  // CTAs per column block along the p rows of the residual (grid.y)
+};
+
+// One warp: C[8 x 8*NCB] (+)= A[8 x K] * Bs[K x 8*NCB] for row block `rb` of A (column-major, leading dimension lda,
+// `rows` valid rows starting at global row a_row0) and the column blocks cb0 .. cb0+NCB-1 of the shared operand Bs
+// ([K4][LD], K4 = K rounded up to 4, rows beyond K are zero).  mma.m8n8k4: lane = (r, k) holds A[r][k] with r = lane/4,
+// k = lane%4; B[k][n] with k = lane%4, n = lane/4; C[r][2*(lane%4) + {0,1}].  The next k-step's A fragment is fetched
+// (through L1) while the current one feeds the tensor pipe.
+template <int NCB>
+__device__ __forceinline__ void warp_gemm(const double* __restrict__ A, int lda, int a_row0, int rows, int rb, const double* Bs, int LD,
+                                          int K, int cb0, double (&acc)[NCB][2]) {
+  const int lane = threadIdx.x & 31, r = lane >> 2, k = lane & 3;
+  const int row = rb * 8 + r;
+  const bool rok = row < rows;
+  const double* ap = A + (size_t)(a_row0 + row);
+  const double* bp = Bs + (size_t)k * LD + cb0 * 8 + r;
+  const int ksteps = (K + 3) >> 2;
+  double a = (rok && k < K) ? __ldg(ap + (size_t)k * lda) : 0.0;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const int kn = (ks + 1) * 4 + k;
+    const double an = (rok && kn < K) ? __ldg(ap + (size_t)kn * lda) : 0.0;
+    const double* b = bp + (size_t)ks * 4 * LD;
+#pragma unroll
+    for (int c = 0; c < NCB; ++c) dmma884q(acc[c][0], acc[c][1], a, b[c * 8]);
+    a = an;
+  }
+}
+
+// grid (ceil(N / NB), psplit), 256 threads.  NB columns of Y per CTA; LD = NB + 8 for NB >= 16 (row stride = 8 mod 16
+// doubles: the 4 x 8 B-fragment of a warp falls into two conflict-free 128-byte wavefronts), 8 for NB = 8.
+template <int NB>
+__global__ void __launch_bounds__(256) project_dmma_kernel(ProjArgs a) {
+  constexpr int LD = NB >= 16 ? NB + 8 : NB;
+  constexpr int NCBT = NB / 8;              // 8-column blocks per CTA
+  constexpr int NCB = NCBT >= 4 ? 4 : NCBT;  // column blocks per warp task
+  constexpr int NCG = NCBT / NCB;           // column groups
+  extern __shared__ __align__(16) double sm[];
+  const int p = a.p, m = a.m, N = a.N;
+  const int p4 = (p + 3) & ~3, m4 = (m + 3) & ~3;
+  double* Ys = sm;                    // [p4][LD]
+  double* Zs = sm + (size_t)p4 * LD;  // [m4][LD]
+  __shared__ double red[8];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, r = lane >> 2, q = lane & 3;
+  const int nb0 = blockIdx.x * NB;
+
+  // ---- stage the Y block (zero beyond p rows / N columns); Z rows beyond m are zeroed once
+  for (int idx = t; idx < p4 * NB; idx += 256) {
+    const int j = idx / NB, nn = idx % NB;
+    double* dst = Ys + (size_t)j * LD + nn;
+    if (j < p && nb0 + nn < N) cp_async8(dst, a.y + (size_t)j * N + nb0 + nn);
+    else *dst = 0.0;
+  }
+  for (int idx = t; idx < (m4 - m) * NB; idx += 256) Zs[(size_t)(m + idx / NB) * LD + idx % NB] = 0.0;
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const bool same_tp = a.P != nullptr && a.P == a.T && a.lat0 == 0 && a.mloc == m;  // general ILMM: Z = T Y is the projection itself
+  // ---- Ty = T[lat0 : lat0 + mloc, :] Y - mean     (slice 0 only)
+  if (blockIdx.y == 0 && !same_tp) {
+    const int nrb = (a.mloc + 7) >> 3;
+    for (int task = warp; task < nrb * NCG; task += 8) {
+      const int rb = task / NCG, cb0 = (task % NCG) * NCB;
+      double acc[NCB][2];
+#pragma unroll
+      for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+      warp_gemm<NCB>(a.T, m, a.lat0, a.mloc, rb, Ys, LD, p, cb0, acc);
+      const int row = rb * 8 + r;
+      if (row < a.mloc) {
+        const double mu = a.means[row];
+#pragma unroll
+        for (int c = 0; c < NCB; ++c) {
+          const int col = nb0 + (cb0 + c) * 8 + 2 * q;
+          double* o = a.ty + (size_t)row * a.ty_stride + col;
+          if (col < N) o[0] = acc[c][0] - mu;
+          if (col + 1 < N) o[1] = acc[c][1] - mu;
+        }
+      }
+    }
+  }
+  if (a.P == nullptr) return;
+  // ---- Z = P Y  (m x NB) into shared memory (every slice needs it)
+  {
+    const int nrb = (m + 7) >> 3;
+    for (int task = warp; task < nrb * NCG; task += 8) {
+      const int rb = task / NCG, cb0 = (task % NCG) * NCB;
+      double acc[NCB][2];
+#pragma unroll
+      for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+      warp_gemm<NCB>(a.P, m, 0, m, rb, Ys, LD, p, cb0, acc);
+      const int row = rb * 8 + r;
+      if (row < m) {
+        const double mu = same_tp ? a.means[row] : 0.0;
+#pragma unroll
+        for (int c = 0; c < NCB; ++c) {
+          const int lc = (cb0 + c) * 8 + 2 * q, col = nb0 + lc;
+          Zs[(size_t)row * LD + lc] = acc[c][0];
+          Zs[(size_t)row * LD + lc + 1] = acc[c][1];
+          if (blockIdx.y == 0) {
+            if (a.z_out) {
+              if (col < N) a.z_out[(size_t)row * N + col] = acc[c][0];
+              if (col + 1 < N) a.z_out[(size_t)row * N + col + 1] = acc[c][1];
+            }
+            if (same_tp) {
+              double* o = a.ty + (size_t)row * a.ty_stride + col;
+              if (col < N) o[0] = acc[c][0] - mu;
+              if (col + 1 < N) o[1] = acc[c][1] - mu;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- R = Y - Q Z over this slice's rows of p; summed squares in a fixed order
+  double ss = 0.0;
+  {
+    const int nrb = (p + 7) >> 3;
+    const int rb_lo = (int)((long long)nrb * blockIdx.y / a.psplit), rb_hi = (int)((long long)nrb * (blockIdx.y + 1) / a.psplit);
+    for (int task = warp; task < (rb_hi - rb_lo) * NCG; task += 8) {
+      const int rb = rb_lo + task / NCG, cb0 = (task % NCG) * NCB;
+      double acc[NCB][2];
+#pragma unroll
+      for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+      warp_gemm<NCB>(a.Q, p, 0, p, rb, Zs, LD, m, cb0, acc);
+      const int row = rb * 8 + r;
+      if (row < p) {
+#pragma unroll
+        for (int c = 0; c < NCB; ++c) {
+          const int lc = (cb0 + c) * 8 + 2 * q, col = nb0 + lc;
+          const double r0 = Ys[(size_t)row * LD + lc] - acc[c][0];      // columns beyond N hold Y = 0 and Z = 0: r = 0
+          const double r1 = Ys[(size_t)row * LD + lc + 1] - acc[c][1];
+          ss = fma(r0, r0, ss);
+          ss = fma(r1, r1, ss);
+          if (a.resid_out) {
+            if (col < N) a.resid_out[(size_t)row * N + col] = r0;
+            if (col + 1 < N) a.resid_out[(size_t)row * N + col + 1] = r1;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w];
+    a.resid_partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+static int g_project_impl = 1;  // 1: DMMA kernel (default); 0: round-1 register-tiled scalar-FMA kernel
+void set_project_impl(int v) { g_project_impl = v; }
+
+// Upper bound of the number of residual partial sums launch_project writes for N columns (callers size and zero the
+// buffer with it, then sum that many entries).
+int project_max_partials(int N) { return ((N + 7) / 8) * 4; }
+
+template <int NB>
+static cudaError_t launch_project_dmma_nb(cudaStream_t st, const ProjArgs& a, int nblocks, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(project_dmma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((unsigned)nblocks, (unsigned)a.psplit);
+  project_dmma_kernel<NB><<<grid, 256, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 int project_block_cols(int p, int m) {
   // largest column block whose Y and Z tiles fit in shared memory (<= 200 KB)
   for (int nt : {4, 2, 1})
@@ -134,6 +330,45 @@ int project_block_cols(int p, int m) {
 cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const double* T, int m, int lat0, int mloc,
                            const double* means, double* ty, size_t ty_stride, const double* P, const double* Q,
                            double* resid_partial, int* nblocks_out, double* resid_out, double* z_out) {
+  if (g_project_impl == 1) {
+    const int p4 = (p + 3) & ~3, m4 = (m + 3) & ~3;
+    int num_sms = 148;
+    {
+      static int cached_sms[64] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cached_sms[dev & 63] == 0) cudaDeviceGetAttribute(&cached_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+      if (cached_sms[dev & 63] > 0) num_sms = cached_sms[dev & 63];
+    }
+    // the widest column block that fits in shared memory and still gives every SM a CTA; else the narrowest that fits
+    int nb = 0;
+    for (int c : {64, 32, 16, 8}) {
+      const size_t sm_c = (size_t)(p4 + m4) * (c >= 16 ? c + 8 : c) * sizeof(double);
+      if (sm_c > 200 * 1024) continue;
+      nb = c;
+      if ((N + c - 1) / c >= num_sms) break;
+    }
+    if (nb != 0) {
+      const int nblocks = (N + nb - 1) / nb;
+      ProjArgs a{y, N, p, T, m, lat0, mloc, means, ty, ty_stride, P, Q, resid_partial, resid_out, z_out, 1};
+      if (P != nullptr && nblocks < num_sms) {  // small N: split the p rows of the residual over up to 4 CTAs per column block
+        int s = num_sms / nblocks;
+        const int nrb = (p + 7) / 8;
+        if (s > 4) s = 4;
+        if (s > nrb) s = nrb;
+        if (s >= 1) a.psplit = s;
+      }
+      if (nblocks_out) *nblocks_out = nblocks * a.psplit;
+      const size_t smem = (size_t)(p4 + m4) * (nb >= 16 ? nb + 8 : nb) * sizeof(double);
+      switch (nb) {
+        case 64: return launch_project_dmma_nb<64>(st, a, nblocks, smem);
+        case 32: return launch_project_dmma_nb<32>(st, a, nblocks, smem);
+        case 16: return launch_project_dmma_nb<16>(st, a, nblocks, smem);
+        default: return launch_project_dmma_nb<8>(st, a, nblocks, smem);
+      }
+    }
+    // p + m too large for one column block of 8 in shared memory: fall through to the register-tiled kernel's own check
+  }
   const int nbcols = project_block_cols(p, m);
   if (nbcols == 0) return cudaErrorInvalidValue;
   const int nblocks = (N + nbcols - 1) / nbcols;

@@ -977,3 +977,32 @@ def test_block_update_is_cheap(lmm):
         post2 = lmm.posterior(post1(mo(x2), 0.1), y2)
         best = min(best, (time.perf_counter() - t0) * 1e3)
     assert best < 0.25 * fresh_ms, (best, fresh_ms)
+
+
+@pytest.mark.parametrize("N,p,m", [(50, 3, 2), (552, 600, 20), (1000, 64, 64), (300, 37, 5), (2050, 130, 33)])
+def test_project_dmma_matches_scalar_kernel_and_oracle(lmm, N, p, m):
+    """The FP64 tensor-core projection kernel (T*Y, (I - UU')Y, residual norm; every column-block width and the p-row split
+    used at small N) against the round-1 scalar-FMA kernel and the oracle: projected rows δ_i, regulariser, logpdf.
+    (552, 600, 20) is the reference's published notebook shape."""
+    x, xs, U, S, fs, y = make_problem(N, p, m, 5, seed=N + p, means=True)
+    om = o.OILMMModel(fs, U, S)
+    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
+    fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+    ctx = lmm.default_context()
+    res = {}
+    try:
+        for impl in (0, 1):
+            ctx.set_option("project_impl", impl)
+            post = lmm.posterior(fx, y)
+            res[impl] = (lmm.logpdf_terms(fx, y), post.f.fs[0].delta, post.f.fs[m - 1].delta)
+    finally:
+        ctx.set_option("project_impl", 1)
+    T, ST = o.project_orthogonal(U, S, 0.1)
+    Y = o.reshape_y(y, N)
+    assert_isapprox(res[1][1], T[0] @ Y - fs[0].mean_const, 1e-12, "projected row 0")
+    assert_isapprox(res[1][2], T[m - 1] @ Y - fs[m - 1].mean_const, 1e-12, "projected last row")
+    assert_isapprox(res[1][1], res[0][1], 1e-12, "DMMA vs scalar projection")
+    reg = o.regulariser_orthogonal(U, S, 0.1, Y)
+    assert rel(res[1][0][m], reg) < RTOL and rel(res[0][0][m], reg) < RTOL
+    ref_terms, _ = o.oilmm_logpdf_terms(om, x, 0.1, y)
+    np.testing.assert_allclose(res[1][0][:m], ref_terms, rtol=RTOL)
