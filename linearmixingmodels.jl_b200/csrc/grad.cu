@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) kgrad_kernel(TiledSym negCinv, const doub
 cudaError_t launch_kgrad(cudaStream_t st, TiledSym negCinv, int batch, const double* xpad, int N, int D, const LatentParams* params,
                          const double* alpha, size_t alpha_stride, int form, double* partial) {
   const size_t smem = (size_t)(2 * TILE * D + 4 * TILE) * sizeof(double);
-  if (smem > 48 * 1024) {
+  if (smem + 1024 > 48 * 1024) {  // static shared memory counts against the default limit too
     cudaError_t e = cudaFuncSetAttribute(kgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) block_trace_kernel(TiledSym negCinv, cons
 cudaError_t launch_kgrad_joint(cudaStream_t st, TiledSym negCinv, const double* x, int N, int D, const LatentParams* params, int m,
                                const double* alpha, int form, double* partial, double* out3, double* B) {
   const size_t smem = (size_t)(2 * TILE * D + 4 * TILE) * sizeof(double);
-  if (smem > 48 * 1024) {
+  if (smem + 1024 > 48 * 1024) {  // static shared memory counts against the default limit too
     cudaError_t e = cudaFuncSetAttribute(kgrad_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }

@@ -182,7 +182,7 @@ static size_t kmat_smem(int D) { return (size_t)(2 * TILE * D + 2 * TILE) * size
 cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const double* xpad, int N, int D,
                             const LatentParams* params, int form, const double* noise_vec, size_t noise_stride, int row0) {
   size_t sm = kmat_smem(D);
-  if (sm > 48 * 1024) {
+  if (sm + 1024 > 48 * 1024) {  // static shared memory counts against the default limit too
     cudaError_t e = cudaFuncSetAttribute(kmat_sym_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
   }
@@ -199,7 +199,7 @@ cudaError_t launch_kmat_sym(cudaStream_t st, TiledSym out, int batch, const doub
 cudaError_t launch_kmat_cross(cudaStream_t st, TiledRect out, int batch, const double* xa_pad, int Na, const double* xb_pad,
                               int Nb, int D, const LatentParams* params, int form) {
   size_t sm = kmat_smem(D);
-  if (sm > 48 * 1024) {
+  if (sm + 1024 > 48 * 1024) {  // static shared memory counts against the default limit too
     cudaError_t e = cudaFuncSetAttribute(kmat_cross_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
   }

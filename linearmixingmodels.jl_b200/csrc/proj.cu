@@ -311,7 +311,7 @@ int project_max_partials(int N) { return ((N + 7) / 8) * 4; }
 
 template <int NB>
 static cudaError_t launch_project_dmma_nb(cudaStream_t st, const ProjArgs& a, int nblocks, size_t smem) {
-  if (smem > 48 * 1024) {
+  if (smem + 1024 > 48 * 1024) {  // static shared memory counts against the 48 KB default limit too
     cudaError_t e = cudaFuncSetAttribute(project_dmma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
@@ -377,7 +377,7 @@ cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const
   cudaError_t e = cudaSuccess;
 #define LMM_LAUNCH_PROJECT(NT_)                                                                                          \
   do {                                                                                                                    \
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(project_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (smem + 4096 > 48 * 1024) e = cudaFuncSetAttribute(project_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                       \
     project_kernel<NT_><<<nblocks, 256, smem, st>>>(y, N, p, T, m, lat0, mloc, means, ty, ty_stride, P, Q, resid_partial, resid_out, z_out); \
   } while (0)
