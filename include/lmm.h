@@ -44,26 +44,51 @@ extern "C" {
 #define LMM_E_OOM (-7)            /* device memory exhausted                                  */
 
 /* Base kernels (KernelFunctions.jl): SEKernel, Matern32Kernel, Matern52Kernel, ExponentialKernel (= Matern12Kernel,
- * κ(d) = exp(-d)) and RationalQuadraticKernel(α) (κ(d²) = (1 + d²/(2α))^(-α), α in `param`). */
+ * κ(d) = exp(-d)), RationalQuadraticKernel(α) (κ(d²) = (1 + d²/(2α))^(-α), α in `param`) and PeriodicKernel(r)
+ * (metric Sinus(r): κ = exp(-0.5 Σ_k (sinpi(x_k - x'_k) / r)²), one r for all dimensions, in `param`). */
 #define LMM_KERNEL_SE 0
 #define LMM_KERNEL_MATERN32 1
 #define LMM_KERNEL_MATERN52 2
 #define LMM_KERNEL_EXPONENTIAL 3
 #define LMM_KERNEL_RATIONAL_QUADRATIC 4
+#define LMM_KERNEL_PERIODIC 5
 
-/* One latent `GP(mean_const, variance * (base_kernel ∘ ScaleTransform(inv_lengthscale) [∘ ARDTransform(ard)]))`.
- * Inputs are multiplied by inv_lengthscale (and, per dimension, by ard[k]) BEFORE distances are taken
- * (KernelFunctions semantics). */
+/* Composite kernels (KernelFunctions `k1 + k2` = KernelSum, `k1 * k2` = KernelProduct; the reference accepts any
+ * AbstractGP latent, src/independent_mogp.jl:10-12): a flat sum or product of up to LMM_MAX_TERMS scaled, stretched base
+ * kernels.  Term 0 is the descriptor's own (kind, variance, inv_lengthscale, ard, param); terms 1.. are `extra[0..n_extra)`.
+ *   LMM_COMPOSE_SUM:      k(x,x') = Σ_t variance_t κ_t(s_t x, s_t x')     (seasonal + trend latents)
+ *   LMM_COMPOSE_PRODUCT:  k(x,x') = Π_t variance_t κ_t(s_t x, s_t x')     (locally periodic latents)
+ * Each term is evaluated exactly like a single kernel (own input scaling, own pairwise distances), then combined left
+ * to right, as KernelFunctions' kernelmatrix(::KernelSum / ::KernelProduct) does. */
+#define LMM_COMPOSE_NONE 0
+#define LMM_COMPOSE_SUM 1
+#define LMM_COMPOSE_PRODUCT 2
+#define LMM_MAX_TERMS 4
+typedef struct lmm_kernel_term {
+  int32_t kind;           /* LMM_KERNEL_*                                   */
+  int32_t reserved;       /* must be 0                                      */
+  double variance;        /* ScaledKernel σ² of this term                   */
+  double inv_lengthscale; /* ScaleTransform s of this term                  */
+  double param;           /* shape parameter (α / r) of this term's kernel  */
+  const double* ard;      /* ARDTransform multipliers of this term (D values) or NULL */
+} lmm_kernel_term;
+
+/* One latent `GP(mean_const, variance * (base_kernel ∘ ScaleTransform(inv_lengthscale) [∘ ARDTransform(ard)]))`, optionally
+ * summed / multiplied with further terms (above).  Inputs are multiplied by inv_lengthscale (and, per dimension, by ard[k])
+ * BEFORE distances are taken (KernelFunctions semantics). */
 #define LMM_MAX_ARD 8
 typedef struct lmm_gp_desc {
   int32_t kind;           /* LMM_KERNEL_*                                   */
-  int32_t reserved;       /* must be 0                                      */
+  int32_t compose;        /* LMM_COMPOSE_NONE (single kernel), _SUM or _PRODUCT over term 0 and `extra` */
   double variance;        /* ScaledKernel σ² (1.0 for a plain kernel)       */
   double inv_lengthscale; /* ScaleTransform s (1.0 for a plain kernel)      */
   double mean_const;      /* ZeroMean -> 0.0; ConstMean(c) -> c             */
   const double* ard;      /* ARDTransform v: D positive per-dimension multipliers (D <= LMM_MAX_ARD), or NULL;
                              read during the call only (posterior handles keep their own copy)           */
-  double param;           /* shape parameter of the base kernel: α of RationalQuadraticKernel; else ignored */
+  double param;           /* shape parameter of the base kernel: α of RationalQuadraticKernel, r of PeriodicKernel; else ignored */
+  int32_t n_extra;        /* number of further terms, 0 .. LMM_MAX_TERMS - 1 (must be 0 when compose == LMM_COMPOSE_NONE) */
+  int32_t reserved2;      /* must be 0                                      */
+  const lmm_kernel_term* extra; /* n_extra terms, read during the call only (or NULL)                        */
 } lmm_gp_desc;
 
 typedef struct lmm_ctx lmm_ctx;   /* owns device, stream, memory pool, optional NCCL communicator */

@@ -28,16 +28,33 @@ class PosDefException(np.linalg.LinAlgError):
         self.latent = latent
 
 
-class GpDesc(C.Structure):
+class KernelTerm(C.Structure):  # lmm_kernel_term: one further term of a composite (sum / product) kernel
     _fields_ = [
         ("kind", C.c_int32),
         ("reserved", C.c_int32),
         ("variance", C.c_double),
         ("inv_lengthscale", C.c_double),
+        ("param", C.c_double),
+        ("ard", C.c_void_p),
+    ]
+
+
+class GpDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("compose", C.c_int32),  # 0 single kernel, 1 KernelSum, 2 KernelProduct over this term and `extra`
+        ("variance", C.c_double),
+        ("inv_lengthscale", C.c_double),
         ("mean_const", C.c_double),
         ("ard", C.c_void_p),  # const double*: D per-dimension multipliers (ARDTransform) or NULL
-        ("param", C.c_double),  # α of RationalQuadraticKernel
+        ("param", C.c_double),  # α of RationalQuadraticKernel, r of PeriodicKernel
+        ("n_extra", C.c_int32),
+        ("reserved2", C.c_int32),
+        ("extra", C.c_void_p),  # const lmm_kernel_term*: n_extra further terms or NULL
     ]
+
+    def __init__(self, kind=0, compose=0, variance=1.0, inv_lengthscale=1.0, mean_const=0.0, ard=None, param=1.0, n_extra=0, reserved2=0, extra=None):
+        super().__init__(kind, compose, variance, inv_lengthscale, mean_const, ard, param, n_extra, reserved2, extra)
 
 
 _dp = C.POINTER(C.c_double)

@@ -29,7 +29,7 @@ from . import _lib
 from ._lib import GpDesc, PosDefException, as_f64, ptr
 
 __all__ = [
-    "SEKernel", "SqExponentialKernel", "Matern32Kernel", "Matern52Kernel", "ExponentialKernel", "Matern12Kernel", "RationalQuadraticKernel", "ScaleTransform", "ARDTransform", "with_lengthscale",
+    "SEKernel", "SqExponentialKernel", "Matern32Kernel", "Matern52Kernel", "ExponentialKernel", "Matern12Kernel", "RationalQuadraticKernel", "PeriodicKernel", "ScaleTransform", "ARDTransform", "with_lengthscale",
     "GP", "MOInputIsotopicByOutputs", "MOInputIsotopicByFeatures", "ColVecs", "RowVecs",
     "ILMM", "OILMM", "Orthogonal", "IndependentMOGP", "independent_mogp", "get_latent_gp",
     "FiniteGP", "Normal", "logpdf", "posterior", "mean_and_var", "mean", "var", "marginals", "rand", "cov", "mean_and_cov",
@@ -140,20 +140,63 @@ def set_default_context(ctx: Optional[Context]) -> None:
 # --------------------------------------------------------------------------------------------
 @dataclass(frozen=True)
 class Kernel:
+    """`variance * (base ∘ ScaleTransform(inv_lengthscale) [∘ ARDTransform(ard)])`, optionally a flat KernelSum / KernelProduct
+    (`k1 + k2`, `k1 * k2`, up to 4 terms) of such kernels: `terms` holds the further terms, `op` 1 = sum, 2 = product."""
+
     kind: int
     variance: float = 1.0
     inv_lengthscale: float = 1.0
     ard: Optional[tuple] = None  # ARDTransform multipliers (one per input dimension)
-    param: float = 1.0  # shape parameter of the base kernel (α of RationalQuadraticKernel)
+    param: float = 1.0  # shape parameter of the base kernel (α of RationalQuadraticKernel, r of PeriodicKernel)
+    op: int = 0  # 0 single kernel, 1 KernelSum, 2 KernelProduct (LMM_COMPOSE_*)
+    terms: tuple = ()  # the further terms of a composite kernel (single Kernels)
+
+    def _single(self) -> "Kernel":
+        return Kernel(self.kind, self.variance, self.inv_lengthscale, self.ard, self.param)
+
+    def all_terms(self) -> tuple:
+        return (self._single(),) + self.terms
+
+    @property
+    def kdiag(self) -> float:
+        """k(x, x): κ(0) = 1 for every supported base kernel, so the sum / product of the term variances."""
+        v = self.variance
+        for t in self.terms:
+            v = v * t.variance if self.op == 2 else v + t.variance
+        return v
+
+    @staticmethod
+    def _from_terms(op: int, ts: tuple) -> "Kernel":
+        if len(ts) > 4:
+            raise TypeError("a composite kernel has at most 4 terms (LMM_MAX_TERMS)")
+        t0 = ts[0]
+        return Kernel(t0.kind, t0.variance, t0.inv_lengthscale, t0.ard, t0.param, op if len(ts) > 1 else 0, tuple(ts[1:]))
+
+    @staticmethod
+    def _combine(op: int, a: "Kernel", b: "Kernel") -> "Kernel":
+        for k in (a, b):
+            if k.op not in (0, op):
+                raise TypeError("liblmm supports flat sums or flat products of base kernels (no sum of products / product of sums)")
+        return Kernel._from_terms(op, a.all_terms() + b.all_terms())
+
+    def __add__(self, other):  # KernelFunctions `k1 + k2` -> KernelSum
+        if not isinstance(other, Kernel):
+            return NotImplemented
+        return Kernel._combine(1, self, other)
 
     def __rmul__(self, s):  # `0.5 * SEKernel()` -> ScaledKernel
         if not (isinstance(s, (int, float)) and s > 0):
             raise TypeError("kernel scale must be a positive real")
-        return Kernel(self.kind, self.variance * float(s), self.inv_lengthscale, self.ard, self.param)
+        if self.op == 1:  # c (k1 + k2) = c k1 + c k2
+            return Kernel._from_terms(1, tuple(Kernel(t.kind, t.variance * float(s), t.inv_lengthscale, t.ard, t.param) for t in self.all_terms()))
+        return Kernel(self.kind, self.variance * float(s), self.inv_lengthscale, self.ard, self.param, self.op, self.terms)
 
-    __mul__ = __rmul__
+    def __mul__(self, other):  # `k1 * k2` -> KernelProduct; `k * 0.5` -> ScaledKernel
+        if isinstance(other, Kernel):
+            return Kernel._combine(2, self, other)
+        return self.__rmul__(other)
 
-    def compose(self, t) -> "Kernel":  # `k ∘ ScaleTransform(s)` / `k ∘ ARDTransform(v)`: inputs are scaled before distances
+    def _transform_single(self, t) -> "Kernel":
         if isinstance(t, ARDTransform):
             v = tuple(float(a) for a in t.v)
             if self.ard is not None:
@@ -162,6 +205,11 @@ class Kernel:
                 v = tuple(a * b for a, b in zip(self.ard, v))
             return Kernel(self.kind, self.variance, self.inv_lengthscale, v, self.param)
         return Kernel(self.kind, self.variance, self.inv_lengthscale * t.s, self.ard, self.param)
+
+    def compose(self, t) -> "Kernel":
+        """`k ∘ ScaleTransform(s)` / `k ∘ ARDTransform(v)`: inputs are scaled before distances are taken; the transform of a
+        KernelSum / KernelProduct feeds every term."""
+        return Kernel._from_terms(self.op, tuple(k._transform_single(t) for k in self.all_terms()))
 
     __matmul__ = compose
 
@@ -206,6 +254,13 @@ def RationalQuadraticKernel(alpha: float = 2.0) -> Kernel:  # κ(d²) = (1 + d²
     return Kernel(4, param=float(alpha))
 
 
+def PeriodicKernel(r: float = 1.0) -> Kernel:
+    """KernelFunctions `PeriodicKernel(; r)`: κ = exp(-0.5 Σ_k (sinpi(x_k - x'_k) / r)²) (metric `Sinus(r)`), one r for all dimensions."""
+    if not r > 0:
+        raise ValueError("PeriodicKernel needs r > 0")
+    return Kernel(5, param=float(r))
+
+
 def with_lengthscale(k: Kernel, l: float) -> Kernel:
     return k.compose(ScaleTransform(1.0 / float(l)))
 
@@ -226,7 +281,7 @@ class GP(AbstractGP):
         else:
             raise TypeError("GP(kernel) or GP(mean_const, kernel)")
         if not isinstance(self.kernel, Kernel):
-            raise TypeError("unsupported kernel type (liblmm supports SE / Matern32 / Matern52, scaled and stretched)")
+            raise TypeError("unsupported kernel type (liblmm supports SE / Matern32 / Matern52 / Exponential / RationalQuadratic / Periodic, scaled, stretched, summed or multiplied)")
 
     def __eq__(self, other):
         return isinstance(other, GP) and (self.mean_const, self.kernel) == (other.mean_const, other.kernel)
@@ -495,15 +550,26 @@ def unpack(fx: FiniteGP):
 
 def _descs(fs: Sequence[GP]):
     arr = (GpDesc * len(fs))()
-    keep = []  # the ARD arrays must outlive the call; they ride on the ctypes array
+    keep = []  # the ARD / extra-term arrays must outlive the call; they ride on the ctypes array
+
+    def ard_ptr(k):
+        if k.ard is None:
+            return None
+        a = np.ascontiguousarray(k.ard, dtype=np.float64)
+        keep.append(a)
+        return a.ctypes.data
+
     for i, f in enumerate(fs):
         g = f.prior if isinstance(f, PosteriorGP) else f
-        ard = None
-        if g.kernel.ard is not None:
-            a = np.ascontiguousarray(g.kernel.ard, dtype=np.float64)
-            keep.append(a)
-            ard = a.ctypes.data
-        arr[i] = GpDesc(g.kernel.kind, 0, g.kernel.variance, g.kernel.inv_lengthscale, g.mean_const, ard, g.kernel.param)
+        k = g.kernel
+        extra, n_extra = None, len(k.terms)
+        if n_extra:
+            ex = (_lib.KernelTerm * n_extra)()
+            for t, q in enumerate(k.terms):
+                ex[t] = _lib.KernelTerm(q.kind, 0, q.variance, q.inv_lengthscale, q.param, ard_ptr(q))
+            keep.append(ex)
+            extra = C.cast(ex, C.c_void_p)
+        arr[i] = GpDesc(k.kind, k.op if n_extra else 0, k.variance, k.inv_lengthscale, g.mean_const, ard_ptr(k), k.param, n_extra, 0, extra)
     arr._keep = keep
     return arr
 
@@ -756,7 +822,7 @@ def mean_and_var(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
         return M, V
     if isinstance(f, GP):  # AbstractGPs `mean_and_var(f(x, σ²))` for a prior GP: (m(x), diag K + σ²)
         Ns = _npoints(fx.x)
-        return np.full(Ns, f.mean_const), np.full(Ns, f.kernel.variance + fx.sigma2)
+        return np.full(Ns, f.mean_const), np.full(Ns, f.kernel.kdiag + fx.sigma2)
     owner = _post_owner(fx)
     needs_device = owner is not None or isinstance(f, ILMM)
     ctx = _ctx_of(fx) if needs_device else None
@@ -791,7 +857,7 @@ def mean_and_var(fx: FiniteGP) -> Tuple[np.ndarray, np.ndarray]:
             raise RuntimeError("out dim of x != out dim of f.")
         # prior: mean const, var = variance + σ² (src/independent_mogp.jl:50-57); trivial, no kernel needed
         M = np.concatenate([np.full(Ns, g.mean_const) for g in f.fs])
-        V = np.concatenate([np.full(Ns, g.kernel.variance + fx.sigma2) for g in f.fs])
+        V = np.concatenate([np.full(Ns, g.kernel.kdiag + fx.sigma2) for g in f.fs])
     else:
         raise TypeError(f"mean_and_var not defined for FiniteGP of {type(f).__name__}")
     if reorder is not None:

@@ -55,20 +55,43 @@ void shard_range(const lmm_ctx* ctx, int m, int& lo, int& hi) {
   hi = (int)(((int64_t)m * (ctx->rank + 1)) / ctx->nranks);
 }
 
+static int check_term(lmm_ctx* ctx, int kind, double variance, double inv_ls, double param, const double* ard, int D) {
+  if (kind < 0 || kind > LMM_KERNEL_PERIODIC)
+    return ctx->fail(LMM_E_UNSUPPORTED, "unsupported kernel kind (SE, Matern32, Matern52, Exponential, RationalQuadratic, Periodic)");
+  if (kind == LMM_KERNEL_RATIONAL_QUADRATIC && !(param > 0.0)) return ctx->fail(LMM_E_ARG, "RationalQuadraticKernel needs α > 0 in `param`");
+  if (kind == LMM_KERNEL_PERIODIC && !(param > 0.0)) return ctx->fail(LMM_E_ARG, "PeriodicKernel needs r > 0 in `param`");
+  if (!(variance > 0.0) || !(inv_ls > 0.0)) return ctx->fail(LMM_E_ARG, "kernel variance and inv_lengthscale must be positive");
+  if (ard) {
+    if (D > LMM_MAX_ARD) return ctx->fail(LMM_E_UNSUPPORTED, "ARDTransform is supported for input dimension D <= 8");
+    for (int k = 0; k < D; ++k)
+      if (!(ard[k] > 0.0)) return ctx->fail(LMM_E_ARG, "ARD multipliers must be positive");
+  }
+  return LMM_OK;
+}
+
 int check_descs(lmm_ctx* ctx, const lmm_gp_desc* d, int m, int D) {
   for (int i = 0; i < m; ++i) {
-    if (d[i].kind < 0 || d[i].kind > LMM_KERNEL_RATIONAL_QUADRATIC)
-      return ctx->fail(LMM_E_UNSUPPORTED, "unsupported kernel kind (SE, Matern32, Matern52, Exponential, RationalQuadratic)");
-    if (d[i].kind == LMM_KERNEL_RATIONAL_QUADRATIC && !(d[i].param > 0.0)) return ctx->fail(LMM_E_ARG, "RationalQuadraticKernel needs α > 0 in `param`");
-    if (!(d[i].variance > 0.0) || !(d[i].inv_lengthscale > 0.0)) return ctx->fail(LMM_E_ARG, "kernel variance and inv_lengthscale must be positive");
-    if (d[i].ard) {
-      if (D > LMM_MAX_ARD) return ctx->fail(LMM_E_UNSUPPORTED, "ARDTransform is supported for input dimension D <= 8");
-      for (int k = 0; k < D; ++k)
-        if (!(d[i].ard[k] > 0.0)) return ctx->fail(LMM_E_ARG, "ARD multipliers must be positive");
+    int rc = check_term(ctx, d[i].kind, d[i].variance, d[i].inv_lengthscale, d[i].param, d[i].ard, D);
+    if (rc) return rc;
+    if (d[i].compose < LMM_COMPOSE_NONE || d[i].compose > LMM_COMPOSE_PRODUCT) return ctx->fail(LMM_E_ARG, "lmm_gp_desc.compose must be 0 (none), 1 (sum) or 2 (product)");
+    if (d[i].n_extra < 0 || d[i].n_extra > LMM_MAX_TERMS - 1) return ctx->fail(LMM_E_UNSUPPORTED, "a composite kernel has at most LMM_MAX_TERMS = 4 terms");
+    if (d[i].compose == LMM_COMPOSE_NONE && d[i].n_extra != 0) return ctx->fail(LMM_E_ARG, "n_extra must be 0 for a single kernel (compose = 0)");
+    if (d[i].n_extra > 0 && !d[i].extra) return ctx->fail(LMM_E_ARG, "n_extra > 0 with a null `extra` pointer");
+    for (int t = 0; t < d[i].n_extra; ++t) {
+      const lmm_kernel_term& q = d[i].extra[t];
+      if ((rc = check_term(ctx, q.kind, q.variance, q.inv_lengthscale, q.param, q.ard, D))) return rc;
     }
   }
   return LMM_OK;
 }
+
+// k(x, x) of a latent's whole kernel (κ(0) = 1 for every supported base kernel): Σ or Π of the term variances.
+double desc_kdiag(const lmm_gp_desc& d) {
+  double v = d.variance;
+  for (int t = 0; t < d.n_extra; ++t) v = (d.compose == LMM_COMPOSE_PRODUCT) ? v * d.extra[t].variance : v + d.extra[t].variance;
+  return v;
+}
+bool desc_is_composite(const lmm_gp_desc& d) { return d.n_extra > 0 || d.kind == LMM_KERNEL_PERIODIC; }
 
 size_t factor_bytes_per_latent(int nt) { return (sym_tiles(nt) + (size_t)nt) * TT * sizeof(double); }
 
@@ -82,7 +105,26 @@ void set_params(LatentParams& q, const lmm_gp_desc& d, double noise, double ls_s
   q.mean = d.mean_const;
   q.param = d.param;
   static_assert(MAX_ARD == LMM_MAX_ARD, "device and ABI limits must agree");
+  static_assert(MAX_TERMS == LMM_MAX_TERMS, "device and ABI limits must agree");
   for (int k = 0; k < MAX_ARD; ++k) q.ard[k] = (d.ard && k < D) ? d.ard[k] : 1.0;
+  q.nterms = 1 + d.n_extra;
+  q.compose = d.compose;
+  q.kdiag = desc_kdiag(d);
+  for (int t = 0; t < MAX_TERMS - 1; ++t) {
+    TermParams& e = q.extra[t];
+    if (t < d.n_extra) {
+      const lmm_kernel_term& src = d.extra[t];
+      e.kind = src.kind;
+      e.ard_dim = src.ard ? D : 0;
+      e.variance = src.variance;
+      e.inv_ls = src.inv_lengthscale * ls_scale;  // a lengthscale sweep stretches every term
+      e.param = src.param;
+      for (int k = 0; k < MAX_ARD; ++k) e.ard[k] = (src.ard && k < D) ? src.ard[k] : 1.0;
+    } else {
+      e.kind = 0; e.ard_dim = 0; e.variance = 0.0; e.inv_ls = 1.0; e.param = 1.0;
+      for (int k = 0; k < MAX_ARD; ++k) e.ard[k] = 1.0;
+    }
+  }
 }
 
 void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const double* noise, int lo, int hi, int D, double ls_scale) {

@@ -11,6 +11,7 @@ namespace lmm {
 
 __device__ __forceinline__ double kernel_pair(const LatentParams& lp, const double* __restrict__ xa, const double* __restrict__ xb,
                                               int D, int form, bool same_point) {
+  if (needs_raw_points(&lp)) return kernel_value_raw(&lp, xa, xb, D, form, same_point);  // composite / periodic latent
   if (same_point) return kappa_eval(lp.kind, lp.variance, 0.0, lp.param);
   double a[64], b[64];
   double sa = 0.0, sb = 0.0;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) ilmm_predict_kernel(TiledRect V, int Ns, 
       const double ha = H[(size_t)a * p + j];
       sm_ = fma(ha, params[a].mean + mlat[(size_t)a * Ns + n], sm_);
       for (int b = 0; b < m; ++b) {
-        const double c = ((a == b) ? (params[a].variance + 1e-18) : 0.0) - G[a * m + b];
+        const double c = ((a == b) ? (params[a].kdiag + 1e-18) : 0.0) - G[a * m + b];
         sv = fma(ha * H[(size_t)b * p + j], c, sv);
       }
     }

@@ -52,7 +52,17 @@ struct TiledRect {
 };
 
 // Per-latent kernel parameters on the device.
-constexpr int MAX_ARD = 8;  // == LMM_MAX_ARD of include/lmm.h
+constexpr int MAX_ARD = 8;    // == LMM_MAX_ARD of include/lmm.h
+constexpr int MAX_TERMS = 4;  // == LMM_MAX_TERMS
+// One further term of a composite (sum / product) kernel.
+struct TermParams {
+  int kind;
+  int ard_dim;
+  double variance;
+  double inv_ls;
+  double param;
+  double ard[MAX_ARD];
+};
 struct LatentParams {
   int kind;
   int ard_dim;  // 0: isotropic ScaleTransform only; D (<= MAX_ARD): inputs are also multiplied by ard[0..D) (ARDTransform)
@@ -60,8 +70,14 @@ struct LatentParams {
   double inv_ls;
   double noise;  // added on the diagonal (ΣT_i for OILMM, σ² for IndependentMOGP)
   double mean;
-  double param;  // α of the RationalQuadraticKernel
+  double param;  // α of the RationalQuadraticKernel, r of the PeriodicKernel
   double ard[MAX_ARD];
+  // composite kernels: nterms = 1 (plain kernel: everything above) .. MAX_TERMS; compose 1 = sum, 2 = product over term 0
+  // (the fields above) and extra[0 .. nterms-2]; kdiag = k(x, x) of the whole kernel (= variance for a plain kernel)
+  int nterms;
+  int compose;
+  double kdiag;
+  TermParams extra[MAX_TERMS - 1];
 };
 // Multiplier of input dimension k: KernelFunctions `k ∘ ScaleTransform(s)` / `k ∘ ARDTransform(v)` scale the inputs
 // BEFORE pairwise distances are taken.  p points at global memory (no dynamically indexed register copy).
@@ -135,6 +151,56 @@ __device__ __forceinline__ double sqdist(const double* a, const double* b, int D
   }
   return d2;
 }
+
+// One term of a kernel on RAW (unscaled) points a, b (D coordinates each): the term's own input scaling, its own pairwise
+// distance (Distances.jl form or direct differences; the PeriodicKernel's Sinus metric always works on differences), κ,
+// variance.  This is what KernelFunctions evaluates per component of a KernelSum / KernelProduct.
+__device__ __forceinline__ double term_value(int kind, int ard_dim, double variance, double inv_ls, double param, const double* ard,
+                                             const double* a, const double* b, int D, int form, bool same_point) {
+  if (same_point) return variance;  // d = 0 exactly on the diagonal (Distances.jl), κ(0) = 1 for every supported kernel
+  if (kind == 5) {  // PeriodicKernel(r): Sinus(r) metric = Σ (sinpi(a_k - b_k) / r)², κ = exp(-d/2)
+    double d = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double sc = ard_dim ? inv_ls * ard[k] : inv_ls;
+      const double sn = sinpi(sc * a[k] - sc * b[k]) / param;
+      d = fma(sn, sn, d);
+    }
+    return variance * exp_nonpos(-0.5 * d);
+  }
+  double d2;
+  if (form == 0) {
+    double sa = 0.0, sb = 0.0, dot = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double sc = ard_dim ? inv_ls * ard[k] : inv_ls;
+      const double ak = sc * a[k], bk = sc * b[k];
+      sa = fma(ak, ak, sa);
+      sb = fma(bk, bk, sb);
+      dot = (D == 1) ? ak * bk : fma(ak, bk, dot);  // D = 1: one rounded product, as the single-kernel fast path and a K = 1 GEMM do
+    }
+    d2 = fma(-2.0, dot, sa + sb);
+    d2 = d2 > 0.0 ? d2 : 0.0;
+  } else {
+    d2 = 0.0;
+    for (int k = 0; k < D; ++k) {
+      const double sc = ard_dim ? inv_ls * ard[k] : inv_ls;
+      const double df = sc * a[k] - sc * b[k];
+      d2 = fma(df, df, d2);
+    }
+  }
+  return kappa_eval(kind, variance, d2, param);
+}
+// Value of a (possibly composite) latent kernel on raw points; gp points at global memory.
+__device__ __forceinline__ double kernel_value_raw(const LatentParams* gp, const double* a, const double* b, int D, int form, bool same_point) {
+  double v = term_value(gp->kind, gp->ard_dim, gp->variance, gp->inv_ls, gp->param, gp->ard, a, b, D, form, same_point);
+  for (int t = 1; t < gp->nterms; ++t) {
+    const TermParams* q = &gp->extra[t - 1];
+    const double w = term_value(q->kind, q->ard_dim, q->variance, q->inv_ls, q->param, q->ard, a, b, D, form, same_point);
+    v = (gp->compose == 2) ? v * w : v + w;
+  }
+  return v;
+}
+// true if the latent needs the raw-point path (composite, or a kernel whose metric is not (Sq)Euclidean)
+__device__ __forceinline__ bool needs_raw_points(const LatentParams* gp) { return gp->nterms > 1 || gp->kind == 5; }
 
 // Programmatic dependent launch (the panel chain of a batch-1 factorisation is three dependent small kernels per tile
 // column): a kernel launched with launch_pdl() may be scheduled as soon as its predecessor in the stream executes

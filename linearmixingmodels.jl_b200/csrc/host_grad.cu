@@ -432,6 +432,9 @@ extern "C" int lmm_oilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, i
   std::lock_guard<std::mutex> lk(ctx->mu);
   int rc = check_common(ctx, latents, m, x, N, D, p, out_dim);
   if (rc) return rc;
+  for (int i = 0; i < m; ++i)
+    if (desc_is_composite(latents[i]))
+      return ctx->fail(LMM_E_UNSUPPORTED, "the logpdf gradient is built for single (Sq)Euclidean base kernels; composite / periodic latents: value only");
   if (!U || !S || !y) return ctx->fail(LMM_E_ARG, "null pointer");
   if (m > p) return ctx->fail(LMM_E_ARG, "more latents than outputs");
   Projection pr;
@@ -451,6 +454,9 @@ extern "C" int lmm_imogp_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* fs, int m,
   std::lock_guard<std::mutex> lk(ctx->mu);
   int rc = check_common(ctx, fs, m, x, N, D, m, out_dim);
   if (rc) return rc;
+  for (int i = 0; i < m; ++i)
+    if (desc_is_composite(fs[i]))
+      return ctx->fail(LMM_E_UNSUPPORTED, "the logpdf gradient is built for single (Sq)Euclidean base kernels; composite / periodic latents: value only");
   if (!y) return ctx->fail(LMM_E_ARG, "null pointer");
   if (!(sigma2 > 0.0)) return ctx->fail(LMM_E_ARG, "noise variance must be positive");
   Projection pr;
@@ -512,6 +518,9 @@ extern "C" int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, in
   std::lock_guard<std::mutex> lk(ctx->mu);
   int rc = check_common(ctx, latents, m, x, N, D, p, out_dim);
   if (rc) return rc;
+  for (int i = 0; i < m; ++i)
+    if (desc_is_composite(latents[i]))
+      return ctx->fail(LMM_E_UNSUPPORTED, "the logpdf gradient is built for single (Sq)Euclidean base kernels; composite / periodic latents: value only");
   if (!H || !y) return ctx->fail(LMM_E_ARG, "null pointer");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;

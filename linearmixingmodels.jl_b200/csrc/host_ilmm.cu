@@ -406,7 +406,7 @@ extern "C" int lmm_ilmm_prior_mean_and_var(lmm_ctx* ctx, const lmm_gp_desc* late
   for (int i = 0; i < m; ++i)
     for (int n = 0; n < Ns; ++n) {
       ML[(size_t)i * Ns + n] = latents[i].mean_const;
-      VL[(size_t)i * Ns + n] = latents[i].variance;
+      VL[(size_t)i * Ns + n] = desc_kdiag(latents[i]);
     }
   DevBuf b_H, b_ML, b_VL, b_out;
   CU(b_H.alloc(ctx, (size_t)p * m * sizeof(double)));
@@ -1025,7 +1025,7 @@ int masked_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double si
     for (int l = 0; l < m; ++l) {
       const double h = post->H[(size_t)l * p + j];
       pm += h * post->descs[l].mean_const;
-      pv += h * h * post->descs[l].variance;
+      pv += h * h * desc_kdiag(post->descs[l]);
     }
     for (int n = 0; n < Ns; ++n) {
       mean[(size_t)j * Ns + n] += pm;

@@ -199,15 +199,39 @@ struct lmm_post {
   size_t bytes = 0;
   int big_n = 0, big_nt = 0;  // ILMM joint dimension mN and its tile count
 
-  // deep copy of the latent descriptions (the caller's ARD arrays are only valid during its call)
+  std::vector<lmm_kernel_term> term_store;  // m x (LMM_MAX_TERMS-1) copies of the callers' extra terms (composite kernels)
+  std::vector<double> term_ard_store;       // m x (LMM_MAX_TERMS-1) x D copies of their ARD vectors
+  // deep copy of the latent descriptions (the caller's ARD / extra-term arrays are only valid during its call)
   void adopt_descs(const lmm_gp_desc* d, int m_, int D_) {
+    constexpr int XT = LMM_MAX_TERMS - 1;
     descs.assign(d, d + m_);
     ard_store.assign((size_t)m_ * D_, 0.0);
-    for (int i = 0; i < m_; ++i)
+    term_store.assign((size_t)m_ * XT, lmm_kernel_term{});
+    term_ard_store.assign((size_t)m_ * XT * D_, 0.0);
+    for (int i = 0; i < m_; ++i) {
       if (d[i].ard) {
         for (int k = 0; k < D_; ++k) ard_store[(size_t)i * D_ + k] = d[i].ard[k];
-        descs[i].ard = ard_store.data() + (size_t)i * D_;
       }
+      for (int t = 0; t < d[i].n_extra && t < XT; ++t) {
+        lmm_kernel_term q = d[i].extra[t];
+        if (q.ard)
+          for (int k = 0; k < D_; ++k) term_ard_store[((size_t)i * XT + t) * D_ + k] = q.ard[k];
+        term_store[(size_t)i * XT + t] = q;
+      }
+    }
+    repoint_descs(D_);
+  }
+  // make every pointer inside descs / term_store refer to this handle's own copies (after adopt_descs or a load)
+  void repoint_descs(int D_) {
+    constexpr int XT = LMM_MAX_TERMS - 1;
+    for (size_t i = 0; i < descs.size(); ++i) {
+      if (descs[i].ard) descs[i].ard = ard_store.data() + i * D_;
+      for (int t = 0; t < XT; ++t) {
+        lmm_kernel_term& q = term_store[i * XT + t];
+        if (q.ard) q.ard = term_ard_store.data() + (i * XT + t) * D_;
+      }
+      descs[i].extra = descs[i].n_extra > 0 ? term_store.data() + i * XT : nullptr;
+    }
   }
   int nloc() const { return hi - lo; }
   size_t npad() const { return (size_t)nt * TILE; }
@@ -266,6 +290,8 @@ cudaError_t copy_in(lmm_ctx* ctx, double* dst, const double* src, size_t n);
 cudaError_t copy_out(lmm_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 void shard_range(const lmm_ctx* ctx, int m, int& lo, int& hi);
 int check_descs(lmm_ctx* ctx, const lmm_gp_desc* d, int m, int D);
+double desc_kdiag(const lmm_gp_desc& d);         // k(x, x) of the whole (possibly composite) kernel
+bool desc_is_composite(const lmm_gp_desc& d);   // more than one term, or a non-(Sq)Euclidean metric (PeriodicKernel)
 void set_params(LatentParams& q, const lmm_gp_desc& d, double noise, double ls_scale, int D);
 size_t factor_bytes_per_latent(int nt);
 void fill_params(std::vector<LatentParams>& hp, const lmm_gp_desc* d, const double* noise, int lo, int hi, int D, double ls_scale = 1.0);

@@ -10,7 +10,7 @@
 // ------------------------------------------------------------------------------------------------
 namespace lmm_host {
 struct PostFileHeader {
-  char magic[8];  // "LMMPOST2"
+  char magic[8];  // "LMMPOST3"
   int32_t kind, m, p, N, D, nt, lo, hi, big_n, big_nt, has_U, has_noise_vec, has_Ept, reserved;
   double sigma2;
   uint64_t n_x, n_L, n_W, n_alpha, n_delta, n_params, n_H, n_noise_vec, n_Ept;  // element counts (doubles; params: structs)
@@ -68,7 +68,7 @@ extern "C" int lmm_post_save(lmm_post* post, const char* path) {
   FILE* f = fopen(path, "wb");
   if (!f) return ctx->fail(LMM_E_ARG, std::string("cannot open ") + path + " for writing");
   PostFileHeader h{};
-  memcpy(h.magic, "LMMPOST2", 8);
+  memcpy(h.magic, "LMMPOST3", 8);
   h.kind = post->kind; h.m = post->m; h.p = post->p; h.N = post->N; h.D = post->D; h.nt = post->nt; h.lo = post->lo; h.hi = post->hi;
   h.big_n = post->big_n; h.big_nt = post->big_nt; h.has_U = post->U.empty() ? 0 : 1;
   h.has_noise_vec = post->d_noise_vec ? 1 : 0; h.has_Ept = post->d_Ept ? 1 : 0;
@@ -81,6 +81,9 @@ extern "C" int lmm_post_save(lmm_post* post, const char* path) {
   // the descriptions hold host pointers (ARD vectors): the file carries the vectors and re-points on load (a non-null
   // pointer in the raw desc only marks "this latent has one")
   if (ok) ok = fwrite(post->ard_store.data(), sizeof(double), post->ard_store.size(), f) == post->ard_store.size();
+  // composite kernels: the extra terms and their ARD vectors, fixed-size blocks (m x 3 terms, m x 3 x D multipliers)
+  if (ok) ok = fwrite(post->term_store.data(), sizeof(lmm_kernel_term), post->term_store.size(), f) == post->term_store.size() &&
+               fwrite(post->term_ard_store.data(), sizeof(double), post->term_ard_store.size(), f) == post->term_ard_store.size();
   if (ok && h.has_U)
     ok = fwrite(post->U.data(), sizeof(double), post->U.size(), f) == post->U.size() &&
          fwrite(post->S.data(), sizeof(double), post->S.size(), f) == post->S.size();
@@ -107,7 +110,7 @@ extern "C" int lmm_post_load(lmm_ctx* ctx, const char* path, lmm_post** out_post
     fclose(f);
     return ctx->fail(LMM_E_ARG, msg);
   };
-  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "LMMPOST2", 8) != 0) return bail("not a liblmm posterior file");
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "LMMPOST3", 8) != 0) return bail("not a liblmm posterior file");
   if (h.kind < POST_OILMM || h.kind > POST_JOINT /* POST_MASKED is never written */ || h.m <= 0 || h.p <= 0 || h.N <= 0 || h.D <= 0 || h.lo < 0 || h.hi < h.lo || h.hi > h.m)
     return bail("corrupt posterior header");
   lmm_post* P = new lmm_post();
@@ -119,8 +122,16 @@ extern "C" int lmm_post_load(lmm_ctx* ctx, const char* path, lmm_post** out_post
   if (ok) {
     P->ard_store.resize((size_t)h.m * h.D);
     ok = fread(P->ard_store.data(), sizeof(double), P->ard_store.size(), f) == P->ard_store.size();
-    for (int i = 0; ok && i < h.m; ++i)
-      if (P->descs[i].ard) P->descs[i].ard = P->ard_store.data() + (size_t)i * h.D;
+    if (ok) {
+      constexpr int XT = LMM_MAX_TERMS - 1;
+      P->term_store.resize((size_t)h.m * XT);
+      P->term_ard_store.resize((size_t)h.m * XT * h.D);
+      ok = fread(P->term_store.data(), sizeof(lmm_kernel_term), P->term_store.size(), f) == P->term_store.size() &&
+           fread(P->term_ard_store.data(), sizeof(double), P->term_ard_store.size(), f) == P->term_ard_store.size();
+      for (int i = 0; ok && i < h.m; ++i)
+        if (P->descs[i].n_extra < 0 || P->descs[i].n_extra > XT) ok = false;
+    }
+    if (ok) P->repoint_descs(h.D);
   }
   if (ok && h.has_U) {
     P->U.resize((size_t)h.p * h.m); P->S.resize(h.m);

@@ -507,7 +507,7 @@ extern "C" int lmm_oilmm_prior_mean_and_var(lmm_ctx* ctx, const lmm_gp_desc* lat
   for (int i = 0; i < m; ++i)
     for (int n = 0; n < Ns; ++n) {
       ML[(size_t)i * Ns + n] = latents[i].mean_const;
-      VL[(size_t)i * Ns + n] = latents[i].variance;
+      VL[(size_t)i * Ns + n] = desc_kdiag(latents[i]);
     }
   DevBuf b_H, b_ML, b_VL, b_out;
   CU(b_H.alloc(ctx, H.size() * sizeof(double)));

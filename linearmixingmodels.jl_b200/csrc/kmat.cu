@@ -50,6 +50,7 @@ __device__ __forceinline__ void stage_points(double* xa, double* xb, double* sa,
     bulk_g2s(xb, gb, bytes, bar);
   }
   mbar_wait(bar, 0);
+  if (needs_raw_points(gp)) return;  // composite / periodic latent: every term scales the raw points itself (kernel_value_raw)
   for (int i = threadIdx.x; i < TILE * D; i += blockDim.x) {
     const double s = input_scale(gp, i % D);
     xa[i] *= s;
@@ -65,6 +66,37 @@ __device__ __forceinline__ void stage_points(double* xa, double* xb, double* sa,
   __syncthreads();
 }
 
+// Composite (KernelSum / KernelProduct) or periodic latent: xa / xb hold RAW points; each term applies its own input scaling,
+// distance and κ (KernelFunctions evaluates the components separately and adds / multiplies the matrices).  Kept out of line
+// so that the single-kernel tile body keeps its register allocation (it runs at 90 % of the HBM write bandwidth).
+template <bool SYM>
+__device__ __noinline__ void kmat_tile_composite(double* __restrict__ tile, const double* xa, const double* xb, int dd, int r0, int c0, int Na,
+                                                 int Nb, double noise, int form, const double* __restrict__ noise_vec, const LatentParams* gp) {
+  const int t = threadIdx.x;
+  const int r = (((2 * t) >> 5) & 15) * 8 + (((2 * t) >> 2) & 7);
+  const int gr = r0 + r;
+  __syncthreads();  // stage_points returned right after the bulk copies landed
+  for (int it = 0; it < 32; ++it) {
+    const int c = 4 * it + ((2 * t) & 3);
+    double2 v;
+    double* vv = reinterpret_cast<double*>(&v);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int gc = c0 + c + q;
+      double val;
+      if (gr >= Na || gc >= Nb) {
+        val = (SYM && gr == gc) ? 1.0 : 0.0;
+      } else {
+        const bool same = SYM && gr == gc;
+        val = kernel_value_raw(gp, xa + (size_t)r * dd, xb + (size_t)(c + q) * dd, dd, form, same);
+        if (same) val += noise_vec ? noise_vec[gr] : noise;
+      }
+      vv[q] = val;
+    }
+    *reinterpret_cast<double2*>(tile + it * 512 + 2 * t) = v;
+  }
+}
+
 // One 128x128 tile of kernel values.  Thread t owns the fixed tile row r(t) and walks the columns
 // c = 4*it + 2*(t&1) + {0,1}: its own scaled point / squared norm are hoisted into registers, the
 // column points are shared-memory broadcasts, and each iteration ends in one coalesced 16-byte
@@ -73,11 +105,15 @@ __device__ __forceinline__ void stage_points(double* xa, double* xb, double* sa,
 template <bool SYM, int DS>
 __device__ __forceinline__ void kmat_tile_body(double* __restrict__ tile, const double* xa, const double* xb, const double* sa,
                                                const double* sb, int D, int r0, int c0, int Na, int Nb, const LatentParams& lp, int form,
-                                               const double* __restrict__ noise_vec = nullptr) {
+                                               const double* __restrict__ noise_vec = nullptr, const LatentParams* gp = nullptr) {
   const int t = threadIdx.x;
   const int r = (((2 * t) >> 5) & 15) * 8 + (((2 * t) >> 2) & 7);
   const int gr = r0 + r;
   const int dd = DS > 0 ? DS : D;
+  if (gp != nullptr && needs_raw_points(gp)) {  // composite (KernelSum / KernelProduct) or periodic latent: out-of-line slow path
+    kmat_tile_composite<SYM>(tile, xa, xb, dd, r0, c0, Na, Nb, lp.noise, form, noise_vec, gp);
+    return;
+  }
   const double* ar = xa + (size_t)r * dd;
   const double sar = sa[r];
   const double a0 = ar[0];
@@ -154,7 +190,7 @@ __global__ void __launch_bounds__(256) kmat_sym_kernel(TiledSym out, const doubl
 
   stage_points(xa, xb, sa, sb, xpad + (size_t)I * TILE * D, xpad + (size_t)J * TILE * D, D, params + b, &bar);
   kmat_tile_body<true, DS>(out.tile(b, I, J), xa, xb, sa, sb, D, I * TILE, J * TILE, N, N, lp, form,
-                           noise_vec ? noise_vec + (size_t)b * noise_stride : nullptr);
+                           noise_vec ? noise_vec + (size_t)b * noise_stride : nullptr, params + b);
 }
 
 // grid: (ntr*ntc, batch).  Rows = points of xa_pad (e.g. x*), cols = points of xb_pad (train x).
@@ -174,7 +210,7 @@ __global__ void __launch_bounds__(256) kmat_cross_kernel(TiledRect out, const do
   const int R = blockIdx.x / out.ntc, J = blockIdx.x % out.ntc;
   const LatentParams lp = params[b];
   stage_points(xa, xb, sa, sb, xa_pad + (size_t)R * TILE * D, xb_pad + (size_t)J * TILE * D, D, params + b, &bar);
-  kmat_tile_body<false, DS>(out.tile(b, R, J), xa, xb, sa, sb, D, R * TILE, J * TILE, Na, Nb, lp, form);
+  kmat_tile_body<false, DS>(out.tile(b, R, J), xa, xb, sa, sb, D, R * TILE, J * TILE, Na, Nb, lp, form, nullptr, params + b);
 }
 
 static size_t kmat_smem(int D) { return (size_t)(2 * TILE * D + 2 * TILE) * sizeof(double); }

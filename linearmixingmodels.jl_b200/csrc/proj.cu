@@ -151,30 +151,98 @@ struct ProjArgs {
   int psplit;  // CTAs per column block along the p rows of the residual (grid.y)
 };
 
-// One warp: C[8 x 8*NCB] (+)= A[8 x K] * Bs[K x 8*NCB] for row block `rb` of A (column-major, leading dimension lda,
-// `rows` valid rows starting at global row a_row0) and the column blocks cb0 .. cb0+NCB-1 of the shared operand Bs
-// ([K4][LD], K4 = K rounded up to 4, rows beyond K are zero).  mma.m8n8k4: lane = (r, k) holds A[r][k] with r = lane/4,
-// k = lane%4; B[k][n] with k = lane%4, n = lane/4; C[r][2*(lane%4) + {0,1}].  The next k-step's A fragment is fetched
-// (through L1) while the current one feeds the tensor pipe.
+// One warp: C[8 x 8*NCB] += A[8 x k-range] * Bs[k-range x 8*NCB] for row block `rb` of A (column-major, leading dimension
+// lda, `rows` valid rows starting at global row a_row0) and the column blocks cb0 .. cb0+NCB-1 of the shared operand Bs
+// ([K4][LD], K4 = K rounded up to 4, rows beyond K are zero), over the k4-steps [ks0, ks1).  mma.m8n8k4: lane = (r, k)
+// holds A[r][k] with r = lane/4, k = lane%4; B[k][n] with k = lane%4, n = lane/4; C[r][2*(lane%4) + {0,1}].  The A
+// fragments of the next FOUR k-steps are in flight (through L1 / L2) while the current four feed the tensor pipe: with a
+// one-step prefetch every k-step paid an L2 round trip at the notebook shape (p = 600: 150 dependent steps).
 template <int NCB>
 __device__ __forceinline__ void warp_gemm(const double* __restrict__ A, int lda, int a_row0, int rows, int rb, const double* Bs, int LD,
-                                          int K, int cb0, double (&acc)[NCB][2]) {
+                                          int K, int cb0, int ks0, int ks1, double (&acc)[NCB][2]) {
   const int lane = threadIdx.x & 31, r = lane >> 2, k = lane & 3;
   const int row = rb * 8 + r;
   const bool rok = row < rows;
   const double* ap = A + (size_t)(a_row0 + row);
   const double* bp = Bs + (size_t)k * LD + cb0 * 8 + r;
-  const int ksteps = (K + 3) >> 2;
-  double a = (rok && k < K) ? __ldg(ap + (size_t)k * lda) : 0.0;
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const int kn = (ks + 1) * 4 + k;
-    const double an = (rok && kn < K) ? __ldg(ap + (size_t)kn * lda) : 0.0;
-    const double* b = bp + (size_t)ks * 4 * LD;
+  auto lda_at = [&](int ks) -> double {
+    const int kk = ks * 4 + k;
+    return (rok && ks < ks1 && kk < K) ? __ldg(ap + (size_t)kk * lda) : 0.0;
+  };
+  double a[4], an[4];
 #pragma unroll
-    for (int c = 0; c < NCB; ++c) dmma884q(acc[c][0], acc[c][1], a, b[c * 8]);
-    a = an;
+  for (int u = 0; u < 4; ++u) a[u] = lda_at(ks0 + u);
+  for (int ks = ks0; ks < ks1; ks += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) an[u] = lda_at(ks + 4 + u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (ks + u < ks1) {  // warp-uniform
+        const double* b = bp + (size_t)(ks + u) * 4 * LD;
+#pragma unroll
+        for (int c = 0; c < NCB; ++c) dmma884q(acc[c][0], acc[c][1], a[u], b[c * 8]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = an[u];
   }
 }
+
+// All 8 warps: the row blocks [rb_lo, rb_hi) x NCG column groups of C = A * Bs, `epi(rb, cb0, acc)` called by the warp
+// that holds the finished accumulators.  With fewer than 8 (row block, column group) tasks the K range is split over the
+// idle warps (2, 4 or 8 slices of at least 8 k4-steps each) and the partial accumulators are summed through `scratch`
+// (8 x NCB x 32 x 2 doubles) in a fixed order -- the notebook shape has m = 20 (3 row blocks) against K = p = 600.
+template <int NCB, int NCG, class Epi>
+__device__ __forceinline__ void gemm_rows(const double* __restrict__ A, int lda, int a_row0, int rows, int rb_lo, int rb_hi,
+                                          const double* Bs, int LD, int K, double* scratch, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntask = (rb_hi - rb_lo) * NCG;
+  const int ksteps = (K + 3) >> 2;
+  int KS = 1;
+  while (KS * 2 * ntask <= 8 && KS * 2 * 8 <= ksteps) KS *= 2;
+  if (KS == 1) {
+    for (int task = warp; task < ntask; task += 8) {
+      const int rb = rb_lo + task / NCG, cb0 = (task % NCG) * NCB;
+      double acc[NCB][2];
+#pragma unroll
+      for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+      warp_gemm<NCB>(A, lda, a_row0, rows, rb, Bs, LD, K, cb0, 0, ksteps, acc);
+      epi(rb, cb0, acc);
+    }
+    return;
+  }
+  const int task = warp / KS, ks = warp % KS;  // ntask * KS <= 8: at most one task per warp
+  const bool active = task < ntask;
+  const int rb = rb_lo + task / NCG, cb0 = (task % NCG) * NCB;
+  double acc[NCB][2];
+#pragma unroll
+  for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+  if (active) {
+    const int k0 = (int)((long long)ksteps * ks / KS), k1 = (int)((long long)ksteps * (ks + 1) / KS);
+    warp_gemm<NCB>(A, lda, a_row0, rows, rb, Bs, LD, K, cb0, k0, k1, acc);
+    if (ks > 0) {
+#pragma unroll
+      for (int c = 0; c < NCB; ++c) {
+        scratch[((size_t)(warp * NCB + c) * 32 + lane) * 2] = acc[c][0];
+        scratch[((size_t)(warp * NCB + c) * 32 + lane) * 2 + 1] = acc[c][1];
+      }
+    }
+  }
+  __syncthreads();
+  if (active && ks == 0) {
+    for (int s2 = 1; s2 < KS; ++s2) {
+#pragma unroll
+      for (int c = 0; c < NCB; ++c) {
+        acc[c][0] += scratch[((size_t)((warp + s2) * NCB + c) * 32 + lane) * 2];
+        acc[c][1] += scratch[((size_t)((warp + s2) * NCB + c) * 32 + lane) * 2 + 1];
+      }
+    }
+    epi(rb, cb0, acc);
+  }
+  __syncthreads();  // scratch may be reused by the next product
+}
+
+constexpr int PROJ_SCRATCH = 8 * 4 * 32 * 2;  // doubles (16 KB)
 
 // grid (ceil(N / NB), psplit), 256 threads.  NB columns of Y per CTA; LD = NB + 8 for NB >= 16 (row stride = 8 mod 16
 // doubles: the 4 x 8 B-fragment of a warp falls into two conflict-free 128-byte wavefronts), 8 for NB = 8.
@@ -187,8 +255,9 @@ __global__ void __launch_bounds__(256) project_dmma_kernel(ProjArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int p = a.p, m = a.m, N = a.N;
   const int p4 = (p + 3) & ~3, m4 = (m + 3) & ~3;
-  double* Ys = sm;                    // [p4][LD]
-  double* Zs = sm + (size_t)p4 * LD;  // [m4][LD]
+  double* Ys = sm;                            // [p4][LD]
+  double* Zs = sm + (size_t)p4 * LD;          // [m4][LD]
+  double* scratch = Zs + (size_t)m4 * LD;     // [PROJ_SCRATCH]
   __shared__ double red[8];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, r = lane >> 2, q = lane & 3;
   const int nb0 = blockIdx.x * NB;
@@ -208,13 +277,7 @@ __global__ void __launch_bounds__(256) project_dmma_kernel(ProjArgs a) {
   const bool same_tp = a.P != nullptr && a.P == a.T && a.lat0 == 0 && a.mloc == m;  // general ILMM: Z = T Y is the projection itself
   // ---- Ty = T[lat0 : lat0 + mloc, :] Y - mean     (slice 0 only)
   if (blockIdx.y == 0 && !same_tp) {
-    const int nrb = (a.mloc + 7) >> 3;
-    for (int task = warp; task < nrb * NCG; task += 8) {
-      const int rb = task / NCG, cb0 = (task % NCG) * NCB;
-      double acc[NCB][2];
-#pragma unroll
-      for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
-      warp_gemm<NCB>(a.T, m, a.lat0, a.mloc, rb, Ys, LD, p, cb0, acc);
+    gemm_rows<NCB, NCG>(a.T, m, a.lat0, a.mloc, 0, (a.mloc + 7) >> 3, Ys, LD, p, scratch, [&](int rb, int cb0, double (&acc)[NCB][2]) {
       const int row = rb * 8 + r;
       if (row < a.mloc) {
         const double mu = a.means[row];
@@ -226,53 +289,40 @@ __global__ void __launch_bounds__(256) project_dmma_kernel(ProjArgs a) {
           if (col + 1 < N) o[1] = acc[c][1] - mu;
         }
       }
-    }
+    });
   }
   if (a.P == nullptr) return;
   // ---- Z = P Y  (m x NB) into shared memory (every slice needs it)
-  {
-    const int nrb = (m + 7) >> 3;
-    for (int task = warp; task < nrb * NCG; task += 8) {
-      const int rb = task / NCG, cb0 = (task % NCG) * NCB;
-      double acc[NCB][2];
+  gemm_rows<NCB, NCG>(a.P, m, 0, m, 0, (m + 7) >> 3, Ys, LD, p, scratch, [&](int rb, int cb0, double (&acc)[NCB][2]) {
+    const int row = rb * 8 + r;
+    if (row < m) {
+      const double mu = same_tp ? a.means[row] : 0.0;
 #pragma unroll
-      for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
-      warp_gemm<NCB>(a.P, m, 0, m, rb, Ys, LD, p, cb0, acc);
-      const int row = rb * 8 + r;
-      if (row < m) {
-        const double mu = same_tp ? a.means[row] : 0.0;
-#pragma unroll
-        for (int c = 0; c < NCB; ++c) {
-          const int lc = (cb0 + c) * 8 + 2 * q, col = nb0 + lc;
-          Zs[(size_t)row * LD + lc] = acc[c][0];
-          Zs[(size_t)row * LD + lc + 1] = acc[c][1];
-          if (blockIdx.y == 0) {
-            if (a.z_out) {
-              if (col < N) a.z_out[(size_t)row * N + col] = acc[c][0];
-              if (col + 1 < N) a.z_out[(size_t)row * N + col + 1] = acc[c][1];
-            }
-            if (same_tp) {
-              double* o = a.ty + (size_t)row * a.ty_stride + col;
-              if (col < N) o[0] = acc[c][0] - mu;
-              if (col + 1 < N) o[1] = acc[c][1] - mu;
-            }
+      for (int c = 0; c < NCB; ++c) {
+        const int lc = (cb0 + c) * 8 + 2 * q, col = nb0 + lc;
+        Zs[(size_t)row * LD + lc] = acc[c][0];
+        Zs[(size_t)row * LD + lc + 1] = acc[c][1];
+        if (blockIdx.y == 0) {
+          if (a.z_out) {
+            if (col < N) a.z_out[(size_t)row * N + col] = acc[c][0];
+            if (col + 1 < N) a.z_out[(size_t)row * N + col + 1] = acc[c][1];
+          }
+          if (same_tp) {
+            double* o = a.ty + (size_t)row * a.ty_stride + col;
+            if (col < N) o[0] = acc[c][0] - mu;
+            if (col + 1 < N) o[1] = acc[c][1] - mu;
           }
         }
       }
     }
-  }
+  });
   __syncthreads();
   // ---- R = Y - Q Z over this slice's rows of p; summed squares in a fixed order
   double ss = 0.0;
   {
     const int nrb = (p + 7) >> 3;
     const int rb_lo = (int)((long long)nrb * blockIdx.y / a.psplit), rb_hi = (int)((long long)nrb * (blockIdx.y + 1) / a.psplit);
-    for (int task = warp; task < (rb_hi - rb_lo) * NCG; task += 8) {
-      const int rb = rb_lo + task / NCG, cb0 = (task % NCG) * NCB;
-      double acc[NCB][2];
-#pragma unroll
-      for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
-      warp_gemm<NCB>(a.Q, p, 0, p, rb, Zs, LD, m, cb0, acc);
+    gemm_rows<NCB, NCG>(a.Q, p, 0, p, rb_lo, rb_hi, Zs, LD, m, scratch, [&](int rb, int cb0, double (&acc)[NCB][2]) {
       const int row = rb * 8 + r;
       if (row < p) {
 #pragma unroll
@@ -288,7 +338,7 @@ __global__ void __launch_bounds__(256) project_dmma_kernel(ProjArgs a) {
           }
         }
       }
-    }
+    });
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -343,7 +393,7 @@ cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const
     // the widest column block that fits in shared memory and still gives every SM a CTA; else the narrowest that fits
     int nb = 0;
     for (int c : {64, 32, 16, 8}) {
-      const size_t sm_c = (size_t)(p4 + m4) * (c >= 16 ? c + 8 : c) * sizeof(double);
+      const size_t sm_c = ((size_t)(p4 + m4) * (c >= 16 ? c + 8 : c) + PROJ_SCRATCH) * sizeof(double);
       if (sm_c > 200 * 1024) continue;
       nb = c;
       if ((N + c - 1) / c >= num_sms) break;
@@ -359,7 +409,7 @@ cudaError_t launch_project(cudaStream_t st, const double* y, int N, int p, const
         if (s >= 1) a.psplit = s;
       }
       if (nblocks_out) *nblocks_out = nblocks * a.psplit;
-      const size_t smem = (size_t)(p4 + m4) * (nb >= 16 ? nb + 8 : nb) * sizeof(double);
+      const size_t smem = ((size_t)(p4 + m4) * (nb >= 16 ? nb + 8 : nb) + PROJ_SCRATCH) * sizeof(double);
       switch (nb) {
         case 64: return launch_project_dmma_nb<64>(st, a, nblocks, smem);
         case 32: return launch_project_dmma_nb<32>(st, a, nblocks, smem);

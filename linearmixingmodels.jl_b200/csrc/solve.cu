@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256) rect_rowsumsq_kernel(TiledRect A, double*
   }
   tile_gemv_n_finish(a0, a1, ys);
   __syncthreads();
-  if (t < TILE) y[(size_t)b * y_stride + R * TILE + t] = params[b].variance - ys[t];
+  if (t < TILE) y[(size_t)b * y_stride + R * TILE + t] = params[b].kdiag - ys[t];
 }
 cudaError_t launch_rect_rowsumsq(cudaStream_t st, TiledRect A, double* y, size_t y_stride, const LatentParams* params, int batch) {
   dim3 grid((unsigned)A.ntr, (unsigned)batch);

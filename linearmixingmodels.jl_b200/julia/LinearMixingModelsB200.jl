@@ -15,14 +15,26 @@ using LinearMixingModels: ILMM, OILMM, Orthogonal, IndependentMOGP, unpack, nois
 
 const liblmm = get(ENV, "LIBLMM", joinpath(@__DIR__, "..", "liblmm.so"))
 
-struct GpDesc            # lmm_gp_desc
+struct KernelTerm        # lmm_kernel_term: one further term of a KernelSum / KernelProduct
     kind::Int32
     reserved::Int32
     variance::Float64
     inv_lengthscale::Float64
+    param::Float64
+    ard::Ptr{Float64}
+end
+
+struct GpDesc            # lmm_gp_desc
+    kind::Int32
+    compose::Int32       # 0 single kernel, 1 KernelSum, 2 KernelProduct over this term and `extra`
+    variance::Float64
+    inv_lengthscale::Float64
     mean_const::Float64
     ard::Ptr{Float64}    # ARDTransform multipliers (D values, kept alive by the caller with GC.@preserve) or C_NULL
-    param::Float64       # α of RationalQuadraticKernel
+    param::Float64       # α of RationalQuadraticKernel, r of PeriodicKernel
+    n_extra::Int32
+    reserved2::Int32
+    extra::Ptr{KernelTerm}
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
@@ -53,37 +65,66 @@ kind(::Matern32Kernel) = Int32(1)
 kind(::Matern52Kernel) = Int32(2)
 kind(::ExponentialKernel) = Int32(3)          # == Matern12Kernel
 kind(::RationalQuadraticKernel) = Int32(4)    # α travels in GpDesc.param
+kind(::PeriodicKernel) = Int32(5)             # r travels in GpDesc.param (one r for all dimensions)
 shape(k) = 1.0
 shape(k::RationalQuadraticKernel) = Float64(only(k.α))   # KernelFunctions default α = 2
-# describe(k) -> (kind, variance, inv_lengthscale, shape parameter, ARD multipliers or nothing)
-describe(k::KernelFunctions.SimpleKernel) = (kind(k), 1.0, 1.0, shape(k), nothing)
-describe(k::ScaledKernel) = (d = describe(k.kernel); (d[1], d[2] * only(k.σ²), d[3], d[4], d[5]))
-function describe(k::TransformedKernel{<:Kernel,<:ScaleTransform})
-    d = describe(k.kernel)
-    return (d[1], d[2], d[3] * only(k.transform.s), d[4], d[5])
+function shape(k::PeriodicKernel)
+    all(==(first(k.r)), k.r) || throw(ArgumentError("PeriodicKernel with per-dimension r is not supported by liblmm"))
+    return Float64(first(k.r))
 end
-# `k ∘ ARDTransform(v)`: inputs are multiplied by v per dimension before distances are taken -> GpDesc.ard
+# One scaled, stretched base kernel: (kind, variance, inv_lengthscale, shape parameter, ARD multipliers or nothing)
+const Term = Tuple{Int32,Float64,Float64,Float64,Union{Nothing,Vector{Float64}}}
+# describe(k) -> (op, terms): op 0 single kernel, 1 KernelSum, 2 KernelProduct (flat, at most 4 terms)
+describe(k::KernelFunctions.SimpleKernel) = (Int32(0), Term[(kind(k), 1.0, 1.0, shape(k), nothing)])
+function describe(k::ScaledKernel)
+    op, ts = describe(k.kernel)
+    c = Float64(only(k.σ²))
+    if op == 1                       # c (k1 + k2) = c k1 + c k2
+        return op, Term[(t[1], t[2] * c, t[3], t[4], t[5]) for t in ts]
+    end
+    t = ts[1]                        # single kernel or product: the factor goes to the first term
+    return op, Term[(t[1], t[2] * c, t[3], t[4], t[5]); ts[2:end]]
+end
+function describe(k::TransformedKernel{<:Kernel,<:ScaleTransform})
+    op, ts = describe(k.kernel)      # the transformed inputs feed every term of a composite
+    s = Float64(only(k.transform.s))
+    return op, Term[(t[1], t[2], t[3] * s, t[4], t[5]) for t in ts]
+end
+# `k ∘ ARDTransform(v)`: inputs are multiplied by v per dimension before distances are taken -> the terms' ard vectors
 function describe(k::TransformedKernel{<:Kernel,<:ARDTransform})
-    d = describe(k.kernel)
+    op, ts = describe(k.kernel)
     v = Vector{Float64}(k.transform.v)
     length(v) <= 8 || throw(ArgumentError("ARDTransform with more than 8 dimensions is not supported by liblmm"))
-    return (d[1], d[2], d[3], d[4], d[5] === nothing ? v : d[5] .* v)
+    return op, Term[(t[1], t[2], t[3], t[4], t[5] === nothing ? copy(v) : t[5] .* v) for t in ts]
 end
+function combine(op::Int32, parts)
+    ts = Term[]
+    for q in parts
+        o, t = describe(q)
+        (o == 0 || o == op) || throw(ArgumentError("liblmm supports flat sums or flat products of base kernels"))
+        append!(ts, t)
+    end
+    length(ts) <= 4 || throw(ArgumentError("a composite kernel has at most 4 terms"))
+    return (length(ts) > 1 ? op : Int32(0)), ts
+end
+describe(k::KernelSum) = combine(Int32(1), k.kernels)          # `k1 + k2`
+describe(k::KernelProduct) = combine(Int32(2), k.kernels)      # `k1 * k2`
 describe(k) = throw(ArgumentError("kernel $(typeof(k)) is not supported by liblmm (no CPU fallback)"))
 meanconst(::AbstractGPs.ZeroMean) = 0.0
 meanconst(m::AbstractGPs.ConstMean) = Float64(m.c)
 # The C descriptors of a vector of latents plus the objects that must stay rooted while the library reads them (the ARD
-# vectors GpDesc.ard points into): every ccall that takes `descs` runs under `GC.@preserve keep`.
+# vectors GpDesc.ard / KernelTerm.ard point into, the KernelTerm arrays GpDesc.extra points into): every ccall that takes
+# `descs` runs under `GC.@preserve keep`.
 function gpdescs(fs::AbstractVector)
-    keep = Vector{Vector{Float64}}()
+    keep = Any[]
+    ardptr(a) = a === nothing ? Ptr{Float64}(C_NULL) : (push!(keep, a); pointer(a))
     descs = map(fs) do f
-        k, v, s, a, ard = describe(f.kernel)
-        p = C_NULL
-        if ard !== nothing
-            push!(keep, ard)
-            p = pointer(ard)
-        end
-        GpDesc(k, 0, v, s, meanconst(f.mean), p, a)
+        op, ts = describe(f.kernel)
+        t0 = ts[1]
+        extra = KernelTerm[KernelTerm(t[1], 0, t[2], t[3], t[4], ardptr(t[5])) for t in ts[2:end]]
+        px = isempty(extra) ? Ptr{KernelTerm}(C_NULL) : (push!(keep, extra); pointer(extra))
+        p = ardptr(t0[5])
+        GpDesc(t0[1], op, t0[2], t0[3], meanconst(f.mean), p, t0[4], length(extra), 0, px)
     end
     return Vector{GpDesc}(descs), keep
 end

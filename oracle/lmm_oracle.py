@@ -36,9 +36,10 @@ import scipy.linalg as sla
 
 LOG2PI = math.log(2.0 * math.pi)
 
-SE, MATERN32, MATERN52, EXPONENTIAL, RATQUAD = 0, 1, 2, 3, 4
+SE, MATERN32, MATERN52, EXPONENTIAL, RATQUAD, PERIODIC = 0, 1, 2, 3, 4, 5
+COMPOSE_NONE, COMPOSE_SUM, COMPOSE_PRODUCT = 0, 1, 2
 KERNEL_NAMES = {SE: "SEKernel", MATERN32: "Matern32Kernel", MATERN52: "Matern52Kernel", EXPONENTIAL: "ExponentialKernel",
-                RATQUAD: "RationalQuadraticKernel"}
+                RATQUAD: "RationalQuadraticKernel", PERIODIC: "PeriodicKernel"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -57,7 +58,12 @@ class Kernel:
     variance: float = 1.0
     inv_lengthscale: float = 1.0
     ard: Optional[tuple] = None  # KernelFunctions ``ARDTransform(v)``: x -> v .* x, composed with the ScaleTransform
-    param: float = 1.0  # α of RationalQuadraticKernel
+    param: float = 1.0  # α of RationalQuadraticKernel, r of PeriodicKernel
+    # KernelFunctions ``k1 + k2`` (KernelSum) / ``k1 * k2`` (KernelProduct): this kernel is term 0, ``terms`` the further
+    # single kernels; kernelmatrix(::KernelSum) = sum of the components' kernel matrices, (::KernelProduct) their
+    # elementwise product -- each component with its own transformed inputs and pairwise distances.
+    op: int = COMPOSE_NONE
+    terms: tuple = ()
 
 
 @dataclass(frozen=True)
@@ -125,17 +131,47 @@ def kappa(kind: int, d2: np.ndarray, param: float = 1.0) -> np.ndarray:
     raise ValueError(f"unsupported kernel kind {kind}")
 
 
-def kernelmatrix(k: Kernel, x: np.ndarray, x2: Optional[np.ndarray] = None, *, form: str = "gemm") -> np.ndarray:
-    """``kernelmatrix(k, x[, x2])`` = ``variance * map(κ, pairwise(metric, s*x, s*x2))``."""
+def _sinpi(d: np.ndarray) -> np.ndarray:
+    """sin(pi d) with the argument reduced first (Julia ``sinpi``): exact zeros at integers, no loss for large |d|."""
+    r = d - 2.0 * np.round(d / 2.0)  # in [-1, 1]
+    return np.sin(np.pi * r)
+
+
+def _kernelmatrix_single(k: Kernel, x: np.ndarray, x2: Optional[np.ndarray], form: str) -> np.ndarray:
     sc = k.inv_lengthscale if k.ard is None else k.inv_lengthscale * np.asarray(k.ard, dtype=np.float64)[None, :]
     xs = _as2d(x) * sc
     x2s = None if x2 is None else _as2d(x2) * sc
+    if k.kind == PERIODIC:
+        # KernelFunctions PeriodicKernel(r): metric Distances.Sinus(r) = sum(abs2(sinpi(a_k - b_k) / r_k)), kappa(d) = exp(-d/2)
+        bb = xs if x2s is None else x2s
+        d = np.zeros((xs.shape[0], bb.shape[0]))
+        for c in range(xs.shape[1]):
+            sn = _sinpi(xs[:, c][:, None] - bb[:, c][None, :]) / k.param
+            d += sn * sn
+        return k.variance * np.exp(-0.5 * d)
     return k.variance * kappa(k.kind, pairwise_sqdist(xs, x2s, form=form), k.param)
 
 
+def kernelmatrix(k: Kernel, x: np.ndarray, x2: Optional[np.ndarray] = None, *, form: str = "gemm") -> np.ndarray:
+    """``kernelmatrix(k, x[, x2])`` = ``variance * map(κ, pairwise(metric, s*x, s*x2))``; for a KernelSum / KernelProduct the
+    components' matrices added / multiplied left to right."""
+    K = _kernelmatrix_single(k, x, x2, form)
+    for t in k.terms:
+        Kt = _kernelmatrix_single(t, x, x2, form)
+        K = K * Kt if k.op == COMPOSE_PRODUCT else K + Kt
+    return K
+
+
+def kernel_kdiag(k: Kernel) -> float:
+    v = k.variance
+    for t in k.terms:
+        v = v * t.variance if k.op == COMPOSE_PRODUCT else v + t.variance
+    return v
+
+
 def kernelmatrix_diag(k: Kernel, x: np.ndarray) -> np.ndarray:
-    """``kernelmatrix_diag(k, x)`` = κ(0)·variance per point."""
-    return np.full(_as2d(x).shape[0], k.variance, dtype=np.float64)
+    """``kernelmatrix_diag(k, x)`` = κ(0)·variance per point (summed / multiplied over the terms of a composite kernel)."""
+    return np.full(_as2d(x).shape[0], kernel_kdiag(k), dtype=np.float64)
 
 
 # --------------------------------------------------------------------------------------------

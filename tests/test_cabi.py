@@ -118,8 +118,10 @@ def test_julia_shim_ccalls_match_the_header():
 
 
 def test_struct_layout_matches_header():
-    assert C.sizeof(_lib.GpDesc) == 48
+    assert C.sizeof(_lib.GpDesc) == 64
     assert _lib.GpDesc.variance.offset == 8 and _lib.GpDesc.mean_const.offset == 24 and _lib.GpDesc.ard.offset == 32
+    assert _lib.GpDesc.param.offset == 40 and _lib.GpDesc.n_extra.offset == 48 and _lib.GpDesc.extra.offset == 56
+    assert C.sizeof(_lib.KernelTerm) == 40 and _lib.KernelTerm.param.offset == 24 and _lib.KernelTerm.ard.offset == 32
 
 
 def test_version_and_host_only_entry_points():
@@ -250,13 +252,20 @@ def test_orthogonal_validate_uses_the_operator_norm(eps, ok):
 def test_julia_shim_describes_shape_parameter_and_ard():
     """the shim used to pass param = 1.0 and ard = C_NULL for every kernel (RationalQuadraticKernel's default
     α = 2 evaluated with α = 1, ARDTransform rejected).  Mechanical check of the source (Julia cannot run here): `describe`
-    carries the shape parameter and the ARD vector, `gpdescs` stores `pointer(ard)` and every ccall that takes the
-    descriptors runs under `GC.@preserve keep`."""
+    carries the shape parameter and the ARD vector, handles KernelSum / KernelProduct / PeriodicKernel, `gpdescs` stores the
+    ARD / extra-term pointers and every ccall that takes the descriptors runs under `GC.@preserve keep`."""
     jl = open(os.path.join(ROOT, "linearmixingmodels.jl_b200", "julia", "LinearMixingModelsB200.jl")).read()
     assert "describe(k::TransformedKernel{<:Kernel,<:ARDTransform})" in jl
-    assert "describe(k::KernelFunctions.SimpleKernel) = (kind(k), 1.0, 1.0, shape(k), nothing)" in jl
-    assert "p = pointer(ard)" in jl and "GpDesc(k, 0, v, s, meanconst(f.mean), p, a)" in jl
+    assert "describe(k::KernelSum)" in jl and "describe(k::KernelProduct)" in jl and "kind(::PeriodicKernel)" in jl
+    assert "(kind(k), 1.0, 1.0, shape(k), nothing)" in jl
+    assert "pointer(a)" in jl and "pointer(extra)" in jl
+    assert "GpDesc(t0[1], op, t0[2], t0[3], meanconst(f.mean), p, t0[4], length(extra), 0, px)" in jl
     assert "GpDesc.(" not in jl  # no call site builds descriptors without the keep-alive list any more
+    # the Julia structs mirror the C layout field for field
+    hdr = open(os.path.join(ROOT, "include", "lmm.h")).read()
+    c_fields = re.findall(r"^\s+(?:const\s+)?(?:int32_t|double|lmm_kernel_term)\s*\*?\s*(\w+);", hdr[hdr.index("typedef struct lmm_gp_desc {"):hdr.index("} lmm_gp_desc;")], flags=re.M)
+    jl_fields = re.findall(r"^\s+(\w+)::", jl[jl.index("struct GpDesc"):jl.index("const CTX")], flags=re.M)
+    assert c_fields == jl_fields, (c_fields, jl_fields)
     for fn_src in re.split(r"(?m)^(?=function )", jl):
         if "= gpdescs(" in fn_src and not fn_src.startswith("function gpdescs"):
             n_desc_calls = len(re.findall(r"ccall\(\(:lmm_[a-z0-9_]+, liblmm\), Cint,\s*\(Ptr\{Cvoid\}, Ptr\{GpDesc\}", fn_src))
