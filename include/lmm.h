@@ -104,31 +104,23 @@ const char* lmm_version(void);
  *   "outer_block"     tile columns per outer Cholesky step (default 8 for batched work, 1-4 by size for the
  *                     look-ahead schedules); 0 = back to automatic
  *   "streams"         latent groups factored concurrently on separate CUDA streams (default 4, 1..8)
- *   "lookahead"       schedule for batches <= 2: 0 plain, 1 left-looking with the wide update split along K,
- *                     2 right-looking with the next block column on the panel stream [default]
- *   "panel_split"     right-looking schedule only: 1 = before a column's diagonal-tile kernel only its diagonal tile is
- *                     updated on the panel stream, the rest of the column on a second high-priority stream (two
- *                     more cross-stream events per column: measured 1-3 % slower up to N=8192, 0.7 % faster at
- *                     N=16384).  Default 0.
- *   "pdl"             programmatic dependent launch along the batch-1 panel chain: the diagonal-tile kernel and the
- *                     small direct GEMMs are launched with programmatic stream serialisation, wait on
- *                     `griddepcontrol.wait` before their first read and release their successor before their
- *                     final stores (N=2048: -12 %, 4096: -5 %, 8192: -3 %).  Default 1; 0 = plain launches.
- *                                                                 [process-wide]
- *   "partition_ilmm"  the joint factor of a general ILMM (one large matrix, factored by every rank of the
- *                     communicator on identical inputs) is partitioned row-cyclically over the ranks: 1 = one
- *                     ncclAllGather of the current block column per step, panels redundant; 2 = the panel TRSM
- *                     distributed too, bulk exchange on a second communicator / stream.  Every rank must make
- *                     the same calls.  Default 0 (replicas).
- *   "profile_partition"  1: per-phase CUDA-event times of schedule 2 on stderr
+ *   "lookahead"       schedule for batches <= 2: 1 = right-looking block schedule, the next block column on a high-priority
+ *                     panel stream, the rest of the trailing update as one large GEMM on a second stream [default]; 0 = plain
+ *   "chain_fused"     1 = where the grids are small (batches <= 2, or few latents x few tile rows) the panel chain of a tile
+ *                     column -- TRSM of the column, update of the next column(s), factorisation of the next diagonal tile --
+ *                     is ONE launch whose CTAs hand tiles to each other through ready counters in global memory, the
+ *                     critical tiles first [default]; 0 = one launch per operation, chained by "pdl"
+ *   "pdl"             programmatic dependent launch along the panel chain: the diagonal-tile kernel, the small direct GEMMs
+ *                     and the fused chain kernel are launched with programmatic stream serialisation, wait on
+ *                     `griddepcontrol.wait` before their first read and release their successor before their final
+ *                     stores.  Default 1; 0 = plain launches.            [process-wide]
+ *   "partition_ilmm"  1 = the joint factor of a general ILMM (one large matrix, factored by every rank of the communicator
+ *                     on identical inputs) is partitioned row-cyclically over the ranks: one ncclAllGather of the current
+ *                     block column per step, panels redundant.  Every rank must make the same calls.  Default 0 (replicas).
  *   "nccl_small_ctas" CTA cap of the panel-chain communicator (takes effect at lmm_comm_init; 0 = NCCL's choice)
- *   "gemm_impl"       0 = cp.async ring + CTA barrier; 1 / 2 = TMA bulk copies + full/empty mbarrier ring with
- *                     16- / 32-column stages (default 2)          [process-wide]
- *   "gemm_small"      grids of at most this many tiles use the latency-optimised direct kernel (default 74,
- *                     0 = never)                                  [process-wide]
- *   "gemm_direct"     variant of that direct kernel: 0 = plain (4 slices per tile, one step of prefetch), 1 / 2 =
- *                     register-ring prefetch with 4 / 8 slices per tile and the zero blocks of the triangular
- *                     inverse skipped (default 2)                 [process-wide]
+ *   "gemm_small"      grids of at most this many tiles use the latency-optimised direct kernel (8 row slices per tile, no
+ *                     shared memory, zero blocks of the triangular inverse skipped) instead of the TMA-pipelined one
+ *                     (default 74, 0 = never)                            [process-wide]
  *   "project_impl"    projection + regulariser residual (T*Y, (I - UU')Y): 1 = FP64 tensor-core (DMMA) kernel with the column
  *                     block / row split sized to the SM count (default); 0 = register-tiled scalar-FMA kernel  [process-wide]
  *   "condition_update" lmm_post_condition on an OILMM / IndependentMOGP posterior: 1 = block-Cholesky update of each latent's
@@ -136,9 +128,7 @@ const char* lmm_version(void);
  *                     0 = re-factorise the union of the inputs, O((N + N₂)³)
  *   "solve_impl"      triangular vector solves (z = L^{-1} r, a = L^{-T} z): 1 = ONE persistent launch per direction, tile rows /
  *                     columns chained through ready flags in global memory (default); 0 = one launch per tile column
- *                                                                 [process-wide]
- *   "potrf_impl"      diagonal-tile kernel: 0 = first generation (right-looking, inverse after the factor),
- *                     1 = left-looking with the inverse built beside the panel steps (default) [process-wide] */
+ *                                                                 [process-wide] */
 int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value);
 /* Counters since context creation: kernels launched by this library, bytes copied H2D / D2H. */
 int lmm_ctx_counters(lmm_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);

@@ -162,7 +162,6 @@ extern "C" int lmm_ctx_create(int device, lmm_ctx** out) {
     cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
     cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, hi_pri);
     cudaStreamCreateWithPriority(&ctx->update_stream, cudaStreamNonBlocking, lo_pri);
-    cudaStreamCreateWithPriority(&ctx->xchg_stream, cudaStreamNonBlocking, hi_pri);
   }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   for (auto& e : ctx->ev_join) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -180,10 +179,8 @@ extern "C" int lmm_ctx_destroy(lmm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm_small && nccl_api().ok) nccl_api().CommDestroy(ctx->comm_small);
-  if (ctx->comm2 && nccl_api().ok) nccl_api().CommDestroy(ctx->comm2);
   if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
-  if (ctx->xbuf2) cudaFree(ctx->xbuf2);
-  cudaStreamDestroy(ctx->xchg_stream);
+  if (ctx->chain_cnt) cudaFree(ctx->chain_cnt);
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& g : ctx->gstream) cudaStreamDestroy(g);
   if (ctx->xbuf) cudaFree(ctx->xbuf);
@@ -219,19 +216,18 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
     if (value < 1 || value > lmm_ctx::MAX_GROUPS) return ctx->fail(LMM_E_ARG, "streams must be in [1, 8]");
     ctx->ngroups = (int)value;
   } else if (k == "lookahead") {
-    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "lookahead must be 0, 1 (left-looking, K-split) or 2 (right-looking)");
+    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_ARG, "lookahead must be 0 (plain) or 1 (right-looking block schedule on two streams)");
     ctx->lookahead = (int)value;
+  } else if (k == "chain_fused") {
+    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_ARG, "chain_fused must be 0 or 1");
+    ctx->chain_fused = (int)value;
   } else if (k == "pdl") {
     set_pdl(value != 0.0);
-  } else if (k == "panel_split") {
-    ctx->panel_split = value != 0.0;
   } else if (k == "nccl_small_ctas") {  // takes effect at lmm_comm_init
     if (value < 0 || value > 32) return ctx->fail(LMM_E_ARG, "nccl_small_ctas must be in [0, 32]");
     ctx->nccl_small_ctas = (int)value;
-  } else if (k == "profile_partition") {
-    ctx->profile_partition = value != 0.0;
   } else if (k == "partition_ilmm") {
-    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "partition_ilmm must be 0, 1 or 2");
+    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_ARG, "partition_ilmm must be 0 or 1");
     ctx->partition_ilmm = (int)value;
   } else if (k == "gemm_small") {
     if (value < 0 || value > 4096) return ctx->fail(LMM_E_ARG, "gemm_small must be in [0, 4096]");
@@ -245,15 +241,6 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "solve_impl") {
     if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_UNSUPPORTED, "solve_impl must be 0 or 1");
     set_solve_impl((int)value);
-  } else if (k == "potrf_impl") {
-    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_UNSUPPORTED, "potrf_impl must be 0 or 1");
-    set_potrf_impl((int)value);
-  } else if (k == "gemm_direct") {
-    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_direct must be 0, 1 or 2");
-    set_gemm_direct((int)value);
-  } else if (k == "gemm_impl") {
-    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_UNSUPPORTED, "gemm_impl must be 0, 1 or 2");
-    set_gemm_impl((int)value);
   } else {
     return ctx->fail(LMM_E_UNSUPPORTED, "unknown option " + k);
   }
@@ -320,7 +307,6 @@ extern "C" int lmm_comm_init(lmm_ctx* ctx, const void* unique_id_128_bytes, int 
       }
     };
     if (ctx->nccl_small_ctas > 0) split(&ctx->comm_small, ctx->nccl_small_ctas);
-    if (api.CommSplit(ctx->comm, 0, rank, &ctx->comm2, nullptr) != 0) ctx->comm2 = nullptr;
   }
   return LMM_OK;
 }

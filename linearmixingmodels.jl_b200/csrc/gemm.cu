@@ -6,137 +6,32 @@
 //   UPDATE: C(I,J) -= sum_{k in [k0,k1)} A(I,k) * B(J,k)^T        (128x128 tiles, K = 128 per k)
 //   TRSM  : C(I,J)  = C(I,J) * W(J)^T        with W(J) = inv(L(J,J)) (lower triangular)
 //
-// One CTA = one 128x128 output tile, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 m8n8k4 DMMA
-// fragments (64 accumulator doubles / thread).  Operands stream through a 4-stage cp.async ring
-// of 16-column k-chunks (16 KB of A + 16 KB of B per stage; chunks of consecutive k-tiles are
-// contiguous in HBM thanks to the row-panel-major tile order).  The k4-interleaved tile layout
-// makes every fragment load a conflict-free 256 B warp access (see common.cuh).
+// gemm_tile_kernel_v2: one CTA = one 128x128 output tile, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 m8n8k4 DMMA
+// fragments (64 accumulator doubles / thread).  Operands arrive by TMA bulk copies (cp.async.bulk -> SASS UBLKCP): one
+// elected thread issues two 32 KB copies per 32-column k-stage into a 3-stage / 192 KB ring; copies complete on `full`
+// mbarriers, the consumer warps release stages through `empty` mbarriers -- no CTA-wide barrier in the main loop.  Chunks of
+// consecutive k-tiles are contiguous in HBM (row-panel-major tile order) and the k4-interleaved tile layout makes every
+// fragment load a conflict-free 256 B warp access (see common.cuh).
+// gemm_direct2_kernel (direct_gemm.cuh): latency-optimised variant for the small grids of a panel chain -- no shared
+// memory, a tile split into 8 row slices (8 SMs per tile), fragments straight from L2 through a register ring.
 // Bound: FP64 tensor pipe (64 FMA/clk/SM): 2*128^3 flop per k-tile per CTA vs 256 KB of L2->SM
 // traffic -> 16 flop/B, far above the L2 balance; HBM traffic is lower still (row panels are
-// shared through L2 by the CTAs of one tile row / column).
+// shared through L2 by the CTAs of one tile row / column).  ncu (profiles/r02_ncu_summary.json): DMMA pipe active 97 % of
+// the cycles, 95.9 % of the FP64 tensor peak over elapsed time on the wide trailing update.
 #include "common.cuh"
 #include "kernels.h"
+#include "direct_gemm.cuh"
 
 namespace lmm {
 
-constexpr int GEMM_STAGES = 4;
-constexpr int CHUNK = 2048;  // doubles per operand per stage (128 rows x 16 k)
-constexpr size_t GEMM_SMEM = (size_t)GEMM_STAGES * 2 * CHUNK * sizeof(double);
+constexpr int CHUNK = 2048;  // doubles per operand per 16 k-columns (128 rows x 16 k)
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256, 1) gemm_tile_kernel(GemmArgs g) {
-  extern __shared__ __align__(128) double smem[];
-  const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y * (g.row_step > 0 ? g.row_step : 1), b = blockIdx.z;
-  if (g.sym && I < J) return;
-  if (g.upper && I > J) return;
-  const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;  // first k-tile of this CTA
-  if (MODE == GEMM_UPDATE && kb >= g.k1) return;
-
-  double* Ctile = g.C.tile(b, I, J);
-  const double* Asrc;
-  const double* Bsrc;
-  int nchunks;
-  if (MODE == GEMM_UPDATE) {
-    Asrc = g.A.tile(b, I, kb);
-    Bsrc = g.B.tile(b, J, kb);
-    nchunks = (g.k1 - kb) * 8;
-  } else {
-    Asrc = Ctile;
-    Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
-    nchunks = 8;
-  }
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 1, wn = warp >> 1;
-
-  double acc[8][4][2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  auto issue = [&](int q) {
-    double* sa = smem + (size_t)(q % GEMM_STAGES) * (2 * CHUNK);
-    double* sb = sa + CHUNK;
-    const double* ga = Asrc + (size_t)q * CHUNK;
-    const double* gb = Bsrc + (size_t)q * CHUNK;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = (tid + i * 256) * 2;
-      cp_async16(sa + idx, ga + idx);
-      cp_async16(sb + idx, gb + idx);
-    }
-  };
-
-#pragma unroll
-  for (int q = 0; q < GEMM_STAGES - 1; ++q) {
-    if (q < nchunks) issue(q);
-    cp_async_commit();
-  }
-
-  for (int q = 0; q < nchunks; ++q) {
-    cp_async_wait<GEMM_STAGES - 2>();
-    __syncthreads();
-    const int qn = q + GEMM_STAGES - 1;
-    if (qn < nchunks) issue(qn);
-    cp_async_commit();
-
-    const double* sa = smem + (size_t)(q % GEMM_STAGES) * (2 * CHUNK) + (wm * 8) * 32 + lane;
-    const double* sb = smem + (size_t)(q % GEMM_STAGES) * (2 * CHUNK) + CHUNK + (wn * 4) * 32 + lane;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      double a[8], bq[4];
-#pragma unroll
-      for (int mb = 0; mb < 8; ++mb) a[mb] = sa[ks * 512 + mb * 32];
-#pragma unroll
-      for (int nb = 0; nb < 4; ++nb) bq[nb] = sb[ks * 512 + nb * 32];
-#pragma unroll
-      for (int mb = 0; mb < 8; ++mb)
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], bq[nb]);
-    }
-  }
-  cp_async_wait<0>();
-
-  // Epilogue.  Accumulator fragment (mb, nb): rows R = wm*64 + mb*8 + lane/4, cols
-  // Cc = wn*32 + nb*8 + 2*(lane%4) + {0,1}  ->  one 16-byte store in the interleaved layout.
-  const int g4 = lane >> 2, t4 = lane & 3;
-#pragma unroll
-  for (int mb = 0; mb < 8; ++mb) {
-#pragma unroll
-    for (int nb = 0; nb < 4; ++nb) {
-      const int cg = wn * 8 + nb * 2 + (t4 >> 1);  // Cc / 4
-      const int off = (cg << 9) + ((wm * 8 + mb) << 5) + (g4 << 2) + ((t4 & 1) << 1);
-      double2* ptr = reinterpret_cast<double2*>(Ctile + off);
-      double2 v;
-      if (MODE == GEMM_UPDATE) {
-        v = *ptr;
-        v.x -= acc[mb][nb][0];
-        v.y -= acc[mb][nb][1];
-      } else {
-        v.x = acc[mb][nb][0];
-        v.y = acc[mb][nb][1];
-      }
-      *ptr = v;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// v2: TMA bulk copies + full/empty mbarrier ring, no CTA-wide barrier in the main loop.
+// TMA bulk copies + full/empty mbarrier ring, no CTA-wide barrier in the main loop.
 // One elected thread (warp 0, lane 0) is the producer on the side: per 16-column k-chunk it issues
 // two 16 KB cp.async.bulk copies (SASS UBLKCP) that complete on the stage's `full` mbarrier; each
 // of the 8 consumer warps waits on `full`, runs its 128 DMMAs and arrives on the stage's `empty`
@@ -330,207 +225,12 @@ __global__ void __launch_bounds__(256, 1) gemm_tile_kernel_v2(GemmArgs g) {
   }
 }
 
-// Latency-optimised variant for SMALL grids (the panel chain of a batch-1 / partitioned factorisation: a handful of
-// tiles whose 17 us per k-tile on one SM sit on the critical path).  One 128x128 tile is split into 4 row slices of 32
-// rows, one CTA each (4x the SMs per tile, a quarter of the time); no shared memory at all: in the k4-interleaved tile
-// layout every m8n8k4 fragment is 32 contiguous doubles in lane order, so each warp loads its A / B fragments with
-// coalesced 256-byte accesses straight from L2 (the 8 warps of a CTA share the A rows through L1).  Warp w owns columns
-// [16w, 16w+16) of the slice: 4 x 2 fragments, 8 DMMAs per k4-step.  TRSM is in place: a CTA only reads its own rows of
-// C(I,J), and a CTA barrier separates its last read from its first write.
-template <int MODE>
-__global__ void __launch_bounds__(256) gemm_direct_kernel(GemmArgs g) {
-  constexpr int SPLIT = 4;
-  const int J = g.j0 + (int)(blockIdx.x / SPLIT), slice = (int)(blockIdx.x % SPLIT);
-  const int I = g.i0 + blockIdx.y * (g.row_step > 0 ? g.row_step : 1), b = blockIdx.z;
-  if (g.sym && I < J) return;
-  if (g.upper && I > J) return;
-  const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;
-  if (MODE == GEMM_UPDATE && kb >= g.k1) return;
-  double* Ctile = g.C.tile(b, I, J);
-  const double* Asrc;
-  const double* Bsrc;
-  int nsteps;
-  if (MODE == GEMM_UPDATE) {
-    Asrc = g.A.tile(b, I, kb);
-    Bsrc = g.B.tile(b, J, kb);
-    nsteps = (g.k1 - kb) * 32;
-  } else {
-    Asrc = Ctile;
-    Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
-    nsteps = 32;
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double* pa = Asrc + (slice * 4) * 32 + lane;   // row blocks slice*4 .. slice*4+3
-  const double* pb = Bsrc + (warp * 2) * 32 + lane;    // column blocks warp*2, warp*2+1
-  double acc[4][2][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  double a[4], bq[2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) a[i] = pa[i * 32];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) bq[j] = pb[j * 32];
-#pragma unroll 4
-  for (int q = 0; q < nsteps; ++q) {
-    double an[4], bn[2];
-    const int qn = (q + 1 < nsteps) ? q + 1 : q;  // prefetch the next k4-step (512 doubles further: tiles of one row panel are contiguous)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) an[i] = pa[(size_t)qn * 512 + i * 32];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) bn[j] = pb[(size_t)qn * 512 + j * 32];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bq[j]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = an[i];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) bq[j] = bn[j];
-  }
-  if (MODE == GEMM_TRSM) __syncthreads();  // every warp of this CTA has finished reading its rows of C(I,J)
-  const int g4 = lane >> 2, t4 = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int cg = warp * 4 + j * 2 + (t4 >> 1);
-      const int off = (cg << 9) + ((slice * 4 + i) << 5) + (g4 << 2) + ((t4 & 1) << 1);
-      double2* ptr = reinterpret_cast<double2*>(Ctile + off);
-      double2 v;
-      if (MODE == GEMM_UPDATE) {
-        v = *ptr;
-        v.x -= acc[i][j][0];
-        v.y -= acc[i][j][1];
-      } else {
-        v.x = acc[i][j][0];
-        v.y = acc[i][j][1];
-      }
-      *ptr = v;
-    }
-}
-
-// Second-generation direct kernel: the same no-shared-memory scheme, with (a) the fragments of the next PF k4-steps in
-// flight while the current ones feed the tensor pipe (a register ring: the plain kernel waits one L2 round trip per
-// k4-step), (b) RB = 4 or 2 row blocks per CTA (a tile split over 4 or 8 SMs), and (c) in TRSM mode the zero blocks of the
-// lower-triangular W(J) skipped: warp w owns column blocks w and 15-w, i.e. 2(w+1) + 2(16-w) = 34 of 64 block-steps.
-template <int MODE, int RB, int PF>
-__global__ void __launch_bounds__(256) gemm_direct2_kernel(GemmArgs g) {
-  constexpr int SPLIT = 16 / RB;
-  const int J = g.j0 + (int)(blockIdx.x / SPLIT), slice = (int)(blockIdx.x % SPLIT);
-  const int I = g.i0 + blockIdx.y * (g.row_step > 0 ? g.row_step : 1), b = blockIdx.z;
-  if (g.sym && I < J) return;
-  if (g.upper && I > J) return;
-  const int kb = (g.k_from_row && I > g.k0) ? I : g.k0;
-  if (MODE == GEMM_UPDATE && kb >= g.k1) return;
-  double* Ctile = g.C.tile(b, I, J);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  pdl_wait();  // everything below reads what the previous kernel of the panel chain wrote
-  const double* Asrc;
-  const double* Bsrc;
-  int nsteps, nb0, nb1, lim0;
-  if (MODE == GEMM_UPDATE) {
-    Asrc = g.A.tile(b, I, kb);
-    Bsrc = g.B.tile(b, J, kb);
-    nsteps = (g.k1 - kb) * 32;
-    nb0 = warp * 2;
-    nb1 = warp * 2 + 1;
-    lim0 = nsteps;
-  } else {
-    Asrc = Ctile;
-    Bsrc = g.W + (size_t)b * g.w_batch_stride + (size_t)J * TT;
-    nb0 = warp;             // W^T block (k8, nb) is zero for k8 > nb: column block nb needs k4-steps q < 2 (nb + 1)
-    nb1 = 15 - warp;
-    lim0 = 2 * (nb0 + 1);
-    nsteps = 2 * (nb1 + 1);
-  }
-  const double* pa = Asrc + (slice * RB) * 32 + lane;
-  const double* pb0 = Bsrc + nb0 * 32 + lane;
-  const double* pb1 = Bsrc + nb1 * 32 + lane;
-  double acc[RB][2][2];
-#pragma unroll
-  for (int i = 0; i < RB; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  const int g4 = lane >> 2, t4 = lane & 3;
-  double2 cv[RB][2];  // UPDATE: the C fragments travel with the first operand fragments, not after the last DMMA
-  if (MODE == GEMM_UPDATE) {
-#pragma unroll
-    for (int i = 0; i < RB; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int cg = (j == 0 ? nb0 : nb1) * 2 + (t4 >> 1);
-        cv[i][j] = *reinterpret_cast<const double2*>(Ctile + (cg << 9) + ((slice * RB + i) << 5) + (g4 << 2) + ((t4 & 1) << 1));
-      }
-  }
-  double ra[PF][RB], rb[PF][2];
-#pragma unroll
-  for (int u = 0; u < PF; ++u) {
-    const int q = u < nsteps ? u : nsteps - 1;
-#pragma unroll
-    for (int i = 0; i < RB; ++i) ra[u][i] = pa[(size_t)q * 512 + i * 32];
-    rb[u][0] = pb0[(size_t)q * 512];
-    rb[u][1] = pb1[(size_t)q * 512];
-  }
-  for (int q0 = 0; q0 < nsteps; q0 += PF) {  // nsteps is even; PF steps per trip, the tail of the last trip is predicated off
-#pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int q = q0 + u;
-      double a[RB], bq[2];
-#pragma unroll
-      for (int i = 0; i < RB; ++i) a[i] = ra[u][i];
-      bq[0] = rb[u][0];
-      bq[1] = rb[u][1];
-      const int qn = (q + PF < nsteps) ? q + PF : nsteps - 1;
-#pragma unroll
-      for (int i = 0; i < RB; ++i) ra[u][i] = pa[(size_t)qn * 512 + i * 32];
-      rb[u][0] = pb0[(size_t)qn * 512];
-      rb[u][1] = pb1[(size_t)qn * 512];
-      if (q < nsteps) {
-        if (MODE == GEMM_UPDATE || q < lim0) {
-#pragma unroll
-          for (int i = 0; i < RB; ++i) dmma884(acc[i][0][0], acc[i][0][1], a[i], bq[0]);
-        }
-#pragma unroll
-        for (int i = 0; i < RB; ++i) dmma884(acc[i][1][0], acc[i][1][1], a[i], bq[1]);
-      }
-    }
-  }
-  pdl_trigger();  // the next kernel of the chain may be scheduled while this one stores
-  if (MODE == GEMM_TRSM) __syncthreads();  // every warp of this CTA has finished reading its rows of C(I,J)
-#pragma unroll
-  for (int i = 0; i < RB; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int cg = (j == 0 ? nb0 : nb1) * 2 + (t4 >> 1);
-      const int off = (cg << 9) + ((slice * RB + i) << 5) + (g4 << 2) + ((t4 & 1) << 1);
-      double2* ptr = reinterpret_cast<double2*>(Ctile + off);
-      double2 v;
-      if (MODE == GEMM_UPDATE) {
-        v = cv[i][j];
-        v.x -= acc[i][j][0];
-        v.y -= acc[i][j][1];
-      } else {
-        v.x = acc[i][j][0];
-        v.y = acc[i][j][1];
-      }
-      *ptr = v;
-    }
-}
-
 static int g_gemm_small = 74;  // grids of at most this many tiles take the latency-optimised kernel (0 = never)
 void set_gemm_small_threshold(int tiles) { g_gemm_small = tiles; }
 
 static bool g_pdl = true;   // programmatic dependent launch along the panel chain (direct kernels + diagonal-tile kernel)
 void set_pdl(int v) { g_pdl = v != 0; }
 bool pdl_enabled() { return g_pdl; }
-
-static int g_gemm_direct = 2;  // 0: plain direct kernel (4 slices, one step of prefetch); 1: register-ring prefetch, 4 slices; 2: ring, 8 slices
-void set_gemm_direct(int v) { g_gemm_direct = v; }
-
-static int g_gemm_impl = 2;  // 0: v1 cp.async ring; 1: v2 (TMA bulk + mbarriers), 16-column stages; 2: v2, 32-column stages
-void set_gemm_impl(int impl) { g_gemm_impl = impl; }
 
 cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols, int nrows, int batch) {
   if (ncols <= 0 || nrows <= 0 || batch <= 0) return cudaSuccess;
@@ -539,54 +239,22 @@ cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols,
   cudaGetDevice(&dev);
   bool& configured = configured_dev[dev & 63];
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel<GEMM_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tile_kernel<GEMM_TRSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_UPDATE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_TRSM, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_UPDATE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_UPDATE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tile_kernel_v2<GEMM_TRSM, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_V2_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   if ((long long)ncols * nrows * batch <= g_gemm_small) {
-    const int split = g_gemm_direct == 2 ? 8 : 4;
-    dim3 gs((unsigned)ncols * split, (unsigned)nrows, (unsigned)batch);
-    if (g_gemm_direct == 2) {
-      if (mode == GEMM_UPDATE)
-        return launch_pdl(g_pdl, gemm_direct2_kernel<GEMM_UPDATE, 2, 8>, gs, dim3(256), 0, st, a);
-      else
-        return launch_pdl(g_pdl, gemm_direct2_kernel<GEMM_TRSM, 2, 8>, gs, dim3(256), 0, st, a);
-    } else if (g_gemm_direct == 1) {
-      if (mode == GEMM_UPDATE)
-        gemm_direct2_kernel<GEMM_UPDATE, 4, 6><<<gs, 256, 0, st>>>(a);
-      else
-        gemm_direct2_kernel<GEMM_TRSM, 4, 6><<<gs, 256, 0, st>>>(a);
-    } else if (mode == GEMM_UPDATE)
-      gemm_direct_kernel<GEMM_UPDATE><<<gs, 256, 0, st>>>(a);
-    else
-      gemm_direct_kernel<GEMM_TRSM><<<gs, 256, 0, st>>>(a);
-    return cudaGetLastError();
+    dim3 gs((unsigned)ncols * DIRECT_SPLIT, (unsigned)nrows, (unsigned)batch);
+    if (mode == GEMM_UPDATE) return launch_pdl(g_pdl, gemm_direct2_kernel<GEMM_UPDATE>, gs, dim3(256), 0, st, a);
+    return launch_pdl(g_pdl, gemm_direct2_kernel<GEMM_TRSM>, gs, dim3(256), 0, st, a);
   }
   dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
-  if (g_gemm_impl == 1) {
-    if (mode == GEMM_UPDATE)
-      gemm_tile_kernel_v2<GEMM_UPDATE, 16><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
-    else
-      gemm_tile_kernel_v2<GEMM_TRSM, 16><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
-  } else if (g_gemm_impl == 2) {
-    if (mode == GEMM_UPDATE)
-      gemm_tile_kernel_v2<GEMM_UPDATE, 32><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
-    else
-      gemm_tile_kernel_v2<GEMM_TRSM, 32><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
-  } else if (mode == GEMM_UPDATE)
-    gemm_tile_kernel<GEMM_UPDATE><<<grid, 256, GEMM_SMEM, st>>>(a);
+  if (mode == GEMM_UPDATE)
+    gemm_tile_kernel_v2<GEMM_UPDATE, 32><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
   else
-    gemm_tile_kernel<GEMM_TRSM><<<grid, 256, GEMM_SMEM, st>>>(a);
+    gemm_tile_kernel_v2<GEMM_TRSM, 32><<<grid, 256, GEMM_V2_SMEM, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -12,8 +12,28 @@ namespace lmm_host {
 // and W(J), J < jstart, are already final; only the tile rows >= jstart are computed -- for the columns J < jstart that
 // is L(I,J) = (A(I,J) - sum_{k<J} L(I,k) L(J,k)') W(J)' (no diagonal-tile step), from column jstart on the ordinary
 // factorisation of the Schur complement.  Cost O(N² N₂) instead of O((N + N₂)³).
+// Counters of the fused panel-chain kernel (potrf.cu: chain_column_kernel): `batch` blocks of chain_counter_ints(nt) ints in
+// a context-owned buffer, zeroed on `st` (every column of a factorisation uses its own entries).
+static cudaError_t chain_counters(lmm_ctx* ctx, cudaStream_t st, int nt, int batch, int** out) {
+  const size_t need = (size_t)batch * chain_counter_ints(nt) * sizeof(int);
+  if (ctx->chain_cnt_bytes < need) {
+    if (ctx->chain_cnt) cudaFree(ctx->chain_cnt);
+    ctx->chain_cnt = nullptr;
+    ctx->chain_cnt_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->chain_cnt, need);
+    if (e != cudaSuccess) return e;
+    ctx->chain_cnt_bytes = need;
+  }
+  *out = (int*)ctx->chain_cnt;
+  return cudaMemsetAsync(ctx->chain_cnt, 0, need, st);
+}
+
+// Tiles of the TRSM of column jj below which a column's panel chain runs as ONE fused launch (chain_column_kernel: sliced,
+// shared-memory-free GEMM roles at one CTA per SM) instead of TMA-pipelined launches per operation.
+constexpr int CHAIN_MAX_TILES = 96;
+
 cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double* W, size_t wstride, int batch, double* logdet,
-                               int* info, int jstart = 0) {
+                               int* info, int jstart = 0, int* counters = nullptr) {
   const int nt = L.nt, ob = ctx->outer_block;
   GemmArgs g{};
   g.A = operand(L);
@@ -23,6 +43,7 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
   g.w_batch_stride = wstride;
   g.sym = 1;
   cudaError_t e;
+  bool factored_ahead = false;  // diagonal tile jj was factored by the previous column's fused chain launch
   for (int s0 = 0; s0 < nt; s0 += ob) {
     const int s1 = (s0 + ob < nt) ? s0 + ob : nt;
     if (s0 > 0) {
@@ -34,91 +55,32 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
     }
     for (int jj = s0; jj < s1; ++jj) {
       const int r0 = jj > jstart ? jj : jstart;
-      if (jj > s0) {
-        g.i0 = r0; g.j0 = jj; g.k0 = s0; g.k1 = jj;
-        if ((e = launch_gemm(st, GEMM_UPDATE, g, 1, nt - r0, batch)) != cudaSuccess) return e;
-        ++ctx->launches;
-        ctx->timings[6] += 1;
+      if (!factored_ahead) {
+        if (jj > s0) {
+          g.i0 = r0; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+          if ((e = launch_gemm(st, GEMM_UPDATE, g, 1, nt - r0, batch)) != cudaSuccess) return e;
+          ++ctx->launches;
+          ctx->timings[6] += 1;
+        }
+        if (jj >= jstart) {
+          if ((e = launch_potrf_tile(st, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
+          ++ctx->launches;
+        }
       }
-      if (jj >= jstart) {
-        if ((e = launch_potrf_tile(st, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
-        ++ctx->launches;
-      }
+      factored_ahead = false;
       const int t0 = jj + 1 > jstart ? jj + 1 : jstart;  // rows of column jj below the diagonal tile that are not final yet
-      if (t0 < nt) {
-        g.i0 = t0; g.j0 = jj;
-        if ((e = launch_gemm(st, GEMM_TRSM, g, 1, nt - t0, batch)) != cudaSuccess) return e;
+      if (t0 >= nt) continue;
+      // small grid, not at a block boundary, nothing above jstart involved: TRSM(jj) + update(jj+1) + potrf(jj+1) in one launch
+      if (counters && ctx->chain_fused && jj + 1 < s1 && jj >= jstart && (long long)(nt - 1 - jj) * batch <= CHAIN_MAX_TILES) {
+        if ((e = launch_chain_column(st, L, W, wstride, jj, s0, jj + 2, 1, batch, logdet, info, counters)) != cudaSuccess) return e;
         ++ctx->launches;
+        factored_ahead = true;
+        continue;
       }
-    }
-  }
-  return cudaSuccess;
-}
-
-// Block-level look-ahead (small batches: nothing else can hide the panel latency).  The wide
-// update of block column b is split along K: part A (all columns before block b-1) runs on the
-// update stream concurrently with the latency-bound panel steps of block b-1 on the high-priority
-// panel stream; part B (the columns of block b-1) follows on the panel stream.
-cudaError_t chol_factor_lookahead(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
-  const int nt = L.nt;
-  // the panel chain is the critical path here: narrower blocks for smaller matrices (measured)
-  const int ob = ctx->outer_block_user ? ctx->outer_block : (nt <= 40 ? 3 : nt <= 96 ? 6 : 8);
-  const int nblk = (nt + ob - 1) / ob;
-  cudaError_t e;
-  while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
-    cudaEvent_t ev;
-    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
-    ctx->blk_ev.push_back(ev);
-  }
-  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream;
-  cudaEvent_t* evI = ctx->blk_ev.data();          // inner(b) done on X
-  cudaEvent_t* evA = ctx->blk_ev.data() + nblk;   // part A(b) done on Y
-  GemmArgs g{};
-  g.A = operand(L); g.B = operand(L); g.C = operand(L);
-  g.W = W; g.w_batch_stride = wstride; g.sym = 1;
-  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
-  bool y_used = false;
-  for (int b = 0; b < nblk; ++b) {
-    const int s0 = b * ob, s1 = (s0 + ob < nt) ? s0 + ob : nt;
-    const int sp = (b >= 1) ? (b - 1) * ob : 0;  // first column of block b-1
-    if (b >= 2) {  // part A on Y: k in [0, sp)
-      if ((e = cudaStreamWaitEvent(Y, evI[b - 2], 0)) != cudaSuccess) return e;
-      g.i0 = s0; g.j0 = s0; g.k0 = 0; g.k1 = sp;
-      if ((e = launch_gemm(Y, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
-      if ((e = cudaEventRecord(evA[b], Y)) != cudaSuccess) return e;
-      if ((e = cudaStreamWaitEvent(X, evA[b], 0)) != cudaSuccess) return e;
+      g.i0 = t0; g.j0 = jj;
+      if ((e = launch_gemm(st, GEMM_TRSM, g, 1, nt - t0, batch)) != cudaSuccess) return e;
       ++ctx->launches;
-      ctx->timings[6] += 1;
-      y_used = true;
     }
-    if (b >= 1) {  // part B on X: k in [sp, s0)
-      g.i0 = s0; g.j0 = s0; g.k0 = sp; g.k1 = s0;
-      if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
-      ++ctx->launches;
-      ctx->timings[6] += 1;
-    }
-    for (int jj = s0; jj < s1; ++jj) {
-      if (jj > s0) {
-        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
-        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
-        ++ctx->launches;
-      }
-      if ((e = launch_potrf_tile(X, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
-      ++ctx->launches;
-      if (jj + 1 < nt) {
-        g.i0 = jj + 1; g.j0 = jj;
-        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
-        ++ctx->launches;
-      }
-    }
-    if ((e = cudaEventRecord(evI[b], X)) != cudaSuccess) return e;
-  }
-  if ((e = cudaStreamWaitEvent(ctx->stream, evI[nblk - 1], 0)) != cudaSuccess) return e;
-  if (y_used) {
-    if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
@@ -139,119 +101,92 @@ cudaError_t launch_trailing(lmm_ctx* ctx, cudaStream_t st, GemmArgs g, int s2, i
   return cudaSuccess;
 }
 
-// Right-looking block schedule with look-ahead (small batches).  After block column kb is factored on the
-// high-priority panel stream X, its update of the NEXT block column runs on X (so the next panel can start at
-// once) while its update of everything further right runs as one large GEMM on the low-priority stream Y:
+// Right-looking block schedule with look-ahead (small batches: nothing else can hide the panel latency).  After block
+// column kb is factored on the high-priority panel stream X, its update of the NEXT block column runs on X (so the next
+// panel can start at once) while its update of everything further right runs as one large GEMM on the low-priority
+// stream Y:
 //   X: [wait Y(kb-2)] update(kb-1 -> kb), panel(kb)            Y: [wait X(kb)] update(kb -> kb+2 .. end)
 // The Y launches have thousands of tiles (no tail effect, unlike the wide left-looking update of one block
 // column) and keep every SM busy while the latency-bound panel steps run beside them; each C tile is
 // read-modify-written once per block column of L (K = `ob` tiles per launch).
+// Panel chain on X, per tile column jj of block [s0, s1): with "chain_fused" (default) ONE launch --
+//   inside the block:      TRSM(jj) + update(column jj+1 by k in [s0, jj]) + potrf(jj+1)
+//   at the block boundary: [wait Y(kb-1)]  TRSM(s1-1) + update(columns [s1, s2) by k in [s0, s1)) + potrf(s1)
+// (chain_column_kernel: the critical tiles (jj+1, jj) -> (jj+1, jj+1) -> diagonal factorisation come first, everything else
+// runs beside the factorisation); without it three launches per column chained by programmatic dependent launch.
 cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info) {
   const int nt = L.nt;
   // the panel chain is the critical path: narrow blocks for small matrices, wider ones (fewer read-modify-write
   // passes over the trailing matrix) once the trailing GEMMs dominate (measured: tools/bench_batch1.py)
-  const int ob = ctx->outer_block_user ? ctx->outer_block : (nt <= 32 ? 1 : nt <= 72 ? 2 : nt <= 112 ? 3 : 4);
+  const bool fused = ctx->chain_fused != 0;
+  const int ob = ctx->outer_block_user ? ctx->outer_block : fused ? (nt <= 72 ? 2 : nt <= 112 ? 3 : 4) : (nt <= 32 ? 1 : nt <= 72 ? 2 : nt <= 112 ? 3 : 4);
   const int nblk = (nt + ob - 1) / ob;
-  // "panel_split": only the DIAGONAL tile of the next column is updated on the panel stream before its factorisation;
-  // the rest of that column -- needed by the TRSM that follows the diagonal-tile kernel, not by the kernel itself -- is
-  // updated on a second high-priority stream X2 meanwhile.
-  const bool split = ctx->panel_split != 0;
   cudaError_t e;
-  while ((int)ctx->blk_ev.size() < 2 * nblk + 2 + 2 * nt + 2) {
+  while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
     cudaEvent_t ev;
     if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     ctx->blk_ev.push_back(ev);
   }
-  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream, X2 = ctx->xchg_stream;
+  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream;
   cudaEvent_t* evX = ctx->blk_ev.data();          // panel(b) done on X
   cudaEvent_t* evY = ctx->blk_ev.data() + nblk;   // trailing update from block b done on Y
-  cudaEvent_t* evT = ctx->blk_ev.data() + 2 * nblk + 2;  // split: TRSM of column j done on X
-  cudaEvent_t* evU = evT + nt;                           // split: rest-of-column update(s) up to column j done on X2
-  int last_u = -1;                                       // latest evU that X has not waited for yet
   GemmArgs g{};
   g.A = operand(L); g.B = operand(L); g.C = operand(L);
   g.W = W; g.w_batch_stride = wstride; g.sym = 1;
+  int* counters = nullptr;
+  if (fused && (e = chain_counters(ctx, ctx->stream, nt, batch, &counters)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
-  if (split && (e = cudaStreamWaitEvent(X2, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  bool factored_ahead = false;  // the block's first diagonal tile was factored by the previous block's boundary launch
   for (int b = 0; b < nblk; ++b) {
     const int s0 = b * ob, s1 = (s0 + ob < nt) ? s0 + ob : nt;
-    if (b >= 1) {
+    const int s2 = (s1 + ob < nt) ? s1 + ob : nt;  // end of the next block
+    if (b >= 1 && !factored_ahead) {
       // every earlier update of this block column (Y launches up to b-2) must have landed
       if (b >= 2 && (e = cudaStreamWaitEvent(X, evY[b - 2], 0)) != cudaSuccess) return e;
-      g.k0 = s0 - ob; g.k1 = s0;
-      if (!split) {
-        g.i0 = s0; g.j0 = s0;
-        if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
-        ++ctx->launches;
-      } else {
-        g.i0 = s0; g.j0 = s0;
-        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, 1, batch)) != cudaSuccess) return e;
-        ++ctx->launches;
-        if (s0 + 1 < nt) {  // all other tiles of the block columns (the symmetric-skip leaves row s0 to the launch above)
-          if (b >= 2 && (e = cudaStreamWaitEvent(X2, evY[b - 2], 0)) != cudaSuccess) return e;
-          if ((e = cudaStreamWaitEvent(X2, evT[s0 - 1], 0)) != cudaSuccess) return e;
-          g.i0 = s0 + 1; g.j0 = s0;
-          if ((e = launch_gemm(X2, GEMM_UPDATE, g, s1 - s0, nt - s0 - 1, batch)) != cudaSuccess) return e;
-          ++ctx->launches;
-          if ((e = cudaEventRecord(evU[s0], X2)) != cudaSuccess) return e;
-          last_u = s0;
-        }
-      }
+      g.k0 = s0 - ob; g.k1 = s0; g.i0 = s0; g.j0 = s0;
+      if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, nt - s0, batch)) != cudaSuccess) return e;
+      ++ctx->launches;
       ctx->timings[6] += 1;
     }
     for (int jj = s0; jj < s1; ++jj) {
-      if (jj > s0) {
-        g.k0 = s0; g.k1 = jj;
-        if (!split) {
-          g.i0 = jj; g.j0 = jj;
+      if (!factored_ahead) {
+        if (jj > s0) {
+          g.k0 = s0; g.k1 = jj; g.i0 = jj; g.j0 = jj;
           if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, batch)) != cudaSuccess) return e;
           ++ctx->launches;
-        } else {
-          g.i0 = jj; g.j0 = jj;
-          if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, 1, batch)) != cudaSuccess) return e;
-          ++ctx->launches;
-          if (jj + 1 < nt) {
-            if ((e = cudaStreamWaitEvent(X2, evT[jj - 1], 0)) != cudaSuccess) return e;
-            g.i0 = jj + 1; g.j0 = jj;
-            if ((e = launch_gemm(X2, GEMM_UPDATE, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
-            ++ctx->launches;
-            if ((e = cudaEventRecord(evU[jj], X2)) != cudaSuccess) return e;
-            last_u = jj;
-          }
         }
+        if ((e = launch_potrf_tile(X, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
+        ++ctx->launches;
       }
-      if ((e = launch_potrf_tile(X, L, W, wstride, jj, batch, logdet, info)) != cudaSuccess) return e;
-      ++ctx->launches;
-      if (jj + 1 < nt) {
-        if (split && last_u >= 0) {
-          if ((e = cudaStreamWaitEvent(X, evU[last_u], 0)) != cudaSuccess) return e;
-          last_u = -1;
+      factored_ahead = false;
+      if (jj + 1 >= nt) continue;
+      if (fused) {
+        int c_end = jj + 2;
+        if (jj + 1 == s1) {  // block boundary: the launch also carries the panel stream's update of the whole next block
+          if (b >= 1 && (e = cudaStreamWaitEvent(X, evY[b - 1], 0)) != cudaSuccess) return e;  // Y(b-1) writes the columns >= s1
+          c_end = s2;
         }
+        if ((e = launch_chain_column(X, L, W, wstride, jj, s0, c_end, 1, batch, logdet, info, counters)) != cudaSuccess) return e;
+        ++ctx->launches;
+        factored_ahead = true;
+      } else {
         g.i0 = jj + 1; g.j0 = jj;
         if ((e = launch_gemm(X, GEMM_TRSM, g, 1, nt - jj - 1, batch)) != cudaSuccess) return e;
         ++ctx->launches;
-        if (split && (e = cudaEventRecord(evT[jj], X)) != cudaSuccess) return e;
       }
     }
     if ((e = cudaEventRecord(evX[b], X)) != cudaSuccess) return e;
-    const int s2 = s1 + ob;  // first column of block b+2
-    if (s2 < nt) {
+    if (s1 + ob < nt) {  // first column of block b+2
       if ((e = cudaStreamWaitEvent(Y, evX[b], 0)) != cudaSuccess) return e;
-      if ((e = launch_trailing(ctx, Y, g, s2, nt, s2, 1, s0, s1, batch)) != cudaSuccess) return e;
-      if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
-    } else if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) {  // no trailing launch left: keep the event chain defined
-      return e;
+      if ((e = launch_trailing(ctx, Y, g, s1 + ob, nt, s1 + ob, 1, s0, s1, batch)) != cudaSuccess) return e;
     }
+    if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
   }
   if ((e = cudaStreamWaitEvent(ctx->stream, evX[nblk - 1], 0)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
-  if (split) {  // every X2 launch is followed by a TRSM on X that waited for it; joined explicitly all the same
-    if ((e = cudaEventRecord(ctx->ev_join[1], X2)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0)) != cudaSuccess) return e;
-  }
   return cudaSuccess;
 }
 
@@ -349,187 +284,31 @@ cudaError_t chol_factor_rowcyclic(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
   return cudaSuccess;
 }
 
-// Second row-cyclic schedule ("partition_ilmm" = 2): the panel's TRSM is distributed as well and the large exchange leaves
-// the critical path.  Per block column b = [s0, s1), next block [s1, s2):
-//   X (panel stream, communicator 1): update(b-1 -> b) on own rows; all-gather of the DIAGONAL block rows [s0, s1) (<= ob
-//     tile rows); diagonal block factored redundantly; TRSM of the OWN rows >= s1; all-gather of the NEXT block's rows
-//     [s1, s2) of the finished panel -- all the next update(b -> b+1) needs besides the own rows.
-//   Z (exchange stream, communicator 2): all-gather of the rows >= s2 of the finished panel -- the bulk of the data --
-//     concurrently with the next panel; it only gates
-//   Y (update stream): update(b -> b+2..end) on own rows.
-// Everything on the panel chain is small (<= 2 ob tile rows exchanged, 1/G of the TRSM and update waves).
-cudaError_t chol_factor_rowcyclic2(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, double* logdet, int* info) {
-  const int nt = L.nt, G = ctx->nranks, me = ctx->rank;
-  const int ob = ctx->outer_block_user ? ctx->outer_block : (nt <= 72 ? 2 : nt <= 160 ? 3 : 4);
-  const int nblk = (nt + ob - 1) / ob;
-  cudaError_t e;
-  while ((int)ctx->blk_ev.size() < 3 * nblk + 3) {
-    cudaEvent_t ev;
-    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
-    ctx->blk_ev.push_back(ev);
-  }
-  auto grow = [&](void*& buf, size_t& have, size_t need) -> cudaError_t {
-    if (have >= need) return cudaSuccess;
-    if (buf) cudaFree(buf);
-    buf = nullptr;
-    have = 0;
-    cudaError_t ee = cudaMalloc(&buf, need);
-    if (ee == cudaSuccess) have = need;
-    return ee;
-  };
-  // small exchanges (<= ob rows): [send | recv]; large ones: sized for the first block
-  const int small_slots = (2 * ob + G - 1) / G;
-  const size_t small_send = (size_t)small_slots * ob * TT;
-  if ((e = grow(ctx->xbuf, ctx->xbuf_bytes, small_send * (size_t)(G + 1) * sizeof(double))) != cudaSuccess) return e;
-  const int big_slots0 = (nt + G - 1) / G;
-  const size_t big_send = (size_t)big_slots0 * ob * TT;
-  if ((e = grow(ctx->xbuf2, ctx->xbuf2_bytes, big_send * (size_t)(G + 1) * sizeof(double))) != cudaSuccess) return e;
-  double* ssend = (double*)ctx->xbuf;
-  double* srecv = ssend + small_send;
-  double* bsend = (double*)ctx->xbuf2;
-  double* brecv = bsend + big_send;
-  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream, Z = ctx->xchg_stream;
-  cudaEvent_t* evX = ctx->blk_ev.data();
-  cudaEvent_t* evY = evX + nblk;
-  cudaEvent_t* evZ = evY + nblk;
-  GemmArgs g{};
-  g.A = operand(L); g.B = operand(L); g.C = operand(L);
-  g.W = W; g.w_batch_stride = wstride; g.sym = 1;
-  auto first_own = [&](int s) { return s + (((me - s % G) % G) + G) % G; };
-  auto own_count = [&](int s) { const int f = first_own(s); return f >= nt ? 0 : (nt - 1 - f) / G + 1; };
-  auto gather = [&](cudaStream_t st, void* comm, int s0, int s1, int ra, int rb, double* sendb, double* recvb) -> cudaError_t {
-    if (rb <= ra) return cudaSuccess;
-    const int slots = (rb - ra + G - 1) / G;
-    cudaError_t ee;
-    if ((ee = launch_rowcyclic_pack(st, L, s0, s1, ra, rb, G, me, slots, sendb)) != cudaSuccess) return ee;
-    if (nccl_api().AllGather(sendb, recvb, (size_t)slots * (s1 - s0) * TT, NCCL_DOUBLE, comm, st) != 0) {
-      ctx->dist_error = 1;
-      return cudaErrorUnknown;
-    }
-    if ((ee = launch_rowcyclic_unpack(st, L, s0, s1, ra, rb, G, me, slots, recvb)) != cudaSuccess) return ee;
-    ctx->launches += 2;
-    return cudaSuccess;
-  };
-  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(Z, ctx->ev_fork, 0)) != cudaSuccess) return e;
-  // optional phase profile of the panel chain: [0] wait for the trailing update, [1] own-row update, [2] exchange,
-  // [3] redundant diagonal / next-block rows, [4] own-row TRSM
-  std::vector<cudaEvent_t> pev;
-  const bool prof = ctx->profile_partition != 0;
-  auto mark = [&]() {
-    if (!prof) return;
-    cudaEvent_t ev;
-    cudaEventCreate(&ev);
-    cudaEventRecord(ev, X);
-    pev.push_back(ev);
-  };
-  for (int b = 0; b < nblk; ++b) {
-    const int s0 = b * ob, s1 = (s0 + ob < nt) ? s0 + ob : nt, s2 = (s1 + ob < nt) ? s1 + ob : nt;
-    mark();
-    if (b >= 2 && (e = cudaStreamWaitEvent(X, evY[b - 2], 0)) != cudaSuccess) return e;
-    mark();
-    if (b >= 1) {
-      const int cnt = own_count(s0);
-      if (cnt > 0) {  // own rows of block column b <- block b-1 (B operand rows [s0, s1) arrived with the previous panel)
-        g.row_step = G; g.i0 = first_own(s0); g.j0 = s0; g.k0 = s0 - ob; g.k1 = s0;
-        if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, cnt, 1)) != cudaSuccess) return e;
-        ++ctx->launches;
-        ctx->timings[6] += 1;
-      }
-      mark();
-      // the diagonal block AND the next block's rows, in one small exchange
-      if ((e = gather(X, ctx->comm_small ? ctx->comm_small : ctx->comm, s0, s1, s0, s2, ssend, srecv)) != cudaSuccess) return e;
-    }
-    if (b == 0) mark();
-    mark();
-    g.row_step = 1;
-    for (int jj = s0; jj < s1; ++jj) {  // diagonal block and the next block's rows [s1, s2): every rank
-      if (jj > s0) {
-        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
-        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, s2 - jj, 1)) != cudaSuccess) return e;
-        ++ctx->launches;
-      }
-      if ((e = launch_potrf_tile(X, L, W, wstride, jj, 1, logdet, info)) != cudaSuccess) return e;
-      ++ctx->launches;
-      if (jj + 1 < s2) {
-        g.i0 = jj + 1; g.j0 = jj;
-        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, s2 - jj - 1, 1)) != cudaSuccess) return e;
-        ++ctx->launches;
-      }
-    }
-    mark();
-    const int cnt1 = s2 < nt ? own_count(s2) : 0;
-    if (cnt1 > 0) {  // own rows below: in-block updates + TRSM, column by column
-      g.row_step = G; g.i0 = first_own(s2);
-      for (int jj = s0; jj < s1; ++jj) {
-        if (jj > s0) {
-          g.j0 = jj; g.k0 = s0; g.k1 = jj;
-          if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, cnt1, 1)) != cudaSuccess) return e;
-          ++ctx->launches;
-        }
-        g.j0 = jj;
-        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, cnt1, 1)) != cudaSuccess) return e;
-        ++ctx->launches;
-      }
-    }
-    mark();
-    if ((e = cudaEventRecord(evX[b], X)) != cudaSuccess) return e;
-    if (s2 < nt) {
-      // the bulk of the panel travels beside the next panel's work and only gates the trailing update
-      if ((e = cudaStreamWaitEvent(Z, evX[b], 0)) != cudaSuccess) return e;
-      if ((e = gather(Z, ctx->comm2, s0, s1, s2, nt, bsend, brecv)) != cudaSuccess) return e;
-      if ((e = cudaEventRecord(evZ[b], Z)) != cudaSuccess) return e;
-      const int cnt2 = own_count(s2);
-      if (cnt2 > 0) {
-        if ((e = cudaStreamWaitEvent(Y, evZ[b], 0)) != cudaSuccess) return e;
-        if ((e = launch_trailing(ctx, Y, g, s2, nt, first_own(s2), G, s0, s1, 1)) != cudaSuccess) return e;
-      }
-    }
-    if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
-  }
-  if ((e = cudaStreamWaitEvent(ctx->stream, evX[nblk - 1], 0)) != cudaSuccess) return e;
-  if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
-  if ((e = cudaEventRecord(ctx->ev_join[1], Z)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0)) != cudaSuccess) return e;
-  if (prof) {
-    cudaStreamSynchronize(X);
-    double acc[5] = {0, 0, 0, 0, 0};
-    for (int b = 0; b < nblk; ++b)
-      for (int k = 0; k < 5; ++k) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, pev[(size_t)b * 6 + k], pev[(size_t)b * 6 + k + 1]);
-        acc[k] += ms;
-      }
-    fprintf(stderr, "[liblmm rank %d] row-cyclic chain, nt=%d ob=%d: wait_trailing %.2f ms, own_update %.2f, exchange %.2f, "
-                    "diag+next rows %.2f, own TRSM %.2f\n", me, nt, ob, acc[0], acc[1], acc[2], acc[3], acc[4]);
-    for (cudaEvent_t ev : pev) cudaEventDestroy(ev);
-  }
-  return cudaSuccess;
-}
-
 // Fork the batch into latent groups on separate streams (joined back into ctx->stream).  jstart > 0: extend a factor whose
 // tile rows < jstart are final (see chol_factor_stream).
 cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info, int jstart) {
   const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
   if (jstart == 0) {  // the look-ahead / partitioned schedules factor from scratch only
     if (ctx->partition_ilmm && ctx->partition_now && batch == 1 && ctx->comm && ctx->nranks > 1 && L.nt >= 2 * ctx->nranks && nccl_api().AllGather)
-      return (ctx->partition_ilmm == 2 && ctx->comm2) ? chol_factor_rowcyclic2(ctx, L, W, wstride, logdet, info)
-                                                      : chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
-    if (ctx->lookahead == 2 && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
-    if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_lookahead(ctx, L, W, wstride, batch, logdet, info);
+      return chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
+    if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
   }
-  if (G <= 1 || L.nt <= 1) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info, jstart);
   cudaError_t e;
+  // small grids (few latents x few tile rows, e.g. the reference's notebook shape: 20 latents, 5 tile columns): ONE stream,
+  // one fused launch per tile column -- stream groups would only multiply the launches
+  int* counters = nullptr;
+  const bool chain_all = ctx->chain_fused && (long long)(L.nt - 1) * batch <= CHAIN_MAX_TILES && L.nt > 1;
+  if (ctx->chain_fused && L.nt > 1 && (e = chain_counters(ctx, ctx->stream, L.nt, batch, &counters)) != cudaSuccess) return e;
+  if (G <= 1 || L.nt <= 1 || chain_all) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info, jstart, counters);
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
   for (int gi = 0; gi < G; ++gi) {
     const int b0 = (int)((int64_t)batch * gi / G), b1 = (int)((int64_t)batch * (gi + 1) / G);
     cudaStream_t st = ctx->gstream[gi];
     if ((e = cudaStreamWaitEvent(st, ctx->ev_fork, 0)) != cudaSuccess) return e;
     TiledSym Lg{L.base + (size_t)b0 * L.batch_stride, L.nt, L.batch_stride};
-    if ((e = chol_factor_stream(ctx, st, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0, logdet + b0, info + b0, jstart)) != cudaSuccess) return e;
+    if ((e = chol_factor_stream(ctx, st, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0, logdet + b0, info + b0, jstart,
+                                counters ? counters + (size_t)b0 * chain_counter_ints(L.nt) : nullptr)) != cudaSuccess)
+      return e;
     if ((e = cudaEventRecord(ctx->ev_join[gi], st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[gi], 0)) != cudaSuccess) return e;
   }

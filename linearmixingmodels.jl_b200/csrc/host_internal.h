@@ -58,12 +58,6 @@ struct lmm_ctx {
   void* comm = nullptr;
   void* comm_small = nullptr;  // few-CTA communicator for the small, latency-critical exchanges on the panel chain
   int nccl_small_ctas = 0;  // 0: NCCL's own choice
-  int profile_partition = 0;  // option "profile_partition": per-phase CUDA-event times of the row-cyclic schedule on stderr
-  void* comm2 = nullptr;  // second communicator (ncclCommSplit): the large exchanges of the partitioned factorisation, which
-                          // overlap the panel chain's small ones on another stream
-  cudaStream_t xchg_stream = nullptr;
-  void* xbuf2 = nullptr;
-  size_t xbuf2_bytes = 0;
   int64_t launches = 0, h2d = 0, d2h = 0;
   size_t total_mem = 0;  // device memory size, queried once (mem_fit)
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -78,8 +72,10 @@ struct lmm_ctx {
   // trailing-update stream, chained by per-block events
   cudaStream_t panel_stream = nullptr, update_stream = nullptr;
   std::vector<cudaEvent_t> blk_ev;
-  int lookahead = 2;  // 0 off, 1 left-looking K-split, 2 right-looking (default)
-  int panel_split = 0;  // right-looking schedule: next column's diagonal tile on the panel stream, the rest of it on a second one
+  int lookahead = 1;  // small batches (<= 2): 1 = right-looking block schedule on two streams (default), 0 = plain
+  int chain_fused = 1;  // panel chain of a column (TRSM + next-column update + next diagonal tile) as ONE launch where the grids are small
+  void* chain_cnt = nullptr;  // ready counters of the fused chain kernel
+  size_t chain_cnt_bytes = 0;
   // one large factor (general ILMM, batch 1) partitioned row-cyclically over the ranks of the communicator
   int partition_ilmm = 0;
   int condition_update = 1;  // sequential conditioning of per-latent posteriors: 1 = block-Cholesky update of the factor, 0 = re-factorise the union

@@ -44,13 +44,17 @@ cudaError_t launch_gemm(cudaStream_t st, int mode, const GemmArgs& a, int ncols,
 void set_gemm_small_threshold(int tiles);  // grids of <= tiles tiles use the latency-optimised direct kernel (default 74; 0 = off)
 void set_pdl(int v);       // 1: programmatic dependent launch along the batch-1 panel chain (default 1)
 bool pdl_enabled();
-void set_gemm_direct(int v);  // direct-kernel variant: 0 plain, 1 register-ring prefetch with 4 slices per tile, 2 with 8 slices
-void set_gemm_impl(int impl);  // 0: cp.async ring + CTA barrier; 1/2: TMA bulk + full/empty mbarrier ring, 16/32-column stages (2 = default)
 
 // ---- potrf.cu : factor diagonal tile (J,J) in place, W(J) = inv(L_JJ), logdet += 2*sum(log diag)
-void set_potrf_impl(int v);  // 0: first-generation diagonal-tile kernel, 1: overlapped-inverse kernel (default)
 cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int batch, double* logdet,
                               int* info);
+
+// Fused panel chain of one tile column (small batches): TRSM of column J, update of the columns (J, c_end) by the k-tiles
+// [k0, J], and (do_potrf) the factorisation of diagonal tile J+1 in ONE launch (potrf.cu: chain_column_kernel).
+// counters: batch * chain_counter_ints(nt) ints, zeroed once per factorisation.
+size_t chain_counter_ints(int nt);
+cudaError_t launch_chain_column(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int k0, int c_end, int do_potrf,
+                                int batch, double* logdet, int* info, int* counters);
 
 // ---- solve.cu
 // forward: z = L^{-1} r; backward: a = L^{-T} r.  rvec[batch][nt*128] is consumed (destroyed).

@@ -4,19 +4,15 @@
 // One CTA (8 warps) per latent; the 128x128 tile lives in shared memory, column-major with
 // ld = 132 (conflict-free DMMA fragment loads: column stride = 8 banks).
 //
-// Two kernels.  potrf_tile_kernel (first generation, "potrf_impl" = 0):
-//   phase C: 16 steps of 8 columns: 8x8 diagonal block factored in registers (rsqrt pivots,
-//            redundantly by every row-owner thread -> no intra-block syncs), panel rows solved
-//            in registers, trailing update of the tile on the FP64 tensor pipe (m8n8k4 DMMA).
-//   phase W: in-place recursive inverse of the lower triangle: 8x8 diagonal blocks by
-//            substitution, then 4 doubling levels  W21 = -W22 (L21 W11)  as DMMA block products;
-//            the temporary L21*W11 lives in the (free) mirrored upper block.
-// potrf_tile_kernel2 (default): left-looking column updates, reciprocal pivot chain, W built beside
-// the panel steps -- described above its definition.
+// potrf_tile_body (below): left-looking column updates inside the tile, reciprocal pivot chain, W built beside the panel
+// steps.  Two kernels run it: potrf_tile_kernel2 (one launch per tile column) and chain_column_kernel, which fuses the
+// whole per-column panel chain of a small-batch factorisation -- TRSM of column J, update of column J+1, diagonal tile
+// J+1 -- into one launch whose CTAs hand tiles to each other through ready counters in global memory.
 // Latency-bound by design (it sits on the critical path of each tile column; the host runs
 // several latent groups on separate streams so the other SMs keep doing trailing updates).
 #include "common.cuh"
 #include "kernels.h"
+#include "direct_gemm.cuh"
 
 namespace lmm {
 
@@ -56,266 +52,9 @@ __device__ __forceinline__ void dmma884p(double& d0, double& d1, double a, doubl
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// C(8x8 at R0,N0) (+)= sign * sum over 8-wide k-blocks  A(R0, K0+8kk) * B(K0+8kk, N0)
-// A block element (r,k) at S[(K0+k)*LD + R0+r]; B block element (k,n) at S[(N0+n)*LD + K0+k].
-__device__ __forceinline__ void block_mma(const double* S, int R0, int KA0, int KB0, int N0, int nk, double neg, double& c0, double& c1,
-                                          int g, int t) {
-  // two independent accumulator chains (even / odd k-blocks) hide the DMMA latency
-  double e0 = 0.0, e1 = 0.0;
-  int kk = 0;
-  for (; kk + 1 < nk; kk += 2) {
-    const int ka = KA0 + 8 * kk, kb = KB0 + 8 * kk;
-    const double a0 = neg * S[(ka + t) * LD + R0 + g];
-    const double a1 = neg * S[(ka + 4 + t) * LD + R0 + g];
-    const double b0 = S[(N0 + g) * LD + kb + t];
-    const double b1 = S[(N0 + g) * LD + kb + 4 + t];
-    const double a2 = neg * S[(ka + 8 + t) * LD + R0 + g];
-    const double a3 = neg * S[(ka + 12 + t) * LD + R0 + g];
-    const double b2 = S[(N0 + g) * LD + kb + 8 + t];
-    const double b3 = S[(N0 + g) * LD + kb + 12 + t];
-    dmma884p(c0, c1, a0, b0);
-    dmma884p(e0, e1, a2, b2);
-    dmma884p(c0, c1, a1, b1);
-    dmma884p(e0, e1, a3, b3);
-  }
-  if (kk < nk) {
-    const int ka = KA0 + 8 * kk, kb = KB0 + 8 * kk;
-    const double a0 = neg * S[(ka + t) * LD + R0 + g];
-    const double a1 = neg * S[(ka + 4 + t) * LD + R0 + g];
-    const double b0 = S[(N0 + g) * LD + kb + t];
-    const double b1 = S[(N0 + g) * LD + kb + 4 + t];
-    dmma884p(c0, c1, a0, b0);
-    dmma884p(c0, c1, a1, b1);
-  }
-  c0 += e0;
-  c1 += e1;
-}
-
-__global__ void __launch_bounds__(256, 1) potrf_tile_kernel(TiledSym L, double* __restrict__ Wbase, size_t w_batch_stride, int J,
-                                                            double* __restrict__ logdet, int* __restrict__ info) {
-  extern __shared__ __align__(16) double S[];  // S[c*LD + r]
-  double* dinv = S + TILE * LD;               // 1 / L[r][r]
-  double* red = dinv + TILE;                  // reduction scratch
-  __shared__ int fail_col;
-  __shared__ unsigned char tri_bi[120], tri_bj[120];  // packed lower-triangular block order (row by row)
-
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  double* tile = L.tile(b, J, J);
-  double* Wt = Wbase + (size_t)b * w_batch_stride + (size_t)J * TT;
-
-  PT(0);
-  if (tid == 0) fail_col = 0x7fffffff;
-  if (tid < 120) {
-    int bi = 0;
-    while ((bi + 1) * (bi + 2) / 2 <= tid) ++bi;
-    tri_bi[tid] = (unsigned char)bi;
-    tri_bj[tid] = (unsigned char)(tid - bi * (bi + 1) / 2);
-  }
-#pragma unroll 16
-  for (int e = tid; e < TT; e += 256) {
-    int r, c;
-    tile_rc(e, r, c);
-    S[c * LD + r] = tile[e];
-  }
-  __syncthreads();
-
-  PT(1);
-  // ---- phase C
-  for (int j0 = 0; j0 < TILE; j0 += 8) {
-    const int r = tid;  // row owner (threads 0..127)
-    double p[8];
-    double d[8][8];
-    const bool active = (tid < TILE) && (r >= j0);
-    if (active) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k <= i; ++k) d[i][k] = S[(j0 + k) * LD + (j0 + i)];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) p[k] = S[(j0 + k) * LD + r];
-    }
-    __syncthreads();
-    if (active) {
-      double dv[8];
-      // right-looking 8x8 factor in registers (short critical path: rsqrt + 2 FMAs per column)
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const double piv = d[jj][jj];
-        if (!(piv > 0.0)) {
-          if (r == j0) atomicMin(&fail_col, j0 + jj);
-        }
-        const double inv = fast_rsqrt(piv);
-        dv[jj] = inv;
-        d[jj][jj] = piv * inv;
-#pragma unroll
-        for (int i = jj + 1; i < 8; ++i) d[i][jj] *= inv;
-#pragma unroll
-        for (int j2 = jj + 1; j2 < 8; ++j2)
-#pragma unroll
-          for (int i = j2; i < 8; ++i) d[i][j2] = fma(-d[i][jj], d[j2][jj], d[i][j2]);
-      }
-      if (r >= j0 + 8) {
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          double v = p[jj];
-#pragma unroll
-          for (int k = 0; k < jj; ++k) v = fma(-p[k], d[jj][k], v);
-          p[jj] = v * dv[jj];
-        }
-      } else {
-        const int i = r - j0;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          double v = 0.0;
-#pragma unroll
-          for (int ii = 0; ii < 8; ++ii)
-            if (ii == i && jj <= ii) v = d[ii][jj];
-          p[jj] = v;
-        }
-        double di = 0.0;
-#pragma unroll
-        for (int ii = 0; ii < 8; ++ii)
-          if (ii == i) di = dv[ii];
-        dinv[r] = di;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) S[(j0 + k) * LD + r] = p[k];
-    }
-    __syncthreads();
-    if (j0 == 0) PT(2);
-    // trailing update of the lower 8x8 blocks of rows/cols [j0+8, 128) on the tensor pipe
-    const int nb = (TILE - j0 - 8) >> 3;
-    const int nblocks = nb * (nb + 1) / 2;
-    for (int base = warp; base < nblocks; base += 32) {  // 4 independent blocks per pass, branch-free
-      double c0[4], c1[4], a0[4], a1[4], b0[4], b1[4];
-      int R0[4], C0[4];
-      bool valid[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        valid[u] = base + 8 * u < nblocks;
-        const int idx = valid[u] ? base + 8 * u : nblocks - 1;  // out-of-range slots recompute a real block, never store
-        R0[u] = j0 + 8 + 8 * tri_bi[idx];
-        C0[u] = j0 + 8 + 8 * tri_bj[idx];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        c0[u] = S[(C0[u] + 2 * t) * LD + R0[u] + g];
-        c1[u] = S[(C0[u] + 2 * t + 1) * LD + R0[u] + g];
-        a0[u] = -S[(j0 + t) * LD + R0[u] + g];
-        a1[u] = -S[(j0 + 4 + t) * LD + R0[u] + g];
-        b0[u] = S[(j0 + t) * LD + C0[u] + g];
-        b1[u] = S[(j0 + 4 + t) * LD + C0[u] + g];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) dmma884p(c0[u], c1[u], a0[u], b0[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) dmma884p(c0[u], c1[u], a1[u], b1[u]);
-      __syncwarp();  // all lanes have read the C blocks of this pass before anyone overwrites them
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (valid[u]) {
-          S[(C0[u] + 2 * t) * LD + R0[u] + g] = c0[u];
-          S[(C0[u] + 2 * t + 1) * LD + R0[u] + g] = c1[u];
-        }
-    }
-    __syncthreads();
-    if (j0 == 0) PT(3);
-  }
-  PT(4);
-
-  // ---- logdet and failure report (fixed reduction order)
-  if (tid < TILE) {
-    double v = log(S[tid * LD + tid]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp] = v;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    logdet[b] += 2.0 * (((red[0] + red[1]) + red[2]) + red[3]);
-    if (fail_col != 0x7fffffff && info[b] == 0) info[b] = J * TILE + fail_col + 1;
-  }
-
-  PT(5);
-  // ---- write L (lower, zero upper)
-#pragma unroll 8
-  for (int e = tid; e < TT; e += 256) {
-    int r, c;
-    tile_rc(e, r, c);
-    tile[e] = (r >= c) ? S[c * LD + r] : 0.0;
-  }
-
-  PT(6);
-  // ---- phase W level 0: invert the 16 diagonal 8x8 blocks in place (thread = one column)
-  {
-    double Lb[8][8];
-    const int blk = tid >> 3, col = tid & 7, o = blk * 8;
-    if (tid < TILE) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int k = 0; k < i; ++k) Lb[i][k] = S[(o + k) * LD + o + i];
-    }
-    __syncthreads();
-    if (tid < TILE) {
-      double w[8];
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        double s = (rr == col) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < rr; ++k) s = fma(-Lb[rr][k], w[k], s);
-        w[rr] = s * dinv[o + rr];
-      }
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) S[(o + col) * LD + o + rr] = w[rr];
-    }
-    __syncthreads();
-  }
-  PT(7);
-  // ---- phase W doubling levels: W21 = -W22 * (L21 * W11)
-  for (int s = 8, lg = 0; s < TILE; s <<= 1, ++lg) {
-    const int sb = s >> 3;               // 8-blocks per side (= 1 << lg)
-    const int npairs = TILE / (2 * s);
-    const int nout = npairs * sb * sb;   // output 8x8 blocks per phase
-    // T(i,j) = sum_{k=j}^{sb-1} L21(i,k) W11(k,j)   -> stored in the mirrored upper block (1,2)
-    for (int ob = warp; ob < nout; ob += 8) {
-      const int q = ob >> (2 * lg), ij = ob & (sb * sb - 1), i = ij & (sb - 1), j = ij >> lg;
-      const int base = q * 2 * s;
-      double c0 = 0.0, c1 = 0.0;
-      // A = L21 block (rows base+s+8i, cols base+8k), B = W11 block (rows base+8k, cols base+8j)
-      block_mma(S, base + s + 8 * i, base + 8 * j, base + 8 * j, base + 8 * j, sb - j, 1.0, c0, c1, g, t);
-      const int TR = base + 8 * i, TC = base + s + 8 * j;
-      S[(TC + 2 * t) * LD + TR + g] = c0;
-      S[(TC + 2 * t + 1) * LD + TR + g] = c1;
-    }
-    __syncthreads();
-    // W21(i,j) = -sum_{k=0}^{i} W22(i,k) T(k,j)
-    for (int ob = warp; ob < nout; ob += 8) {
-      const int q = ob >> (2 * lg), ij = ob & (sb * sb - 1), i = ij & (sb - 1), j = ij >> lg;
-      const int base = q * 2 * s;
-      double c0 = 0.0, c1 = 0.0;
-      // A = W22 block (rows base+s+8i, cols base+s+8k), B = T block (rows base+8k, cols base+s+8j)
-      block_mma(S, base + s + 8 * i, base + s, base, base + s + 8 * j, i + 1, -1.0, c0, c1, g, t);
-      const int WR = base + s + 8 * i, WC = base + 8 * j;
-      S[(WC + 2 * t) * LD + WR + g] = c0;
-      S[(WC + 2 * t + 1) * LD + WR + g] = c1;
-    }
-    __syncthreads();
-  }
-  PT(8);
-#pragma unroll 8
-  for (int e = tid; e < TT; e += 256) {
-    int r, c;
-    tile_rc(e, r, c);
-    Wt[e] = (r >= c) ? S[c * LD + r] : 0.0;
-  }
-  PT(9);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// Second-generation diagonal-tile kernel (default).  Same results (L, W = inv(L), logdet, info), about half the cycles:
+// The diagonal-tile factorisation.  Compared with a right-looking tile kernel with the inverse after the factor (round 1's
+// first generation: 47 us) it needs about two thirds of the cycles:
 //   * LEFT-looking inside the tile.  The first kernel's right-looking trailing update re-reads and re-writes every 8x8
 //     block of the tile once per panel step (6 loads + 2 stores per pair of DMMAs: shared-memory-bandwidth bound, a third
 //     of its cycles); here the column block about to be factored is brought up to date in one go,
@@ -487,25 +226,22 @@ __device__ __forceinline__ void w_lower_left(double* S, const double* dinv, int 
   }
 }
 
-__global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double* __restrict__ Wbase, size_t w_batch_stride, int J,
-                                                             double* __restrict__ logdet, int* __restrict__ info) {
-  extern __shared__ __align__(16) double S[];  // S[c*LD + r]: L in the lower triangle, W^T strictly above the diagonal
-  double* dinv = S + TILE * LD;               // 1 / L[r][r] = W[r][r]
+// tile: diagonal tile (J,J) in HBM (factored in place); Wt: where W(J) goes; S: POTRF_SMEM bytes of dynamic shared memory;
+// fail_col_p: one shared int.  logdet_b / info_b: this latent's accumulators.  The caller has made the tile's latest
+// contents visible (stream order, griddepcontrol.wait or a ready counter) before calling.
+__device__ __forceinline__ void potrf_tile_body(double* __restrict__ tile, double* __restrict__ Wt, int J, double* __restrict__ logdet_b,
+                                                int* __restrict__ info_b, double* S, int* fail_col_p) {
+  double* dinv = S + TILE * LD;               // 1 / L[r][r] = W[r][r];  S[c*LD + r]: L in the lower triangle, W^T strictly above
   double* red = dinv + TILE;
-  __shared__ int fail_col;
-
-  const int b = blockIdx.x;
+  int& fail_col = *fail_col_p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  double* tile = L.tile(b, J, J);
-  double* Wt = Wbase + (size_t)b * w_batch_stride + (size_t)J * TT;
 
   PT(0);
   if (tid == 0) fail_col = 0x7fffffff;
-  pdl_wait();  // the tile was written by the previous kernel of the panel chain
 #pragma unroll 16
   for (int e2 = tid; e2 < TT / 2; e2 += 256) {
-    const double2 v = reinterpret_cast<const double2*>(tile)[e2];
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(tile) + e2);  // L2: in the fused chain kernel other SMs wrote it in this launch
     int r, c;
     tile_rc(2 * e2, r, c);
     S[c * LD + r] = v.x;
@@ -648,8 +384,8 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double*
   __syncthreads();
   PT(5);
   if (tid == 0) {
-    logdet[b] += 2.0 * (((red[0] + red[1]) + red[2]) + red[3]);
-    if (fail_col != 0x7fffffff && info[b] == 0) info[b] = J * TILE + fail_col + 1;
+    *logdet_b += 2.0 * (((red[0] + red[1]) + red[2]) + red[3]);
+    if (fail_col != 0x7fffffff && *info_b == 0) *info_b = J * TILE + fail_col + 1;
   }
   PT(6);
   pdl_trigger();  // the column's TRSM may be scheduled while L and W are stored
@@ -671,8 +407,14 @@ __global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double*
   PT(9);
 }
 
-static int g_potrf_impl = 1;  // 0: first-generation kernel (right-looking, W after L); 1: left-looking, W rows overlapped
-void set_potrf_impl(int v) { g_potrf_impl = v; }
+__global__ void __launch_bounds__(256, 1) potrf_tile_kernel2(TiledSym L, double* __restrict__ Wbase, size_t w_batch_stride, int J,
+                                                             double* __restrict__ logdet, int* __restrict__ info) {
+  extern __shared__ __align__(16) double S[];
+  __shared__ int fail_col;
+  const int b = blockIdx.x;
+  pdl_wait();  // the tile was written by the previous kernel of the panel chain
+  potrf_tile_body(L.tile(b, J, J), Wbase + (size_t)b * w_batch_stride + (size_t)J * TT, J, logdet + b, info + b, S, &fail_col);
+}
 
 cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int batch, double* logdet,
                               int* info) {
@@ -681,17 +423,177 @@ cudaError_t launch_potrf_tile(cudaStream_t st, TiledSym L, double* W, size_t w_b
   cudaGetDevice(&dev);
   bool& configured = configured_dev[dev & 63];
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(potrf_tile_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(potrf_tile_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (g_potrf_impl == 1)
-    return launch_pdl(pdl_enabled(), potrf_tile_kernel2, dim3(batch), dim3(256), POTRF_SMEM, st, L, W, w_batch_stride, J, logdet, info);
-  else
-    potrf_tile_kernel<<<batch, 256, POTRF_SMEM, st>>>(L, W, w_batch_stride, J, logdet, info);
-  return cudaGetLastError();
+  return launch_pdl(pdl_enabled(), potrf_tile_kernel2, dim3(batch), dim3(256), POTRF_SMEM, st, L, W, w_batch_stride, J, logdet, info);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The per-column panel chain of a small-batch factorisation in ONE launch.
+// For tile column J (already factored: L(J,J), W(J) final), per latent b:
+//     role T, CTA (I, s):     L(I,J)[slice s]    = C(I,J)[slice s] W(J)'                             I in (J, nt)
+//     role U, CTA (I, c, s):  C(I,c)[slice s]   -= sum_{k in [k0, J]} L(I,k)[slice s] L(c,k)'        c in (J, c_end), I in [c, nt)
+//     role P, one CTA:        factor C(J+1,J+1) -> L(J+1,J+1), W(J+1), logdet, info                  (do_potrf)
+// instead of three (or more) dependent launches.  [k0, J] is the k-tile range the columns (J, c_end) still have to receive
+// on the panel stream (k0 = first column of the current block; earlier columns were applied by the trailing updates);
+// c_end = J + 2 inside a block (just the next column), the end of the NEXT block at a block boundary.
+// Dependencies inside the launch run through counters in global memory (the 8 slice CTAs of a tile add 1 each): U(I, c, .)
+// needs the tiles (I,J) and (c,J) of role T -- but only for its LAST k-tile, the k < J part runs before it looks at a
+// counter --, P needs the 8 slices of U(J+1, J+1, .).  Block order = priority order = dependency order: the 8 slices of
+// T(J+1), the 8 slices of U(J+1,J+1), P -- the critical path gets the first 17 block indices and P then keeps one SM for
+// its ~30 us while everything else streams through the others --, then the T slices of the rows below, then the remaining U
+// slices; the latent index is the FASTEST grid dimension, so that order holds across the batch.  Consumers only wait for
+// CTAs with a lower linear block index, which are dispatched first; a bounded wait traps instead of hanging the GPU.
+// What leaves the critical path: the launch boundaries potrf -> TRSM -> update -> potrf, and every TRSM / update tile below
+// row J+1 (they now run beside the diagonal-tile factorisation instead of in front of it).
+// Counters: cnt[b][J * nt + I] for role T, cnt[b][nt * nt + J + 1] for the diagonal tile of role U; zeroed once per
+// factorisation (every column uses its own entries).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_cnt(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_count(const int* p, int target) {
+  if (threadIdx.x == 0) {
+    if (ld_acquire_cnt(p) < target) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      unsigned ns = 32;
+      while (ld_acquire_cnt(p) < target) {
+        __nanosleep(ns);
+        if (ns < 256) ns <<= 1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void signal_count(int* p) {
+  __syncthreads();  // every thread's stores of this slice are issued
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(p, 1);
+  }
+}
+
+struct ChainArgs {
+  TiledSym L;
+  double* W;
+  size_t w_batch_stride;
+  double* logdet;
+  int* info;
+  int* cnt;           // [batch][nt * nt + nt + 1]
+  int J, k0, c_end, do_potrf;
+};
+
+// grid (batch, 8 * (nT + nU) + (do_potrf ? 1 : 0)), 256 threads, POTRF_SMEM bytes of dynamic shared memory.
+__global__ void __launch_bounds__(256, 1) chain_column_kernel(ChainArgs a) {
+  extern __shared__ __align__(16) double S[];
+  __shared__ int fail_col;
+  const int nt = a.L.nt, J = a.J, b = blockIdx.x, warp = threadIdx.x >> 5;
+  const int nT = nt - 1 - J;  // tiles of role T (rows J+1 .. nt-1)
+  int* cnt = a.cnt + (size_t)b * ((size_t)nt * nt + nt + 1);
+  const int np = a.do_potrf ? 1 : 0;
+  const bool has_u = a.c_end > J + 1;
+  int bid = blockIdx.y, role, I, c = J + 1, slice;  // role 0 = T, 1 = U, 2 = P
+  if (bid < DIRECT_SPLIT) {
+    role = 0; I = J + 1; slice = bid;
+  } else if (has_u && bid < 2 * DIRECT_SPLIT) {
+    role = 1; I = J + 1; slice = bid - DIRECT_SPLIT;
+  } else if (bid < (has_u ? 2 : 1) * DIRECT_SPLIT + np) {
+    role = 2; I = J + 1; slice = 0;
+  } else {
+    bid -= (has_u ? 2 : 1) * DIRECT_SPLIT + np;
+    const int rest = (nT - 1) * DIRECT_SPLIT;
+    if (bid < rest) {
+      role = 0; I = J + 2 + bid / DIRECT_SPLIT; slice = bid % DIRECT_SPLIT;
+    } else {
+      role = 1;
+      bid -= rest;
+      int u = bid / DIRECT_SPLIT;
+      slice = bid % DIRECT_SPLIT;
+      int rows_c = nt - (J + 2);  // column J+1 without its diagonal tile
+      while (u >= rows_c) {
+        u -= rows_c;
+        ++c;
+        rows_c = nt - c;
+      }
+      I = (c == J + 1) ? J + 2 + u : c + u;
+    }
+  }
+  pdl_wait();  // column J (and the trailing updates ordered before this launch) are complete and visible
+  if (role == 0) {
+    // ---- role T: TRSM of one slice of tile (I, J)
+    double* Ctile = a.L.tile(b, I, J);
+    int nb0, nb1, lim0, nsteps;
+    direct_blocks<GEMM_TRSM>(warp, 1, nb0, nb1, lim0, nsteps);
+    double acc[DIRECT_RB][2][2] = {};
+    double2 cv[DIRECT_RB][2] = {};
+    direct_accumulate<GEMM_TRSM>(Ctile, a.W + (size_t)b * a.w_batch_stride + (size_t)J * TT, slice, nb0, nb1, lim0, nsteps, acc);
+    __syncthreads();  // every warp of this CTA has finished reading its rows of C(I,J)
+    direct_store_c<GEMM_TRSM>(Ctile, slice, nb0, nb1, cv, acc);
+    signal_count(cnt + (size_t)J * nt + I);
+    return;
+  }
+  if (role == 1) {
+    // ---- role U: update of one slice of tile (I, c) by the k-tiles [k0, J]
+    double* Ctile = a.L.tile(b, I, c);
+    int nb0 = warp * 2, nb1 = warp * 2 + 1, lim0, nsteps;
+    double acc[DIRECT_RB][2][2] = {};
+    double2 cv[DIRECT_RB][2];
+    direct_load_c(Ctile, slice, nb0, nb1, cv);
+    if (a.k0 < J) {  // the columns of this block before J: final before this launch
+      direct_blocks<GEMM_UPDATE>(warp, J - a.k0, nb0, nb1, lim0, nsteps);
+      direct_accumulate<GEMM_UPDATE>(a.L.tile(b, I, a.k0), a.L.tile(b, c, a.k0), slice, nb0, nb1, lim0, nsteps, acc);
+    }
+    // k = J: produced by role T of this launch -- all 8 slices of the B operand's tile (c, J) and of the A operand's tile (I, J)
+    wait_count(cnt + (size_t)J * nt + c, DIRECT_SPLIT);
+    if (I != c) wait_count(cnt + (size_t)J * nt + I, DIRECT_SPLIT);
+    direct_blocks<GEMM_UPDATE>(warp, 1, nb0, nb1, lim0, nsteps);
+    direct_accumulate<GEMM_UPDATE>(a.L.tile(b, I, J), a.L.tile(b, c, J), slice, nb0, nb1, lim0, nsteps, acc);
+    direct_store_c<GEMM_UPDATE>(Ctile, slice, nb0, nb1, cv, acc);
+    if (I == J + 1 && c == J + 1) signal_count(cnt + (size_t)nt * nt + J + 1);
+    return;
+  }
+  // ---- role P: the next diagonal tile
+  if (has_u) wait_count(cnt + (size_t)nt * nt + J + 1, DIRECT_SPLIT);
+  potrf_tile_body(a.L.tile(b, J + 1, J + 1), a.W + (size_t)b * a.w_batch_stride + (size_t)(J + 1) * TT, J + 1, a.logdet + b, a.info + b, S,
+                  &fail_col);
+}
+
+size_t chain_counter_ints(int nt) { return (size_t)nt * nt + nt + 1; }
+
+// One launch for tile column J: TRSM of the column, update of the columns (J, c_end) by the k-tiles [k0, J], and (do_potrf)
+// the factorisation of diagonal tile J+1.  c_end <= J + 1: no update (then do_potrf must be 0: the diagonal tile would not
+// be up to date).
+cudaError_t launch_chain_column(cudaStream_t st, TiledSym L, double* W, size_t w_batch_stride, int J, int k0, int c_end, int do_potrf,
+                                int batch, double* logdet, int* info, int* counters) {
+  static bool configured_dev[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(chain_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int nt = L.nt, nT = nt - 1 - J;
+  if (nT <= 0 || batch <= 0) return cudaSuccess;
+  if (c_end > nt) c_end = nt;
+  if (c_end <= J + 1) {
+    c_end = J + 1;
+    do_potrf = 0;
+  }
+  long long nU = 0;
+  for (int c = J + 1; c < c_end; ++c) nU += nt - c;
+  ChainArgs a{L, W, w_batch_stride, logdet, info, counters, J, k0, c_end, do_potrf};
+  dim3 grid((unsigned)batch, (unsigned)((nT + nU) * DIRECT_SPLIT + (do_potrf ? 1 : 0)));
+  return launch_pdl(pdl_enabled(), chain_column_kernel, grid, dim3(256), POTRF_SMEM, st, a);
 }
 
 }  // namespace lmm

@@ -72,46 +72,51 @@ def test_potrf_batched_matches_lapack(lmm, N, batch):
 
 
 def test_potrf_small_batch_schedules(lmm):
-    """Batch-1 schedules (plain, left-looking K-split look-ahead, right-looking look-ahead) at several block
-    widths all reproduce LAPACK's factor."""
-    rng = np.random.default_rng(5)
-    N = 2300
-    A = rng.standard_normal((N, N))
-    A = A @ A.T / N + np.eye(N)
-    Lr = sla.cholesky(A, lower=True)
+    """Batch-1 / batch-2 schedules -- plain, right-looking look-ahead on two streams, each with the panel chain as one fused
+    launch per tile column (chain_column_kernel: TRSM + next-column update + next diagonal tile handed over through ready
+    counters) or as three PDL-chained launches -- at several block widths all reproduce LAPACK's factor.  N = 2300 (18 tile
+    columns: block boundaries, a ragged last tile) and N = 4500 (36 columns: automatic block width 2)."""
     ctx = lmm.default_context()
     try:
-        for la, ob, split, pdl in ((0, 0, 0, 0), (1, 0, 0, 0), (1, 5, 0, 0), (2, 0, 0, 0), (2, 1, 0, 0), (2, 3, 0, 0), (2, 7, 0, 0), (2, 0, 1, 0),
-                                   (2, 1, 1, 0), (2, 3, 1, 0), (2, 18, 1, 0), (2, 0, 0, 1), (2, 1, 0, 1), (2, 3, 1, 1), (0, 0, 0, 1), (1, 2, 0, 1)):
-            ctx.set_option("lookahead", la)
-            ctx.set_option("outer_block", ob)
-            ctx.set_option("panel_split", split)
-            ctx.set_option("pdl", pdl)
-            L, logdet, info = lmm.potrf_batched(A)
-            assert info[0] == 0
-            np.testing.assert_allclose(L[0], Lr, rtol=1e-10, atol=1e-12, err_msg=f"lookahead={la} outer_block={ob} panel_split={split} pdl={pdl}")
-            assert rel(logdet[0], 2 * np.sum(np.log(np.diag(Lr)))) < 1e-11
+        for N, batch in ((2300, 1), (2300, 2), (4500, 1)):
+            rng = np.random.default_rng(N)
+            A = rng.standard_normal((batch, N, N))
+            A = A @ np.transpose(A, (0, 2, 1)) / N + np.eye(N)[None]
+            Lr = [sla.cholesky(A[b], lower=True) for b in range(batch)]
+            configs = ((0, 0, 0, 0), (0, 0, 1, 1), (1, 0, 0, 0), (1, 1, 0, 1), (1, 3, 0, 1), (1, 0, 1, 0), (1, 0, 1, 1), (1, 1, 1, 1), (1, 2, 1, 1),
+                       (1, 3, 1, 1), (1, 5, 1, 0), (1, 7, 1, 1), (1, 18, 1, 1))
+            for la, ob, fused, pdl in (configs if N == 2300 else ((1, 0, 1, 1), (1, 4, 1, 1), (1, 0, 0, 1))):
+                ctx.set_option("lookahead", la)
+                ctx.set_option("outer_block", ob)
+                ctx.set_option("chain_fused", fused)
+                ctx.set_option("pdl", pdl)
+                L, logdet, info = lmm.potrf_batched(A)
+                for b in range(batch):
+                    assert info[b] == 0
+                    np.testing.assert_allclose(L[b], Lr[b], rtol=1e-10, atol=1e-12, err_msg=f"N={N} batch={batch} lookahead={la} outer_block={ob} chain_fused={fused} pdl={pdl}")
+                    assert rel(logdet[b], 2 * np.sum(np.log(np.diag(Lr[b])))) < 1e-11
     finally:
-        ctx.set_option("lookahead", 2)
+        ctx.set_option("lookahead", 1)
         ctx.set_option("outer_block", 0)
-        ctx.set_option("panel_split", 0)
+        ctx.set_option("chain_fused", 1)
         ctx.set_option("pdl", 1)
 
 
-@pytest.mark.parametrize("potrf_impl", [0, 1])
-def test_potrf_reports_non_pd(lmm, potrf_impl):
-    """LAPACK `info` semantics (1-based index of the first non-positive pivot), every diagonal-tile kernel; the pivot sits
-    in the second tile and in the middle of an 8-column panel step."""
+@pytest.mark.parametrize("fused", [0, 1])
+def test_potrf_reports_non_pd(lmm, fused):
+    """LAPACK `info` semantics (1-based index of the first non-positive pivot), through the standalone diagonal-tile kernel and
+    through the fused chain kernel's factorisation role; the pivot sits in the second tile and in the middle of an 8-column
+    panel step."""
     A = np.eye(200)
     A[150, 150] = -1.0
     B = np.eye(200)
     B[5, 5] = 0.0
     ctx = lmm.default_context()
-    ctx.set_option("potrf_impl", potrf_impl)
+    ctx.set_option("chain_fused", fused)
     try:
         L, logdet, info = lmm.potrf_batched(np.stack([np.eye(200), A, B]))
     finally:
-        ctx.set_option("potrf_impl", 1)
+        ctx.set_option("chain_fused", 1)
     assert info[0] == 0 and info[1] == 151 and info[2] == 6
 
 
@@ -171,21 +176,22 @@ def test_oilmm_mid_size_multi_tile(lmm):
     np.testing.assert_allclose(V, Vr, rtol=RTOL)
 
 
-@pytest.mark.parametrize("impl,streams,outer,small", [(0, 1, 8, 74), (1, 1, 3, 74), (0, 4, 16, 0), (1, 8, 1, 0), (2, 2, 8, 0), (2, 1, 5, 74),
-                                                      (2, 4, 8, 4096)])
-def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer, small):
-    """Both GEMM pipelines (cp.async ring / TMA bulk + mbarrier ring), the latency-optimised direct kernel for small grids
-    (off / default threshold / everywhere), any stream-group count and any outer block width give the same factor
-    (N = 1100: 9 tile columns, batch 3)."""
+@pytest.mark.parametrize("streams,outer,small,fused", [(1, 8, 74, 1), (1, 3, 74, 0), (4, 16, 0, 1), (8, 1, 0, 0), (2, 8, 0, 1), (1, 5, 74, 1),
+                                                       (4, 8, 4096, 1), (4, 8, 4096, 0), (1, 2, 4096, 1)])
+def test_streams_blocking_and_small_grid_kernels_agree(lmm, streams, outer, small, fused):
+    """The TMA-pipelined GEMM, the latency-optimised direct kernel for small grids (off / default threshold / everywhere), the
+    fused per-column chain kernel, any stream-group count and any outer block width give the same factor: batched OILMM
+    (N = 1100: 9 tile columns, batch 3 -- small enough for the fused chain) and a single general-ILMM factor (batch 1,
+    right-looking schedule)."""
     N, p, m, Ns = 1100, 5, 3, 70
     x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=77, means=True)
     om = o.OILMMModel(fs, U, S)
     f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
     ctx = lmm.default_context()
-    ctx.set_option("gemm_impl", impl)
     ctx.set_option("streams", streams)
     ctx.set_option("outer_block", outer)
     ctx.set_option("gemm_small", small)
+    ctx.set_option("chain_fused", fused)
     try:
         fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
         post, lp = lmm.posterior(fx, y, with_logpdf=True)
@@ -194,51 +200,21 @@ def test_gemm_impls_streams_and_blocking_agree(lmm, impl, streams, outer, small)
         Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
         assert_isapprox(M, Mr, RTOL)
         np.testing.assert_allclose(V, Vr, rtol=RTOL)
+        assert_isapprox(post.f.fs[m - 1].C, o.oilmm_posterior(om, x, 0.1, y).fs[m - 1].L, RTOL, "factor")
+        # general ILMM: one (mN x mN) factor, batch 1
+        rng = np.random.default_rng(5)
+        N2, p2, m2 = 600, 4, 3
+        x2 = np.sort(rng.uniform(0, 6, N2))
+        H = rng.uniform(0, 1, (p2, m2))
+        fs2 = [o.GP(o.Kernel(k, 1.0, s)) for k, s in zip([o.SE, o.MATERN32, o.MATERN52], [0.9, 1.2, 1.5])]
+        y2 = rng.standard_normal(p2 * N2)
+        f2 = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs2]), H)
+        assert rel(lmm.logpdf(f2(lmm.MOInputIsotopicByOutputs(x2, p2), 0.1), y2), o.ilmm_logpdf(fs2, H, x2, 0.1, y2)) < RTOL
     finally:
-        ctx.set_option("gemm_impl", 2)
         ctx.set_option("streams", 4)
         ctx.set_option("outer_block", 0)
         ctx.set_option("gemm_small", 74)
-
-
-@pytest.mark.parametrize("potrf_impl,direct,small,lookahead", [(0, 0, 74, 2), (1, 1, 4096, 2), (1, 2, 4096, 2), (0, 2, 4096, 0), (1, 0, 0, 1),
-                                                                (1, 1, 4096, 1), (1, 2, 74, 2), (1, 0, 4096, 0)])
-def test_panel_kernel_variants_agree(lmm, potrf_impl, direct, small, lookahead):
-    """Both diagonal-tile kernels (inverse after the factor / inverse block rows overlapped with the panel steps) and the three
-    direct-GEMM variants (plain / register-ring prefetch with 4 or 8 slices per tile, zero blocks of W skipped) give the
-    same factor: batched OILMM (N = 1100, batch 3) and a single general-ILMM factor (batch 1, right-looking schedule)."""
-    N, p, m, Ns = 1100, 5, 3, 70
-    x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=78, means=True)
-    om = o.OILMMModel(fs, U, S)
-    f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
-    ctx = lmm.default_context()
-    ctx.set_option("potrf_impl", potrf_impl)
-    ctx.set_option("gemm_direct", direct)
-    ctx.set_option("gemm_small", small)
-    ctx.set_option("lookahead", lookahead)
-    try:
-        fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
-        post, lp = lmm.posterior(fx, y, with_logpdf=True)
-        assert rel(lp, o.oilmm_logpdf(om, x, 0.1, y)) < RTOL
-        M, V = lmm.mean_and_var(post(lmm.MOInputIsotopicByOutputs(xs, p), 0.1))
-        Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.1, y), xs, 0.1)
-        assert_isapprox(M, Mr, RTOL)
-        np.testing.assert_allclose(V, Vr, rtol=RTOL)
-        # general ILMM: one (mN x mN) factor, batch 1
-        rng = np.random.default_rng(5)
-        N2, p2, m2 = 500, 4, 3
-        x2 = np.sort(rng.uniform(0, 6, N2))
-        H = rng.uniform(0, 1, (p2, m2))
-        fs2 = [o.GP(o.Kernel(o.SE, 1.0, 1.3)), o.GP(o.Kernel(o.MATERN32)), o.GP(o.Kernel(o.MATERN52, 0.7, 0.8))]
-        y2 = rng.standard_normal(N2 * p2)
-        f2 = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs2]), H)
-        lp2 = lmm.logpdf(f2(lmm.MOInputIsotopicByOutputs(x2, p2), 0.05), y2)
-        assert rel(lp2, o.ilmm_logpdf(fs2, H, x2, 0.05, y2)) < RTOL
-    finally:
-        ctx.set_option("potrf_impl", 1)
-        ctx.set_option("gemm_direct", 2)
-        ctx.set_option("gemm_small", 74)
-        ctx.set_option("lookahead", 2)
+        ctx.set_option("chain_fused", 1)
 
 
 def test_distance_form_option(lmm):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Batch-1 / batch-2 Cholesky schedules (ILMM-shaped work): plain, left-looking K-split look-ahead (1), right-looking
-look-ahead (2), over outer_block widths and the small-grid threshold of the latency-optimised GEMM kernel.
+"""Batch-1 / batch-2 Cholesky schedules (ILMM-shaped work): plain (0), right-looking look-ahead on two streams (1), over
+outer_block widths and the small-grid threshold of the latency-optimised GEMM kernel.
 Prints JSON lines; tuning aid.   usage: bench_batch1.py [NxB,NxB,...] [lookaheads] [outer_blocks] [gemm_small values]"""
 import json
 import os
@@ -14,7 +14,7 @@ if __name__ == "__main__":
     ctx = lmm.default_context()
     arg = lambda i, d: sys.argv[i] if len(sys.argv) > i else d
     cfgs = arg(1, "4096x1,8192x1,16384x1,8192x2")
-    las = [int(v) for v in arg(2, "2").split(",")]
+    las = [int(v) for v in arg(2, "1").split(",")]
     obs = [int(v) for v in arg(3, "0,1,2,3,4").split(",")]
     smalls = [int(v) for v in arg(4, "74").split(",")]
     for cfg in cfgs.split(","):

@@ -33,18 +33,15 @@ if __name__ == "__main__":
     ap.add_argument("--configs", default="8192x8,16384x8,4096x16,2048x32")
     ap.add_argument("--streams", default="1,2,4,8")
     ap.add_argument("--outer", default="8")
-    ap.add_argument("--impl", default="1")
     args = ap.parse_args()
     ctx = lmm.default_context()
-    impls = [int(v) for v in args.impl.split(",")]
     for cfg in args.configs.split(","):
         N, batch = [int(v) for v in cfg.split("x")]
         for ob in [int(v) for v in args.outer.split(",")]:
             ctx.set_option("outer_block", ob)
-            for st, impl in [(int(v), i) for v in args.streams.split(",") for i in impls]:
+            for st in [int(v) for v in args.streams.split(",")]:
                 ctx.set_option("streams", st)
-                ctx.set_option("gemm_impl", impl)
                 ms, ms_k, ld = run(ctx, N, batch)
                 tf = batch * N ** 3 / 3.0 / (ms * 1e-3) / 1e12
-                print(json.dumps({"N": N, "batch": batch, "outer_block": ob, "streams": st, "gemm_impl": impl, "chol_ms": round(ms, 3), "kmat_ms": round(ms_k, 3),
+                print(json.dumps({"N": N, "batch": batch, "outer_block": ob, "streams": st, "chol_ms": round(ms, 3), "kmat_ms": round(ms_k, 3),
                                   "tflops": round(tf, 2), "logdet0": ld}), flush=True)
