@@ -226,6 +226,57 @@ def run_reference(args, cfg):
     }))
 
 
+def multi_gpu_extras(lmm, ctx, dist, torch, world, rank):
+    """Driver-visible records of the two other multi-GPU paths of the north star, run by every rank AFTER the timed region
+    (they are collective) and attached to rank 0's JSON line; neither touches `value`.
+    (1) `ilmm_rowcyclic`: ONE large factor (general-ILMM-shaped work, N = 16384) factored by every rank on identical
+        inputs, replicated vs row-cyclic partitioned over the ranks (option "partition_ilmm": trailing updates split by tile
+        row, one ncclAllGather of the current block column per step); time = max over ranks, parity = logdet.
+    (2) `c5_sweep`: BASELINE config 5 -- OILMM p = 256, m = 128, N = 8192, 32 lengthscale settings in one
+        lmm_oilmm_logpdf_sweep call, the (sweep x latent) grid of 4096 factorizations block-sharded over the ranks."""
+    from tools.chol_bench import run
+
+    def maxed(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {}
+    rec = {"N": 16384, "ranks": world}
+    for part, key in ((0, "replicated"), (1, "rowcyclic")):
+        ctx.set_option("partition_ilmm", part)
+        dist.barrier()
+        ms, _, ld = run(ctx, 16384, 1, reps=2)
+        rec[key + "_ms"] = maxed(ms)
+        rec[key + "_logdet"] = ld
+    ctx.set_option("partition_ilmm", 0)
+    rec["speedup"] = rec["replicated_ms"] / rec["rowcyclic_ms"]
+    rec["logdet_rel_diff"] = abs(rec["rowcyclic_logdet"] - rec["replicated_logdet"]) / abs(rec["replicated_logdet"])
+    rec["tflops_rowcyclic"] = 16384 ** 3 / 3.0 / (rec["rowcyclic_ms"] * 1e-3) / 1e12
+    out["ilmm_rowcyclic"] = rec
+    p, m, N, nsweep = 256, 128, 8192, 32
+    rng = np.random.default_rng(0)
+    x = np.sort(rng.uniform(0, N / 100.0, N))
+    U, S, _ = np.linalg.svd(np.random.default_rng(1).uniform(0, 1, (p, m)), full_matrices=False)
+    f = lmm.ILMM(lmm.independent_mogp([lmm.GP(lmm.SEKernel()) for _ in range(m)]), lmm.Orthogonal(U, S))
+    y = rng.standard_normal(p * N)
+    fx = f(lmm.MOInputIsotopicByOutputs(x, p), 0.1)
+    scales = np.geomspace(0.25, 4.0, nsweep)
+    lmm.logpdf_sweep(fx, y, scales)  # warm-up
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    vals = lmm.logpdf_sweep(fx, y, scales)
+    torch.cuda.synchronize()
+    sec = maxed(time.perf_counter() - t0)
+    flops = m * nsweep * N ** 3 / 3.0
+    out["c5_sweep"] = {"config": f"BASELINE config 5: OILMM p={p} m={m} N={N} x {nsweep} lengthscales in one call", "n_gpus": world,
+                       "seconds_per_call": sec, "factorizations": m * nsweep, "tflops_total": flops / sec / 1e12,
+                       "tflops_per_gpu": flops / sec / 1e12 / world, "logpdf_at_scale_1": float(vals[int(np.argmin(np.abs(scales - 1.0)))]),
+                       "argmax_scale": float(scales[int(np.argmax(vals))])}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -236,6 +287,7 @@ def main():
     ap.add_argument("--m", type=int, default=64)
     ap.add_argument("--N", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the untimed multi-GPU records (row-cyclic ILMM factor, config-5 sweep)")
     ap.add_argument("--streams", type=int, default=0, help="latent groups on separate CUDA streams (0 = library default)")
     args = ap.parse_args()
     p, m, N = args.p, args.m, args.N
@@ -337,6 +389,8 @@ def main():
     pred_ms = float(ctx.last_timings()[5])
     post_s.f.fs[0]._owner.free()
     barrier()
+    extras = multi_gpu_extras(lmm, ctx, dist, torch, world, rank) if (world > 1 and not args.no_extras) else None
+    barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -372,6 +426,8 @@ def main():
         "prediction_check_ms": pred_ms,
         "logpdf": lp,
     }
+    if extras:
+        out.update(extras)
     if world > 1:
         dist.destroy_process_group()
         # the same eval + prediction on ONE GPU (a second, communicator-less context on rank 0's device), untimed

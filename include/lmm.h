@@ -109,7 +109,9 @@ const char* lmm_version(void);
  *   "chain_fused"     1 = where the grids are small (batches <= 2, or few latents x few tile rows) the panel chain of a tile
  *                     column -- TRSM of the column, update of the next column(s), factorisation of the next diagonal tile --
  *                     is ONE launch whose CTAs hand tiles to each other through ready counters in global memory, the
- *                     critical tiles first [default]; 0 = one launch per operation, chained by "pdl"
+ *                     critical tiles first [default: single factors up to N = 4096 and small batched grids, where the chain
+ *                     is the run time]; 2 = also for larger single factors (measured slower from N = 8192 on: the trailing
+ *                     GEMMs set the time there); 0 = one launch per operation, chained by "pdl"
  *   "pdl"             programmatic dependent launch along the panel chain: the diagonal-tile kernel, the small direct GEMMs
  *                     and the fused chain kernel are launched with programmatic stream serialisation, wait on
  *                     `griddepcontrol.wait` before their first read and release their successor before their final
@@ -321,11 +323,21 @@ int lmm_ilmm_logpdf_grad(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const 
 /* Heterotopic / missing-data ILMM (unsupported in the reference, examples/oilmm_and_ilmm.ipynb:112).
  * Entries of y (host memory) that are NaN are unobserved; exact inference on the observed entries of the dense model
  * y ~ N((H ⊗ I) m, Σ_l (h_l h_l') ⊗ K_l + σ² I) -- the model the reference's tests use as the ILMM's ground truth
- * (test/ilmm.jl:5).  Pass U*sqrt(S) as H for an OILMM.  The returned handle answers lmm_post_mean_and_var (all p outputs
- * at x*), lmm_post_info and lmm_post_free.  out_post / out_logpdf nullable (not both); n_observed nullable. */
+ * (test/ilmm.jl:5).  Pass U*sqrt(S) as H for an OILMM.  The returned handle answers lmm_post_mean_and_var,
+ * lmm_post_mean_and_cov (all p outputs at x*), lmm_post_rand (AbstractGPs' generic FiniteGP rand on the dense model:
+ * mean + chol(C + σ²I) z with ONE vector z_latent of p*Ns standard normals, z_noise ignored), lmm_post_save / lmm_post_load,
+ * lmm_post_info and lmm_post_free.  out_post / out_logpdf nullable (not both); n_observed nullable. */
 int lmm_ilmm_masked_posterior(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
                               const double* H, int p, double sigma2, const double* y, int out_dim,
                               lmm_post** out_post, double* out_logpdf, int* n_observed, int* info);
+/* Heterotopic OILMM whose mask is PER INPUT: at every input either all p outputs are observed or all are NaN (whole time
+ * steps missing).  Conditioning on the observed entries is then the ordinary OILMM (src/oilmm.jl:79-93, 116-134) on the
+ * observed inputs -- the projection stays exact and the latents independent, O(m N_obs³) instead of the dense model's
+ * O((p N)³) -- and the handle is a full OILMM posterior (every lmm_post_* call).  A mask that is not per-input returns
+ * LMM_E_UNSUPPORTED: use lmm_ilmm_masked_posterior.  out_post / out_logpdf nullable (not both). */
+int lmm_oilmm_masked_posterior(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D,
+                               const double* U, const double* S, int p, double sigma2, const double* y, int out_dim,
+                               lmm_post** out_post, double* out_logpdf, int* n_observed_inputs, int* info_latent);
 
 /* ---- batched blocked Cholesky primitive: the `cholesky(Symmetric(C))` / dpotrf call site ---- */
 /* A: batch matrices, each N x N column-major (lower triangle read).  L_out (nullable): same

@@ -979,6 +979,13 @@ def _rand_one(rng, fx: FiniteGP) -> np.ndarray:
         rc = lib.lmm_mvn_logpdf_rand(ctx.handle, ptr(M), ptr(Cf), p * N, None, None, ptr(z), ptr(out), C.byref(il))
         ctx.check(rc)
         return out
+    if isinstance(f, _MissingDataPosterior):
+        if f.prior.H.shape[0] != p:
+            raise RuntimeError("out dim of x != out dim of f.")
+        z = rng.standard_normal(p * N)
+        rc = lib.lmm_post_rand(owner.handle, ptr(pts), N, fx.sigma2, ptr(z), None, ptr(out), C.byref(il))
+        ctx.check(rc, il.value)
+        return out
     if isinstance(f, _JointPosterior):
         z = rng.standard_normal(p * N)
         rc = lib.lmm_post_rand(owner.handle, ptr(pts), N, fx.sigma2, ptr(z), None, ptr(out), C.byref(il))
@@ -1141,6 +1148,8 @@ def load_posterior(path: str, prior, ctx: Optional[Context] = None):
     if len(priors) != m.value:
         ctx.lib.lmm_post_free(h)
         raise ValueError("the prior model does not match the saved posterior")
+    if kind.value == 4:  # missing-data posterior of the dense model
+        return _MissingDataPosterior(_PostHandle(ctx, h, N.value), prior, 0)
     if kind.value in (2, 3):  # joint factor: general ILMM / IndependentMOGP under a dense Σy
         joint = _JointPosterior(_PostHandle(ctx, h, N.value, joint_n=m.value * N.value), IndependentMOGP(priors))
         return ILMM(joint, prior.H) if kind.value == 2 else joint
@@ -1150,17 +1159,25 @@ def load_posterior(path: str, prior, ctx: Optional[Context] = None):
 
 
 class _MissingDataPosterior(AbstractGP):
-    """Posterior of an ILMM / OILMM conditioned on a partially observed y (NaN = missing): `mean_and_var` / `mean` / `var` /
-    `marginals` at new inputs for all outputs."""
+    """Posterior of an ILMM / OILMM conditioned on a partially observed y (NaN = missing) through the dense multi-output model:
+    `mean_and_var` / `mean` / `var` / `marginals` / `mean_and_cov` / `cov` / `rand` at new inputs for all outputs, save / load."""
 
     def __init__(self, owner: _PostHandle, prior: ILMM, n_observed: int):
         self._owner, self.prior, self.n_observed = owner, prior, n_observed
 
 
+def _nan_mask_is_per_input(y: np.ndarray, p: int, N: int) -> bool:
+    nan = np.isnan(y.reshape(p, N))
+    cnt = nan.sum(axis=0)
+    return bool(np.all((cnt == 0) | (cnt == p)))
+
+
 def posterior_missing(fx: FiniteGP, y, with_logpdf: bool = False):
     """Heterotopic / missing-data conditioning (the reference leaves it unsupported): entries of `y` that are NaN
-    are unobserved.  Exact inference on the observed entries of the dense multi-output model; works for `ILMM(fs, H)` with a
-    dense H or an `Orthogonal` H.  Returns a posterior whose FiniteGPs answer `mean_and_var` / `mean` / `var` / `marginals`."""
+    are unobserved.  An OILMM whose mask is per input (whole time steps missing) stays an OILMM on the observed inputs --
+    per-latent O(m N_obs³), and the result is an ordinary OILMM posterior with every method; any other mask is conditioned
+    exactly on the observed entries of the dense multi-output model (`ILMM(fs, H)` with a dense or an `Orthogonal` H) and
+    returns a posterior whose FiniteGPs answer `mean_and_var` / `mean` / `var` / `marginals` / `mean_and_cov` / `cov` / `rand`."""
     lat, H, s2, _ = unpack(fx)
     if not isinstance(lat, IndependentMOGP) or any(isinstance(g, PosteriorGP) for g in lat.fs):
         raise TypeError("posterior_missing needs an ILMM / OILMM over prior latents")
@@ -1173,6 +1190,13 @@ def posterior_missing(fx: FiniteGP, y, with_logpdf: bool = False):
     if yv.shape[0] != N * p:
         raise ValueError("length of y does not match the inputs")
     h, out, nobs, info = C.c_void_p(), C.c_double(), C.c_int(0), C.c_int(0)
+    if isinstance(H, Orthogonal) and _nan_mask_is_per_input(yv, p, N):
+        rc = ctx.lib.lmm_oilmm_masked_posterior(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H.U), ptr(H.S), p, s2, ptr(yv), fx.x.out_dim,
+                                                C.byref(h), C.byref(out), C.byref(nobs), C.byref(info))
+        ctx.check(rc, info.value)
+        owner = _PostHandle(ctx, h, nobs.value)
+        post = ILMM(IndependentMOGP([PosteriorGP(owner, i, g) for i, g in enumerate(lat.fs)]), H)
+        return (post, out.value) if with_logpdf else post
     rc = ctx.lib.lmm_ilmm_masked_posterior(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(Hm), p, s2, ptr(yv), fx.x.out_dim, C.byref(h),
                                            C.byref(out), C.byref(nobs), C.byref(info))
     ctx.check(rc)
@@ -1181,7 +1205,8 @@ def posterior_missing(fx: FiniteGP, y, with_logpdf: bool = False):
 
 
 def logpdf_missing(fx: FiniteGP, y) -> float:
-    """logpdf of the observed (non-NaN) entries of `y` under the ILMM / OILMM `fx` (dense model)."""
+    """logpdf of the observed (non-NaN) entries of `y` under the ILMM / OILMM `fx` (per-input masks of an OILMM: the OILMM
+    logpdf on the observed inputs; otherwise the dense model)."""
     lat, H, s2, _ = unpack(fx)
     ctx = default_context()
     pts = _points(fx.x.x)
@@ -1190,6 +1215,11 @@ def logpdf_missing(fx: FiniteGP, y) -> float:
     p, m = Hm.shape
     yv = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
     out, info = C.c_double(), C.c_int(0)
+    if isinstance(H, Orthogonal) and _nan_mask_is_per_input(yv, p, N):
+        rc = ctx.lib.lmm_oilmm_masked_posterior(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(H.U), ptr(H.S), p, s2, ptr(yv), fx.x.out_dim,
+                                                None, C.byref(out), None, C.byref(info))
+        ctx.check(rc, info.value)
+        return out.value
     rc = ctx.lib.lmm_ilmm_masked_posterior(ctx.handle, _descs(lat.fs), m, ptr(pts), N, D, ptr(Hm), p, s2, ptr(yv), fx.x.out_dim, None,
                                            C.byref(out), None, C.byref(info))
     ctx.check(rc)

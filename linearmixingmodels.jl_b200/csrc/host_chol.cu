@@ -118,8 +118,12 @@ cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t
   const int nt = L.nt;
   // the panel chain is the critical path: narrow blocks for small matrices, wider ones (fewer read-modify-write
   // passes over the trailing matrix) once the trailing GEMMs dominate (measured: tools/bench_batch1.py)
-  const bool fused = ctx->chain_fused != 0;
-  const int ob = ctx->outer_block_user ? ctx->outer_block : fused ? (nt <= 72 ? 2 : nt <= 112 ? 3 : 4) : (nt <= 32 ? 1 : nt <= 72 ? 2 : nt <= 112 ? 3 : 4);
+  // Fused chain launches pay off while the chain IS the run time (measured, profiles/r02_panel_chain.md: N = 1024 -13 %,
+  // 2048 -4 %, 4096 -2 %); from N = 8192 on the trailing GEMMs of the other stream set the time and the sliced, one-CTA-per-SM
+  // roles of the fused kernel only take SMs away from them (+10 %), so larger matrices keep one launch per operation
+  // ("chain_fused" = 2 forces the fused kernel everywhere).
+  const bool fused = ctx->chain_fused == 2 || (ctx->chain_fused == 1 && nt <= 32);
+  const int ob = ctx->outer_block_user ? ctx->outer_block : fused ? (nt <= 32 ? 3 : nt <= 112 ? 3 : 4) : (nt <= 32 ? 1 : nt <= 72 ? 2 : nt <= 112 ? 3 : 4);
   const int nblk = (nt + ob - 1) / ob;
   cudaError_t e;
   while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {

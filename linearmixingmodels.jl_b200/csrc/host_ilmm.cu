@@ -501,7 +501,7 @@ extern "C" int lmm_post_mean_and_cov(lmm_post* post, const double* xs, int Ns, d
   CU(b_cov.alloc(ctx, (size_t)dim * dim * sizeof(double)));
   CU(b_mean.alloc(ctx, 2 * (size_t)dim * sizeof(double)));
   CU(cudaMemsetAsync(b_mean.p, 0, 2 * (size_t)dim * sizeof(double), st));
-  if (post->kind == POST_MASKED) return ctx->fail(LMM_E_UNSUPPORTED, "a missing-data posterior offers mean_and_var only");
+  if (post->kind == POST_MASKED) return masked_post_mean_and_cov(post, xs, Ns, sigma2, mean, cov);
   if (post->joint()) {
     // joint latent posterior: C_lat = blockdiag(K**) + 1e-18 I - V V',  V = Kc L^{-T}
     const int N = post->N, D = post->D, bnt = post->big_nt, ntr = ntiles(m * Ns);
@@ -1035,3 +1035,157 @@ int masked_post_mean_and_var(lmm_post* post, const double* xs, int Ns, double si
   return LMM_OK;
 }
 }  // namespace lmm_host
+
+namespace lmm_host {
+// Predictive pieces of the missing-data (dense-model) posterior at x*: mean (p Ns, by outputs) and the tiled
+// covariance  C = Σ_l (h_l h_l') ⊗ K_l(x*, x*) + e0 I - V V',  V = K_{*,obs} L^{-T}  (dimension p Ns).
+struct MaskedPredictive {
+  DevBuf xs, V, mean, C;
+  int ntr = 0, rows = 0;
+};
+int masked_predictive(lmm_post* post, const double* xs, int Ns, double e0, MaskedPredictive& P) {
+  lmm_ctx* ctx = post->ctx;
+  cudaStream_t st = ctx->stream;
+  const int m = post->m, p = post->p, N = post->N, D = post->D, bnt = post->big_nt, nobs = post->big_n;
+  if ((int64_t)p * Ns > 46000) return ctx->fail(LMM_E_UNSUPPORTED, "dense covariance output too large");
+  P.rows = p * Ns;
+  P.ntr = ntiles(P.rows);
+  DevBuf b_zero, b_e0, b_pm;
+  CU(P.xs.alloc(ctx, (size_t)Ns * D * sizeof(double)));
+  CU(copy_in(ctx, P.xs.as<double>(), xs, (size_t)Ns * D));
+  CU(P.V.alloc(ctx, (size_t)P.ntr * bnt * TT * sizeof(double)));
+  TiledRect V{P.V.as<double>(), P.ntr, bnt, (size_t)P.ntr * bnt * TT};
+  CU(launch_assemble_masked_cross(st, V, P.xs.as<double>(), Ns, post->d_obs, nobs, post->d_xpad, N, D, post->d_params, m, p, post->d_H,
+                                  ctx->distance_form));
+  CU(b_zero.alloc(ctx, sizeof(LatentParams)));
+  CU(cudaMemsetAsync(b_zero.p, 0, sizeof(LatentParams), st));
+  CU(P.mean.alloc(ctx, (size_t)P.ntr * TILE * sizeof(double)));
+  CU(launch_rect_gemv(st, V, post->d_alpha, (size_t)bnt * TILE, P.mean.as<double>(), (size_t)P.ntr * TILE, b_zero.as<LatentParams>(), 0, 1));
+  CU(trsm_right_lt(ctx, V, post->Lsym(), post->d_W, post->wstride(), 1));
+  // prior means of the outputs (constants along n) added on the device
+  std::vector<double> pm((size_t)P.rows, 0.0);
+  for (int j = 0; j < p; ++j) {
+    double v = 0.0;
+    for (int l = 0; l < m; ++l) v += post->H[(size_t)l * p + j] * post->descs[l].mean_const;
+    for (int n = 0; n < Ns; ++n) pm[(size_t)j * Ns + n] = v;
+  }
+  CU(b_pm.alloc(ctx, (size_t)P.rows * sizeof(double)));
+  CU(copy_in(ctx, b_pm.as<double>(), pm.data(), (size_t)P.rows));
+  CU(launch_axpy(st, P.mean.as<double>(), b_pm.as<double>(), (size_t)P.rows, 1.0));
+  CU(b_e0.alloc(ctx, sizeof(double)));
+  CU(copy_in(ctx, b_e0.as<double>(), &e0, 1));
+  CU(P.C.alloc(ctx, sym_tiles(P.ntr) * TT * sizeof(double)));
+  TiledSym C{P.C.as<double>(), P.ntr, sym_tiles(P.ntr) * TT};
+  CU(launch_assemble_ilmm(st, C, P.xs.as<double>(), Ns, D, post->d_params, m, p, b_e0.as<double>(), post->d_H, 1, ctx->distance_form));
+  GemmArgs g{};
+  g.A = operand(V); g.B = operand(V); g.C = operand(C);
+  g.i0 = 0; g.j0 = 0; g.k0 = 0; g.k1 = bnt; g.sym = 1;
+  CU(launch_gemm(st, GEMM_UPDATE, g, P.ntr, P.ntr, 1));
+  ctx->launches += 5;
+  CU(cudaStreamSynchronize(st));  // the host-side staging vectors go out of scope
+  return LMM_OK;
+}
+
+// mean_and_cov(post(x*, σ²)) of the missing-data posterior: dense (p Ns)², by outputs.
+int masked_post_mean_and_cov(lmm_post* post, const double* xs, int Ns, double sigma2, double* mean, double* cov) {
+  lmm_ctx* ctx = post->ctx;
+  cudaStream_t st = ctx->stream;
+  MaskedPredictive P;
+  int rc = masked_predictive(post, xs, Ns, sigma2, P);
+  if (rc) return rc;
+  DevBuf dense;
+  CU(dense.alloc(ctx, (size_t)P.rows * P.rows * sizeof(double)));
+  CU(cudaMemsetAsync(dense.p, 0, (size_t)P.rows * P.rows * sizeof(double), st));
+  TiledSym C{P.C.as<double>(), P.ntr, sym_tiles(P.ntr) * TT};
+  CU(launch_untile_lower(st, C, 0, dense.as<double>(), P.rows));
+  ++ctx->launches;
+  std::vector<double> h((size_t)P.rows * P.rows);
+  CU(copy_out(ctx, h.data(), dense.p, h.size() * sizeof(double)));
+  if (mean) CU(copy_out(ctx, mean, P.mean.p, (size_t)P.rows * sizeof(double)));
+  CU(cudaStreamSynchronize(st));
+  for (int c = 0; c < P.rows; ++c)  // mirror the lower triangle
+    for (int r = c; r < P.rows; ++r) {
+      cov[(size_t)c * P.rows + r] = h[(size_t)c * P.rows + r];
+      cov[(size_t)r * P.rows + c] = h[(size_t)c * P.rows + r];
+    }
+  return LMM_OK;
+}
+
+// rand(rng, post(x*, σ²)) of the missing-data posterior -- AbstractGPs' generic FiniteGP rand on the dense model:
+// mean + chol(C + σ² I) z with ONE vector z of p Ns standard normals (by outputs).
+int masked_post_rand(lmm_post* post, const double* xs, int Ns, double sigma2, const double* z, double* out, int* info) {
+  lmm_ctx* ctx = post->ctx;
+  cudaStream_t st = ctx->stream;
+  MaskedPredictive P;
+  int rc = masked_predictive(post, xs, Ns, sigma2, P);
+  if (rc) return rc;
+  const size_t bpad = (size_t)P.ntr * TILE;
+  DevBuf b_W, b_logdet, b_info, b_z, b_X;
+  CU(b_W.alloc(ctx, (size_t)P.ntr * TT * sizeof(double)));
+  CU(b_logdet.alloc(ctx, sizeof(double)));
+  CU(b_info.alloc(ctx, sizeof(int)));
+  CU(cudaMemsetAsync(b_logdet.p, 0, sizeof(double), st));
+  CU(cudaMemsetAsync(b_info.p, 0, sizeof(int), st));
+  TiledSym C{P.C.as<double>(), P.ntr, sym_tiles(P.ntr) * TT};
+  CU(chol_factor(ctx, C, b_W.as<double>(), (size_t)P.ntr * TT, 1, b_logdet.as<double>(), b_info.as<int>()));
+  CU(b_z.alloc(ctx, bpad * sizeof(double)));
+  CU(cudaMemsetAsync(b_z.p, 0, bpad * sizeof(double), st));
+  CU(copy_in(ctx, b_z.as<double>(), z, (size_t)P.rows));
+  CU(b_X.alloc(ctx, bpad * sizeof(double)));
+  CU(launch_lower_gemv(st, C, b_z.as<double>(), bpad, b_X.as<double>(), bpad, 1));
+  CU(launch_axpy(st, b_X.as<double>(), P.mean.as<double>(), (size_t)P.rows, 1.0));
+  ctx->launches += 2;
+  int hinfo = 0;
+  CU(copy_out(ctx, &hinfo, b_info.p, sizeof(int)));
+  CU(copy_out(ctx, out, b_X.p, (size_t)P.rows * sizeof(double)));
+  CU(cudaStreamSynchronize(st));
+  if (hinfo > 0) {
+    if (info) *info = hinfo > P.rows ? P.rows : hinfo;
+    ctx->err = "PosDefException: the missing-data predictive covariance is not positive definite";
+    return hinfo > P.rows ? P.rows : hinfo;
+  }
+  if (info) *info = -1;
+  return LMM_OK;
+}
+}  // namespace lmm_host
+
+// Heterotopic OILMM whose mask is PER INPUT (at every input either all p outputs are observed or none is: sensors that drop
+// whole time steps).  Conditioning on the observed entries is then the ordinary OILMM on the observed inputs -- the
+// projection T*Y stays exact, the latents stay independent, cost O(m N_obs³) instead of the dense model's O((p N)³) -- and the
+// returned handle is a full OILMM posterior (marginals, cov, rand, logpdf, conditioning, gradients, save / load).
+// A mask that is not per-input returns LMM_E_UNSUPPORTED: use lmm_ilmm_masked_posterior (dense model) with H = U sqrt(S).
+extern "C" int lmm_oilmm_masked_posterior(lmm_ctx* ctx, const lmm_gp_desc* latents, int m, const double* x, int N, int D, const double* U,
+                                          const double* S, int p, double sigma2, const double* y, int out_dim, lmm_post** out_post,
+                                          double* out_logpdf, int* n_observed_inputs, int* info_latent) {
+  if (!ctx) return LMM_E_ARG;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (out_post) *out_post = nullptr;
+    int rc = check_common(ctx, latents, m, x, N, D, p, out_dim);
+    if (rc) return rc;
+    if (!U || !S || !y || (!out_post && !out_logpdf)) return ctx->fail(LMM_E_ARG, "null pointer");
+    if (is_device_ptr(y) || is_device_ptr(x)) return ctx->fail(LMM_E_UNSUPPORTED, "the missing-data path takes host x and y (the mask is read on the host)");
+  }
+  std::vector<int> keep;
+  for (int i = 0; i < N; ++i) {
+    int nan = 0;
+    for (int j = 0; j < p; ++j) nan += (y[(size_t)j * N + i] != y[(size_t)j * N + i]) ? 1 : 0;
+    if (nan == 0) keep.push_back(i);
+    else if (nan != p) {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      return ctx->fail(LMM_E_UNSUPPORTED, "the mask is not per-input (some outputs observed, some missing at one input): use lmm_ilmm_masked_posterior");
+    }
+  }
+  const int No = (int)keep.size();
+  if (n_observed_inputs) *n_observed_inputs = No;
+  if (No == 0) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->fail(LMM_E_ARG, "every observation is missing");
+  }
+  std::vector<double> xo((size_t)No * D), yo((size_t)p * No);
+  for (int k = 0; k < No; ++k) {
+    for (int d = 0; d < D; ++d) xo[(size_t)k * D + d] = x[(size_t)keep[k] * D + d];
+    for (int j = 0; j < p; ++j) yo[(size_t)j * No + k] = y[(size_t)j * N + keep[k]];
+  }
+  return lmm_oilmm_posterior(ctx, latents, m, xo.data(), No, D, U, S, p, sigma2, yo.data(), out_dim, out_post, out_logpdf, nullptr, info_latent);
+}

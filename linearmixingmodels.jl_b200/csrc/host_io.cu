@@ -11,7 +11,7 @@
 namespace lmm_host {
 struct PostFileHeader {
   char magic[8];  // "LMMPOST3"
-  int32_t kind, m, p, N, D, nt, lo, hi, big_n, big_nt, has_U, has_noise_vec, has_Ept, reserved;
+  int32_t kind, m, p, N, D, nt, lo, hi, big_n, big_nt, has_U, has_noise_vec, has_Ept, n_obs;  // n_obs: POST_MASKED observed entries (ints after the arrays)
   double sigma2;
   uint64_t n_x, n_L, n_W, n_alpha, n_delta, n_params, n_H, n_noise_vec, n_Ept;  // element counts (doubles; params: structs)
 };
@@ -64,7 +64,6 @@ extern "C" int lmm_post_save(lmm_post* post, const char* path) {
   lmm_ctx* ctx = post->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  if (post->kind == POST_MASKED) return ctx->fail(LMM_E_UNSUPPORTED, "a missing-data posterior cannot be saved yet");
   FILE* f = fopen(path, "wb");
   if (!f) return ctx->fail(LMM_E_ARG, std::string("cannot open ") + path + " for writing");
   PostFileHeader h{};
@@ -72,6 +71,7 @@ extern "C" int lmm_post_save(lmm_post* post, const char* path) {
   h.kind = post->kind; h.m = post->m; h.p = post->p; h.N = post->N; h.D = post->D; h.nt = post->nt; h.lo = post->lo; h.hi = post->hi;
   h.big_n = post->big_n; h.big_nt = post->big_nt; h.has_U = post->U.empty() ? 0 : 1;
   h.has_noise_vec = post->d_noise_vec ? 1 : 0; h.has_Ept = post->d_Ept ? 1 : 0;
+  h.n_obs = post->kind == POST_MASKED ? post->big_n : 0;
   h.sigma2 = post->sigma2;
   post_array_sizes(post, h);
   int rc = LMM_OK;
@@ -94,6 +94,7 @@ extern "C" int lmm_post_save(lmm_post* post, const char* path) {
     const size_t bytes = (size_t)cnt[k] * (k == 5 ? sizeof(LatentParams) : sizeof(double));
     if (bytes && arrs[k]) rc = stream_out(ctx, f, arrs[k], bytes);
   }
+  if (rc == LMM_OK && h.n_obs > 0) rc = stream_out(ctx, f, post->d_obs, (size_t)h.n_obs * sizeof(int));
   if (fclose(f) != 0 && rc == LMM_OK) rc = ctx->fail(LMM_E_ARG, "close failed while saving a posterior");
   return rc;
 }
@@ -111,7 +112,7 @@ extern "C" int lmm_post_load(lmm_ctx* ctx, const char* path, lmm_post** out_post
     return ctx->fail(LMM_E_ARG, msg);
   };
   if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "LMMPOST3", 8) != 0) return bail("not a liblmm posterior file");
-  if (h.kind < POST_OILMM || h.kind > POST_JOINT /* POST_MASKED is never written */ || h.m <= 0 || h.p <= 0 || h.N <= 0 || h.D <= 0 || h.lo < 0 || h.hi < h.lo || h.hi > h.m)
+  if (h.kind < POST_OILMM || h.kind > POST_MASKED || (h.kind == POST_MASKED) != (h.n_obs > 0) || (h.kind == POST_MASKED && h.n_obs != h.big_n) || h.m <= 0 || h.p <= 0 || h.N <= 0 || h.D <= 0 || h.lo < 0 || h.hi < h.lo || h.hi > h.m)
     return bail("corrupt posterior header");
   lmm_post* P = new lmm_post();
   P->ctx = ctx; P->kind = h.kind; P->m = h.m; P->p = h.p; P->N = h.N; P->D = h.D; P->nt = h.nt; P->lo = h.lo; P->hi = h.hi;
@@ -172,8 +173,19 @@ extern "C" int lmm_post_load(lmm_ctx* ctx, const char* path, lmm_post** out_post
     *slots[k] = d;
     if (bytes) rc = stream_in(ctx, f, d, bytes);
   }
+  if (rc == LMM_OK && h.n_obs > 0) {  // missing-data posterior: the list of observed entries
+    void* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, (size_t)h.n_obs * sizeof(int), ctx->stream);
+    if (e != cudaSuccess) rc = ctx->fail_cuda(e, "cudaMallocAsync (posterior load)", __LINE__);
+    else {
+      P->d_obs = (int*)d;
+      total += (size_t)h.n_obs * sizeof(int);
+      rc = stream_in(ctx, f, d, (size_t)h.n_obs * sizeof(int));
+    }
+  }
   fclose(f);
   if (rc != LMM_OK) {
+    if (P->d_obs) cudaFreeAsync(P->d_obs, ctx->stream);
     for (void** sl : slots)
       if (*sl) cudaFreeAsync(*sl, ctx->stream);
     cudaStreamSynchronize(ctx->stream);

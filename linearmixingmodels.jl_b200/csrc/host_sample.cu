@@ -289,8 +289,8 @@ extern "C" int lmm_post_rand(lmm_post* post, const double* xs, int Ns, double si
   lmm_ctx* ctx = post->ctx;
   std::lock_guard<std::mutex> lk(ctx->mu);
   CU(cudaSetDevice(ctx->device));
-  if (post->kind != POST_IMOGP && post->kind != POST_JOINT && !z_noise) return ctx->fail(LMM_E_ARG, "null pointer");
-  if (post->kind == POST_MASKED) return ctx->fail(LMM_E_UNSUPPORTED, "a missing-data posterior offers mean_and_var only");
+  if (post->kind != POST_IMOGP && post->kind != POST_JOINT && post->kind != POST_MASKED && !z_noise) return ctx->fail(LMM_E_ARG, "null pointer");
+  if (post->kind == POST_MASKED) return masked_post_rand(post, xs, Ns, sigma2, z_latent, out, info_latent);  // z_latent: p*Ns normals
   if (post->joint()) return ilmm_post_rand(post, xs, Ns, sigma2, z_latent, z_noise, out, info_latent);
   cudaStream_t st = ctx->stream;
   // OILMM: latents sampled at the default FiniteGP noise 1e-18 (src/oilmm.jl:47); IndependentMOGP: σ²

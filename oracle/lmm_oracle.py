@@ -712,6 +712,21 @@ def missing_data_posterior_mean_and_var(fs, H, x, sigma2, y, xs, sigma2_pred) ->
     return mean, var
 
 
+def missing_data_posterior_mean_and_cov(fs, H, x, sigma2, y, xs, sigma2_pred) -> Tuple[np.ndarray, np.ndarray]:
+    """Posterior mean and full covariance (+ sigma2_pred I) of ALL outputs at xs given the observed entries of y (dense model)."""
+    y = np.asarray(y, dtype=np.float64)
+    obs = np.flatnonzero(~np.isnan(y))
+    C = dense_mogp_cov(fs, H, x)[np.ix_(obs, obs)] + sigma2 * np.eye(len(obs))
+    L = _chol_lower(C)
+    alpha = _bwd(L, _fwd(L, y[obs] - dense_mogp_mean(fs, H, x)[obs]))
+    Ksx = dense_mogp_cov(fs, H, xs, x)[:, obs]
+    V = _fwd(L, Ksx.T)
+    mean = dense_mogp_mean(fs, H, xs) + Ksx @ alpha
+    cov = dense_mogp_cov(fs, H, xs) - V.T @ V
+    cov[np.diag_indices_from(cov)] += sigma2_pred
+    return mean, cov
+
+
 # --------------------------------------------------------------------------------------------
 # Gradients of the logpdf (for the rrule; checked against central finite differences in tests)
 # --------------------------------------------------------------------------------------------
