@@ -123,7 +123,7 @@ cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t
   // roles of the fused kernel only take SMs away from them (+10 %), so larger matrices keep one launch per operation
   // ("chain_fused" = 2 forces the fused kernel everywhere).
   const bool fused = ctx->chain_fused == 2 || (ctx->chain_fused == 1 && nt <= 32);
-  const int ob = ctx->outer_block_user ? ctx->outer_block : fused ? (nt <= 32 ? 3 : nt <= 112 ? 3 : 4) : (nt <= 32 ? 1 : nt <= 72 ? 2 : nt <= 112 ? 3 : 4);
+  const int ob = ctx->outer_block_user ? ctx->outer_block : fused ? (nt <= 112 ? 3 : 4) : (nt <= 32 ? 1 : nt <= 48 ? 2 : nt <= 112 ? 3 : 4);
   const int nblk = (nt + ob - 1) / ob;
   cudaError_t e;
   while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
