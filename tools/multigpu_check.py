@@ -96,6 +96,23 @@ def main():
     errs["imogp_vector_noise"] = abs(lmm.logpdf(fi(lmm.MOInputIsotopicByOutputs(x, m), vn), yi) - o.imogp_logpdf_noise(fs, x, vn, yi)) / abs(
         o.imogp_logpdf_noise(fs, x, vn, yi))
     post2.f.fs[0]._owner.free()
+    # a factorisation that fails on SOME ranks only: prior rand of an OILMM whose first latents are SE kernels on 700
+    # points 0.01 apart (K + 1e-18 I is numerically singular: PosDefException, as in the reference) and whose last latents are
+    # Exponential kernels (fine).  Every rank must raise the SAME exception (collective verdict) instead of some ranks hanging in
+    # the all-reduce that follows, and the next collective call must still work.
+    gmix = [lmm.GP(lmm.SEKernel()) if i < (m + 1) // 2 else lmm.GP(lmm.ExponentialKernel()) for i in range(m)]
+    fmix = lmm.ILMM(lmm.independent_mogp(gmix), lmm.Orthogonal(U, S))
+    verdict = [-1.0, -1.0]
+    try:
+        lmm.rand(np.random.default_rng(3), fmix(lmm.MOInputIsotopicByOutputs(x, p), 0.1))
+    except lmm.PosDefException as e:
+        verdict = [float(e.info), float(e.latent)]
+    tv = torch.tensor(verdict, dtype=torch.float64, device="cuda")
+    allv = [torch.zeros_like(tv) for _ in range(world)]
+    dist.all_gather(allv, tv)
+    same = all(bool(torch.equal(a, allv[0])) for a in allv)
+    errs["posdef_collective"] = 0.0 if (same and verdict[0] > 0 and verdict[1] == 0.0) else 1.0
+    errs["after_posdef_logpdf"] = abs(lmm.logpdf(fx, y) - ref) / abs(ref)
     worst = max(errs.values())
     ok = worst < 1e-6 and max(errs[k] for k in ("logpdf", "mean", "var", "post_logpdf", "grad_value")) < 1e-9
     print(f"rank {rank}/{world}: {'OK' if ok else 'FAIL'} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
