@@ -109,9 +109,9 @@ const char* lmm_version(void);
  *   "chain_fused"     1 = where the grids are small (batches <= 2, or few latents x few tile rows) the panel chain of a tile
  *                     column -- TRSM of the column, update of the next column(s), factorisation of the next diagonal tile --
  *                     is ONE launch whose CTAs hand tiles to each other through ready counters in global memory, the
- *                     critical tiles first [default: single factors up to N = 4096 and small batched grids, where the chain
- *                     is the run time]; 2 = also for larger single factors (measured slower from N = 8192 on: the trailing
- *                     GEMMs set the time there); 0 = one launch per operation, chained by "pdl"
+ *                     critical tiles first [default: single factors up to N = 4096, the last 31 tile columns of larger ones
+ *                     and small batched grids -- where the chain is the run time]; 2 = everywhere (measured slower from
+ *                     N = 8192 on: the trailing GEMMs set the time there); 0 = one launch per operation, chained by "pdl"
  *   "pdl"             programmatic dependent launch along the panel chain: the diagonal-tile kernel, the small direct GEMMs
  *                     and the fused chain kernel are launched with programmatic stream serialisation, wait on
  *                     `griddepcontrol.wait` before their first read and release their successor before their final

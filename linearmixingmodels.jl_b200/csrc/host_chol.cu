@@ -122,8 +122,13 @@ cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t
   // 2048 -4 %, 4096 -2 %); from N = 8192 on the trailing GEMMs of the other stream set the time and the sliced, one-CTA-per-SM
   // roles of the fused kernel only take SMs away from them (+10 %), so larger matrices keep one launch per operation
   // ("chain_fused" = 2 forces the fused kernel everywhere).
-  const bool fused = ctx->chain_fused == 2 || (ctx->chain_fused == 1 && nt <= 32);
-  const int ob = ctx->outer_block_user ? ctx->outer_block : fused ? (nt <= 112 ? 3 : 4) : (nt <= 32 ? 1 : nt <= 48 ? 2 : nt <= 112 ? 3 : 4);
+  // Larger factors fuse only their TAIL: once at most CHAIN_TAIL_ROWS tile rows are left below the column the trailing GEMMs
+  // are small again and the chain is what remains.
+  constexpr int CHAIN_TAIL_ROWS = 31;
+  const bool fused_all = ctx->chain_fused == 2 || (ctx->chain_fused == 1 && nt <= 32);
+  auto use_fused = [&](int jj) { return fused_all || (ctx->chain_fused == 1 && (long long)(nt - 1 - jj) * batch <= CHAIN_TAIL_ROWS); };
+  const bool fused = ctx->chain_fused != 0;  // some column may take the fused launch: counters needed
+  const int ob = ctx->outer_block_user ? ctx->outer_block : fused_all ? (nt <= 112 ? 3 : 4) : (nt <= 32 ? 1 : nt <= 48 ? 2 : nt <= 112 ? 3 : 4);
   const int nblk = (nt + ob - 1) / ob;
   cudaError_t e;
   while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
@@ -166,7 +171,7 @@ cudaError_t chol_factor_rightlooking(lmm_ctx* ctx, TiledSym L, double* W, size_t
       }
       factored_ahead = false;
       if (jj + 1 >= nt) continue;
-      if (fused) {
+      if (use_fused(jj)) {
         int c_end = jj + 2;
         if (jj + 1 == s1) {  // block boundary: the launch also carries the panel stream's update of the whole next block
           if (b >= 1 && (e = cudaStreamWaitEvent(X, evY[b - 1], 0)) != cudaSuccess) return e;  // Y(b-1) writes the columns >= s1
@@ -232,6 +237,8 @@ cudaError_t chol_factor_rowcyclic(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
   g.W = W; g.w_batch_stride = wstride; g.sym = 1;
   auto first_own = [&](int s) { return s + (((me - s % G) % G) + G) % G; };
   auto own_count = [&](int s) { const int f = first_own(s); return f >= nt ? 0 : (nt - 1 - f) / G + 1; };
+  int* counters = nullptr;
+  if (ctx->chain_fused && (e = chain_counters(ctx, ctx->stream, nt, 1, &counters)) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
@@ -259,15 +266,26 @@ cudaError_t chol_factor_rowcyclic(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
       ctx->launches += 2;
     }
     g.row_step = 1;
+    bool factored_ahead = false;
     for (int jj = s0; jj < s1; ++jj) {  // the panel: every rank, all rows
-      if (jj > s0) {
-        g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
-        if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, 1)) != cudaSuccess) return e;
+      if (!factored_ahead) {
+        if (jj > s0) {
+          g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+          if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nt - jj, 1)) != cudaSuccess) return e;
+          ++ctx->launches;
+        }
+        if ((e = launch_potrf_tile(X, L, W, wstride, jj, 1, logdet, info)) != cudaSuccess) return e;
         ++ctx->launches;
       }
-      if ((e = launch_potrf_tile(X, L, W, wstride, jj, 1, logdet, info)) != cudaSuccess) return e;
-      ++ctx->launches;
-      if (jj + 1 < nt) {
+      factored_ahead = false;
+      if (jj + 1 >= nt) continue;
+      if (counters && jj + 1 < s1 && (ctx->chain_fused == 2 || nt - 1 - jj <= 40)) {
+        // inside a block the redundant panel chain is one fused launch per column (the chain is what bounds this schedule) once
+        // the column is short enough for the sliced roles (above ~40 tiles the TMA-pipelined TRSM launch is the faster one)
+        if ((e = launch_chain_column(X, L, W, wstride, jj, s0, jj + 2, 1, 1, logdet, info, counters)) != cudaSuccess) return e;
+        ++ctx->launches;
+        factored_ahead = true;
+      } else {
         g.i0 = jj + 1; g.j0 = jj;
         if ((e = launch_gemm(X, GEMM_TRSM, g, 1, nt - jj - 1, 1)) != cudaSuccess) return e;
         ++ctx->launches;
