@@ -115,15 +115,16 @@ def fp64_peak_tflops():
 def ncu_traffic(p, N, mloc):
     """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the Cholesky launch sequence of
     one step on one rank, from the committed ncu pass over a full C4 eval
-    (profiles/r01_launches_c4_summary.json: 64 latents); per-latent work is independent, so a rank
+    (profiles/r02_launches_c4_summary.json, falling back to round 1's: 64 latents); per-latent work is independent, so a rank
     holding mloc latents moves mloc/64 of it.  null for any other problem size."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_launches_c4_summary.json")) as fh:
-            d = json.load(fh)
-        if p == 64 and N == 16384:
-            return d["cholesky_sequence"]["dram_bytes_per_step"] * mloc / 64.0
-    except Exception:
-        pass
+    for name in ("r02_launches_c4_summary.json", "r01_launches_c4_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                d = json.load(fh)
+            if p == 64 and N == 16384:
+                return d["cholesky_sequence"]["dram_bytes_per_step"] * mloc / 64.0
+        except Exception:
+            continue
     return None
 
 
