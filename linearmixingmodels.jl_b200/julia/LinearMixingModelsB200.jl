@@ -504,8 +504,38 @@ function posterior_missing(fx::FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}
     return DevicePosterior(h[]), lp[], Int(nobs[])
 end
 
+# An OILMM whose mask is per input (whole time steps missing) stays an OILMM on the observed inputs: a full posterior.
+function posterior_missing(fx::FiniteGP{<:OILMM{<:IndependentMOGP{<:Vector{<:GP}}}}, y::AbstractVector{<:Real})
+    fs, H, σ², x = unpack(fx)
+    X, D = points(x)
+    descs, keep = gpdescs(fs.fs)
+    h = Ref{Ptr{Cvoid}}(C_NULL); lp = Ref{Float64}(0.0); nobs = Ref{Cint}(0); il = Ref{Cint}(-1)
+    rc = GC.@preserve keep ccall((:lmm_oilmm_masked_posterior, liblmm), Cint,
+        (Ptr{Cvoid}, Ptr{GpDesc}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Cint,
+         Ptr{Ptr{Cvoid}}, Ptr{Float64}, Ptr{Cint}, Ptr{Cint}),
+        ctx(), descs, length(descs), X, length(x), D, Matrix{Float64}(H.U), Vector{Float64}(diag(H.S)), size(H, 1), Float64(σ²),
+        Vector{Float64}(y), fx.x.out_dim, h, lp, nobs, il)
+    if rc == -3   # the mask is not per-input: the dense model (method above) on H = U sqrt(S)
+        return invoke(posterior_missing, Tuple{FiniteGP{<:ILMM{<:IndependentMOGP{<:Vector{<:GP}}}},AbstractVector{<:Real}}, fx, y)
+    end
+    check(rc)
+    owner = DevicePosterior(h[])
+    return ILMM(IndependentMOGP([DeviceLatentPosterior(owner, i - 1, f) for (i, f) in enumerate(fs.fs)]), H), lp[], Int(nobs[])
+end
+
+# --- one latent of a posterior on its own: mean_and_var(get_latent_gp(post).fs[i](x*, σ²)), the call src/oilmm.jl:61 makes ---
+function AbstractGPs.mean_and_var(fx::FiniteGP{<:DeviceLatentPosterior})
+    X, _ = points(fx.x)
+    n = length(fx.x)
+    M = Vector{Float64}(undef, n); V = Vector{Float64}(undef, n)
+    check(ccall((:lmm_post_latent_mean_and_var, liblmm), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Float64, Ptr{Float64}, Ptr{Float64}),
+        fx.f.owner.handle, fx.f.index, X, n, Float64(noise_var(fx.Σy)), M, V))
+    return M, V
+end
+
 # --- tunables and teardown ------------------------------------------------------------------------------------------
-set_option(key::AbstractString, value::Real) = check(GC.@preserve keep ccall((:lmm_ctx_set_option, liblmm), Cint, (Ptr{Cvoid}, Cstring, Float64), ctx(), key, Float64(value)))
+set_option(key::AbstractString, value::Real) = check(ccall((:lmm_ctx_set_option, liblmm), Cint, (Ptr{Cvoid}, Cstring, Float64), ctx(), key, Float64(value)))
 version() = unsafe_string(ccall((:lmm_version, liblmm), Cstring, ()))
 function __init__()
     atexit() do

@@ -266,6 +266,10 @@ def test_julia_shim_describes_shape_parameter_and_ard():
     c_fields = re.findall(r"^\s+(?:const\s+)?(?:int32_t|double|lmm_kernel_term)\s*\*?\s*(\w+);", hdr[hdr.index("typedef struct lmm_gp_desc {"):hdr.index("} lmm_gp_desc;")], flags=re.M)
     jl_fields = re.findall(r"^\s+(\w+)::", jl[jl.index("struct GpDesc"):jl.index("const CTX")], flags=re.M)
     assert c_fields == jl_fields, (c_fields, jl_fields)
+    # `keep` only exists where gpdescs built it: no stray `GC.@preserve keep` in another definition (per top-level definition)
+    for defn in re.split(r"(?m)^(?=function |[a-z_]+\(.*\) = )", jl):
+        if "GC.@preserve keep" in defn:
+            assert "= gpdescs(" in defn, defn[:100]
     for fn_src in re.split(r"(?m)^(?=function )", jl):
         if "= gpdescs(" in fn_src and not fn_src.startswith("function gpdescs"):
             n_desc_calls = len(re.findall(r"ccall\(\(:lmm_[a-z0-9_]+, liblmm\), Cint,\s*\(Ptr\{Cvoid\}, Ptr\{GpDesc\}", fn_src))
