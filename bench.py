@@ -255,6 +255,11 @@ def multi_gpu_extras(lmm, ctx, dist, torch, world, rank):
     rec["logdet_rel_diff"] = abs(rec["rowcyclic_logdet"] - rec["replicated_logdet"]) / abs(rec["replicated_logdet"])
     rec["tflops_rowcyclic"] = 16384 ** 3 / 3.0 / (rec["rowcyclic_ms"] * 1e-3) / 1e12
     out["ilmm_rowcyclic"] = rec
+    # the same joint dimension through the public API (lmm.logpdf of a general ILMM, p = 8, m = 4, N = 4096): replicated vs row-cyclic vs
+    # row-cyclic with DISTRIBUTED STORAGE (each rank assembles and keeps 1/G of the joint matrix; "partition_ilmm" = 2)
+    from tools.multigpu_ilmm import ilmm_logpdf_record
+
+    out["ilmm_distributed"] = ilmm_logpdf_record(lmm, ctx, dist, torch, 8, 4, 4096)
     p, m, N, nsweep = 256, 128, 8192, 32
     rng = np.random.default_rng(0)
     x = np.sort(rng.uniform(0, N / 100.0, N))

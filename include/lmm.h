@@ -119,6 +119,11 @@ const char* lmm_version(void);
  *   "partition_ilmm"  1 = the joint factor of a general ILMM (one large matrix, factored by every rank of the communicator
  *                     on identical inputs) is partitioned row-cyclically over the ranks: one ncclAllGather of the current
  *                     block column per step, panels redundant.  Every rank must make the same calls.  Default 0 (replicas).
+ *                     2 = as 1, and lmm_ilmm_logpdf additionally DISTRIBUTES THE STORAGE: every rank assembles and keeps only
+ *                     the tile rows it owns (1/G of the joint matrix) plus two block-column windows; both operands of every
+ *                     trailing update come from the all-gathered window, the right-hand side rides along as an extra tile
+ *                     row (z = L^{-1} δ falls out of the panel TRSMs), so a joint dimension that does not fit one GPU runs.
+ *                     Calls that need the whole factor afterwards (posterior, gradient) behave as with 1.
  *   "nccl_small_ctas" CTA cap of the panel-chain communicator (takes effect at lmm_comm_init; 0 = NCCL's choice)
  *   "gemm_small"      grids of at most this many tiles use the latency-optimised direct kernel (8 row slices per tile, no
  *                     shared memory, zero blocks of the triangular inverse skipped) instead of the TMA-pipelined one
@@ -137,7 +142,8 @@ int lmm_ctx_counters(lmm_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes,
 /* CUDA-event time (ms) of the device work of the most recent compute call, and of its dominant
  * stages: [0] total, [1] kernel-matrix build, [2] Cholesky, [3] solves, [4] projection,
  * [5] prediction (cross-cov + TRSM + back-projection), [6] Cholesky trailing-update GEMM launches
- * count (as a double), [7] reserved. */
+ * count (as a double), [7] reserved.  After a distributed-storage ILMM logpdf ("partition_ilmm" = 2) the slots [4], [5], [7]
+ * hold BYTES instead: the matrix rows this rank stores, its exchange / window workspace, the whole packed matrix. */
 int lmm_ctx_last_timings(lmm_ctx* ctx, double out_ms[8]);
 
 /* ---- multi-GPU: one process (and one context) per GPU; latents are block-sharded over ranks --- */

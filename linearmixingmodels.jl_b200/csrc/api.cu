@@ -227,7 +227,7 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
     if (value < 0 || value > 32) return ctx->fail(LMM_E_ARG, "nccl_small_ctas must be in [0, 32]");
     ctx->nccl_small_ctas = (int)value;
   } else if (k == "partition_ilmm") {
-    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_ARG, "partition_ilmm must be 0 or 1");
+    if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "partition_ilmm must be 0, 1 or 2");
     ctx->partition_ilmm = (int)value;
   } else if (k == "gemm_small") {
     if (value < 0 || value > 4096) return ctx->fail(LMM_E_ARG, "gemm_small must be in [0, 4096]");

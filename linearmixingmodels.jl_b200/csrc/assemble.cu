@@ -33,11 +33,18 @@ __global__ void __launch_bounds__(256) assemble_ilmm_kernel(TiledSym out, const 
                                                             const LatentParams* __restrict__ params, int m, int q,
                                                             const double* __restrict__ E, const double* __restrict__ Hm, int mode,
                                                             int form) {
-  const int tl = blockIdx.x;
-  int I = (int)((sqrt(8.0 * (double)tl + 1.0) - 1.0) * 0.5);
-  while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tl) ++I;
-  while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
-  const int J = tl - (int)((size_t)I * (I + 1) / 2);
+  int I, J;
+  if (out.cyc_G) {  // distributed storage: grid (tile columns, own rows); this rank builds the tile rows it owns
+    I = out.cyc_r + (int)blockIdx.y * out.cyc_G;
+    J = blockIdx.x;
+    if (J > I) return;
+  } else {
+    const int tl = blockIdx.x;
+    I = (int)((sqrt(8.0 * (double)tl + 1.0) - 1.0) * 0.5);
+    while ((size_t)(I + 1) * (I + 2) / 2 <= (size_t)tl) ++I;
+    while ((size_t)I * (I + 1) / 2 > (size_t)tl) --I;
+    J = tl - (int)((size_t)I * (I + 1) / 2);
+  }
   const int dim = q * N;
   double* tile = out.tile(0, I, J);
   for (int e = threadIdx.x; e < TT; e += 256) {
@@ -69,6 +76,12 @@ __global__ void __launch_bounds__(256) assemble_ilmm_kernel(TiledSym out, const 
 
 cudaError_t launch_assemble_ilmm(cudaStream_t st, TiledSym out, const double* x, int N, int D, const LatentParams* params, int m,
                                  int q, const double* E, const double* Hm, int mode, int form) {
+  if (out.cyc_G) {  // out.nt = tile rows of the matrix proper (a right-hand-side row below it is written by launch_rhs_row)
+    if (out.nt <= out.cyc_r) return cudaSuccess;
+    dim3 grid((unsigned)out.nt, (unsigned)((out.nt - 1 - out.cyc_r) / out.cyc_G + 1));
+    assemble_ilmm_kernel<<<grid, 256, 0, st>>>(out, x, N, D, params, m, q, E, Hm, mode, form);
+    return cudaGetLastError();
+  }
   assemble_ilmm_kernel<<<(unsigned)sym_tiles(out.nt), 256, 0, st>>>(out, x, N, D, params, m, q, E, Hm, mode, form);
   return cudaGetLastError();
 }

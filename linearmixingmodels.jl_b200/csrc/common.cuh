@@ -33,12 +33,34 @@ __host__ __device__ __forceinline__ size_t sym_tile_index(int I, int J) {
 }
 __host__ __device__ __forceinline__ size_t sym_tiles(int nt) { return (size_t)nt * (size_t)(nt + 1) / 2; }
 
+// Tiles of the rows a rank owns in a row-cyclic partition (rank r of G owns the tile rows I = r, r + G, ...): row
+// I = r + l*G holds its I + 1 tiles contiguously at l*(r+1) + G*l*(l-1)/2 (the rows before it hold r+1, r+G+1, ... tiles).
+__host__ __device__ __forceinline__ size_t cyc_tile_index(int I, int J, int G, int r) {
+  const size_t l = (size_t)((I - r) / G);
+  return l * (size_t)(r + 1) + (size_t)G * (l * (l - 1) / 2) + (size_t)J;
+}
+__host__ __device__ __forceinline__ size_t cyc_tiles(int nrows, int G, int r) {  // tiles of the rows < nrows rank r owns
+  if (nrows <= r) return 0;
+  const int cnt = (nrows - 1 - r) / G + 1;
+  return cyc_tile_index(r + cnt * G, 0, G, r);
+}
+
 struct TiledSym {
   double* base;
   int nt;
   size_t batch_stride;  // doubles
+  // Two alternative tile addressings of the partitioned (distributed-storage) factorisation, batch 1; all 0 = packed lower:
+  //   ntc > 0:   a rectangular WINDOW of the matrix, tile (I, J) at ((I - row0) * ntc + (J - col0)) -- the block column a
+  //              panel is factored in; every kernel that takes a TiledSym (diagonal tile, fused chain) then works on it
+  //   cyc_G > 0: only the tile rows I = cyc_r (mod cyc_G) exist, packed as cyc_tile_index says
+  int ntc = 0, row0 = 0, col0 = 0;
+  int cyc_G = 0, cyc_r = 0;
   __host__ __device__ __forceinline__ double* tile(int b, int I, int J) const {
-    return base + (size_t)b * batch_stride + sym_tile_index(I, J) * TT;
+    size_t idx;
+    if (ntc) idx = (size_t)(I - row0) * (size_t)ntc + (size_t)(J - col0);
+    else if (cyc_G) idx = cyc_tile_index(I, J, cyc_G, cyc_r);
+    else idx = sym_tile_index(I, J);
+    return base + (size_t)b * batch_stride + idx * TT;
   }
 };
 

@@ -306,6 +306,148 @@ cudaError_t chol_factor_rowcyclic(lmm_ctx* ctx, TiledSym L, double* W, size_t ws
   return cudaSuccess;
 }
 
+// Row-cyclic factorisation with DISTRIBUTED STORAGE: rank r holds only the tile rows I = r (mod G) of
+// the matrix (`Lown`, cyclic-packed: 1/G of the matrix) plus two block-column windows `P` (all rows x ob tile columns).  Per
+// block column b = [s0, s1):
+//   X: [wait Y(b-2)]  own rows of block column b  -=  P(b-1) P(b-1)'           (the look-ahead update, operands from the window)
+//      pack own rows -> ncclAllGather -> unpack into the window P(b) -- every rank now holds the whole block column
+//      panel on P(b), redundantly on every rank (diagonal tile, TRSM-as-GEMM, in-block updates; <= one wave of tiles, so the
+//      redundancy costs no time); own rows of the finished window -> Lown (the distributed factor)
+//   Y: [wait X(b)]    own rows of the columns >= s1 + ob  -=  P(b) P(b)'       (97 % of the flops, split G ways)
+// Both operands of every trailing update come from the window, so a finished column of L is never needed from another
+// rank again and the all-gather of block b+1 (on X) runs beside the trailing update of block b (on Y); the two windows
+// alternate.  `nrows` may exceed the `nc` columns that are factored: the extra tile row (the right-hand side, launch_rhs_row)
+// receives the panel TRSMs and ends up as z = L^{-1} rhs -- the forward solve needs no distributed sweep; its segments
+// are copied into `zvec` (on every rank) as the windows finish.  logdet / info / W(J) are computed by every rank.
+// Per rank: cyc_tiles(nrows) + (3 + 1/G) * nrows * ob tiles instead of sym_tiles(nrows).
+size_t rowcyclic_dist_workspace_tiles(int nrows, int G, int ob) {
+  const size_t slots = (size_t)(nrows + G - 1) / G;
+  return slots * ob * (size_t)(G + 1) + 2 * (size_t)nrows * ob;
+}
+int rowcyclic_dist_block(const lmm_ctx* ctx, int nc) { return ctx->outer_block_user ? ctx->outer_block : (nc <= 72 ? 2 : nc <= 112 ? 3 : 4); }
+
+cudaError_t chol_factor_rowcyclic_dist(lmm_ctx* ctx, TiledSym Lown, int nrows, int nc, double* W, size_t wstride, double* logdet, int* info,
+                                       double* zvec) {
+  const int G = ctx->nranks, me = ctx->rank;
+  const int ob = rowcyclic_dist_block(ctx, nc);
+  const int nblk = (nc + ob - 1) / ob;
+  cudaError_t e;
+  while ((int)ctx->blk_ev.size() < 2 * nblk + 2) {
+    cudaEvent_t ev;
+    if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    ctx->blk_ev.push_back(ev);
+  }
+  const int max_slots = (nrows + G - 1) / G;
+  const size_t send_elems = (size_t)max_slots * ob * TT, win_elems = (size_t)nrows * ob * TT;
+  const size_t need = rowcyclic_dist_workspace_tiles(nrows, G, ob) * TT * sizeof(double);
+  if (ctx->xbuf_bytes < need) {
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
+    ctx->xbuf = nullptr;
+    ctx->xbuf_bytes = 0;
+    if ((e = cudaMalloc(&ctx->xbuf, need)) != cudaSuccess) return e;
+    ctx->xbuf_bytes = need;
+  }
+  double* sendb = (double*)ctx->xbuf;
+  double* recvb = sendb + send_elems;
+  double* win[2] = {recvb + send_elems * (size_t)G, recvb + send_elems * (size_t)G + win_elems};
+  cudaStream_t X = ctx->panel_stream, Y = ctx->update_stream;
+  cudaEvent_t* evX = ctx->blk_ev.data();
+  cudaEvent_t* evY = ctx->blk_ev.data() + nblk;
+  auto first_own = [&](int s) { return s + (((me - s % G) % G) + G) % G; };
+  auto own_count = [&](int s) { const int f = first_own(s); return f >= nrows ? 0 : (nrows - 1 - f) / G + 1; };
+  auto window = [&](int b) {  // block column b as a TiledSym: rows >= b*ob, tile columns [b*ob, b*ob + ob)
+    TiledSym P{win[b & 1], nrows, 0};
+    P.ntc = ob; P.row0 = b * ob; P.col0 = b * ob;
+    return P;
+  };
+  int* counters = nullptr;
+  if (ctx->chain_fused && (e = chain_counters(ctx, ctx->stream, nrows, 1, &counters)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(X, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(Y, ctx->ev_fork, 0)) != cudaSuccess) return e;
+  GemmArgs g{};
+  g.W = W; g.w_batch_stride = wstride; g.sym = 1;
+  for (int b = 0; b < nblk; ++b) {
+    const int s0 = b * ob, s1 = (s0 + ob < nc) ? s0 + ob : nc;
+    const TiledSym P = window(b);
+    if (b >= 1) {
+      if (b >= 2 && (e = cudaStreamWaitEvent(X, evY[b - 2], 0)) != cudaSuccess) return e;  // Y(b-2): last writer of these columns, last reader of this window
+      const int cnt = own_count(s0);
+      if (cnt > 0) {
+        const TiledSym Pp = window(b - 1);
+        g.A = operand(Pp); g.B = operand(Pp); g.C = operand(Lown);
+        g.row_step = G; g.i0 = first_own(s0); g.j0 = s0; g.k0 = s0 - ob; g.k1 = s0;
+        if ((e = launch_gemm(X, GEMM_UPDATE, g, s1 - s0, cnt, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+        ctx->timings[6] += 1;
+      }
+    }
+    // exchange: every rank receives the whole block column into its window
+    const int slots = (nrows - s0 + G - 1) / G;
+    if ((e = launch_rowcyclic_pack(X, Lown, s0, s0 + ob, s0, nrows, G, me, slots, sendb)) != cudaSuccess) return e;
+    if (nccl_api().AllGather(sendb, recvb, (size_t)slots * ob * TT, NCCL_DOUBLE, ctx->comm_small ? ctx->comm_small : ctx->comm, X) != 0) {
+      ctx->dist_error = 1;
+      return cudaErrorUnknown;
+    }
+    if ((e = launch_rowcyclic_unpack(X, P, s0, s0 + ob, s0, nrows, G, -1, slots, recvb)) != cudaSuccess) return e;
+    ctx->launches += 2;
+    // the panel, on the window: every rank, all rows
+    g.A = operand(P); g.B = operand(P); g.C = operand(P);
+    g.row_step = 1;
+    bool factored_ahead = false;
+    for (int jj = s0; jj < s1; ++jj) {
+      if (!factored_ahead) {
+        if (jj > s0) {
+          g.i0 = jj; g.j0 = jj; g.k0 = s0; g.k1 = jj;
+          if ((e = launch_gemm(X, GEMM_UPDATE, g, 1, nrows - jj, 1)) != cudaSuccess) return e;
+          ++ctx->launches;
+        }
+        if ((e = launch_potrf_tile(X, P, W, wstride, jj, 1, logdet, info)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+      factored_ahead = false;
+      if (jj + 1 >= nrows) continue;
+      if (counters && jj + 1 < s1 && (ctx->chain_fused == 2 || nrows - 1 - jj <= 40)) {
+        if ((e = launch_chain_column(X, P, W, wstride, jj, s0, jj + 2, 1, 1, logdet, info, counters)) != cudaSuccess) return e;
+        ++ctx->launches;
+        factored_ahead = true;
+      } else {
+        g.i0 = jj + 1; g.j0 = jj;
+        if ((e = launch_gemm(X, GEMM_TRSM, g, 1, nrows - jj - 1, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+      }
+    }
+    if ((e = cudaEventRecord(evX[b], X)) != cudaSuccess) return e;
+    // trailing update of the own rows right of the NEXT block column (which X updates itself before its exchange)
+    const int s2 = s1 + ob;
+    if (s2 < nc) {
+      const int f2 = first_own(s2), cnt2 = own_count(s2);
+      if (cnt2 > 0) {
+        if ((e = cudaStreamWaitEvent(Y, evX[b], 0)) != cudaSuccess) return e;
+        GemmArgs t = g;
+        t.A = operand(P); t.B = operand(P); t.C = operand(Lown);
+        t.i0 = f2; t.j0 = s2; t.k0 = s0; t.k1 = s1; t.row_step = G;
+        if ((e = launch_gemm(Y, GEMM_UPDATE, t, nc - s2, cnt2, 1)) != cudaSuccess) return e;
+        ++ctx->launches;
+        ctx->timings[6] += 1;
+      }
+    }
+    if ((e = cudaEventRecord(evY[b], Y)) != cudaSuccess) return e;
+    // off the critical path (X, after the event the trailing update waits for): the finished rows go home, z is collected
+    if ((e = launch_tile_rows_copy(X, Lown, P, s0, s1, first_own(s0), G, nrows)) != cudaSuccess) return e;
+    ++ctx->launches;
+    if (zvec && nrows > nc) {
+      if ((e = launch_rhs_row_extract(X, P, nc, s0, s1, zvec)) != cudaSuccess) return e;
+      ++ctx->launches;
+    }
+  }
+  if ((e = cudaEventRecord(ctx->ev_join[1], X)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_join[0], Y)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
 // Fork the batch into latent groups on separate streams (joined back into ctx->stream).  jstart > 0: extend a factor whose
 // tile rows < jstart are final (see chol_factor_stream).
 cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int batch, double* logdet, int* info, int jstart) {

@@ -165,8 +165,70 @@ int ilmm_grad_chain(lmm_ctx* ctx, const GeneralProjection& gp, const std::vector
 
 // Returns LMM_OK, a positive pivot (PosDefException) or a negative error.  Stage timings [1] assemble,
 // [2] Cholesky, [3] solves are written to ctx->timings.
+// logpdf-only evaluation with the joint matrix DISTRIBUTED over the ranks (option "partition_ilmm" = 2): this rank assembles
+// and stores only the tile rows it owns (1/G of the matrix), the right-hand side rides along as one extra tile row, and
+// chol_factor_rowcyclic_dist leaves logdet (every rank) and z = L^{-1} δ (every rank) -- no full copy of the matrix
+// exists anywhere, so a joint dimension that does not fit one GPU runs.  Same outputs and stage timings as joint_factor.
+static int joint_factor_distributed(lmm_ctx* ctx, JointBuild& J, int* info) {
+  cudaStream_t st = ctx->stream;
+  const int G = ctx->nranks, me = ctx->rank, nc = J.bnt, nrows = nc + 1;
+  const size_t own_tiles = cyc_tiles(nrows, G, me);
+  const size_t ws_tiles = rowcyclic_dist_workspace_tiles(nrows, G, rowcyclic_dist_block(ctx, nc));
+  DevBuf b_z;
+  CU(J.L.alloc(ctx, (own_tiles > 0 ? own_tiles : 1) * TT * sizeof(double)));
+  CU(J.W.alloc(ctx, (size_t)nc * TT * sizeof(double)));
+  CU(J.logdet.alloc(ctx, sizeof(double)));
+  CU(J.info.alloc(ctx, sizeof(int)));
+  CU(J.quad.alloc(ctx, sizeof(double)));
+  CU(b_z.alloc(ctx, J.bpad * sizeof(double)));
+  CU(cudaMemsetAsync(J.logdet.p, 0, sizeof(double), st));
+  CU(cudaMemsetAsync(J.info.p, 0, sizeof(int), st));
+  TiledSym Lown{J.L.as<double>(), nc, 0};
+  Lown.cyc_G = G; Lown.cyc_r = me;
+  CU(cudaEventRecord(ctx->ev[1], st));
+  CU(launch_assemble_ilmm(st, Lown, J.x.as<double>(), J.N, J.D, J.params.as<LatentParams>(), J.m, J.q, J.E.as<double>(), J.H.as<double>(),
+                          J.mode, ctx->distance_form));
+  ++ctx->launches;
+  if (nc % G == me) {  // the owner of the extra tile row writes the right-hand side
+    CU(launch_rhs_row(st, Lown, nc, J.delta.as<double>()));
+    ++ctx->launches;
+  }
+  CU(cudaEventRecord(ctx->ev[2], st));
+  Lown.nt = nrows;
+  CU(chol_factor_rowcyclic_dist(ctx, Lown, nrows, nc, J.W.as<double>(), (size_t)nc * TT, J.logdet.as<double>(), J.info.as<int>(), b_z.as<double>()));
+  CU(cudaEventRecord(ctx->ev[3], st));
+  CU(launch_sumsq(st, b_z.as<double>(), J.bpad, (int)J.bpad, 1, J.quad.as<double>()));
+  ++ctx->launches;
+  int hinfo = 0;
+  CU(copy_out(ctx, &J.hlogdet, J.logdet.p, sizeof(double)));
+  CU(copy_out(ctx, &J.hquad, J.quad.p, sizeof(double)));
+  CU(copy_out(ctx, &hinfo, J.info.p, sizeof(int)));
+  CU(cudaEventRecord(ctx->ev[4], st));
+  CU(cudaStreamSynchronize(st));
+  {
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[4]);
+    cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&d, ctx->ev[3], ctx->ev[4]);
+    ctx->timings[0] = a; ctx->timings[1] = b; ctx->timings[2] = c; ctx->timings[3] = d;
+    // memory of this evaluation, in bytes: the matrix rows this rank holds, its exchange / window workspace, the whole matrix
+    const double tb = (double)TT * sizeof(double);
+    ctx->timings[4] = (double)own_tiles * tb; ctx->timings[5] = (double)ws_tiles * tb; ctx->timings[7] = (double)sym_tiles(nc) * tb;
+  }
+  if (hinfo > 0) {
+    if (info) *info = hinfo > J.big ? J.big : hinfo;
+    ctx->err = "PosDefException: the joint covariance is not positive definite";
+    return hinfo > J.big ? J.big : hinfo;
+  }
+  if (info) *info = 0;
+  return LMM_OK;
+}
+
 int joint_factor(lmm_ctx* ctx, JointBuild& J, bool want_alpha, int* info) {
   cudaStream_t st = ctx->stream;
+  if (!want_alpha && ctx->partition_ilmm == 2 && ctx->comm && ctx->nranks > 1 && J.bnt >= 2 * ctx->nranks && nccl_api().AllGather)
+    return joint_factor_distributed(ctx, J, info);
   CU(J.L.alloc(ctx, sym_tiles(J.bnt) * TT * sizeof(double)));
   CU(J.W.alloc(ctx, (size_t)J.bnt * TT * sizeof(double)));
   CU(J.logdet.alloc(ctx, sizeof(double)));

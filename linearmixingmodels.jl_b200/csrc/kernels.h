@@ -17,13 +17,24 @@ cudaError_t launch_kmat_cross(cudaStream_t st, TiledRect out, int batch, const d
 struct TileOperand {
   double* base;
   size_t batch_stride;  // doubles
-  int rect;             // 0: packed-lower tiles, 1: rectangular (row-major by tile, ntc tiles per row)
+  int rect;             // 0: packed-lower tiles, 1: rectangular (row-major by tile, ntc tiles per row; window origin row0 / col0),
+                        // 2: the rows one rank of a row-cyclic partition owns (cyc_tile_index)
   int ntc;
+  int row0 = 0, col0 = 0;
+  int cyc_G = 0, cyc_r = 0;
   __host__ __device__ __forceinline__ double* tile(int b, int I, int k) const {
-    return base + (size_t)b * batch_stride + (rect ? ((size_t)I * ntc + k) : sym_tile_index(I, k)) * TT;
+    size_t idx;
+    if (rect == 1) idx = (size_t)(I - row0) * (size_t)ntc + (size_t)(k - col0);
+    else if (rect == 2) idx = cyc_tile_index(I, k, cyc_G, cyc_r);
+    else idx = sym_tile_index(I, k);
+    return base + (size_t)b * batch_stride + idx * TT;
   }
 };
-inline TileOperand operand(const TiledSym& s) { return TileOperand{s.base, s.batch_stride, 0, s.nt}; }
+inline TileOperand operand(const TiledSym& s) {
+  if (s.ntc) return TileOperand{s.base, s.batch_stride, 1, s.ntc, s.row0, s.col0, 0, 0};
+  if (s.cyc_G) return TileOperand{s.base, s.batch_stride, 2, s.nt, 0, 0, s.cyc_G, s.cyc_r};
+  return TileOperand{s.base, s.batch_stride, 0, s.nt};
+}
 inline TileOperand operand(const TiledRect& r) { return TileOperand{r.base, r.batch_stride, 1, r.ntc}; }
 struct GemmArgs {
   TileOperand A;          // rows I of the left operand (UPDATE only)
@@ -82,6 +93,10 @@ cudaError_t launch_tile_from_dense(cudaStream_t st, TiledSym L, int batch, const
 cudaError_t launch_rowcyclic_pack(cudaStream_t st, TiledSym L, int s0, int s1, int ra, int rb, int G, int rank, int slots, double* buf);
 cudaError_t launch_rowcyclic_unpack(cudaStream_t st, TiledSym L, int s0, int s1, int ra, int rb, int G, int rank, int slots,
                                     const double* all);
+// distributed-storage variant (tiles addressed through the TiledSym window / cyclic views)
+cudaError_t launch_tile_rows_copy(cudaStream_t st, TiledSym dst, TiledSym src, int s0, int s1, int first, int step, int rows_end);
+cudaError_t launch_rhs_row(cudaStream_t st, TiledSym L, int I, const double* rhs);
+cudaError_t launch_rhs_row_extract(cudaStream_t st, TiledSym L, int I, int s0, int s1, double* z);
 
 // ---- proj.cu
 // Ty[i][n] = sum_j T[i + lat0][j] Y[j][n] - mean_i  (i < mloc), written to ty[i*ty_stride + n], zero padding to ty_stride

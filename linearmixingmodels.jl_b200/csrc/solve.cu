@@ -532,4 +532,47 @@ cudaError_t launch_rowcyclic_unpack(cudaStream_t st, TiledSym L, int s0, int s1,
   return cudaGetLastError();
 }
 
+
+// ---- distributed-storage row-cyclic factorisation (host_chol.cu: chol_factor_rowcyclic_dist) ----
+// dst(I, J) = src(I, J) for the tile rows I = first, first + step, ... < rows_end and the tile columns [s0, s1), J <= I:
+// the finished panel window -> the owner's packed rows.
+__global__ void __launch_bounds__(256) tile_rows_copy_kernel(TiledSym dst, TiledSym src, int s0, int first, int step, int rows_end) {
+  const int I = first + blockIdx.x * step, J = s0 + blockIdx.y;
+  if (I >= rows_end || J > I) return;
+  const double2* a = reinterpret_cast<const double2*>(src.tile(0, I, J));
+  double2* d = reinterpret_cast<double2*>(dst.tile(0, I, J));
+  for (int e = threadIdx.x; e < TT / 2; e += 256) d[e] = a[e];
+}
+cudaError_t launch_tile_rows_copy(cudaStream_t st, TiledSym dst, TiledSym src, int s0, int s1, int first, int step, int rows_end) {
+  if (first >= rows_end || s1 <= s0) return cudaSuccess;
+  dim3 grid((unsigned)((rows_end - 1 - first) / step + 1), (unsigned)(s1 - s0));
+  tile_rows_copy_kernel<<<grid, 256, 0, st>>>(dst, src, s0, first, step, rows_end);
+  return cudaGetLastError();
+}
+// The right-hand side as ONE extra tile row under the matrix: tile (I, J), J < I, holds rhs[J*128 ..] in its row 0 and zeros
+// below; the factorisation then leaves z = L^{-1} rhs in that row (the forward solve rides on the panel TRSMs).
+__global__ void __launch_bounds__(256) rhs_row_kernel(TiledSym L, int I, const double* __restrict__ rhs) {
+  const int J = blockIdx.x;
+  double* t = L.tile(0, I, J);
+  for (int e = threadIdx.x; e < TT; e += 256) {
+    int r, c;
+    tile_rc(e, r, c);
+    t[e] = (r == 0 && J < I) ? rhs[(size_t)J * TILE + c] : 0.0;
+  }
+}
+cudaError_t launch_rhs_row(cudaStream_t st, TiledSym L, int I, const double* rhs) {
+  rhs_row_kernel<<<(unsigned)(I + 1), 256, 0, st>>>(L, I, rhs);
+  return cudaGetLastError();
+}
+// z[J*128 + c] = row 0 of tile (I, J), J in [s0, s1)
+__global__ void __launch_bounds__(128) rhs_row_extract_kernel(TiledSym L, int I, int s0, double* __restrict__ z) {
+  const int J = s0 + blockIdx.x, c = threadIdx.x;
+  z[(size_t)J * TILE + c] = L.tile(0, I, J)[tile_elem(0, c)];
+}
+cudaError_t launch_rhs_row_extract(cudaStream_t st, TiledSym L, int I, int s0, int s1, double* z) {
+  if (s1 <= s0) return cudaSuccess;
+  rhs_row_extract_kernel<<<(unsigned)(s1 - s0), 128, 0, st>>>(L, I, s0, z);
+  return cudaGetLastError();
+}
+
 }  // namespace lmm

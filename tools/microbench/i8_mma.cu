@@ -1,0 +1,220 @@
+// tcgen05.mma kind::i8 on B200 (sm_100a): correctness of the hand-built shared-memory / instruction descriptors against a CPU
+// int32 reference, and the sustained issue rate of int8 MMAs (M = 128, N = 64 / 128 / 256, K = 32 per instruction) with operands
+// in the canonical K-major no-swizzle ("interleaved") shared-memory layout -- the building block of an integer-slice (Ozaki)
+// FP64 trailing update.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o i8_mma i8_mma.cu
+//
+// Operand tile in shared memory (R rows x 128 K-bytes, int8, K-major): core matrix = 8 rows x 16 bytes = 128 contiguous bytes;
+//     offset(r, k) = (k / 16) * (R / 8 * 128) + (r / 8) * 128 + (r % 8) * 16 + (k % 16)
+// i.e. SBO (stride between 8-row groups) = 128 B, LBO (stride between 16-byte K chunks) = R * 16 B.  One MMA consumes two K
+// chunks (K = 32); the next K step advances the descriptor's start address by 2 * LBO.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x)                                                                                  \
+  do {                                                                                         \
+    cudaError_t e_ = (x);                                                                      \
+    if (e_ != cudaSuccess) {                                                                   \
+      printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__);                  \
+      exit(1);                                                                                 \
+    }                                                                                          \
+  } while (0)
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
+  // c_format S32 = 2 @ [4,6); a_format signed = 1 @ [7,10); b_format signed = 1 @ [10,13); K-major both; n_dim = N >> 3 @ [17,23);
+  // m_dim = M >> 4 @ [24,29)
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
+  return d;                // layout_type 0 = no swizzle, base_offset 0
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(s_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128, 1) i8_mma_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int32_t* __restrict__ D,
+                                                        int reps, int nacc, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;               // 128 x 128 bytes
+  uint8_t* sB = smem + 128 * 128;   // N x 128 bytes
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * 128 / 16; i += 128) reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(A)[i];
+  for (int i = tid; i < N * 128 / 16; i += 128) reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(B)[i];
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  constexpr uint32_t idesc = make_idesc_i8(128, N);
+  const uint32_t a0 = s_u32(sA), b0 = s_u32(sB);
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) {
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const uint32_t dcol = (uint32_t)((r % nacc) * N);  // accumulator r % nacc
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = make_sdesc(a0 + ks * 2 * (128 * 16), 128 * 16, 128);
+        const uint64_t bd = make_sdesc(b0 + ks * 2 * (N * 16), N * 16, 128);
+        mma_i8(tmem + dcol, ad, bd, idesc, (r >= nacc || ks > 0) ? 1u : 0u);
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) {
+    t1 = clock64();
+    if (cycles) cycles[blockIdx.x] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // accumulator 0 -> global (block 0 only): warp w reads TMEM lanes 32w .. 32w+31 (= rows), 32 columns per load
+  if (D && blockIdx.x == 0) {
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+          "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+            "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 32; ++j) D[(size_t)tid * N + c0 + j] = (int32_t)v[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+static size_t canon(int R, int r, int k) { return (size_t)(k / 16) * (R / 8 * 128) + (size_t)(r / 8) * 128 + (r % 8) * 16 + (k % 16); }
+
+template <int N>
+static int run(int sms, double clock_ghz) {
+  std::vector<int8_t> hA(128 * 128), hB((size_t)N * 128), cA(128 * 128), cB((size_t)N * 128);
+  srand(7 + N);
+  for (auto& v : hA) v = (int8_t)(rand() % 129 - 64);
+  for (auto& v : hB) v = (int8_t)(rand() % 129 - 64);
+  for (int r = 0; r < 128; ++r)
+    for (int k = 0; k < 128; ++k) cA[canon(128, r, k)] = hA[r * 128 + k];
+  for (int r = 0; r < N; ++r)
+    for (int k = 0; k < 128; ++k) cB[canon(N, r, k)] = hB[r * 128 + k];
+  int8_t *dA, *dB;
+  int32_t* dD;
+  long long* dC;
+  CK(cudaMalloc(&dA, cA.size()));
+  CK(cudaMalloc(&dB, cB.size()));
+  CK(cudaMalloc(&dD, (size_t)128 * N * 4));
+  CK(cudaMalloc(&dC, 1024 * sizeof(long long)));
+  CK(cudaMemcpy(dA, cA.data(), cA.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, cB.data(), cB.size(), cudaMemcpyHostToDevice));
+  const size_t smem = 128 * 128 + (size_t)N * 128;
+  CK(cudaFuncSetAttribute(i8_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // ---- correctness: one pass (4 MMAs, K = 128) into accumulator 0
+  i8_mma_kernel<N><<<1, 128, smem>>>(dA, dB, dD, 1, 1, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> hD((size_t)128 * N);
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+  long long bad = 0;
+  for (int i = 0; i < 128; ++i)
+    for (int j = 0; j < N; ++j) {
+      int32_t s = 0;
+      for (int k = 0; k < 128; ++k) s += (int32_t)hA[i * 128 + k] * (int32_t)hB[j * 128 + k];
+      if (s != hD[(size_t)i * N + j]) {
+        if (bad < 4) printf("  mismatch N=%d (%d,%d): got %d want %d\n", N, i, j, hD[(size_t)i * N + j], s);
+        ++bad;
+      }
+    }
+  printf("{\"test\": \"i8_mma_correct\", \"M\": 128, \"N\": %d, \"K\": 128, \"mismatches\": %lld}\n", N, bad);
+  // ---- accumulate check: 3 passes into one accumulator = 3x
+  i8_mma_kernel<N><<<1, 128, smem>>>(dA, dB, dD, 3, 1, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> hD3((size_t)128 * N);
+  CK(cudaMemcpy(hD3.data(), dD, hD3.size() * 4, cudaMemcpyDeviceToHost));
+  long long bad3 = 0;
+  for (size_t i = 0; i < hD.size(); ++i) bad3 += (hD3[i] != 3 * hD[i]);
+  printf("{\"test\": \"i8_mma_accumulate\", \"N\": %d, \"mismatches\": %lld}\n", N, bad3);
+  // ---- rate: reps passes of 4 MMAs round-robin over nacc accumulators; 1 CTA alone, then one CTA per SM
+  const int nacc = 512 / N;
+  for (int grid : {1, sms}) {
+    const int reps = 4096;
+    i8_mma_kernel<N><<<grid, 128, smem>>>(dA, dB, nullptr, 64, nacc, dC);  // warm-up
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    i8_mma_kernel<N><<<grid, 128, smem>>>(dA, dB, nullptr, reps, nacc, dC);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> hc(grid);
+    CK(cudaMemcpy(hc.data(), dC, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long cmax = 0;
+    for (long long c : hc) cmax = c > cmax ? c : cmax;
+    const double macs = (double)reps * 4 * 128.0 * N * 32;
+    printf("{\"test\": \"i8_mma_rate\", \"N\": %d, \"ctas\": %d, \"mma_per_cta\": %d, \"cycles_per_mma\": %.2f, \"mac_per_clk_per_sm\": %.1f, "
+           "\"smem_bytes_per_clk\": %.1f, \"ms\": %.3f, \"total_tops\": %.1f}\n",
+           N, grid, reps * 4, (double)cmax / (reps * 4), macs / (double)cmax, (double)reps * 4 * (128 + N) * 32 / (double)cmax, ms,
+           2.0 * macs * grid / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
+  return bad == 0 && bad3 == 0;
+}
+
+int main() {
+  cudaDeviceProp pr;
+  CK(cudaGetDeviceProperties(&pr, 0));
+  printf("{\"device\": \"%s\", \"sms\": %d, \"cc\": \"%d.%d\"}\n", pr.name, pr.multiProcessorCount, pr.major, pr.minor);
+  int ok = 1;
+  ok &= run<64>(pr.multiProcessorCount, 0);
+  ok &= run<128>(pr.multiProcessorCount, 0);
+  ok &= run<256>(pr.multiProcessorCount, 0);
+  printf("{\"all_correct\": %s}\n", ok ? "true" : "false");
+  return ok ? 0 : 1;
+}
