@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--N", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the untimed multi-GPU records (row-cyclic ILMM factor, config-5 sweep)")
+    ap.add_argument("--ozaki", type=int, default=0, help="integer-slice (int8 tcgen05) trailing update with this many digit planes (6/7/8); 0 = DMMA (default)")
     ap.add_argument("--streams", type=int, default=0, help="latent groups on separate CUDA streams (0 = library default)")
     args = ap.parse_args()
     p, m, N = args.p, args.m, args.N
@@ -324,6 +325,8 @@ def main():
         lmm.dist.init_context_distributed(ctx)
     if args.streams > 0:
         ctx.set_option("streams", args.streams)
+    if args.ozaki:
+        ctx.set_option("ozaki", args.ozaki)
 
     x, U, S, inv_ls, y, s2 = workload(p, m, N)
     H = lmm.Orthogonal(U, S)

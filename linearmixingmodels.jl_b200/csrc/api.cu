@@ -184,6 +184,8 @@ extern "C" int lmm_ctx_destroy(lmm_ctx* ctx) {
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& g : ctx->gstream) cudaStreamDestroy(g);
   if (ctx->xbuf) cudaFree(ctx->xbuf);
+  if (ctx->oz_slices) cudaFree(ctx->oz_slices);
+  if (ctx->oz_scale) cudaFree(ctx->oz_scale);
   cudaStreamDestroy(ctx->panel_stream);
   cudaStreamDestroy(ctx->update_stream);
   for (auto& e : ctx->blk_ev) cudaEventDestroy(e);
@@ -229,6 +231,12 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "partition_ilmm") {
     if (value != 0.0 && value != 1.0 && value != 2.0) return ctx->fail(LMM_E_ARG, "partition_ilmm must be 0, 1 or 2");
     ctx->partition_ilmm = (int)value;
+  } else if (k == "ozaki") {
+    if (value != 0.0 && value != 6.0 && value != 7.0 && value != 8.0) return ctx->fail(LMM_E_ARG, "ozaki must be 0 (DMMA) or 6, 7, 8 (int8 digit planes)");
+    ctx->ozaki = (int)value;
+  } else if (k == "ozaki_min_k") {
+    if (value < 1 || value > 4096) return ctx->fail(LMM_E_ARG, "ozaki_min_k must be in [1, 4096]");
+    ctx->ozaki_min_k = (int)value;
   } else if (k == "gemm_small") {
     if (value < 0 || value > 4096) return ctx->fail(LMM_E_ARG, "gemm_small must be in [0, 4096]");
     set_gemm_small_threshold((int)value);

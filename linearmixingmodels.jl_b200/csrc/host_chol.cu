@@ -32,9 +32,24 @@ static cudaError_t chain_counters(lmm_ctx* ctx, cudaStream_t st, int nt, int bat
 // shared-memory-free GEMM roles at one CTA per SM) instead of TMA-pipelined launches per operation.
 constexpr int CHAIN_MAX_TILES = 96;
 
+// Workspace of the optional integer-slice (Ozaki) trailing update for the latents [0, batch) of one chol_factor_stream call.
+struct OzWs {
+  uint8_t* slices;
+  size_t slice_stride;  // bytes per latent
+  double* scale;
+  size_t scale_stride;  // doubles per latent
+  int S, min_k;
+};
+
 cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double* W, size_t wstride, int batch, double* logdet,
-                               int* info, int jstart = 0, int* counters = nullptr) {
+                               int* info, int jstart = 0, int* counters = nullptr, const OzWs* oz = nullptr) {
   const int nt = L.nt, ob = ctx->outer_block;
+  if (oz && (jstart != 0 || nt <= ob || nt < oz->min_k + 1)) oz = nullptr;  // no wide update this scheme would take
+  if (oz) {
+    cudaError_t eo = launch_ozaki_scales(st, L, batch, oz->scale, oz->scale_stride);  // reads the diagonal BEFORE it is factored
+    if (eo != cudaSuccess) return eo;
+    ++ctx->launches;
+  }
   GemmArgs g{};
   g.A = operand(L);
   g.B = operand(L);
@@ -49,7 +64,12 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
     if (s0 > 0) {
       const int r0 = s0 > jstart ? s0 : jstart;  // first tile row that still has to be computed
       g.i0 = r0; g.j0 = s0; g.k0 = 0; g.k1 = s0;
-      if ((e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, nt - r0, batch)) != cudaSuccess) return e;
+      // exact int32 accumulation needs S * K * 64^2 < 2^31
+      if (oz && s0 >= oz->min_k && (long long)s0 * TILE * oz->S * 4096 < (1ll << 31))
+        e = launch_ozaki_update(st, L, oz->slices, oz->slice_stride, oz->scale, oz->scale_stride, r0, nt - r0, s0, s1 - s0, s0, batch, oz->S);
+      else
+        e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, nt - r0, batch);
+      if (e != cudaSuccess) return e;
       ++ctx->launches;
       ctx->timings[6] += 1;
     }
@@ -81,8 +101,53 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
       if ((e = launch_gemm(st, GEMM_TRSM, g, 1, nt - t0, batch)) != cudaSuccess) return e;
       ++ctx->launches;
     }
+    if (oz && s1 < nt) {  // the block column is final: digit planes of its tiles below the block, for the later wide updates
+      if ((e = launch_ozaki_slice(st, L, oz->scale, oz->scale_stride, oz->slices, oz->slice_stride, s1, nt - s1, s0, s1 - s0, batch, oz->S)) !=
+          cudaSuccess)
+        return e;
+      ++ctx->launches;
+    }
   }
   return cudaSuccess;
+}
+
+// Grow the context's Ozaki workspace for up to `batch` latents of nt tile rows; returns how many latents fit (0: none -- stay on
+// DMMA).  One cudaMemGetInfo / cudaMalloc when the shape grows, nothing afterwards.
+static int ozaki_workspace(lmm_ctx* ctx, int nt, int batch, OzWs& ws) {
+  const size_t per_slices = sym_tiles(nt) * (size_t)ctx->ozaki * 16384, per_scale = (size_t)nt * TILE;
+  size_t have = per_slices ? ctx->oz_slices_bytes / per_slices : 0;
+  if (have < (size_t)batch) {
+    cudaStreamSynchronize(ctx->stream);  // the old buffer may still be in use by work queued earlier
+    if (ctx->oz_slices) cudaFree(ctx->oz_slices);
+    ctx->oz_slices = nullptr;
+    ctx->oz_slices_bytes = 0;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    const size_t reserve = (size_t)6 << 30;  // leave room for the caller's later allocations (solves, predictions)
+    size_t fit = free_b > reserve ? (free_b - reserve) / per_slices : 0;
+    if (fit > (size_t)batch) fit = (size_t)batch;
+    if (fit == 0) return 0;
+    if (cudaMalloc(&ctx->oz_slices, fit * per_slices) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    ctx->oz_slices_bytes = fit * per_slices;
+    have = fit;
+  }
+  if (have > (size_t)batch) have = (size_t)batch;
+  if (ctx->oz_scale_bytes < have * per_scale * sizeof(double)) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->oz_scale) cudaFree(ctx->oz_scale);
+    ctx->oz_scale = nullptr;
+    ctx->oz_scale_bytes = 0;
+    if (cudaMalloc(&ctx->oz_scale, have * per_scale * sizeof(double)) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    ctx->oz_scale_bytes = have * per_scale * sizeof(double);
+  }
+  ws = OzWs{(uint8_t*)ctx->oz_slices, per_slices, ctx->oz_scale, per_scale, ctx->ozaki, ctx->ozaki_min_k};
+  return (int)have;
 }
 
 // Trailing update of the columns >= s2 (tile rows first_row, first_row + row_step, ... < nt) by the k-tiles [k0, k1): ONE
@@ -458,20 +523,45 @@ cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int
     if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
   }
   cudaError_t e;
+  // optional integer-slice trailing update: workspace for as many latents as fit; a larger batch is factored in chunks
+  OzWs ozws{};
+  const OzWs* oz = nullptr;
+  if (ctx->ozaki && jstart == 0 && L.nt > ctx->outer_block && L.nt > ctx->ozaki_min_k && L.ntc == 0 && L.cyc_G == 0) {
+    const int fit = ozaki_workspace(ctx, L.nt, batch, ozws);
+    if (fit > 0) {
+      oz = &ozws;
+      if (fit < batch) {
+        for (int c0 = 0; c0 < batch; c0 += fit) {
+          const int cb = batch - c0 < fit ? batch - c0 : fit;
+          TiledSym Lc{L.base + (size_t)c0 * L.batch_stride, L.nt, L.batch_stride};
+          if ((e = chol_factor(ctx, Lc, W + (size_t)c0 * wstride, wstride, cb, logdet + c0, info + c0, 0)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+      }
+    }
+  }
+  auto oz_at = [&](int b0, OzWs& tmp) -> const OzWs* {
+    if (!oz) return nullptr;
+    tmp = *oz;
+    tmp.slices += (size_t)b0 * oz->slice_stride;
+    tmp.scale += (size_t)b0 * oz->scale_stride;
+    return &tmp;
+  };
   // small grids (few latents x few tile rows, e.g. the reference's notebook shape: 20 latents, 5 tile columns): ONE stream,
   // one fused launch per tile column -- stream groups would only multiply the launches
   int* counters = nullptr;
   const bool chain_all = ctx->chain_fused && (long long)(L.nt - 1) * batch <= CHAIN_MAX_TILES && L.nt > 1;
   if (ctx->chain_fused && L.nt > 1 && (e = chain_counters(ctx, ctx->stream, L.nt, batch, &counters)) != cudaSuccess) return e;
-  if (G <= 1 || L.nt <= 1 || chain_all) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info, jstart, counters);
+  if (G <= 1 || L.nt <= 1 || chain_all) return chol_factor_stream(ctx, ctx->stream, L, W, wstride, batch, logdet, info, jstart, counters, oz);
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
   for (int gi = 0; gi < G; ++gi) {
     const int b0 = (int)((int64_t)batch * gi / G), b1 = (int)((int64_t)batch * (gi + 1) / G);
     cudaStream_t st = ctx->gstream[gi];
     if ((e = cudaStreamWaitEvent(st, ctx->ev_fork, 0)) != cudaSuccess) return e;
     TiledSym Lg{L.base + (size_t)b0 * L.batch_stride, L.nt, L.batch_stride};
+    OzWs oztmp{};
     if ((e = chol_factor_stream(ctx, st, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0, logdet + b0, info + b0, jstart,
-                                counters ? counters + (size_t)b0 * chain_counter_ints(L.nt) : nullptr)) != cudaSuccess)
+                                counters ? counters + (size_t)b0 * chain_counter_ints(L.nt) : nullptr, oz_at(b0, oztmp))) != cudaSuccess)
       return e;
     if ((e = cudaEventRecord(ctx->ev_join[gi], st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[gi], 0)) != cudaSuccess) return e;

@@ -81,6 +81,13 @@ struct lmm_ctx {
   int condition_update = 1;  // sequential conditioning of per-latent posteriors: 1 = block-Cholesky update of the factor, 0 = re-factorise the union
   int partition_now = 0;  // set by the callers whose factorisation is replicated on every rank (ILMM joint factor)
   int dist_error = 0;  // NCCL failure inside the partitioned schedule (reported by the caller)
+  // integer-slice (Ozaki) trailing update on the int8 tensor cores: 0 = off (DMMA, default), 6 / 7 / 8 = digit planes
+  int ozaki = 0;
+  int ozaki_min_k = 8;        // wide updates over fewer k-tiles stay on DMMA (the int8 epilogue is per output tile, not per k)
+  void* oz_slices = nullptr;  // [latents in flight][sym_tiles][S * 16 KB], grown on demand
+  size_t oz_slices_bytes = 0;
+  double* oz_scale = nullptr;
+  size_t oz_scale_bytes = 0;
   void* xbuf = nullptr;  // exchange buffers of the row-cyclic schedule (send | all-gathered), grown on demand
   size_t xbuf_bytes = 0;
 

@@ -1,0 +1,312 @@
+// Integer-slice (Ozaki-scheme) FP64 trailing update on the int8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) -- the
+// one route past the native FP64 pipe (DMMA: 37 TFLOP/s) the batched Cholesky already saturates.
+// OPTIONAL ("ozaki" = 6 / 7 / 8 slices; default 0 = DMMA, which stays the reference path).  Replaces, for the WIDE left-looking
+// update of a block column only, the dsyrk/dgemm LAPACK's dpotrf makes under `cholesky(Symmetric(C))` (src/oilmm.jl:90,128 via
+// AbstractGPs):      C(I,J) -= sum_{k < s0} L(I,k) L(J,k)'         (128 x 128 tiles, K = 128 per k-tile)
+//
+// Every finished row i of L is written as  L(i,k) = 2^E_i * sum_{t < S} q_t(i,k) 2^(-6-7t)  with int8 digits |q_t| <= 64 and ONE
+// exponent per row of the whole matrix: |L(i,k)| <= sqrt(A_ii) < 2^E_i (row i of L has 2-norm sqrt(A_ii)), so E_i is known from the
+// diagonal before the factorisation starts and all k-tiles of a row share it -- integer partial sums can then be accumulated
+// over the whole K range.  Digit extraction is exact (scaling by powers of two, round-to-nearest, exact remainders).  Then
+//     L(i,:) . L(j,:) = 2^(E_i+E_j-12) * sum_d 2^(-7d) * [ sum_{t+u=d} sum_k q_t(i,k) q_u(j,k) ]          d = 0 .. S-1
+// where every bracket is an EXACT int32 sum on the tensor cores ((d+1) * K * 64^2 < 2^31 for K <= 65536 / (d+1): K <= 8192 columns at
+// d = 7... checked on the host: K * (d+1) * 4096 < 2^31) and the dropped terms (t + u >= S) are below 2^(-7S-5) * K of the row
+// scales: S = 8 truncates at 2^-56 -- the same normwise bound |dC| <= c eps |L||L|' an FP64 GEMM has, with eps = 2^-53.
+// S(S+1)/2 = 36 int8 MMAs replace one FP64 tile product: 36 * 4 * 71 clk = 10.2 k clk against 32.8 k clk of DMMA
+// (profiles/r02_i8_mma.jsonl: M = 128, N = 128, K = 32 issues every 71 clk).
+//
+// Kernel (one CTA = one 128 x 128 output tile, 6 warps): warp 4 = producer (1-D TMA bulk copies of int8 slices into a 3-stage
+// ring), warp 5 = MMA issuer (one thread), warps 0-3 = epilogue (TMEM -> registers -> C).  TMEM holds four 128-column int32
+// accumulators (all 512 columns), one per d, so the K range is swept twice: pass A for d = 0..3 (needs slices 0..3 of both
+// operands), pass B for d = 4..S-1 (all slices); after each pass the epilogue converts (exact int32 -> double), combines by
+// Horner in 2^-7, scales by the row / column exponents and subtracts from C.
+// HBM layout of the sliced tile (I,k) (S * 16 KB, at sym_tile_index(I,k) * S * 16384 bytes): [K quarter kq][slice t][4096 B], the
+// 4096 B being the canonical K-major no-swizzle UMMA operand of 128 rows x 32 K-bytes: [16-byte K chunk (2)][row (128)][16 B]
+// (core matrix = 8 rows x 16 B contiguous; LBO = 2048, SBO = 128) -- a bulk copy lands it in shared memory ready for the MMA.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace lmm {
+
+constexpr int OZ_QB = 4096;                    // bytes of one slice of one K quarter (128 rows x 32 K-bytes)
+constexpr int OZ_RING_BYTES = 192 * 1024;      // pass A: 6 stages of 2 x 4 slices (32 KB), pass B: 3 stages of 2 x 8 slices (64 KB)
+constexpr int OZ_STAGES_A = 6, OZ_STAGES_B = 3;
+constexpr size_t OZ_SMEM = (size_t)OZ_RING_BYTES + 2048;  // + alignment slack, barriers, column scales
+
+__device__ __forceinline__ uint32_t oz_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void oz_mb_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void oz_mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(oz_s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_mb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(oz_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_mb_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(oz_s32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 28)) __trap();  // never hang the GPU on a protocol bug
+  }
+}
+__device__ __forceinline__ void oz_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(oz_s32(dst)), "l"(src),
+               "r"(bytes), "r"(oz_s32(bar))
+               : "memory");
+}
+// instruction descriptor of tcgen05.mma kind::i8: D = S32 (2 @ bit 4), A / B signed int8 (1 @ bits 7 / 10), both K-major,
+// N >> 3 @ bit 17, M >> 4 @ bit 24
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// shared-memory matrix descriptor: start address >> 4, LBO >> 4 @ 16 (between the two 16-byte K chunks of one MMA), SBO >> 4 @ 32
+// (between 8-row groups), descriptor version 1 @ 46, no swizzle
+__device__ __forceinline__ uint64_t oz_sdesc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_s32(bar)) : "memory");
+}
+__device__ __forceinline__ double oz_i2d(uint32_t v) {  // exact int32 -> double: 2^52 + 2^31 + v as a bit pattern, one DADD
+  return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+struct OzakiArgs {
+  const uint8_t* slices;      // sliced factor [batch][sym_tiles][S * 16384]
+  size_t slice_batch_stride;  // bytes
+  const double* scale;        // [batch][npad]: 2^(E_row - 6)
+  size_t scale_batch_stride;  // doubles
+  TileOperand C;
+  int i0, j0, k1;             // tile (I, J) = (i0 + blockIdx.y, j0 + blockIdx.x); k-tiles [0, k1)
+  int S;                      // slices (6, 7 or 8)
+};
+
+__global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
+  extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
+  const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
+  if (I < J) return;
+  // 1024-aligned carve-up: stages, then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 127) & ~(uintptr_t)127);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_RING_BYTES);
+  // each pass has its own ring geometry and its own barriers: [pass][full 0..5 | empty 0..5]
+  uint64_t* acc_full = bars + 24;              // MMAs of the current pass complete
+  uint64_t* acc_empty = acc_full + 1;          // epilogue of pass A has drained TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  double* colscale = reinterpret_cast<double*>(bars + 32);  // [128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = g.S;
+  if (tid == 0) {
+    for (int s = 0; s < 24; ++s) oz_mb_init(&bars[s], 1);
+    oz_mb_init(acc_full, 1);
+    oz_mb_init(acc_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(oz_s32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < 128) colscale[tid] = g.scale[(size_t)b * g.scale_batch_stride + (size_t)J * TILE + tid];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const size_t tile_bytes = (size_t)S * 16384;
+  const int nq = g.k1 * 4;  // K quarters per pass
+  const int nsA = S < 4 ? S : 4;
+
+  if (warp == 4) {
+    // ===== producer: per K quarter one bulk copy of the needed slices of A(I,k) and one of B(J,k)
+    if (lane == 0) {
+      const uint8_t* Abase = g.slices + (size_t)b * g.slice_batch_stride + sym_tile_index(I, 0) * tile_bytes;
+      const uint8_t* Bbase = g.slices + (size_t)b * g.slice_batch_stride + sym_tile_index(J, 0) * tile_bytes;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int ns = pass ? S : nsA;
+        if (pass && S <= 4) break;
+        const int nst = pass ? OZ_STAGES_B : OZ_STAGES_A;
+        const uint32_t half = (uint32_t)(pass ? 8 : 4) * OZ_QB, bytes = (uint32_t)ns * OZ_QB;
+        uint64_t* full = bars + 12 * pass;
+        uint64_t* empty = full + 6;
+        if (pass) oz_mb_wait(acc_full, 0);  // every MMA of pass A has read its stage: the ring can change geometry
+        for (int kq = 0; kq < nq; ++kq) {
+          const int s = kq % nst;
+          oz_mb_wait(&empty[s], ((kq / nst) & 1) ^ 1);
+          uint8_t* st = smem + (size_t)s * (2 * half);
+          oz_mb_expect_tx(&full[s], 2 * bytes);
+          const size_t off = (size_t)(kq >> 2) * tile_bytes + (size_t)(kq & 3) * S * OZ_QB;
+          oz_bulk_load(st, Abase + off, bytes, &full[s]);
+          oz_bulk_load(st + half, Bbase + off, bytes, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer: accumulator d - dlo at TMEM columns (d - dlo) * 128
+    if (lane == 0) {
+      for (int pass = 0; pass < 2; ++pass) {
+        const int ns = pass ? S : nsA;
+        const int dlo = pass ? 4 : 0, dhi = pass ? S - 1 : nsA - 1;
+        if (pass && S <= 4) break;
+        const int nst = pass ? OZ_STAGES_B : OZ_STAGES_A;
+        const uint32_t half = (uint32_t)(pass ? 8 : 4) * OZ_QB;
+        uint64_t* full = bars + 12 * pass;
+        uint64_t* empty = full + 6;
+        if (pass) {
+          oz_mb_wait(acc_empty, 0);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        uint32_t started = 0;  // bit d - dlo: the accumulator has received its first MMA of this pass
+        for (int kq = 0; kq < nq; ++kq) {
+          const int s = kq % nst;
+          oz_mb_wait(&full[s], (kq / nst) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = oz_s32(smem + (size_t)s * (2 * half)), sb = sa + half;
+          for (int d = dlo; d <= dhi; ++d) {
+            const int tlo = d - (ns - 1) > 0 ? d - (ns - 1) : 0, thi = d < ns - 1 ? d : ns - 1;
+            for (int t = tlo; t <= thi; ++t) {
+              const int u = d - t;
+              oz_mma(tmem + (uint32_t)(d - dlo) * 128u, oz_sdesc(sa + (uint32_t)t * OZ_QB), oz_sdesc(sb + (uint32_t)u * OZ_QB),
+                     (started >> (d - dlo)) & 1u);
+              started |= 1u << (d - dlo);
+            }
+          }
+          oz_commit(&empty[s]);  // the stage is free once these MMAs have read it
+        }
+        oz_commit(acc_full);
+      }
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes / tile rows 32w .. 32w + 31
+    const int r = warp * 32 + lane;
+    const double rs = g.scale[(size_t)b * g.scale_batch_stride + (size_t)I * TILE + r];
+    double* Ctile = g.C.tile(b, I, J);
+    for (int pass = 0; pass < 2; ++pass) {
+      const int dlo = pass ? 4 : 0, dhi = pass ? S - 1 : nsA - 1;
+      if (pass && S <= 4) break;
+      const int nd = dhi - dlo + 1;
+      oz_mb_wait(acc_full, (uint32_t)pass);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const double ps = pass ? rs * 3.7252902984619140625e-09 : rs;  // 2^-28: pass B starts at d = 4
+      for (int c0 = 0; c0 < 128; c0 += 8) {
+        uint32_t v[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          if (a < nd) {
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 128 + c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(v[a][0]), "=r"(v[a][1]), "=r"(v[a][2]), "=r"(v[a][3]), "=r"(v[a][4]), "=r"(v[a][5]), "=r"(v[a][6]), "=r"(v[a][7])
+                         : "r"(taddr)
+                         : "memory");
+          }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // two groups of 4 columns = two 32-byte runs of the k4-interleaved tile
+          const int c = c0 + 4 * h;
+          double2* cp = reinterpret_cast<double2*>(Ctile + tile_elem(r, c));
+          double2 x0 = cp[0], x1 = cp[1];
+          double o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int a = 3; a >= 0; --a)
+              if (a < nd) acc = fma(acc, 0.0078125, oz_i2d(v[a][4 * h + j]));
+            o[j] = acc * (ps * colscale[c + j]);
+          }
+          x0.x -= o[0]; x0.y -= o[1]; x1.x -= o[2]; x1.y -= o[3];
+          cp[0] = x0; cp[1] = x1;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (pass == 0) oz_mb_arrive(acc_empty);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---- row exponents from the diagonal of the matrix that is about to be factored: scale = 2^(E - 6), 2^E > sqrt(A_ii)
+__global__ void __launch_bounds__(128) ozaki_scale_kernel(TiledSym L, double* __restrict__ scale, size_t scale_batch_stride) {
+  const int I = blockIdx.x, b = blockIdx.y, r = threadIdx.x;
+  const double a = L.tile(b, I, I)[tile_elem(r, r)];
+  int e = 0;
+  if (a > 0.0 && a < 1e300) e = ilogb(sqrt(a)) + 1;
+  scale[(size_t)b * scale_batch_stride + (size_t)I * TILE + r] = scalbn(1.0, e - 6);
+}
+
+// ---- slice the finished tiles (I, k), I in [i0, i0 + gridDim.y), k in [k0, k0 + gridDim.x): 256 threads, thread = (row, 16 columns)
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(TiledSym L, const double* __restrict__ scale, size_t scale_batch_stride,
+                                                          uint8_t* __restrict__ slices, size_t slice_batch_stride, int i0, int k0, int S) {
+  const int k = k0 + blockIdx.x, I = i0 + blockIdx.y, b = blockIdx.z;
+  const double* tile = L.tile(b, I, k);
+  uint8_t* out = slices + (size_t)b * slice_batch_stride + sym_tile_index(I, k) * ((size_t)S * 16384);
+  for (int it = threadIdx.x; it < 1024; it += 256) {
+    const int r = it & 127, c16 = it >> 7;  // 16 columns c16*16 .. +15 of row r
+    const double inv = 1.0 / scale[(size_t)b * scale_batch_stride + (size_t)I * TILE + r];  // 2^(6 - E): exact
+    double y[16];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      const double2* p = reinterpret_cast<const double2*>(tile + (size_t)(4 * c16 + gq) * 512 + 4 * r);
+      const double2 a = p[0], c = p[1];
+      y[4 * gq + 0] = a.x * inv; y[4 * gq + 1] = a.y * inv; y[4 * gq + 2] = c.x * inv; y[4 * gq + 3] = c.y * inv;
+    }
+    uint8_t* dst = out + (size_t)(c16 >> 1) * S * OZ_QB + (size_t)(c16 & 1) * 2048 + (size_t)r * 16;
+    for (int t = 0; t < S; ++t) {
+      uint32_t w[4];
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        uint32_t pk = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double& v = y[4 * gq + j];
+          double q = rint(v);
+          q = fmin(fmax(q, -127.0), 127.0);
+          v = (v - q) * 128.0;
+          pk |= ((uint32_t)(__double2int_rn(q)) & 0xFFu) << (8 * j);
+        }
+        w[gq] = pk;
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)t * OZ_QB) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+cudaError_t launch_ozaki_scales(cudaStream_t st, TiledSym L, int batch, double* scale, size_t scale_batch_stride) {
+  ozaki_scale_kernel<<<dim3((unsigned)L.nt, (unsigned)batch), 128, 0, st>>>(L, scale, scale_batch_stride);
+  return cudaGetLastError();
+}
+cudaError_t launch_ozaki_slice(cudaStream_t st, TiledSym L, const double* scale, size_t scale_batch_stride, uint8_t* slices,
+                               size_t slice_batch_stride, int i0, int nrows, int k0, int ncols, int batch, int S) {
+  if (nrows <= 0 || ncols <= 0 || batch <= 0) return cudaSuccess;
+  ozaki_slice_kernel<<<dim3((unsigned)ncols, (unsigned)nrows, (unsigned)batch), 256, 0, st>>>(L, scale, scale_batch_stride, slices,
+                                                                                            slice_batch_stride, i0, k0, S);
+  return cudaGetLastError();
+}
+cudaError_t launch_ozaki_update(cudaStream_t st, TiledSym L, const uint8_t* slices, size_t slice_batch_stride, const double* scale,
+                                size_t scale_batch_stride, int i0, int nrows, int j0, int ncols, int k1, int batch, int S) {
+  if (nrows <= 0 || ncols <= 0 || batch <= 0 || k1 <= 0) return cudaSuccess;
+  static bool configured_dev[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& configured = configured_dev[dev & 63];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ozaki_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  OzakiArgs a{slices, slice_batch_stride, scale, scale_batch_stride, operand(L), i0, j0, k1, S};
+  ozaki_update_kernel<<<dim3((unsigned)ncols, (unsigned)nrows, (unsigned)batch), 192, OZ_SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace lmm
