@@ -170,6 +170,11 @@ extern "C" int lmm_ctx_create(int device, lmm_ctx** out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
+  // LMM_OZAKI=6|7|8: start with the integer-slice trailing update switched on (runs a whole test suite / application on it unchanged)
+  if (const char* oz = getenv("LMM_OZAKI")) {
+    const int v = atoi(oz);
+    if (v == 6 || v == 7 || v == 8) ctx->ozaki = v;
+  }
   *out = ctx;
   return LMM_OK;
 }

@@ -81,6 +81,22 @@ __device__ __forceinline__ double oz_i2d(uint32_t v) {  // exact int32 -> double
   return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
 }
 
+// The MMAs of one K quarter (K = 32) of one pass, fully unrolled: the issuing thread must not spend more than the ~71 clk an MMA
+// takes on loop bookkeeping and descriptor arithmetic (slice t of a stage is 4096 B = 256 descriptor units further on).
+// PASS 0: d = 0 .. min(S,4)-1 over the slices 0..3; PASS 1: d = 4 .. S-1 over all S slices.  first: the accumulators start here.
+template <int S, int PASS>
+__device__ __forceinline__ void oz_issue_quarter(uint32_t tmem, uint64_t a0, uint64_t b0, bool first) {
+  constexpr int NS = PASS ? S : (S < 4 ? S : 4);
+  constexpr int DLO = PASS ? 4 : 0, DHI = PASS ? S - 1 : NS - 1;
+#pragma unroll
+  for (int d = DLO; d <= DHI; ++d) {
+    const int tlo = d - (NS - 1) > 0 ? d - (NS - 1) : 0, thi = d < NS - 1 ? d : NS - 1;
+#pragma unroll
+    for (int t = tlo; t <= thi; ++t)
+      oz_mma(tmem + (uint32_t)(d - DLO) * 128u, a0 + (uint64_t)(t * 256), b0 + (uint64_t)((d - t) * 256), (first && t == tlo) ? 0u : 1u);
+  }
+}
+
 struct OzakiArgs {
   const uint8_t* slices;      // sliced factor [batch][sym_tiles][S * 16384]
   size_t slice_batch_stride;  // bytes
@@ -91,6 +107,7 @@ struct OzakiArgs {
   int S;                      // slices (6, 7 or 8)
 };
 
+template <int S>
 __global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
   extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
   const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
@@ -104,7 +121,6 @@ __global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
   double* colscale = reinterpret_cast<double*>(bars + 32);  // [128]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = g.S;
   if (tid == 0) {
     for (int s = 0; s < 24; ++s) oz_mb_init(&bars[s], 1);
     oz_mb_init(acc_full, 1);
@@ -152,8 +168,6 @@ __global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
     // ===== MMA issuer: accumulator d - dlo at TMEM columns (d - dlo) * 128
     if (lane == 0) {
       for (int pass = 0; pass < 2; ++pass) {
-        const int ns = pass ? S : nsA;
-        const int dlo = pass ? 4 : 0, dhi = pass ? S - 1 : nsA - 1;
         if (pass && S <= 4) break;
         const int nst = pass ? OZ_STAGES_B : OZ_STAGES_A;
         const uint32_t half = (uint32_t)(pass ? 8 : 4) * OZ_QB;
@@ -163,21 +177,14 @@ __global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
           oz_mb_wait(acc_empty, 0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        uint32_t started = 0;  // bit d - dlo: the accumulator has received its first MMA of this pass
         for (int kq = 0; kq < nq; ++kq) {
           const int s = kq % nst;
           oz_mb_wait(&full[s], (kq / nst) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = oz_s32(smem + (size_t)s * (2 * half)), sb = sa + half;
-          for (int d = dlo; d <= dhi; ++d) {
-            const int tlo = d - (ns - 1) > 0 ? d - (ns - 1) : 0, thi = d < ns - 1 ? d : ns - 1;
-            for (int t = tlo; t <= thi; ++t) {
-              const int u = d - t;
-              oz_mma(tmem + (uint32_t)(d - dlo) * 128u, oz_sdesc(sa + (uint32_t)t * OZ_QB), oz_sdesc(sb + (uint32_t)u * OZ_QB),
-                     (started >> (d - dlo)) & 1u);
-              started |= 1u << (d - dlo);
-            }
-          }
+          const uint32_t sa = oz_s32(smem + (size_t)s * (2 * half));
+          const uint64_t a0 = oz_sdesc(sa), b0 = oz_sdesc(sa + half);
+          if (pass) oz_issue_quarter<S, 1>(tmem, a0, b0, kq == 0);
+          else oz_issue_quarter<S, 0>(tmem, a0, b0, kq == 0);
           oz_commit(&empty[s]);  // the stage is free once these MMAs have read it
         }
         oz_commit(acc_full);
@@ -268,11 +275,12 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(TiledSym L, const doub
         uint32_t pk = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          // round to nearest by the 1.5 * 2^52 shift: the low word of t is the digit in two's complement, t - M the digit as a
+          // double (two DADDs instead of a rounding and a conversion instruction); |v| <= 64 (1 + few eps), so no clamp is needed
           double& v = y[4 * gq + j];
-          double q = rint(v);
-          q = fmin(fmax(q, -127.0), 127.0);
-          v = (v - q) * 128.0;
-          pk |= ((uint32_t)(__double2int_rn(q)) & 0xFFu) << (8 * j);
+          const double t = v + 6755399441055744.0;
+          v = (v - (t - 6755399441055744.0)) * 128.0;
+          pk |= ((uint32_t)__double2loint(t) & 0xFFu) << (8 * j);
         }
         w[gq] = pk;
       }
@@ -300,12 +308,18 @@ cudaError_t launch_ozaki_update(cudaStream_t st, TiledSym L, const uint8_t* slic
   cudaGetDevice(&dev);
   bool& configured = configured_dev[dev & 63];
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ozaki_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_update_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
     if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ozaki_update_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ozaki_update_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM)) != cudaSuccess) return e;
     configured = true;
   }
   OzakiArgs a{slices, slice_batch_stride, scale, scale_batch_stride, operand(L), i0, j0, k1, S};
-  ozaki_update_kernel<<<dim3((unsigned)ncols, (unsigned)nrows, (unsigned)batch), 192, OZ_SMEM, st>>>(a);
+  const dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
+  if (S == 8) ozaki_update_kernel<8><<<grid, 192, OZ_SMEM, st>>>(a);
+  else if (S == 7) ozaki_update_kernel<7><<<grid, 192, OZ_SMEM, st>>>(a);
+  else if (S == 6) ozaki_update_kernel<6><<<grid, 192, OZ_SMEM, st>>>(a);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

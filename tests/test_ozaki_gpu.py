@@ -1,6 +1,8 @@
 """GPU parity of the optional integer-slice (Ozaki) trailing update (csrc/ozaki.cu: int8 tcgen05 MMAs with exact int32 accumulation in
 TMEM): the factor against LAPACK and the DMMA path, and an OILMM logpdf + posterior + marginals against the CPU oracle at the north
 star's 1e-9.  DMMA stays the default; these tests switch the option on and off again."""
+import os
+
 import numpy as np
 import pytest
 import scipy.linalg as sla
@@ -18,7 +20,7 @@ def lmm():
 
     ctx = lmm_b200.default_context()
     yield lmm_b200
-    ctx.set_option("ozaki", 0)
+    ctx.set_option("ozaki", int(os.environ.get("LMM_OZAKI", "0")))  # the library default, or what the whole run was started with
     ctx.set_option("ozaki_min_k", 8)
     ctx.set_option("outer_block", 0)
 
@@ -34,9 +36,10 @@ def spd(N, batch, seed, cond_boost=0.0):
     return A
 
 
-@pytest.mark.parametrize("S,tol", [(8, 5e-14), (7, 5e-13), (6, 5e-11)])
+@pytest.mark.parametrize("S,tol", [(8, 5e-14), (7, 2e-11), (6, 2e-9)])
 def test_factor_matches_lapack(lmm, S, tol):
-    """Normwise relative error of L per matrix; S = 8 truncates at 2^-56 (FP64 level), every plane less costs 2^7."""
+    """Normwise relative error of L per matrix (rows scaled over e^-3 .. e^3); S = 8 truncates at 2^-56 (FP64 level: measured 2.1e-14
+    against 1.6e-14 for DMMA), every plane less costs 2^7 (measured 2.5e-12 and 3.1e-10)."""
     ctx = lmm.default_context()
     N, batch = 2600, 3  # 21 tile rows: wide updates at s0 = 8 and 16 take the int8 path (K = 8 and 16 k-tiles)
     A = spd(N, batch, seed=S)
