@@ -227,6 +227,31 @@ def run_reference(args, cfg):
     }))
 
 
+def int8_peak_tops():
+    """Dense int8 tensor peak of this pool's B200, measured by tools/microbench/i8_mma.cu (profiles/r02_i8_mma.jsonl: M = 128, N = 256
+    MMAs on all 148 SMs); nominal 4500.  MEASURED_PEAKS.json has no int8 entry."""
+    try:
+        best = 0.0
+        for ln in open(os.path.join(ROOT, "profiles", "r02_i8_mma.jsonl")):
+            d = json.loads(ln)
+            if d.get("test", "").startswith("i8_mma") and d.get("test", "").endswith("rate"):
+                best = max(best, float(d.get("total_tops", 0.0)))
+        if best > 0:
+            return best, "measured: tools/microbench/i8_mma.cu on all SMs (profiles/r02_i8_mma.jsonl); nominal dense int8 4500"
+    except Exception:
+        pass
+    return 4500.0, "nominal dense int8 (no measurement file)"
+
+
+def ncu_traffic_ozaki():
+    """dram bytes (read + write) of ONE launch of the int8 update from the committed ncu --set full capture (profiles/r02_ncu_ozaki.json)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_ozaki.json")))
+        return d["ozaki_update_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def multi_gpu_extras(lmm, ctx, dist, torch, world, rank):
     """Driver-visible records of the two other multi-GPU paths of the north star, run by every rank AFTER the timed region
     (they are collective) and attached to rank 0's JSON line; neither touches `value`.
@@ -294,7 +319,8 @@ def main():
     ap.add_argument("--N", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the untimed multi-GPU records (row-cyclic ILMM factor, config-5 sweep)")
-    ap.add_argument("--ozaki", type=int, default=0, help="integer-slice (int8 tcgen05) trailing update with this many digit planes (6/7/8); 0 = DMMA (default)")
+    ap.add_argument("--ozaki", type=int, default=8, help="digit planes (6/7/8) of the integer-slice (int8 tcgen05) trailing update of the timed path; "
+                                                          "0 = FP64 DMMA only (the library's own default; always measured beside it as `dmma_path`)")
     ap.add_argument("--streams", type=int, default=0, help="latent groups on separate CUDA streams (0 = library default)")
     args = ap.parse_args()
     p, m, N = args.p, args.m, args.N
@@ -325,8 +351,7 @@ def main():
         lmm.dist.init_context_distributed(ctx)
     if args.streams > 0:
         ctx.set_option("streams", args.streams)
-    if args.ozaki:
-        ctx.set_option("ozaki", args.ozaki)
+    ctx.set_option("ozaki", args.ozaki)
 
     x, U, S, inv_ls, y, s2 = workload(p, m, N)
     H = lmm.Orthogonal(U, S)
@@ -398,6 +423,39 @@ def main():
     pred_ms = float(ctx.last_timings()[5])
     post_s.f.fs[0]._owner.free()
     barrier()
+    # ---- untimed: (1) the int8 trailing-update kernel on its own -- one eval on ONE stream with CUDA events around every launch of
+    # it (library option "ozaki_time"); (2) the same eval on the FP64 DMMA path (option "ozaki" = 0) for the step time it would have
+    # had and for the difference of the results.
+    oz_kernel = None
+    dmma = None
+    if args.ozaki:
+        ctx.set_option("streams", 1)
+        ctx.set_option("ozaki_time", 1)
+        ctx.last_timings()  # drop earlier events
+        step(fx_dev, yd)
+        tmk = ctx.last_timings()
+        ctx.set_option("ozaki_time", 0)
+        ctx.set_option("streams", args.streams if args.streams > 0 else 4)
+        oz_kernel = {"ms": float(tmk[7]), "tile_products": float(tmk[5])}
+        ctx.set_option("ozaki", 0)
+        step(fx_dev, yd)
+        barrier()
+        dm_ms, dm_chol = 0.0, 0.0
+        nd_steps = min(2, args.steps)
+        for _ in range(nd_steps):
+            lp_d, tmd = step(fx_dev, yd)
+            dm_ms += tmd[0]; dm_chol += tmd[2]
+        post_d, lp_d = lmm.posterior(fx_dev, yd, with_logpdf=True)
+        M_d, V_d = lmm.mean_and_var(post_d(lmm.MOInputIsotopicByOutputs(xs_chk, p), s2))
+        post_d.f.fs[0]._owner.free()
+        ctx.set_option("ozaki", args.ozaki)
+        barrier()
+        dstats = torch.tensor([dm_ms / nd_steps, dm_chol / nd_steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dstats, op=dist.ReduceOp.MAX)
+        dmma = {"ms_per_step": float(dstats[0]), "cholesky_ms": float(dstats[1]), "steps": nd_steps, "logpdf": lp_d,
+                "logpdf_rel_diff": abs(lp_s - lp_d) / abs(lp_d), "mean_relnorm": float(np.linalg.norm(M_s - M_d) / np.linalg.norm(M_d)),
+                "var_max_rel": float(np.max(np.abs(V_s - V_d) / np.abs(V_d)))}
     extras = multi_gpu_extras(lmm, ctx, dist, torch, world, rank) if (world > 1 and not args.no_extras) else None
     barrier()
     if rank != 0:
@@ -414,19 +472,45 @@ def main():
     achieved = chol_flops / (chol_ms_max / K * 1e-3) / 1e12
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     pipe_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12  # 64 FP64 FMA / clk / SM (DMMA and DFMA share it: profiles/r01_fp64_mix.json)
-    out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg["config"],
-        "e2e": {"value": 1e3 / (e2e_ms / K), "unit": UNIT, "h2d_bytes_per_step": int((hh1 - hh0) / K), "d2h_bytes_per_step": int((dh1 - dh0) / K)},
-        "gpu_launches": int(launches.item()),
-        "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "batched blocked Cholesky (gemm_tile_kernel_v2 DMMA updates + TRSM-as-GEMM + potrf_tile_kernel2)",
+    if args.ozaki:
+        cfg["config"]["trailing_update"] = (
+            f"wide left-looking updates as an integer-slice (Ozaki) product on the int8 tensor cores: {args.ozaki} 7-bit digit planes per FP64 operand, "
+            f"{args.ozaki * (args.ozaki + 1) // 2} tcgen05.mma kind::i8 per 128^3 tile product, exact int32 accumulation in TMEM, FP64 recombination; panels, in-block "
+            "updates, triangular solves, kernel matrices in FP64 (DMMA / DFMA).  The library default is DMMA everywhere (--ozaki 0): measured beside it as dmma_path")
+    dmma_roofline = {"bound": "tensor", "kernel": "batched blocked Cholesky (gemm_tile_kernel_v2 DMMA updates + TRSM-as-GEMM + potrf_tile_kernel2)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(p, N, mloc),
                      "peak_source": peak_src, "flops_per_rank_step": chol_flops,
                      "fp64_pipe_peak": pipe_peak, "frac_of_fp64_pipe_peak": achieved / pipe_peak,
                      "fp64_pipe_peak_source": f"148 SM x 64 FMA/clk x 2 x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)",
-                     "whole_eval_tflops": (m * (N ** 3 / 3.0 + 2.0 * N * N) + 4.0 * p * m * N) / (ms_per_step * 1e-3) / 1e12 / world},
+                     "whole_eval_tflops": (m * (N ** 3 / 3.0 + 2.0 * N * N) + 4.0 * p * m * N) / (ms_per_step * 1e-3) / 1e12 / world}
+    if args.ozaki and oz_kernel and oz_kernel["ms"] > 0:
+        # dominant kernel of the timed path: the int8 wide update.  Algorithmic work of its launches = tile products x S(S+1)/2 MMAs x
+        # 2 * 128^3 int8 ops, over the summed CUDA-event time of exactly those launches (one stream: serial).
+        i8_peak, i8_src = int8_peak_tops()
+        nmma = args.ozaki * (args.ozaki + 1) // 2
+        ops = oz_kernel["tile_products"] * nmma * 2.0 * 128 ** 3
+        a_tops = ops / (oz_kernel["ms"] * 1e-3) / 1e12
+        dd = dmma["cholesky_ms"] if dmma else None
+        roof = {"bound": "tensor", "kernel": f"ozaki_update_kernel<{args.ozaki}> (tcgen05.mma.cta_group::1.kind::i8, TMEM int32 accumulators, TMA bulk-copy ring)",
+                "achieved": a_tops, "peak": i8_peak, "unit": "TOP/s", "frac": a_tops / i8_peak, "traffic": ncu_traffic_ozaki(),
+                "peak_source": i8_src, "int8_ops_per_rank_step": ops, "kernel_ms_per_step": oz_kernel["ms"],
+                "kernel_share_of_step": oz_kernel["ms"] / (ev_ms / K),
+                "fp64_equivalent_tflops_of_the_kernel": oz_kernel["tile_products"] * 2.0 * 128 ** 3 / (oz_kernel["ms"] * 1e-3) / 1e12,
+                "fp64_equivalent_tflops_of_the_cholesky": achieved, "fp64_pipe_peak": pipe_peak,
+                "cholesky_speedup_over_dmma": (dd / (chol_ms_max / K)) if dd else None,
+                "note": "the kernel time is taken on one stream in an untimed pass right after the timed region (CUDA events around each launch); "
+                        "FP64-equivalent = 2 * 128^3 flop per tile product, i.e. what the DMMA path would have executed"}
+    else:
+        roof = dmma_roofline
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": ("f64 (wide Cholesky updates: f64 split into int8 digit planes, exact int32 accumulation)" if args.ozaki else "f64"),
+        "data": "synthetic", "config": cfg["config"],
+        "e2e": {"value": 1e3 / (e2e_ms / K), "unit": UNIT, "h2d_bytes_per_step": int((hh1 - hh0) / K), "d2h_bytes_per_step": int((dh1 - dh0) / K)},
+        "gpu_launches": int(launches.item()),
+        "clocks": clocks,
+        "roofline": roof,
         "stage_ms_per_step": {"stage_in+project": proj_ms / K, "kmat": kmat_ms / K, "cholesky": chol_ms / K, "solves": solve_ms / K},
         "hbm_stage_gbs": {"kmat_written": mloc * 8.0 * N * (N + 1) / 2 / (kmat_ms / K * 1e-3) / 1e9,
                           "solves_read": 2 * mloc * 8.0 * N * (N + 1) / 2 / (solve_ms / K * 1e-3) / 1e9,
@@ -435,6 +519,15 @@ def main():
         "prediction_check_ms": pred_ms,
         "logpdf": lp,
     }
+    if dmma:
+        fl = mloc * (N ** 3) / 3.0
+        dmma["value"] = 1e3 / dmma["ms_per_step"]
+        dmma["cholesky_tflops"] = fl / (dmma["cholesky_ms"] * 1e-3) / 1e12
+        dmma["frac_of_fp64_pipe_peak"] = dmma["cholesky_tflops"] / pipe_peak
+        dmma["frac_of_measured_dgemm"] = dmma["cholesky_tflops"] / peak
+        dmma["what"] = ("the same eval with the library's default FP64 DMMA trailing update (option ozaki = 0), measured untimed right after the timed region; "
+                        "logpdf / posterior mean / variance differences are timed path vs this path at 256 test points")
+        out["dmma_path"] = dmma
     if extras:
         out.update(extras)
     if world > 1:

@@ -133,6 +133,17 @@ const char* lmm_version(void);
  *   "condition_update" lmm_post_condition on an OILMM / IndependentMOGP posterior: 1 = block-Cholesky update of each latent's
  *                     factor, L21 = K21 L11^{-T}, L22 = chol(K22 + Σ2 - L21 L21'), O(N² N₂) (default, what AbstractGPs does);
  *                     0 = re-factorise the union of the inputs, O((N + N₂)³)
+ *   "ozaki"           6 | 7 | 8: the WIDE trailing update of the batched blocked Cholesky runs as an integer-slice (Ozaki-scheme) product on
+ *                     the int8 tensor cores (tcgen05.mma kind::i8, exact int32 accumulation in TMEM) with that many 7-bit digit
+ *                     planes per FP64 operand, instead of FP64 DMMA; everything else (panels, in-block updates, solves) stays
+ *                     FP64.  8 planes truncate at 2^-56 of the row scale (measured normwise factor error 2e-14, DMMA 6e-16 .. 2e-14);
+ *                     each plane less costs 2^7 in accuracy and saves ~12 % of the update time.  Default 0 = DMMA (the north
+ *                     star's prescription); LMM_OZAKI in the environment sets the initial value.
+ *   "ozaki_min_k"     wide updates over fewer k-tiles than this stay on DMMA (default 8: the int8 epilogue costs per output tile)
+ *   "ozaki_single_nt" with "ozaki" on, batches <= 2 keep the right-looking DMMA schedule unless the factor has at least this many tile
+ *                     rows, from which on it takes the batched schedule and with it the int8 update (default 64, i.e. N >= 8192:
+ *                     N = 16384 batch 1: 45.9 -> 30.2 ms, batch 2: 88.9 -> 44.4 ms; 0 = never)
+ *   "ozaki_time"      1 = time every int8 update launch with CUDA events: see lmm_ctx_last_timings (default 0)
  *   "solve_impl"      triangular vector solves (z = L^{-1} r, a = L^{-T} z): 1 = ONE persistent launch per direction, tile rows /
  *                     columns chained through ready flags in global memory (default); 0 = one launch per tile column
  *                                                                 [process-wide] */
@@ -143,7 +154,9 @@ int lmm_ctx_counters(lmm_ctx* ctx, int64_t* kernel_launches, int64_t* h2d_bytes,
  * stages: [0] total, [1] kernel-matrix build, [2] Cholesky, [3] solves, [4] projection,
  * [5] prediction (cross-cov + TRSM + back-projection), [6] Cholesky trailing-update GEMM launches
  * count (as a double), [7] reserved.  After a distributed-storage ILMM logpdf ("partition_ilmm" = 2) the slots [4], [5], [7]
- * hold BYTES instead: the matrix rows this rank stores, its exchange / window workspace, the whole packed matrix. */
+ * hold BYTES instead: the matrix rows this rank stores, its exchange / window workspace, the whole packed matrix.  With the option
+ * "ozaki_time" = 1, [7] is the summed CUDA-event time (ms) of the int8 trailing-update launches since the previous query and [5] the
+ * number of 128^3 tile products they covered (serial launches, i.e. "streams" = 1, make the sum a duration). */
 int lmm_ctx_last_timings(lmm_ctx* ctx, double out_ms[8]);
 
 /* ---- multi-GPU: one process (and one context) per GPU; latents are block-sharded over ranks --- */

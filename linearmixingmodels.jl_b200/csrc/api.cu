@@ -239,6 +239,12 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "ozaki") {
     if (value != 0.0 && value != 6.0 && value != 7.0 && value != 8.0) return ctx->fail(LMM_E_ARG, "ozaki must be 0 (DMMA) or 6, 7, 8 (int8 digit planes)");
     ctx->ozaki = (int)value;
+  } else if (k == "ozaki_time") {
+    if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_ARG, "ozaki_time must be 0 or 1");
+    ctx->ozaki_time = (int)value;
+  } else if (k == "ozaki_single_nt") {
+    if (value < 0 || value > 65536) return ctx->fail(LMM_E_ARG, "ozaki_single_nt must be in [0, 65536]");
+    ctx->ozaki_single_nt = (int)value;
   } else if (k == "ozaki_min_k") {
     if (value < 1 || value > 4096) return ctx->fail(LMM_E_ARG, "ozaki_min_k must be in [1, 4096]");
     ctx->ozaki_min_k = (int)value;
@@ -273,6 +279,20 @@ extern "C" int lmm_ctx_last_timings(lmm_ctx* ctx, double out_ms[8]) {
   if (!ctx || !out_ms) return LMM_E_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   for (int i = 0; i < 8; ++i) out_ms[i] = ctx->timings[i];
+  if (!ctx->oz_events.empty()) {  // "ozaki_time": the int8 update launches of the last call(s), summed; events are consumed here
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < ctx->oz_events.size(); i += 2) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(ctx->oz_events[i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->oz_events[i], ctx->oz_events[i + 1]) == cudaSuccess)
+        sum += ms;
+      cudaEventDestroy(ctx->oz_events[i]);
+      cudaEventDestroy(ctx->oz_events[i + 1]);
+    }
+    ctx->oz_events.clear();
+    out_ms[7] = sum;
+    out_ms[5] = ctx->oz_tile_products;
+    ctx->oz_tile_products = 0.0;
+  }
   return LMM_OK;
 }
 

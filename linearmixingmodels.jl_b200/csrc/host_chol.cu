@@ -43,9 +43,13 @@ struct OzWs {
 
 cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double* W, size_t wstride, int batch, double* logdet,
                                int* info, int jstart = 0, int* counters = nullptr, const OzWs* oz = nullptr) {
-  const int nt = L.nt, ob = ctx->outer_block;
+  const int nt = L.nt;
+  int ob = ctx->outer_block;
   if (oz && (jstart != 0 || nt <= ob || nt < oz->min_k + 1)) oz = nullptr;  // no wide update this scheme would take
   if (oz) {
+    // narrower blocks: the in-block updates stay on DMMA, and at ob = 4 they are half as much work (measured at 16 latents of
+    // N = 16384: 323 ms at ob = 8, 306 at 4, 315 at 6, 340 at 12)
+    if (!ctx->outer_block_user) ob = 4;
     cudaError_t eo = launch_ozaki_scales(st, L, batch, oz->scale, oz->scale_stride);  // reads the diagonal BEFORE it is factored
     if (eo != cudaSuccess) return eo;
     ++ctx->launches;
@@ -65,9 +69,19 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
       const int r0 = s0 > jstart ? s0 : jstart;  // first tile row that still has to be computed
       g.i0 = r0; g.j0 = s0; g.k0 = 0; g.k1 = s0;
       // exact int32 accumulation needs S * K * 64^2 < 2^31
-      if (oz && s0 >= oz->min_k && (long long)s0 * TILE * oz->S * 4096 < (1ll << 31))
+      if (oz && s0 >= oz->min_k && (long long)s0 * TILE * oz->S * 4096 < (1ll << 31)) {
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (ctx->ozaki_time && cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess) cudaEventRecord(ev0, st);
         e = launch_ozaki_update(st, L, oz->slices, oz->slice_stride, oz->scale, oz->scale_stride, r0, nt - r0, s0, s1 - s0, s0, batch, oz->S);
-      else
+        if (ev0 && ev1) {
+          cudaEventRecord(ev1, st);
+          ctx->oz_events.push_back(ev0);
+          ctx->oz_events.push_back(ev1);
+          double tp = 0.0;  // 128^3 tile products of this launch: tiles (I, J), I >= J, times s0 k-tiles
+          for (int J = s0; J < s1; ++J) tp += (double)(nt - (J > r0 ? J : r0)) * s0;
+          ctx->oz_tile_products += tp * batch;
+        }
+      } else
         e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, nt - r0, batch);
       if (e != cudaSuccess) return e;
       ++ctx->launches;
@@ -520,7 +534,10 @@ cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int
   if (jstart == 0) {  // the look-ahead / partitioned schedules factor from scratch only
     if (ctx->partition_ilmm && ctx->partition_now && batch == 1 && ctx->comm && ctx->nranks > 1 && L.nt >= 2 * ctx->nranks && nccl_api().AllGather)
       return chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
-    if (ctx->lookahead && batch <= 2 && L.nt >= 12) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
+    // (with the integer-slice update on, a LARGE single factor is faster on the batched left-looking schedule: its wide updates run
+    // at 2-3x the DMMA rate, which outweighs the exposed panel chain -- "ozaki_single_nt" tile rows and up)
+    const bool oz_single = ctx->ozaki && ctx->ozaki_single_nt > 0 && L.nt >= ctx->ozaki_single_nt;
+    if (ctx->lookahead && batch <= 2 && L.nt >= 12 && !oz_single) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
   }
   cudaError_t e;
   // optional integer-slice trailing update: workspace for as many latents as fit; a larger batch is factored in chunks

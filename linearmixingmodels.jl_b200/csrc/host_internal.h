@@ -83,6 +83,11 @@ struct lmm_ctx {
   int dist_error = 0;  // NCCL failure inside the partitioned schedule (reported by the caller)
   // integer-slice (Ozaki) trailing update on the int8 tensor cores: 0 = off (DMMA, default), 6 / 7 / 8 = digit planes
   int ozaki = 0;
+  int ozaki_time = 0;         // 1: CUDA events around every int8 update launch; their sum (ms) and the tile products they cover are
+                              // reported by lmm_ctx_last_timings in slots [7] and [5] (meaningful with "streams" = 1: serial launches)
+  std::vector<cudaEvent_t> oz_events;
+  double oz_tile_products = 0.0;
+  int ozaki_single_nt = 64;   // batch <= 2: use the batched schedule (and with it the int8 update) from this many tile rows on (0 = never)
   int ozaki_min_k = 8;        // wide updates over fewer k-tiles stay on DMMA (the int8 epilogue is per output tile, not per k)
   void* oz_slices = nullptr;  // [latents in flight][sym_tiles][S * 16 KB], grown on demand
   size_t oz_slices_bytes = 0;

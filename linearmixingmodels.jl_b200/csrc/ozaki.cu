@@ -97,6 +97,58 @@ __device__ __forceinline__ void oz_issue_quarter(uint32_t tmem, uint64_t a0, uin
   }
 }
 
+// Epilogue, 8 warps: warp w owns the TMEM lane quadrant w % 4 (tile rows 32 (w % 4) .. + 31, one per lane) and the column half
+// w / 4 (64 columns).  A thread keeps its 64 values of C(I,J) in REGISTERS for the whole kernel: they are loaded when the kernel
+// starts (the loads complete behind the MMA phase -- a load-after-wait epilogue was latency-bound: 16 dependent L2 round trips
+// per pass held the tensor pipe at 63 %), both passes subtract into them, and they are stored once at the end.
+constexpr int OZ_THREADS = 320;  // warps 0-7: epilogue, warp 8: producer, warp 9: MMA issuer
+__device__ __forceinline__ void oz_epi_load(const double* Ctile, int r, int ch, double (&c)[64]) {
+#pragma unroll
+  for (int gq = 0; gq < 16; ++gq) {
+    const double2* p = reinterpret_cast<const double2*>(Ctile + tile_elem(r, 64 * ch + 4 * gq));
+    const double2 x0 = p[0], x1 = p[1];
+    c[4 * gq + 0] = x0.x; c[4 * gq + 1] = x0.y; c[4 * gq + 2] = x1.x; c[4 * gq + 3] = x1.y;
+  }
+}
+__device__ __forceinline__ void oz_epi_store(double* Ctile, int r, int ch, const double (&c)[64]) {
+#pragma unroll
+  for (int gq = 0; gq < 16; ++gq) {
+    double2* p = reinterpret_cast<double2*>(Ctile + tile_elem(r, 64 * ch + 4 * gq));
+    p[0] = make_double2(c[4 * gq + 0], c[4 * gq + 1]);
+    p[1] = make_double2(c[4 * gq + 2], c[4 * gq + 3]);
+  }
+}
+// One pass: the ND int32 accumulators -> exact doubles, Horner in 2^-7, row / column scales, c -= result.
+template <int ND>
+__device__ __forceinline__ void oz_epi_pass(uint32_t tmem, int quad, int ch, double ps, const double* colscale, double (&c)[64]) {
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 4) {
+    uint32_t v[ND][4];
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * 128 + 64 * ch + c0);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v[a][0]), "=r"(v[a][1]), "=r"(v[a][2]), "=r"(v[a][3])
+                   : "r"(taddr)
+                   : "memory");
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double acc = oz_i2d(v[ND - 1][j]);
+#pragma unroll
+      for (int a = ND - 2; a >= 0; --a) acc = fma(acc, 0.0078125, oz_i2d(v[a][j]));
+      c[c0 + j] = fma(-acc, ps * colscale[64 * ch + c0 + j], c[c0 + j]);
+    }
+  }
+}
+template <int S>
+__device__ __forceinline__ void oz_epi_both(uint32_t tmem, int quad, int ch, int pass, double rs, const double* colscale, double (&c)[64]) {
+  constexpr int NDA = S < 4 ? S : 4, NDB = S > 4 ? S - 4 : 1;
+  if (pass == 0) oz_epi_pass<NDA>(tmem, quad, ch, rs, colscale, c);
+  else oz_epi_pass<NDB>(tmem, quad, ch, rs * 3.7252902984619140625e-09, colscale, c);  // 2^-28: pass B starts at d = 4
+}
+
 struct OzakiArgs {
   const uint8_t* slices;      // sliced factor [batch][sym_tiles][S * 16384]
   size_t slice_batch_stride;  // bytes
@@ -108,7 +160,7 @@ struct OzakiArgs {
 };
 
 template <int S>
-__global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g) {
   extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
   const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
   if (I < J) return;
@@ -124,7 +176,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
   if (tid == 0) {
     for (int s = 0; s < 24; ++s) oz_mb_init(&bars[s], 1);
     oz_mb_init(acc_full, 1);
-    oz_mb_init(acc_empty, 128);
+    oz_mb_init(acc_empty, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -140,7 +192,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
   const int nq = g.k1 * 4;  // K quarters per pass
   const int nsA = S < 4 ? S : 4;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===== producer: per K quarter one bulk copy of the needed slices of A(I,k) and one of B(J,k)
     if (lane == 0) {
       const uint8_t* Abase = g.slices + (size_t)b * g.slice_batch_stride + sym_tile_index(I, 0) * tile_bytes;
@@ -164,7 +216,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===== MMA issuer: accumulator d - dlo at TMEM columns (d - dlo) * 128
     if (lane == 0) {
       for (int pass = 0; pass < 2; ++pass) {
@@ -191,56 +243,33 @@ __global__ void __launch_bounds__(192, 1) ozaki_update_kernel(OzakiArgs g) {
       }
     }
   } else {
-    // ===== epilogue: warp w owns TMEM lanes / tile rows 32w .. 32w + 31
-    const int r = warp * 32 + lane;
+    // ===== epilogue (warps 0-7): C(I,J) lives in registers from here to the end
+    const int quad = warp & 3, ch = warp >> 2, r = quad * 32 + lane;
     const double rs = g.scale[(size_t)b * g.scale_batch_stride + (size_t)I * TILE + r];
     double* Ctile = g.C.tile(b, I, J);
+    double c[64];
+    oz_epi_load(Ctile, r, ch, c);
     for (int pass = 0; pass < 2; ++pass) {
-      const int dlo = pass ? 4 : 0, dhi = pass ? S - 1 : nsA - 1;
       if (pass && S <= 4) break;
-      const int nd = dhi - dlo + 1;
       oz_mb_wait(acc_full, (uint32_t)pass);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const double ps = pass ? rs * 3.7252902984619140625e-09 : rs;  // 2^-28: pass B starts at d = 4
-      for (int c0 = 0; c0 < 128; c0 += 8) {
-        uint32_t v[4][8];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          if (a < nd) {
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 128 + c0);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(v[a][0]), "=r"(v[a][1]), "=r"(v[a][2]), "=r"(v[a][3]), "=r"(v[a][4]), "=r"(v[a][5]), "=r"(v[a][6]), "=r"(v[a][7])
-                         : "r"(taddr)
-                         : "memory");
-          }
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {  // two groups of 4 columns = two 32-byte runs of the k4-interleaved tile
-          const int c = c0 + 4 * h;
-          double2* cp = reinterpret_cast<double2*>(Ctile + tile_elem(r, c));
-          double2 x0 = cp[0], x1 = cp[1];
-          double o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            double acc = 0.0;
-#pragma unroll
-            for (int a = 3; a >= 0; --a)
-              if (a < nd) acc = fma(acc, 0.0078125, oz_i2d(v[a][4 * h + j]));
-            o[j] = acc * (ps * colscale[c + j]);
-          }
-          x0.x -= o[0]; x0.y -= o[1]; x1.x -= o[2]; x1.y -= o[3];
-          cp[0] = x0; cp[1] = x1;
-        }
-      }
+      oz_epi_both<S>(tmem, quad, ch, pass, rs, colscale, c);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       if (pass == 0) oz_mb_arrive(acc_empty);
     }
+    oz_epi_store(Ctile, r, ch, c);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
+
+// A CTA-PAIR variant (tcgen05 cta_group::2, M = 256: each SM reads its own 128 rows of A and only half of B per MMA, which lifts the
+// shared-memory cap -- tools/microbench/i8_mma.cu measures 64.0 clk per MMA for the pair against 71 for one CTA) was built, passed
+// the same tests and was REMOVED: with the stage hand-shake across two CTAs (relay of the peer's `full` barrier, multicast
+// commits) and the same 3-stage depth in pass B it reached 56-63 % tensor-pipe activity and 308-343 ms where this kernel needs
+// 287 ms (16 latents, N = 16384; profiles/r02_ozaki.md).  One more thing learnt there: a kernel that uses cta_group::2 only
+// launches when the pair is adjacent in x (cluster (2,1,1)); (1,2,1) fails with cudaErrorInvalidClusterSize.
 
 // ---- row exponents from the diagonal of the matrix that is about to be factored: scale = 2^(E - 6), 2^E > sqrt(A_ii)
 __global__ void __launch_bounds__(128) ozaki_scale_kernel(TiledSym L, double* __restrict__ scale, size_t scale_batch_stride) {
@@ -316,9 +345,9 @@ cudaError_t launch_ozaki_update(cudaStream_t st, TiledSym L, const uint8_t* slic
   }
   OzakiArgs a{slices, slice_batch_stride, scale, scale_batch_stride, operand(L), i0, j0, k1, S};
   const dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
-  if (S == 8) ozaki_update_kernel<8><<<grid, 192, OZ_SMEM, st>>>(a);
-  else if (S == 7) ozaki_update_kernel<7><<<grid, 192, OZ_SMEM, st>>>(a);
-  else if (S == 6) ozaki_update_kernel<6><<<grid, 192, OZ_SMEM, st>>>(a);
+  if (S == 8) ozaki_update_kernel<8><<<grid, OZ_THREADS, OZ_SMEM, st>>>(a);
+  else if (S == 7) ozaki_update_kernel<7><<<grid, OZ_THREADS, OZ_SMEM, st>>>(a);
+  else if (S == 6) ozaki_update_kernel<6><<<grid, OZ_THREADS, OZ_SMEM, st>>>(a);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

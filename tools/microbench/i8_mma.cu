@@ -131,6 +131,104 @@ __global__ void __launch_bounds__(128, 1) i8_mma_kernel(const int8_t* __restrict
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ---- cta_group::2: one MMA spans a CTA pair (M = 256: each CTA supplies its own 128 rows of A and HALF of B's N rows, and holds
+// the accumulator rows of its own A rows in its own TMEM).  Per SM and MMA that is 4 KB of A + 2 KB of B from shared memory
+// instead of 8 KB.  Only the leader (cluster rank 0) issues; the commit is multicast to the barrier of both CTAs.
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mma_i8_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+// A: [2 CTAs][128 rows x 128 K] canonical; B: N = 128 rows x 128 K canonical [chunk][128 rows][16 B]; CTA r stages rows 64r .. 64r+63 of B as
+// [chunk (8)][64 rows][16 B] (LBO = 1024).  D: [256 x 128] int32.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    i8_mma_2cta_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int32_t* __restrict__ D, int reps, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t rank = cluster_rank();
+  uint8_t* sA = smem;              // 128 x 128 bytes (own rows)
+  uint8_t* sB = smem + 128 * 128;  // 64 x 128 bytes (own half of N)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * 128 / 16; i += 128) reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(A + (size_t)rank * 128 * 128)[i];
+  for (int i = tid; i < 64 * 128 / 16; i += 128) {  // unit i = (chunk, row in half): source [chunk][128 rows][16]
+    const int chunk = i / 64, row = i % 64;
+    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(B)[chunk * 128 + rank * 64 + row];
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();  // both CTAs' operands staged, barriers initialised, TMEM allocated
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  constexpr uint32_t idesc = make_idesc_i8(256, 128);
+  const uint32_t a0 = s_u32(sA), b0 = s_u32(sB);
+  long long t0 = 0, t1 = 0;
+  if (rank == 0 && tid == 0) {
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const uint32_t dcol = (uint32_t)((r % 4) * 128);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = make_sdesc(a0 + ks * 2 * (128 * 16), 128 * 16, 128);
+        const uint64_t bd = make_sdesc(b0 + ks * 2 * (64 * 16), 64 * 16, 128);
+        mma_i8_2cta(tmem + dcol, ad, bd, idesc, (r >= 4 || ks > 0) ? 1u : 0u);
+      }
+    }
+    mma_commit_2cta(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (rank == 0 && tid == 0) {
+    t1 = clock64();
+    if (cycles) cycles[blockIdx.x / 2] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (D && blockIdx.x < 2) {
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+          "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+            "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 32; ++j) D[((size_t)rank * 128 + tid) * 128 + c0 + j] = (int32_t)v[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 static size_t canon(int R, int r, int k) { return (size_t)(k / 16) * (R / 8 * 128) + (size_t)(r / 8) * 128 + (r % 8) * 16 + (k % 16); }
 
 template <int N>
@@ -207,6 +305,68 @@ static int run(int sms, double clock_ghz) {
   return bad == 0 && bad3 == 0;
 }
 
+static int run_2cta(int sms) {
+  std::vector<int8_t> hA(256 * 128), hB(128 * 128), cA(256 * 128), cB(128 * 128);
+  srand(99);
+  for (auto& v : hA) v = (int8_t)(rand() % 129 - 64);
+  for (auto& v : hB) v = (int8_t)(rand() % 129 - 64);
+  for (int h = 0; h < 2; ++h)
+    for (int r = 0; r < 128; ++r)
+      for (int k = 0; k < 128; ++k) cA[(size_t)h * 128 * 128 + canon(128, r, k)] = hA[(h * 128 + r) * 128 + k];
+  for (int r = 0; r < 128; ++r)
+    for (int k = 0; k < 128; ++k) cB[canon(128, r, k)] = hB[r * 128 + k];
+  int8_t *dA, *dB;
+  int32_t* dD;
+  long long* dC;
+  CK(cudaMalloc(&dA, cA.size()));
+  CK(cudaMalloc(&dB, cB.size()));
+  CK(cudaMalloc(&dD, (size_t)256 * 128 * 4));
+  CK(cudaMalloc(&dC, 1024 * sizeof(long long)));
+  CK(cudaMemcpy(dA, cA.data(), cA.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, cB.data(), cB.size(), cudaMemcpyHostToDevice));
+  const size_t smem = 128 * 128 + 64 * 128;
+  i8_mma_2cta_kernel<<<2, 128, smem>>>(dA, dB, dD, 1, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> hD((size_t)256 * 128);
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+  long long bad = 0;
+  for (int i = 0; i < 256; ++i)
+    for (int j = 0; j < 128; ++j) {
+      int32_t s = 0;
+      for (int k = 0; k < 128; ++k) s += (int32_t)hA[i * 128 + k] * (int32_t)hB[j * 128 + k];
+      if (s != hD[(size_t)i * 128 + j]) {
+        if (bad < 6) printf("  2cta mismatch (%d,%d): got %d want %d\n", i, j, hD[(size_t)i * 128 + j], s);
+        ++bad;
+      }
+    }
+  printf("{\"test\": \"i8_mma_2cta_correct\", \"M\": 256, \"N\": 128, \"K\": 128, \"mismatches\": %lld}\n", bad);
+  for (int pairs : {1, sms / 2}) {
+    const int reps = 4096;
+    i8_mma_2cta_kernel<<<2 * pairs, 128, smem>>>(dA, dB, nullptr, 64, dC);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    i8_mma_2cta_kernel<<<2 * pairs, 128, smem>>>(dA, dB, nullptr, reps, dC);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> hc(pairs);
+    CK(cudaMemcpy(hc.data(), dC, pairs * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long cmax = 0;
+    for (long long c : hc) cmax = c > cmax ? c : cmax;
+    const double macs = (double)reps * 4 * 256.0 * 128 * 32;
+    printf("{\"test\": \"i8_mma_2cta_rate\", \"M\": 256, \"N\": 128, \"cta_pairs\": %d, \"cycles_per_mma\": %.2f, \"mac_per_clk_per_sm\": %.1f, "
+           "\"smem_bytes_per_clk_per_sm\": %.1f, \"ms\": %.3f, \"total_tops\": %.1f}\n",
+           pairs, (double)cmax / (reps * 4), macs / 2 / (double)cmax, (double)reps * 4 * (128 + 64) * 32 / (double)cmax, ms,
+           2.0 * macs * pairs / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
+  return bad == 0;
+}
+
 int main() {
   cudaDeviceProp pr;
   CK(cudaGetDeviceProperties(&pr, 0));
@@ -215,6 +375,7 @@ int main() {
   ok &= run<64>(pr.multiProcessorCount, 0);
   ok &= run<128>(pr.multiProcessorCount, 0);
   ok &= run<256>(pr.multiProcessorCount, 0);
+  ok &= run_2cta(pr.multiProcessorCount);
   printf("{\"all_correct\": %s}\n", ok ? "true" : "false");
   return ok ? 0 : 1;
 }
