@@ -269,6 +269,15 @@ def multi_gpu_extras(lmm, ctx, dist, torch, world, rank):
 
     out = {}
     rec = {"N": 16384, "ranks": world}
+    # the partitioned schedules run the FP64 DMMA trailing update: compare like with like (int8 option off), then note what the
+    # int8 update does for the unpartitioned factor on one GPU
+    oz_saved = int(getattr(ctx, "_bench_ozaki", 0))
+    if oz_saved:
+        ctx.set_option("ozaki", oz_saved)
+        ms_oz, _, ld_oz = run(ctx, 16384, 1, reps=2)
+        rec["replicated_int8_update_ms"] = maxed(ms_oz)
+        rec["replicated_int8_update_logdet"] = ld_oz
+    ctx.set_option("ozaki", 0)
     for part, key in ((0, "replicated"), (1, "rowcyclic")):
         ctx.set_option("partition_ilmm", part)
         dist.barrier()
@@ -285,6 +294,7 @@ def multi_gpu_extras(lmm, ctx, dist, torch, world, rank):
     from tools.multigpu_ilmm import ilmm_logpdf_record
 
     out["ilmm_distributed"] = ilmm_logpdf_record(lmm, ctx, dist, torch, 8, 4, 4096)
+    ctx.set_option("ozaki", oz_saved)
     p, m, N, nsweep = 256, 128, 8192, 32
     rng = np.random.default_rng(0)
     x = np.sort(rng.uniform(0, N / 100.0, N))
@@ -303,7 +313,8 @@ def multi_gpu_extras(lmm, ctx, dist, torch, world, rank):
     flops = m * nsweep * N ** 3 / 3.0
     out["c5_sweep"] = {"config": f"BASELINE config 5: OILMM p={p} m={m} N={N} x {nsweep} lengthscales in one call", "n_gpus": world,
                        "seconds_per_call": sec, "factorizations": m * nsweep, "tflops_total": flops / sec / 1e12,
-                       "tflops_per_gpu": flops / sec / 1e12 / world, "logpdf_at_scale_1": float(vals[int(np.argmin(np.abs(scales - 1.0)))]),
+                       "tflops_per_gpu": flops / sec / 1e12 / world, "trailing_update": (f"int8 digit planes: {oz_saved}" if oz_saved else "FP64 DMMA"),
+                       "logpdf_at_scale_1": float(vals[int(np.argmin(np.abs(scales - 1.0)))]),
                        "argmax_scale": float(scales[int(np.argmax(vals))])}
     return out
 
@@ -352,6 +363,7 @@ def main():
     if args.streams > 0:
         ctx.set_option("streams", args.streams)
     ctx.set_option("ozaki", args.ozaki)
+    ctx._bench_ozaki = args.ozaki
 
     x, U, S, inv_ls, y, s2 = workload(p, m, N)
     H = lmm.Orthogonal(U, S)
