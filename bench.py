@@ -444,8 +444,7 @@ def main():
         ctx.set_option("streams", 1)
         ctx.set_option("ozaki_time", 1)
         ctx.last_timings()  # drop earlier events
-        step(fx_dev, yd)
-        tmk = ctx.last_timings()
+        _, tmk = step(fx_dev, yd)  # (step() reads the timings itself: the event sum is consumed by that read)
         ctx.set_option("ozaki_time", 0)
         ctx.set_option("streams", args.streams if args.streams > 0 else 4)
         oz_kernel = {"ms": float(tmk[7]), "tile_products": float(tmk[5])}

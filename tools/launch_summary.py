@@ -12,7 +12,7 @@ import json
 import re
 import sys
 
-CHOL = ("potrf_tile_kernel2", "gemm_tile_kernel_v2", "gemm_direct2_kernel", "chain_column_kernel")
+CHOL = ("potrf_tile_kernel2", "gemm_tile_kernel_v2", "gemm_direct2_kernel", "chain_column_kernel", "ozaki_update_kernel", "ozaki_slice_kernel", "ozaki_scale_kernel")
 
 
 def main():
