@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the untimed multi-GPU records (row-cyclic ILMM factor, config-5 sweep)")
     ap.add_argument("--ozaki", type=int, default=8, help="digit planes (6/7/8) of the integer-slice (int8 tcgen05) trailing update of the timed path; "
                                                           "0 = FP64 DMMA only (the library's own default; always measured beside it as `dmma_path`)")
+    ap.add_argument("--no-dmma", action="store_true", help="skip the untimed kernel-timing pass and the DMMA comparison (for runs under ncu)")
     ap.add_argument("--streams", type=int, default=0, help="latent groups on separate CUDA streams (0 = library default)")
     args = ap.parse_args()
     p, m, N = args.p, args.m, args.N
@@ -440,7 +441,7 @@ def main():
     # had and for the difference of the results.
     oz_kernel = None
     dmma = None
-    if args.ozaki:
+    if args.ozaki and not args.no_dmma:
         ctx.set_option("streams", 1)
         ctx.set_option("ozaki_time", 1)
         ctx.last_timings()  # drop earlier events

@@ -139,7 +139,8 @@ const char* lmm_version(void);
  *                     FP64.  8 planes truncate at 2^-56 of the row scale (measured normwise factor error 2e-14, DMMA 6e-16 .. 2e-14);
  *                     each plane less costs 2^7 in accuracy and saves ~12 % of the update time.  Default 0 = DMMA (the north
  *                     star's prescription); LMM_OZAKI in the environment sets the initial value.
- *   "ozaki_min_k"     wide updates over fewer k-tiles than this stay on DMMA (default 8: the int8 epilogue costs per output tile)
+ *   "ozaki_min_k"     wide updates over fewer k-tiles than this stay on DMMA (default 4: the int8 epilogue costs per output tile); with
+ *                     "ozaki" on, "outer_block" defaults to 2 tile columns (the in-block updates stay on DMMA)
  *   "ozaki_single_nt" with "ozaki" on, batches <= 2 keep the right-looking DMMA schedule unless the factor has at least this many tile
  *                     rows, from which on it takes the batched schedule and with it the int8 update (default 64, i.e. N >= 8192:
  *                     N = 16384 batch 1: 45.9 -> 30.2 ms, batch 2: 88.9 -> 44.4 ms; 0 = never)

@@ -47,9 +47,10 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
   int ob = ctx->outer_block;
   if (oz && (jstart != 0 || nt <= ob || nt < oz->min_k + 1)) oz = nullptr;  // no wide update this scheme would take
   if (oz) {
-    // narrower blocks: the in-block updates stay on DMMA, and at ob = 4 they are half as much work (measured at 16 latents of
-    // N = 16384: 323 ms at ob = 8, 306 at 4, 315 at 6, 340 at 12)
-    if (!ctx->outer_block_user) ob = 4;
+    // narrow blocks: the in-block updates stay on DMMA, so the narrower the block the less of the work is left at the FP64 rate
+    // (measured at 16 / 8 latents of N = 16384, final kernel: ob = 4: 286.8 / 147.5 ms, ob = 2 with min_k = 4: 275.5 / 143.1,
+    // ob = 1: 274.8 / 147.1, ob = 3: 281.8 / 144.7; with the first kernel generation: 323 ms at ob = 8, 340 at 12)
+    if (!ctx->outer_block_user) ob = 2;
     cudaError_t eo = launch_ozaki_scales(st, L, batch, oz->scale, oz->scale_stride);  // reads the diagonal BEFORE it is factored
     if (eo != cudaSuccess) return eo;
     ++ctx->launches;

@@ -21,7 +21,7 @@ def lmm():
     ctx = lmm_b200.default_context()
     yield lmm_b200
     ctx.set_option("ozaki", int(os.environ.get("LMM_OZAKI", "0")))  # the library default, or what the whole run was started with
-    ctx.set_option("ozaki_min_k", 8)
+    ctx.set_option("ozaki_min_k", 4)
     ctx.set_option("outer_block", 0)
 
 
