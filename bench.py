@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the untimed multi-GPU records (row-cyclic ILMM factor, config-5 sweep)")
     ap.add_argument("--ozaki", type=int, default=8, help="digit planes (6/7/8) of the integer-slice (int8 tcgen05) trailing update of the timed path; "
                                                           "0 = FP64 DMMA only (the library's own default; always measured beside it as `dmma_path`)")
+    ap.add_argument("--ozaki-bits", type=int, default=7, help="bits per digit plane: 7 = radix 128 (8 planes = 55 bits), 8 = radix 256 (7 planes = 54 bits)")
     ap.add_argument("--no-dmma", action="store_true", help="skip the untimed kernel-timing pass and the DMMA comparison (for runs under ncu)")
     ap.add_argument("--streams", type=int, default=0, help="latent groups on separate CUDA streams (0 = library default)")
     args = ap.parse_args()
@@ -364,6 +365,7 @@ def main():
     if args.streams > 0:
         ctx.set_option("streams", args.streams)
     ctx.set_option("ozaki", args.ozaki)
+    ctx.set_option("ozaki_bits", args.ozaki_bits)
     ctx._bench_ozaki = args.ozaki
 
     x, U, S, inv_ls, y, s2 = workload(p, m, N)

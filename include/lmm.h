@@ -139,6 +139,10 @@ const char* lmm_version(void);
  *                     FP64.  8 planes truncate at 2^-56 of the row scale (measured normwise factor error 2e-14, DMMA 6e-16 .. 2e-14);
  *                     each plane less costs 2^7 in accuracy and saves ~12 % of the update time.  Default 0 = DMMA (the north
  *                     star's prescription); LMM_OZAKI in the environment sets the initial value.
+ *   "ozaki_bits"      bits per digit plane: 7 = radix 128, digits |q| <= 64 (default; P planes carry 6 + 7 (P - 1) bits, exact int32 sums for
+ *                     K * P < 524288 columns) or 8 = radix 256, balanced digits in [-128, 127] (6 + 8 (P - 1) bits: 7 planes = 54 bits with 28
+ *                     instead of 36 MMAs per tile product; exact int32 sums for K * P < 131072 columns, i.e. N <= 18724 at 7 planes --
+ *                     beyond that the update of a block column falls back to DMMA).  LMM_OZAKI_BITS sets the initial value.
  *   "ozaki_min_k"     wide updates over fewer k-tiles than this stay on DMMA (default 4: the int8 epilogue costs per output tile); with
  *                     "ozaki" on, "outer_block" defaults to 2 tile columns (the in-block updates stay on DMMA)
  *   "ozaki_single_nt" with "ozaki" on, batches <= 2 keep the right-looking DMMA schedule unless the factor has at least this many tile

@@ -175,6 +175,10 @@ extern "C" int lmm_ctx_create(int device, lmm_ctx** out) {
     const int v = atoi(oz);
     if (v == 6 || v == 7 || v == 8) ctx->ozaki = v;
   }
+  if (const char* ob = getenv("LMM_OZAKI_BITS")) {
+    const int v = atoi(ob);
+    if (v == 7 || v == 8) ctx->ozaki_bits = v;
+  }
   *out = ctx;
   return LMM_OK;
 }
@@ -239,6 +243,9 @@ extern "C" int lmm_ctx_set_option(lmm_ctx* ctx, const char* key, double value) {
   } else if (k == "ozaki") {
     if (value != 0.0 && value != 6.0 && value != 7.0 && value != 8.0) return ctx->fail(LMM_E_ARG, "ozaki must be 0 (DMMA) or 6, 7, 8 (int8 digit planes)");
     ctx->ozaki = (int)value;
+  } else if (k == "ozaki_bits") {
+    if (value != 7.0 && value != 8.0) return ctx->fail(LMM_E_ARG, "ozaki_bits must be 7 (radix 128) or 8 (radix 256)");
+    ctx->ozaki_bits = (int)value;
   } else if (k == "ozaki_time") {
     if (value != 0.0 && value != 1.0) return ctx->fail(LMM_E_ARG, "ozaki_time must be 0 or 1");
     ctx->ozaki_time = (int)value;

@@ -38,7 +38,7 @@ struct OzWs {
   size_t slice_stride;  // bytes per latent
   double* scale;
   size_t scale_stride;  // doubles per latent
-  int S, min_k;
+  int S, min_k, bits;  // digit planes, smallest K (k-tiles) the int8 update takes, bits per digit (7: radix 128, 8: radix 256)
 };
 
 cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double* W, size_t wstride, int batch, double* logdet,
@@ -69,11 +69,11 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
     if (s0 > 0) {
       const int r0 = s0 > jstart ? s0 : jstart;  // first tile row that still has to be computed
       g.i0 = r0; g.j0 = s0; g.k0 = 0; g.k1 = s0;
-      // exact int32 accumulation needs S * K * 64^2 < 2^31
-      if (oz && s0 >= oz->min_k && (long long)s0 * TILE * oz->S * 4096 < (1ll << 31)) {
+      // exact int32 accumulation: (pairs per accumulator <= S) * K * (largest digit)^2 < 2^31
+      if (oz && s0 >= oz->min_k && (long long)s0 * TILE * oz->S * (oz->bits == 8 ? 16384 : 4096) < (1ll << 31)) {
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (ctx->ozaki_time && cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess) cudaEventRecord(ev0, st);
-        e = launch_ozaki_update(st, L, oz->slices, oz->slice_stride, oz->scale, oz->scale_stride, r0, nt - r0, s0, s1 - s0, s0, batch, oz->S);
+        e = launch_ozaki_update(st, L, oz->slices, oz->slice_stride, oz->scale, oz->scale_stride, r0, nt - r0, s0, s1 - s0, s0, batch, oz->S, oz->bits);
         if (ev0 && ev1) {
           cudaEventRecord(ev1, st);
           ctx->oz_events.push_back(ev0);
@@ -117,7 +117,7 @@ cudaError_t chol_factor_stream(lmm_ctx* ctx, cudaStream_t st, TiledSym L, double
       ++ctx->launches;
     }
     if (oz && s1 < nt) {  // the block column is final: digit planes of its tiles below the block, for the later wide updates
-      if ((e = launch_ozaki_slice(st, L, oz->scale, oz->scale_stride, oz->slices, oz->slice_stride, s1, nt - s1, s0, s1 - s0, batch, oz->S)) !=
+      if ((e = launch_ozaki_slice(st, L, oz->scale, oz->scale_stride, oz->slices, oz->slice_stride, s1, nt - s1, s0, s1 - s0, batch, oz->S, oz->bits)) !=
           cudaSuccess)
         return e;
       ++ctx->launches;
@@ -161,7 +161,7 @@ static int ozaki_workspace(lmm_ctx* ctx, int nt, int batch, OzWs& ws) {
     }
     ctx->oz_scale_bytes = have * per_scale * sizeof(double);
   }
-  ws = OzWs{(uint8_t*)ctx->oz_slices, per_slices, ctx->oz_scale, per_scale, ctx->ozaki, ctx->ozaki_min_k};
+  ws = OzWs{(uint8_t*)ctx->oz_slices, per_slices, ctx->oz_scale, per_scale, ctx->ozaki, ctx->ozaki_min_k, ctx->ozaki_bits};
   return (int)have;
 }
 

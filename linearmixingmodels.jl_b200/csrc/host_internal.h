@@ -83,6 +83,7 @@ struct lmm_ctx {
   int dist_error = 0;  // NCCL failure inside the partitioned schedule (reported by the caller)
   // integer-slice (Ozaki) trailing update on the int8 tensor cores: 0 = off (DMMA, default), 6 / 7 / 8 = digit planes
   int ozaki = 0;
+  int ozaki_bits = 7;         // bits per digit plane: 7 = radix 128 (digits |q| <= 64), 8 = radix 256 (digits in [-128, 127])
   int ozaki_time = 0;         // 1: CUDA events around every int8 update launch; their sum (ms) and the tile products they cover are
                               // reported by lmm_ctx_last_timings in slots [7] and [5] (meaningful with "streams" = 1: serial launches)
   std::vector<cudaEvent_t> oz_events;

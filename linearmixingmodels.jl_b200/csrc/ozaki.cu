@@ -119,8 +119,9 @@ __device__ __forceinline__ void oz_epi_store(double* Ctile, int r, int ch, const
   }
 }
 // One pass: the ND int32 accumulators -> exact doubles, Horner in 2^-7, row / column scales, c -= result.
-template <int ND>
+template <int ND, int BITS>
 __device__ __forceinline__ void oz_epi_pass(uint32_t tmem, int quad, int ch, double ps, const double* colscale, double (&c)[64]) {
+  constexpr double RINV = BITS == 8 ? 0.00390625 : 0.0078125;  // 1 / radix
 #pragma unroll
   for (int c0 = 0; c0 < 64; c0 += 4) {
     uint32_t v[ND][4];
@@ -137,16 +138,17 @@ __device__ __forceinline__ void oz_epi_pass(uint32_t tmem, int quad, int ch, dou
     for (int j = 0; j < 4; ++j) {
       double acc = oz_i2d(v[ND - 1][j]);
 #pragma unroll
-      for (int a = ND - 2; a >= 0; --a) acc = fma(acc, 0.0078125, oz_i2d(v[a][j]));
+      for (int a = ND - 2; a >= 0; --a) acc = fma(acc, RINV, oz_i2d(v[a][j]));
       c[c0 + j] = fma(-acc, ps * colscale[64 * ch + c0 + j], c[c0 + j]);
     }
   }
 }
-template <int S>
+template <int S, int BITS>
 __device__ __forceinline__ void oz_epi_both(uint32_t tmem, int quad, int ch, int pass, double rs, const double* colscale, double (&c)[64]) {
   constexpr int NDA = S < 4 ? S : 4, NDB = S > 4 ? S - 4 : 1;
-  if (pass == 0) oz_epi_pass<NDA>(tmem, quad, ch, rs, colscale, c);
-  else oz_epi_pass<NDB>(tmem, quad, ch, rs * 3.7252902984619140625e-09, colscale, c);  // 2^-28: pass B starts at d = 4
+  constexpr double R4 = BITS == 8 ? 2.3283064365386962890625e-10 : 3.7252902984619140625e-09;  // radix^-4: pass B starts at d = 4
+  if (pass == 0) oz_epi_pass<NDA, BITS>(tmem, quad, ch, rs, colscale, c);
+  else oz_epi_pass<NDB, BITS>(tmem, quad, ch, rs * R4, colscale, c);
 }
 
 struct OzakiArgs {
@@ -159,7 +161,7 @@ struct OzakiArgs {
   int S;                      // slices (6, 7 or 8)
 };
 
-template <int S>
+template <int S, int BITS>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g) {
   extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
   const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g
       if (pass && S <= 4) break;
       oz_mb_wait(acc_full, (uint32_t)pass);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      oz_epi_both<S>(tmem, quad, ch, pass, rs, colscale, c);
+      oz_epi_both<S, BITS>(tmem, quad, ch, pass, rs, colscale, c);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       if (pass == 0) oz_mb_arrive(acc_empty);
     }
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(128) ozaki_scale_kernel(TiledSym L, double* __
 
 // ---- slice the finished tiles (I, k), I in [i0, i0 + gridDim.y), k in [k0, k0 + gridDim.x): 256 threads, thread = (row, 16 columns)
 __global__ void __launch_bounds__(256) ozaki_slice_kernel(TiledSym L, const double* __restrict__ scale, size_t scale_batch_stride,
-                                                          uint8_t* __restrict__ slices, size_t slice_batch_stride, int i0, int k0, int S) {
+                                                          uint8_t* __restrict__ slices, size_t slice_batch_stride, int i0, int k0, int S, int bits) {
   const int k = k0 + blockIdx.x, I = i0 + blockIdx.y, b = blockIdx.z;
   const double* tile = L.tile(b, I, k);
   uint8_t* out = slices + (size_t)b * slice_batch_stride + sym_tile_index(I, k) * ((size_t)S * 16384);
@@ -297,6 +299,29 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(TiledSym L, const doub
       y[4 * gq + 0] = a.x * inv; y[4 * gq + 1] = a.y * inv; y[4 * gq + 2] = c.x * inv; y[4 * gq + 3] = c.y * inv;
     }
     uint8_t* dst = out + (size_t)(c16 >> 1) * S * OZ_QB + (size_t)(c16 & 1) * 2048 + (size_t)r * 16;
+    if (bits == 8) {
+      // radix 256, digits in [-128, 127]: X = round(y * 256^(S-1)) as a 64-bit integer (|X| <= 2^(6 + 8 (S-1)) < 2^63), balanced digits
+      // from the bottom with exact carries, the top plane keeps what is left (|q_0| <= 65)
+      uint32_t w[8][4] = {};
+      const double up = __longlong_as_double((long long)(1023 + 8 * (S - 1)) << 52);  // 256^(S-1), exact
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        long long X = __double2ll_rn(y[e] * up);
+#pragma unroll
+        for (int t = 7; t >= 1; --t) {  // (static plane indices: w stays in registers)
+          if (t < S) {
+            const long long q = ((X + 128) & 255) - 128;
+            X = (X - q) >> 8;
+            w[t][e >> 2] |= ((uint32_t)q & 0xFFu) << (8 * (e & 3));
+          }
+        }
+        w[0][e >> 2] |= ((uint32_t)X & 0xFFu) << (8 * (e & 3));
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (t < S) *reinterpret_cast<uint4*>(dst + (size_t)t * OZ_QB) = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+      continue;
+    }
     for (int t = 0; t < S; ++t) {
       uint32_t w[4];
 #pragma unroll
@@ -323,33 +348,41 @@ cudaError_t launch_ozaki_scales(cudaStream_t st, TiledSym L, int batch, double* 
   return cudaGetLastError();
 }
 cudaError_t launch_ozaki_slice(cudaStream_t st, TiledSym L, const double* scale, size_t scale_batch_stride, uint8_t* slices,
-                               size_t slice_batch_stride, int i0, int nrows, int k0, int ncols, int batch, int S) {
+                               size_t slice_batch_stride, int i0, int nrows, int k0, int ncols, int batch, int S, int bits) {
   if (nrows <= 0 || ncols <= 0 || batch <= 0) return cudaSuccess;
   ozaki_slice_kernel<<<dim3((unsigned)ncols, (unsigned)nrows, (unsigned)batch), 256, 0, st>>>(L, scale, scale_batch_stride, slices,
-                                                                                            slice_batch_stride, i0, k0, S);
+                                                                                            slice_batch_stride, i0, k0, S, bits);
   return cudaGetLastError();
 }
-cudaError_t launch_ozaki_update(cudaStream_t st, TiledSym L, const uint8_t* slices, size_t slice_batch_stride, const double* scale,
-                                size_t scale_batch_stride, int i0, int nrows, int j0, int ncols, int k1, int batch, int S) {
-  if (nrows <= 0 || ncols <= 0 || batch <= 0 || k1 <= 0) return cudaSuccess;
-  static bool configured_dev[64] = {false};
+template <int S, int BITS>
+static cudaError_t oz_launch(cudaStream_t st, dim3 grid, const OzakiArgs& a) {
+  static bool configured_dev[64] = {false};  // function attributes are per device (and per instantiation)
   int dev = 0;
   cudaGetDevice(&dev);
   bool& configured = configured_dev[dev & 63];
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ozaki_update_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_update_kernel<S, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
     if (e != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ozaki_update_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ozaki_update_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM)) != cudaSuccess) return e;
     configured = true;
   }
+  ozaki_update_kernel<S, BITS><<<grid, OZ_THREADS, OZ_SMEM, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_ozaki_update(cudaStream_t st, TiledSym L, const uint8_t* slices, size_t slice_batch_stride, const double* scale,
+                                size_t scale_batch_stride, int i0, int nrows, int j0, int ncols, int k1, int batch, int S, int bits) {
+  if (nrows <= 0 || ncols <= 0 || batch <= 0 || k1 <= 0) return cudaSuccess;
   OzakiArgs a{slices, slice_batch_stride, scale, scale_batch_stride, operand(L), i0, j0, k1, S};
   const dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
-  if (S == 8) ozaki_update_kernel<8><<<grid, OZ_THREADS, OZ_SMEM, st>>>(a);
-  else if (S == 7) ozaki_update_kernel<7><<<grid, OZ_THREADS, OZ_SMEM, st>>>(a);
-  else if (S == 6) ozaki_update_kernel<6><<<grid, OZ_THREADS, OZ_SMEM, st>>>(a);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (bits == 8) {
+    if (S == 7) return oz_launch<7, 8>(st, grid, a);
+    if (S == 6) return oz_launch<6, 8>(st, grid, a);
+    if (S == 8) return oz_launch<8, 8>(st, grid, a);
+    return cudaErrorInvalidValue;
+  }
+  if (S == 8) return oz_launch<8, 7>(st, grid, a);
+  if (S == 7) return oz_launch<7, 7>(st, grid, a);
+  if (S == 6) return oz_launch<6, 7>(st, grid, a);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace lmm

@@ -21,6 +21,7 @@ def lmm():
     ctx = lmm_b200.default_context()
     yield lmm_b200
     ctx.set_option("ozaki", int(os.environ.get("LMM_OZAKI", "0")))  # the library default, or what the whole run was started with
+    ctx.set_option("ozaki_bits", int(os.environ.get("LMM_OZAKI_BITS", "7")))
     ctx.set_option("ozaki_min_k", 4)
     ctx.set_option("outer_block", 0)
 
@@ -36,23 +37,25 @@ def spd(N, batch, seed, cond_boost=0.0):
     return A
 
 
-@pytest.mark.parametrize("S,tol", [(8, 5e-14), (7, 2e-11), (6, 2e-9)])
-def test_factor_matches_lapack(lmm, S, tol):
+@pytest.mark.parametrize("S,bits,tol", [(8, 7, 5e-14), (7, 7, 2e-11), (6, 7, 2e-9), (7, 8, 1e-13), (6, 8, 2e-11)])
+def test_factor_matches_lapack(lmm, S, bits, tol):
     """Normwise relative error of L per matrix (rows scaled over e^-3 .. e^3); S = 8 truncates at 2^-56 (FP64 level: measured 2.1e-14
-    against 1.6e-14 for DMMA), every plane less costs 2^7 (measured 2.5e-12 and 3.1e-10)."""
+    against 1.6e-14 for DMMA), every plane less costs 2^7 (measured 2.5e-12 and 3.1e-10).  Radix 256 (bits = 8, balanced digits in
+    [-128, 127]): 7 planes carry 54 bits -- the accuracy of 8 radix-128 planes with 28 instead of 36 MMAs per tile product."""
     ctx = lmm.default_context()
     N, batch = 2600, 3  # 21 tile rows: wide updates at s0 = 8 and 16 take the int8 path (K = 8 and 16 k-tiles)
     A = spd(N, batch, seed=S)
     ctx.set_option("ozaki", 0)
     L0, ld0, info0 = lmm.potrf_batched(A)
     ctx.set_option("ozaki", S)
+    ctx.set_option("ozaki_bits", bits)
     L1, ld1, info1 = lmm.potrf_batched(A)
     assert not info0.any() and not info1.any()
     for b in range(batch):
         Lr = sla.cholesky(A[b], lower=True)
         e0, e1 = relnorm(L0[b], Lr), relnorm(L1[b], Lr)
         assert e0 < 2e-14, e0
-        assert e1 < tol, (S, e1)
+        assert e1 < tol, (S, bits, e1)
         assert abs(ld1[b] - ld0[b]) <= max(1e-11, tol) * abs(ld0[b]) + 1e-9
 
 
@@ -65,11 +68,13 @@ def test_small_k_and_block_widths(lmm):
         for ob, mink in ((2, 1), (3, 2), (5, 4), (0, 4), (8, 8)):
             ctx.set_option("outer_block", ob)
             ctx.set_option("ozaki_min_k", mink)
-            ctx.set_option("ozaki", 8)
-            L, ld, info = lmm.potrf_batched(A)
-            assert not info.any()
-            for b in range(3):
-                assert relnorm(L[b], Lr[b]) < 5e-14, (N, ob, mink)
+            for S, bits in ((8, 7), (7, 8)):
+                ctx.set_option("ozaki", S)
+                ctx.set_option("ozaki_bits", bits)
+                L, ld, info = lmm.potrf_batched(A)
+                assert not info.any()
+                for b in range(3):
+                    assert relnorm(L[b], Lr[b]) < 1e-13, (N, ob, mink, S, bits)
 
 
 def test_not_positive_definite_is_reported(lmm):
@@ -91,10 +96,11 @@ def test_oilmm_against_oracle(lmm):
     om = o.OILMMModel(fs, U, S)
     lp_ref = o.oilmm_logpdf(om, x, 0.05, y)
     Mr, Vr = o.oilmm_mean_and_var(o.oilmm_posterior(om, x, 0.05, y), xs, 0.05)
-    for Sn in (8, 7):
+    for Sn, bits in ((8, 7), (7, 7), (7, 8)):
         ctx.set_option("ozaki", Sn)
+        ctx.set_option("ozaki_bits", bits)
         post, lp = lmm.posterior(f(O(x, p), 0.05), y, with_logpdf=True)
         M, V = lmm.mean_and_var(post(O(xs, p), 0.05))
-        assert abs(lp - lp_ref) <= 1e-9 * abs(lp_ref), (Sn, lp, lp_ref)
-        assert_isapprox(M, Mr, 1e-9, f"posterior mean, {Sn} planes")
-        assert_isapprox(V, Vr, 1e-9, f"posterior variance, {Sn} planes")
+        assert abs(lp - lp_ref) <= 1e-9 * abs(lp_ref), (Sn, bits, lp, lp_ref)
+        assert_isapprox(M, Mr, 1e-9, f"posterior mean, {Sn} planes of {bits} bits")
+        assert_isapprox(V, Vr, 1e-9, f"posterior variance, {Sn} planes of {bits} bits")
