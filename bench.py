@@ -330,9 +330,9 @@ def main():
     ap.add_argument("--N", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the untimed multi-GPU records (row-cyclic ILMM factor, config-5 sweep)")
-    ap.add_argument("--ozaki", type=int, default=8, help="digit planes (6/7/8) of the integer-slice (int8 tcgen05) trailing update of the timed path; "
+    ap.add_argument("--ozaki", type=int, default=7, help="digit planes (6/7/8) of the integer-slice (int8 tcgen05) trailing update of the timed path; "
                                                           "0 = FP64 DMMA only (the library's own default; always measured beside it as `dmma_path`)")
-    ap.add_argument("--ozaki-bits", type=int, default=7, help="bits per digit plane: 7 = radix 128 (8 planes = 55 bits), 8 = radix 256 (7 planes = 54 bits)")
+    ap.add_argument("--ozaki-bits", type=int, default=8, help="bits per digit plane: 7 = radix 128 (8 planes = 55 bits), 8 = radix 256 (7 planes = 54 bits)")
     ap.add_argument("--no-dmma", action="store_true", help="skip the untimed kernel-timing pass and the DMMA comparison (for runs under ncu)")
     ap.add_argument("--streams", type=int, default=0, help="latent groups on separate CUDA streams (0 = library default)")
     args = ap.parse_args()
@@ -488,7 +488,8 @@ def main():
     pipe_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12  # 64 FP64 FMA / clk / SM (DMMA and DFMA share it: profiles/r01_fp64_mix.json)
     if args.ozaki:
         cfg["config"]["trailing_update"] = (
-            f"wide left-looking updates as an integer-slice (Ozaki) product on the int8 tensor cores: {args.ozaki} 7-bit digit planes per FP64 operand, "
+            f"wide left-looking updates as an integer-slice (Ozaki) product on the int8 tensor cores: {args.ozaki} digit planes of {args.ozaki_bits} bits per FP64 operand "
+            f"({6 + args.ozaki_bits * (args.ozaki - 1)} bits below the row scale), "
             f"{args.ozaki * (args.ozaki + 1) // 2} tcgen05.mma kind::i8 per 128^3 tile product, exact int32 accumulation in TMEM, FP64 recombination; panels, in-block "
             "updates, triangular solves, kernel matrices in FP64 (DMMA / DFMA).  The library default is DMMA everywhere (--ozaki 0): measured beside it as dmma_path")
     dmma_roofline = {"bound": "tensor", "kernel": "batched blocked Cholesky (gemm_tile_kernel_v2 DMMA updates + TRSM-as-GEMM + potrf_tile_kernel2)",

@@ -33,11 +33,13 @@ def main():
     ap.add_argument("--passes", type=int, default=2)
     ap.add_argument("--solve-impl", type=int, default=1)
     ap.add_argument("--ozaki", type=int, default=0, help="int8 digit planes of the optional integer-slice trailing update (0 = DMMA)")
+    ap.add_argument("--ozaki-bits", type=int, default=7, help="bits per digit plane (7: radix 128, 8: radix 256)")
     args = ap.parse_args()
     ctx = lmm.default_context()
     ctx.set_option("streams", 1)
     ctx.set_option("solve_impl", args.solve_impl)
     ctx.set_option("ozaki", args.ozaki)
+    ctx.set_option("ozaki_bits", args.ozaki_bits)
     rng = np.random.default_rng(0)
     if args.mode == "chol":
         x = np.sort(rng.uniform(0, args.N / 100.0, args.N))
