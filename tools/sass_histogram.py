@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Opcode histogram per kernel of liblmm.so (cuobjdump -sass): the SASS proof of what each kernel runs on --
 DMMA.8x8x4 (FP64 tensor core), UBLKCP (cp.async.bulk, the TMA bulk-copy engine), SYNCS (mbarrier), LDGSTS (cp.async),
-ACQBULK / PREEXIT (programmatic dependent launch), DFMA / DADD / DMUL (FP64 pipe), MUFU (RCP64H / RSQ64H seeds).
+ACQBULK / PREEXIT (programmatic dependent launch), DFMA / DADD / DMUL (FP64 pipe), MUFU (RCP64H / RSQ64H seeds), UTCIMMA (tcgen05.mma kind::i8),
+UTCBAR (tcgen05.commit), UTCATOMSWS (TMEM allocation), LDTM (tcgen05.ld).
 
     python tools/sass_histogram.py > profiles/r02_sass_opcodes.txt
 """
@@ -14,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "linearmixingmodels.jl_b200", "liblmm.so")
 INTEREST = ["DMMA", "UBLKCP", "SYNCS", "LDGSTS", "ACQBULK", "PREEXIT", "DFMA", "DADD", "DMUL", "MUFU", "LDS", "STS", "LDG", "STG", "BAR", "SHFL",
-            "NANOSLEEP", "ATOM", "RED", "UTMALDG", "UTCHMMA", "LDTM"]
+            "NANOSLEEP", "ATOM", "RED", "UTMALDG", "UTCHMMA", "UTCIMMA", "UTCBAR", "UTCATOMSWS", "LDTM"]
 
 
 def main():
