@@ -195,6 +195,7 @@ extern "C" int lmm_ctx_destroy(lmm_ctx* ctx) {
   if (ctx->xbuf) cudaFree(ctx->xbuf);
   if (ctx->oz_slices) cudaFree(ctx->oz_slices);
   if (ctx->oz_scale) cudaFree(ctx->oz_scale);
+  if (ctx->oz_x) cudaFree(ctx->oz_x);
   cudaStreamDestroy(ctx->panel_stream);
   cudaStreamDestroy(ctx->update_stream);
   for (auto& e : ctx->blk_ev) cudaEventDestroy(e);

@@ -587,10 +587,32 @@ cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int
   return cudaSuccess;
 }
 
+// Workspace of the integer-slice path of the prediction sweep for the latents [0, batch) of one trsm_right_lt_stream call: digit planes
+// and row scales of the finished factor (right operand) and of the finished columns of X (left operand).
+struct OzPred {
+  uint8_t* lsl; size_t lsl_stride; double* lsc; size_t lsc_stride;
+  uint8_t* xsl; size_t xsl_stride; double* xsc; size_t xsc_stride;
+  const LatentParams* params;  // kdiag = k(x*, x*) bounds the squared row norms of X = K(x*,x) L^{-T}
+  int S, bits, min_k;
+};
+
 // X <- X L^{-T} for a rectangular tiled X (rows = e.g. test points): the same update/TRSM sweep
-// with X's tile rows appended under the factor.
-cudaError_t trsm_right_lt_stream(lmm_ctx* ctx, cudaStream_t st, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch) {
-  const int nt = L.nt, ob = ctx->outer_block;
+// with X's tile rows appended under the factor.  With `oz` the wide updates (K = s0 k-tiles against all finished columns) run as
+// integer-slice products on the int8 tensor cores, exactly as in chol_factor_stream: the factor is sliced once up front (row scales =
+// row 2-norms of L), every finished block column of X right after its TRSM (row scales from the prior variance).
+cudaError_t trsm_right_lt_stream(lmm_ctx* ctx, cudaStream_t st, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch,
+                                 const OzPred* oz = nullptr) {
+  const int nt = L.nt;
+  int ob = ctx->outer_block;
+  cudaError_t e;
+  if (oz && nt <= 8) oz = nullptr;
+  if (oz) {
+    if (!ctx->outer_block_user) ob = 2;
+    if ((e = launch_ozaki_factor_scales(st, L, batch, oz->lsc, oz->lsc_stride)) != cudaSuccess) return e;
+    if ((e = launch_ozaki_slice(st, L, oz->lsc, oz->lsc_stride, oz->lsl, oz->lsl_stride, 1, nt - 1, 0, nt - 1, batch, oz->S, oz->bits)) != cudaSuccess) return e;
+    if ((e = launch_ozaki_const_scales(st, oz->params, X.ntr, batch, oz->xsc, oz->xsc_stride)) != cudaSuccess) return e;
+    ctx->launches += 3;
+  }
   GemmArgs g{};
   g.A = operand(X);
   g.B = operand(L);
@@ -599,12 +621,16 @@ cudaError_t trsm_right_lt_stream(lmm_ctx* ctx, cudaStream_t st, TiledRect X, Til
   g.w_batch_stride = wstride;
   g.sym = 0;
   g.i0 = 0;
-  cudaError_t e;
   for (int s0 = 0; s0 < nt; s0 += ob) {
     const int s1 = (s0 + ob < nt) ? s0 + ob : nt;
     if (s0 > 0) {
       g.j0 = s0; g.k0 = 0; g.k1 = s0;
-      if ((e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, X.ntr, batch)) != cudaSuccess) return e;
+      if (oz && s0 >= oz->min_k && (long long)s0 * TILE * oz->S * (oz->bits == 8 ? 16384 : 4096) < (1ll << 31))
+        e = launch_ozaki_update_rect(st, X, oz->xsl, oz->xsl_stride, oz->xsc, oz->xsc_stride, oz->lsl, oz->lsl_stride, oz->lsc, oz->lsc_stride, s0,
+                                     s1 - s0, s0, batch, oz->S, oz->bits);
+      else
+        e = launch_gemm(st, GEMM_UPDATE, g, s1 - s0, X.ntr, batch);
+      if (e != cudaSuccess) return e;
       ++ctx->launches;
     }
     for (int jj = s0; jj < s1; ++jj) {
@@ -617,13 +643,53 @@ cudaError_t trsm_right_lt_stream(lmm_ctx* ctx, cudaStream_t st, TiledRect X, Til
       if ((e = launch_gemm(st, GEMM_TRSM, g, 1, X.ntr, batch)) != cudaSuccess) return e;
       ++ctx->launches;
     }
+    if (oz && s1 < nt) {  // the block column of X is final: its digit planes, for the later wide updates
+      if ((e = launch_ozaki_slice_rect(st, X, oz->xsc, oz->xsc_stride, oz->xsl, oz->xsl_stride, s0, s1 - s0, batch, oz->S, oz->bits)) != cudaSuccess) return e;
+      ++ctx->launches;
+    }
   }
   return cudaSuccess;
 }
 
-cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch) {
+// `xbound` (device, one LatentParams per latent of the batch; nullable): kdiag bounds the squared row norms of the result -- what the
+// integer-slice path needs to fix the row scales of X in advance.  Without it, or with the option off, every update runs on DMMA.
+cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch, const LatentParams* xbound) {
   const int G = ctx->ngroups < batch ? ctx->ngroups : batch;
-  if (G <= 1) return trsm_right_lt_stream(ctx, ctx->stream, X, L, W, wstride, batch);
+  OzPred oz{};
+  bool use_oz = false;
+  if (ctx->ozaki && xbound && L.nt > 8 && L.ntc == 0 && L.cyc_G == 0) {
+    OzWs ws{};
+    if (ozaki_workspace(ctx, L.nt, batch, ws) >= batch) {
+      const size_t per_x = (size_t)X.ntr * X.ntc * ctx->ozaki * 16384, per_xs = (size_t)X.ntr * TILE;
+      const size_t need = (size_t)batch * (per_x + per_xs * sizeof(double));
+      if (ctx->oz_x_bytes < need) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->oz_x) cudaFree(ctx->oz_x);
+        ctx->oz_x = nullptr;
+        ctx->oz_x_bytes = 0;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > need + ((size_t)4 << 30) && cudaMalloc(&ctx->oz_x, need) == cudaSuccess)
+          ctx->oz_x_bytes = need;
+        else
+          cudaGetLastError();
+      }
+      if (ctx->oz_x_bytes >= need) {
+        use_oz = true;
+        oz = OzPred{ws.slices, ws.slice_stride, ws.scale, ws.scale_stride, (uint8_t*)ctx->oz_x, per_x,
+                    (double*)((uint8_t*)ctx->oz_x + (size_t)batch * per_x), per_xs, xbound, ws.S, ws.bits, ws.min_k};
+      }
+    }
+  }
+  auto oz_at = [&](int b0, OzPred& tmp) -> const OzPred* {
+    if (!use_oz) return nullptr;
+    tmp = oz;
+    tmp.lsl += (size_t)b0 * oz.lsl_stride; tmp.lsc += (size_t)b0 * oz.lsc_stride;
+    tmp.xsl += (size_t)b0 * oz.xsl_stride; tmp.xsc += (size_t)b0 * oz.xsc_stride;
+    tmp.params += b0;
+    return &tmp;
+  };
+  OzPred t0{};
+  if (G <= 1) return trsm_right_lt_stream(ctx, ctx->stream, X, L, W, wstride, batch, oz_at(0, t0));
   cudaError_t e;
   if ((e = cudaEventRecord(ctx->ev_fork, ctx->stream)) != cudaSuccess) return e;
   for (int gi = 0; gi < G; ++gi) {
@@ -632,7 +698,8 @@ cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W
     if ((e = cudaStreamWaitEvent(st, ctx->ev_fork, 0)) != cudaSuccess) return e;
     TiledRect Xg{X.base + (size_t)b0 * X.batch_stride, X.ntr, X.ntc, X.batch_stride};
     TiledSym Lg{L.base + (size_t)b0 * L.batch_stride, L.nt, L.batch_stride};
-    if ((e = trsm_right_lt_stream(ctx, st, Xg, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0)) != cudaSuccess) return e;
+    OzPred tg{};
+    if ((e = trsm_right_lt_stream(ctx, st, Xg, Lg, W + (size_t)b0 * wstride, wstride, b1 - b0, oz_at(b0, tg))) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ctx->ev_join[gi], st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join[gi], 0)) != cudaSuccess) return e;
   }

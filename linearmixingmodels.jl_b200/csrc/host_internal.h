@@ -92,6 +92,8 @@ struct lmm_ctx {
   int ozaki_min_k = 4;        // wide updates over fewer k-tiles stay on DMMA (the int8 epilogue is per output tile, not per k)
   void* oz_slices = nullptr;  // [latents in flight][sym_tiles][S * 16 KB], grown on demand
   size_t oz_slices_bytes = 0;
+  void* oz_x = nullptr;       // prediction sweep: digit planes + row scales of X
+  size_t oz_x_bytes = 0;
   double* oz_scale = nullptr;
   size_t oz_scale_bytes = 0;
   void* xbuf = nullptr;  // exchange buffers of the row-cyclic schedule (send | all-gathered), grown on demand
@@ -334,7 +336,7 @@ cudaError_t chol_factor_rowcyclic_dist(lmm_ctx* ctx, TiledSym Lown, int nrows, i
                                        double* zvec);
 size_t rowcyclic_dist_workspace_tiles(int nrows, int G, int ob);
 int rowcyclic_dist_block(const lmm_ctx* ctx, int nc);
-cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch);
+cudaError_t trsm_right_lt(lmm_ctx* ctx, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch, const LatentParams* xbound = nullptr);
 cudaError_t trsm_right_lt_upper(lmm_ctx* ctx, cudaStream_t st, TiledRect X, TiledSym L, const double* W, size_t wstride, int batch);
 
 }  // namespace lmm_host

@@ -390,7 +390,7 @@ int post_latent_marginals(lmm_post* post, const double* d_xspad, int Ns, int nts
     CU(launch_kmat_cross(st, V, nb, d_xspad, Ns, post->d_xpad, post->N, post->D, dp, ctx->distance_form));
     CU(launch_rect_gemv(st, V, post->d_alpha + (size_t)g0 * post->npad(), post->npad(), d_ML + (size_t)c0 * nspad, nspad, dp, 1, nb));
     ctx->launches += 2;
-    CU(trsm_right_lt(ctx, V, Lc, Wc, post->wstride(), nb));
+    CU(trsm_right_lt(ctx, V, Lc, Wc, post->wstride(), nb, dp));  // dp: k(x*,x*) bounds the row norms (int8 path, if the option is on)
     CU(launch_rect_rowsumsq(st, V, d_VL + (size_t)c0 * nspad, nspad, dp, nb));
     ++ctx->launches;
   }

@@ -159,13 +159,19 @@ struct OzakiArgs {
   TileOperand C;
   int i0, j0, k1;             // tile (I, J) = (i0 + blockIdx.y, j0 + blockIdx.x); k-tiles [0, k1)
   int S;                      // slices (6, 7 or 8)
+  // left operand from a RECTANGULAR sliced matrix X (prediction: X L^{-T} sweep) instead of the factor itself; null = the factor
+  const uint8_t* a_slices;    // [batch][ntr * a_ntc tiles][S * 16384]
+  size_t a_batch_stride;      // bytes
+  int a_ntc;                  // tiles per row of X
+  const double* a_scale;      // [batch][ntr * 128]
+  size_t a_scale_stride;
 };
 
 template <int S, int BITS>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g) {
   extern __shared__ __align__(1024) uint8_t oz_smem_raw[];
   const int J = g.j0 + blockIdx.x, I = g.i0 + blockIdx.y, b = blockIdx.z;
-  if (I < J) return;
+  if (!g.a_slices && I < J) return;
   // 1024-aligned carve-up: stages, then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 127) & ~(uintptr_t)127);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)OZ_RING_BYTES);
@@ -197,7 +203,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g
   if (warp == 8) {
     // ===== producer: per K quarter one bulk copy of the needed slices of A(I,k) and one of B(J,k)
     if (lane == 0) {
-      const uint8_t* Abase = g.slices + (size_t)b * g.slice_batch_stride + sym_tile_index(I, 0) * tile_bytes;
+      const uint8_t* Abase = g.a_slices ? g.a_slices + (size_t)b * g.a_batch_stride + (size_t)I * g.a_ntc * tile_bytes
+                                        : g.slices + (size_t)b * g.slice_batch_stride + sym_tile_index(I, 0) * tile_bytes;
       const uint8_t* Bbase = g.slices + (size_t)b * g.slice_batch_stride + sym_tile_index(J, 0) * tile_bytes;
       for (int pass = 0; pass < 2; ++pass) {
         const int ns = pass ? S : nsA;
@@ -247,7 +254,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g
   } else {
     // ===== epilogue (warps 0-7): C(I,J) lives in registers from here to the end
     const int quad = warp & 3, ch = warp >> 2, r = quad * 32 + lane;
-    const double rs = g.scale[(size_t)b * g.scale_batch_stride + (size_t)I * TILE + r];
+    const double rs = g.a_slices ? g.a_scale[(size_t)b * g.a_scale_stride + (size_t)I * TILE + r]
+                                 : g.scale[(size_t)b * g.scale_batch_stride + (size_t)I * TILE + r];
     double* Ctile = g.C.tile(b, I, J);
     double c[64];
     oz_epi_load(Ctile, r, ch, c);
@@ -283,11 +291,14 @@ __global__ void __launch_bounds__(128) ozaki_scale_kernel(TiledSym L, double* __
 }
 
 // ---- slice the finished tiles (I, k), I in [i0, i0 + gridDim.y), k in [k0, k0 + gridDim.x): 256 threads, thread = (row, 16 columns)
-__global__ void __launch_bounds__(256) ozaki_slice_kernel(TiledSym L, const double* __restrict__ scale, size_t scale_batch_stride,
-                                                          uint8_t* __restrict__ slices, size_t slice_batch_stride, int i0, int k0, int S, int bits) {
+// out_ntc = 0: the factor (packed-lower tile order, tiles with k > I skipped); > 0: a rectangular matrix with out_ntc tiles per row
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(TileOperand L, const double* __restrict__ scale, size_t scale_batch_stride,
+                                                          uint8_t* __restrict__ slices, size_t slice_batch_stride, int i0, int k0, int S, int bits,
+                                                          int out_ntc) {
   const int k = k0 + blockIdx.x, I = i0 + blockIdx.y, b = blockIdx.z;
+  if (!out_ntc && k > I) return;
   const double* tile = L.tile(b, I, k);
-  uint8_t* out = slices + (size_t)b * slice_batch_stride + sym_tile_index(I, k) * ((size_t)S * 16384);
+  uint8_t* out = slices + (size_t)b * slice_batch_stride + (out_ntc ? (size_t)I * out_ntc + k : sym_tile_index(I, k)) * ((size_t)S * 16384);
   for (int it = threadIdx.x; it < 1024; it += 256) {
     const int r = it & 127, c16 = it >> 7;  // 16 columns c16*16 .. +15 of row r
     const double inv = 1.0 / scale[(size_t)b * scale_batch_stride + (size_t)I * TILE + r];  // 2^(6 - E): exact
@@ -350,8 +361,49 @@ cudaError_t launch_ozaki_scales(cudaStream_t st, TiledSym L, int batch, double* 
 cudaError_t launch_ozaki_slice(cudaStream_t st, TiledSym L, const double* scale, size_t scale_batch_stride, uint8_t* slices,
                                size_t slice_batch_stride, int i0, int nrows, int k0, int ncols, int batch, int S, int bits) {
   if (nrows <= 0 || ncols <= 0 || batch <= 0) return cudaSuccess;
-  ozaki_slice_kernel<<<dim3((unsigned)ncols, (unsigned)nrows, (unsigned)batch), 256, 0, st>>>(L, scale, scale_batch_stride, slices,
-                                                                                            slice_batch_stride, i0, k0, S, bits);
+  ozaki_slice_kernel<<<dim3((unsigned)ncols, (unsigned)nrows, (unsigned)batch), 256, 0, st>>>(operand(L), scale, scale_batch_stride, slices,
+                                                                                            slice_batch_stride, i0, k0, S, bits, 0);
+  return cudaGetLastError();
+}
+cudaError_t launch_ozaki_slice_rect(cudaStream_t st, TiledRect X, const double* scale, size_t scale_batch_stride, uint8_t* slices,
+                                    size_t slice_batch_stride, int k0, int ncols, int batch, int S, int bits) {
+  if (X.ntr <= 0 || ncols <= 0 || batch <= 0) return cudaSuccess;
+  ozaki_slice_kernel<<<dim3((unsigned)ncols, (unsigned)X.ntr, (unsigned)batch), 256, 0, st>>>(operand(X), scale, scale_batch_stride, slices,
+                                                                                             slice_batch_stride, 0, k0, S, bits, X.ntc);
+  return cudaGetLastError();
+}
+
+// ---- row scales for the prediction sweep X <- X L^{-T}.  Rows of the finished factor: 2^E > ||L(i,:)||_2 (one pass over the row panel);
+// rows of X = K(x*,x) L^{-T}: ||X(r,:)||^2 <= k(x*,x*), the prior variance (LatentParams.kdiag).
+__global__ void __launch_bounds__(128) ozaki_factor_scale_kernel(TiledSym L, double* __restrict__ scale, size_t scale_batch_stride) {
+  const int I = blockIdx.x, b = blockIdx.y, r = threadIdx.x;
+  double s = 0.0;
+  for (int J = 0; J <= I; ++J) {
+    const double* t = L.tile(b, I, J);
+    for (int c4 = 0; c4 < 32; ++c4) {
+      const double2* p = reinterpret_cast<const double2*>(t + (size_t)c4 * 512 + 4 * r);
+      const double2 a = p[0], c = p[1];
+      s = fma(a.x, a.x, s); s = fma(a.y, a.y, s); s = fma(c.x, c.x, s); s = fma(c.y, c.y, s);
+    }
+  }
+  int e = 0;
+  if (s > 0.0 && s < 1e300) e = ilogb(sqrt(s) * 1.0000001) + 1;
+  scale[(size_t)b * scale_batch_stride + (size_t)I * TILE + r] = scalbn(1.0, e - 6);
+}
+__global__ void __launch_bounds__(128) ozaki_const_scale_kernel(const LatentParams* __restrict__ params, double* __restrict__ scale,
+                                                                size_t scale_batch_stride) {
+  const int R = blockIdx.x, b = blockIdx.y, r = threadIdx.x;
+  const double v = params[b].kdiag;
+  int e = 0;
+  if (v > 0.0 && v < 1e300) e = ilogb(sqrt(v) * 1.0000001) + 1;
+  scale[(size_t)b * scale_batch_stride + (size_t)R * TILE + r] = scalbn(1.0, e - 6);
+}
+cudaError_t launch_ozaki_factor_scales(cudaStream_t st, TiledSym L, int batch, double* scale, size_t scale_batch_stride) {
+  ozaki_factor_scale_kernel<<<dim3((unsigned)L.nt, (unsigned)batch), 128, 0, st>>>(L, scale, scale_batch_stride);
+  return cudaGetLastError();
+}
+cudaError_t launch_ozaki_const_scales(cudaStream_t st, const LatentParams* params, int ntr, int batch, double* scale, size_t scale_batch_stride) {
+  ozaki_const_scale_kernel<<<dim3((unsigned)ntr, (unsigned)batch), 128, 0, st>>>(params, scale, scale_batch_stride);
   return cudaGetLastError();
 }
 template <int S, int BITS>
@@ -368,11 +420,25 @@ static cudaError_t oz_launch(cudaStream_t st, dim3 grid, const OzakiArgs& a) {
   ozaki_update_kernel<S, BITS><<<grid, OZ_THREADS, OZ_SMEM, st>>>(a);
   return cudaGetLastError();
 }
+cudaError_t oz_dispatch(cudaStream_t st, dim3 grid, const OzakiArgs& a, int S, int bits);
 cudaError_t launch_ozaki_update(cudaStream_t st, TiledSym L, const uint8_t* slices, size_t slice_batch_stride, const double* scale,
                                 size_t scale_batch_stride, int i0, int nrows, int j0, int ncols, int k1, int batch, int S, int bits) {
   if (nrows <= 0 || ncols <= 0 || batch <= 0 || k1 <= 0) return cudaSuccess;
-  OzakiArgs a{slices, slice_batch_stride, scale, scale_batch_stride, operand(L), i0, j0, k1, S};
+  OzakiArgs a{slices, slice_batch_stride, scale, scale_batch_stride, operand(L), i0, j0, k1, S, nullptr, 0, 0, nullptr, 0};
   const dim3 grid((unsigned)ncols, (unsigned)nrows, (unsigned)batch);
+  return oz_dispatch(st, grid, a, S, bits);
+}
+// X(R, J) -= sum_{k < k1} X(R,k) L(J,k)' for all tile rows R of the rectangular X and J in [j0, j0 + ncols): the wide update of the
+// prediction sweep X <- X L^{-T}, left operand from the sliced finished columns of X, right operand from the sliced factor.
+cudaError_t launch_ozaki_update_rect(cudaStream_t st, TiledRect X, const uint8_t* xslices, size_t xslice_batch_stride, const double* xscale,
+                                     size_t xscale_stride, const uint8_t* lslices, size_t lslice_batch_stride, const double* lscale,
+                                     size_t lscale_stride, int j0, int ncols, int k1, int batch, int S, int bits) {
+  if (X.ntr <= 0 || ncols <= 0 || batch <= 0 || k1 <= 0) return cudaSuccess;
+  OzakiArgs a{lslices, lslice_batch_stride, lscale, lscale_stride, operand(X), 0, j0, k1, S, xslices, xslice_batch_stride, X.ntc, xscale, xscale_stride};
+  const dim3 grid((unsigned)ncols, (unsigned)X.ntr, (unsigned)batch);
+  return oz_dispatch(st, grid, a, S, bits);
+}
+cudaError_t oz_dispatch(cudaStream_t st, dim3 grid, const OzakiArgs& a, int S, int bits) {
   if (bits == 8) {
     if (S == 7) return oz_launch<7, 8>(st, grid, a);
     if (S == 6) return oz_launch<6, 8>(st, grid, a);

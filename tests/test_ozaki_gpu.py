@@ -89,7 +89,7 @@ def test_not_positive_definite_is_reported(lmm):
 def test_oilmm_against_oracle(lmm):
     """logpdf, posterior marginals: the north star's 1e-9 with the int8 trailing update (N = 3000: 24 tile rows)."""
     ctx = lmm.default_context()
-    N, p, m, Ns = 3000, 6, 5, 64
+    N, p, m, Ns = 3000, 6, 5, 300  # 24 tile rows of the factor, 3 (ragged) tile rows of test points: the int8 path also runs the prediction sweep
     x, xs, U, S, fs, y = make_problem(N, p, m, Ns, seed=21)
     f = lmm.ILMM(lmm.independent_mogp([to_lmm_gp(lmm, g) for g in fs]), lmm.Orthogonal(U, S))
     O = lmm.MOInputIsotopicByOutputs
