@@ -556,7 +556,7 @@ def main():
         lmm.set_default_context(ctx)
         out["sharded_vs_unsharded"] = {
             "what": f"{world}-rank sharded eval (NCCL all-reduce of lml terms; prediction at {Ns_chk} points with the NCCL all-reduce of the "
-                    "partial back-projections) vs the same calls on one GPU",
+                    "partial back-projections; the timed path) vs the same calls on one GPU in a fresh context with the library's defaults (FP64 DMMA everywhere)",
             "logpdf_rel": abs(lp_s - lp_u) / abs(lp_u),
             "mean_relnorm": float(np.linalg.norm(M_s - M_u) / np.linalg.norm(M_u)),
             "var_max_rel": float(np.max(np.abs(V_s - V_u) / np.abs(V_u)))}
