@@ -135,8 +135,9 @@ const char* lmm_version(void);
  *                     0 = re-factorise the union of the inputs, O((N + N₂)³)
  *   "ozaki"           6 | 7 | 8: the WIDE trailing update of the batched blocked Cholesky runs as an integer-slice (Ozaki-scheme) product on
  *                     the int8 tensor cores (tcgen05.mma kind::i8, exact int32 accumulation in TMEM) with that many 7-bit digit
- *                     planes per FP64 operand, instead of FP64 DMMA; everything else (panels, in-block updates, solves) stays
- *                     FP64.  8 planes truncate at 2^-56 of the row scale (measured normwise factor error 2e-14, DMMA 6e-16 .. 2e-14);
+ *                     planes per FP64 operand, instead of FP64 DMMA -- and so do the wide updates of the prediction sweep K(x*,x) L^{-T} of
+ *                     per-latent posteriors (mean_and_var / marginals); everything else (panels, in-block updates, TRSMs, solves, kernel
+ *                     matrices) stays FP64.  8 planes truncate at 2^-56 of the row scale (measured normwise factor error 2e-14, DMMA 6e-16 .. 2e-14);
  *                     each plane less costs 2^7 in accuracy and saves ~12 % of the update time.  Default 0 = DMMA (the north
  *                     star's prescription); LMM_OZAKI in the environment sets the initial value.
  *   "ozaki_bits"      bits per digit plane: 7 = radix 128, digits |q| <= 64 (default; P planes carry 6 + 7 (P - 1) bits, exact int32 sums for
@@ -146,8 +147,9 @@ const char* lmm_version(void);
  *   "ozaki_min_k"     wide updates over fewer k-tiles than this stay on DMMA (default 4: the int8 epilogue costs per output tile); with
  *                     "ozaki" on, "outer_block" defaults to 2 tile columns (the in-block updates stay on DMMA)
  *   "ozaki_single_nt" with "ozaki" on, batches <= 2 keep the right-looking DMMA schedule unless the factor has at least this many tile
- *                     rows, from which on it takes the batched schedule and with it the int8 update (default 64, i.e. N >= 8192:
- *                     N = 16384 batch 1: 45.9 -> 30.2 ms, batch 2: 88.9 -> 44.4 ms; 0 = never)
+ *                     rows (two thirds of it for a batch of 2), from which on it takes the batched schedule and with it the int8 update
+ *                     (default 96, i.e. N >= 12288: N = 16384: 45.9 -> 33 ms, two factors 88.9 -> 44 ms, while a single N = 8192
+ *                     factor is faster on the right-looking DMMA schedule: 7.1 vs 8.6 ms; 0 = never)
  *   "ozaki_time"      1 = time every int8 update launch with CUDA events: see lmm_ctx_last_timings (default 0)
  *   "solve_impl"      triangular vector solves (z = L^{-1} r, a = L^{-T} z): 1 = ONE persistent launch per direction, tile rows /
  *                     columns chained through ready flags in global memory (default); 0 = one launch per tile column

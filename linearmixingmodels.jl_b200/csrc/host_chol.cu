@@ -537,7 +537,8 @@ cudaError_t chol_factor(lmm_ctx* ctx, TiledSym L, double* W, size_t wstride, int
       return chol_factor_rowcyclic(ctx, L, W, wstride, logdet, info);
     // (with the integer-slice update on, a LARGE single factor is faster on the batched left-looking schedule: its wide updates run
     // at 2-3x the DMMA rate, which outweighs the exposed panel chain -- "ozaki_single_nt" tile rows and up)
-    const bool oz_single = ctx->ozaki && ctx->ozaki_single_nt > 0 && L.nt >= ctx->ozaki_single_nt;
+    // (measured, 7 planes of 8 bits: N = 16384: 45.9 -> 33.1 ms, two factors 88.9 -> 44.4 ms; N = 8192: 7.1 -> 8.6 ms, two: 12.6 -> 8.7 ms)
+    const bool oz_single = ctx->ozaki && ctx->ozaki_single_nt > 0 && L.nt >= (batch == 1 ? ctx->ozaki_single_nt : ctx->ozaki_single_nt * 2 / 3);
     if (ctx->lookahead && batch <= 2 && L.nt >= 12 && !oz_single) return chol_factor_rightlooking(ctx, L, W, wstride, batch, logdet, info);
   }
   cudaError_t e;

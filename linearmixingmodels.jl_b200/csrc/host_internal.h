@@ -88,7 +88,7 @@ struct lmm_ctx {
                               // reported by lmm_ctx_last_timings in slots [7] and [5] (meaningful with "streams" = 1: serial launches)
   std::vector<cudaEvent_t> oz_events;
   double oz_tile_products = 0.0;
-  int ozaki_single_nt = 64;   // batch <= 2: use the batched schedule (and with it the int8 update) from this many tile rows on (0 = never)
+  int ozaki_single_nt = 96;   // batch <= 2: use the batched schedule (and with it the int8 update) from this many tile rows on (0 = never)
   int ozaki_min_k = 4;        // wide updates over fewer k-tiles stay on DMMA (the int8 epilogue is per output tile, not per k)
   void* oz_slices = nullptr;  // [latents in flight][sym_tiles][S * 16 KB], grown on demand
   size_t oz_slices_bytes = 0;
