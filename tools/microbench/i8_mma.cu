@@ -229,6 +229,88 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ---- A operand from TENSOR MEMORY (tcgen05.mma ... [d], [a_tmem], b_desc): the A planes of a stage are copied shared -> tensor memory
+// once (tcgen05.cp 128x256b: 128 rows x 32 bytes = one K = 32 operand, 8 TMEM columns) and every MMA then reads only B from shared
+// memory -- 4 KB instead of 8 KB per MMA.  Checks the copy + the TS form against the CPU and times the TS issue rate.
+__device__ __forceinline__ void cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__global__ void __launch_bounds__(128, 1) i8_mma_ts_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int32_t* __restrict__ D,
+                                                           int reps, int recopy, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * 128;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * 128 / 16; i += 128) reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(A)[i];
+  for (int i = tid; i < 128 * 128 / 16; i += 128) reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(B)[i];
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  constexpr uint32_t idesc = make_idesc_i8(128, 128);
+  const uint32_t a0 = s_u32(sA), b0 = s_u32(sB);
+  const uint32_t acol = 384;  // A staging area: columns 384 .. 415 (4 K-steps x 8 columns)
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) {
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (r == 0 || recopy) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) cp_128x256b(tmem + acol + 8 * ks, make_sdesc(a0 + ks * 2 * (128 * 16), 128 * 16, 128));
+      }
+      const uint32_t dcol = (uint32_t)((r % 3) * 128);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_i8_ts(tmem + dcol, tmem + acol + 8 * ks, make_sdesc(b0 + ks * 2 * (128 * 16), 128 * 16, 128), idesc, (r >= 3 || ks > 0) ? 1u : 0u);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) {
+    t1 = clock64();
+    if (cycles) cycles[blockIdx.x] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (D && blockIdx.x == 0) {
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+          "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+            "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 32; ++j) D[(size_t)tid * 128 + c0 + j] = (int32_t)v[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 static size_t canon(int R, int r, int k) { return (size_t)(k / 16) * (R / 8 * 128) + (size_t)(r / 8) * 128 + (r % 8) * 16 + (k % 16); }
 
 template <int N>
@@ -367,6 +449,66 @@ static int run_2cta(int sms) {
   return bad == 0;
 }
 
+static int run_ts(int sms) {
+  std::vector<int8_t> hA(128 * 128), hB(128 * 128), cA(128 * 128), cB(128 * 128);
+  srand(1234);
+  for (auto& v : hA) v = (int8_t)(rand() % 256 - 128);
+  for (auto& v : hB) v = (int8_t)(rand() % 256 - 128);
+  for (int r = 0; r < 128; ++r)
+    for (int k = 0; k < 128; ++k) {
+      cA[canon(128, r, k)] = hA[r * 128 + k];
+      cB[canon(128, r, k)] = hB[r * 128 + k];
+    }
+  int8_t *dA, *dB;
+  int32_t* dD;
+  long long* dC;
+  CK(cudaMalloc(&dA, cA.size()));
+  CK(cudaMalloc(&dB, cB.size()));
+  CK(cudaMalloc(&dD, (size_t)128 * 128 * 4));
+  CK(cudaMalloc(&dC, 1024 * sizeof(long long)));
+  CK(cudaMemcpy(dA, cA.data(), cA.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, cB.data(), cB.size(), cudaMemcpyHostToDevice));
+  const size_t smem = 2 * 128 * 128;
+  i8_mma_ts_kernel<<<1, 128, smem>>>(dA, dB, dD, 1, 1, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> hD((size_t)128 * 128);
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+  long long bad = 0;
+  for (int i = 0; i < 128; ++i)
+    for (int j = 0; j < 128; ++j) {
+      int32_t s = 0;
+      for (int k = 0; k < 128; ++k) s += (int32_t)hA[i * 128 + k] * (int32_t)hB[j * 128 + k];
+      if (s != hD[(size_t)i * 128 + j]) {
+        if (bad < 6) printf("  TS mismatch (%d,%d): got %d want %d\n", i, j, hD[(size_t)i * 128 + j], s);
+        ++bad;
+      }
+    }
+  printf("{\"test\": \"i8_mma_ts_correct\", \"what\": \"tcgen05.cp 128x256b smem -> TMEM, then tcgen05.mma with A from TMEM\", \"mismatches\": %lld}\n", bad);
+  for (int recopy : {0, 1})
+    for (int grid : {1, sms}) {
+      const int reps = 4096;
+      i8_mma_ts_kernel<<<grid, 128, smem>>>(dA, dB, nullptr, 64, recopy, dC);
+      CK(cudaDeviceSynchronize());
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0));
+      i8_mma_ts_kernel<<<grid, 128, smem>>>(dA, dB, nullptr, reps, recopy, dC);
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      std::vector<long long> hc(grid);
+      CK(cudaMemcpy(hc.data(), dC, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+      long long cmax = 0;
+      for (long long c : hc) cmax = c > cmax ? c : cmax;
+      printf("{\"test\": \"i8_mma_ts_rate\", \"copy_A_every_pass\": %d, \"ctas\": %d, \"cycles_per_mma\": %.2f, \"mac_per_clk_per_sm\": %.1f, \"ms\": %.3f}\n",
+             recopy, grid, (double)cmax / (reps * 4), (double)reps * 4 * 128.0 * 128 * 32 / (double)cmax, ms);
+    }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
+  return bad == 0;
+}
+
 int main() {
   cudaDeviceProp pr;
   CK(cudaGetDeviceProperties(&pr, 0));
@@ -376,6 +518,7 @@ int main() {
   ok &= run<128>(pr.multiProcessorCount, 0);
   ok &= run<256>(pr.multiProcessorCount, 0);
   ok &= run_2cta(pr.multiProcessorCount);
+  ok &= run_ts(pr.multiProcessorCount);
   printf("{\"all_correct\": %s}\n", ok ? "true" : "false");
   return ok ? 0 : 1;
 }
