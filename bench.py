@@ -470,7 +470,14 @@ def main():
         dmma = {"ms_per_step": float(dstats[0]), "cholesky_ms": float(dstats[1]), "steps": nd_steps, "logpdf": lp_d,
                 "logpdf_rel_diff": abs(lp_s - lp_d) / abs(lp_d), "mean_relnorm": float(np.linalg.norm(M_s - M_d) / np.linalg.norm(M_d)),
                 "var_max_rel": float(np.max(np.abs(V_s - V_d) / np.abs(V_d)))}
-    extras = multi_gpu_extras(lmm, ctx, dist, torch, world, rank) if (world > 1 and not args.no_extras) else None
+    extras = None
+    if world > 1 and not args.no_extras:
+        try:  # untimed records: a failure there (the same on every rank: identical inputs and calls) must not cost the timed result
+            extras = multi_gpu_extras(lmm, ctx, dist, torch, world, rank)
+        except Exception as exc:  # noqa: BLE001
+            extras = {"extras_error": f"{type(exc).__name__}: {exc}"[:500]}
+            ctx.set_option("partition_ilmm", 0)
+            ctx.set_option("ozaki", args.ozaki)
     barrier()
     if rank != 0:
         if world > 1:
