@@ -1,28 +1,34 @@
 // Integer-slice (Ozaki-scheme) FP64 trailing update on the int8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) -- the
 // one route past the native FP64 pipe (DMMA: 37 TFLOP/s) the batched Cholesky already saturates.
-// OPTIONAL ("ozaki" = 6 / 7 / 8 slices; default 0 = DMMA, which stays the reference path).  Replaces, for the WIDE left-looking
-// update of a block column only, the dsyrk/dgemm LAPACK's dpotrf makes under `cholesky(Symmetric(C))` (src/oilmm.jl:90,128 via
-// AbstractGPs):      C(I,J) -= sum_{k < s0} L(I,k) L(J,k)'         (128 x 128 tiles, K = 128 per k-tile)
+// OPTIONAL ("ozaki" = 6 / 7 / 8 digit planes of "ozaki_bits" = 7 / 8 bits; default 0 = DMMA, which stays the reference path).
+// Replaces, for the WIDE left-looking update of a block column only, the dsyrk/dgemm LAPACK's dpotrf makes under
+// `cholesky(Symmetric(C))` (src/oilmm.jl:90,128 via AbstractGPs):
+//     C(I,J) -= sum_{k < s0} L(I,k) L(J,k)'         (128 x 128 tiles, K = 128 per k-tile)
+// and the same update of the prediction sweep X <- X L^{-T} (K10; rectangular left operand).
 //
-// Every finished row i of L is written as  L(i,k) = 2^E_i * sum_{t < S} q_t(i,k) 2^(-6-7t)  with int8 digits |q_t| <= 64 and ONE
-// exponent per row of the whole matrix: |L(i,k)| <= sqrt(A_ii) < 2^E_i (row i of L has 2-norm sqrt(A_ii)), so E_i is known from the
-// diagonal before the factorisation starts and all k-tiles of a row share it -- integer partial sums can then be accumulated
-// over the whole K range.  Digit extraction is exact (scaling by powers of two, round-to-nearest, exact remainders).  Then
-//     L(i,:) . L(j,:) = 2^(E_i+E_j-12) * sum_d 2^(-7d) * [ sum_{t+u=d} sum_k q_t(i,k) q_u(j,k) ]          d = 0 .. S-1
-// where every bracket is an EXACT int32 sum on the tensor cores ((d+1) * K * 64^2 < 2^31 for K <= 65536 / (d+1): K <= 8192 columns at
-// d = 7... checked on the host: K * (d+1) * 4096 < 2^31) and the dropped terms (t + u >= S) are below 2^(-7S-5) * K of the row
-// scales: S = 8 truncates at 2^-56 -- the same normwise bound |dC| <= c eps |L||L|' an FP64 GEMM has, with eps = 2^-53.
-// S(S+1)/2 = 36 int8 MMAs replace one FP64 tile product: 36 * 4 * 71 clk = 10.2 k clk against 32.8 k clk of DMMA
+// Every finished row i of L is written as  L(i,k) = 2^E_i * 2^-6 * sum_{t < S} q_t(i,k) R^-t  with int8 digits and ONE exponent per
+// row of the whole matrix: |L(i,k)| <= sqrt(A_ii) < 2^E_i (row i of L has 2-norm sqrt(A_ii)), so E_i is known from the diagonal
+// before the factorisation starts and all k-tiles of a row share it -- integer partial sums can then be accumulated over the
+// whole K range.  Two radices: R = 128 (digits |q_t| <= 64 from round-to-nearest remainders) and R = 256 (balanced digits in
+// [-128, 127] from one rounding to a 64-bit integer and exact carries; the top plane keeps |q_0| <= 65).  Extraction is exact.  Then
+//     L(i,:) . L(j,:) = 2^(E_i+E_j-12) * sum_d R^-d * [ sum_{t+u=d} sum_k q_t(i,k) q_u(j,k) ]          d = 0 .. S-1
+// where every bracket is an EXACT int32 sum on the tensor cores (at most S pairs per d: S * K * max|q|^2 < 2^31, checked on the
+// host: K <= 65535 columns for 8 planes of 7 bits, 18724 for 7 planes of 8 bits) and the dropped terms (t + u >= S) are below
+// R^-(S-1) * 2^-13 * K of the row scales: 8 x 7 bits truncates at 2^-56, 7 x 8 bits at 2^-55 -- the normwise bound
+// |dC| <= c eps |L||L|' of an FP64 GEMM, with the fixed-point grid relative to the row norms (measured factor error 2e-14 / 1e-13).
+// S(S+1)/2 int8 MMAs (36 / 28) replace one FP64 tile product: 28 * 4 * 71 clk = 8.0 k clk against 32.8 k clk of DMMA
 // (profiles/r02_i8_mma.jsonl: M = 128, N = 128, K = 32 issues every 71 clk).
 //
-// Kernel (one CTA = one 128 x 128 output tile, 6 warps): warp 4 = producer (1-D TMA bulk copies of int8 slices into a 3-stage
-// ring), warp 5 = MMA issuer (one thread), warps 0-3 = epilogue (TMEM -> registers -> C).  TMEM holds four 128-column int32
-// accumulators (all 512 columns), one per d, so the K range is swept twice: pass A for d = 0..3 (needs slices 0..3 of both
-// operands), pass B for d = 4..S-1 (all slices); after each pass the epilogue converts (exact int32 -> double), combines by
-// Horner in 2^-7, scales by the row / column exponents and subtracts from C.
-// HBM layout of the sliced tile (I,k) (S * 16 KB, at sym_tile_index(I,k) * S * 16384 bytes): [K quarter kq][slice t][4096 B], the
+// Kernel (one CTA = one 128 x 128 output tile, 10 warps): warps 0-7 = epilogue (the C tile lives in their registers from the
+// first instruction to the last), warp 8 = producer (1-D TMA bulk copies of digit planes into an mbarrier ring), warp 9 = MMA
+// issuer (one thread, issue loop unrolled at compile time).  TMEM holds four 128-column int32 accumulators (all 512 columns),
+// one per d, so the K range is swept twice: pass A for d = 0..3 (planes 0..3 of both operands; 6 stages of 32 KB), pass B for
+// d = 4..S-1 (all planes; 3 stages of 64 KB); after each pass the epilogue converts (exact int32 -> double), combines by Horner
+// in 1/R, scales by the row / column exponents and subtracts from the registers; one store at the end.
+// HBM layout of the sliced tile (I,k) (S * 16 KB, at sym_tile_index(I,k) * S * 16384 bytes): [K quarter kq][plane t][4096 B], the
 // 4096 B being the canonical K-major no-swizzle UMMA operand of 128 rows x 32 K-bytes: [16-byte K chunk (2)][row (128)][16 B]
 // (core matrix = 8 rows x 16 B contiguous; LBO = 2048, SBO = 128) -- a bulk copy lands it in shared memory ready for the MMA.
+// Measurements, kernel generations, what was tried and dropped (CTA pairs, A operand from tensor memory): profiles/r02_ozaki.md.
 #include "common.cuh"
 #include "kernels.h"
 
