@@ -19,12 +19,17 @@
 // S(S+1)/2 int8 MMAs (36 / 28) replace one FP64 tile product: 28 * 4 * 71 clk = 8.0 k clk against 32.8 k clk of DMMA
 // (profiles/r02_i8_mma.jsonl: M = 128, N = 128, K = 32 issues every 71 clk).
 //
-// Kernel (one CTA = one 128 x 128 output tile, 10 warps): warps 0-7 = epilogue (the C tile lives in their registers from the
-// first instruction to the last), warp 8 = producer (1-D TMA bulk copies of digit planes into an mbarrier ring), warp 9 = MMA
-// issuer (one thread, issue loop unrolled at compile time).  TMEM holds four 128-column int32 accumulators (all 512 columns),
-// one per d, so the K range is swept twice: pass A for d = 0..3 (planes 0..3 of both operands; 6 stages of 32 KB), pass B for
-// d = 4..S-1 (all planes; 3 stages of 64 KB); after each pass the epilogue converts (exact int32 -> double), combines by Horner
-// in 1/R, scales by the row / column exponents and subtracts from the registers; one store at the end.
+// Kernel (one CTA = one 128 x 128 output tile, 11 warps): warps 0-7 = epilogue (the C tile lives in their registers from the
+// first instruction to the last), warp 8 = producer (1-D TMA bulk copies of digit planes into an mbarrier ring), warps 9 and 10 =
+// MMA issuers (one thread each, even / odd stages, issue loops unrolled at compile time; plane-major order with the A operand
+// kept in the collector).  TMEM holds four 128-column int32 accumulators (all 512 columns), one per d, so the K range is swept
+// twice: pass A for d = 0..3 (planes 0..3 of both operands; 6 stages of 32 KB), pass B for d = 4..S-1 (all planes; S = 7: 4 stages
+// of 56 KB); after each pass the epilogue converts (exact int32 -> double), combines by Horner in 1/R, scales by the row / column
+// exponents and subtracts from the registers; one store at the end.
+// What bounded the earlier generations, in the order it was found (profiles/r02_ozaki.md): run-time loops in the issuing thread;
+// a load-after-wait epilogue; and the issuer's per-stage hand-shake (wait, fence, commit: ~450 clk), which does not overlap with
+// its own MMAs -- switching the MMAs, the TMA stream and the epilogue off one by one showed time = hand-shakes + MMAs, whatever the
+// operand stream did; two issuers hide one's hand-shake behind the other's MMAs (16 latents of N = 16384: 236 -> 189 ms).
 // HBM layout of the sliced tile (I,k) (S * 16 KB, at sym_tile_index(I,k) * S * 16384 bytes): [K quarter kq][plane t][4096 B], the
 // 4096 B being the canonical K-major no-swizzle UMMA operand of 128 rows x 32 K-bytes: [16-byte K chunk (2)][row (128)][16 B]
 // (core matrix = 8 rows x 16 B contiguous; LBO = 2048, SBO = 128) -- a bulk copy lands it in shared memory ready for the MMA.
@@ -35,9 +40,13 @@
 namespace lmm {
 
 constexpr int OZ_QB = 4096;                    // bytes of one slice of one K quarter (128 rows x 32 K-bytes)
-constexpr int OZ_RING_BYTES = 192 * 1024;      // pass A: 6 stages of 2 x 4 slices (32 KB), pass B: 3 stages of 2 x 8 slices (64 KB)
-constexpr int OZ_STAGES_A = 6, OZ_STAGES_B = 3;
-constexpr size_t OZ_SMEM = (size_t)OZ_RING_BYTES + 2048;  // + alignment slack, barriers, column scales
+constexpr int OZ_RING_BYTES = 224 * 1024;      // stage = the planes one pass needs of one K quarter of both operands: pass A 2 x 4 x 4 KB
+                                               // (6 stages), pass B 2 x S x 4 KB (S = 7: 56 KB, 4 stages; S = 8: 64 KB, 3 stages)
+// Stages of a pass.  An EVEN count lets two issuing threads alternate (each owns every other stage); an odd one falls back to one.
+__host__ __device__ constexpr int oz_stages(int planes) {
+  return OZ_RING_BYTES / (2 * planes * OZ_QB) >= 6 ? 6 : (OZ_RING_BYTES / (2 * planes * OZ_QB) >= 4 ? 4 : OZ_RING_BYTES / (2 * planes * OZ_QB));
+}
+constexpr size_t OZ_SMEM = (size_t)OZ_RING_BYTES + 2048;  // + alignment slack, barriers, column scales (231 424 of the 232 448 B a CTA may have)
 
 __device__ __forceinline__ uint32_t oz_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void oz_mb_init(uint64_t* bar, int count) {
@@ -60,6 +69,23 @@ __device__ __forceinline__ void oz_mb_wait(uint64_t* bar, uint32_t parity) {
     if (!done && ++spins > (1u << 28)) __trap();  // never hang the GPU on a protocol bug
   }
 }
+// The same wait for the 256 epilogue threads, which sit out a whole MMA pass (tens to hundreds of microseconds): back off between
+// polls.  A tight try_wait loop of 8 warps showed up as 80 % of all warp samples in ncu and takes shared-memory / issue bandwidth
+// from the tensor core's operand reads and the TMA fills.
+__device__ __forceinline__ void oz_mb_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0, ns = 64;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(oz_s32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+    if (ns < 1024) ns <<= 1;
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void oz_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(oz_s32(dst)), "l"(src),
                "r"(bytes), "r"(oz_s32(bar))
@@ -80,6 +106,25 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
       : "memory");
 }
+// The same MMA with the A operand kept in / taken from the tensor core's collector buffer: consecutive MMAs that share A (one digit
+// plane of the left operand against several planes of the right one) read it from shared memory once (SASS: A_KEEP / A_REUSE).
+// mode 0: plain, 1: fill (read A, keep it), 2: use (reuse, keep), 3: lastuse (reuse, release)
+__device__ __forceinline__ void oz_mma_coll(int mode, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  if (mode == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
+                 : "memory");
+  else if (mode == 2)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
+                 : "memory");
+  else if (mode == 3)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
+                 : "memory");
+  else
+    oz_mma(tmem_d, adesc, bdesc, accumulate);
+}
 __device__ __forceinline__ void oz_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_s32(bar)) : "memory");
 }
@@ -94,12 +139,18 @@ template <int S, int PASS>
 __device__ __forceinline__ void oz_issue_quarter(uint32_t tmem, uint64_t a0, uint64_t b0, bool first) {
   constexpr int NS = PASS ? S : (S < 4 ? S : 4);
   constexpr int DLO = PASS ? 4 : 0, DHI = PASS ? S - 1 : NS - 1;
+  // plane t of the left operand against every plane u of the right one with DLO <= t + u <= DHI: t-major, so that consecutive
+  // MMAs share A (collector reuse) and never write the same accumulator back to back (d = t + u changes with u).  Measured
+  // (tools/microbench/i8_mma.cu): 64.0 clk per MMA in this order against 71 with the accumulator-major one.
 #pragma unroll
-  for (int d = DLO; d <= DHI; ++d) {
-    const int tlo = d - (NS - 1) > 0 ? d - (NS - 1) : 0, thi = d < NS - 1 ? d : NS - 1;
+  for (int t = 0; t < NS; ++t) {
+    const int ulo = DLO - t > 0 ? DLO - t : 0, uhi = DHI - t < NS - 1 ? DHI - t : NS - 1;
 #pragma unroll
-    for (int t = tlo; t <= thi; ++t)
-      oz_mma(tmem + (uint32_t)(d - DLO) * 128u, a0 + (uint64_t)(t * 256), b0 + (uint64_t)((d - t) * 256), (first && t == tlo) ? 0u : 1u);
+    for (int u = ulo; u <= uhi; ++u) {
+      const int mode = uhi == ulo ? 0 : (u == ulo ? 1 : (u == uhi ? 3 : 2));
+      // every accumulator of a pass is first written by plane t = 0 (u = d), so "first" only concerns t = 0
+      oz_mma_coll(mode, tmem + (uint32_t)(t + u - DLO) * 128u, a0 + (uint64_t)(t * 256), b0 + (uint64_t)(u * 256), (first && t == 0) ? 0u : 1u);
+    }
   }
 }
 
@@ -107,7 +158,7 @@ __device__ __forceinline__ void oz_issue_quarter(uint32_t tmem, uint64_t a0, uin
 // w / 4 (64 columns).  A thread keeps its 64 values of C(I,J) in REGISTERS for the whole kernel: they are loaded when the kernel
 // starts (the loads complete behind the MMA phase -- a load-after-wait epilogue was latency-bound: 16 dependent L2 round trips
 // per pass held the tensor pipe at 63 %), both passes subtract into them, and they are stored once at the end.
-constexpr int OZ_THREADS = 320;  // warps 0-7: epilogue, warp 8: producer, warp 9: MMA issuer
+constexpr int OZ_THREADS = 352;  // warps 0-7: epilogue, warp 8: producer, warps 9 and 10: MMA issuers (even / odd stages)
 __device__ __forceinline__ void oz_epi_load(const double* Ctile, int r, int ch, double (&c)[64]) {
 #pragma unroll
   for (int gq = 0; gq < 16; ++gq) {
@@ -184,12 +235,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g
   // each pass has its own ring geometry and its own barriers: [pass][full 0..5 | empty 0..5]
   uint64_t* acc_full = bars + 24;              // MMAs of the current pass complete
   uint64_t* acc_empty = acc_full + 1;          // epilogue of pass A has drained TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  uint64_t* init_done = acc_empty + 1;         // [2]: the issuer of quarter 0 has issued it (the accumulators of the pass are initialised)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 3);
   double* colscale = reinterpret_cast<double*>(bars + 32);  // [128]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < 24; ++s) oz_mb_init(&bars[s], 1);
-    oz_mb_init(acc_full, 1);
+    oz_mb_init(acc_full, 2);
+    oz_mb_init(&init_done[0], 1);
+    oz_mb_init(&init_done[1], 1);
     oz_mb_init(acc_empty, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,8 +269,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g
       for (int pass = 0; pass < 2; ++pass) {
         const int ns = pass ? S : nsA;
         if (pass && S <= 4) break;
-        const int nst = pass ? OZ_STAGES_B : OZ_STAGES_A;
-        const uint32_t half = (uint32_t)(pass ? 8 : 4) * OZ_QB, bytes = (uint32_t)ns * OZ_QB;
+        const int nst = pass ? oz_stages(S) : oz_stages(S < 4 ? S : 4);
+        const uint32_t half = (uint32_t)ns * OZ_QB, bytes = half;
         uint64_t* full = bars + 12 * pass;
         uint64_t* empty = full + 6;
         if (pass) oz_mb_wait(acc_full, 0);  // every MMA of pass A has read its stage: the ring can change geometry
@@ -231,20 +285,37 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g
         }
       }
     }
-  } else if (warp == 9) {
-    // ===== MMA issuer: accumulator d - dlo at TMEM columns (d - dlo) * 128
+  } else if (warp == 9 || warp == 10) {
+    // ===== MMA issuers: accumulator d - dlo at TMEM columns (d - dlo) * 128.  TWO issuing threads, one for the even and one for the
+    // odd K quarters: the per-stage hand-shake of an issuer (wait for the stage, fence, commit: ~450 clk, measured with the MMAs
+    // switched off) does not overlap with its own MMAs -- with one issuer the tensor pipe idled that long after every stage
+    // (66 % of peak whatever the operand stream did); with two, one issues while the other shakes hands.  int32 accumulation
+    // commutes, so the interleaving of the two streams is irrelevant EXCEPT for quarter 0, whose MMAs initialise the accumulators:
+    // the odd issuer starts a pass only after the even one has issued quarter 0 (init_done).  Each issuer commits its own
+    // stages; acc_full completes when both have committed their last one.
     if (lane == 0) {
+      const int who = warp - 9;
       for (int pass = 0; pass < 2; ++pass) {
         if (pass && S <= 4) break;
-        const int nst = pass ? OZ_STAGES_B : OZ_STAGES_A;
-        const uint32_t half = (uint32_t)(pass ? 8 : 4) * OZ_QB;
+        const int nst = pass ? oz_stages(S) : oz_stages(S < 4 ? S : 4);
+        const uint32_t half = (uint32_t)(pass ? S : (S < 4 ? S : 4)) * OZ_QB;
         uint64_t* full = bars + 12 * pass;
         uint64_t* empty = full + 6;
+        // two issuers only with an even stage count: each then owns every other stage of the ring, so neither can run a whole
+        // barrier phase ahead of the other on a shared stage (with 3 stages the odd issuer's second quarter is the even one's
+        // first stage: its parity wait would pass before that stage has ever been filled)
+        const bool dual = (nst & 1) == 0;
+        if (who == 1 && !dual) {
+          if (pass) oz_mb_wait(acc_full, 0);  // (its arrival must count for THIS pass's phase of the barrier)
+          oz_mb_arrive(acc_full);
+          continue;
+        }
         if (pass) {
           oz_mb_wait(acc_empty, 0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        for (int kq = 0; kq < nq; ++kq) {
+        if (who == 1) oz_mb_wait(&init_done[pass], 0);
+        for (int kq = who; kq < nq; kq += (dual ? 2 : 1)) {
           const int s = kq % nst;
           oz_mb_wait(&full[s], (kq / nst) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -253,6 +324,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g
           if (pass) oz_issue_quarter<S, 1>(tmem, a0, b0, kq == 0);
           else oz_issue_quarter<S, 0>(tmem, a0, b0, kq == 0);
           oz_commit(&empty[s]);  // the stage is free once these MMAs have read it
+          if (kq == 0) oz_mb_arrive(&init_done[pass]);
         }
         oz_commit(acc_full);
       }
@@ -267,7 +339,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_update_kernel(OzakiArgs g
     oz_epi_load(Ctile, r, ch, c);
     for (int pass = 0; pass < 2; ++pass) {
       if (pass && S <= 4) break;
-      oz_mb_wait(acc_full, (uint32_t)pass);
+      oz_mb_wait_relaxed(acc_full, (uint32_t)pass);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       oz_epi_both<S, BITS>(tmem, quad, ch, pass, rs, colscale, c);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -427,6 +499,7 @@ static cudaError_t oz_launch(cudaStream_t st, dim3 grid, const OzakiArgs& a) {
   return cudaGetLastError();
 }
 cudaError_t oz_dispatch(cudaStream_t st, dim3 grid, const OzakiArgs& a, int S, int bits);
+
 cudaError_t launch_ozaki_update(cudaStream_t st, TiledSym L, const uint8_t* slices, size_t slice_batch_stride, const double* scale,
                                 size_t scale_batch_stride, int i0, int nrows, int j0, int ncols, int k1, int batch, int S, int bits) {
   if (nrows <= 0 || ncols <= 0 || batch <= 0 || k1 <= 0) return cudaSuccess;

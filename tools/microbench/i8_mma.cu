@@ -311,6 +311,89 @@ __global__ void __launch_bounds__(128, 1) i8_mma_ts_kernel(const int8_t* __restr
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ---- collector reuse of the A operand: consecutive MMAs with the SAME A (different B, different accumulators) issued as
+// .collector::a::fill / ::use / ::lastuse read A from shared memory once per group instead of once per MMA (SASS: A_KEEP / A_REUSE).
+// acc g (g = 0..2) = sum_ks A_ks * B_{(ks+g) % 4}' -- checked against the CPU; rate with and without the reuse.
+template <int MODE>  // 0: plain, 1: fill, 2: use, 3: lastuse
+__device__ __forceinline__ void mma_i8_coll(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (MODE == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else if constexpr (MODE == 2)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else if constexpr (MODE == 3)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    mma_i8(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+template <int REUSE>
+__global__ void __launch_bounds__(128, 1) i8_mma_coll_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int32_t* __restrict__ D,
+                                                             int reps, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * 128;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * 128 / 16; i += 128) reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(A)[i];
+  for (int i = tid; i < 128 * 128 / 16; i += 128) reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(B)[i];
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  constexpr uint32_t idesc = make_idesc_i8(128, 128);
+  const uint32_t a0 = s_u32(sA), b0 = s_u32(sB);
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) {
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = make_sdesc(a0 + ks * 4096, 2048, 128);
+        const uint32_t acc = (r > 0 || ks > 0) ? 1u : 0u;
+        mma_i8_coll<REUSE ? 1 : 0>(tmem + 0, ad, make_sdesc(b0 + ((ks + 0) & 3) * 4096, 2048, 128), idesc, acc);
+        mma_i8_coll<REUSE ? 2 : 0>(tmem + 128, ad, make_sdesc(b0 + ((ks + 1) & 3) * 4096, 2048, 128), idesc, acc);
+        mma_i8_coll<REUSE ? 3 : 0>(tmem + 256, ad, make_sdesc(b0 + ((ks + 2) & 3) * 4096, 2048, 128), idesc, acc);
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) {
+    t1 = clock64();
+    if (cycles) cycles[blockIdx.x] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (D && blockIdx.x == 0) {
+    for (int c0 = 0; c0 < 384; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+          "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+            "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 32; ++j) D[(size_t)tid * 384 + c0 + j] = (int32_t)v[j];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 static size_t canon(int R, int r, int k) { return (size_t)(k / 16) * (R / 8 * 128) + (size_t)(r / 8) * 128 + (r % 8) * 16 + (k % 16); }
 
 template <int N>
@@ -509,6 +592,68 @@ static int run_ts(int sms) {
   return bad == 0;
 }
 
+template <int REUSE>
+static int run_coll(int sms) {
+  std::vector<int8_t> hA(128 * 128), hB(128 * 128), cA(128 * 128), cB(128 * 128);
+  srand(4321);
+  for (auto& v : hA) v = (int8_t)(rand() % 256 - 128);
+  for (auto& v : hB) v = (int8_t)(rand() % 256 - 128);
+  for (int r = 0; r < 128; ++r)
+    for (int k = 0; k < 128; ++k) {
+      cA[canon(128, r, k)] = hA[r * 128 + k];
+      cB[canon(128, r, k)] = hB[r * 128 + k];
+    }
+  int8_t *dA, *dB;
+  int32_t* dD;
+  long long* dC;
+  CK(cudaMalloc(&dA, cA.size()));
+  CK(cudaMalloc(&dB, cB.size()));
+  CK(cudaMalloc(&dD, (size_t)128 * 384 * 4));
+  CK(cudaMalloc(&dC, 1024 * sizeof(long long)));
+  CK(cudaMemcpy(dA, cA.data(), cA.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, cB.data(), cB.size(), cudaMemcpyHostToDevice));
+  const size_t smem = 2 * 128 * 128;
+  i8_mma_coll_kernel<REUSE><<<1, 128, smem>>>(dA, dB, dD, 1, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> hD((size_t)128 * 384);
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+  long long bad = 0;
+  for (int g = 0; g < 3; ++g)
+    for (int i = 0; i < 128; ++i)
+      for (int j = 0; j < 128; ++j) {
+        int32_t s = 0;
+        for (int ks = 0; ks < 4; ++ks)
+          for (int kk = 0; kk < 32; ++kk) s += (int32_t)hA[i * 128 + ks * 32 + kk] * (int32_t)hB[j * 128 + ((ks + g) & 3) * 32 + kk];
+        if (s != hD[(size_t)i * 384 + g * 128 + j]) {
+          if (bad < 6) printf("  collector mismatch acc %d (%d,%d): got %d want %d\n", g, i, j, hD[(size_t)i * 384 + g * 128 + j], s);
+          ++bad;
+        }
+      }
+  printf("{\"test\": \"i8_mma_collector_correct\", \"a_reuse\": %d, \"mismatches\": %lld}\n", REUSE, bad);
+  for (int grid : {1, sms}) {
+    const int reps = 2048;
+    i8_mma_coll_kernel<REUSE><<<grid, 128, smem>>>(dA, dB, nullptr, 64, dC);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    i8_mma_coll_kernel<REUSE><<<grid, 128, smem>>>(dA, dB, nullptr, reps, dC);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> hc(grid);
+    CK(cudaMemcpy(hc.data(), dC, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long cmax = 0;
+    for (long long c : hc) cmax = c > cmax ? c : cmax;
+    printf("{\"test\": \"i8_mma_collector_rate\", \"a_reuse\": %d, \"group\": 3, \"ctas\": %d, \"cycles_per_mma\": %.2f, \"mac_per_clk_per_sm\": %.1f, \"ms\": %.3f}\n", REUSE,
+           grid, (double)cmax / (reps * 12), (double)reps * 12 * 128.0 * 128 * 32 / (double)cmax, ms);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
+  return bad == 0;
+}
+
 int main() {
   cudaDeviceProp pr;
   CK(cudaGetDeviceProperties(&pr, 0));
@@ -519,6 +664,8 @@ int main() {
   ok &= run<256>(pr.multiProcessorCount, 0);
   ok &= run_2cta(pr.multiProcessorCount);
   ok &= run_ts(pr.multiProcessorCount);
+  ok &= run_coll<0>(pr.multiProcessorCount);
+  ok &= run_coll<1>(pr.multiProcessorCount);
   printf("{\"all_correct\": %s}\n", ok ? "true" : "false");
   return ok ? 0 : 1;
 }
