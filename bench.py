@@ -227,19 +227,23 @@ def run_reference(args, cfg):
     }))
 
 
-def int8_peak_tops():
-    """Dense int8 tensor peak of this pool's B200, measured by tools/microbench/i8_mma.cu (profiles/r02_i8_mma.jsonl: M = 128, N = 256
-    MMAs on all 148 SMs); nominal 4500.  MEASURED_PEAKS.json has no int8 entry."""
-    try:
-        best = 0.0
-        for ln in open(os.path.join(ROOT, "profiles", "r02_i8_mma.jsonl")):
-            d = json.loads(ln)
-            if d.get("test", "").startswith("i8_mma") and d.get("test", "").endswith("rate"):
-                best = max(best, float(d.get("total_tops", 0.0)))
-        if best > 0:
-            return best, "measured: tools/microbench/i8_mma.cu on all SMs (profiles/r02_i8_mma.jsonl); nominal dense int8 4500"
-    except Exception:
-        pass
+def int8_peak_tops(sm_mhz=1965.0):
+    """Dense int8 tensor peak of this pool's B200: the per-SM rate MEASURED by tools/microbench/i8_mma.cu in SM cycles (8190 MAC/clk/SM
+    = the nominal 8192; profiles/r02_i8_mma*.jsonl) x 148 SMs x 2 x the SM clock sampled during the run -- 4.76 POPS at 1965 MHz (NVIDIA's
+    nominal 4.5 POPS assumes a lower clock).  The wall-clock rate of the microbenchmark's own 1 ms kernels (4.09 POPS, launch included)
+    is a LOWER bound and was what earlier lines of this round used.  MEASURED_PEAKS.json has no int8 entry."""
+    best = 0.0
+    for name in ("r02_i8_mma.jsonl", "r02_i8_mma_2cta.jsonl"):
+        try:
+            for ln in open(os.path.join(ROOT, "profiles", name)):
+                d = json.loads(ln)
+                if "rate" in d.get("test", ""):
+                    best = max(best, float(d.get("mac_per_clk_per_sm", 0.0)))
+        except Exception:
+            pass
+    if best > 0:
+        return 148 * best * 2 * sm_mhz * 1e6 / 1e12, (f"measured {best:.0f} int8 MAC/clk/SM (tools/microbench/i8_mma.cu, profiles/r02_i8_mma*.jsonl) x 148 SM x 2 x "
+                                                      f"{sm_mhz:.0f} MHz (median SM clock sampled during the timed region); nominal dense int8: 4500")
     return 4500.0, "nominal dense int8 (no measurement file)"
 
 
@@ -508,7 +512,7 @@ def main():
     if args.ozaki and oz_kernel and oz_kernel["ms"] > 0:
         # dominant kernel of the timed path: the int8 wide update.  Algorithmic work of its launches = tile products x S(S+1)/2 MMAs x
         # 2 * 128^3 int8 ops, over the summed CUDA-event time of exactly those launches (one stream: serial).
-        i8_peak, i8_src = int8_peak_tops()
+        i8_peak, i8_src = int8_peak_tops(sm_mhz)
         nmma = args.ozaki * (args.ozaki + 1) // 2
         ops = oz_kernel["tile_products"] * nmma * 2.0 * 128 ** 3
         a_tops = ops / (oz_kernel["ms"] * 1e-3) / 1e12
