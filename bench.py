@@ -9,6 +9,9 @@ config 4), Float64, latents block-sharded over the ranks (strong scaling of one 
 
 One step = one eval = logpdf(fx, y) AND posterior(fx, y) on the same (fx, y), one shared
 factorisation per latent (the reference factorises twice; SURVEY.md §8d counts it once).
+Timed path (default): the wide Cholesky updates run as integer-slice products on the int8 tensor cores (--ozaki 7 --ozaki-bits 8:
+library options "ozaki" / "ozaki_bits"; FP64 results to ~1e-13, checked in every line against the CPU oracle (`parity_check`) and
+against the library's default all-FP64 DMMA path, which is measured in the same process (`dmma_path`); --ozaki 0 times that path).
 `value`: inputs x, y already resident in HBM (device pointers through the C ABI), timed with the
 CUDA events liblmm records on its own compute stream around all device work of the call.
 `e2e`: the same call with pinned HOST buffers, H2D/D2H inside the timed region, wall clock between
