@@ -52,3 +52,42 @@ def test_int32_bound():
     for S, bits, K in ((7, 8, 18724), (8, 7, 65535)):
         q = 128 if bits == 8 else 64
         assert S * K * q * q < 2 ** 31
+
+
+@pytest.mark.parametrize("S", [6, 7, 8])
+def test_issue_order_covers_every_pair_once(S):
+    """The plane-major issue loops of the kernel enumerate exactly the pairs t + u < S, every accumulator of a pass is first written by
+    plane t = 0 (the kernel initialises accumulators only there), MMAs that share the A plane are consecutive and form one
+    fill -> use* -> lastuse group, and a pass never needs more than the four accumulators tensor memory holds."""
+    from tools.ozaki_model import issue_order
+
+    seen = set()
+    for pas in (0, 1):
+        order = issue_order(S, pas)
+        accs = {}
+        for i, (t, u, acc, mode) in enumerate(order):
+            assert 0 <= acc < 4
+            assert (t, u) not in seen
+            seen.add((t, u))
+            accs.setdefault(acc, t)
+        assert all(first_t == 0 for first_t in accs.values())
+        # collector groups
+        i = 0
+        while i < len(order):
+            t = order[i][0]
+            grp = [o for o in order if o[0] == t]
+            assert order[i:i + len(grp)] == grp  # consecutive
+            modes = [o[3] for o in grp]
+            assert modes == ([0] if len(grp) == 1 else [1] + [2] * (len(grp) - 2) + [3])
+            i += len(grp)
+    assert seen == {(t, u) for t in range(S) for u in range(S) if t + u < S}
+    assert len(seen) == S * (S + 1) // 2
+
+
+def test_stage_counts_and_issuer_split():
+    from tools.ozaki_model import stages
+
+    assert stages(4) == 6 and stages(7) == 4 and stages(6) == 4  # even: two issuing threads alternate
+    assert stages(8) == 3                                        # odd: one issuer (a shared stage would let the parity wait pass a phase early)
+    for planes in (4, 6, 7, 8):
+        assert stages(planes) * 2 * planes * 4096 <= 224 * 1024

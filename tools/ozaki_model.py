@@ -68,3 +68,24 @@ def product(pa, sa, pb, sb, bits):
 def int32_bound_ok(K, S, bits):
     """the host's check (chol_factor_stream): pairs per accumulator <= S, each product <= (largest digit)^2."""
     return K * S * (16384 if bits == 8 else 4096) < 2 ** 31
+
+
+def issue_order(S, pas):
+    """The MMAs of one K quarter of pass `pas` in the order oz_issue_quarter<S, PASS> issues them: (t, u, accumulator, collector mode)
+    with mode 0 = plain, 1 = fill, 2 = use, 3 = lastuse (same loop bounds as the kernel)."""
+    ns = S if pas else min(S, 4)
+    dlo, dhi = (4, S - 1) if pas else (0, ns - 1)
+    out = []
+    for t in range(ns):
+        ulo = max(dlo - t, 0)
+        uhi = min(dhi - t, ns - 1)
+        for u in range(ulo, uhi + 1):
+            mode = 0 if uhi == ulo else (1 if u == ulo else (3 if u == uhi else 2))
+            out.append((t, u, t + u - dlo, mode))
+    return out
+
+
+def stages(planes, ring=224 * 1024):
+    """oz_stages(): stages of a pass in the 224 KB ring (even counts let the two issuing threads own alternate stages)."""
+    n = ring // (2 * planes * 4096)
+    return 6 if n >= 6 else (4 if n >= 4 else n)
