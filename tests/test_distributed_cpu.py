@@ -89,7 +89,7 @@ def test_cyclic_index_is_a_packing():
             assert total == nrows * (nrows + 1) // 2
 
 
-@pytest.mark.parametrize("G,ob,nt", [(2, 2, 9), (3, 4, 10), (4, 1, 9), (2, 3, 8)])
+@pytest.mark.parametrize("G,ob,nt", [(2, 2, 9), (3, 4, 10), (4, 1, 9), (2, 3, 8), (8, 2, 20), (8, 4, 19), (8, 3, 17)])
 def test_rowcyclic_dist_schedule_single_process(G, ob, nt):
     """All G ranks simulated in one process: factor, logdet and z = L^{-1} rhs against NumPy; no rank ever holds more than its rows."""
     import scipy.linalg as sla
